@@ -1,0 +1,244 @@
+"""TEST INFRASTRUCTURE ONLY — CPU oracle (Python twin) of the sumcheck drivers and exemplar instances.
+
+Follows:
+  joltworks/src/subprotocols/sumcheck.rs:565-599 (Sumcheck::prove), :30-184 (BatchedSumcheck::prove),
+        :653-686 (SumcheckInstanceProof::verify)
+  joltworks/src/subprotocols/sumcheck_prover.rs:10-68 (SumcheckInstanceProver trait)
+  jolt-atlas-core/src/onnx_proof/ops/mul.rs:160-185, add.rs:283-304, sub.rs:267, square.rs:163,
+        einsum/dot.rs:290-375 (EqSchedule::None), cube.rs:159-166
+  joltworks/src/subprotocols/mles_product_sum.rs:15-129,330-376 (product of d MLEs, split-eq weighted)
+  joltworks/src/subprotocols/hamming_weight.rs:118-139 (sum_i gamma_i * ra_i, one eval)
+Challenges are carried as masked u128 ints; field values are ints mod P.
+Parity unpinned at the byte level (no reference KATs).
+"""
+from __future__ import annotations
+
+from . import field as F
+from .field import P
+from .poly import GruenSplitEq, bind, sumcheck_evals, LOW_TO_HIGH, HIGH_TO_LOW
+from .unipoly import UniPoly, CompressedUniPoly
+
+
+# ----------------------------------------------------------------------------- instances
+class Instance:
+    """Mirror of SumcheckInstanceProver: num_rounds/input_claim/compute_message/ingest_challenge."""
+    degree = 0
+
+    def num_rounds(self): raise NotImplementedError
+    def input_claim(self): raise NotImplementedError
+    def compute_message(self, rnd, previous_claim): raise NotImplementedError
+    def ingest_challenge(self, c_u128, rnd): raise NotImplementedError
+    def final_claims(self): return []
+
+
+def _log2(n):
+    assert n & (n - 1) == 0 and n > 0
+    return n.bit_length() - 1
+
+
+class SplitEqInstance(Instance):
+    """Family S (SURVEY §8a addendum): split-eq weighted, LowToHigh binding.
+    kind in {add, sub, mul, square, cube(same-MLE power 3), prod (product of d MLEs)}"""
+
+    def __init__(self, kind, w_fr, polys, claim):
+        self.kind = kind
+        self.eq = GruenSplitEq(w_fr, LOW_TO_HIGH)
+        self.polys = [list(p) for p in polys]
+        self.claim = claim % P
+        self.degree = {"add": 2, "sub": 2, "mul": 3, "square": 3, "cube": 4}.get(kind, len(polys) + 1)
+
+    def num_rounds(self): return len(self.eq.w)
+    def input_claim(self): return self.claim
+
+    def compute_message(self, rnd, prev):
+        ps = self.polys
+        k = self.kind
+        if k in ("add", "sub"):
+            sgn = 1 if k == "add" else -1
+            [q0] = self.eq.fold(lambda g: [ps[0][2 * g] + sgn * ps[1][2 * g]], 1)
+            return self.eq.gruen_poly_deg_2(q0, prev)
+        if k == "mul":
+            def f(g):
+                l0, r0 = ps[0][2 * g], ps[1][2 * g]
+                return [l0 * r0 % P, (ps[0][2 * g + 1] - l0) * (ps[1][2 * g + 1] - r0) % P]
+            q0, q2 = self.eq.fold(f, 2)
+            return self.eq.gruen_poly_deg_3(q0, q2, prev)
+        if k == "square":
+            def f(g):
+                o0 = ps[0][2 * g]
+                d = ps[0][2 * g + 1] - o0
+                return [o0 * o0 % P, d * d % P]
+            q0, q2 = self.eq.fold(f, 2)
+            return self.eq.gruen_poly_deg_3(q0, q2, prev)
+        # product of d linear factors on the grid {1..d-1, inf}  (mles_product_sum.rs)
+        if k == "cube":
+            factors = [ps[0]] * 3
+        else:
+            factors = ps
+        d = len(factors)
+
+        def f(g):
+            out = []
+            for x in list(range(1, d)) + [None]:
+                acc = 1
+                for z in factors:
+                    p0, p1 = z[2 * g], z[2 * g + 1]
+                    acc = acc * ((p1 - p0) if x is None else (p0 + x * (p1 - p0))) % P
+                out.append(acc)
+            return out
+        sums = [s * self.eq.current_scalar % P for s in self.eq.fold(f, d)]
+        return finish_mles_product_sum_from_evals(sums, prev, self.eq)
+
+    def ingest_challenge(self, c, rnd):
+        r = F.challenge_to_fr(c)
+        self.eq.bind(r)
+        self.polys = [bind(p, r, LOW_TO_HIGH) for p in self.polys]
+
+    def final_claims(self):
+        return [p[0] for p in self.polys]
+
+
+def finish_mles_product_sum_from_evals(sum_evals, claim, eq):
+    """mles_product_sum.rs:330-376."""
+    r = eq.current_w()
+    eq0, eq1 = (1 - r) % P, r
+    if len(sum_evals) == 1:
+        at0 = (claim - eq1 * sum_evals[0]) % P
+    else:
+        at0 = (claim - eq1 * sum_evals[0]) * F.fr_inv(eq0) % P
+    tmp = UniPoly.from_evals_toom([at0] + list(sum_evals)).coeffs
+    cc, xc = (1 - r) % P, (2 * r - 1) % P
+    coeffs = [0] * (len(tmp) + 1)
+    for i, c in enumerate(tmp):
+        coeffs[i] = (coeffs[i] + c * cc) % P
+        coeffs[i + 1] = (coeffs[i + 1] + c * xc) % P
+    return UniPoly.from_coeff(coeffs)
+
+
+class DotInstance(Instance):
+    """Family D: plain products via sumcheck_evals, HighToLow (einsum/dot.rs EqSchedule::None, degree 2;
+    with a third bound MLE (eq) of the same length, degree 3)."""
+
+    def __init__(self, polys, claim):
+        self.polys = [list(p) for p in polys]
+        self.claim = claim % P
+        self.degree = len(polys)
+
+    def num_rounds(self): return _log2(len(self.polys[0]))
+    def input_claim(self): return self.claim
+
+    def compute_message(self, rnd, prev):
+        half = len(self.polys[0]) // 2
+        deg = self.degree
+        acc = [0] * deg
+        for i in range(half):
+            evs = [sumcheck_evals(p, i, deg, HIGH_TO_LOW) for p in self.polys]
+            for k in range(deg):
+                t = 1
+                for e in evs:
+                    t = t * e[k] % P
+                acc[k] = (acc[k] + t) % P
+        return UniPoly.from_evals_and_hint(prev, acc)
+
+    def ingest_challenge(self, c, rnd):
+        r = F.challenge_to_fr(c)
+        self.polys = [bind(p, r, HIGH_TO_LOW) for p in self.polys]
+
+    def final_claims(self):
+        return [p[0] for p in self.polys]
+
+
+class HammingInstance(Instance):
+    """hamming_weight.rs:118-139: sum_j sum_i gamma_i * ra_i[j]; degree 1, LowToHigh."""
+    degree = 1
+
+    def __init__(self, polys, gammas, claim):
+        self.polys = [list(p) for p in polys]
+        self.gammas = list(gammas)
+        self.claim = claim % P
+
+    def num_rounds(self): return _log2(len(self.polys[0]))
+    def input_claim(self): return self.claim
+
+    def compute_message(self, rnd, prev):
+        half = len(self.polys[0]) // 2
+        acc = 0
+        for p, g in zip(self.polys, self.gammas):
+            acc = (acc + g * sum(p[2 * j] for j in range(half))) % P
+        return UniPoly.from_evals_and_hint(prev, [acc])
+
+    def ingest_challenge(self, c, rnd):
+        r = F.challenge_to_fr(c)
+        self.polys = [bind(p, r, LOW_TO_HIGH) for p in self.polys]
+
+    def final_claims(self):
+        return [p[0] for p in self.polys]
+
+
+# ----------------------------------------------------------------------------- drivers
+def sumcheck_prove(inst, transcript):
+    """Sumcheck::prove (sumcheck.rs:565-599). Returns (compressed polys, challenges u128, final claim)."""
+    n = inst.num_rounds()
+    claim = inst.input_claim()
+    transcript.append_scalar(claim)
+    prev = claim
+    rs, cps = [], []
+    for rnd in range(n):
+        uni = inst.compute_message(rnd, prev)
+        cp = uni.compress()
+        cp.append_to_transcript(transcript)
+        c = transcript.challenge_scalar_optimized()
+        rs.append(c)
+        prev = uni.evaluate(F.challenge_to_fr(c))
+        inst.ingest_challenge(c, rnd)
+        cps.append(cp)
+    return cps, rs, prev
+
+
+def batched_sumcheck_prove(insts, transcript):
+    """BatchedSumcheck::prove (sumcheck.rs:30-184), front-loaded batching."""
+    max_rounds = max(i.num_rounds() for i in insts)
+    for i in insts:
+        transcript.append_scalar(i.input_claim())
+    coeffs = transcript.challenge_vector(len(insts))
+    claims = [F.mul_pow_2(i.input_claim(), max_rounds - i.num_rounds()) for i in insts]
+    rs, cps = [], []
+    for rnd in range(max_rounds):
+        remaining = max_rounds - rnd
+        unis = []
+        for inst, prev in zip(insts, claims):
+            nr = inst.num_rounds()
+            if remaining > nr:
+                unis.append(UniPoly.from_coeff([F.mul_pow_2(inst.input_claim(), remaining - nr - 1)]))
+            else:
+                unis.append(inst.compute_message(rnd - (max_rounds - nr), prev))
+        batched = UniPoly.from_coeff([])
+        for u, cf in zip(unis, coeffs):
+            batched.add_assign(u.scaled(cf))
+        cp = batched.compress()
+        cp.append_to_transcript(transcript)
+        c = transcript.challenge_scalar_optimized()
+        rs.append(c)
+        rf = F.challenge_to_fr(c)
+        claims = [u.evaluate(rf) for u in unis]
+        for inst in insts:
+            nr = inst.num_rounds()
+            if remaining <= nr:
+                inst.ingest_challenge(c, rnd - (max_rounds - nr))
+        cps.append(cp)
+    return cps, rs, coeffs, claims
+
+
+def sumcheck_verify(cps, claim, num_rounds, degree_bound, transcript):
+    """SumcheckInstanceProof::verify (sumcheck.rs:653-686). Returns (final claim, challenges)."""
+    assert len(cps) == num_rounds
+    e = claim % P
+    rs = []
+    for cp in cps:
+        if cp.degree() > degree_bound:
+            raise ValueError("InvalidInputLength")
+        cp.append_to_transcript(transcript)
+        c = transcript.challenge_scalar_optimized()
+        rs.append(c)
+        e = cp.eval_from_hint(e, F.challenge_to_fr(c))
+    return e, rs
