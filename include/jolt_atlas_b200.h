@@ -1,0 +1,152 @@
+/*
+ * jolt_atlas_b200.h — C ABI of the B200-native proving hot path of jolt-atlas.
+ *
+ * The reference (ICME-Lab/jolt-atlas) has no FFI; its seams are Rust traits.
+ * Each entry point below states the reference interface it replaces (file:line under the
+ * reference root).  `rust-shim/` and INTEGRATION.md show the binding a maintainer adds.
+ *
+ * Conventions
+ *   Fr       : uint64_t[4] little-endian limbs, MONTGOMERY form (R = 2^256) — the in-memory
+ *              layout of ark_bn254::Fr (BigInt<4>); the reference transmutes it the same way
+ *              (joltworks/src/field/ark.rs:21-29).
+ *   challenge: uint64_t[4] = {0, 0, lo, hi}, the 125-bit MontU128Challenge
+ *              (joltworks/src/field/challenge/mont_ark_u128.rs:51-63).
+ *   G1 affine: uint64_t[8] = Fq x[4], Fq y[4], Montgomery form; infinity is carried in a flag.
+ *   order    : JA_LOW_TO_HIGH / JA_HIGH_TO_LOW == BindingOrder (multilinear_polynomial.rs).
+ *   status   : every call returns 0 on success, <0 on error (ja_last_error has the text).
+ *              Nothing unwinds across the ABI.  Prover-side callers panic on error (the
+ *              reference prover panics on invariant violations); a verifier-side caller maps
+ *              errors to ProofVerifyError::InternalError (joltworks/src/utils/errors.rs:16-50).
+ *   memory   : host pointers are borrowed for the duration of the call; device objects are
+ *              opaque handles owned by the library until the matching *_free.
+ *   threads  : a ja_ctx serialises its calls internally (PCS::commit is invoked from rayon
+ *              workers, jolt-atlas-core/src/onnx_proof/prover.rs:243-248).
+ *   There is NO CPU fallback: without a CUDA device ja_init fails.
+ */
+#ifndef JOLT_ATLAS_B200_H
+#define JOLT_ATLAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ja_ctx ja_ctx;
+typedef struct ja_poly ja_poly;       /* device-resident MultilinearPolynomial (dense Fr, or compact i32 before its first bind) */
+typedef struct ja_spliteq ja_spliteq; /* device-resident GruenSplitEqPolynomial */
+typedef struct ja_srs ja_srs;         /* device-resident KZG SRS (g1_powers) */
+
+enum { JA_LOW_TO_HIGH = 0, JA_HIGH_TO_LOW = 1 };
+
+enum {
+  JA_OK = 0,
+  JA_ERR_CUDA = -1,          /* CUDA runtime failure (text in ja_last_error) */
+  JA_ERR_INVALID = -2,       /* bad argument (null, non power of two, length mismatch) */
+  JA_ERR_KEY_LENGTH = -3,    /* == ProofVerifyError::KeyLengthError: SRS shorter than the polynomial */
+  JA_ERR_NO_DEVICE = -4,
+  JA_ERR_UNSUPPORTED = -5
+};
+
+/* Round-evaluation bodies (SURVEY §8a addendum).  Family S = split-eq weighted, LowToHigh
+ * (GruenSplitEqPolynomial::par_fold_out_in_unreduced, split_eq_poly.rs:569-597); family D = plain
+ * products via sumcheck_evals at X in {0,2,3} (multilinear_polynomial.rs:873-905), HighToLow. */
+enum {
+  JA_EVAL_ADD = 0,      /* [l0+r0]                      ops/add.rs:283-296        n_out=1 */
+  JA_EVAL_SUB = 1,      /* [l0-r0]                      ops/sub.rs:267            n_out=1 */
+  JA_EVAL_MUL = 2,      /* [l0*r0, dl*dr]               ops/mul.rs:160-176        n_out=2 */
+  JA_EVAL_SQUARE = 3,   /* [o0^2, do^2]                 ops/square.rs:163         n_out=2 */
+  JA_EVAL_PROD = 4,     /* prod_i (p_i0 + X dp_i) on {1..d-1,inf} * current_scalar is applied by the caller;
+                           mles_product_sum.rs:61-129   n_out=d (d = n_polys, 2..32) */
+  JA_EVAL_POW = 5,      /* same-MLE power (p0 + X dp)^d on {1..d-1,inf}; d passed in aux_u32; cube.rs:159 */
+  JA_EVAL_IDENT = 6,    /* [p0]  ps_shout / identity-RC cycle rounds, opening reduction; n_out=1 */
+  JA_EVAL_DOT2 = 16,    /* [sum l(0)r(0), sum l(2)r(2)]             einsum/dot.rs:292-303   n_out=2 */
+  JA_EVAL_DOT3 = 17,    /* [sum l r e at 0,2,3], three MLEs of equal length  dot.rs:330-350   n_out=3 */
+  JA_EVAL_SUM1 = 18,    /* [sum_i gamma_i * sum_j p_i[2j]]  LowToHigh one eval  hamming_weight.rs:118-139 (aux = gammas) */
+  JA_EVAL_SUMHI = 19    /* [sum_{j<n/2} p[j]]  HighToLow one eval  ops/sum/axis.rs:220-233 */
+};
+
+/* ---- context ---------------------------------------------------------------------------- */
+int32_t ja_init(int32_t device, ja_ctx** out);
+void ja_shutdown(ja_ctx*);
+/* copies the calling thread's last error text (NUL terminated) */
+void ja_last_error(char* buf, size_t cap);
+int32_t ja_sync(ja_ctx*);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+uint64_t ja_launch_count(const ja_ctx*);
+
+/* ---- polynomials: MultilinearPolynomial<Fr> (joltworks/src/poly/multilinear_polynomial.rs:22-35) ---- */
+/* LargeScalars(DensePolynomial) from a host Fr array; n must be a power of two. */
+int32_t ja_poly_from_fr(ja_ctx*, const uint64_t* z, size_t n, ja_poly** out);
+/* I32Scalars(CompactPolynomial<i32>) — `MultilinearPolynomial::from(tensor.padded_next_power_of_two())`
+ * (ops/mul.rs:146-147).  Stays 4 B/coeff on device until the first bind (compact_polynomial.rs:272-353). */
+int32_t ja_poly_from_i32(ja_ctx*, const int32_t* z, size_t n, ja_poly** out);
+/* uninitialised dense poly of length n (output of device-side producers) */
+int32_t ja_poly_alloc(ja_ctx*, size_t n, ja_poly** out);
+int32_t ja_poly_clone(ja_ctx*, const ja_poly*, ja_poly** out);
+size_t ja_poly_len(const ja_poly*);
+/* copy current (bound) coefficients to the host as Fr; cap >= len */
+int32_t ja_poly_to_host(ja_ctx*, const ja_poly*, uint64_t* out, size_t cap);
+void ja_poly_free(ja_ctx*, ja_poly*);
+
+/* PolynomialBinding::bind_parallel (multilinear_polynomial.rs:728-742) ->
+ * DensePolynomial::bound_poly_var_top_zero_optimized (dense_mlpoly.rs:126-141, HighToLow) /
+ * bound_poly_var_bot_01_optimized (:219-239, LowToHigh) / CompactPolynomial::bind_parallel. */
+int32_t ja_bind(ja_ctx*, ja_poly*, const uint64_t r[4], int32_t order);
+/* several polys, one challenge, one launch (every `ingest_challenge`, e.g. ops/mul.rs:179-185) */
+int32_t ja_bind_many(ja_ctx*, ja_poly* const* polys, size_t n_polys, const uint64_t r[4], int32_t order);
+/* PolynomialBinding::final_claim (multilinear_polynomial.rs:744-762): len must be 1 */
+int32_t ja_final_claim(ja_ctx*, const ja_poly*, uint64_t out[4]);
+/* MultilinearPolynomial::evaluate (multilinear_polynomial.rs:766-862 -> dense_mlpoly.rs:265-305):
+ * point = m challenges-or-field elements (Fr Montgomery limbs), r[0] binds the MSB. */
+int32_t ja_poly_evaluate(ja_ctx*, const ja_poly*, const uint64_t* point, size_t m, uint64_t out[4]);
+
+/* EqPolynomial::evals_with_scaling (joltworks/src/poly/eq_poly.rs:77-101,149-167,225-252):
+ * table of 2^m Fr, big-endian index (r[0] = MSB); scale may be NULL (= 1). */
+int32_t ja_eq_evals(ja_ctx*, const uint64_t* r, size_t m, const uint64_t* scale_or_null, ja_poly** out);
+
+/* ---- GruenSplitEqPolynomial (joltworks/src/poly/split_eq_poly.rs:67-598) -------------------- */
+/* new_with_scaling (:86-145): w = m Fr (Montgomery limbs; challenges are valid Fr limbs) */
+int32_t ja_spliteq_new(ja_ctx*, const uint64_t* w, size_t m, int32_t order, const uint64_t* scale_or_null,
+                       ja_spliteq** out);
+/* bind (:331-372) */
+int32_t ja_spliteq_bind(ja_ctx*, ja_spliteq*, const uint64_t r[4]);
+/* get_current_scalar (:495) / get_current_w (:499-504) */
+int32_t ja_spliteq_current_scalar(const ja_spliteq*, uint64_t out[4]);
+int32_t ja_spliteq_current_w(const ja_spliteq*, uint64_t out[4]);
+/* merge (:473-493): dense eq table of the unbound variables times current_scalar */
+int32_t ja_spliteq_merge(ja_ctx*, const ja_spliteq*, ja_poly** out);
+void ja_spliteq_free(ja_ctx*, ja_spliteq*);
+
+/* One round's reduced sums (the host does the O(1) interpolation: gruen_poly_deg_2/3,
+ * UniPoly::from_evals_and_hint, finish_mles_product_sum_from_evals).
+ * Replaces the body of every `compute_message` listed in the enum above.
+ * eq must be non-NULL for family S and NULL for family D.  out_evals = n_out Fr. */
+int32_t ja_round_eval(ja_ctx*, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
+                      const ja_spliteq* eq_or_null, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32,
+                      uint64_t* out_evals, size_t n_out);
+
+/* Einsum operand fold / i32 tensor x eq-vector (ops/einsum/mk_kn_mn.rs:47-79):
+ *   transpose==0: out[j] = sum_i from_i32(A[i*cols + j]) * eq[i]   (eq has `rows` entries, out has `cols`)
+ *   transpose==1: out[i] = sum_j from_i32(A[i*cols + j]) * eq[j]   (eq has `cols` entries, out has `rows`) */
+int32_t ja_tensor_fold_i32(ja_ctx*, const int32_t* A, size_t rows, size_t cols, const ja_poly* eq,
+                           int32_t transpose, ja_poly** out);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
+/* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see this stream). */
+int32_t ja_timer_begin(ja_ctx*);
+int32_t ja_timer_end(ja_ctx*, float* out_ms);
+/* Re-run ONE kernel `iters` times back to back on resident synthetic operands of 2^log_n Fr (inputs are
+ * never consumed, so every iteration does identical work; 2^log_n * 32 B should exceed the 126 MB L2).
+ *   which: 0 = bind LowToHigh, 1 = bind HighToLow (n_polys polys per launch),
+ *          2 = round eval MUL (split-eq, 2 polys), 3 = round eval DOT2, 4 = round eval ADD
+ * Returns the average device time per launch in *out_ms. */
+int32_t ja_bench_kernel(ja_ctx*, int32_t which, int32_t log_n, int32_t n_polys, int32_t iters, float* out_ms);
+/* register-resident Montgomery-product loop; returns achieved Fr-mul/s in *out_mul_per_s */
+int32_t ja_calibrate_fr_mul(ja_ctx*, int32_t iters, double* out_mul_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOLT_ATLAS_B200_H */

@@ -1,0 +1,10 @@
+"""jolt_atlas_b200 — B200-native (sm_100a) proving hot path of jolt-atlas behind a C ABI.
+
+Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C ABI + the C++ host driver) and
+the thin Python mirror of the reference's polynomial / sumcheck / PCS interface (`api.py`).
+Importing this package does not load CUDA; `api.Context()` does and fails loudly without a GPU.
+"""
+from .api import (  # noqa: F401
+    BindingOrder, Context, EqPolynomial, EvalKernel, GruenSplitEqPolynomial, JoltAtlasError,
+    MultilinearPolynomial, bind_many, round_eval, tensor_fold_i32,
+)

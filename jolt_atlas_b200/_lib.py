@@ -1,0 +1,83 @@
+"""ctypes loader for the in-tree C-ABI library.  Fails loudly when the library is missing: there is
+no Python/CPU fallback for any kernel."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libjolt_atlas_b200.so")
+
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+u32p = C.POINTER(C.c_uint32)
+vp = C.c_void_p
+vpp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes).  Must list every symbol include/jolt_atlas_b200.h declares
+# (tests/test_abi.py checks the header against this table and against the built .so).
+SIGNATURES = {
+    "ja_init": (C.c_int32, [C.c_int32, vpp]),
+    "ja_shutdown": (None, [vp]),
+    "ja_last_error": (None, [C.c_char_p, C.c_size_t]),
+    "ja_sync": (C.c_int32, [vp]),
+    "ja_launch_count": (C.c_uint64, [vp]),
+    "ja_poly_from_fr": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
+    "ja_poly_from_i32": (C.c_int32, [vp, i32p, C.c_size_t, vpp]),
+    "ja_poly_alloc": (C.c_int32, [vp, C.c_size_t, vpp]),
+    "ja_poly_clone": (C.c_int32, [vp, vp, vpp]),
+    "ja_poly_len": (C.c_size_t, [vp]),
+    "ja_poly_to_host": (C.c_int32, [vp, vp, u64p, C.c_size_t]),
+    "ja_poly_free": (None, [vp, vp]),
+    "ja_bind": (C.c_int32, [vp, vp, u64p, C.c_int32]),
+    "ja_bind_many": (C.c_int32, [vp, vpp, C.c_size_t, u64p, C.c_int32]),
+    "ja_final_claim": (C.c_int32, [vp, vp, u64p]),
+    "ja_poly_evaluate": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p]),
+    "ja_eq_evals": (C.c_int32, [vp, u64p, C.c_size_t, u64p, vpp]),
+    "ja_spliteq_new": (C.c_int32, [vp, u64p, C.c_size_t, C.c_int32, u64p, vpp]),
+    "ja_spliteq_bind": (C.c_int32, [vp, vp, u64p]),
+    "ja_spliteq_current_scalar": (C.c_int32, [vp, u64p]),
+    "ja_spliteq_current_w": (C.c_int32, [vp, u64p]),
+    "ja_spliteq_merge": (C.c_int32, [vp, vp, vpp]),
+    "ja_spliteq_free": (None, [vp, vp]),
+    "ja_round_eval": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, u64p, C.c_size_t, C.c_uint32, u64p, C.c_size_t]),
+    "ja_tensor_fold_i32": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vp, C.c_int32, vpp]),
+    "ja_timer_begin": (C.c_int32, [vp]),
+    "ja_timer_end": (C.c_int32, [vp, C.POINTER(C.c_float)]),
+    "ja_bench_kernel": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    "ja_calibrate_fr_mul": (C.c_int32, [vp, C.c_int32, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+class JoltAtlasError(RuntimeError):
+    """Raised for any non-zero status from the C ABI (the reference prover panics in the same places)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"jolt_atlas_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m jolt_atlas_b200.build` "
+            "(this package has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        buf = C.create_string_buffer(1024)
+        load().ja_last_error(buf, 1024)
+        raise JoltAtlasError(status, buf.value.decode("utf-8", "replace"))

@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's polynomial interface on top of the C ABI.
+
+Names and argument meaning follow the reference (joltworks/src/poly/*.rs) so parity tests read like
+the reference's own tests:
+  MultilinearPolynomial.{from_fr, from_i32, bind_parallel, final_claim, evaluate, len}
+        multilinear_polynomial.rs:22-35, :657-667, :728-762, :766-862
+  EqPolynomial.evals                      eq_poly.rs:77-101
+  GruenSplitEqPolynomial.{new, bind, merge, get_current_scalar, get_current_w}   split_eq_poly.rs:86-504
+  BindingOrder                            multilinear_polynomial.rs (LowToHigh / HighToLow)
+
+Field elements cross this layer as numpy uint64 arrays of shape (..., 4): little-endian limbs in
+Montgomery form, exactly ark_bn254::Fr's memory layout; challenges are {0, 0, lo, hi}.
+Errors from the C ABI raise JoltAtlasError (the reference prover panics at the same points).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import JoltAtlasError, check  # noqa: F401
+
+
+class BindingOrder:
+    LowToHigh = 0
+    HighToLow = 1
+
+
+class EvalKernel:
+    ADD, SUB, MUL, SQUARE, PROD, POW, IDENT = 0, 1, 2, 3, 4, 5, 6
+    DOT2, DOT3, SUM1, SUMHI = 16, 17, 18, 19
+    N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 16: 2, 17: 3, 18: 1, 19: 1}
+
+
+def _u64p(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_lib.u64p)
+
+
+def _fr_arg(x) -> np.ndarray:
+    a = np.ascontiguousarray(x, dtype=np.uint64)
+    assert a.shape[-1] == 4
+    return a
+
+
+class Context:
+    """Owns one CUDA device context/stream of the library (ja_init / ja_shutdown)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.ja_init(device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.ja_shutdown(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        check(self._lib.ja_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.ja_launch_count(self._h))
+
+    def timer_begin(self):
+        check(self._lib.ja_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        out = C.c_float()
+        check(self._lib.ja_timer_end(self._h, C.byref(out)))
+        return out.value
+
+    def bench_kernel(self, which: int, log_n: int, n_polys: int = 1, iters: int = 20) -> float:
+        """Average device milliseconds per launch of one kernel on resident synthetic operands."""
+        out = C.c_float()
+        check(self._lib.ja_bench_kernel(self._h, which, log_n, n_polys, iters, C.byref(out)))
+        return out.value
+
+    def calibrate_fr_mul(self, iters: int = 2000) -> float:
+        out = C.c_double()
+        check(self._lib.ja_calibrate_fr_mul(self._h, iters, C.byref(out)))
+        return out.value
+
+
+class MultilinearPolynomial:
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+
+    # -- constructors
+    @staticmethod
+    def from_fr(ctx: Context, z) -> "MultilinearPolynomial":
+        z = _fr_arg(z)
+        h = C.c_void_p()
+        check(ctx._lib.ja_poly_from_fr(ctx._h, _u64p(z), z.shape[0], C.byref(h)))
+        return MultilinearPolynomial(ctx, h)
+
+    @staticmethod
+    def from_i32(ctx: Context, z) -> "MultilinearPolynomial":
+        z = np.ascontiguousarray(z, dtype=np.int32)
+        h = C.c_void_p()
+        check(ctx._lib.ja_poly_from_i32(ctx._h, z.ctypes.data_as(_lib.i32p), z.shape[0], C.byref(h)))
+        return MultilinearPolynomial(ctx, h)
+
+    def clone(self) -> "MultilinearPolynomial":
+        h = C.c_void_p()
+        check(self.ctx._lib.ja_poly_clone(self.ctx._h, self._h, C.byref(h)))
+        return MultilinearPolynomial(self.ctx, h)
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_poly_free(self.ctx._h, self._h)
+            self._h = None
+
+    def __len__(self):
+        return int(self.ctx._lib.ja_poly_len(self._h))
+
+    def to_host(self) -> np.ndarray:
+        n = len(self)
+        out = np.empty((n, 4), dtype=np.uint64)
+        check(self.ctx._lib.ja_poly_to_host(self.ctx._h, self._h, _u64p(out), n))
+        return out
+
+    # -- PolynomialBinding
+    def bind_parallel(self, r, order: int):
+        r = _fr_arg(r)
+        check(self.ctx._lib.ja_bind(self.ctx._h, self._h, _u64p(r), order))
+
+    bind = bind_parallel
+
+    def final_claim(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        check(self.ctx._lib.ja_final_claim(self.ctx._h, self._h, _u64p(out)))
+        return out
+
+    # -- PolynomialEvaluation
+    def evaluate(self, point) -> np.ndarray:
+        point = _fr_arg(point).reshape(-1, 4)
+        out = np.empty(4, dtype=np.uint64)
+        check(self.ctx._lib.ja_poly_evaluate(self.ctx._h, self._h, _u64p(point), point.shape[0], _u64p(out)))
+        return out
+
+
+def bind_many(ctx: Context, polys, r, order: int):
+    """One `ingest_challenge`: bind several polynomials with the same challenge in one launch."""
+    r = _fr_arg(r)
+    arr = (C.c_void_p * len(polys))(*[p._h for p in polys])
+    check(ctx._lib.ja_bind_many(ctx._h, arr, len(polys), _u64p(r), order))
+
+
+class EqPolynomial:
+    @staticmethod
+    def evals(ctx: Context, r, scaling=None) -> MultilinearPolynomial:
+        r = _fr_arg(r).reshape(-1, 4)
+        h = C.c_void_p()
+        sc = _u64p(_fr_arg(scaling)) if scaling is not None else None
+        check(ctx._lib.ja_eq_evals(ctx._h, _u64p(r) if r.shape[0] else None, r.shape[0], sc, C.byref(h)))
+        return MultilinearPolynomial(ctx, h)
+
+
+class GruenSplitEqPolynomial:
+    def __init__(self, ctx: Context, w, order: int, scaling=None):
+        w = _fr_arg(w).reshape(-1, 4)
+        self.ctx = ctx
+        h = C.c_void_p()
+        sc = _u64p(_fr_arg(scaling)) if scaling is not None else None
+        check(ctx._lib.ja_spliteq_new(ctx._h, _u64p(w) if w.shape[0] else None, w.shape[0], order, sc, C.byref(h)))
+        self._h = h
+
+    new = classmethod(lambda cls, ctx, w, order: cls(ctx, w, order))
+
+    def bind(self, r):
+        check(self.ctx._lib.ja_spliteq_bind(self.ctx._h, self._h, _u64p(_fr_arg(r))))
+
+    def get_current_scalar(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        check(self.ctx._lib.ja_spliteq_current_scalar(self._h, _u64p(out)))
+        return out
+
+    def get_current_w(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        check(self.ctx._lib.ja_spliteq_current_w(self._h, _u64p(out)))
+        return out
+
+    def merge(self) -> MultilinearPolynomial:
+        h = C.c_void_p()
+        check(self.ctx._lib.ja_spliteq_merge(self.ctx._h, self._h, C.byref(h)))
+        return MultilinearPolynomial(self.ctx, h)
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_spliteq_free(self.ctx._h, self._h)
+            self._h = None
+
+
+def round_eval(ctx: Context, kernel_id: int, polys, eq: GruenSplitEqPolynomial | None = None,
+               aux_fr=None, aux_u32: int = 0, n_out: int | None = None) -> np.ndarray:
+    """Reduced sums of one `compute_message` body (see EvalKernel / include/jolt_atlas_b200.h)."""
+    if n_out is None:
+        n_out = EvalKernel.N_OUT[kernel_id]
+    arr = (C.c_void_p * len(polys))(*[p._h for p in polys])
+    out = np.empty((n_out, 4), dtype=np.uint64)
+    aux = _fr_arg(aux_fr).reshape(-1, 4) if aux_fr is not None else None
+    check(ctx._lib.ja_round_eval(ctx._h, kernel_id, arr, len(polys), eq._h if eq is not None else None,
+                                 _u64p(aux) if aux is not None else None, aux.shape[0] if aux is not None else 0,
+                                 aux_u32, _u64p(out), n_out))
+    return out
+
+
+def tensor_fold_i32(ctx: Context, A, eq: MultilinearPolynomial, transpose: bool) -> MultilinearPolynomial:
+    A = np.ascontiguousarray(A, dtype=np.int32)
+    rows, cols = A.shape
+    h = C.c_void_p()
+    check(ctx._lib.ja_tensor_fold_i32(ctx._h, A.ctypes.data_as(_lib.i32p), rows, cols, eq._h, int(transpose), C.byref(h)))
+    return MultilinearPolynomial(ctx, h)

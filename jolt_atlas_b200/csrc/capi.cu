@@ -1,0 +1,687 @@
+// C ABI implementation (include/jolt_atlas_b200.h): handle management, launch geometry, error mapping.
+// Kernels live in poly_kernels.cuh / msm_kernels.cuh.  No CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/jolt_atlas_b200.h"
+#include "fr_host.hpp"
+#include "poly_kernels.cuh"
+
+using namespace ja;
+using ja::host::FrH;
+
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define JA_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(JA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+#define JA_REQUIRE(cond, msg) \
+  do { if (!(cond)) return fail(JA_ERR_INVALID, msg); } while (0)
+
+struct ja_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::recursive_mutex mu;
+  Fr* d_partials = nullptr;        // kMaxGrid * kMaxOut
+  unsigned int* d_counter = nullptr;
+  Fr* d_out = nullptr;             // kMaxOut
+  uint64_t* h_pinned = nullptr;    // staging for small D2H/H2D
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+static constexpr int kMaxGrid = kSMs * 8;
+static constexpr int kMaxOut = 32;
+static constexpr size_t kPinnedBytes = 1 << 16;
+
+struct ja_poly {
+  size_t len = 0;
+  Fr* buf[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};
+  int cur = 0;
+  Fr* data() const { return buf[cur]; }
+};
+
+struct ja_spliteq {
+  int order = 0;
+  int m = 0;
+  int current_index = 0;
+  FrH current_scalar;
+  std::vector<FrH> w;
+  // prefix tables: level k (2^k entries) at offset 2^k - 1
+  Fr* out_levels = nullptr;
+  Fr* in_levels = nullptr;
+  int out_len = 1;   // E_out_vec.len()  (current table = level out_len-1)
+  int in_len = 1;    // E_in_vec.len()
+  const Fr* e_out() const { return out_levels + ((size_t(1) << (out_len - 1)) - 1); }
+  const Fr* e_in() const { return in_levels + ((size_t(1) << (in_len - 1)) - 1); }
+};
+
+static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline int log2z(size_t n) { int k = 0; while ((size_t(1) << k) < n) k++; return k; }
+static inline Challenge to_challenge(const uint64_t r[4]) {
+  Challenge c;
+  c.c[0] = (uint32_t)r[2]; c.c[1] = (uint32_t)(r[2] >> 32);
+  c.c[2] = (uint32_t)r[3]; c.c[3] = (uint32_t)(r[3] >> 32);
+  return c;
+}
+static inline Fr to_dev(const FrH& h) { Fr r; memcpy(r.l, h.l, 32); return r; }
+static inline unsigned grid_for(size_t work) {
+  size_t b = (work + kBlock - 1) / kBlock;
+  if (b < 1) b = 1;
+  if (b > (size_t)kSMs * 8) b = (size_t)kSMs * 8;
+  return (unsigned)b;
+}
+
+static int32_t dev_alloc(ja_ctx* c, size_t bytes, void** out) {
+  JA_CUDA(cudaMallocAsync(out, bytes ? bytes : 32, c->stream));
+  return JA_OK;
+}
+static void dev_free(ja_ctx* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
+
+extern "C" {
+
+void ja_last_error(char* buf, size_t cap) {
+  if (!buf || !cap) return;
+  snprintf(buf, cap, "%s", g_last_error.c_str());
+}
+
+int32_t ja_init(int32_t device, ja_ctx** out) {
+  if (!out) return fail(JA_ERR_INVALID, "ja_init: out is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(JA_ERR_NO_DEVICE, std::string("ja_init: no CUDA device (") + cudaGetErrorString(e) +
+                                      "); this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail(JA_ERR_INVALID, "ja_init: bad device index");
+  JA_CUDA(cudaSetDevice(device));
+  ja_ctx* c = new ja_ctx();
+  c->device = device;
+  JA_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  JA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thresh = UINT64_MAX;
+  JA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  JA_CUDA(cudaMalloc(&c->d_partials, sizeof(Fr) * kMaxGrid * kMaxOut));
+  JA_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+  JA_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
+  JA_CUDA(cudaMalloc(&c->d_out, sizeof(Fr) * kMaxOut));
+  JA_CUDA(cudaMallocHost(&c->h_pinned, kPinnedBytes));
+  JA_CUDA(cudaEventCreate(&c->ev0));
+  JA_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return JA_OK;
+}
+
+void ja_shutdown(ja_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
+  cudaFreeHost(c->h_pinned);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int32_t ja_sync(ja_ctx* c) {
+  JA_REQUIRE(c, "ja_sync: null ctx");
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  return JA_OK;
+}
+
+uint64_t ja_launch_count(const ja_ctx* c) { return c ? c->launches : 0; }
+
+// ---- polynomials --------------------------------------------------------------------------------
+int32_t ja_poly_alloc(ja_ctx* c, size_t n, ja_poly** out) {
+  JA_REQUIRE(c && out, "ja_poly_alloc: null argument");
+  JA_REQUIRE(is_pow2(n), "ja_poly_alloc: length must be a power of two");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  ja_poly* p = new ja_poly();
+  p->len = n;
+  int32_t st = dev_alloc(c, n * sizeof(Fr), (void**)&p->buf[0]);
+  if (st) { delete p; return st; }
+  p->cap[0] = n;
+  *out = p;
+  return JA_OK;
+}
+
+int32_t ja_poly_from_fr(ja_ctx* c, const uint64_t* z, size_t n, ja_poly** out) {
+  JA_REQUIRE(c && z && out, "ja_poly_from_fr: null argument");
+  int32_t st = ja_poly_alloc(c, n, out);
+  if (st) return st;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaMemcpyAsync((*out)->buf[0], z, n * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));   // host buffer is only borrowed for the call
+  return JA_OK;
+}
+
+int32_t ja_poly_from_i32(ja_ctx* c, const int32_t* z, size_t n, ja_poly** out) {
+  JA_REQUIRE(c && z && out, "ja_poly_from_i32: null argument");
+  int32_t st = ja_poly_alloc(c, n, out);
+  if (st) return st;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  int* tmp = nullptr;
+  st = dev_alloc(c, n * sizeof(int), (void**)&tmp);
+  if (st) return st;
+  JA_CUDA(cudaMemcpyAsync(tmp, z, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  k_i32_to_fr<<<grid_for(n), kBlock, 0, c->stream>>>(tmp, (*out)->buf[0], n);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  dev_free(c, tmp);
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  return JA_OK;
+}
+
+int32_t ja_poly_clone(ja_ctx* c, const ja_poly* src, ja_poly** out) {
+  JA_REQUIRE(c && src && out, "ja_poly_clone: null argument");
+  int32_t st = ja_poly_alloc(c, src->len, out);
+  if (st) return st;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaMemcpyAsync((*out)->buf[0], src->data(), src->len * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream));
+  return JA_OK;
+}
+
+size_t ja_poly_len(const ja_poly* p) { return p ? p->len : 0; }
+
+int32_t ja_poly_to_host(ja_ctx* c, const ja_poly* p, uint64_t* out, size_t cap) {
+  JA_REQUIRE(c && p && out, "ja_poly_to_host: null argument");
+  JA_REQUIRE(cap >= p->len, "ja_poly_to_host: output too small");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  JA_CUDA(cudaMemcpyAsync(out, p->data(), p->len * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  return JA_OK;
+}
+
+void ja_poly_free(ja_ctx* c, ja_poly* p) {
+  if (!c || !p) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  dev_free(c, p->buf[0]);
+  dev_free(c, p->buf[1]);
+  delete p;
+}
+
+int32_t ja_bind_many(ja_ctx* c, ja_poly* const* polys, size_t n_polys, const uint64_t r[4], int32_t order) {
+  JA_REQUIRE(c && polys && r, "ja_bind: null argument");
+  JA_REQUIRE(order == JA_LOW_TO_HIGH || order == JA_HIGH_TO_LOW, "ja_bind: bad binding order");
+  if (n_polys == 0) return JA_OK;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const Challenge ch = to_challenge(r);
+  JA_REQUIRE(r[0] == 0 && r[1] == 0, "ja_bind: challenge limbs 0,1 must be zero (MontU128Challenge)");
+  size_t done = 0;
+  while (done < n_polys) {
+    // group consecutive polys of equal length into one launch
+    const size_t len = polys[done]->len;
+    JA_REQUIRE(len >= 2, "ja_bind: polynomial is already fully bound");
+    const size_t half = len / 2;
+    BindArgs args;
+    size_t cnt = 0;
+    while (done + cnt < n_polys && cnt < (size_t)kMaxBindPolys && polys[done + cnt]->len == len) {
+      ja_poly* p = polys[done + cnt];
+      JA_REQUIRE(p != nullptr, "ja_bind: null polynomial");
+      if (order == JA_HIGH_TO_LOW) {
+        args.in[cnt] = p->data(); args.out[cnt] = p->data();   // in place: thread i touches i and i+half only
+      } else {
+        const int nxt = 1 - p->cur;
+        if (p->cap[nxt] < half) {
+          dev_free(c, p->buf[nxt]);
+          p->buf[nxt] = nullptr; p->cap[nxt] = 0;
+          int32_t st = dev_alloc(c, half * sizeof(Fr), (void**)&p->buf[nxt]);
+          if (st) return st;
+          p->cap[nxt] = half;
+        }
+        args.in[cnt] = p->data(); args.out[cnt] = p->buf[nxt];
+      }
+      cnt++;
+    }
+    dim3 grid(grid_for(half), (unsigned)cnt);
+    if (order == JA_LOW_TO_HIGH) k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
+    else                         k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
+    c->launches++;
+    JA_CUDA(cudaGetLastError());
+    for (size_t q = 0; q < cnt; q++) {
+      ja_poly* p = polys[done + q];
+      if (order == JA_LOW_TO_HIGH) p->cur = 1 - p->cur;
+      p->len = half;
+    }
+    done += cnt;
+  }
+  return JA_OK;
+}
+
+int32_t ja_bind(ja_ctx* c, ja_poly* p, const uint64_t r[4], int32_t order) {
+  JA_REQUIRE(p, "ja_bind: null polynomial");
+  ja_poly* arr[1] = {p};
+  return ja_bind_many(c, arr, 1, r, order);
+}
+
+int32_t ja_final_claim(ja_ctx* c, const ja_poly* p, uint64_t out[4]) {
+  JA_REQUIRE(c && p && out, "ja_final_claim: null argument");
+  JA_REQUIRE(p->len == 1, "ja_final_claim: polynomial is not fully bound (len != 1)");
+  return ja_poly_to_host(c, p, out, 1);
+}
+
+// ---- eq tables -----------------------------------------------------------------------------------
+static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& scale, Fr* out /* 2^m */) {
+  const size_t mh = m / 2, ml = m - mh;
+  Fr* d_r = nullptr;
+  Fr* lv[2] = {nullptr, nullptr};
+  int32_t st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_r);
+  if (st) return st;
+  if (m) {
+    JA_REQUIRE(m * 32 <= kPinnedBytes, "eq_evals: too many variables");
+    memcpy(c->h_pinned, r, m * 32);
+    JA_CUDA(cudaMemcpyAsync(d_r, c->h_pinned, m * 32, cudaMemcpyHostToDevice, c->stream));
+  }
+  st = dev_alloc(c, (size_t(2) << mh) * sizeof(Fr), (void**)&lv[0]);
+  if (st) return st;
+  st = dev_alloc(c, (size_t(2) << ml) * sizeof(Fr), (void**)&lv[1]);
+  if (st) return st;
+  EqLevelsArgs a;
+  a.w[0] = d_r; a.m[0] = (int)mh; a.rev[0] = 0; a.buf[0] = lv[0]; a.scale[0] = to_dev(scale);
+  a.w[1] = d_r + mh; a.m[1] = (int)ml; a.rev[1] = 0; a.buf[1] = lv[1]; a.scale[1] = to_dev(host::FR_ONE);
+  k_eq_levels<<<2, 1024, 0, c->stream>>>(a);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  const size_t n = size_t(1) << m;
+  k_eq_expand<<<grid_for(n), kBlock, 0, c->stream>>>(lv[0] + ((size_t(1) << mh) - 1), lv[1] + ((size_t(1) << ml) - 1),
+                                                    (int)ml, n, out);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  // h_pinned is reused by later calls: make sure the H2D copy has been consumed
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  dev_free(c, d_r); dev_free(c, lv[0]); dev_free(c, lv[1]);
+  return JA_OK;
+}
+
+int32_t ja_eq_evals(ja_ctx* c, const uint64_t* r, size_t m, const uint64_t* scale_or_null, ja_poly** out) {
+  JA_REQUIRE(c && out && (r || m == 0), "ja_eq_evals: null argument");
+  JA_REQUIRE(m <= 34, "ja_eq_evals: too many variables");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  int32_t st = ja_poly_alloc(c, size_t(1) << m, out);
+  if (st) return st;
+  FrH scale = scale_or_null ? host::from_limbs(scale_or_null) : host::FR_ONE;
+  return eq_evals_device(c, reinterpret_cast<const FrH*>(r), m, scale, (*out)->buf[0]);
+}
+
+// ---- split eq --------------------------------------------------------------------------------------
+int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, const uint64_t* scale_or_null,
+                       ja_spliteq** out) {
+  JA_REQUIRE(c && out && (w || m == 0), "ja_spliteq_new: null argument");
+  JA_REQUIRE(order == JA_LOW_TO_HIGH || order == JA_HIGH_TO_LOW, "ja_spliteq_new: bad binding order");
+  JA_REQUIRE(m <= 60, "ja_spliteq_new: too many variables");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  ja_spliteq* s = new ja_spliteq();
+  s->order = order; s->m = (int)m;
+  s->current_scalar = scale_or_null ? host::from_limbs(scale_or_null) : host::FR_ONE;
+  s->w.resize(m);
+  for (size_t i = 0; i < m; i++) s->w[i] = host::from_limbs(w + 4 * i);
+  // split_eq_poly.rs:95-143
+  size_t n_out_vars, n_in_vars, off_out, off_in;
+  if (m == 0) { n_out_vars = n_in_vars = 0; off_out = off_in = 0; s->current_index = 0; }
+  else if (order == JA_LOW_TO_HIGH) {
+    const size_t half = m / 2;            // w = [w_out (half) | w_in (m-1-half) | w_last]
+    n_out_vars = half; n_in_vars = m - 1 - half; off_out = 0; off_in = half;
+    s->current_index = (int)m;
+  } else {
+    const size_t half = m / 2;            // w = [w_first | w_in (half) | w_out (m-1-half)]
+    n_in_vars = half; n_out_vars = m - 1 - half; off_in = 1; off_out = 1 + half;
+    if (n_in_vars > m - 1) { n_in_vars = m - 1; n_out_vars = 0; }
+    s->current_index = 0;
+  }
+  s->out_len = (int)n_out_vars + 1; s->in_len = (int)n_in_vars + 1;
+  Fr* d_w = nullptr;
+  int32_t st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_w);
+  if (st) { delete s; return st; }
+  if (m) {
+    JA_REQUIRE(m * 32 <= kPinnedBytes, "ja_spliteq_new: too many variables");
+    memcpy(c->h_pinned, w, m * 32);
+    JA_CUDA(cudaMemcpyAsync(d_w, c->h_pinned, m * 32, cudaMemcpyHostToDevice, c->stream));
+  }
+  st = dev_alloc(c, (size_t(2) << n_out_vars) * sizeof(Fr), (void**)&s->out_levels);
+  if (st) { delete s; return st; }
+  st = dev_alloc(c, (size_t(2) << n_in_vars) * sizeof(Fr), (void**)&s->in_levels);
+  if (st) { delete s; return st; }
+  EqLevelsArgs a;
+  const int rev = order == JA_HIGH_TO_LOW ? 1 : 0;
+  a.w[0] = d_w + off_out; a.m[0] = (int)n_out_vars; a.rev[0] = rev; a.buf[0] = s->out_levels; a.scale[0] = to_dev(host::FR_ONE);
+  a.w[1] = d_w + off_in;  a.m[1] = (int)n_in_vars;  a.rev[1] = rev; a.buf[1] = s->in_levels;  a.scale[1] = to_dev(host::FR_ONE);
+  k_eq_levels<<<2, 1024, 0, c->stream>>>(a);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  dev_free(c, d_w);
+  *out = s;
+  return JA_OK;
+}
+
+int32_t ja_spliteq_bind(ja_ctx* c, ja_spliteq* s, const uint64_t r[4]) {
+  JA_REQUIRE(c && s && r, "ja_spliteq_bind: null argument");
+  const FrH rr = host::from_limbs(r);
+  const int n = s->m;
+  // split_eq_poly.rs:331-372
+  if (s->order == JA_LOW_TO_HIGH) {
+    JA_REQUIRE(s->current_index >= 1, "ja_spliteq_bind: already fully bound");
+    const FrH wv = s->w[s->current_index - 1];
+    const FrH prod = host::mul(wv, rr);
+    FrH f = host::sub(host::sub(host::FR_ONE, wv), rr);
+    f = host::add(host::add(f, prod), prod);
+    s->current_scalar = host::mul(s->current_scalar, f);
+    s->current_index -= 1;
+    if (n / 2 < s->current_index && s->in_len > 1) s->in_len--;
+    else if (0 < s->current_index && s->out_len > 1) s->out_len--;
+  } else {
+    JA_REQUIRE(s->current_index < n, "ja_spliteq_bind: already fully bound");
+    const FrH wv = s->w[s->current_index];
+    const FrH prod = host::mul(wv, rr);
+    FrH f = host::sub(host::sub(host::FR_ONE, wv), rr);
+    f = host::add(host::add(f, prod), prod);
+    s->current_scalar = host::mul(s->current_scalar, f);
+    s->current_index += 1;
+    if (s->current_index <= n / 2 && s->in_len > 1) s->in_len--;
+    else if (s->current_index <= n && s->out_len > 1) s->out_len--;
+  }
+  return JA_OK;
+}
+
+int32_t ja_spliteq_current_scalar(const ja_spliteq* s, uint64_t out[4]) {
+  JA_REQUIRE(s && out, "ja_spliteq_current_scalar: null argument");
+  memcpy(out, s->current_scalar.l, 32);
+  return JA_OK;
+}
+
+int32_t ja_spliteq_current_w(const ja_spliteq* s, uint64_t out[4]) {
+  JA_REQUIRE(s && out, "ja_spliteq_current_w: null argument");
+  if (s->order == JA_LOW_TO_HIGH) {
+    JA_REQUIRE(s->current_index >= 1, "ja_spliteq_current_w: fully bound");
+    memcpy(out, s->w[s->current_index - 1].l, 32);
+  } else {
+    JA_REQUIRE(s->current_index < s->m, "ja_spliteq_current_w: fully bound");
+    memcpy(out, s->w[s->current_index].l, 32);
+  }
+  return JA_OK;
+}
+
+int32_t ja_spliteq_merge(ja_ctx* c, const ja_spliteq* s, ja_poly** out) {
+  JA_REQUIRE(c && s && out, "ja_spliteq_merge: null argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const FrH* w; size_t m;
+  if (s->order == JA_LOW_TO_HIGH) { w = s->w.data(); m = (size_t)s->current_index; }
+  else { w = s->w.data() + s->current_index; m = (size_t)(s->m - s->current_index); }
+  int32_t st = ja_poly_alloc(c, size_t(1) << m, out);
+  if (st) return st;
+  return eq_evals_device(c, w, m, s->current_scalar, (*out)->buf[0]);
+}
+
+void ja_spliteq_free(ja_ctx* c, ja_spliteq* s) {
+  if (!c || !s) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  dev_free(c, s->out_levels); dev_free(c, s->in_levels);
+  delete s;
+}
+
+}  // extern "C"
+
+// ---- round evaluation ------------------------------------------------------------------------------
+template <int KID>
+static void launch_s(ja_ctx* c, const EvalPolys& P, const ja_spliteq* eq, size_t G) {
+  const int bits_in = eq->in_len - 1;
+  size_t tiles = (G + kBlock - 1) / kBlock;
+  size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
+  size_t tpb = (tiles + grid - 1) / grid;
+  grid = (tiles + tpb - 1) / tpb;
+  k_round_eval_s<KID><<<(unsigned)grid, kBlock, 0, c->stream>>>(P, eq->e_out(), eq->e_in(), bits_in, G, tpb,
+                                                                c->d_partials, c->d_counter, c->d_out);
+  c->launches++;
+}
+
+extern "C" {
+
+int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
+                      const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32,
+                      uint64_t* out_evals, size_t n_out) {
+  (void)aux_fr; (void)n_aux; (void)aux_u32;
+  JA_REQUIRE(c && polys && out_evals, "ja_round_eval: null argument");
+  JA_REQUIRE(n_polys >= 1 && n_polys <= 4, "ja_round_eval: unsupported number of polynomials");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const size_t len = polys[0]->len;
+  JA_REQUIRE(len >= 2, "ja_round_eval: polynomial already fully bound");
+  EvalPolys P;
+  for (size_t i = 0; i < 4; i++) P.p[i] = nullptr;
+  for (size_t i = 0; i < n_polys; i++) {
+    JA_REQUIRE(polys[i] && polys[i]->len == len, "ja_round_eval: polynomial length mismatch");
+    P.p[i] = polys[i]->data();
+  }
+  const size_t G = len / 2;
+  size_t want_out = 0, want_polys = 0;
+  bool family_s = true;
+  switch (kernel_id) {
+    case JA_EVAL_ADD: case JA_EVAL_SUB: want_out = 1; want_polys = 2; break;
+    case JA_EVAL_MUL: want_out = 2; want_polys = 2; break;
+    case JA_EVAL_SQUARE: want_out = 2; want_polys = 1; break;
+    case JA_EVAL_IDENT: want_out = 1; want_polys = 1; break;
+    case JA_EVAL_DOT2: want_out = 2; want_polys = 2; family_s = false; break;
+    case JA_EVAL_DOT3: want_out = 3; want_polys = 3; family_s = false; break;
+    default: return fail(JA_ERR_UNSUPPORTED, "ja_round_eval: kernel_id not implemented");
+  }
+  JA_REQUIRE(n_out == want_out, "ja_round_eval: wrong n_out for kernel_id");
+  JA_REQUIRE(n_polys == want_polys, "ja_round_eval: wrong n_polys for kernel_id");
+  if (family_s) {
+    JA_REQUIRE(eq != nullptr, "ja_round_eval: split-eq handle required for family S");
+    JA_REQUIRE(eq->order == JA_LOW_TO_HIGH, "ja_round_eval: family S expects a LowToHigh split-eq");
+    const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
+    JA_REQUIRE(cover == G, "ja_round_eval: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+    switch (kernel_id) {
+      case JA_EVAL_ADD: launch_s<0>(c, P, eq, G); break;
+      case JA_EVAL_SUB: launch_s<1>(c, P, eq, G); break;
+      case JA_EVAL_MUL: launch_s<2>(c, P, eq, G); break;
+      case JA_EVAL_SQUARE: launch_s<3>(c, P, eq, G); break;
+      case JA_EVAL_IDENT: launch_s<6>(c, P, eq, G); break;
+    }
+  } else {
+    JA_REQUIRE(eq == nullptr, "ja_round_eval: family D takes no split-eq handle");
+    unsigned grid = grid_for(G);
+    if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+    if (kernel_id == JA_EVAL_DOT2)
+      k_round_eval_dot<2><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out);
+    else
+      k_round_eval_dot<3><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out);
+    c->launches++;
+  }
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out_evals, c->h_pinned, n_out * sizeof(Fr));
+  return JA_OK;
+}
+
+// ---- MLE evaluation ----------------------------------------------------------------------------------
+int32_t ja_poly_evaluate(ja_ctx* c, const ja_poly* p, const uint64_t* point, size_t m, uint64_t out[4]) {
+  JA_REQUIRE(c && p && out && (point || m == 0), "ja_poly_evaluate: null argument");
+  JA_REQUIRE((size_t(1) << m) == p->len, "ja_poly_evaluate: point length does not match polynomial");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  // sum_x eq(point, x) * Z[x]  (dense_mlpoly.rs:265-305 computes the same sum with the two half tables)
+  ja_poly* eq = nullptr;
+  int32_t st = ja_eq_evals(c, point, m, nullptr, &eq);
+  if (st) return st;
+  unsigned grid = grid_for(p->len);
+  if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+  k_dot_full<<<grid, kBlock, 0, c->stream>>>(p->data(), eq->data(), p->len, c->d_partials, c->d_counter, c->d_out);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_pinned, sizeof(Fr));
+  ja_poly_free(c, eq);
+  return JA_OK;
+}
+
+// ---- tensor fold ---------------------------------------------------------------------------------------
+int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols, const ja_poly* eq,
+                           int32_t transpose, ja_poly** out) {
+  JA_REQUIRE(c && A && eq && out, "ja_tensor_fold_i32: null argument");
+  JA_REQUIRE(rows && cols, "ja_tensor_fold_i32: empty tensor");
+  JA_REQUIRE(eq->len >= (transpose ? cols : rows), "ja_tensor_fold_i32: eq table shorter than the folded axis");
+  const size_t out_n = transpose ? rows : cols;
+  JA_REQUIRE(is_pow2(out_n), "ja_tensor_fold_i32: output length must be a power of two");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  int* dA = nullptr;
+  int32_t st = dev_alloc(c, rows * cols * sizeof(int), (void**)&dA);
+  if (st) return st;
+  JA_CUDA(cudaMemcpyAsync(dA, A, rows * cols * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  st = ja_poly_alloc(c, out_n, out);
+  if (st) return st;
+  if (transpose) {
+    size_t threads = rows * 32;
+    k_fold_rows<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(dA, rows, cols, eq->data(), (*out)->buf[0]);
+    c->launches++;
+  } else {
+    // split rows so that the grid has >= ~4 waves worth of threads
+    size_t col_blocks = (cols + kBlock - 1) / kBlock;
+    size_t slices = 1;
+    while (col_blocks * slices < (size_t)kSMs * 4 && slices * 8 <= rows) slices *= 2;
+    size_t rps = (rows + slices - 1) / slices;
+    Fr* partial = nullptr;
+    st = dev_alloc(c, slices * cols * sizeof(Fr), (void**)&partial);
+    if (st) return st;
+    dim3 grid((unsigned)col_blocks, (unsigned)slices);
+    k_fold_cols<<<grid, kBlock, 0, c->stream>>>(dA, rows, cols, eq->data(), rps, partial);
+    k_fold_cols_finish<<<(unsigned)col_blocks, kBlock, 0, c->stream>>>(partial, slices, cols, (*out)->buf[0]);
+    c->launches += 2;
+    dev_free(c, partial);
+  }
+  JA_CUDA(cudaGetLastError());
+  dev_free(c, dA);
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  return JA_OK;
+}
+
+// ---- measurement hooks ------------------------------------------------------------------------------------
+int32_t ja_timer_begin(ja_ctx* c) {
+  JA_REQUIRE(c, "ja_timer_begin: null ctx");
+  JA_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return JA_OK;
+}
+int32_t ja_timer_end(ja_ctx* c, float* out_ms) {
+  JA_REQUIRE(c && out_ms, "ja_timer_end: null argument");
+  JA_CUDA(cudaEventRecord(c->ev1, c->stream));
+  JA_CUDA(cudaEventSynchronize(c->ev1));
+  JA_CUDA(cudaEventElapsedTime(out_ms, c->ev0, c->ev1));
+  return JA_OK;
+}
+
+__global__ void k_fill_pseudo(Fr* out, size_t n, uint32_t seed) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Fr v;   // canonical: top limb < 0x30000000
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; v.l[k] = x; }
+    v.l[7] &= 0x1fffffffu;
+    fp_store(out + i, v);
+  }
+}
+
+int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys, int32_t iters, float* out_ms) {
+  JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 1 && log_n <= 30, "ja_bench_kernel: bad argument");
+  JA_REQUIRE(n_polys >= 1 && n_polys <= kMaxBindPolys, "ja_bench_kernel: bad n_polys");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const size_t n = size_t(1) << log_n, half = n / 2;
+  const int np = (which == 0 || which == 1) ? n_polys : 2;
+  std::vector<Fr*> src(np, nullptr), dst(np, nullptr);
+  int32_t st;
+  for (int i = 0; i < np; i++) {
+    if ((st = dev_alloc(c, n * sizeof(Fr), (void**)&src[i]))) return st;
+    k_fill_pseudo<<<kSMs * 8, kBlock, 0, c->stream>>>(src[i], n, 17u + i);
+    if (which <= 1) { if ((st = dev_alloc(c, half * sizeof(Fr), (void**)&dst[i]))) return st; }
+  }
+  JA_CUDA(cudaGetLastError());
+  const uint64_t rr[4] = {0, 0, 0x0123456789abcdefull, 0x0fedcba987654321ull};
+  const Challenge ch = to_challenge(rr);
+  ja_spliteq* eq = nullptr;
+  if (which == 2 || which == 4) {
+    std::vector<uint64_t> w((size_t)log_n * 4);
+    for (int i = 0; i < log_n; i++) { w[4 * i] = 0; w[4 * i + 1] = 0; w[4 * i + 2] = 0x9e3779b97f4a7c15ull * (i + 1); w[4 * i + 3] = 0x0123456789abcdefull + i; }
+    if ((st = ja_spliteq_new(c, w.data(), (size_t)log_n, JA_LOW_TO_HIGH, nullptr, &eq))) return st;
+  }
+  auto launch = [&]() {
+    if (which <= 1) {
+      BindArgs args;
+      for (int i = 0; i < np; i++) { args.in[i] = src[i]; args.out[i] = dst[i]; }
+      dim3 grid(grid_for(half), (unsigned)np);
+      if (which == 0) k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
+      else            k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
+      c->launches++;
+    } else {
+      EvalPolys P; P.p[0] = src[0]; P.p[1] = src[1]; P.p[2] = P.p[3] = nullptr;
+      if (which == 2) launch_s<2>(c, P, eq, half);
+      else if (which == 4) launch_s<0>(c, P, eq, half);
+      else {
+        unsigned grid = grid_for(half);
+        if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+        k_round_eval_dot<2><<<grid, kBlock, 0, c->stream>>>(P, half, c->d_partials, c->d_counter, c->d_out);
+        c->launches++;
+      }
+    }
+  };
+  for (int i = 0; i < 3; i++) launch();   // warm-up
+  JA_CUDA(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < iters; i++) launch();
+  JA_CUDA(cudaEventRecord(c->ev1, c->stream));
+  JA_CUDA(cudaEventSynchronize(c->ev1));
+  JA_CUDA(cudaGetLastError());
+  float ms = 0;
+  JA_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  *out_ms = ms / iters;
+  for (int i = 0; i < np; i++) { dev_free(c, src[i]); dev_free(c, dst[i]); }
+  if (eq) ja_spliteq_free(c, eq);
+  return JA_OK;
+}
+
+// ---- calibration -----------------------------------------------------------------------------------------
+int32_t ja_calibrate_fr_mul(ja_ctx* c, int32_t iters, double* out_mul_per_s) {
+  JA_REQUIRE(c && out_mul_per_s && iters > 0, "ja_calibrate_fr_mul: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  Fr* d = nullptr;
+  int32_t st = dev_alloc(c, kBlock * sizeof(Fr), (void**)&d);
+  if (st) return st;
+  cudaEvent_t e0, e1;
+  JA_CUDA(cudaEventCreate(&e0)); JA_CUDA(cudaEventCreate(&e1));
+  const unsigned grid = kSMs * 8;
+  k_calib_fr_mul<<<grid, kBlock, 0, c->stream>>>(d, 16);   // warm-up
+  JA_CUDA(cudaEventRecord(e0, c->stream));
+  k_calib_fr_mul<<<grid, kBlock, 0, c->stream>>>(d, iters);
+  JA_CUDA(cudaEventRecord(e1, c->stream));
+  c->launches += 2;
+  JA_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  JA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *out_mul_per_s = (double)grid * kBlock * 4.0 * iters / (ms * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  dev_free(c, d);
+  return JA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// Sumcheck-side kernels: variable binding, eq tables, split-eq round evaluation, dot-style rounds,
+// i32 tensor folds.  Every kernel states the reference loop it replaces.
+// All arithmetic is canonical BN254-Fr Montgomery (fp.cuh); sums are exact field sums, hence
+// independent of reduction order / grid shape (bit-identical to the CPU prover).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "fp.cuh"
+
+namespace ja {
+
+constexpr int kSMs = 148;             // B200
+constexpr int kBlock = 256;
+
+// ---- small helpers ---------------------------------------------------------------------------
+// Montgomery form of a signed 32-bit integer with ONE product row: |v| * 2^288 * 2^-32 = |v| * R.
+// (field/ark.rs:125-136 from_i32)
+JA_DEV Fr fr_from_i32(int v) {
+  const uint32_t c288[8] = {0x15b8b9dau, 0x93e78865u, 0xb05ea154u, 0x16df2426u,
+                            0x302ab839u, 0x1271b743u, 0xec6c226eu, 0x06bc037eu};  // 2^288 mod p
+  uint32_t mag = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+  Fr r;
+  fp_mont_rows<FrParams, 1>(r.l, c288, &mag);
+  fp_final_sub<FrParams>(r.l);
+  return v < 0 ? fp_neg<FrParams>(r) : r;
+}
+// |v| up to 2^32 (difference of two i32): sign + 33-bit magnitude handled with two rows of 2^320.
+JA_DEV Fr fr_from_i64_small(long long v) {
+  const uint32_t c320[8] = {0x7c5fb586u, 0xb4c6edf9u, 0xbfeb93beu, 0x708c8d50u,
+                            0x04f7e0efu, 0x9ffd1de4u, 0x9a392866u, 0x215b02acu};  // 2^320 mod p
+  unsigned long long mag = v < 0 ? (unsigned long long)(-v) : (unsigned long long)v;
+  uint32_t b[2] = {(uint32_t)mag, (uint32_t)(mag >> 32)};
+  Fr r;
+  fp_mont_rows<FrParams, 2>(r.l, c320, b);
+  fp_final_sub<FrParams>(r.l);
+  return v < 0 ? fp_neg<FrParams>(r) : r;
+}
+
+JA_DEV Fr fr_shfl_down(const Fr& a, int delta) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, a.l[i], delta);
+  return r;
+}
+JA_DEV Fr fr_warp_sum(Fr a) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) a = fp_add<FrParams>(a, fr_shfl_down(a, d));
+  return a;  // lane 0 holds the sum
+}
+
+// Block-wide exact field sum of NOUT values per thread, then grid-wide via per-block partials and a
+// "last block" pass.  `partials` holds gridDim.x * NOUT Fr; `counter` must be 0 on entry and is reset.
+template <int NOUT>
+JA_DEV void grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out) {
+  __shared__ Fr s_part[kBlock / 32][NOUT];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) {
+    Fr v = fr_warp_sum(acc[k]);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+      Fr v = lane < (blockDim.x >> 5) ? s_part[lane][k] : fp_zero<FrParams>();
+      v = fr_warp_sum(v);
+      if (lane == 0) fp_store(&partials[(size_t)blockIdx.x * NOUT + k], v);
+    }
+  }
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) out[k] = partials[k];
+    }
+    return;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicInc(counter, gridDim.x - 1);   // wraps back to 0 after the last block
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) {
+    Fr v = fp_zero<FrParams>();
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+      const volatile uint32_t* p = reinterpret_cast<const volatile uint32_t*>(&partials[(size_t)b * NOUT + k]);
+      Fr t;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t.l[i] = p[i];
+      v = fp_add<FrParams>(v, t);
+    }
+    v = fr_warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+      Fr v = lane < (blockDim.x >> 5) ? s_part[lane][k] : fp_zero<FrParams>();
+      v = fr_warp_sum(v);
+      if (lane == 0) fp_store(&out[k], v);
+    }
+  }
+}
+
+// ---- variable binding (the "fold") ------------------------------------------------------------
+// LowToHigh: out[i] = a[2i] + r*(a[2i+1]-a[2i])      dense_mlpoly.rs:219-239
+// HighToLow: out[i] = a[i] + r*(a[i+half]-a[i])      dense_mlpoly.rs:126-141
+// Up to kMaxBindPolys polynomials of the same length per launch (one `ingest_challenge`).
+constexpr int kMaxBindPolys = 32;
+struct BindArgs {
+  const Fr* in[kMaxBindPolys];
+  Fr* out[kMaxBindPolys];
+};
+
+template <bool LOW_TO_HIGH>
+__global__ void __launch_bounds__(kBlock) k_bind(BindArgs args, Challenge r, size_t half) {
+  const Fr* __restrict__ in = args.in[blockIdx.y];
+  Fr* __restrict__ out = args.out[blockIdx.y];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    Fr a, b;
+    if (LOW_TO_HIGH) { a = fp_load(in + 2 * i); b = fp_load(in + 2 * i + 1); }
+    else             { a = fp_load(in + i);     b = fp_load(in + i + half); }
+    Fr m = fp_sub<FrParams>(b, a);
+    fp_store(out + i, fp_add<FrParams>(a, fp_mul_challenge<FrParams>(m, r)));
+  }
+}
+
+// First bind of a compact i32 polynomial (compact_polynomial.rs:272-353): 4 B/coeff in, 32 B/coeff out.
+template <bool LOW_TO_HIGH>
+__global__ void __launch_bounds__(kBlock) k_bind_i32(const int* __restrict__ in, Fr* __restrict__ out,
+                                                    Challenge r, size_t half) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    int a, b;
+    if (LOW_TO_HIGH) { int2 v = __ldg(reinterpret_cast<const int2*>(in) + i); a = v.x; b = v.y; }
+    else             { a = __ldg(in + i); b = __ldg(in + i + half); }
+    Fr fa = fr_from_i32(a);
+    Fr m = fr_from_i64_small((long long)b - (long long)a);
+    fp_store(out + i, fp_add<FrParams>(fa, fp_mul_challenge<FrParams>(m, r)));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_i32_to_fr(const int* __restrict__ in, Fr* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    fp_store(out + i, fr_from_i32(__ldg(in + i)));
+}
+
+// ---- eq tables ---------------------------------------------------------------------------------
+// All prefix tables of eq(w, .) in one buffer: level j (2^j entries) at offset 2^j - 1.
+//   rev == 0: EqPolynomial::evals_cached      (eq_poly.rs:174-194)   level j+1: [2i+1] = prev[i]*w[j], [2i] = prev[i]-[2i+1]
+//   rev == 1: EqPolynomial::evals_cached_rev  (eq_poly.rs:198-217)   level j+1: [i+2^j] = prev[i]*w[m-1-j], [i] = prev[i]-that
+// One block per table (blockIdx.x selects the descriptor): the levels are tiny (<= 2^13 products).
+struct EqLevelsArgs {
+  const Fr* w[2];
+  int m[2];
+  int rev[2];
+  Fr* buf[2];
+  Fr scale[2];
+};
+__global__ void __launch_bounds__(1024) k_eq_levels(EqLevelsArgs a) {
+  const int t = blockIdx.x;
+  const Fr* w = a.w[t];
+  const int m = a.m[t], rev = a.rev[t];
+  Fr* buf = a.buf[t];
+  if (threadIdx.x == 0) fp_store(buf, a.scale[t]);
+  __syncthreads();
+  for (int j = 0; j < m; j++) {
+    const Fr wj = rev ? w[m - 1 - j] : w[j];
+    const Fr* prev = buf + ((size_t(1) << j) - 1);
+    Fr* cur = buf + ((size_t(1) << (j + 1)) - 1);
+    for (size_t i = threadIdx.x; i < (size_t(1) << j); i += blockDim.x) {
+      Fr s = prev[i];
+      Fr hi = fp_mul<FrParams>(s, wj);
+      Fr lo = fp_sub<FrParams>(s, hi);
+      if (rev) { fp_store(cur + i + (size_t(1) << j), hi); fp_store(cur + i, lo); }
+      else     { fp_store(cur + 2 * i + 1, hi); fp_store(cur + 2 * i, lo); }
+    }
+    __syncthreads();
+  }
+}
+
+// out[x] = hi[x >> bits_lo] * lo[x & mask]   — EqPolynomial::evals (eq_poly.rs:77-101) as an outer product
+__global__ void __launch_bounds__(kBlock) k_eq_expand(const Fr* __restrict__ hi, const Fr* __restrict__ lo,
+                                                     int bits_lo, size_t n, Fr* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t mask = (size_t(1) << bits_lo) - 1;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride)
+    fp_store(out + x, fp_mul<FrParams>(fp_load(hi + (x >> bits_lo)), fp_load(lo + (x & mask))));
+}
+
+// ---- family S: split-eq weighted round evaluation, LowToHigh ------------------------------------
+// sum_{x_out} E_out[x_out] * ( sum_{x_in} E_in[x_in] * f(g) ),  g = (x_out << bits_in) | x_in
+// (GruenSplitEqPolynomial::par_fold_out_in_unreduced, split_eq_poly.rs:526-597).
+// Blocks own contiguous runs of g so a thread keeps one x_out for as long as possible and applies
+// E_out once per run (the reference's delayed outer product).
+struct EvalPolys {
+  const Fr* p[4];
+};
+
+template <int KID> struct SBody;
+template <> struct SBody<0> {  // ADD  ops/add.rs:283-296
+  static constexpr int NOUT = 1;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[1]) {
+    v[0] = fp_add<FrParams>(fp_load(P.p[0] + 2 * g), fp_load(P.p[1] + 2 * g)); }
+};
+template <> struct SBody<1> {  // SUB  ops/sub.rs:267
+  static constexpr int NOUT = 1;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[1]) {
+    v[0] = fp_sub<FrParams>(fp_load(P.p[0] + 2 * g), fp_load(P.p[1] + 2 * g)); }
+};
+template <> struct SBody<2> {  // MUL  ops/mul.rs:160-176
+  static constexpr int NOUT = 2;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[2]) {
+    Fr l0 = fp_load(P.p[0] + 2 * g), l1 = fp_load(P.p[0] + 2 * g + 1);
+    Fr r0 = fp_load(P.p[1] + 2 * g), r1 = fp_load(P.p[1] + 2 * g + 1);
+    v[0] = fp_mul<FrParams>(l0, r0);
+    v[1] = fp_mul<FrParams>(fp_sub<FrParams>(l1, l0), fp_sub<FrParams>(r1, r0)); }
+};
+template <> struct SBody<3> {  // SQUARE  ops/square.rs:163
+  static constexpr int NOUT = 2;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[2]) {
+    Fr o0 = fp_load(P.p[0] + 2 * g), o1 = fp_load(P.p[0] + 2 * g + 1);
+    Fr d = fp_sub<FrParams>(o1, o0);
+    v[0] = fp_sqr<FrParams>(o0);
+    v[1] = fp_sqr<FrParams>(d); }
+};
+template <> struct SBody<6> {  // IDENT  ps_shout/mod.rs:464-488, opening_reduction.rs:355-403
+  static constexpr int NOUT = 1;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[1]) { v[0] = fp_load(P.p[0] + 2 * g); }
+};
+
+template <int KID>
+__global__ void __launch_bounds__(kBlock)
+k_round_eval_s(EvalPolys P, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+               size_t tiles_per_block, Fr* partials, unsigned int* counter, Fr* out) {
+  constexpr int NOUT = SBody<KID>::NOUT;
+  Fr outer[NOUT], inner[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)blockIdx.x * tiles_per_block * kBlock;
+  size_t g_end = g_begin + tiles_per_block * kBlock;
+  if (g_end > G) g_end = G;
+  size_t cur_xout = ~size_t(0);
+  for (size_t g = g_begin + threadIdx.x; g < g_end; g += kBlock) {
+    const size_t x_out = g >> bits_in;
+    if (x_out != cur_xout) {
+      if (cur_xout != ~size_t(0)) {
+        Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) {
+          outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+          inner[k] = fp_zero<FrParams>();
+        }
+      }
+      cur_xout = x_out;
+    }
+    Fr v[NOUT];
+    SBody<KID>::eval(P, g, v);
+    Fr ei = fp_load(e_in + (g & mask_in));
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
+  }
+  if (cur_xout != ~size_t(0)) {
+    Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+  }
+  grid_sum<NOUT>(outer, partials, counter, out);
+}
+
+// ---- family D: plain products at X in {0,2,3}, HighToLow ----------------------------------------
+// sumcheck_evals (multilinear_polynomial.rs:873-905): e0 = a, e_k = b + (k-1)(b-a).
+template <int NPOLY>   // 2: einsum/dot.rs:292-303 ; 3: dot.rs:330-350 with eq as a third MLE of equal length
+__global__ void __launch_bounds__(kBlock)
+k_round_eval_dot(EvalPolys P, size_t half, Fr* partials, unsigned int* counter, Fr* out) {
+  constexpr int NOUT = NPOLY;
+  Fr acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) acc[k] = fp_zero<FrParams>();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    Fr prod[NOUT];
+#pragma unroll
+    for (int q = 0; q < NPOLY; q++) {
+      Fr a = fp_load(P.p[q] + i), b = fp_load(P.p[q] + i + half);
+      Fr m = fp_sub<FrParams>(b, a);
+      Fr e = fp_add<FrParams>(b, m);   // X = 2
+      if (q == 0) { prod[0] = a; prod[1] = e; } else { prod[0] = fp_mul<FrParams>(prod[0], a); prod[1] = fp_mul<FrParams>(prod[1], e); }
+      if (NOUT == 3) {
+        Fr e3 = fp_add<FrParams>(e, m);  // X = 3
+        if (q == 0) prod[2] = e3; else prod[2] = fp_mul<FrParams>(prod[2], e3);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) acc[k] = fp_add<FrParams>(acc[k], prod[k]);
+  }
+  grid_sum<NOUT>(acc, partials, counter, out);
+}
+
+// plain sum_i a[i]*b[i] over n entries (MLE evaluation against a dense eq table)
+__global__ void __launch_bounds__(kBlock) k_dot_full(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t n,
+                                                    Fr* partials, unsigned int* counter, Fr* out) {
+  Fr acc[1];
+  acc[0] = fp_zero<FrParams>();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc[0] = fp_add<FrParams>(acc[0], fp_mul<FrParams>(fp_load(a + i), fp_load(b + i)));
+  grid_sum<1>(acc, partials, counter, out);
+}
+
+// ---- i32 tensor folds (einsum operand fold, ops/einsum/mk_kn_mn.rs:47-79) ------------------------
+// transpose == 0: out[j] = sum_i from_i32(A[i*cols+j]) * eq[i]; thread per column, rows split over grid.y,
+//                 partial[y][j] summed by k_fold_cols_finish.
+__global__ void __launch_bounds__(kBlock)
+k_fold_cols(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __restrict__ eq,
+            size_t rows_per_slice, Fr* __restrict__ partial) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  size_t i0 = (size_t)blockIdx.y * rows_per_slice, i1 = i0 + rows_per_slice;
+  if (i1 > rows) i1 = rows;
+  Fr acc = fp_zero<FrParams>();
+  for (size_t i = i0; i < i1; i++) {
+    int v = __ldg(A + i * cols + j);
+    if (v != 0) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(fr_from_i32(v), fp_load(eq + i)));
+  }
+  fp_store(partial + (size_t)blockIdx.y * cols + j, acc);
+}
+__global__ void __launch_bounds__(kBlock)
+k_fold_cols_finish(const Fr* __restrict__ partial, size_t slices, size_t cols, Fr* __restrict__ out) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  Fr acc = fp_zero<FrParams>();
+  for (size_t s = 0; s < slices; s++) acc = fp_add<FrParams>(acc, fp_load(partial + s * cols + j));
+  fp_store(out + j, acc);
+}
+// transpose == 1: out[i] = sum_j from_i32(A[i*cols+j]) * eq[j]; one warp per row.
+__global__ void __launch_bounds__(kBlock)
+k_fold_rows(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __restrict__ eq, Fr* __restrict__ out) {
+  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  Fr acc = fp_zero<FrParams>();
+  for (size_t j = lane; j < cols; j += 32) {
+    int v = __ldg(A + row * cols + j);
+    if (v != 0) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(fr_from_i32(v), fp_load(eq + j)));
+  }
+  acc = fr_warp_sum(acc);
+  if (lane == 0) fp_store(out + row, acc);
+}
+
+// ---- calibration: register-resident Montgomery products (roofline denominator for integer-bound kernels)
+__global__ void __launch_bounds__(kBlock) k_calib_fr_mul(Fr* out, int iters) {
+  Fr a = fp_one<FrParams>(), b = fp_r2<FrParams>(), c = fp_one<FrParams>(), d = fp_r2<FrParams>();
+  a.l[0] += threadIdx.x; c.l[1] += blockIdx.x;
+  for (int i = 0; i < iters; i++) {   // 4 independent products per iteration
+    a = fp_mul<FrParams>(a, b);
+    c = fp_mul<FrParams>(c, d);
+    b = fp_mul<FrParams>(b, a);
+    d = fp_mul<FrParams>(d, c);
+  }
+  Fr s = fp_add<FrParams>(fp_add<FrParams>(a, b), fp_add<FrParams>(c, d));
+  if (s.l[7] == 0xdeadbeefu) fp_store(out + threadIdx.x, s);   // never true for canonical values; keeps the loop alive
+}
+
+}  // namespace ja
