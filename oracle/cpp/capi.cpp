@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE ONLY — C entry points of the CPU oracle for ctypes (tests/, __graft_entry__.smoke(),
+// bench.py's cpu_baseline / --impl reference leg).  The product library never links or loads this.
+#include <omp.h>
+#include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "sumcheck.hpp"
+#include "hyperkzg.hpp"
+
+using namespace orc;
+
+static inline FrVec load_fr(const uint64_t* p, size_t n) { FrVec v(n); memcpy((void*)v.data(), p, n * 32); return v; }
+static inline void store_fr(uint64_t* p, const Fr& x) { memcpy(p, x.l, 32); }
+static inline G1Affine load_pt(const uint64_t* p, bool inf = false) { G1Affine a; memcpy(a.x.l, p, 32); memcpy(a.y.l, p + 4, 32); a.inf = inf; return a; }
+static inline void store_pt(uint64_t* p, int32_t* inf, const G1Affine& a) { memcpy(p, a.x.l, 32); memcpy(p + 4, a.y.l, 32); if (inf) *inf = a.inf ? 1 : 0; }
+
+extern "C" {
+
+int orc_num_threads() { return omp_get_max_threads(); }
+void orc_set_threads(int n) { omp_set_num_threads(n); }
+
+void orc_blake2b256(const uint8_t* data, size_t n, uint8_t out[32]) { Blake2b256 h; h.update(data, n); h.finalize(out); }
+
+// field ops on arrays (for cross-checking the arithmetic itself): op 0 add, 1 sub, 2 mul, 3 mul by challenge limbs
+void orc_fr_binop(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    Fr x = Fr::from_raw(a + 4 * i), y = Fr::from_raw(b + 4 * i), r;
+    r = op == 0 ? x + y : op == 1 ? x - y : x * y;
+    store_fr(out + 4 * i, r);
+  }
+}
+void orc_fr_from_i64(const int64_t* v, size_t n, uint64_t* out) { for (size_t i = 0; i < n; i++) store_fr(out + 4 * i, Fr::from_i64(v[i])); }
+
+void orc_bind(uint64_t* z, size_t n, const uint64_t r[4], int order) {
+  FrVec v = load_fr(z, n);
+  bind_poly(v, Fr::from_raw(r), order);
+  memcpy(z, v.data(), v.size() * 32);
+}
+void orc_eq_evals(const uint64_t* r, size_t m, const uint64_t* scale, uint64_t* out) {
+  FrVec rr = load_fr(r, m);
+  FrVec ev = eq_evals(rr.data(), m, scale ? Fr::from_raw(scale) : Fr::one());
+  memcpy(out, ev.data(), ev.size() * 32);
+}
+void orc_evaluate(const uint64_t* z, size_t n, const uint64_t* point, size_t m, uint64_t out[4]) {
+  FrVec v = load_fr(z, n), p = load_fr(point, m);
+  store_fr(out, evaluate(v, p.data(), m));
+}
+
+// Sumcheck::prove over one instance.
+//   family 0 (split-eq, LowToHigh): kind = SKind, w = m Fr;  family 1 (dot, HighToLow): w ignored.
+// Outputs: coeffs[rounds][max_coeffs][4] (compressed: all but the linear term), ncoeffs[rounds], challenges[rounds][4],
+// final_claims[npoly][4], state[32] (transcript state after the last challenge).
+int orc_sumcheck_prove(int family, int kind, unsigned pow_d, const uint64_t* polys, size_t npoly, size_t n,
+                       const uint64_t* w, size_t m, const uint64_t claim[4], const char* label,
+                       size_t max_coeffs, uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges,
+                       uint64_t* final_claims, uint8_t state[32]) {
+  std::vector<FrVec> ps;
+  for (size_t i = 0; i < npoly; i++) ps.push_back(load_fr(polys + 4 * n * i, n));
+  std::unique_ptr<Instance> inst;
+  if (family == 0) { FrVec ww = load_fr(w, m); inst.reset(new SplitEqInstance(kind, ww.data(), m, std::move(ps), Fr::from_raw(claim), pow_d)); }
+  else inst.reset(new DotInstance(std::move(ps), Fr::from_raw(claim)));
+  Transcript t(label);
+  SumcheckProof pf = sumcheck_prove(*inst, t);
+  for (size_t r = 0; r < pf.compressed_polys.size(); r++) {
+    if (pf.compressed_polys[r].size() > max_coeffs) return -1;
+    ncoeffs[r] = (uint32_t)pf.compressed_polys[r].size();
+    for (size_t k = 0; k < pf.compressed_polys[r].size(); k++) store_fr(coeffs + 4 * (r * max_coeffs + k), pf.compressed_polys[r][k]);
+    memcpy(challenges + 4 * r, pf.challenges[r].data(), 32);
+  }
+  std::vector<Fr> fc = inst->final_claims();
+  for (size_t i = 0; i < fc.size(); i++) store_fr(final_claims + 4 * i, fc[i]);
+  memcpy(state, t.state, 32);
+  return (int)pf.compressed_polys.size();
+}
+
+// ---- curve / MSM ----
+void orc_srs_powers(const uint64_t tau_mont[4], size_t n, uint64_t* out_xy) {
+  std::vector<G1Affine> s = srs_powers(Fr::from_raw(tau_mont), n);
+  for (size_t i = 0; i < n; i++) store_pt(out_xy + 8 * i, nullptr, s[i]);
+}
+static std::vector<G1Affine> load_bases(const uint64_t* xy, size_t n) {
+  std::vector<G1Affine> b(n);
+  for (size_t i = 0; i < n; i++) b[i] = load_pt(xy + 8 * i);
+  return b;
+}
+void orc_msm_fr(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int32_t* inf) {
+  std::vector<G1Affine> b = load_bases(bases_xy, n);
+  FrVec s = load_fr(scalars, n);
+  store_pt(out_xy, inf, to_affine(msm_fr(b.data(), s.data(), n)));
+}
+void orc_msm_i64(const uint64_t* bases_xy, const int64_t* scalars, size_t n, uint64_t out_xy[8], int32_t* inf) {
+  std::vector<G1Affine> b = load_bases(bases_xy, n);
+  store_pt(out_xy, inf, to_affine(msm_i64(b.data(), scalars, n)));
+}
+void orc_sum_indexed(const uint64_t* bases_xy, size_t n_bases, const uint64_t* idx, size_t n, uint64_t out_xy[8], int32_t* inf) {
+  std::vector<G1Affine> b = load_bases(bases_xy, n_bases);
+  store_pt(out_xy, inf, to_affine(sum_indexed(b.data(), idx, n)));
+}
+int orc_on_curve(const uint64_t xy[8]) { return on_curve(load_pt(xy)) ? 1 : 0; }
+void orc_scalar_mul(const uint64_t xy[8], const uint64_t k_mont[4], uint64_t out_xy[8], int32_t* inf) {
+  uint64_t k[4]; Fr::from_raw(k_mont).to_canonical(k);
+  store_pt(out_xy, inf, to_affine(scalar_mul(load_pt(xy), k)));
+}
+
+// HyperKZG::open.  point = ell challenge limbs.  Outputs: com[(ell-1)][8] + com_inf, w[3][8] + w_inf, v[3][ell][4], state[32].
+void orc_hyperkzg_open(const uint64_t* srs_xy, size_t n, const uint64_t* poly, const uint64_t* point, size_t ell,
+                       const char* label, uint64_t* com_xy, int32_t* com_inf, uint64_t* w_xy, int32_t* w_inf,
+                       uint64_t* v, uint8_t state[32]) {
+  std::vector<G1Affine> srs = load_bases(srs_xy, n);
+  FrVec p = load_fr(poly, n);
+  std::vector<Fr> pt = load_fr(point, ell);
+  Transcript t(label);
+  HyperKZGProof pf = hyperkzg_open(srs, p, pt, t);
+  for (size_t i = 0; i < pf.com.size(); i++) store_pt(com_xy + 8 * i, com_inf + i, pf.com[i]);
+  for (size_t i = 0; i < 3; i++) store_pt(w_xy + 8 * i, w_inf + i, pf.w[i]);
+  for (size_t i = 0; i < 3; i++) for (size_t j = 0; j < ell; j++) store_fr(v + 4 * (i * ell + j), pf.v[i][j]);
+  memcpy(state, t.state, 32);
+}
+
+// ---- CPU baseline timing legs (bench.py): same synthetic workloads as ja_bench_kernel, on all host threads ----
+static FrVec pseudo(size_t n, uint32_t seed) {
+  FrVec v(n);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed; uint32_t l[8];
+    for (int k = 0; k < 8; k++) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; l[k] = x; }
+    l[7] &= 0x1fffffffu;
+    memcpy(v[i].l, l, 32);
+  }
+  return v;
+}
+// which: 0 bind LowToHigh, 1 bind HighToLow, 2 MUL round eval, 3 DOT2 round eval, 4 ADD round eval.  Returns ms per pass.
+double orc_bench_kernel(int which, int log_n, int iters) {
+  const size_t n = size_t(1) << log_n;
+  FrVec a = pseudo(n, 17), b = pseudo(n, 18);
+  const uint64_t rr[4] = {0, 0, 0x0123456789abcdefull, 0x0fedcba987654321ull};
+  const Fr r = Fr::from_raw(rr);
+  std::vector<Fr> w(log_n);
+  for (int i = 0; i < log_n; i++) { uint64_t c[4] = {0, 0, 0x9e3779b97f4a7c15ull * (i + 1), 0x0123456789abcdefull + i}; w[i] = Fr::from_raw(c); }
+  GruenSplitEq eq(w.data(), (size_t)log_n, LOW_TO_HIGH);
+  double best = 1e30;
+  volatile uint64_t sink = 0;
+  for (int it = 0; it < iters; it++) {
+    FrVec z = a;
+    auto t0 = std::chrono::steady_clock::now();
+    if (which <= 1) { bind_poly(z, r, which); sink += z[0].l[0]; }
+    else if (which == 2) { Fr q[2]; eq.fold<2>([&](size_t g, Fr* v) { Fr l0 = a[2 * g], r0 = b[2 * g]; v[0] = l0 * r0; v[1] = (a[2 * g + 1] - l0) * (b[2 * g + 1] - r0); }, q); sink += q[0].l[0]; }
+    else if (which == 4) { Fr q[1]; eq.fold<1>([&](size_t g, Fr* v) { v[0] = a[2 * g] + b[2 * g]; }, q); sink += q[0].l[0]; }
+    else { DotInstance d({a, b}, Fr::zero()); auto t1 = std::chrono::steady_clock::now(); UniPoly u = d.compute_message(0, Fr::zero()); sink += u.coeffs[0].l[0]; t0 = t1; }
+    auto t1 = std::chrono::steady_clock::now();
+    double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (ms < best) best = ms;
+  }
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// TEST INFRASTRUCTURE ONLY — CPU oracle (C++ restatement) of the sumcheck drivers and exemplar instances.
+//   joltworks/src/subprotocols/sumcheck.rs:565-599 (Sumcheck::prove), :30-184 (BatchedSumcheck::prove)
+//   jolt-atlas-core/src/onnx_proof/ops/{add.rs:283-304, sub.rs:267, mul.rs:160-185, square.rs:163, cube.rs:159-166}
+//   jolt-atlas-core/src/onnx_proof/ops/einsum/dot.rs:290-375 (EqSchedule::None and the 3-MLE cubic)
+//   joltworks/src/subprotocols/mles_product_sum.rs:15-129, :330-376
+//   joltworks/src/subprotocols/hamming_weight.rs:118-139
+// Parity unpinned at the byte level (no reference KATs); cross-checked against oracle/pyref.
+#pragma once
+#include <memory>
+#include "poly.hpp"
+#include "transcript.hpp"
+
+namespace orc {
+
+struct Instance {
+  virtual ~Instance() {}
+  virtual size_t num_rounds() const = 0;
+  virtual size_t degree() const = 0;
+  virtual Fr input_claim() const = 0;
+  virtual UniPoly compute_message(size_t round, const Fr& previous_claim) = 0;
+  virtual void ingest_challenge(const Fr& r, size_t round) = 0;
+  virtual std::vector<Fr> final_claims() const = 0;
+};
+
+// mles_product_sum.rs:330-376
+inline UniPoly finish_mles_product_sum_from_evals(const std::vector<Fr>& sum_evals, const Fr& claim, const GruenSplitEq& eq) {
+  const Fr r = eq.current_w();
+  const Fr eq0 = Fr::one() - r, eq1 = r;
+  Fr at0 = sum_evals.size() == 1 ? claim - eq1 * sum_evals[0] : (claim - eq1 * sum_evals[0]) * eq0.inv();
+  std::vector<Fr> toom; toom.push_back(at0);
+  toom.insert(toom.end(), sum_evals.begin(), sum_evals.end());
+  std::vector<Fr> tmp = UniPoly::from_evals_toom(toom).coeffs;
+  const Fr cc = Fr::one() - r, xc = r + r - Fr::one();
+  std::vector<Fr> coeffs(tmp.size() + 1, Fr::zero());
+  for (size_t i = 0; i < tmp.size(); i++) { coeffs[i] += tmp[i] * cc; coeffs[i + 1] += tmp[i] * xc; }
+  return UniPoly::from_coeff(coeffs);
+}
+
+// gruen_poly_deg_3 / deg_2 (split_eq_poly.rs:379-471)
+inline UniPoly gruen_poly_deg_3(const GruenSplitEq& eq, const Fr& q_constant, const Fr& q_quadratic, const Fr& s01) {
+  Fr eq1 = eq.current_scalar * eq.current_w();
+  Fr eq0 = eq.current_scalar - eq1;
+  Fr eqm = eq1 - eq0, eq2 = eq1 + eqm, eq3 = eq2 + eqm;
+  Fr c0 = eq0 * q_constant, c1 = s01 - c0;
+  Fr q1 = c1 * eq1.inv();
+  Fr e2 = q_quadratic + q_quadratic;
+  Fr q2 = q1 + q1 - q_constant + e2;
+  Fr q3 = q2 + q1 - q_constant + e2 + e2;
+  return UniPoly::from_evals({c0, c1, eq2 * q2, eq3 * q3});
+}
+inline UniPoly gruen_poly_deg_2(const GruenSplitEq& eq, const Fr& q0, const Fr& prev) {
+  Fr eq1 = eq.current_scalar * eq.current_w();
+  Fr eq0 = eq.current_scalar - eq1;
+  Fr eqm = eq1 - eq0, eq2 = eq1 + eqm;
+  Fr c0 = eq0 * q0, c1 = prev - c0;
+  Fr l1 = c1 * eq1.inv();
+  Fr l2 = l1 + l1 - q0;
+  return UniPoly::from_evals({c0, c1, eq2 * l2});
+}
+
+enum SKind { S_ADD = 0, S_SUB = 1, S_MUL = 2, S_SQUARE = 3, S_PROD = 4, S_POW = 5 };
+
+// Family S: split-eq weighted, LowToHigh
+struct SplitEqInstance : Instance {
+  int kind; unsigned pow_d;
+  GruenSplitEq eq;
+  std::vector<FrVec> polys;
+  Fr claim;
+  SplitEqInstance(int kind_, const Fr* w, size_t m, std::vector<FrVec> p, Fr claim_, unsigned pow_d_ = 0)
+      : kind(kind_), pow_d(pow_d_), eq(w, m, LOW_TO_HIGH), polys(std::move(p)), claim(claim_) {}
+  size_t num_rounds() const override { return eq.w.size(); }
+  size_t degree() const override {
+    switch (kind) { case S_ADD: case S_SUB: return 2; case S_MUL: case S_SQUARE: return 3;
+                    case S_POW: return pow_d + 1; default: return polys.size() + 1; }
+  }
+  Fr input_claim() const override { return claim; }
+  UniPoly compute_message(size_t, const Fr& prev) override {
+    if (kind == S_ADD || kind == S_SUB) {
+      Fr q[1];
+      const FrVec &l = polys[0], &r = polys[1];
+      if (kind == S_ADD) eq.fold<1>([&](size_t g, Fr* v) { v[0] = l[2 * g] + r[2 * g]; }, q);
+      else eq.fold<1>([&](size_t g, Fr* v) { v[0] = l[2 * g] - r[2 * g]; }, q);
+      return gruen_poly_deg_2(eq, q[0], prev);
+    }
+    if (kind == S_MUL) {
+      Fr q[2];
+      const FrVec &l = polys[0], &r = polys[1];
+      eq.fold<2>([&](size_t g, Fr* v) {
+        Fr l0 = l[2 * g], r0 = r[2 * g];
+        v[0] = l0 * r0; v[1] = (l[2 * g + 1] - l0) * (r[2 * g + 1] - r0); }, q);
+      return gruen_poly_deg_3(eq, q[0], q[1], prev);
+    }
+    if (kind == S_SQUARE) {
+      Fr q[2];
+      const FrVec& o = polys[0];
+      eq.fold<2>([&](size_t g, Fr* v) { Fr d = o[2 * g + 1] - o[2 * g]; v[0] = o[2 * g].sqr(); v[1] = d.sqr(); }, q);
+      return gruen_poly_deg_3(eq, q[0], q[1], prev);
+    }
+    const size_t d = kind == S_POW ? pow_d : polys.size();
+    std::vector<Fr> sums(d);
+    eq.fold_dyn(d, [&](size_t g, Fr* v) {
+      // prod_i (p_i0 + X*dp_i) on the grid {1, ..., d-1, inf}
+      for (size_t k = 0; k < d; k++) v[k] = Fr::one();
+      for (size_t i = 0; i < d; i++) {
+        const FrVec& z = kind == S_POW ? polys[0] : polys[i];
+        Fr p0 = z[2 * g], dp = z[2 * g + 1] - p0;
+        Fr cur = p0;
+        for (size_t k = 0; k + 1 < d; k++) { cur += dp; v[k] *= cur; }   // X = k+1
+        v[d - 1] *= dp;                                                   // X = inf
+      }
+    }, sums.data());
+    for (auto& s : sums) s *= eq.current_scalar;
+    return finish_mles_product_sum_from_evals(sums, prev, eq);
+  }
+  void ingest_challenge(const Fr& r, size_t) override {
+    eq.bind(r);
+    for (auto& p : polys) bind_poly(p, r, LOW_TO_HIGH);
+  }
+  std::vector<Fr> final_claims() const override { std::vector<Fr> f; for (auto& p : polys) f.push_back(p[0]); return f; }
+};
+
+// Family D: plain products at X in {0,2,3}, HighToLow
+struct DotInstance : Instance {
+  std::vector<FrVec> polys; Fr claim;
+  DotInstance(std::vector<FrVec> p, Fr c) : polys(std::move(p)), claim(c) {}
+  size_t num_rounds() const override { size_t k = 0; while ((size_t(1) << k) < polys[0].size()) k++; return k; }
+  size_t degree() const override { return polys.size(); }
+  Fr input_claim() const override { return claim; }
+  UniPoly compute_message(size_t, const Fr& prev) override {
+    const size_t half = polys[0].size() / 2, deg = polys.size();
+    const int nt = omp_get_max_threads();
+    std::vector<Fr> part((size_t)nt * deg, Fr::zero());
+#pragma omp parallel if (half >= 256)
+    {
+      std::vector<Fr> acc(deg, Fr::zero()), prod(deg);
+#pragma omp for schedule(static)
+      for (size_t i = 0; i < half; i++) {
+        for (size_t q = 0; q < deg; q++) {
+          Fr a = polys[q][i], b = polys[q][i + half];
+          Fr m = b - a, e = b;
+          for (size_t k = 0; k < deg; k++) {
+            Fr val = k == 0 ? a : (e += m, e);
+            prod[k] = q == 0 ? val : prod[k] * val;
+          }
+        }
+        for (size_t k = 0; k < deg; k++) acc[k] += prod[k];
+      }
+      for (size_t k = 0; k < deg; k++) part[(size_t)omp_get_thread_num() * deg + k] = acc[k];
+    }
+    std::vector<Fr> ev(deg, Fr::zero());
+    for (size_t k = 0; k < deg; k++) for (int t = 0; t < nt; t++) ev[k] += part[(size_t)t * deg + k];
+    return UniPoly::from_evals_and_hint(prev, ev);
+  }
+  void ingest_challenge(const Fr& r, size_t) override { for (auto& p : polys) bind_poly(p, r, HIGH_TO_LOW); }
+  std::vector<Fr> final_claims() const override { std::vector<Fr> f; for (auto& p : polys) f.push_back(p[0]); return f; }
+};
+
+// hamming_weight.rs:118-139
+struct HammingInstance : Instance {
+  std::vector<FrVec> polys; std::vector<Fr> gammas; Fr claim;
+  HammingInstance(std::vector<FrVec> p, std::vector<Fr> g, Fr c) : polys(std::move(p)), gammas(std::move(g)), claim(c) {}
+  size_t num_rounds() const override { size_t k = 0; while ((size_t(1) << k) < polys[0].size()) k++; return k; }
+  size_t degree() const override { return 1; }
+  Fr input_claim() const override { return claim; }
+  UniPoly compute_message(size_t, const Fr& prev) override {
+    Fr acc = Fr::zero();
+    for (size_t i = 0; i < polys.size(); i++) {
+      Fr s = Fr::zero();
+      for (size_t j = 0; j < polys[i].size() / 2; j++) s += polys[i][2 * j];
+      acc += gammas[i] * s;
+    }
+    return UniPoly::from_evals_and_hint(prev, {acc});
+  }
+  void ingest_challenge(const Fr& r, size_t) override { for (auto& p : polys) bind_poly(p, r, LOW_TO_HIGH); }
+  std::vector<Fr> final_claims() const override { std::vector<Fr> f; for (auto& p : polys) f.push_back(p[0]); return f; }
+};
+
+struct SumcheckProof {
+  std::vector<std::vector<Fr>> compressed_polys;   // coeffs except linear term, per round
+  std::vector<std::array<uint64_t, 4>> challenges; // {0,0,lo,hi}
+  Fr final_claim;
+};
+
+// Sumcheck::prove (sumcheck.rs:565-599)
+inline SumcheckProof sumcheck_prove(Instance& inst, Transcript& t) {
+  SumcheckProof pf;
+  const size_t n = inst.num_rounds();
+  Fr prev = inst.input_claim();
+  t.append_scalar(prev);
+  for (size_t round = 0; round < n; round++) {
+    UniPoly uni = inst.compute_message(round, prev);
+    std::vector<Fr> cp = uni.compress();
+    append_compressed(t, cp);
+    std::array<uint64_t, 4> c; t.challenge_optimized(c.data());
+    const Fr r = Fr::from_raw(c.data());
+    prev = uni.evaluate(r);
+    inst.ingest_challenge(r, round);
+    pf.compressed_polys.push_back(cp); pf.challenges.push_back(c);
+  }
+  pf.final_claim = prev;
+  return pf;
+}
+
+// BatchedSumcheck::prove (sumcheck.rs:30-184)
+inline SumcheckProof batched_sumcheck_prove(std::vector<Instance*>& insts, Transcript& t, std::vector<Fr>* coeffs_out = nullptr) {
+  SumcheckProof pf;
+  size_t max_rounds = 0;
+  for (auto* i : insts) if (i->num_rounds() > max_rounds) max_rounds = i->num_rounds();
+  for (auto* i : insts) t.append_scalar(i->input_claim());
+  std::vector<Fr> coeffs = t.challenge_vector(insts.size());
+  std::vector<Fr> claims;
+  for (auto* i : insts) claims.push_back(i->input_claim().mul_pow_2((unsigned)(max_rounds - i->num_rounds())));
+  for (size_t round = 0; round < max_rounds; round++) {
+    const size_t remaining = max_rounds - round;
+    std::vector<UniPoly> unis;
+    for (size_t k = 0; k < insts.size(); k++) {
+      const size_t nr = insts[k]->num_rounds();
+      if (remaining > nr) unis.push_back(UniPoly::from_coeff({insts[k]->input_claim().mul_pow_2((unsigned)(remaining - nr - 1))}));
+      else unis.push_back(insts[k]->compute_message(round - (max_rounds - nr), claims[k]));
+    }
+    UniPoly batched = UniPoly::from_coeff({});
+    for (size_t k = 0; k < insts.size(); k++) batched.add_assign(unis[k].scaled(coeffs[k]));
+    std::vector<Fr> cp = batched.compress();
+    append_compressed(t, cp);
+    std::array<uint64_t, 4> c; t.challenge_optimized(c.data());
+    const Fr r = Fr::from_raw(c.data());
+    for (size_t k = 0; k < insts.size(); k++) claims[k] = unis[k].evaluate(r);
+    for (size_t k = 0; k < insts.size(); k++) {
+      const size_t nr = insts[k]->num_rounds();
+      if (remaining <= nr) insts[k]->ingest_challenge(r, round - (max_rounds - nr));
+    }
+    pf.compressed_polys.push_back(cp); pf.challenges.push_back(c);
+  }
+  pf.final_claim = Fr::zero();
+  for (size_t k = 0; k < insts.size(); k++) pf.final_claim += claims[k] * coeffs[k];
+  if (coeffs_out) *coeffs_out = coeffs;
+  return pf;
+}
+
+}  // namespace orc

@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front-end of the C++ CPU oracle (oracle/cpp -> oracle/lib/liboracle_cpu.so).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_oracle
+
+u64p = C.POINTER(C.c_uint64)
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = build_oracle.LIB
+        if not os.path.exists(path):
+            path = build_oracle.build()
+        _lib = C.CDLL(path)
+        _lib.orc_bench_kernel.restype = C.c_double
+        _lib.orc_bench_kernel.argtypes = [C.c_int, C.c_int, C.c_int]
+        _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_sumcheck_prove.restype = C.c_int
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def blake2b256(data: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    lib().orc_blake2b256(data, C.c_size_t(len(data)), out)
+    return out.raw
+
+
+def fr_binop(op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    out = np.empty_like(a)
+    lib().orc_fr_binop(op, _p(a), _p(b), C.c_size_t(a.shape[0]), _p(out))
+    return out
+
+
+def fr_from_i64(v) -> np.ndarray:
+    v = np.ascontiguousarray(v, dtype=np.int64)
+    out = np.empty((v.shape[0], 4), dtype=np.uint64)
+    lib().orc_fr_from_i64(_p(v), C.c_size_t(v.shape[0]), _p(out))
+    return out
+
+
+def bind(z: np.ndarray, r: np.ndarray, order: int) -> np.ndarray:
+    z = np.ascontiguousarray(z, dtype=np.uint64).copy()
+    r = np.ascontiguousarray(r, dtype=np.uint64)
+    lib().orc_bind(_p(z), C.c_size_t(z.shape[0]), _p(r), order)
+    return z[: z.shape[0] // 2].copy()
+
+
+def eq_evals(r: np.ndarray, scale=None) -> np.ndarray:
+    r = np.ascontiguousarray(r, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty((1 << r.shape[0], 4), dtype=np.uint64)
+    sc = _p(np.ascontiguousarray(scale, dtype=np.uint64)) if scale is not None else None
+    lib().orc_eq_evals(_p(r), C.c_size_t(r.shape[0]), sc, _p(out))
+    return out
+
+
+def evaluate(z: np.ndarray, point: np.ndarray) -> np.ndarray:
+    z = np.ascontiguousarray(z, dtype=np.uint64)
+    point = np.ascontiguousarray(point, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_evaluate(_p(z), C.c_size_t(z.shape[0]), _p(point), C.c_size_t(point.shape[0]), _p(out))
+    return out
+
+
+def sumcheck_prove(family: int, kind: int, polys: np.ndarray, w, claim: np.ndarray, label: bytes, pow_d: int = 0):
+    """polys: (npoly, n, 4) Montgomery limbs.  Returns dict(coeffs=[per-round arrays], challenges, final_claims, state)."""
+    polys = np.ascontiguousarray(polys, dtype=np.uint64)
+    npoly, n, _ = polys.shape
+    rounds = n.bit_length() - 1
+    w = np.ascontiguousarray(w if w is not None else np.zeros((0, 4)), dtype=np.uint64).reshape(-1, 4)
+    claim = np.ascontiguousarray(claim, dtype=np.uint64)
+    maxc = 40
+    coeffs = np.zeros((rounds, maxc, 4), dtype=np.uint64)
+    ncoeffs = np.zeros(rounds, dtype=np.uint32)
+    chal = np.zeros((rounds, 4), dtype=np.uint64)
+    fin = np.zeros((npoly, 4), dtype=np.uint64)
+    state = C.create_string_buffer(32)
+    rc = lib().orc_sumcheck_prove(family, kind, C.c_uint(pow_d), _p(polys), C.c_size_t(npoly), C.c_size_t(n), _p(w),
+                                  C.c_size_t(w.shape[0]), _p(claim), label, C.c_size_t(maxc), _p(coeffs), _p(ncoeffs),
+                                  _p(chal), _p(fin), state)
+    assert rc == rounds, rc
+    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(rounds)], "challenges": chal,
+            "final_claims": fin, "state": state.raw}
+
+
+def srs_powers(tau_mont: np.ndarray, n: int) -> np.ndarray:
+    out = np.empty((n, 8), dtype=np.uint64)
+    lib().orc_srs_powers(_p(np.ascontiguousarray(tau_mont, dtype=np.uint64)), C.c_size_t(n), _p(out))
+    return out
+
+
+def msm_fr(bases: np.ndarray, scalars: np.ndarray):
+    out = np.empty(8, dtype=np.uint64)
+    inf = C.c_int32()
+    lib().orc_msm_fr(_p(bases), _p(np.ascontiguousarray(scalars, dtype=np.uint64)), C.c_size_t(scalars.shape[0]), _p(out), C.byref(inf))
+    return out, bool(inf.value)
+
+
+def msm_i64(bases: np.ndarray, scalars) -> tuple:
+    s = np.ascontiguousarray(scalars, dtype=np.int64)
+    out = np.empty(8, dtype=np.uint64)
+    inf = C.c_int32()
+    lib().orc_msm_i64(_p(bases), _p(s), C.c_size_t(s.shape[0]), _p(out), C.byref(inf))
+    return out, bool(inf.value)
+
+
+def sum_indexed(bases: np.ndarray, idx) -> tuple:
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    out = np.empty(8, dtype=np.uint64)
+    inf = C.c_int32()
+    lib().orc_sum_indexed(_p(bases), C.c_size_t(bases.shape[0]), _p(idx), C.c_size_t(idx.shape[0]), _p(out), C.byref(inf))
+    return out, bool(inf.value)
+
+
+def hyperkzg_open(srs: np.ndarray, poly: np.ndarray, point: np.ndarray, label: bytes):
+    n = poly.shape[0]
+    ell = point.shape[0]
+    com = np.zeros((max(ell - 1, 1), 8), dtype=np.uint64)
+    com_inf = np.zeros(max(ell - 1, 1), dtype=np.int32)
+    w = np.zeros((3, 8), dtype=np.uint64)
+    w_inf = np.zeros(3, dtype=np.int32)
+    v = np.zeros((3, ell, 4), dtype=np.uint64)
+    state = C.create_string_buffer(32)
+    lib().orc_hyperkzg_open(_p(srs), C.c_size_t(n), _p(np.ascontiguousarray(poly, dtype=np.uint64)),
+                            _p(np.ascontiguousarray(point, dtype=np.uint64)), C.c_size_t(ell), label,
+                            _p(com), _p(com_inf), _p(w), _p(w_inf), _p(v), state)
+    return {"com": com[: ell - 1], "com_inf": com_inf[: ell - 1], "w": w, "w_inf": w_inf, "v": v, "state": state.raw}
+
+
+def bench_kernel(which: int, log_n: int, iters: int = 3) -> float:
+    return lib().orc_bench_kernel(which, log_n, iters)
