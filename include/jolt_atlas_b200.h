@@ -133,6 +133,35 @@ int32_t ja_round_eval(ja_ctx*, int32_t kernel_id, const ja_poly* const* polys, s
 int32_t ja_tensor_fold_i32(ja_ctx*, const int32_t* A, size_t rows, size_t cols, const ja_poly* eq,
                            int32_t transpose, ja_poly** out);
 
+/* ---- SRS residency + MSM (commitment half) ---------------------------------------------------------
+ * Scalar width tags of ja_msm_host == the variants VariableBaseMSM::msm dispatches on (joltworks/src/msm/mod.rs:27-181). */
+enum { JA_MSM_FR = 0, JA_MSM_U8 = 1, JA_MSM_U16 = 2, JA_MSM_U32 = 3, JA_MSM_U64 = 4, JA_MSM_I32 = 5, JA_MSM_I64 = 6 };
+/* Upload g1_powers once per ProverSetup (hyperkzg/commitment_scheme.rs:36-44 setup_prover -> kzg.rs:108-143
+ * KZGProverKey); the Rust shim repacks ark's G1Affine {x, y, infinity} into x||y Montgomery limbs. */
+int32_t ja_srs_upload(ja_ctx*, const uint64_t* g1_affine_xy, size_t n_points, ja_srs** out);
+size_t ja_srs_len(const ja_srs*);
+void ja_srs_free(ja_ctx*, ja_srs*);
+/* UnivariateKZG::commit_as_univariate on a device-resident dense polynomial (kzg.rs:285-298 ->
+ * VariableBaseMSM::msm LargeScalars, msm/mod.rs:32-37): sum_i Z[i] * g1_powers[i].
+ * JA_ERR_KEY_LENGTH when the SRS is shorter than the polynomial (ProofVerifyError::KeyLengthError). */
+int32_t ja_msm_fr(ja_ctx*, const ja_srs*, const ja_poly* scalars, uint64_t out_xy[8], int32_t* is_inf);
+/* UnivariateKZG::commit_variable_batch / batch_msm (kzg.rs:227-243, msm/mod.rs:309-318): `count` polynomials of
+ * any lengths against the same SRS prefix, ONE bucket pipeline for the whole batch.  out_xy = count x 8 limbs. */
+int32_t ja_msm_fr_batch(ja_ctx*, const ja_srs*, const ja_poly* const* polys, size_t count, uint64_t* out_xy,
+                        int32_t* is_inf);
+/* MSM over host scalars of any width (HyperKZG::commit of compact polynomials, commitment_scheme.rs:54-73):
+ * scalars = n elements of the type named by width_tag (JA_MSM_FR: n x 4 Montgomery limbs); bases are
+ * g1_powers[base_offset .. base_offset + n).  Signed widths reproduce msm(pos) - msm(neg) (msm/mod.rs:93-176). */
+int32_t ja_msm_host(ja_ctx*, const ja_srs*, size_t base_offset, const void* scalars, int32_t width_tag, size_t n,
+                    uint64_t out_xy[8], int32_t* is_inf);
+/* HyperKZG::commit_one_hot (hyperkzg/mod.rs:520-554 -> jolt_optimizations::batch_g1_additions_multi):
+ * sum of g1_powers[indices[i]]; the caller forms indices k*T + t exactly as the reference does. */
+int32_t ja_g1_sum_indexed(ja_ctx*, const ja_srs*, const uint64_t* indices, size_t n, uint64_t out_xy[8],
+                          int32_t* is_inf);
+/* batch_commit_one_hot (hyperkzg/mod.rs:558-596): `count` index lists, list i = indices[offsets[i] .. offsets[i+1]). */
+int32_t ja_g1_sum_indexed_batch(ja_ctx*, const ja_srs*, const uint64_t* indices, const uint64_t* offsets, size_t count,
+                                uint64_t* out_xy, int32_t* is_inf);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
 /* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see this stream). */
 int32_t ja_timer_begin(ja_ctx*);

@@ -6,5 +6,6 @@ Importing this package does not load CUDA; `api.Context()` does and fails loudly
 """
 from .api import (  # noqa: F401
     BindingOrder, Context, EqPolynomial, EvalKernel, GruenSplitEqPolynomial, JoltAtlasError,
-    MultilinearPolynomial, bind_many, round_eval, tensor_fold_i32,
+    MsmWidth, MultilinearPolynomial, SRS, bind_many, g1_sum_indexed, g1_sum_indexed_batch, msm_fr, msm_fr_batch,
+    msm_host, round_eval, tensor_fold_i32,
 )

@@ -221,3 +221,81 @@ def tensor_fold_i32(ctx: Context, A, eq: MultilinearPolynomial, transpose: bool)
     h = C.c_void_p()
     check(ctx._lib.ja_tensor_fold_i32(ctx._h, A.ctypes.data_as(_lib.i32p), rows, cols, eq._h, int(transpose), C.byref(h)))
     return MultilinearPolynomial(ctx, h)
+
+
+# ---- commitment half: SRS residency, MSM, one-hot point sums (joltworks/src/msm/mod.rs, hyperkzg/) ----
+class MsmWidth:
+    FR, U8, U16, U32, U64, I32, I64 = range(7)
+    DTYPE = {1: np.uint8, 2: np.uint16, 3: np.uint32, 4: np.uint64, 5: np.int32, 6: np.int64}
+
+
+class SRS:
+    """Device-resident g1_powers of a KZGProverKey (kzg.rs:108-143): (n, 8) uint64 affine x||y Montgomery limbs."""
+
+    def __init__(self, ctx: Context, g1_affine_xy):
+        pts = np.ascontiguousarray(g1_affine_xy, dtype=np.uint64).reshape(-1, 8)
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(ctx._lib.ja_srs_upload(ctx._h, _u64p(pts), pts.shape[0], C.byref(h)))
+        self._h = h
+
+    def __len__(self):
+        return int(self.ctx._lib.ja_srs_len(self._h))
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_srs_free(self.ctx._h, self._h)
+            self._h = None
+
+
+def _pt_out(count: int):
+    return np.zeros((count, 8), dtype=np.uint64), np.zeros(count, dtype=np.int32)
+
+
+def msm_fr(ctx: Context, srs: SRS, scalars: MultilinearPolynomial):
+    """UnivariateKZG::commit_as_univariate on a device polynomial -> (xy limbs, is_infinity)."""
+    out, inf = _pt_out(1)
+    check(ctx._lib.ja_msm_fr(ctx._h, srs._h, scalars._h, _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+    return out[0], bool(inf[0])
+
+
+def msm_fr_batch(ctx: Context, srs: SRS, polys):
+    """UnivariateKZG::commit_variable_batch: one bucket pipeline for all polynomials."""
+    out, inf = _pt_out(max(len(polys), 1))
+    arr = (C.c_void_p * max(len(polys), 1))(*[p._h for p in polys])
+    check(ctx._lib.ja_msm_fr_batch(ctx._h, srs._h, arr, len(polys), _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+    return out[: len(polys)], inf[: len(polys)].astype(bool)
+
+
+def msm_host(ctx: Context, srs: SRS, scalars, width: int, base_offset: int = 0):
+    """VariableBaseMSM::msm over host scalars of the given width tag (MsmWidth)."""
+    if width == MsmWidth.FR:
+        s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    else:
+        s = np.ascontiguousarray(scalars, dtype=MsmWidth.DTYPE[width]).reshape(-1)
+    out, inf = _pt_out(1)
+    check(ctx._lib.ja_msm_host(ctx._h, srs._h, base_offset, s.ctypes.data_as(C.c_void_p), width, s.shape[0],
+                               _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+    return out[0], bool(inf[0])
+
+
+def g1_sum_indexed(ctx: Context, srs: SRS, indices):
+    """HyperKZG::commit_one_hot: sum of g1_powers[indices]."""
+    idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+    out, inf = _pt_out(1)
+    check(ctx._lib.ja_g1_sum_indexed(ctx._h, srs._h, _u64p(idx) if idx.shape[0] else None, idx.shape[0], _u64p(out),
+                                     inf.ctypes.data_as(_lib.i32p)))
+    return out[0], bool(inf[0])
+
+
+def g1_sum_indexed_batch(ctx: Context, srs: SRS, index_lists):
+    """HyperKZG::batch_commit_one_hot."""
+    offs = np.zeros(len(index_lists) + 1, dtype=np.uint64)
+    for i, l in enumerate(index_lists):
+        offs[i + 1] = offs[i] + len(l)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.uint64) for l in index_lists])
+                                if index_lists else np.zeros(0), dtype=np.uint64)
+    out, inf = _pt_out(max(len(index_lists), 1))
+    check(ctx._lib.ja_g1_sum_indexed_batch(ctx._h, srs._h, _u64p(flat) if flat.shape[0] else None, _u64p(offs),
+                                           len(index_lists), _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+    return out[: len(index_lists)], inf[: len(index_lists)].astype(bool)

@@ -1,93 +1,10 @@
 // C ABI implementation (include/jolt_atlas_b200.h): handle management, launch geometry, error mapping.
 // Kernels live in poly_kernels.cuh / msm_kernels.cuh.  No CPU fallback anywhere in this file.
-#include <cuda_runtime.h>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "../../include/jolt_atlas_b200.h"
-#include "fr_host.hpp"
+#include "common.hpp"
 #include "poly_kernels.cuh"
 
-using namespace ja;
-using ja::host::FrH;
-
 static thread_local std::string g_last_error;
-
-static int32_t fail(int32_t code, const std::string& msg) {
-  g_last_error = msg;
-  return code;
-}
-#define JA_CUDA(expr)                                                                         \
-  do {                                                                                        \
-    cudaError_t _e = (expr);                                                                  \
-    if (_e != cudaSuccess)                                                                    \
-      return fail(JA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
-  } while (0)
-#define JA_REQUIRE(cond, msg) \
-  do { if (!(cond)) return fail(JA_ERR_INVALID, msg); } while (0)
-
-struct ja_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::recursive_mutex mu;
-  Fr* d_partials = nullptr;        // kMaxGrid * kMaxOut
-  unsigned int* d_counter = nullptr;
-  Fr* d_out = nullptr;             // kMaxOut
-  uint64_t* h_pinned = nullptr;    // staging for small D2H/H2D
-  uint64_t launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
-static constexpr int kMaxGrid = kSMs * 8;
-static constexpr int kMaxOut = 32;
-static constexpr size_t kPinnedBytes = 1 << 16;
-
-struct ja_poly {
-  size_t len = 0;
-  Fr* buf[2] = {nullptr, nullptr};
-  size_t cap[2] = {0, 0};
-  int cur = 0;
-  Fr* data() const { return buf[cur]; }
-};
-
-struct ja_spliteq {
-  int order = 0;
-  int m = 0;
-  int current_index = 0;
-  FrH current_scalar;
-  std::vector<FrH> w;
-  // prefix tables: level k (2^k entries) at offset 2^k - 1
-  Fr* out_levels = nullptr;
-  Fr* in_levels = nullptr;
-  int out_len = 1;   // E_out_vec.len()  (current table = level out_len-1)
-  int in_len = 1;    // E_in_vec.len()
-  const Fr* e_out() const { return out_levels + ((size_t(1) << (out_len - 1)) - 1); }
-  const Fr* e_in() const { return in_levels + ((size_t(1) << (in_len - 1)) - 1); }
-};
-
-static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
-static inline int log2z(size_t n) { int k = 0; while ((size_t(1) << k) < n) k++; return k; }
-static inline Challenge to_challenge(const uint64_t r[4]) {
-  Challenge c;
-  c.c[0] = (uint32_t)r[2]; c.c[1] = (uint32_t)(r[2] >> 32);
-  c.c[2] = (uint32_t)r[3]; c.c[3] = (uint32_t)(r[3] >> 32);
-  return c;
-}
-static inline Fr to_dev(const FrH& h) { Fr r; memcpy(r.l, h.l, 32); return r; }
-static inline unsigned grid_for(size_t work) {
-  size_t b = (work + kBlock - 1) / kBlock;
-  if (b < 1) b = 1;
-  if (b > (size_t)kSMs * 8) b = (size_t)kSMs * 8;
-  return (unsigned)b;
-}
-
-static int32_t dev_alloc(ja_ctx* c, size_t bytes, void** out) {
-  JA_CUDA(cudaMallocAsync(out, bytes ? bytes : 32, c->stream));
-  return JA_OK;
-}
-static void dev_free(ja_ctx* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
+std::string& ja_err_slot() { return g_last_error; }
 
 extern "C" {
 

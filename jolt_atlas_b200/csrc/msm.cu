@@ -1,0 +1,253 @@
+// C ABI for the commitment half of the hot path: SRS residency, batched Pippenger MSM, one-hot point sums.
+// Kernels: msm_kernels.cuh.  No CPU fallback.
+#include "common.hpp"
+#include "msm_kernels.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+static inline uint32_t ceil_div_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// window width for n pairs of nbits-bit scalars: minimise nwin * (n + ~3 * 2^(c-1)) (madds + bucket reduction)
+static uint32_t pick_window(size_t n, uint32_t nbits) {
+  if (const char* e = getenv("JA_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 22) return (uint32_t)v; }
+  uint32_t best_c = 2; double best = 1e300;
+  for (uint32_t c = 2; c <= 20; c++) {
+    const double nwin = (double)((nbits + 1 + c - 1) / c);
+    const double cost = nwin * ((double)n + 3.0 * (double)(1u << (c - 1)) + 2000.0);
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  return best_c;
+}
+
+struct MsmJob {        // host-side description of one MSM of a batch
+  const void* d_scalars; size_t n; uint32_t kind; uint32_t nbits; size_t base_offset;
+};
+
+static uint32_t run_length() {
+  if (const char* e = getenv("JA_MSM_T")) { int v = atoi(e); if (v >= 4 && v <= 4096) return (uint32_t)v; }
+  return 64;
+}
+
+// Runs the whole pipeline for `jobs` on c->stream; results (count x MsmResult) land in host memory `out`.
+static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, MsmResult* out) {
+  const uint32_t count = (uint32_t)jobs.size();
+  if (count == 0) return JA_OK;
+  std::vector<MsmDesc> descs(count);
+  std::vector<MsmWindow> wins;
+  uint64_t total_n = 0, nbt = 0, e_max = 0;
+  uint32_t max_segs = 1;
+  for (uint32_t m = 0; m < count; m++) {
+    const MsmJob& j = jobs[m];
+    MsmDesc& d = descs[m];
+    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.pad = 0;
+    if (j.kind == MSM_INDEXED) { d.c = 1; d.nwin = 1; d.nb = 1; }
+    else {
+      d.c = pick_window(j.n, j.nbits);
+      d.nwin = (j.nbits + 1 + d.c - 1) / d.c;
+      d.nb = 1u << (d.c - 1);
+    }
+    d.bucket_base = (uint32_t)nbt; d.win_base = (uint32_t)wins.size();
+    d.entry_base = (uint32_t)total_n; d.base_offset = (uint32_t)j.base_offset;
+    for (uint32_t w = 0; w < d.nwin; w++) wins.push_back(MsmWindow{(uint32_t)(nbt + (uint64_t)w * d.nb), d.nb, d.c, m});
+    max_segs = std::max(max_segs, ceil_div_u32(d.nb, kSegBuckets));
+    nbt += (uint64_t)d.nwin * d.nb;
+    total_n += j.n;
+    e_max += (uint64_t)j.n * d.nwin;
+  }
+  JA_REQUIRE(total_n < (1ull << 31) && nbt < (1ull << 31) && e_max < (1ull << 32) - 4096, "msm: batch too large for 32-bit indexing");
+  if (total_n == 0) {
+    for (uint32_t m = 0; m < count; m++) { memset(&out[m], 0, sizeof(MsmResult)); out[m].inf = 1; }
+    return JA_OK;
+  }
+  const uint32_t T = run_length();
+  const uint32_t nruns = ceil_div_u32(e_max, T);
+  const uint32_t nwins = (uint32_t)wins.size();
+
+  // one workspace allocation, carved up (all sub-buffers 128 B aligned)
+  auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t off = 0;
+  const size_t o_desc = off; off = align(off + sizeof(MsmDesc) * count);
+  const size_t o_wins = off; off = align(off + sizeof(MsmWindow) * nwins);
+  const size_t o_offsets = off; off = align(off + sizeof(uint32_t) * (nbt + 1));
+  const size_t o_cursor = off; off = align(off + sizeof(uint32_t) * (nbt + 1));
+  const size_t ntiles = (nbt + 1 + kScanTile - 1) / kScanTile;
+  const size_t o_tiles = off; off = align(off + sizeof(uint32_t) * ntiles);
+  const size_t o_entries = off; off = align(off + sizeof(uint32_t) * (e_max + 1));
+  const size_t o_big = off; off = align(off + sizeof(uint32_t) * (nruns / kBigSpan + 2));
+  const size_t o_bigcount = off; off = align(off + sizeof(uint32_t));
+  const size_t o_buckets = off; off = align(off + sizeof(G1X) * nbt);
+  const size_t o_head = off; off = align(off + sizeof(G1X) * nruns);
+  const size_t o_tail = off; off = align(off + sizeof(G1X) * nruns);
+  const size_t o_seg = off; off = align(off + sizeof(G1X) * (size_t)nwins * max_segs);
+  const size_t o_wsum = off; off = align(off + sizeof(G1X) * nwins);
+  const size_t o_res = off; off = align(off + sizeof(MsmResult) * count);
+  char* ws = nullptr;
+  int32_t st = dev_alloc(c, off, (void**)&ws);
+  if (st) return st;
+  MsmDesc* d_desc = (MsmDesc*)(ws + o_desc);
+  MsmWindow* d_wins = (MsmWindow*)(ws + o_wins);
+  uint32_t* d_offsets = (uint32_t*)(ws + o_offsets);
+  uint32_t* d_cursor = (uint32_t*)(ws + o_cursor);
+  uint32_t* d_tiles = (uint32_t*)(ws + o_tiles);
+  uint32_t* d_entries = (uint32_t*)(ws + o_entries);
+  uint32_t* d_big = (uint32_t*)(ws + o_big);
+  uint32_t* d_bigcount = (uint32_t*)(ws + o_bigcount);
+  G1X* d_buckets = (G1X*)(ws + o_buckets);
+  G1X* d_head = (G1X*)(ws + o_head);
+  G1X* d_tail = (G1X*)(ws + o_tail);
+  G1X* d_seg = (G1X*)(ws + o_seg);
+  G1X* d_wsum = (G1X*)(ws + o_wsum);
+  MsmResult* d_res = (MsmResult*)(ws + o_res);
+
+  cudaStream_t s = c->stream;
+  JA_CUDA(cudaMemcpyAsync(d_desc, descs.data(), sizeof(MsmDesc) * count, cudaMemcpyHostToDevice, s));
+  JA_CUDA(cudaMemcpyAsync(d_wins, wins.data(), sizeof(MsmWindow) * nwins, cudaMemcpyHostToDevice, s));
+  JA_CUDA(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nbt + 1), s));
+  JA_CUDA(cudaMemsetAsync(d_bigcount, 0, sizeof(uint32_t), s));
+  const uint32_t nthreads_n = (uint32_t)total_n;
+  k_msm_hist<<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, d_offsets);
+  k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles);
+  k_scan_top<<<1, kScanBlock, 0, s>>>(d_tiles, ntiles);
+  k_scan_add<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles);
+  JA_CUDA(cudaMemcpyAsync(d_cursor, d_offsets, sizeof(uint32_t) * (nbt + 1), cudaMemcpyDeviceToDevice, s));
+  k_msm_scatter<<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, d_cursor, d_entries);
+  k_msm_accumulate<<<ceil_div_u32(nruns, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T,
+                                                           d_buckets, d_head, d_tail);
+  k_msm_combine<<<ceil_div_u32(nbt, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, T, d_head, d_tail, d_buckets, d_big,
+                                                      d_bigcount);
+  k_msm_combine_big<<<kSMs * 2, 128, 0, s>>>(d_offsets, T, d_head, d_tail, d_buckets, d_big, d_bigcount);
+  dim3 g_red(ceil_div_u32(max_segs, 128), nwins);
+  k_msm_bucket_reduce<<<g_red, 128, 0, s>>>(d_wins, d_buckets, max_segs, d_seg);
+  k_msm_window_sum<<<nwins, 128, 0, s>>>(d_wins, d_seg, max_segs, d_wsum);
+  k_msm_final<<<ceil_div_u32(count, 32), 32, 0, s>>>(d_desc, count, d_wsum, d_res);
+  c->launches += 11;
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaMemcpyAsync(out, d_res, sizeof(MsmResult) * count, cudaMemcpyDeviceToHost, s));
+  JA_CUDA(cudaStreamSynchronize(s));
+  dev_free(c, ws);
+  return JA_OK;
+}
+
+static void store_result(const MsmResult& r, uint64_t* out_xy, int32_t* is_inf) {
+  memcpy(out_xy, r.x.l, 32);
+  memcpy(out_xy + 4, r.y.l, 32);
+  if (is_inf) *is_inf = (int32_t)r.inf;
+}
+
+static const uint32_t kKindBits[8] = {254, 8, 16, 32, 64, 32, 64, 1};
+static const uint32_t kKindBytes[8] = {32, 1, 2, 4, 8, 4, 8, 8};
+
+extern "C" {
+
+int32_t ja_srs_upload(ja_ctx* c, const uint64_t* g1_affine_xy, size_t n_points, ja_srs** out) {
+  JA_REQUIRE(c && g1_affine_xy && out && n_points > 0, "ja_srs_upload: null or empty argument");
+  JA_REQUIRE(n_points < (size_t(1) << 31), "ja_srs_upload: SRS too large");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  ja_srs* s = new ja_srs();
+  s->n = n_points;
+  cudaError_t e = cudaMalloc((void**)&s->points, n_points * sizeof(G1Aff));
+  if (e != cudaSuccess) { delete s; return fail(JA_ERR_CUDA, std::string("ja_srs_upload: ") + cudaGetErrorString(e)); }
+  JA_CUDA(cudaMemcpyAsync(s->points, g1_affine_xy, n_points * sizeof(G1Aff), cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  *out = s;
+  return JA_OK;
+}
+
+size_t ja_srs_len(const ja_srs* s) { return s ? s->n : 0; }
+
+void ja_srs_free(ja_ctx* c, ja_srs* s) {
+  if (!c || !s) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(s->points);
+  delete s;
+}
+
+int32_t ja_msm_fr_batch(ja_ctx* c, const ja_srs* srs, const ja_poly* const* polys, size_t count, uint64_t* out_xy,
+                        int32_t* is_inf) {
+  JA_REQUIRE(c && srs && (polys || count == 0) && out_xy, "ja_msm_fr_batch: null argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  std::vector<MsmJob> jobs(count);
+  for (size_t i = 0; i < count; i++) {
+    JA_REQUIRE(polys[i], "ja_msm_fr_batch: null polynomial");
+    if (polys[i]->len > srs->n)
+      return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, polynomial needs " +
+                                         std::to_string(polys[i]->len));
+    jobs[i] = MsmJob{polys[i]->data(), polys[i]->len, MSM_FR, 254, 0};
+  }
+  std::vector<MsmResult> res(count);
+  int32_t st = msm_engine(c, srs, jobs, res.data());
+  if (st) return st;
+  for (size_t i = 0; i < count; i++) store_result(res[i], out_xy + 8 * i, is_inf ? is_inf + i : nullptr);
+  return JA_OK;
+}
+
+int32_t ja_msm_fr(ja_ctx* c, const ja_srs* srs, const ja_poly* scalars, uint64_t out_xy[8], int32_t* is_inf) {
+  const ja_poly* arr[1] = {scalars};
+  return ja_msm_fr_batch(c, srs, arr, 1, out_xy, is_inf);
+}
+
+int32_t ja_msm_host(ja_ctx* c, const ja_srs* srs, size_t base_offset, const void* scalars, int32_t width_tag, size_t n,
+                    uint64_t out_xy[8], int32_t* is_inf) {
+  JA_REQUIRE(c && srs && (scalars || n == 0) && out_xy, "ja_msm_host: null argument");
+  JA_REQUIRE(width_tag >= 0 && width_tag <= 6, "ja_msm_host: bad width tag");
+  if (base_offset + n > srs->n)
+    return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, MSM needs " +
+                                       std::to_string(base_offset + n));
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  MsmResult res;
+  if (n == 0) { memset(&res, 0, sizeof(res)); res.inf = 1; store_result(res, out_xy, is_inf); return JA_OK; }
+  void* d = nullptr;
+  const size_t bytes = n * kKindBytes[width_tag];
+  int32_t st = dev_alloc(c, bytes, &d);
+  if (st) return st;
+  JA_CUDA(cudaMemcpyAsync(d, scalars, bytes, cudaMemcpyHostToDevice, c->stream));
+  std::vector<MsmJob> jobs{MsmJob{d, n, (uint32_t)width_tag, kKindBits[width_tag], base_offset}};
+  st = msm_engine(c, srs, jobs, &res);
+  dev_free(c, d);
+  if (st) return st;
+  store_result(res, out_xy, is_inf);
+  return JA_OK;
+}
+
+int32_t ja_g1_sum_indexed_batch(ja_ctx* c, const ja_srs* srs, const uint64_t* indices, const uint64_t* offsets,
+                                size_t count, uint64_t* out_xy, int32_t* is_inf) {
+  JA_REQUIRE(c && srs && offsets && out_xy, "ja_g1_sum_indexed_batch: null argument");
+  if (count == 0) return JA_OK;
+  const size_t total = offsets[count];
+  JA_REQUIRE(indices || total == 0, "ja_g1_sum_indexed_batch: null indices");
+  for (size_t i = 0; i < total; i++)
+    if (indices[i] >= srs->n)
+      return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, index " +
+                                         std::to_string(indices[i]) + " requested");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  uint64_t* d = nullptr;
+  int32_t st = dev_alloc(c, (total ? total : 1) * 8, (void**)&d);
+  if (st) return st;
+  if (total) JA_CUDA(cudaMemcpyAsync(d, indices, total * 8, cudaMemcpyHostToDevice, c->stream));
+  std::vector<MsmJob> jobs(count);
+  for (size_t i = 0; i < count; i++) {
+    JA_REQUIRE(offsets[i + 1] >= offsets[i], "ja_g1_sum_indexed_batch: offsets must be non-decreasing");
+    jobs[i] = MsmJob{d + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), MSM_INDEXED, 1, 0};
+  }
+  std::vector<MsmResult> res(count);
+  st = msm_engine(c, srs, jobs, res.data());
+  dev_free(c, d);
+  if (st) return st;
+  for (size_t i = 0; i < count; i++) store_result(res[i], out_xy + 8 * i, is_inf ? is_inf + i : nullptr);
+  return JA_OK;
+}
+
+int32_t ja_g1_sum_indexed(ja_ctx* c, const ja_srs* srs, const uint64_t* indices, size_t n, uint64_t out_xy[8],
+                          int32_t* is_inf) {
+  const uint64_t offs[2] = {0, n};
+  return ja_g1_sum_indexed_batch(c, srs, indices, offs, 1, out_xy, is_inf);
+}
+
+}  // extern "C"

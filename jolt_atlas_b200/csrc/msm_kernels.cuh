@@ -1,0 +1,343 @@
+// Multi-scalar multiplication over BN254 G1: batched Pippenger (bucket method) for sm_100a.
+//
+// Replaces the MSM family the reference reaches through joltworks/src/msm/mod.rs:27-181
+// (VariableBaseMSM::msm by scalar width -> ark-ec, external), :309-318 (batch_msm), and
+// joltworks/src/poly/commitment/hyperkzg/mod.rs:520-596 (commit_one_hot / batch_commit_one_hot ->
+// jolt_optimizations::batch_g1_additions_multi, external).  The result of an MSM is a group element, so
+// any complete algorithm yields the reference's affine point bit for bit.
+//
+// One pipeline serves a whole BATCH of MSMs that share the SRS (HyperKZG::open commits l-1 folded
+// polynomials at once; witness commitment sums hundreds of one-hot index lists):
+//   1  k_msm_hist      signed-digit recoding of every scalar, histogram over (msm, window, bucket)
+//   2  k_scan*         exclusive scan of the histogram -> bucket offsets
+//   3  k_msm_scatter   counting-sort scatter of (base index | sign) by bucket
+//   4  k_msm_accumulate  every thread sums a FIXED-SIZE run of T sorted entries (mixed XYZZ additions);
+//                      runs are cut at bucket boundaries, so load balance does not depend on how the
+//                      digits are distributed (one-hot commits are a single bucket, small scalars are
+//                      skewed).  Buckets inside one run are final; buckets spanning runs leave one
+//                      partial per run (head / tail).
+//   5  k_msm_combine   per bucket: add the partials of the runs it spans (wide buckets go to a
+//                      block-cooperative kernel, k_msm_combine_big)
+//   6  k_msm_bucket_reduce / k_msm_window_sum   sum_b (b+1) * B_b per window: per-thread running sums over
+//                      segments of buckets + one small scalar multiple, then a block tree per window
+//   7  k_msm_final     Horner over the windows (c doublings each) and conversion to affine
+// Integer-throughput bound (8M+2S per pair and window); the 64 B base gathers are hidden behind it.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ec.cuh"
+
+namespace ja {
+
+enum MsmKind : uint32_t {
+  MSM_FR = 0,      // Fr scalars, Montgomery form (LargeScalars)
+  MSM_U8 = 1, MSM_U16 = 2, MSM_U32 = 3, MSM_U64 = 4,   // msm_u8/u16/u32/u64
+  MSM_I32 = 5, MSM_I64 = 6,                            // I32Scalars / I64Scalars: msm(pos) - msm(neg) == signed digits
+  MSM_INDEXED = 7  // sum of selected bases (one-hot commit): scalars = u64 base indices, every digit is 1
+};
+
+struct MsmDesc {
+  const void* scalars;
+  uint32_t n;            // pairs in this MSM
+  uint32_t kind;
+  uint32_t c;            // window bits (signed digits in [-2^(c-1), 2^(c-1)])
+  uint32_t nwin;         // windows
+  uint32_t nb;           // buckets per window = 2^(c-1)
+  uint32_t bucket_base;  // first global bucket id of this MSM
+  uint32_t win_base;     // first global window id of this MSM
+  uint32_t entry_base;   // prefix sum of n over the batch (thread -> msm lookup)
+  uint32_t base_offset;  // SRS index of base 0 (ignored for MSM_INDEXED)
+  uint32_t pad;
+};
+
+constexpr uint32_t kSignBit = 0x80000000u;
+
+// msm id of global scalar position g: largest m with entry_base[m] <= g
+JA_DEV uint32_t msm_find(const MsmDesc* __restrict__ d, uint32_t count, uint32_t g) {
+  uint32_t lo = 0, hi = count - 1;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if (d[mid].entry_base <= g) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// magnitude limbs (little-endian u32, zero padded to 10 words) and sign of scalar j of MSM d
+JA_DEV bool msm_load_scalar(const MsmDesc& d, uint32_t j, uint32_t (&s)[10]) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) s[i] = 0;
+  bool neg = false;
+  switch (d.kind) {
+    case MSM_FR: {
+      Fr a = fp_load(reinterpret_cast<const Fr*>(d.scalars) + j);
+      const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+      Fr r;
+      fp_mont_rows<FrParams, 8>(r.l, a.l, one);     // a * R^-1: Montgomery -> canonical integer
+      fp_final_sub<FrParams>(r.l);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = r.l[i];
+      break; }
+    case MSM_U8: s[0] = reinterpret_cast<const uint8_t*>(d.scalars)[j]; break;
+    case MSM_U16: s[0] = reinterpret_cast<const uint16_t*>(d.scalars)[j]; break;
+    case MSM_U32: s[0] = reinterpret_cast<const uint32_t*>(d.scalars)[j]; break;
+    case MSM_U64: { unsigned long long v = reinterpret_cast<const unsigned long long*>(d.scalars)[j];
+      s[0] = (uint32_t)v; s[1] = (uint32_t)(v >> 32); break; }
+    case MSM_I32: { int v = reinterpret_cast<const int*>(d.scalars)[j];
+      neg = v < 0; s[0] = neg ? (uint32_t)(-(long long)v) : (uint32_t)v; break; }
+    case MSM_I64: { long long v = reinterpret_cast<const long long*>(d.scalars)[j];
+      neg = v < 0; unsigned long long m = neg ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
+      s[0] = (uint32_t)m; s[1] = (uint32_t)(m >> 32); break; }
+    default: break;
+  }
+  return neg;
+}
+
+// Visit the non-zero signed digits of scalar j: f(key, payload) with key = global bucket id.
+template <class F>
+JA_DEV void msm_for_each_digit(const MsmDesc& d, uint32_t j, F&& f) {
+  if (d.kind == MSM_INDEXED) {
+    unsigned long long idx = reinterpret_cast<const unsigned long long*>(d.scalars)[j];
+    f(d.bucket_base, (uint32_t)idx);
+    return;
+  }
+  uint32_t s[10];
+  const bool neg = msm_load_scalar(d, j, s);
+  const uint32_t c = d.c, nb = d.nb, full = 1u << c;
+  const uint32_t base = d.base_offset + j;
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < d.nwin; w++) {
+    const uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
+    unsigned long long two = ((unsigned long long)s[word + 1] << 32) | s[word];
+    uint32_t raw = (uint32_t)((two >> sh) & (full - 1)) + carry;
+    bool dneg = false;
+    if (raw > nb) { raw = full - raw; carry = 1; dneg = true; } else carry = 0;
+    if (raw) f(d.bucket_base + w * nb + (raw - 1), base | ((dneg != neg) ? kSignBit : 0u));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_msm_hist(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n, uint32_t* __restrict__ hist) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_n) return;
+  const uint32_t m = msm_find(descs, count, g);
+  const MsmDesc d = descs[m];
+  msm_for_each_digit(d, g - d.entry_base, [&](uint32_t key, uint32_t) { atomicAdd(hist + key, 1u); });
+}
+
+__global__ void __launch_bounds__(256)
+k_msm_scatter(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n, uint32_t* __restrict__ cursor,
+              uint32_t* __restrict__ entries) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_n) return;
+  const uint32_t m = msm_find(descs, count, g);
+  const MsmDesc d = descs[m];
+  msm_for_each_digit(d, g - d.entry_base, [&](uint32_t key, uint32_t payload) {
+    entries[atomicAdd(cursor + key, 1u)] = payload; });
+}
+
+// ---- exclusive scan of a u32 array (histogram -> offsets), 3 launches ------------------------------
+constexpr int kScanBlock = 512, kScanItems = 8, kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0, winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+    s_warp[lane] = winc - w;          // exclusive prefix of warp totals
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  uint32_t res = inc - v + s_warp[warp];
+  if (total) *total = s_warp[32];
+  __syncthreads();
+  return res;
+}
+
+// in-place: data[i] <- exclusive prefix within its tile; tile_sums[tile] = tile total
+__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(uint32_t* data, size_t n, uint32_t* tile_sums) {
+  __shared__ uint32_t s_warp[33];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) { v[i] = base + i < n ? data[base + i] : 0; sum += v[i]; }
+  uint32_t total;
+  uint32_t pre = block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) { if (base + i < n) data[base + i] = pre; pre += v[i]; }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of tile_sums in place
+__global__ void __launch_bounds__(kScanBlock) k_scan_top(uint32_t* tile_sums, size_t ntiles) {
+  __shared__ uint32_t s_warp[33];
+  uint32_t running = 0;
+  for (size_t base = 0; base < ntiles; base += kScanBlock) {
+    const size_t i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0, total;
+    uint32_t pre = block_excl_scan(v, s_warp, &total);
+    if (i < ntiles) tile_sums[i] = running + pre;
+    running += total;
+  }
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_add(uint32_t* data, size_t n, const uint32_t* tile_sums) {
+  const uint32_t add = tile_sums[blockIdx.x];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) if (base + i < n) data[base + i] += add;
+}
+
+// ---- pass A: fixed-size runs of the sorted entry list ------------------------------------------------
+// offsets has nbt + 1 entries (offsets[nbt] = number of entries E).  Thread t owns entries [t*T, (t+1)*T).
+__global__ void __launch_bounds__(128)
+k_msm_accumulate(const uint32_t* __restrict__ offsets, uint32_t nbt, const uint32_t* __restrict__ entries,
+                 const G1Aff* __restrict__ bases, uint32_t T, G1X* __restrict__ bucket_sums,
+                 G1X* __restrict__ head, G1X* __restrict__ tail) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t E = offsets[nbt];
+  const unsigned long long start64 = (unsigned long long)t * T;
+  if (start64 >= E) return;
+  const uint32_t start = (uint32_t)start64;
+  const uint32_t end = (E - start < T) ? E : start + T;
+  // bucket containing `start`: largest b with offsets[b] <= start (skipping empty buckets to the right)
+  uint32_t lo = 0, hi = nbt - 1;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if (__ldg(offsets + mid) <= start) lo = mid; else hi = mid - 1;
+  }
+  uint32_t b = lo;
+  uint32_t next_off = __ldg(offsets + b + 1);
+  uint32_t pos = start;
+  uint32_t e = __ldg(entries + pos);
+  G1Aff pt = g1aff_load(bases + (e & ~kSignBit));
+  while (pos < end) {
+    const uint32_t seg_end = next_off < end ? next_off : end;
+    G1X acc;
+    for (uint32_t p = pos; p < seg_end; p++) {
+      const G1Aff cur = pt;
+      const bool neg = (e & kSignBit) != 0;
+      if (p + 1 < end) { e = __ldg(entries + p + 1); pt = g1aff_load(bases + (e & ~kSignBit)); }
+      if (p == pos) { acc = g1x_from_aff(cur); if (neg) acc.Y = fq_neg(acc.Y); }
+      else g1x_madd(acc, cur, neg);
+    }
+    const bool complete = __ldg(offsets + b) >= start && next_off <= end;
+    if (complete) g1x_store(bucket_sums + b, acc);
+    else if (pos == start) g1x_store(head + t, acc);
+    else g1x_store(tail + t, acc);
+    pos = seg_end;
+    if (pos < end) {
+      do { b++; next_off = __ldg(offsets + b + 1); } while (next_off <= pos);
+    }
+  }
+}
+
+// ---- pass B: per bucket, add the partials of the runs it spans -------------------------------------
+constexpr uint32_t kBigSpan = 48;
+JA_DEV G1X msm_piece(const G1X* head, const G1X* tail, uint32_t c, uint32_t c0, bool starts_on_run) {
+  return (c == c0 && !starts_on_run) ? g1x_load(tail + c) : g1x_load(head + c);
+}
+__global__ void __launch_bounds__(128)
+k_msm_combine(const uint32_t* __restrict__ offsets, uint32_t nbt, uint32_t T, const G1X* __restrict__ head,
+              const G1X* __restrict__ tail, G1X* __restrict__ bucket_sums, uint32_t* __restrict__ big_list,
+              uint32_t* __restrict__ big_count) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbt) return;
+  const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+  if (o0 == o1) { g1x_store(bucket_sums + b, g1x_inf()); return; }
+  const uint32_t c0 = o0 / T, c1 = (o1 - 1) / T;
+  if (c0 == c1) return;                       // final value written by pass A
+  if (c1 - c0 > kBigSpan) { big_list[atomicAdd(big_count, 1u)] = b; return; }
+  const bool on_run = (o0 % T) == 0;
+  G1X acc = msm_piece(head, tail, c0, c0, on_run);
+  for (uint32_t c = c0 + 1; c <= c1; c++) g1x_add(acc, g1x_load(head + c));
+  g1x_store(bucket_sums + b, acc);
+}
+// wide buckets (skewed digits, one-hot sums): one block per bucket, strided partial sums + shared-memory tree
+__global__ void __launch_bounds__(128)
+k_msm_combine_big(const uint32_t* __restrict__ offsets, uint32_t T, const G1X* __restrict__ head,
+                  const G1X* __restrict__ tail, G1X* __restrict__ bucket_sums, const uint32_t* __restrict__ big_list,
+                  const uint32_t* __restrict__ big_count) {
+  __shared__ G1X s_acc[128];
+  const uint32_t nbig = *big_count;
+  for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
+    const uint32_t b = big_list[i];
+    const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+    const uint32_t c0 = o0 / T, c1 = (o1 - 1) / T;
+    const bool on_run = (o0 % T) == 0;
+    G1X acc = g1x_inf();
+    for (uint32_t c = c0 + threadIdx.x; c <= c1; c += blockDim.x) g1x_add(acc, msm_piece(head, tail, c, c0, on_run));
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+      if (threadIdx.x < s) { G1X a = s_acc[threadIdx.x]; g1x_add(a, s_acc[threadIdx.x + s]); s_acc[threadIdx.x] = a; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) g1x_store(bucket_sums + b, s_acc[0]);
+    __syncthreads();
+  }
+}
+
+// ---- bucket reduction: W = sum_b (b+1) * B_b per window ------------------------------------------------
+struct MsmWindow { uint32_t bucket_base, nb, c, msm; };
+constexpr uint32_t kSegBuckets = 32;
+// grid (ceil(max_segs/128), n_windows); seg_part[w * max_segs + seg]
+__global__ void __launch_bounds__(128)
+k_msm_bucket_reduce(const MsmWindow* __restrict__ wins, const G1X* __restrict__ bucket_sums, uint32_t max_segs,
+                    G1X* __restrict__ seg_part) {
+  const MsmWindow w = wins[blockIdx.y];
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lo = seg * kSegBuckets;
+  if (lo >= w.nb) return;
+  const uint32_t hi = lo + kSegBuckets < w.nb ? lo + kSegBuckets : w.nb;
+  G1X run = g1x_inf(), tot = g1x_inf();
+  for (uint32_t b = hi; b-- > lo;) {
+    g1x_add(run, g1x_load(bucket_sums + w.bucket_base + b));
+    g1x_add(tot, run);
+  }
+  // sum_b (b+1) B_b = sum_b (b-lo+1) B_b + lo * sum_b B_b
+  if (lo) g1x_add(tot, g1x_mul_small(run, lo));
+  g1x_store(seg_part + (size_t)blockIdx.y * max_segs + seg, tot);
+}
+// one block per window: tree sum of its segment partials
+__global__ void __launch_bounds__(128)
+k_msm_window_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ seg_part, uint32_t max_segs,
+                 G1X* __restrict__ window_sums) {
+  __shared__ G1X s_acc[128];
+  const MsmWindow w = wins[blockIdx.x];
+  const uint32_t nsegs = (w.nb + kSegBuckets - 1) / kSegBuckets;
+  G1X acc = g1x_inf();
+  for (uint32_t s = threadIdx.x; s < nsegs; s += blockDim.x) g1x_add(acc, g1x_load(seg_part + (size_t)blockIdx.x * max_segs + s));
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s && threadIdx.x + s < nsegs) { G1X a = s_acc[threadIdx.x]; g1x_add(a, s_acc[threadIdx.x + s]); s_acc[threadIdx.x] = a; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) g1x_store(window_sums + blockIdx.x, s_acc[0]);
+}
+
+// ---- final: Horner over windows + affine conversion; one thread per MSM -------------------------------
+struct MsmResult { Fq x, y; uint32_t inf; uint32_t pad[3]; };   // 80 B
+__global__ void __launch_bounds__(32)
+k_msm_final(const MsmDesc* __restrict__ descs, uint32_t count, const G1X* __restrict__ window_sums,
+            MsmResult* __restrict__ out) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= count) return;
+  const MsmDesc d = descs[m];
+  G1X acc = g1x_inf();
+  for (uint32_t w = d.nwin; w-- > 0;) {
+    if (!g1x_is_inf(acc)) for (uint32_t k = 0; k < d.c; k++) acc = g1x_dbl(acc);
+    g1x_add(acc, g1x_load(window_sums + d.win_base + w));
+  }
+  MsmResult r;
+  if (g1x_is_inf(acc)) { r.x = fp_zero<FqParams>(); r.y = fp_zero<FqParams>(); r.inf = 1; }
+  else { G1Aff a = g1x_to_aff(acc); r.x = a.x; r.y = a.y; r.inf = 0; }
+  r.pad[0] = r.pad[1] = r.pad[2] = 0;
+  out[m] = r;
+}
+
+}  // namespace ja

@@ -9,8 +9,11 @@
 
 namespace ja {
 
+#ifndef JA_COMMON_CONSTS
+#define JA_COMMON_CONSTS
 constexpr int kSMs = 148;             // B200
 constexpr int kBlock = 256;
+#endif
 
 // ---- small helpers ---------------------------------------------------------------------------
 // Montgomery form of a signed 32-bit integer with ONE product row: |v| * 2^288 * 2^-32 = |v| * R.
