@@ -37,6 +37,7 @@ typedef struct ja_ctx ja_ctx;
 typedef struct ja_poly ja_poly;       /* device-resident MultilinearPolynomial (dense Fr, or compact i32 before its first bind) */
 typedef struct ja_spliteq ja_spliteq; /* device-resident GruenSplitEqPolynomial */
 typedef struct ja_srs ja_srs;         /* device-resident KZG SRS (g1_powers) */
+typedef struct ja_hkzg ja_hkzg;       /* in-flight HyperKZG::open (folded polynomials resident on the device) */
 
 enum { JA_LOW_TO_HIGH = 0, JA_HIGH_TO_LOW = 1 };
 
@@ -139,6 +140,10 @@ enum { JA_MSM_FR = 0, JA_MSM_U8 = 1, JA_MSM_U16 = 2, JA_MSM_U32 = 3, JA_MSM_U64 
 /* Upload g1_powers once per ProverSetup (hyperkzg/commitment_scheme.rs:36-44 setup_prover -> kzg.rs:108-143
  * KZGProverKey); the Rust shim repacks ark's G1Affine {x, y, infinity} into x||y Montgomery limbs. */
 int32_t ja_srs_upload(ja_ctx*, const uint64_t* g1_affine_xy, size_t n_points, ja_srs** out);
+/* SRS::setup's fixed-base loop on device (hyperkzg/kzg.rs:45-66): g1_powers[i] = beta^i * g1.  The caller samples
+ * beta and g1 (arkworks UniformRand over ChaCha20 stays on the host, kzg.rs:34-36). */
+int32_t ja_srs_generate(ja_ctx*, const uint64_t g1_xy[8], const uint64_t beta[4], size_t n_points, ja_srs** out);
+int32_t ja_srs_to_host(ja_ctx*, const ja_srs*, size_t first, size_t count, uint64_t* out_xy);
 size_t ja_srs_len(const ja_srs*);
 void ja_srs_free(ja_ctx*, ja_srs*);
 /* UnivariateKZG::commit_as_univariate on a device-resident dense polynomial (kzg.rs:285-298 ->
@@ -162,6 +167,28 @@ int32_t ja_g1_sum_indexed(ja_ctx*, const ja_srs*, const uint64_t* indices, size_
 int32_t ja_g1_sum_indexed_batch(ja_ctx*, const ja_srs*, const uint64_t* indices, const uint64_t* offsets, size_t count,
                                 uint64_t* out_xy, int32_t* is_inf);
 
+/* ---- HyperKZG::open (joltworks/src/poly/commitment/hyperkzg/mod.rs:400-447) --------------------------------------
+ * Split at the two transcript interaction points so that a Rust caller keeps its own Blake2bTranscript:
+ *   begin    Phase 1: l-1 folds Pi[j] = point[l-i-1]*(prev[2j+1]-prev[2j]) + prev[2j] (:413-428) and
+ *            commit_variable_batch(polys[1..]) (kzg.rs:227-243) -> com (l-1 points).  point = l challenges {0,0,lo,hi}.
+ *            caller: transcript.append_points(com); r = transcript.challenge_scalar()            (:439-440)
+ *   evals    v[i][j] = eval_as_univariate(polys[j], u[i]), u = [r, -r, r^2] (:441, :245-257); v_out = 3 x l Fr, point-major
+ *            caller: transcript.append_scalars(v); q_powers = transcript.challenge_scalar_powers(l)   (:258-260)
+ *   witness  B = sum_k q^k polys[k] (:262-270), h_i = (B - B(u_i))/(x - u_i) (:213-229), w = commit_batch(h) (3 points)
+ *            caller: transcript.append_points(w); transcript.challenge_scalar()                   (:276-277)
+ * Errors: JA_ERR_KEY_LENGTH (SRS too short), JA_ERR_INVALID (length != 2^l, as the reference's assert_eq!). */
+int32_t ja_hyperkzg_open_begin(ja_ctx*, const ja_srs*, const ja_poly* poly, const uint64_t* point, size_t ell,
+                               ja_hkzg** out, uint64_t* com_xy, int32_t* com_inf);
+int32_t ja_hyperkzg_open_evals(ja_ctx*, ja_hkzg*, const uint64_t r[4], uint64_t* v_out);
+int32_t ja_hyperkzg_open_witness(ja_ctx*, ja_hkzg*, const uint64_t r[4], const uint64_t* q_powers, uint64_t* w_xy,
+                                 int32_t* w_inf);
+void ja_hyperkzg_open_free(ja_ctx*, ja_hkzg*);
+/* The same three steps with the library's own Blake2b transcript (joltworks/src/transcripts/blake2b.rs) in between:
+ * transcript_state/n_rounds are the running state and round counter, read on entry and written back. */
+int32_t ja_hyperkzg_open(ja_ctx*, const ja_srs*, const ja_poly* poly, const uint64_t* point, size_t ell,
+                         uint8_t transcript_state[32], uint32_t* n_rounds, uint64_t* com_xy, int32_t* com_inf,
+                         uint64_t* w_xy, int32_t* w_inf, uint64_t* v_out);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
 /* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see this stream). */
 int32_t ja_timer_begin(ja_ctx*);
@@ -172,6 +199,8 @@ int32_t ja_timer_end(ja_ctx*, float* out_ms);
  *          2 = round eval MUL (split-eq, 2 polys), 3 = round eval DOT2, 4 = round eval ADD
  * Returns the average device time per launch in *out_ms. */
 int32_t ja_bench_kernel(ja_ctx*, int32_t which, int32_t log_n, int32_t n_polys, int32_t iters, float* out_ms);
+/* device-side pseudo-random canonical Fr (xorshift of the index; synthetic bench operands) */
+int32_t ja_poly_random(ja_ctx*, size_t n, uint32_t seed, ja_poly** out);
 /* register-resident Montgomery-product loop; returns achieved Fr-mul/s in *out_mul_per_s */
 int32_t ja_calibrate_fr_mul(ja_ctx*, int32_t iters, double* out_mul_per_s);
 

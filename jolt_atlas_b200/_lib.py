@@ -43,6 +43,8 @@ SIGNATURES = {
     "ja_round_eval": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, u64p, C.c_size_t, C.c_uint32, u64p, C.c_size_t]),
     "ja_tensor_fold_i32": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vp, C.c_int32, vpp]),
     "ja_srs_upload": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
+    "ja_srs_generate": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),
+    "ja_srs_to_host": (C.c_int32, [vp, vp, C.c_size_t, C.c_size_t, u64p]),
     "ja_srs_len": (C.c_size_t, [vp]),
     "ja_srs_free": (None, [vp, vp]),
     "ja_msm_fr": (C.c_int32, [vp, vp, vp, u64p, i32p]),
@@ -50,9 +52,15 @@ SIGNATURES = {
     "ja_msm_host": (C.c_int32, [vp, vp, C.c_size_t, vp, C.c_int32, C.c_size_t, u64p, i32p]),
     "ja_g1_sum_indexed": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p, i32p]),
     "ja_g1_sum_indexed_batch": (C.c_int32, [vp, vp, u64p, u64p, C.c_size_t, u64p, i32p]),
+    "ja_hyperkzg_open_begin": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, vpp, u64p, i32p]),
+    "ja_hyperkzg_open_evals": (C.c_int32, [vp, vp, u64p, u64p]),
+    "ja_hyperkzg_open_witness": (C.c_int32, [vp, vp, u64p, u64p, u64p, i32p]),
+    "ja_hyperkzg_open_free": (None, [vp, vp]),
+    "ja_hyperkzg_open": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, C.c_char_p, u32p, u64p, i32p, u64p, i32p, u64p]),
     "ja_timer_begin": (C.c_int32, [vp]),
     "ja_timer_end": (C.c_int32, [vp, C.POINTER(C.c_float)]),
     "ja_bench_kernel": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    "ja_poly_random": (C.c_int32, [vp, C.c_size_t, C.c_uint32, vpp]),
     "ja_calibrate_fr_mul": (C.c_int32, [vp, C.c_int32, C.POINTER(C.c_double)]),
 }
 

@@ -110,6 +110,13 @@ class MultilinearPolynomial:
         check(ctx._lib.ja_poly_from_i32(ctx._h, z.ctypes.data_as(_lib.i32p), z.shape[0], C.byref(h)))
         return MultilinearPolynomial(ctx, h)
 
+    @staticmethod
+    def random(ctx: Context, n: int, seed: int = 1) -> "MultilinearPolynomial":
+        """Device-generated pseudo-random canonical Fr coefficients (synthetic bench operands)."""
+        h = C.c_void_p()
+        check(ctx._lib.ja_poly_random(ctx._h, n, seed, C.byref(h)))
+        return MultilinearPolynomial(ctx, h)
+
     def clone(self) -> "MultilinearPolynomial":
         h = C.c_void_p()
         check(self.ctx._lib.ja_poly_clone(self.ctx._h, self._h, C.byref(h)))
@@ -239,6 +246,23 @@ class SRS:
         check(ctx._lib.ja_srs_upload(ctx._h, _u64p(pts), pts.shape[0], C.byref(h)))
         self._h = h
 
+    @classmethod
+    def generate(cls, ctx: Context, g1_xy, beta, n: int) -> "SRS":
+        """SRS::setup's fixed-base loop on device: g1_powers[i] = beta^i * g1."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        h = C.c_void_p()
+        g = np.ascontiguousarray(g1_xy, dtype=np.uint64).reshape(8)
+        check(ctx._lib.ja_srs_generate(ctx._h, _u64p(g), _u64p(_fr_arg(beta)), n, C.byref(h)))
+        self._h = h
+        return self
+
+    def to_host(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = len(self) - first if count is None else count
+        out = np.empty((count, 8), dtype=np.uint64)
+        check(self.ctx._lib.ja_srs_to_host(self.ctx._h, self._h, first, count, _u64p(out)))
+        return out
+
     def __len__(self):
         return int(self.ctx._lib.ja_srs_len(self._h))
 
@@ -299,3 +323,62 @@ def g1_sum_indexed_batch(ctx: Context, srs: SRS, index_lists):
     check(ctx._lib.ja_g1_sum_indexed_batch(ctx._h, srs._h, _u64p(flat) if flat.shape[0] else None, _u64p(offs),
                                            len(index_lists), _u64p(out), inf.ctypes.data_as(_lib.i32p)))
     return out[: len(index_lists)], inf[: len(index_lists)].astype(bool)
+
+
+# ---- HyperKZG::open (hyperkzg/mod.rs:400-447) ----
+class Blake2bTranscriptState:
+    """Running state + round counter of a Blake2bTranscript (transcripts/blake2b.rs:11-26), as the library's
+    all-in-one entry points exchange it.  new(label) follows blake2b.rs:81-100."""
+
+    def __init__(self, label: bytes):
+        import hashlib
+        assert len(label) <= 32
+        self.state = hashlib.blake2b(label + b"\0" * (32 - len(label)), digest_size=32).digest()
+        self.n_rounds = 0
+
+
+def hyperkzg_open(ctx: Context, srs: SRS, poly: MultilinearPolynomial, point, transcript: Blake2bTranscriptState):
+    """HyperKZG::open -> dict(com, com_inf, w, w_inf, v); advances `transcript` exactly as the reference does."""
+    point = _fr_arg(point).reshape(-1, 4)
+    ell = point.shape[0]
+    com, com_inf = _pt_out(max(ell - 1, 1))
+    w, w_inf = _pt_out(3)
+    v = np.zeros((3, ell, 4), dtype=np.uint64)
+    st = C.create_string_buffer(transcript.state, 32)
+    nr = C.c_uint32(transcript.n_rounds)
+    check(ctx._lib.ja_hyperkzg_open(ctx._h, srs._h, poly._h, _u64p(point), ell, st, C.byref(nr), _u64p(com),
+                                    com_inf.ctypes.data_as(_lib.i32p), _u64p(w), w_inf.ctypes.data_as(_lib.i32p), _u64p(v)))
+    transcript.state = st.raw
+    transcript.n_rounds = nr.value
+    return {"com": com[: ell - 1], "com_inf": com_inf[: ell - 1], "w": w, "w_inf": w_inf, "v": v}
+
+
+class HyperKZGOpening:
+    """The split form of HyperKZG::open for callers that own the transcript (the Rust shim's shape)."""
+
+    def __init__(self, ctx: Context, srs: SRS, poly: MultilinearPolynomial, point):
+        point = _fr_arg(point).reshape(-1, 4)
+        self.ctx, self.ell = ctx, point.shape[0]
+        self.com, self.com_inf = _pt_out(max(self.ell - 1, 1))
+        h = C.c_void_p()
+        check(ctx._lib.ja_hyperkzg_open_begin(ctx._h, srs._h, poly._h, _u64p(point), self.ell, C.byref(h),
+                                              _u64p(self.com), self.com_inf.ctypes.data_as(_lib.i32p)))
+        self._h = h
+        self.com, self.com_inf = self.com[: self.ell - 1], self.com_inf[: self.ell - 1]
+
+    def evals(self, r) -> np.ndarray:
+        v = np.zeros((3, self.ell, 4), dtype=np.uint64)
+        check(self.ctx._lib.ja_hyperkzg_open_evals(self.ctx._h, self._h, _u64p(_fr_arg(r)), _u64p(v)))
+        return v
+
+    def witness(self, r, q_powers):
+        w, w_inf = _pt_out(3)
+        q = _fr_arg(q_powers).reshape(-1, 4)
+        check(self.ctx._lib.ja_hyperkzg_open_witness(self.ctx._h, self._h, _u64p(_fr_arg(r)), _u64p(q), _u64p(w),
+                                                     w_inf.ctypes.data_as(_lib.i32p)))
+        return w, w_inf
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_hyperkzg_open_free(self.ctx._h, self._h)
+            self._h = None

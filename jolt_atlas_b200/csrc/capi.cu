@@ -519,6 +519,17 @@ __global__ void k_fill_pseudo(Fr* out, size_t n, uint32_t seed) {
   }
 }
 
+int32_t ja_poly_random(ja_ctx* c, size_t n, uint32_t seed, ja_poly** out) {
+  JA_REQUIRE(c && out, "ja_poly_random: null argument");
+  int32_t st = ja_poly_alloc(c, n, out);
+  if (st) return st;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  k_fill_pseudo<<<kSMs * 8, kBlock, 0, c->stream>>>((*out)->buf[0], n, seed);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  return JA_OK;
+}
+
 int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys, int32_t iters, float* out_ms) {
   JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 1 && log_n <= 30, "ja_bench_kernel: bad argument");
   JA_REQUIRE(n_polys >= 1 && n_polys <= kMaxBindPolys, "ja_bench_kernel: bad n_polys");
@@ -587,9 +598,9 @@ int32_t ja_calibrate_fr_mul(ja_ctx* c, int32_t iters, double* out_mul_per_s) {
   cudaEvent_t e0, e1;
   JA_CUDA(cudaEventCreate(&e0)); JA_CUDA(cudaEventCreate(&e1));
   const unsigned grid = kSMs * 8;
-  k_calib_fr_mul<<<grid, kBlock, 0, c->stream>>>(d, 16);   // warm-up
+  k_calib_mul<FrParams><<<grid, kBlock, 0, c->stream>>>(d, 16);   // warm-up
   JA_CUDA(cudaEventRecord(e0, c->stream));
-  k_calib_fr_mul<<<grid, kBlock, 0, c->stream>>>(d, iters);
+  k_calib_mul<FrParams><<<grid, kBlock, 0, c->stream>>>(d, iters);
   JA_CUDA(cudaEventRecord(e1, c->stream));
   c->launches += 2;
   JA_CUDA(cudaEventSynchronize(e1));

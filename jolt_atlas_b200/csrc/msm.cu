@@ -12,17 +12,16 @@ static inline uint32_t ceil_div_u32(uint64_t a, uint64_t b) { return (uint32_t)(
 static uint32_t pick_window(size_t n, uint32_t nbits) {
   if (const char* e = getenv("JA_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 22) return (uint32_t)v; }
   uint32_t best_c = 2; double best = 1e300;
-  for (uint32_t c = 2; c <= 20; c++) {
-    const double nwin = (double)((nbits + 1 + c - 1) / c);
-    const double cost = nwin * ((double)n + 3.0 * (double)(1u << (c - 1)) + 2000.0);
+  for (uint32_t c = 2; c <= 16; c++) {   // c > 16: scatter + bucket reduction outgrow the saved additions (measured)
+    const uint32_t nwin = (nbits + 1 + c - 1) / c;
+    const uint32_t top_bits = nbits + 1 - (nwin - 1) * c;                 // content bits of the top window (incl. carry)
+    const double top_frac = 1.0 - 1.0 / (double)(1ull << (top_bits < 30 ? top_bits : 30));
+    // mixed additions (one per non-zero digit) + bucket reduction (2 full additions per bucket) + fixed per-window work
+    const double cost = ((double)(nwin - 1) + top_frac) * (double)n + (double)nwin * (2.8 * (double)(1u << (c - 1)) + 2000.0);
     if (cost < best) { best = cost; best_c = c; }
   }
   return best_c;
 }
-
-struct MsmJob {        // host-side description of one MSM of a batch
-  const void* d_scalars; size_t n; uint32_t kind; uint32_t nbits; size_t base_offset;
-};
 
 static uint32_t run_length() {
   if (const char* e = getenv("JA_MSM_T")) { int v = atoi(e); if (v >= 4 && v <= 4096) return (uint32_t)v; }
@@ -36,7 +35,7 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   std::vector<MsmDesc> descs(count);
   std::vector<MsmWindow> wins;
   uint64_t total_n = 0, nbt = 0, e_max = 0;
-  uint32_t max_segs = 1;
+  uint32_t max_segs = 1, max_nwin = 1;
   for (uint32_t m = 0; m < count; m++) {
     const MsmJob& j = jobs[m];
     MsmDesc& d = descs[m];
@@ -51,6 +50,7 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
     d.entry_base = (uint32_t)total_n; d.base_offset = (uint32_t)j.base_offset;
     for (uint32_t w = 0; w < d.nwin; w++) wins.push_back(MsmWindow{(uint32_t)(nbt + (uint64_t)w * d.nb), d.nb, d.c, m});
     max_segs = std::max(max_segs, ceil_div_u32(d.nb, kSegBuckets));
+    max_nwin = std::max(max_nwin, d.nwin);
     nbt += (uint64_t)d.nwin * d.nb;
     total_n += j.n;
     e_max += (uint64_t)j.n * d.nwin;
@@ -101,30 +101,56 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   MsmResult* d_res = (MsmResult*)(ws + o_res);
 
   cudaStream_t s = c->stream;
+  // JA_MSM_PROFILE=1: per-stage CUDA-event timings on stderr (tuning aid; adds synchronisation)
+  const bool prof = getenv("JA_MSM_PROFILE") != nullptr;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  auto stage = [&](const char* name) { if (!prof) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); marks.push_back({name, e}); };
+#define STAGE(name) stage(name)
+  stage("begin");
   JA_CUDA(cudaMemcpyAsync(d_desc, descs.data(), sizeof(MsmDesc) * count, cudaMemcpyHostToDevice, s));
   JA_CUDA(cudaMemcpyAsync(d_wins, wins.data(), sizeof(MsmWindow) * nwins, cudaMemcpyHostToDevice, s));
   JA_CUDA(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nbt + 1), s));
   JA_CUDA(cudaMemsetAsync(d_bigcount, 0, sizeof(uint32_t), s));
   const uint32_t nthreads_n = (uint32_t)total_n;
-  k_msm_hist<<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, d_offsets);
+  k_msm_digits<false><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_offsets, nullptr);
+  STAGE("hist");
   k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles);
   k_scan_top<<<1, kScanBlock, 0, s>>>(d_tiles, ntiles);
   k_scan_add<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles);
   JA_CUDA(cudaMemcpyAsync(d_cursor, d_offsets, sizeof(uint32_t) * (nbt + 1), cudaMemcpyDeviceToDevice, s));
-  k_msm_scatter<<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, d_cursor, d_entries);
-  k_msm_accumulate<<<ceil_div_u32(nruns, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T,
-                                                           d_buckets, d_head, d_tail);
+  STAGE("scan");
+  k_msm_digits<true><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_cursor, d_entries);
+  STAGE("scatter");
+  {
+    int occ = 4;
+    if (const char* e = getenv("JA_MSM_OCC")) occ = atoi(e);
+    const unsigned g = ceil_div_u32(nruns, 128);
+    if (occ <= 4) k_msm_accumulate<4><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail);
+    else if (occ == 5) k_msm_accumulate<5><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail);
+    else k_msm_accumulate<6><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail);
+  }
+  STAGE("accumulate");
   k_msm_combine<<<ceil_div_u32(nbt, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, T, d_head, d_tail, d_buckets, d_big,
                                                       d_bigcount);
   k_msm_combine_big<<<kSMs * 2, 128, 0, s>>>(d_offsets, T, d_head, d_tail, d_buckets, d_big, d_bigcount);
+  STAGE("combine");
   dim3 g_red(ceil_div_u32(max_segs, 128), nwins);
   k_msm_bucket_reduce<<<g_red, 128, 0, s>>>(d_wins, d_buckets, max_segs, d_seg);
   k_msm_window_sum<<<nwins, 128, 0, s>>>(d_wins, d_seg, max_segs, d_wsum);
+  STAGE("bucket_reduce");
   k_msm_final<<<ceil_div_u32(count, 32), 32, 0, s>>>(d_desc, count, d_wsum, d_res);
+  STAGE("final");
   c->launches += 11;
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaMemcpyAsync(out, d_res, sizeof(MsmResult) * count, cudaMemcpyDeviceToHost, s));
   JA_CUDA(cudaStreamSynchronize(s));
+  if (prof) {
+    fprintf(stderr, "[msm] n=%llu nbt=%llu e_max=%llu T=%u:", (unsigned long long)total_n, (unsigned long long)nbt, (unsigned long long)e_max, T);
+    for (size_t i = 1; i < marks.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second); fprintf(stderr, " %s=%.3f", marks[i].first, ms); }
+    fprintf(stderr, "\n");
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
+#undef STAGE
   dev_free(c, ws);
   return JA_OK;
 }
@@ -133,6 +159,14 @@ static void store_result(const MsmResult& r, uint64_t* out_xy, int32_t* is_inf) 
   memcpy(out_xy, r.x.l, 32);
   memcpy(out_xy + 4, r.y.l, 32);
   if (is_inf) *is_inf = (int32_t)r.inf;
+}
+
+int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, uint64_t* out_xy, int32_t* is_inf) {
+  std::vector<MsmResult> res(jobs.size());
+  int32_t st = msm_engine(c, srs, jobs, res.data());
+  if (st) return st;
+  for (size_t i = 0; i < jobs.size(); i++) store_result(res[i], out_xy + 8 * i, is_inf ? is_inf + i : nullptr);
+  return JA_OK;
 }
 
 static const uint32_t kKindBits[8] = {254, 8, 16, 32, 64, 32, 64, 1};
@@ -152,6 +186,40 @@ int32_t ja_srs_upload(ja_ctx* c, const uint64_t* g1_affine_xy, size_t n_points, 
   JA_CUDA(cudaMemcpyAsync(s->points, g1_affine_xy, n_points * sizeof(G1Aff), cudaMemcpyHostToDevice, c->stream));
   JA_CUDA(cudaStreamSynchronize(c->stream));
   *out = s;
+  return JA_OK;
+}
+
+int32_t ja_srs_generate(ja_ctx* c, const uint64_t g1_xy[8], const uint64_t beta[4], size_t n_points, ja_srs** out) {
+  JA_REQUIRE(c && g1_xy && beta && out && n_points > 0, "ja_srs_generate: null or empty argument");
+  JA_REQUIRE(n_points < (size_t(1) << 31), "ja_srs_generate: SRS too large");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  ja_srs* s = new ja_srs();
+  s->n = n_points;
+  cudaError_t e = cudaMalloc((void**)&s->points, n_points * sizeof(G1Aff));
+  if (e != cudaSuccess) { delete s; return fail(JA_ERR_CUDA, std::string("ja_srs_generate: ") + cudaGetErrorString(e)); }
+  G1Aff* table = nullptr;
+  int32_t st = dev_alloc(c, 256 * sizeof(G1Aff), (void**)&table);
+  if (st) { cudaFree(s->points); delete s; return st; }
+  G1Aff g; memcpy(g.x.l, g1_xy, 32); memcpy(g.y.l, g1_xy + 4, 32);
+  Fr b; memcpy(b.l, beta, 32);
+  k_srs_table<<<1, 1, 0, c->stream>>>(g, table);
+  k_srs_powers<<<ceil_div_u32(n_points, 128), 128, 0, c->stream>>>(table, b, (uint32_t)n_points, s->points);
+  c->launches += 2;
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  dev_free(c, table);
+  *out = s;
+  return JA_OK;
+}
+
+int32_t ja_srs_to_host(ja_ctx* c, const ja_srs* s, size_t first, size_t count, uint64_t* out_xy) {
+  JA_REQUIRE(c && s && out_xy, "ja_srs_to_host: null argument");
+  JA_REQUIRE(first + count <= s->n, "ja_srs_to_host: range outside the SRS");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  JA_CUDA(cudaMemcpyAsync(out_xy, s->points + first, count * sizeof(G1Aff), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
   return JA_OK;
 }
 

@@ -92,47 +92,77 @@ JA_DEV bool msm_load_scalar(const MsmDesc& d, uint32_t j, uint32_t (&s)[10]) {
   return neg;
 }
 
-// Visit the non-zero signed digits of scalar j: f(key, payload) with key = global bucket id.
-template <class F>
-JA_DEV void msm_for_each_digit(const MsmDesc& d, uint32_t j, F&& f) {
-  if (d.kind == MSM_INDEXED) {
-    unsigned long long idx = reinterpret_cast<const unsigned long long*>(d.scalars)[j];
-    f(d.bucket_base, (uint32_t)idx);
+// Warp-aggregated atomics: lanes that hit the same bucket elect a leader which issues ONE atomicAdd for the
+// group (degenerate top windows, small scalars and one-hot sums put millions of entries on a few counters).
+JA_DEV uint32_t warp_agg_atomic_add(uint32_t* ctr, uint32_t key, bool active) {
+  // returns this lane's slot: base (leader's atomicAdd result) + rank among same-key lanes; undefined if !active
+  const uint32_t amask = __ballot_sync(0xffffffffu, active);
+  uint32_t res = 0;
+  if (active) {
+    const uint32_t peers = __match_any_sync(amask, key);
+    const int leader = __ffs(peers) - 1;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(ctr + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    res = base + __popc(peers & ((1u << lane) - 1));
+  }
+  return res;
+}
+
+// Signed digit w of scalar j (0 = none): key = global bucket id, payload = base index | sign.
+struct MsmDigitIter {
+  uint32_t s[10]; bool neg; uint32_t carry; uint32_t base;
+};
+JA_DEV bool msm_digit(const MsmDesc& d, MsmDigitIter& it, uint32_t w, uint32_t& key, uint32_t& payload) {
+  const uint32_t c = d.c, nb = d.nb, full = 1u << c;
+  const uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
+  unsigned long long two = ((unsigned long long)it.s[word + 1] << 32) | it.s[word];
+  uint32_t raw = (uint32_t)((two >> sh) & (full - 1)) + it.carry;
+  bool dneg = false;
+  if (raw > nb) { raw = full - raw; it.carry = 1; dneg = true; } else it.carry = 0;
+  if (!raw) return false;
+  key = d.bucket_base + w * nb + (raw - 1);
+  payload = it.base | ((dneg != it.neg) ? kSignBit : 0u);
+  return true;
+}
+
+// SCATTER == false: histogram; SCATTER == true: counting-sort scatter through `ctr` (a copy of the offsets).
+// Whole warps stay converged (threads past the end are inactive lanes) so the aggregated atomics are legal.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+k_msm_digits(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n, uint32_t max_nwin,
+             uint32_t* __restrict__ ctr, uint32_t* __restrict__ entries) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = g < total_n;
+  MsmDesc d; d.kind = MSM_INDEXED; d.nwin = 0; d.entry_base = 0; d.bucket_base = 0;
+  if (live) d = descs[msm_find(descs, count, g)];
+  const uint32_t j = g - d.entry_base;
+  if (__all_sync(0xffffffffu, !live || d.kind == MSM_INDEXED)) {
+    uint32_t payload = 0;
+    if (live) payload = (uint32_t)reinterpret_cast<const unsigned long long*>(d.scalars)[j];
+    const uint32_t slot = warp_agg_atomic_add(ctr, d.bucket_base, live);
+    if (SCATTER && live) entries[slot] = payload;
     return;
   }
-  uint32_t s[10];
-  const bool neg = msm_load_scalar(d, j, s);
-  const uint32_t c = d.c, nb = d.nb, full = 1u << c;
-  const uint32_t base = d.base_offset + j;
-  uint32_t carry = 0;
-  for (uint32_t w = 0; w < d.nwin; w++) {
-    const uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
-    unsigned long long two = ((unsigned long long)s[word + 1] << 32) | s[word];
-    uint32_t raw = (uint32_t)((two >> sh) & (full - 1)) + carry;
-    bool dneg = false;
-    if (raw > nb) { raw = full - raw; carry = 1; dneg = true; } else carry = 0;
-    if (raw) f(d.bucket_base + w * nb + (raw - 1), base | ((dneg != neg) ? kSignBit : 0u));
+  MsmDigitIter it;
+  it.neg = false; it.carry = 0; it.base = d.base_offset + j;
+  if (live && d.kind != MSM_INDEXED) it.neg = msm_load_scalar(d, j, it.s);
+  else {
+#pragma unroll
+    for (int i = 0; i < 10; i++) it.s[i] = 0;
   }
-}
-
-__global__ void __launch_bounds__(256)
-k_msm_hist(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n, uint32_t* __restrict__ hist) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total_n) return;
-  const uint32_t m = msm_find(descs, count, g);
-  const MsmDesc d = descs[m];
-  msm_for_each_digit(d, g - d.entry_base, [&](uint32_t key, uint32_t) { atomicAdd(hist + key, 1u); });
-}
-
-__global__ void __launch_bounds__(256)
-k_msm_scatter(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n, uint32_t* __restrict__ cursor,
-              uint32_t* __restrict__ entries) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total_n) return;
-  const uint32_t m = msm_find(descs, count, g);
-  const MsmDesc d = descs[m];
-  msm_for_each_digit(d, g - d.entry_base, [&](uint32_t key, uint32_t payload) {
-    entries[atomicAdd(cursor + key, 1u)] = payload; });
+  if (live && d.kind == MSM_INDEXED) {      // mixed warp (batch boundary): plain atomics for the indexed lanes
+    const uint32_t slot = atomicAdd(ctr + d.bucket_base, 1u);
+    if (SCATTER) entries[slot] = (uint32_t)reinterpret_cast<const unsigned long long*>(d.scalars)[j];
+  }
+  const bool digits = live && d.kind != MSM_INDEXED;
+  for (uint32_t w = 0; w < max_nwin; w++) {
+    uint32_t key = 0, payload = 0;
+    const bool has = digits && w < d.nwin && msm_digit(d, it, w, key, payload);
+    const uint32_t slot = warp_agg_atomic_add(ctr, key, has);
+    if (SCATTER && has) entries[slot] = payload;
+  }
 }
 
 // ---- exclusive scan of a u32 array (histogram -> offsets), 3 launches ------------------------------
@@ -160,7 +190,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 }
 
 // in-place: data[i] <- exclusive prefix within its tile; tile_sums[tile] = tile total
-__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(uint32_t* data, size_t n, uint32_t* tile_sums) {
+static __global__ void __launch_bounds__(kScanBlock) k_scan_tiles(uint32_t* data, size_t n, uint32_t* tile_sums) {
   __shared__ uint32_t s_warp[33];
   const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems], sum = 0;
@@ -173,7 +203,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_tiles(uint32_t* data, size_
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 // single block: exclusive scan of tile_sums in place
-__global__ void __launch_bounds__(kScanBlock) k_scan_top(uint32_t* tile_sums, size_t ntiles) {
+static __global__ void __launch_bounds__(kScanBlock) k_scan_top(uint32_t* tile_sums, size_t ntiles) {
   __shared__ uint32_t s_warp[33];
   uint32_t running = 0;
   for (size_t base = 0; base < ntiles; base += kScanBlock) {
@@ -184,7 +214,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_top(uint32_t* tile_sums, si
     running += total;
   }
 }
-__global__ void __launch_bounds__(kScanBlock) k_scan_add(uint32_t* data, size_t n, const uint32_t* tile_sums) {
+static __global__ void __launch_bounds__(kScanBlock) k_scan_add(uint32_t* data, size_t n, const uint32_t* tile_sums) {
   const uint32_t add = tile_sums[blockIdx.x];
   const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
 #pragma unroll
@@ -193,7 +223,9 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_add(uint32_t* data, size_t 
 
 // ---- pass A: fixed-size runs of the sorted entry list ------------------------------------------------
 // offsets has nbt + 1 entries (offsets[nbt] = number of entries E).  Thread t owns entries [t*T, (t+1)*T).
-__global__ void __launch_bounds__(128)
+// MINB = resident blocks per SM the register allocation is capped for (4: 128 regs, 5: 96, 6: 80 + small spills)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_msm_accumulate(const uint32_t* __restrict__ offsets, uint32_t nbt, const uint32_t* __restrict__ entries,
                  const G1Aff* __restrict__ bases, uint32_t T, G1X* __restrict__ bucket_sums,
                  G1X* __restrict__ head, G1X* __restrict__ tail) {
@@ -211,28 +243,29 @@ k_msm_accumulate(const uint32_t* __restrict__ offsets, uint32_t nbt, const uint3
   }
   uint32_t b = lo;
   uint32_t next_off = __ldg(offsets + b + 1);
-  uint32_t pos = start;
-  uint32_t e = __ldg(entries + pos);
+  uint32_t seg_first = start;
+  bool begins_here = __ldg(offsets + b) == start;
+  uint32_t e = __ldg(entries + start);
   G1Aff pt = g1aff_load(bases + (e & ~kSignBit));
-  while (pos < end) {
-    const uint32_t seg_end = next_off < end ? next_off : end;
-    G1X acc;
-    for (uint32_t p = pos; p < seg_end; p++) {
-      const G1Aff cur = pt;
-      const bool neg = (e & kSignBit) != 0;
-      if (p + 1 < end) { e = __ldg(entries + p + 1); pt = g1aff_load(bases + (e & ~kSignBit)); }
-      if (p == pos) { acc = g1x_from_aff(cur); if (neg) acc.Y = fq_neg(acc.Y); }
-      else g1x_madd(acc, cur, neg);
+  G1X acc = g1x_inf();
+  // ONE flat loop: every iteration is a uniform mixed addition for all 32 lanes; bucket boundaries only add a
+  // short divergent flush (the accumulator restarts from infinity, which g1x_madd treats as a copy).
+  for (uint32_t p = start; p < end; p++) {
+    if (p == next_off) {
+      G1X* dst = begins_here ? bucket_sums + b : (seg_first == start ? head + t : tail + t);
+      g1x_store(dst, acc);
+      acc = g1x_inf();
+      seg_first = p; begins_here = true;
+      do { b++; next_off = __ldg(offsets + b + 1); } while (next_off <= p);
     }
-    const bool complete = __ldg(offsets + b) >= start && next_off <= end;
-    if (complete) g1x_store(bucket_sums + b, acc);
-    else if (pos == start) g1x_store(head + t, acc);
-    else g1x_store(tail + t, acc);
-    pos = seg_end;
-    if (pos < end) {
-      do { b++; next_off = __ldg(offsets + b + 1); } while (next_off <= pos);
-    }
+    const G1Aff cur = pt;
+    const bool neg = (e & kSignBit) != 0;
+    if (p + 1 < end) { e = __ldg(entries + p + 1); pt = g1aff_load(bases + (e & ~kSignBit)); }
+    g1x_madd(acc, cur, neg);
   }
+  const bool complete = begins_here && next_off <= end;
+  G1X* dst = complete ? bucket_sums + b : (seg_first == start ? head + t : tail + t);
+  g1x_store(dst, acc);
 }
 
 // ---- pass B: per bucket, add the partials of the runs it spans -------------------------------------
@@ -240,7 +273,7 @@ constexpr uint32_t kBigSpan = 48;
 JA_DEV G1X msm_piece(const G1X* head, const G1X* tail, uint32_t c, uint32_t c0, bool starts_on_run) {
   return (c == c0 && !starts_on_run) ? g1x_load(tail + c) : g1x_load(head + c);
 }
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_msm_combine(const uint32_t* __restrict__ offsets, uint32_t nbt, uint32_t T, const G1X* __restrict__ head,
               const G1X* __restrict__ tail, G1X* __restrict__ bucket_sums, uint32_t* __restrict__ big_list,
               uint32_t* __restrict__ big_count) {
@@ -257,7 +290,7 @@ k_msm_combine(const uint32_t* __restrict__ offsets, uint32_t nbt, uint32_t T, co
   g1x_store(bucket_sums + b, acc);
 }
 // wide buckets (skewed digits, one-hot sums): one block per bucket, strided partial sums + shared-memory tree
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_msm_combine_big(const uint32_t* __restrict__ offsets, uint32_t T, const G1X* __restrict__ head,
                   const G1X* __restrict__ tail, G1X* __restrict__ bucket_sums, const uint32_t* __restrict__ big_list,
                   const uint32_t* __restrict__ big_count) {
@@ -285,7 +318,7 @@ k_msm_combine_big(const uint32_t* __restrict__ offsets, uint32_t T, const G1X* _
 struct MsmWindow { uint32_t bucket_base, nb, c, msm; };
 constexpr uint32_t kSegBuckets = 32;
 // grid (ceil(max_segs/128), n_windows); seg_part[w * max_segs + seg]
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_msm_bucket_reduce(const MsmWindow* __restrict__ wins, const G1X* __restrict__ bucket_sums, uint32_t max_segs,
                     G1X* __restrict__ seg_part) {
   const MsmWindow w = wins[blockIdx.y];
@@ -303,7 +336,7 @@ k_msm_bucket_reduce(const MsmWindow* __restrict__ wins, const G1X* __restrict__ 
   g1x_store(seg_part + (size_t)blockIdx.y * max_segs + seg, tot);
 }
 // one block per window: tree sum of its segment partials
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_msm_window_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ seg_part, uint32_t max_segs,
                  G1X* __restrict__ window_sums) {
   __shared__ G1X s_acc[128];
@@ -322,7 +355,7 @@ k_msm_window_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ seg
 
 // ---- final: Horner over windows + affine conversion; one thread per MSM -------------------------------
 struct MsmResult { Fq x, y; uint32_t inf; uint32_t pad[3]; };   // 80 B
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
 k_msm_final(const MsmDesc* __restrict__ descs, uint32_t count, const G1X* __restrict__ window_sums,
             MsmResult* __restrict__ out) {
   const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,6 +371,56 @@ k_msm_final(const MsmDesc* __restrict__ descs, uint32_t count, const G1X* __rest
   else { G1Aff a = g1x_to_aff(acc); r.x = a.x; r.y = a.y; r.inf = 0; }
   r.pad[0] = r.pad[1] = r.pad[2] = 0;
   out[m] = r;
+}
+
+}  // namespace ja
+
+// ---- SRS generation: g1_powers[i] = beta^i * g1  (SRS::setup, hyperkzg/kzg.rs:26-93; FixedBase::msm) ----------
+// Fixed-base: table[k] = 2^k * g1 (affine, built once by k_srs_table), then every point is a sum of <= 254 table
+// entries (mixed additions only, no doublings) followed by one inversion.
+namespace ja {
+
+static __global__ void k_srs_table(G1Aff g1, G1Aff* __restrict__ table /*254*/) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  G1X cur = g1x_from_aff(g1);
+  for (int k = 0; k < 254; k++) {
+    table[k] = g1x_to_aff(cur);
+    cur = g1x_dbl(cur);
+  }
+}
+
+JA_DEV Fr fr_pow_u32(const Fr& b, uint32_t e) {
+  Fr r = fp_one<FrParams>();
+  if (e == 0) return r;
+  for (int bit = 31 - __clz(e); bit >= 0; bit--) {
+    r = fp_sqr<FrParams>(r);
+    if ((e >> bit) & 1) r = fp_mul<FrParams>(r, b);
+  }
+  return r;
+}
+
+static __global__ void __launch_bounds__(128)
+k_srs_powers(const G1Aff* __restrict__ table, Fr beta, uint32_t n, G1Aff* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = fr_pow_u32(beta, i);
+  const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  Fr canon;
+  fp_mont_rows<FrParams, 8>(canon.l, s.l, one);
+  fp_final_sub<FrParams>(canon.l);
+  G1X acc = g1x_inf();
+#pragma unroll 1
+  for (int w = 0; w < 8; w++) {
+    uint32_t bits = canon.l[w];
+    while (bits) {
+      const int k = __ffs(bits) - 1;
+      bits &= bits - 1;
+      g1x_madd(acc, g1aff_load(table + 32 * w + k), false);
+    }
+  }
+  // beta^i != 0 => acc is never the identity for a generator of the prime-order group
+  G1Aff a = g1x_to_aff(acc);
+  fp_store(&out[i].x, a.x); fp_store(&out[i].y, a.y);
 }
 
 }  // namespace ja

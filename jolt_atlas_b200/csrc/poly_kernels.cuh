@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kBlock) k_bind_i32(const int* __restrict__ in,
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_i32_to_fr(const int* __restrict__ in, Fr* __restrict__ out, size_t n) {
+static __global__ void __launch_bounds__(kBlock) k_i32_to_fr(const int* __restrict__ in, Fr* __restrict__ out, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     fp_store(out + i, fr_from_i32(__ldg(in + i)));
@@ -170,7 +170,7 @@ struct EqLevelsArgs {
   Fr* buf[2];
   Fr scale[2];
 };
-__global__ void __launch_bounds__(1024) k_eq_levels(EqLevelsArgs a) {
+static __global__ void __launch_bounds__(1024) k_eq_levels(EqLevelsArgs a) {
   const int t = blockIdx.x;
   const Fr* w = a.w[t];
   const int m = a.m[t], rev = a.rev[t];
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(1024) k_eq_levels(EqLevelsArgs a) {
 }
 
 // out[x] = hi[x >> bits_lo] * lo[x & mask]   — EqPolynomial::evals (eq_poly.rs:77-101) as an outer product
-__global__ void __launch_bounds__(kBlock) k_eq_expand(const Fr* __restrict__ hi, const Fr* __restrict__ lo,
+static __global__ void __launch_bounds__(kBlock) k_eq_expand(const Fr* __restrict__ hi, const Fr* __restrict__ lo,
                                                      int bits_lo, size_t n, Fr* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t mask = (size_t(1) << bits_lo) - 1;
@@ -312,7 +312,7 @@ k_round_eval_dot(EvalPolys P, size_t half, Fr* partials, unsigned int* counter, 
 }
 
 // plain sum_i a[i]*b[i] over n entries (MLE evaluation against a dense eq table)
-__global__ void __launch_bounds__(kBlock) k_dot_full(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t n,
+static __global__ void __launch_bounds__(kBlock) k_dot_full(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t n,
                                                     Fr* partials, unsigned int* counter, Fr* out) {
   Fr acc[1];
   acc[0] = fp_zero<FrParams>();
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kBlock) k_dot_full(const Fr* __restrict__ a, c
 // ---- i32 tensor folds (einsum operand fold, ops/einsum/mk_kn_mn.rs:47-79) ------------------------
 // transpose == 0: out[j] = sum_i from_i32(A[i*cols+j]) * eq[i]; thread per column, rows split over grid.y,
 //                 partial[y][j] summed by k_fold_cols_finish.
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_fold_cols(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __restrict__ eq,
             size_t rows_per_slice, Fr* __restrict__ partial) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,7 +339,7 @@ k_fold_cols(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __res
   }
   fp_store(partial + (size_t)blockIdx.y * cols + j, acc);
 }
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_fold_cols_finish(const Fr* __restrict__ partial, size_t slices, size_t cols, Fr* __restrict__ out) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
@@ -348,7 +348,7 @@ k_fold_cols_finish(const Fr* __restrict__ partial, size_t slices, size_t cols, F
   fp_store(out + j, acc);
 }
 // transpose == 1: out[i] = sum_j from_i32(A[i*cols+j]) * eq[j]; one warp per row.
-__global__ void __launch_bounds__(kBlock)
+static __global__ void __launch_bounds__(kBlock)
 k_fold_rows(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __restrict__ eq, Fr* __restrict__ out) {
   const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -363,16 +363,19 @@ k_fold_rows(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __res
 }
 
 // ---- calibration: register-resident Montgomery products (roofline denominator for integer-bound kernels)
-__global__ void __launch_bounds__(kBlock) k_calib_fr_mul(Fr* out, int iters) {
-  Fr a = fp_one<FrParams>(), b = fp_r2<FrParams>(), c = fp_one<FrParams>(), d = fp_r2<FrParams>();
-  a.l[0] += threadIdx.x; c.l[1] += blockIdx.x;
-  for (int i = 0; i < iters; i++) {   // 4 independent products per iteration
-    a = fp_mul<FrParams>(a, b);
-    c = fp_mul<FrParams>(c, d);
-    b = fp_mul<FrParams>(b, a);
-    d = fp_mul<FrParams>(d, c);
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_calib_mul(Fp<M>* out, int iters) {
+  // four independent product chains, every operand thread-variant (no uniform-datapath shortcut)
+  Fp<M> a = fp_one<M>(), b = fp_r2<M>(), c = fp_one<M>(), d = fp_r2<M>();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  a.l[0] += t; b.l[1] ^= t * 2654435761u; c.l[2] += t * 40503u; d.l[3] ^= t;
+  for (int i = 0; i < iters; i++) {
+    a = fp_mul<M>(a, b);
+    c = fp_mul<M>(c, d);
+    b = fp_mul<M>(b, a);
+    d = fp_mul<M>(d, c);
   }
-  Fr s = fp_add<FrParams>(fp_add<FrParams>(a, b), fp_add<FrParams>(c, d));
+  Fp<M> s = fp_add<M>(fp_add<M>(a, b), fp_add<M>(c, d));
   if (s.l[7] == 0xdeadbeefu) fp_store(out + threadIdx.x, s);   // never true for canonical values; keeps the loop alive
 }
 

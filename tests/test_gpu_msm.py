@@ -213,3 +213,15 @@ def test_msm_linearity_large(ctx):
     x, y = F.fq_from_mont(xy1[:4]), F.fq_from_mont(xy1[4:])
     assert (y * y - x * x * x - 3) % F.Q == 0
     s.free(); s2.free()
+
+
+def test_srs_generate_matches_oracle(ctx):
+    """SRS::setup's fixed-base loop (kzg.rs:45-66): g1_powers[i] = beta^i * g1, against the oracle's scalar_mul."""
+    from jolt_atlas_b200 import SRS
+    n = 300
+    want = ORC.srs_powers(to_mont_array([TAU])[0], n)
+    g1 = np.concatenate([np.array(F.fq_to_mont(1), dtype=np.uint64), np.array(F.fq_to_mont(2), dtype=np.uint64)])
+    s = SRS.generate(ctx, g1, to_mont_array([TAU])[0], n)
+    assert len(s) == n
+    assert np.array_equal(s.to_host(), want)
+    s.free()
