@@ -128,6 +128,19 @@ int32_t ja_round_eval(ja_ctx*, int32_t kernel_id, const ja_poly* const* polys, s
                       const ja_spliteq* eq_or_null, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32,
                       uint64_t* out_evals, size_t n_out);
 
+/* Sumcheck::prove for ONE instance (joltworks/src/subprotocols/sumcheck.rs:565-599) with the library's Blake2b
+ * transcript between the kernels: append_scalar(claim); per round compute_message (ja_round_eval + interpolation),
+ * append the compressed round polynomial (unipoly.rs:550-558), r_j = challenge_scalar_optimized, claim = uni(r_j),
+ * ingest_challenge (ja_bind_many + split-eq bind).  kind = JA_EVAL_*; family S/PROD/POW take eq_w = one Fr per round
+ * (w of GruenSplitEqPolynomial::new, LowToHigh), the others NULL.  The polynomials are consumed (bound to length 1).
+ * Outputs: out_coeffs[round][max_coeffs][4] (compressed: every coefficient but the linear one), out_ncoeffs[round],
+ * out_challenges[round][4] ({0,0,lo,hi}), out_final_claims[n_polys][4]; transcript_state / n_rounds are read and
+ * written back (Blake2bTranscript state + round counter, blake2b.rs:11-26). */
+int32_t ja_sumcheck_prove(ja_ctx*, int32_t kind, ja_poly* const* polys, size_t n_polys, const uint64_t* eq_w, size_t eq_m,
+                          const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32, const uint64_t claim[4],
+                          uint8_t transcript_state[32], uint32_t* n_rounds, size_t max_coeffs, uint64_t* out_coeffs,
+                          uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_final_claims);
+
 /* Einsum operand fold / i32 tensor x eq-vector (ops/einsum/mk_kn_mn.rs:47-79):
  *   transpose==0: out[j] = sum_i from_i32(A[i*cols + j]) * eq[i]   (eq has `rows` entries, out has `cols`)
  *   transpose==1: out[i] = sum_j from_i32(A[i*cols + j]) * eq[j]   (eq has `cols` entries, out has `rows`) */

@@ -41,6 +41,8 @@ SIGNATURES = {
     "ja_spliteq_merge": (C.c_int32, [vp, vp, vpp]),
     "ja_spliteq_free": (None, [vp, vp]),
     "ja_round_eval": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, u64p, C.c_size_t, C.c_uint32, u64p, C.c_size_t]),
+    "ja_sumcheck_prove": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint32, u64p,
+                                      C.c_char_p, u32p, C.c_size_t, u64p, u32p, u64p, u64p]),
     "ja_tensor_fold_i32": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vp, C.c_int32, vpp]),
     "ja_srs_upload": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
     "ja_srs_generate": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),

@@ -31,6 +31,7 @@ class EvalKernel:
     ADD, SUB, MUL, SQUARE, PROD, POW, IDENT = 0, 1, 2, 3, 4, 5, 6
     DOT2, DOT3, SUM1, SUMHI = 16, 17, 18, 19
     N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 16: 2, 17: 3, 18: 1, 19: 1}
+    FAMILY_S = (0, 1, 2, 3, 4, 5, 6)
 
 
 def _u64p(a: np.ndarray):
@@ -382,3 +383,28 @@ class HyperKZGOpening:
         if self._h:
             self.ctx._lib.ja_hyperkzg_open_free(self.ctx._h, self._h)
             self._h = None
+
+
+# ---- Sumcheck::prove (subprotocols/sumcheck.rs:565-599) ----
+def sumcheck_prove(ctx: Context, kind: int, polys, claim, transcript: Blake2bTranscriptState, eq_w=None, gammas=None,
+                   pow_d: int = 0, max_coeffs: int = 40):
+    """One instance through the device kernels + the library transcript.  Consumes `polys`.
+    Returns dict(coeffs=[per-round compressed coefficient arrays], challenges, final_claims)."""
+    n = len(polys[0])
+    rounds = n.bit_length() - 1
+    arr = (C.c_void_p * len(polys))(*[p._h for p in polys])
+    w = _fr_arg(eq_w).reshape(-1, 4) if eq_w is not None else None
+    g = _fr_arg(gammas).reshape(-1, 4) if gammas is not None else None
+    coeffs = np.zeros((rounds, max_coeffs, 4), dtype=np.uint64)
+    ncoeffs = np.zeros(rounds, dtype=np.uint32)
+    chal = np.zeros((rounds, 4), dtype=np.uint64)
+    fin = np.zeros((len(polys), 4), dtype=np.uint64)
+    st = C.create_string_buffer(transcript.state, 32)
+    nr = C.c_uint32(transcript.n_rounds)
+    check(ctx._lib.ja_sumcheck_prove(ctx._h, kind, arr, len(polys), _u64p(w) if w is not None else None,
+                                     w.shape[0] if w is not None else 0, _u64p(g) if g is not None else None,
+                                     g.shape[0] if g is not None else 0, pow_d, _u64p(_fr_arg(claim)), st, C.byref(nr),
+                                     max_coeffs, _u64p(coeffs), ncoeffs.ctypes.data_as(_lib.u32p), _u64p(chal), _u64p(fin)))
+    transcript.state = st.raw
+    transcript.n_rounds = nr.value
+    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(rounds)], "challenges": chal, "final_claims": fin}

@@ -30,8 +30,8 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   uint64_t thresh = UINT64_MAX;
   JA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   JA_CUDA(cudaMalloc(&c->d_partials, sizeof(Fr) * kMaxGrid * kMaxOut));
-  JA_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
-  JA_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
+  JA_CUDA(cudaMalloc(&c->d_counter, 64 * sizeof(unsigned int)));
+  JA_CUDA(cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int)));
   JA_CUDA(cudaMalloc(&c->d_out, sizeof(Fr) * kMaxOut));
   JA_CUDA(cudaMallocHost(&c->h_pinned, kPinnedBytes));
   JA_CUDA(cudaEventCreate(&c->ev0));
@@ -374,38 +374,44 @@ extern "C" {
 int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
                       const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32,
                       uint64_t* out_evals, size_t n_out) {
-  (void)aux_fr; (void)n_aux; (void)aux_u32;
   JA_REQUIRE(c && polys && out_evals, "ja_round_eval: null argument");
-  JA_REQUIRE(n_polys >= 1 && n_polys <= 4, "ja_round_eval: unsupported number of polynomials");
+  JA_REQUIRE(n_polys >= 1 && n_polys <= (size_t)kMaxProdPolys, "ja_round_eval: unsupported number of polynomials");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   const size_t len = polys[0]->len;
   JA_REQUIRE(len >= 2, "ja_round_eval: polynomial already fully bound");
-  EvalPolys P;
-  for (size_t i = 0; i < 4; i++) P.p[i] = nullptr;
-  for (size_t i = 0; i < n_polys; i++) {
+  for (size_t i = 0; i < n_polys; i++)
     JA_REQUIRE(polys[i] && polys[i]->len == len, "ja_round_eval: polynomial length mismatch");
-    P.p[i] = polys[i]->data();
-  }
+  EvalPolys P;
+  for (size_t i = 0; i < 4; i++) P.p[i] = i < n_polys ? polys[i]->data() : nullptr;
   const size_t G = len / 2;
   size_t want_out = 0, want_polys = 0;
-  bool family_s = true;
+  enum { FAM_S, FAM_D, FAM_PROD, FAM_SUM } fam = FAM_S;
   switch (kernel_id) {
     case JA_EVAL_ADD: case JA_EVAL_SUB: want_out = 1; want_polys = 2; break;
     case JA_EVAL_MUL: want_out = 2; want_polys = 2; break;
     case JA_EVAL_SQUARE: want_out = 2; want_polys = 1; break;
     case JA_EVAL_IDENT: want_out = 1; want_polys = 1; break;
-    case JA_EVAL_DOT2: want_out = 2; want_polys = 2; family_s = false; break;
-    case JA_EVAL_DOT3: want_out = 3; want_polys = 3; family_s = false; break;
+    case JA_EVAL_PROD: want_out = n_polys; want_polys = n_polys; fam = FAM_PROD; break;
+    case JA_EVAL_POW: want_out = aux_u32; want_polys = 1; fam = FAM_PROD; break;
+    case JA_EVAL_DOT2: want_out = 2; want_polys = 2; fam = FAM_D; break;
+    case JA_EVAL_DOT3: want_out = 3; want_polys = 3; fam = FAM_D; break;
+    case JA_EVAL_SUM1: want_out = 1; want_polys = n_polys; fam = FAM_SUM; break;
+    case JA_EVAL_SUMHI: want_out = 1; want_polys = 1; fam = FAM_SUM; break;
     default: return fail(JA_ERR_UNSUPPORTED, "ja_round_eval: kernel_id not implemented");
   }
   JA_REQUIRE(n_out == want_out, "ja_round_eval: wrong n_out for kernel_id");
   JA_REQUIRE(n_polys == want_polys, "ja_round_eval: wrong n_polys for kernel_id");
-  if (family_s) {
+  size_t n_dev = n_out;      // Fr values to copy back from d_out
+  if (fam == FAM_S || fam == FAM_PROD) {
     JA_REQUIRE(eq != nullptr, "ja_round_eval: split-eq handle required for family S");
     JA_REQUIRE(eq->order == JA_LOW_TO_HIGH, "ja_round_eval: family S expects a LowToHigh split-eq");
     const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
     JA_REQUIRE(cover == G, "ja_round_eval: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+  } else {
+    JA_REQUIRE(eq == nullptr, "ja_round_eval: this kernel_id takes no split-eq handle");
+  }
+  if (fam == FAM_S) {
     switch (kernel_id) {
       case JA_EVAL_ADD: launch_s<0>(c, P, eq, G); break;
       case JA_EVAL_SUB: launch_s<1>(c, P, eq, G); break;
@@ -413,8 +419,24 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
       case JA_EVAL_SQUARE: launch_s<3>(c, P, eq, G); break;
       case JA_EVAL_IDENT: launch_s<6>(c, P, eq, G); break;
     }
-  } else {
-    JA_REQUIRE(eq == nullptr, "ja_round_eval: family D takes no split-eq handle");
+  } else if (fam == FAM_PROD) {
+    const int d = kernel_id == JA_EVAL_POW ? (int)aux_u32 : (int)n_polys;
+    JA_REQUIRE(d >= 2 && d <= kMaxProdPolys, "ja_round_eval: product degree must be in 2..32");
+    ProdPolys PP;
+    for (int i = 0; i < kMaxProdPolys; i++) PP.p[i] = i < (int)n_polys ? polys[i]->data() : nullptr;
+    const unsigned chunks = (unsigned)((d + kProdChunk - 1) / kProdChunk);
+    const int bits_in = eq->in_len - 1;
+    size_t tiles = (G + kBlock - 1) / kBlock;
+    size_t gx = tiles < (size_t)kSMs * 2 ? tiles : (size_t)kSMs * 2;
+    size_t tpb = (tiles + gx - 1) / gx;
+    gx = (tiles + tpb - 1) / tpb;
+    dim3 grid((unsigned)gx, chunks);
+    if (kernel_id == JA_EVAL_POW)
+      k_round_eval_prod<true><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter);
+    else
+      k_round_eval_prod<false><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter);
+    c->launches++;
+  } else if (fam == FAM_D) {
     unsigned grid = grid_for(G);
     if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
     if (kernel_id == JA_EVAL_DOT2)
@@ -422,11 +444,31 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
     else
       k_round_eval_dot<3><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out);
     c->launches++;
+  } else {
+    SumPolys SP;
+    for (int i = 0; i < kMaxProdPolys; i++) SP.p[i] = i < (int)n_polys ? polys[i]->data() : nullptr;
+    unsigned gx = grid_for(G);
+    if (gx > (unsigned)kSMs * 2) gx = kSMs * 2;
+    dim3 grid(gx, (unsigned)n_polys);
+    if (kernel_id == JA_EVAL_SUM1) k_round_sum<2><<<grid, kBlock, 0, c->stream>>>(SP, G, c->d_partials, c->d_out, c->d_counter);
+    else                           k_round_sum<1><<<grid, kBlock, 0, c->stream>>>(SP, G, c->d_partials, c->d_out, c->d_counter);
+    c->launches++;
+    n_dev = n_polys;
+    JA_REQUIRE(aux_fr == nullptr || n_aux == n_polys, "ja_round_eval: SUM1 takes one gamma per polynomial");
   }
   JA_CUDA(cudaGetLastError());
-  JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, n_dev * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   JA_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(out_evals, c->h_pinned, n_out * sizeof(Fr));
+  if (fam == FAM_SUM) {
+    // hamming_weight.rs:126-133: sum_i gamma_i * (sum_j ra_i[2j]); O(d) scalar glue on the d returned sums
+    const FrH* sums = reinterpret_cast<const FrH*>(c->h_pinned);
+    FrH acc = host::FR_ZERO;
+    for (size_t i = 0; i < n_polys; i++)
+      acc = host::add(acc, aux_fr ? host::mul(host::from_limbs(aux_fr + 4 * i), sums[i]) : sums[i]);
+    memcpy(out_evals, acc.l, 32);
+  } else {
+    memcpy(out_evals, c->h_pinned, n_out * sizeof(Fr));
+  }
   return JA_OK;
 }
 

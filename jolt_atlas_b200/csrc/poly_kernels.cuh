@@ -282,6 +282,88 @@ k_round_eval_s(EvalPolys P, const Fr* __restrict__ e_out, const Fr* __restrict__
   grid_sum<NOUT>(outer, partials, counter, out);
 }
 
+// ---- family S, product of d linear factors (RA virtualisation; Cube as a same-MLE power) -----------------------
+// compute_mles_product_sum (mles_product_sum.rs:15-129): per pair g evaluate prod_i (p_i0 + X*dp_i) on the grid
+// X in {1, ..., d-1, inf}, weight by the split eq tables, sum -> d field elements (current_scalar and the Toom
+// interpolation stay with the caller, :330-376).  blockIdx.y selects a chunk of KC consecutive grid points so the
+// per-thread state is KC products + 2*KC accumulators regardless of d; the factors are re-read per chunk (L2 hits).
+// SAME == true: all d factors are polys[0] (compute_mle_product_sum, :41-55,:135-205, Cube x^3).
+constexpr int kMaxProdPolys = 32;
+struct ProdPolys { const Fr* p[kMaxProdPolys]; };
+constexpr int kProdChunk = 4;
+
+template <bool SAME>
+__global__ void __launch_bounds__(kBlock)
+k_round_eval_prod(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+                  size_t tiles_per_block, Fr* partials /* [gridDim.y][gridDim.x][KC] */, Fr* block_out /* [gridDim.y][KC] */,
+                  unsigned int* counters /* gridDim.y */) {
+  constexpr int KC = kProdChunk;
+  const int k0 = blockIdx.y * KC;                 // grid point index of this chunk's first output
+  Fr outer[KC], inner[KC];
+#pragma unroll
+  for (int k = 0; k < KC; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)blockIdx.x * tiles_per_block * kBlock;
+  size_t g_end = g_begin + tiles_per_block * kBlock;
+  if (g_end > G) g_end = G;
+  size_t cur_xout = ~size_t(0);
+  // Montgomery form of the small integer k0 + 1 (first grid point X of the chunk)
+  const Fr x0 = fr_from_i32(k0 + 1);
+  for (size_t g = g_begin + threadIdx.x; g < g_end; g += kBlock) {
+    const size_t x_out = g >> bits_in;
+    if (x_out != cur_xout) {
+      if (cur_xout != ~size_t(0)) {
+        const Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+          inner[k] = fp_zero<FrParams>();
+        }
+      }
+      cur_xout = x_out;
+    }
+    Fr v[KC];
+    for (int i = 0; i < d; i++) {
+      const Fr* z = SAME ? P.p[0] : P.p[i];
+      const Fr p0 = fp_load(z + 2 * g);
+      const Fr dp = fp_sub<FrParams>(fp_load(z + 2 * g + 1), p0);
+      Fr cur = fp_add<FrParams>(p0, fp_mul<FrParams>(dp, x0));     // factor at X = k0 + 1
+#pragma unroll
+      for (int k = 0; k < KC; k++) {
+        const int idx = k0 + k;
+        const Fr val = idx == d - 1 ? dp : cur;                     // last grid point is X = inf (leading coefficient)
+        v[k] = i == 0 ? val : fp_mul<FrParams>(v[k], val);
+        cur = fp_add<FrParams>(cur, dp);
+      }
+    }
+    const Fr ei = fp_load(e_in + (g & mask_in));
+#pragma unroll
+    for (int k = 0; k < KC; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
+  }
+  if (cur_xout != ~size_t(0)) {
+    const Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+    for (int k = 0; k < KC; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+  }
+  grid_sum<KC>(outer, partials + (size_t)blockIdx.y * gridDim.x * KC, counters + blockIdx.y, block_out + (size_t)blockIdx.y * KC);
+}
+
+// ---- plain sums (no eq): Hamming weight (sum_j p_i[2j], LowToHigh; hamming_weight.rs:118-139) and Sum over an axis
+// (sum_{j<n/2} p[j], HighToLow; ops/sum/axis.rs:220-233).  blockIdx.y = polynomial; out[i] = the sum of poly i.
+// The gamma combination of the Hamming instance is O(d) host work on the returned sums.
+struct SumPolys { const Fr* p[kMaxProdPolys]; };
+template <int STRIDE>
+__global__ void __launch_bounds__(kBlock)
+k_round_sum(SumPolys P, size_t half, Fr* partials, Fr* out, unsigned int* counters) {
+  const Fr* __restrict__ z = P.p[blockIdx.y];
+  Fr acc[1];
+  acc[0] = fp_zero<FrParams>();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride)
+    acc[0] = fp_add<FrParams>(acc[0], fp_load(z + STRIDE * j));
+  grid_sum<1>(acc, partials + (size_t)blockIdx.y * gridDim.x, counters + blockIdx.y, out + blockIdx.y);
+}
+
 // ---- family D: plain products at X in {0,2,3}, HighToLow ----------------------------------------
 // sumcheck_evals (multilinear_polynomial.rs:873-905): e0 = a, e_k = b + (k-1)(b-a).
 template <int NPOLY>   // 2: einsum/dot.rs:292-303 ; 3: dot.rs:330-350 with eq as a third MLE of equal length

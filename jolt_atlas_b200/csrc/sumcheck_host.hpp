@@ -1,0 +1,149 @@
+// Host-side O(degree) glue of the sumcheck driver: round-polynomial assembly from the reduced sums the kernels
+// return, compression, evaluation.  Tiny per-round scalar math between kernel launches (not a fallback for any kernel).
+//   UniPoly::{from_evals, from_evals_and_hint, from_evals_toom, from_coeff, compress, evaluate}   unipoly.rs:39-153,219-245,307-318
+//   GruenSplitEqPolynomial::{gruen_poly_deg_2, gruen_poly_deg_3}                                  split_eq_poly.rs:379-471
+//   finish_mles_product_sum_from_evals                                                            mles_product_sum.rs:330-376
+// Interpolation results are unique polynomials, so the closed forms / Lagrange sums below give the same coefficients
+// as the reference's Gaussian elimination; only the TRIMMING rules change transcript bytes and are kept exactly:
+// from_evals of 3 or 4 values keeps its length, the general path and from_coeff drop trailing zeros.
+#pragma once
+#include <vector>
+#include "fr_host.hpp"
+
+namespace ja {
+namespace host {
+
+typedef std::vector<FrH> Coeffs;
+
+static inline Coeffs trim(Coeffs c) {           // UniPoly::from_coeff (unipoly.rs:39-52)
+  while (!c.empty() && c.back().is_zero()) c.pop_back();
+  if (c.empty()) c.push_back(FR_ZERO);
+  return c;
+}
+
+// coefficients of the unique polynomial of degree < m through (i, e[i]), i = 0..m-1 (no trimming)
+static inline Coeffs interpolate_0_to_m(const FrH* e, size_t m) {
+  // master(x) = prod_j (x - j), by straightforward convolution
+  Coeffs master;
+  master.assign(m + 1, FR_ZERO);
+  master[0] = FR_ONE;
+  for (size_t j = 0; j < m; j++) {
+    const FrH fj = from_u64(j);
+    Coeffs next(m + 1, FR_ZERO);
+    for (size_t k = 0; k <= j; k++) {
+      next[k + 1] = add(next[k + 1], master[k]);
+      next[k] = sub(next[k], mul(master[k], fj));
+    }
+    master = next;
+  }
+  // factorials
+  std::vector<FrH> fact(m, FR_ONE);
+  for (size_t i = 1; i < m; i++) fact[i] = mul(fact[i - 1], from_u64(i));
+  Coeffs out(m, FR_ZERO);
+  for (size_t i = 0; i < m; i++) {
+    if (e[i].is_zero()) continue;
+    // w_i = e[i] / (i! * (m-1-i)! * (-1)^(m-1-i))
+    FrH w = mul(e[i], inv(mul(fact[i], fact[m - 1 - i])));
+    if ((m - 1 - i) & 1) w = neg(w);
+    // L_i numerator = master / (x - i) by synthetic division
+    const FrH fi = from_u64(i);
+    FrH carry = FR_ZERO;
+    for (size_t k = m; k-- > 0;) {
+      carry = add(master[k + 1], mul(carry, fi));
+      out[k] = add(out[k], mul(w, carry));
+    }
+  }
+  return out;
+}
+
+static inline Coeffs from_evals(const std::vector<FrH>& e) {    // unipoly.rs:55-92,136-153
+  const size_t n = e.size();
+  if (n == 3) {
+    const FrH two_inv = inv(from_u64(2));
+    const FrH c2 = mul(add(sub(sub(e[0], e[1]), e[1]), e[2]), two_inv);
+    const FrH c1 = sub(sub(e[1], e[0]), c2);
+    return Coeffs{e[0], c1, c2};
+  }
+  if (n == 4) {
+    const FrH two_inv = inv(from_u64(2)), six_inv = inv(from_u64(6));
+    const FrH c3 = mul(add(sub(e[3], e[0]), mul(sub(e[1], e[2]), from_u64(3))), six_inv);
+    const FrH c2 = sub(sub(sub(mul(add(sub(sub(e[0], e[1]), e[1]), e[2]), two_inv), c3), c3), c3);
+    const FrH c1 = sub(sub(sub(e[1], e[0]), c2), c3);
+    return Coeffs{e[0], c1, c2, c3};
+  }
+  return trim(interpolate_0_to_m(e.data(), n));
+}
+static inline Coeffs from_evals_and_hint(const FrH& hint, const std::vector<FrH>& evals) {   // unipoly.rs:96-101
+  std::vector<FrH> e = evals;
+  e.insert(e.begin() + 1, sub(hint, e[0]));
+  return from_evals(e);
+}
+// values at 0..n-2 and the leading coefficient (value "at infinity") -> n coefficients, no trimming (unipoly.rs:104-134)
+static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
+  const size_t n = e.size();
+  const FrH lead = e[n - 1];
+  std::vector<FrH> low(n - 1);
+  for (size_t i = 0; i + 1 < n; i++) {
+    FrH pw = FR_ONE; const FrH x = from_u64(i);
+    for (size_t k = 0; k + 1 < n; k++) pw = mul(pw, x);      // i^(n-1)
+    low[i] = sub(e[i], mul(lead, pw));
+  }
+  Coeffs c = interpolate_0_to_m(low.data(), n - 1);
+  c.push_back(lead);
+  return c;
+}
+static inline FrH evaluate(const Coeffs& c, const FrH& r) {    // unipoly.rs:219-245
+  FrH acc = c[0], pw = r;
+  for (size_t i = 1; i < c.size(); i++) { acc = add(acc, mul(pw, c[i])); pw = mul(pw, r); }
+  return acc;
+}
+static inline Coeffs compress(const Coeffs& c) {                 // unipoly.rs:307-318: everything but the linear term
+  if (c.size() < 2) return c;
+  Coeffs o; o.push_back(c[0]);
+  o.insert(o.end(), c.begin() + 2, c.end());
+  return o;
+}
+
+// split_eq_poly.rs:432-471
+static inline Coeffs gruen_poly_deg_2(const FrH& current_scalar, const FrH& current_w, const FrH& q0, const FrH& prev) {
+  const FrH eq1 = mul(current_scalar, current_w);
+  const FrH eq0 = sub(current_scalar, eq1);
+  const FrH eqm = sub(eq1, eq0), eq2 = add(eq1, eqm);
+  const FrH c0 = mul(eq0, q0), c1 = sub(prev, c0);
+  const FrH l1 = mul(c1, inv(eq1));
+  const FrH l2 = sub(add(l1, l1), q0);
+  return from_evals({c0, c1, mul(eq2, l2)});
+}
+// split_eq_poly.rs:379-426
+static inline Coeffs gruen_poly_deg_3(const FrH& current_scalar, const FrH& current_w, const FrH& q_constant,
+                                      const FrH& q_quadratic, const FrH& s01) {
+  const FrH eq1 = mul(current_scalar, current_w);
+  const FrH eq0 = sub(current_scalar, eq1);
+  const FrH eqm = sub(eq1, eq0), eq2 = add(eq1, eqm), eq3 = add(eq2, eqm);
+  const FrH c0 = mul(eq0, q_constant), c1 = sub(s01, c0);
+  const FrH q1 = mul(c1, inv(eq1));
+  const FrH e2 = add(q_quadratic, q_quadratic);
+  const FrH q2 = add(sub(add(q1, q1), q_constant), e2);
+  const FrH q3 = add(add(sub(add(q2, q1), q_constant), e2), e2);
+  return from_evals({c0, c1, mul(eq2, q2), mul(eq3, q3)});
+}
+// mles_product_sum.rs:330-376: sums = values of the eq-free product polynomial on {1..d-1, inf} (already times
+// current_scalar); recover its value at 0 from the claim, interpolate, multiply by the linear eq factor.
+static inline Coeffs finish_mles_product_sum_from_evals(const std::vector<FrH>& sum_evals, const FrH& claim, const FrH& r) {
+  const FrH eq0 = sub(FR_ONE, r), eq1 = r;
+  FrH at0 = sub(claim, mul(eq1, sum_evals[0]));
+  if (sum_evals.size() != 1) at0 = mul(at0, inv(eq0));
+  std::vector<FrH> toom; toom.push_back(at0);
+  toom.insert(toom.end(), sum_evals.begin(), sum_evals.end());
+  const Coeffs tmp = from_evals_toom(toom);
+  const FrH cc = sub(FR_ONE, r), xc = sub(add(r, r), FR_ONE);
+  Coeffs coeffs(tmp.size() + 1, FR_ZERO);
+  for (size_t i = 0; i < tmp.size(); i++) {
+    coeffs[i] = add(coeffs[i], mul(tmp[i], cc));
+    coeffs[i + 1] = add(coeffs[i + 1], mul(tmp[i], xc));
+  }
+  return trim(coeffs);
+}
+
+}  // namespace host
+}  // namespace ja
