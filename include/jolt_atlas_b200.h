@@ -37,6 +37,7 @@ typedef struct ja_ctx ja_ctx;
 typedef struct ja_poly ja_poly;       /* device-resident MultilinearPolynomial (dense Fr, or compact i32 before its first bind) */
 typedef struct ja_spliteq ja_spliteq; /* device-resident GruenSplitEqPolynomial */
 typedef struct ja_srs ja_srs;         /* device-resident KZG SRS (g1_powers) */
+typedef struct ja_onehot ja_onehot;   /* device-resident batch of one-hot index lists (OneHotPolynomial::nonzero_indices as k*T+t) */
 typedef struct ja_hkzg ja_hkzg;       /* in-flight HyperKZG::open (folded polynomials resident on the device) */
 
 enum { JA_LOW_TO_HIGH = 0, JA_HIGH_TO_LOW = 1 };
@@ -83,6 +84,9 @@ int32_t ja_poly_from_fr(ja_ctx*, const uint64_t* z, size_t n, ja_poly** out);
 /* I32Scalars(CompactPolynomial<i32>) — `MultilinearPolynomial::from(tensor.padded_next_power_of_two())`
  * (ops/mul.rs:146-147).  Stays 4 B/coeff on device until the first bind (compact_polynomial.rs:272-353). */
 int32_t ja_poly_from_i32(ja_ctx*, const int32_t* z, size_t n, ja_poly** out);
+/* RaPolynomial materialisation (joltworks/src/poly/ra_poly.rs:31-81; shout.rs:549-598): out[t] = table[idx[t]] with
+ * table = K eq evaluations; idx[t] == 0xFFFFFFFF (None) -> 0.  n must be a power of two. */
+int32_t ja_poly_from_lookup(ja_ctx*, const uint64_t* table, size_t K, const uint32_t* idx, size_t n, ja_poly** out);
 /* uninitialised dense poly of length n (output of device-side producers) */
 int32_t ja_poly_alloc(ja_ctx*, size_t n, ja_poly** out);
 int32_t ja_poly_clone(ja_ctx*, const ja_poly*, ja_poly** out);
@@ -179,6 +183,11 @@ int32_t ja_g1_sum_indexed(ja_ctx*, const ja_srs*, const uint64_t* indices, size_
 /* batch_commit_one_hot (hyperkzg/mod.rs:558-596): `count` index lists, list i = indices[offsets[i] .. offsets[i+1]). */
 int32_t ja_g1_sum_indexed_batch(ja_ctx*, const ja_srs*, const uint64_t* indices, const uint64_t* offsets, size_t count,
                                 uint64_t* out_xy, int32_t* is_inf);
+
+/* The same with the index lists resident on the device (uploaded once per proof; the opening reduction reuses them). */
+int32_t ja_onehot_upload(ja_ctx*, const uint64_t* indices, const uint64_t* offsets, size_t count, ja_onehot** out);
+int32_t ja_onehot_commit(ja_ctx*, const ja_srs*, const ja_onehot*, uint64_t* out_xy, int32_t* is_inf);
+void ja_onehot_free(ja_ctx*, ja_onehot*);
 
 /* ---- HyperKZG::open (joltworks/src/poly/commitment/hyperkzg/mod.rs:400-447) --------------------------------------
  * Split at the two transcript interaction points so that a Rust caller keeps its own Blake2bTranscript:

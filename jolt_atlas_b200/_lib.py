@@ -24,6 +24,7 @@ SIGNATURES = {
     "ja_launch_count": (C.c_uint64, [vp]),
     "ja_poly_from_fr": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
     "ja_poly_from_i32": (C.c_int32, [vp, i32p, C.c_size_t, vpp]),
+    "ja_poly_from_lookup": (C.c_int32, [vp, u64p, C.c_size_t, u32p, C.c_size_t, vpp]),
     "ja_poly_alloc": (C.c_int32, [vp, C.c_size_t, vpp]),
     "ja_poly_clone": (C.c_int32, [vp, vp, vpp]),
     "ja_poly_len": (C.c_size_t, [vp]),
@@ -54,6 +55,9 @@ SIGNATURES = {
     "ja_msm_host": (C.c_int32, [vp, vp, C.c_size_t, vp, C.c_int32, C.c_size_t, u64p, i32p]),
     "ja_g1_sum_indexed": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p, i32p]),
     "ja_g1_sum_indexed_batch": (C.c_int32, [vp, vp, u64p, u64p, C.c_size_t, u64p, i32p]),
+    "ja_onehot_upload": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),
+    "ja_onehot_commit": (C.c_int32, [vp, vp, vp, u64p, i32p]),
+    "ja_onehot_free": (None, [vp, vp]),
     "ja_hyperkzg_open_begin": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, vpp, u64p, i32p]),
     "ja_hyperkzg_open_evals": (C.c_int32, [vp, vp, u64p, u64p]),
     "ja_hyperkzg_open_witness": (C.c_int32, [vp, vp, u64p, u64p, u64p, i32p]),

@@ -112,6 +112,16 @@ class MultilinearPolynomial:
         return MultilinearPolynomial(ctx, h)
 
     @staticmethod
+    def from_lookup(ctx: Context, table, idx) -> "MultilinearPolynomial":
+        """RaPolynomial materialisation: out[t] = table[idx[t]] (idx 0xFFFFFFFF = None -> 0)."""
+        table = _fr_arg(table).reshape(-1, 4)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        h = C.c_void_p()
+        check(ctx._lib.ja_poly_from_lookup(ctx._h, _u64p(table), table.shape[0], idx.ctypes.data_as(_lib.u32p), idx.shape[0],
+                                           C.byref(h)))
+        return MultilinearPolynomial(ctx, h)
+
+    @staticmethod
     def random(ctx: Context, n: int, seed: int = 1) -> "MultilinearPolynomial":
         """Device-generated pseudo-random canonical Fr coefficients (synthetic bench operands)."""
         h = C.c_void_p()
@@ -324,6 +334,31 @@ def g1_sum_indexed_batch(ctx: Context, srs: SRS, index_lists):
     check(ctx._lib.ja_g1_sum_indexed_batch(ctx._h, srs._h, _u64p(flat) if flat.shape[0] else None, _u64p(offs),
                                            len(index_lists), _u64p(out), inf.ctypes.data_as(_lib.i32p)))
     return out[: len(index_lists)], inf[: len(index_lists)].astype(bool)
+
+
+class OneHotBatch:
+    """Device-resident batch of one-hot index lists (k*T + t per non-None entry, hyperkzg/mod.rs:536-542)."""
+
+    def __init__(self, ctx: Context, index_lists):
+        self.ctx, self.count = ctx, len(index_lists)
+        offs = np.zeros(self.count + 1, dtype=np.uint64)
+        for i, l in enumerate(index_lists):
+            offs[i + 1] = offs[i] + len(l)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.uint64) for l in index_lists]), dtype=np.uint64)
+        h = C.c_void_p()
+        check(ctx._lib.ja_onehot_upload(ctx._h, _u64p(flat) if flat.shape[0] else None, _u64p(offs), self.count, C.byref(h)))
+        self._h = h
+
+    def commit(self, srs: SRS):
+        """HyperKZG::batch_commit_one_hot over the resident lists."""
+        out, inf = _pt_out(self.count)
+        check(self.ctx._lib.ja_onehot_commit(self.ctx._h, srs._h, self._h, _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+        return out, inf.astype(bool)
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_onehot_free(self.ctx._h, self._h)
+            self._h = None
 
 
 # ---- HyperKZG::open (hyperkzg/mod.rs:400-447) ----

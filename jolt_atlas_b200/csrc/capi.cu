@@ -100,6 +100,26 @@ int32_t ja_poly_from_i32(ja_ctx* c, const int32_t* z, size_t n, ja_poly** out) {
   return JA_OK;
 }
 
+int32_t ja_poly_from_lookup(ja_ctx* c, const uint64_t* table, size_t K, const uint32_t* idx, size_t n, ja_poly** out) {
+  JA_REQUIRE(c && table && idx && out && K > 0, "ja_poly_from_lookup: null argument");
+  for (size_t i = 0; i < n; i++)
+    JA_REQUIRE(idx[i] == 0xffffffffu || idx[i] < K, "ja_poly_from_lookup: index outside the table");
+  int32_t st = ja_poly_alloc(c, n, out);
+  if (st) return st;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  Fr* d_table = nullptr; uint32_t* d_idx = nullptr;
+  if ((st = dev_alloc(c, K * sizeof(Fr), (void**)&d_table))) return st;
+  if ((st = dev_alloc(c, n * sizeof(uint32_t), (void**)&d_idx))) return st;
+  JA_CUDA(cudaMemcpyAsync(d_table, table, K * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaMemcpyAsync(d_idx, idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  k_gather_small_table<<<grid_for(n), kBlock, 0, c->stream>>>(d_table, d_idx, n, (*out)->buf[0]);
+  c->launches++;
+  JA_CUDA(cudaGetLastError());
+  dev_free(c, d_table); dev_free(c, d_idx);
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  return JA_OK;
+}
+
 int32_t ja_poly_clone(ja_ctx* c, const ja_poly* src, ja_poly** out) {
   JA_REQUIRE(c && src && out, "ja_poly_clone: null argument");
   int32_t st = ja_poly_alloc(c, src->len, out);

@@ -65,6 +65,12 @@ struct ja_srs {
   size_t n = 0;
 };
 
+struct ja_onehot {
+  uint64_t* d_indices = nullptr;        // concatenated base indices k*T + t of every list
+  std::vector<uint64_t> offsets;       // count + 1
+  uint64_t max_index = 0;
+};
+
 // one MSM of a batch (msm.cu): kind/nbits as in msm_kernels.cuh (0 = Fr Montgomery scalars, 254 bits)
 struct MsmJob { const void* d_scalars; size_t n; uint32_t kind; uint32_t nbits; size_t base_offset; };
 int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, uint64_t* out_xy, int32_t* is_inf);

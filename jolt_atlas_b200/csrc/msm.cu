@@ -312,6 +312,49 @@ int32_t ja_g1_sum_indexed_batch(ja_ctx* c, const ja_srs* srs, const uint64_t* in
   return JA_OK;
 }
 
+// Device-resident batch of one-hot index lists (the committed OneHotPolynomials of a proof stay in HBM between the
+// commitment and the opening reduction).
+int32_t ja_onehot_upload(ja_ctx* c, const uint64_t* indices, const uint64_t* offsets, size_t count, ja_onehot** out) {
+  JA_REQUIRE(c && offsets && out && count > 0, "ja_onehot_upload: null or empty argument");
+  const size_t total = offsets[count];
+  JA_REQUIRE(indices || total == 0, "ja_onehot_upload: null indices");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  ja_onehot* h = new ja_onehot();
+  h->offsets.assign(offsets, offsets + count + 1);
+  for (size_t i = 0; i < count; i++)
+    if (offsets[i + 1] < offsets[i]) { delete h; return fail(JA_ERR_INVALID, "ja_onehot_upload: offsets must be non-decreasing"); }
+  for (size_t i = 0; i < total; i++) if (indices[i] > h->max_index) h->max_index = indices[i];
+  int32_t st = dev_alloc(c, (total ? total : 1) * 8, (void**)&h->d_indices);
+  if (st) { delete h; return st; }
+  if (total) JA_CUDA(cudaMemcpyAsync(h->d_indices, indices, total * 8, cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  *out = h;
+  return JA_OK;
+}
+
+int32_t ja_onehot_commit(ja_ctx* c, const ja_srs* srs, const ja_onehot* h, uint64_t* out_xy, int32_t* is_inf) {
+  JA_REQUIRE(c && srs && h && out_xy, "ja_onehot_commit: null argument");
+  const size_t count = h->offsets.size() - 1;
+  if (h->offsets[count] && h->max_index >= srs->n)
+    return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, index " +
+                                       std::to_string(h->max_index) + " requested");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  std::vector<MsmJob> jobs(count);
+  for (size_t i = 0; i < count; i++)
+    jobs[i] = MsmJob{h->d_indices + h->offsets[i], (size_t)(h->offsets[i + 1] - h->offsets[i]), MSM_INDEXED, 1, 0};
+  return ja_msm_run(c, srs, jobs, out_xy, is_inf);
+}
+
+void ja_onehot_free(ja_ctx* c, ja_onehot* h) {
+  if (!c || !h) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  dev_free(c, h->d_indices);
+  delete h;
+}
+
 int32_t ja_g1_sum_indexed(ja_ctx* c, const ja_srs* srs, const uint64_t* indices, size_t n, uint64_t out_xy[8],
                           int32_t* is_inf) {
   const uint64_t offs[2] = {0, n};

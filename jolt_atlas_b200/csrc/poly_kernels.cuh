@@ -158,6 +158,17 @@ static __global__ void __launch_bounds__(kBlock) k_i32_to_fr(const int* __restri
     fp_store(out + i, fr_from_i32(__ldg(in + i)));
 }
 
+// RaPolynomial materialisation (joltworks/src/poly/ra_poly.rs:31-81, shout.rs:549-598 compute_ra_evals): out[t] =
+// table[idx[t]] for a small table (K <= 2^16 eq evaluations); idx == 0xFFFFFFFF (None) gives 0.
+static __global__ void __launch_bounds__(kBlock)
+k_gather_small_table(const Fr* __restrict__ table, const uint32_t* __restrict__ idx, size_t n, Fr* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const uint32_t k = __ldg(idx + t);
+    fp_store(out + t, k == 0xffffffffu ? fp_zero<FrParams>() : fp_load(table + k));
+  }
+}
+
 // ---- eq tables ---------------------------------------------------------------------------------
 // All prefix tables of eq(w, .) in one buffer: level j (2^j entries) at offset 2^j - 1.
 //   rev == 0: EqPolynomial::evals_cached      (eq_poly.rs:174-194)   level j+1: [2i+1] = prev[i]*w[j], [2i] = prev[i]-[2i+1]

@@ -50,20 +50,71 @@ void orc_evaluate(const uint64_t* z, size_t n, const uint64_t* point, size_t m, 
   store_fr(out, evaluate(v, p.data(), m));
 }
 
+// Einsum operand fold (jolt-atlas-core/src/onnx_proof/ops/einsum/mk_kn_mn.rs:47-79): i32 matrix x eq-vector.
+//   transpose == 0: out[j] = sum_i from_i32(A[i*cols+j]) * eq[i];  transpose == 1: out[i] = sum_j from_i32(A[i*cols+j]) * eq[j]
+void orc_tensor_fold_i32(const int32_t* A, size_t rows, size_t cols, const uint64_t* eq, int transpose, uint64_t* out) {
+  const size_t n_eq = transpose ? cols : rows, n_out = transpose ? rows : cols;
+  FrVec e = load_fr(eq, n_eq);
+  FrVec o(n_out, Fr::zero());
+  if (transpose) {
+#pragma omp parallel for if (rows * cols >= 4096)
+    for (size_t i = 0; i < rows; i++) {
+      Fr acc = Fr::zero();
+      for (size_t j = 0; j < cols; j++) { int32_t v = A[i * cols + j]; if (v) acc += Fr::from_i64(v) * e[j]; }
+      o[i] = acc;
+    }
+  } else {
+#pragma omp parallel for if (rows * cols >= 4096)
+    for (size_t j = 0; j < cols; j++) {
+      Fr acc = Fr::zero();
+      for (size_t i = 0; i < rows; i++) { int32_t v = A[i * cols + j]; if (v) acc += Fr::from_i64(v) * e[i]; }
+      o[j] = acc;
+    }
+  }
+  memcpy(out, o.data(), n_out * 32);
+}
+
 // Sumcheck::prove over one instance.
 //   family 0 (split-eq, LowToHigh): kind = SKind, w = m Fr;  family 1 (dot, HighToLow): w ignored.
 // Outputs: coeffs[rounds][max_coeffs][4] (compressed: all but the linear term), ncoeffs[rounds], challenges[rounds][4],
 // final_claims[npoly][4], state[32] (transcript state after the last challenge).
+static int sumcheck_prove_t(int family, int kind, unsigned pow_d, const uint64_t* polys, size_t npoly, size_t n,
+                            const uint64_t* w, size_t m, const uint64_t claim[4], const uint64_t* gammas, Transcript& t,
+                            size_t max_coeffs, uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges,
+                            uint64_t* final_claims);
 int orc_sumcheck_prove(int family, int kind, unsigned pow_d, const uint64_t* polys, size_t npoly, size_t n,
                        const uint64_t* w, size_t m, const uint64_t claim[4], const char* label,
                        size_t max_coeffs, uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges,
                        uint64_t* final_claims, uint8_t state[32]) {
+  Transcript t(label);
+  int rc = sumcheck_prove_t(family, kind, pow_d, polys, npoly, n, w, m, claim, nullptr, t, max_coeffs, coeffs, ncoeffs, challenges, final_claims);
+  memcpy(state, t.state, 32);
+  return rc;
+}
+// same, resuming a running transcript (state + round counter read and written back); family 2 = Hamming (gammas)
+int orc_sumcheck_prove_st(int family, int kind, unsigned pow_d, const uint64_t* polys, size_t npoly, size_t n,
+                          const uint64_t* w, size_t m, const uint64_t claim[4], const uint64_t* gammas,
+                          uint8_t state[32], uint32_t* n_rounds,
+                          size_t max_coeffs, uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges, uint64_t* final_claims) {
+  Transcript t(state, *n_rounds);
+  int rc = sumcheck_prove_t(family, kind, pow_d, polys, npoly, n, w, m, claim, gammas, t, max_coeffs, coeffs, ncoeffs, challenges, final_claims);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+  return rc;
+}
+static int sumcheck_prove_t(int family, int kind, unsigned pow_d, const uint64_t* polys, size_t npoly, size_t n,
+                            const uint64_t* w, size_t m, const uint64_t claim[4], const uint64_t* gammas, Transcript& t,
+                            size_t max_coeffs, uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges,
+                            uint64_t* final_claims) {
   std::vector<FrVec> ps;
   for (size_t i = 0; i < npoly; i++) ps.push_back(load_fr(polys + 4 * n * i, n));
   std::unique_ptr<Instance> inst;
   if (family == 0) { FrVec ww = load_fr(w, m); inst.reset(new SplitEqInstance(kind, ww.data(), m, std::move(ps), Fr::from_raw(claim), pow_d)); }
-  else inst.reset(new DotInstance(std::move(ps), Fr::from_raw(claim)));
-  Transcript t(label);
+  else if (family == 1) inst.reset(new DotInstance(std::move(ps), Fr::from_raw(claim)));
+  else {
+    std::vector<Fr> g(npoly, Fr::one());
+    if (gammas) for (size_t i = 0; i < npoly; i++) g[i] = Fr::from_raw(gammas + 4 * i);
+    inst.reset(new HammingInstance(std::move(ps), g, Fr::from_raw(claim)));
+  }
   SumcheckProof pf = sumcheck_prove(*inst, t);
   for (size_t r = 0; r < pf.compressed_polys.size(); r++) {
     if (pf.compressed_polys[r].size() > max_coeffs) return -1;
@@ -73,7 +124,6 @@ int orc_sumcheck_prove(int family, int kind, unsigned pow_d, const uint64_t* pol
   }
   std::vector<Fr> fc = inst->final_claims();
   for (size_t i = 0; i < fc.size(); i++) store_fr(final_claims + 4 * i, fc[i]);
-  memcpy(state, t.state, 32);
   return (int)pf.compressed_polys.size();
 }
 
@@ -107,18 +157,31 @@ void orc_scalar_mul(const uint64_t xy[8], const uint64_t k_mont[4], uint64_t out
 }
 
 // HyperKZG::open.  point = ell challenge limbs.  Outputs: com[(ell-1)][8] + com_inf, w[3][8] + w_inf, v[3][ell][4], state[32].
+static void hyperkzg_open_t(const uint64_t* srs_xy, size_t n, const uint64_t* poly, const uint64_t* point, size_t ell,
+                            Transcript& t, uint64_t* com_xy, int32_t* com_inf, uint64_t* w_xy, int32_t* w_inf, uint64_t* v);
 void orc_hyperkzg_open(const uint64_t* srs_xy, size_t n, const uint64_t* poly, const uint64_t* point, size_t ell,
                        const char* label, uint64_t* com_xy, int32_t* com_inf, uint64_t* w_xy, int32_t* w_inf,
                        uint64_t* v, uint8_t state[32]) {
+  Transcript t(label);
+  hyperkzg_open_t(srs_xy, n, poly, point, ell, t, com_xy, com_inf, w_xy, w_inf, v);
+  memcpy(state, t.state, 32);
+}
+void orc_hyperkzg_open_st(const uint64_t* srs_xy, size_t n, const uint64_t* poly, const uint64_t* point, size_t ell,
+                          uint8_t state[32], uint32_t* n_rounds, uint64_t* com_xy, int32_t* com_inf, uint64_t* w_xy,
+                          int32_t* w_inf, uint64_t* v) {
+  Transcript t(state, *n_rounds);
+  hyperkzg_open_t(srs_xy, n, poly, point, ell, t, com_xy, com_inf, w_xy, w_inf, v);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+static void hyperkzg_open_t(const uint64_t* srs_xy, size_t n, const uint64_t* poly, const uint64_t* point, size_t ell,
+                            Transcript& t, uint64_t* com_xy, int32_t* com_inf, uint64_t* w_xy, int32_t* w_inf, uint64_t* v) {
   std::vector<G1Affine> srs = load_bases(srs_xy, n);
   FrVec p = load_fr(poly, n);
   std::vector<Fr> pt = load_fr(point, ell);
-  Transcript t(label);
   HyperKZGProof pf = hyperkzg_open(srs, p, pt, t);
   for (size_t i = 0; i < pf.com.size(); i++) store_pt(com_xy + 8 * i, com_inf + i, pf.com[i]);
   for (size_t i = 0; i < 3; i++) store_pt(w_xy + 8 * i, w_inf + i, pf.w[i]);
   for (size_t i = 0; i < 3; i++) for (size_t j = 0; j < ell; j++) store_fr(v + 4 * (i * ell + j), pf.v[i][j]);
-  memcpy(state, t.state, 32);
 }
 
 // ---- CPU baseline timing legs (bench.py): same synthetic workloads as ja_bench_kernel, on all host threads ----

@@ -58,7 +58,7 @@ inline UniPoly gruen_poly_deg_2(const GruenSplitEq& eq, const Fr& q0, const Fr& 
   return UniPoly::from_evals({c0, c1, eq2 * l2});
 }
 
-enum SKind { S_ADD = 0, S_SUB = 1, S_MUL = 2, S_SQUARE = 3, S_PROD = 4, S_POW = 5 };
+enum SKind { S_ADD = 0, S_SUB = 1, S_MUL = 2, S_SQUARE = 3, S_PROD = 4, S_POW = 5, S_IDENT = 6 };
 
 // Family S: split-eq weighted, LowToHigh
 struct SplitEqInstance : Instance {
@@ -70,7 +70,7 @@ struct SplitEqInstance : Instance {
       : kind(kind_), pow_d(pow_d_), eq(w, m, LOW_TO_HIGH), polys(std::move(p)), claim(claim_) {}
   size_t num_rounds() const override { return eq.w.size(); }
   size_t degree() const override {
-    switch (kind) { case S_ADD: case S_SUB: return 2; case S_MUL: case S_SQUARE: return 3;
+    switch (kind) { case S_ADD: case S_SUB: case S_IDENT: return 2; case S_MUL: case S_SQUARE: return 3;
                     case S_POW: return pow_d + 1; default: return polys.size() + 1; }
   }
   Fr input_claim() const override { return claim; }
@@ -80,6 +80,12 @@ struct SplitEqInstance : Instance {
       const FrVec &l = polys[0], &r = polys[1];
       if (kind == S_ADD) eq.fold<1>([&](size_t g, Fr* v) { v[0] = l[2 * g] + r[2 * g]; }, q);
       else eq.fold<1>([&](size_t g, Fr* v) { v[0] = l[2 * g] - r[2 * g]; }, q);
+      return gruen_poly_deg_2(eq, q[0], prev);
+    }
+    if (kind == S_IDENT) {   // ps_shout / identity-RC cycle rounds, dense opening reduction: [p0]
+      Fr q[1];
+      const FrVec& z = polys[0];
+      eq.fold<1>([&](size_t g, Fr* v) { v[0] = z[2 * g]; }, q);
       return gruen_poly_deg_2(eq, q[0], prev);
     }
     if (kind == S_MUL) {

@@ -72,6 +72,7 @@ struct Transcript {
     memcpy(pad, label.data(), label.size());
     Blake2b256 h; h.update(pad, 32); h.finalize(state);
   }
+  Transcript(const uint8_t st[32], uint32_t rounds) : n_rounds(rounds) { memcpy(state, st, 32); }   // resume a running transcript
   Blake2b256 hasher() const {                       // :31-37
     Blake2b256 h; h.update(state, 32);
     uint8_t packed[32] = {0};

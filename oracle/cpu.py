@@ -99,6 +99,65 @@ def sumcheck_prove(family: int, kind: int, polys: np.ndarray, w, claim: np.ndarr
             "final_claims": fin, "state": state.raw}
 
 
+def tensor_fold_i32(A: np.ndarray, eq: np.ndarray, transpose: bool) -> np.ndarray:
+    A = np.ascontiguousarray(A, dtype=np.int32)
+    rows, cols = A.shape
+    eq = np.ascontiguousarray(eq, dtype=np.uint64)
+    out = np.empty((rows if transpose else cols, 4), dtype=np.uint64)
+    lib().orc_tensor_fold_i32(_p(A), C.c_size_t(rows), C.c_size_t(cols), _p(eq), int(transpose), _p(out))
+    return out
+
+
+class TranscriptState:
+    """Running Blake2bTranscript state + round counter (blake2b.rs:11-26); new(label) per blake2b.rs:81-100."""
+
+    def __init__(self, label: bytes):
+        import hashlib
+        self.state = hashlib.blake2b(label + b"\0" * (32 - len(label)), digest_size=32).digest()
+        self.n_rounds = 0
+
+
+def sumcheck_prove_st(family: int, kind: int, polys: np.ndarray, w, claim: np.ndarray, t: TranscriptState, pow_d: int = 0,
+                      gammas=None):
+    """Like sumcheck_prove but resumes / advances the running transcript `t`.  family 2 = Hamming weight (gammas)."""
+    polys = np.ascontiguousarray(polys, dtype=np.uint64)
+    npoly, n, _ = polys.shape
+    rounds = n.bit_length() - 1
+    w = np.ascontiguousarray(w if w is not None else np.zeros((0, 4)), dtype=np.uint64).reshape(-1, 4)
+    claim = np.ascontiguousarray(claim, dtype=np.uint64)
+    g = _p(np.ascontiguousarray(gammas, dtype=np.uint64)) if gammas is not None else None
+    maxc = 40
+    coeffs = np.zeros((rounds, maxc, 4), dtype=np.uint64)
+    ncoeffs = np.zeros(rounds, dtype=np.uint32)
+    chal = np.zeros((rounds, 4), dtype=np.uint64)
+    fin = np.zeros((npoly, 4), dtype=np.uint64)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    rc = lib().orc_sumcheck_prove_st(family, kind, C.c_uint(pow_d), _p(polys), C.c_size_t(npoly), C.c_size_t(n), _p(w),
+                                     C.c_size_t(w.shape[0]), _p(claim), g, st, C.byref(nr), C.c_size_t(maxc), _p(coeffs),
+                                     _p(ncoeffs), _p(chal), _p(fin))
+    assert rc == rounds, rc
+    t.state, t.n_rounds = st.raw, nr.value
+    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(rounds)], "challenges": chal, "final_claims": fin}
+
+
+def hyperkzg_open_st(srs: np.ndarray, poly: np.ndarray, point: np.ndarray, t: TranscriptState):
+    n = poly.shape[0]
+    ell = point.shape[0]
+    com = np.zeros((max(ell - 1, 1), 8), dtype=np.uint64)
+    com_inf = np.zeros(max(ell - 1, 1), dtype=np.int32)
+    w = np.zeros((3, 8), dtype=np.uint64)
+    w_inf = np.zeros(3, dtype=np.int32)
+    v = np.zeros((3, ell, 4), dtype=np.uint64)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    lib().orc_hyperkzg_open_st(_p(srs), C.c_size_t(n), _p(np.ascontiguousarray(poly, dtype=np.uint64)),
+                               _p(np.ascontiguousarray(point, dtype=np.uint64)), C.c_size_t(ell), st, C.byref(nr),
+                               _p(com), _p(com_inf), _p(w), _p(w_inf), _p(v))
+    t.state, t.n_rounds = st.raw, nr.value
+    return {"com": com[: ell - 1], "com_inf": com_inf[: ell - 1], "w": w, "w_inf": w_inf, "v": v}
+
+
 def srs_powers(tau_mont: np.ndarray, n: int) -> np.ndarray:
     out = np.empty((n, 8), dtype=np.uint64)
     lib().orc_srs_powers(_p(np.ascontiguousarray(tau_mont, dtype=np.uint64)), C.c_size_t(n), _p(out))

@@ -45,7 +45,7 @@ class SplitEqInstance(Instance):
         self.eq = GruenSplitEq(w_fr, LOW_TO_HIGH)
         self.polys = [list(p) for p in polys]
         self.claim = claim % P
-        self.degree = {"add": 2, "sub": 2, "mul": 3, "square": 3, "cube": 4}.get(kind, len(polys) + 1)
+        self.degree = {"add": 2, "sub": 2, "ident": 2, "mul": 3, "square": 3, "cube": 4}.get(kind, len(polys) + 1)
 
     def num_rounds(self): return len(self.eq.w)
     def input_claim(self): return self.claim
@@ -56,6 +56,9 @@ class SplitEqInstance(Instance):
         if k in ("add", "sub"):
             sgn = 1 if k == "add" else -1
             [q0] = self.eq.fold(lambda g: [ps[0][2 * g] + sgn * ps[1][2 * g]], 1)
+            return self.eq.gruen_poly_deg_2(q0, prev)
+        if k == "ident":
+            (q0,) = self.eq.fold(lambda g: [ps[0][2 * g]], 1)
             return self.eq.gruen_poly_deg_2(q0, prev)
         if k == "mul":
             def f(g):

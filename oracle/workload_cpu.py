@@ -1,0 +1,55 @@
+"""TEST INFRASTRUCTURE ONLY — CPU twin of jolt_atlas_b200/workload.py::run_device on the C++ oracle (OpenMP), stage for
+stage and with the same chained transcript.  Used by tests (parity of every commitment / round polynomial / final
+claim / transcript state), by __graft_entry__.smoke() and by bench.py's cpu_baseline and --impl reference legs."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import cpu as ORC
+
+D_CLAMP = 16
+
+
+def _index_lists(ni):
+    T = ni.hot_k.shape[1]
+    t = np.arange(T, dtype=np.uint64)
+    return [ni.hot_k[i].astype(np.uint64) * np.uint64(T) + t for i in range(ni.d_hot)]
+
+
+def run_cpu(srs_host: np.ndarray, inputs, rlc_host: np.ndarray, node_limit: int | None = None, do_open: bool = True):
+    """srs_host: (n, 8) affine Montgomery limbs; rlc_host: (2^ell, 4) Fr of the polynomial to open.
+    node_limit bounds the number of nodes processed (bench samples)."""
+    t = ORC.TranscriptState(b"ONNXProof")
+    out = {"commitments": [], "states": [], "finals": []}
+    claim = inputs["claim"]
+    nodes = inputs["nodes"] if node_limit is None else inputs["nodes"][:node_limit]
+    for ni in nodes:
+        spec = ni.spec
+        coms = [ORC.sum_indexed(srs_host, idx) for idx in _index_lists(ni)]
+        out["commitments"].append((np.stack([c[0] for c in coms]), np.array([c[1] for c in coms])))
+        ra = [np.ascontiguousarray(ni.tables[j][ni.hot_k[j]]) for j in range(ni.d_hot)]
+        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra[0]]), ni.eq_w, claim, t)
+        out["finals"].append(r["final_claims"])
+        r = ORC.sumcheck_prove_st(2, 0, np.stack(ra[:D_CLAMP]), None, claim, t, gammas=ni.gammas[:D_CLAMP])
+        out["finals"].append(r["final_claims"])
+        r = ORC.sumcheck_prove_st(0, 4, np.stack(ra[:D_CLAMP]), ni.eq_w, claim, t)
+        out["finals"].append(r["final_claims"])
+        if spec.kind == "einsum":
+            left = ORC.tensor_fold_i32(ni.A, ORC.eq_evals(ni.eq_rows), False)
+            right = ORC.tensor_fold_i32(ni.B, ORC.eq_evals(ni.eq_cols), True)
+            r = ORC.sumcheck_prove_st(1, 0, np.stack([left, right]), None, claim, t)
+        else:
+            a, b = ORC.fr_from_i64(ni.A), ORC.fr_from_i64(ni.B)
+            r = ORC.sumcheck_prove_st(0, 2 if spec.kind == "mul" else 0, np.stack([a, b]), ni.eq_w, claim, t)
+        out["finals"].append(r["final_claims"])
+        if ni.d_hot > D_CLAMP:
+            r = ORC.sumcheck_prove_st(0, 6, np.stack([ra[D_CLAMP]]), ni.eq_w, claim, t)
+            out["finals"].append(r["final_claims"])
+            r = ORC.sumcheck_prove_st(0, 4, np.stack(ra[D_CLAMP:]), ni.eq_w, claim, t)
+            out["finals"].append(r["final_claims"])
+        out["states"].append(t.state)
+    if do_open:
+        n = 1 << inputs["ell"]
+        out["open"] = ORC.hyperkzg_open_st(srs_host[:n], rlc_host, inputs["open_point"], t)
+        out["states"].append(t.state)
+    return out

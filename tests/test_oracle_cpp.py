@@ -124,3 +124,24 @@ def test_msm_random_vs_python():
     sc[0] = 0; sc[1] = 1; sc[2] = P - 1
     got, inf = ORC.msm_fr(fq_arr(bases), to_mont_array(sc))
     assert pt_from(got, inf) == C.msm_pippenger(bases, sc, c=7)
+
+
+def test_ident_instance_matches_python_twin():
+    """S_IDENT (ps_shout / identity-RC cycle rounds, dense opening reduction) is not in the golden file: compare the two
+    oracles directly on a seeded case."""
+    from oracle.pyref import sumcheck as SC
+    from oracle.pyref import transcript as TR
+    rng = random.Random(21)
+    m = 6
+    z = [rng.randrange(P) for _ in range(1 << m)]
+    w_c = [rng.getrandbits(128) & F.CHALLENGE_MASK for _ in range(m)]
+    w = [F.challenge_to_fr(c) for c in w_c]
+    claim = PL.evaluate(z, w)
+    t = TR.Blake2bTranscript(b"ident")
+    inst = SC.SplitEqInstance("ident", w, [z], claim)
+    cps, rs, fin = SC.sumcheck_prove(inst, t)
+    res = ORC.sumcheck_prove(0, 6, np.stack([to_mont_array(z)]), np.array([F.challenge_limbs(c) for c in w_c], dtype=np.uint64),
+                             to_mont_array([claim])[0], b"ident")
+    assert [from_mont_array(cp) for cp in res["coeffs"]] == [list(cp.coeffs_except_linear_term) for cp in cps]
+    assert res["state"] == t.state
+    assert from_mont_array(res["final_claims"]) == inst.final_claims()

@@ -110,6 +110,7 @@ def test_sumcheck_instances_prove_verify():
         "add": ([a, b], [(x + y) % P for x, y in zip(a, b)], lambda f: f[0] + f[1]),
         "sub": ([a, b], [(x - y) % P for x, y in zip(a, b)], lambda f: f[0] - f[1]),
         "square": ([a], [x * x % P for x in a], lambda f: f[0] ** 2),
+        "ident": ([a], a, lambda f: f[0]),
         "cube": ([a], [x ** 3 % P for x in a], lambda f: f[0] ** 3),
         "prod": ([a, b, a], [x * y * x % P for x, y in zip(a, b)], lambda f: f[0] * f[1] * f[2]),
     }
