@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the proving hot path.
+
+  python bench.py --gpus N --steps K --warmup W                  this repo's CUDA path (C ABI through jolt_atlas_b200)
+  python bench.py --impl reference --gpus N --steps K --warmup W  the CPU restatement (oracle/, OpenMP) on the host cores
+
+A "step" is ONE prove-shaped pass (jolt_atlas_b200/workload.py): for every node of the nanoGPT-shaped graph the one-hot
+witness commitments, the lookup / RA / operator / range-check sumchecks with a chained Blake2b transcript, then one
+HyperKZG opening (ell = 18).  metric = seconds per pass (BASELINE.json: "ONNXProof::prove sec (nanoGPT ...)").
+
+  value     device-resident inputs (uploaded once before the timed region), CUDA events on the library's stream
+  e2e       same pass through the public API with HOST (pinned) buffers: H2D of every input and D2H of every
+            commitment / round polynomial / claim inside the timed region
+  roofline  the dominant kernel class of the pass, timed live with CUDA events (ja_profile_*), vs MEASURED_PEAKS.json
+  cpu_baseline  the C++ oracle on the host cores, bounded sample (rank 0, N = 1 only)
+
+No number here is taken under a profiler.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+TAU = 0x1234567890abcdef1122334455667788          # fixed test "toxic waste": SRS = [tau^i] G (SURVEY §8c SRS note)
+def metric_name(config: str) -> str:
+    return "ONNXProof::prove sec (%s-shaped prove pass)" % config
+
+
+def _limbs(x: int, n: int = 4) -> list[int]:
+    return [(x >> (64 * k)) & ((1 << 64) - 1) for k in range(n)]
+
+
+def g1_generator_mont() -> np.ndarray:
+    rq = (1 << 256) % Q
+    return np.array(_limbs(rq) + _limbs(2 * rq % Q), dtype=np.uint64)       # (1, 2) in Montgomery form
+
+
+def tau_mont() -> np.ndarray:
+    from jolt_atlas_b200.workload import P, R
+    return np.array(_limbs(TAU * R % P), dtype=np.uint64)
+
+
+def peaks() -> tuple[dict, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md, the clocks line)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pin_inputs(inputs):
+    """Move the per-proof host inputs into pinned memory (torch is plumbing here: cudaHostAlloc)."""
+    import torch
+
+    def pin(a: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+    keep = []
+    for ni in inputs["nodes"]:
+        for name in ("hot_k", "tables", "A", "B", "eq_w", "gammas", "eq_rows", "eq_cols"):
+            v = getattr(ni, name)
+            if v is not None:
+                setattr(ni, name, pin(v))
+    inputs["open_point"] = pin(inputs["open_point"])
+    return keep
+
+
+def d2h_bytes(result) -> int:
+    total = 0
+    for com, inf in result["commitments"]:
+        total += com.nbytes + np.asarray(inf).nbytes
+    for f in result["finals"]:
+        total += f.nbytes
+    total += result.get("msg_bytes", 0)
+    for k in ("com", "v", "w"):
+        total += result["open"][k].nbytes
+    return total
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_pass_seconds(srs_host, inputs, rlc_host, budget_s: float):
+    """Time the C++ oracle (OpenMP, all host threads) on the workload.  Full pass when it fits the budget, else
+    layer 0 x (number of identical layers) + lm_head + the opening, each timed once."""
+    from oracle import cpu as ORC
+    from oracle import workload_cpu as WC
+    nodes = inputs["nodes"]
+    per_layer = 10
+    t0 = time.perf_counter()
+    WC.run_cpu(srs_host, inputs, rlc_host, node_limit=per_layer, do_open=False)
+    t_layer = time.perf_counter() - t0
+    n_layers = (len(nodes) - 1) // per_layer
+    est_nodes = t_layer * n_layers * 1.05
+    if est_nodes * 1.3 <= budget_s:
+        t0 = time.perf_counter()
+        WC.run_cpu(srs_host, inputs, rlc_host)
+        return time.perf_counter() - t0, "full pass: %d nodes + HyperKZG open ell=%d" % (len(nodes), inputs["ell"])
+    head = dict(inputs)
+    head["nodes"] = nodes[n_layers * per_layer:]
+    t0 = time.perf_counter()
+    WC.run_cpu(srs_host, head, rlc_host, do_open=True)
+    t_tail = time.perf_counter() - t0
+    return (t_layer * n_layers + t_tail,
+            "layer 0 (%d of %d nodes) timed once and counted x%d, + lm_head + HyperKZG open ell=%d timed once"
+            % (per_layer, len(nodes), n_layers, inputs["ell"]))
+
+
+def synthetic_rlc_host(n: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)           # canonical (< p)
+    return a
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the same pass on the host cores (oracle/cpp, OpenMP).  The reference
+    itself is Rust with un-vendored git dependencies and cannot be built in this image."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu as ORC
+    from oracle import workload_cpu as WC
+    from jolt_atlas_b200 import workload as W
+    inputs = W.build_inputs(args.config)
+    n = 1 << inputs["ell"]
+    srs_host = ORC.srs_powers(tau_mont(), n)
+    rlc_host = synthetic_rlc_host(n, inputs["rlc_seed"])
+    total_steps = args.steps + args.warmup
+    budget = 150.0 / max(total_steps, 1)
+    # calibrate once, then decide between the full pass and the bounded sample
+    secs, sample = cpu_pass_seconds(srs_host, inputs, rlc_host, budget)
+    full = sample.startswith("full")
+    times = []
+    for i in range(total_steps):
+        if full:
+            t0 = time.perf_counter()
+            WC.run_cpu(srs_host, inputs, rlc_host)
+            dt = time.perf_counter() - t0
+        else:
+            dt, _ = cpu_pass_seconds(srs_host, inputs, rlc_host, 0.0)
+        if i >= args.warmup:
+            times.append(dt)
+    val = float(np.mean(times)) if times else secs
+    cores = ORC.num_threads()
+    line = {"impl": "reference", "metric": metric_name(args.config), "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64x4 Montgomery (BN254 Fr/Fq)", "data": "synthetic",
+            "config": W.config_dict(args.config, inputs),
+            "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_device_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from jolt_atlas_b200 import SRS, Context, MultilinearPolynomial
+    from jolt_atlas_b200 import workload as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = Context(local)
+    # independent proofs per rank (weak scaling: the path has no cross-proof exchange); see DESIGN.md §Multi-GPU
+    inputs = W.build_inputs(args.config, seed=None if rank == 0 else W.CONFIGS[args.config]["seed"] + rank)
+    n = 1 << inputs["ell"]
+    srs = SRS.generate(ctx, g1_generator_mont(), tau_mont(), n)
+    resident = W.make_resident(ctx, inputs)
+    pin_inputs(inputs)
+    ctx.sync()
+
+    # ---- device-resident leg ----
+    for _ in range(args.warmup):
+        W.run_device(ctx, srs, inputs, resident=resident)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    ctx.timer_begin()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        W.run_device(ctx, srs, inputs, resident=resident)
+    dev_ms = ctx.timer_end()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    ms = max(dev_ms, 0.0)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+
+    # ---- end-to-end leg: host buffers in, proof data out, every step ----
+    W.run_device(ctx, srs, inputs)          # warm the upload path
+    barrier()
+    ctx.timer_begin()
+    last = None
+    for _ in range(args.steps):
+        last = W.run_device(ctx, srs, inputs)
+    e2e_ms = ctx.timer_end()
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_per_step = e2e_ms / args.steps
+    h2d = W.h2d_bytes(inputs)
+    d2h = d2h_bytes(last)
+
+    line = None
+    if rank == 0:
+        # ---- live per-class kernel profile (one extra pass, not part of any headline number) ----
+        ctx.profile_begin()
+        W.run_device(ctx, srs, inputs, resident=resident)
+        prof = ctx.profile_end()
+        pk, pk_kind = peaks()
+        roof = W.roofline_from_profile(prof, inputs, pk, pk_kind, ctx)
+        units = W.count_units(inputs)
+        line = {"metric": metric_name(args.config), "value": ms_per_step / 1e3 / world, "unit": "s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64x4 Montgomery (BN254 Fr/Fq)", "data": "synthetic",
+                "config": W.config_dict(args.config, inputs, world),
+                "clocks": clocks,
+                "e2e": {"value": e2e_per_step / 1e3 / world, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches),
+                "wall_ms_per_step": wall_ms / args.steps,
+                "units_per_step": units,
+                "roofline": roof["dominant"], "kernel_classes": roof["classes"], "kernel_sweep": roof["sweep"]}
+        if world == 1 and not args.no_cpu:
+            rlc = MultilinearPolynomial.random(ctx, n, inputs["rlc_seed"])
+            rlc_host = rlc.to_host(); rlc.free()
+            from oracle import cpu as ORC
+            secs, sample = cpu_pass_seconds(srs.to_host(), inputs, rlc_host, 30.0)
+            line["cpu_baseline"] = {"value": secs, "unit": "s", "cores": ORC.num_threads(), "kind": "port", "sample": sample}
+    W.free_resident(resident)
+    srs.free()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="nanoGPT", choices=["nanoGPT", "microgpt"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_device_arm(args)
+
+
+if __name__ == "__main__":
+    main()

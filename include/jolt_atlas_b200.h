@@ -215,6 +215,13 @@ int32_t ja_hyperkzg_open(ja_ctx*, const ja_srs*, const ja_poly* poly, const uint
 /* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see this stream). */
 int32_t ja_timer_begin(ja_ctx*);
 int32_t ja_timer_end(ja_ctx*, float* out_ms);
+/* Per-kernel-class launch profile: between begin and end every kernel launch of this context is bracketed by CUDA
+ * events on the context's stream; end returns, per class k < ja_profile_class_count(), the number of launches and
+ * the summed device milliseconds.  Adds event overhead: never wrap a headline timing in it. */
+int32_t ja_profile_begin(ja_ctx*);
+int32_t ja_profile_end(ja_ctx*, uint64_t* out_launches, double* out_ms, size_t n_classes);
+int32_t ja_profile_class_count(void);
+const char* ja_profile_class_name(int32_t k);
 /* Re-run ONE kernel `iters` times back to back on resident synthetic operands of 2^log_n Fr (inputs are
  * never consumed, so every iteration does identical work; 2^log_n * 32 B should exceed the 126 MB L2).
  *   which: 0 = bind LowToHigh, 1 = bind HighToLow (n_polys polys per launch),

@@ -63,6 +63,10 @@ SIGNATURES = {
     "ja_hyperkzg_open_witness": (C.c_int32, [vp, vp, u64p, u64p, u64p, i32p]),
     "ja_hyperkzg_open_free": (None, [vp, vp]),
     "ja_hyperkzg_open": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, C.c_char_p, u32p, u64p, i32p, u64p, i32p, u64p]),
+    "ja_profile_begin": (C.c_int32, [vp]),
+    "ja_profile_end": (C.c_int32, [vp, u64p, C.POINTER(C.c_double), C.c_size_t]),
+    "ja_profile_class_count": (C.c_int32, []),
+    "ja_profile_class_name": (C.c_char_p, [C.c_int32]),
     "ja_timer_begin": (C.c_int32, [vp]),
     "ja_timer_end": (C.c_int32, [vp, C.POINTER(C.c_float)]),
     "ja_bench_kernel": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),

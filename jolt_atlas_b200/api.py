@@ -79,6 +79,18 @@ class Context:
         check(self._lib.ja_timer_end(self._h, C.byref(out)))
         return out.value
 
+    def profile_begin(self):
+        check(self._lib.ja_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """{class name: {"launches": n, "ms": summed device ms}} for the launches since profile_begin."""
+        k = int(self._lib.ja_profile_class_count())
+        cnt = np.zeros(k, dtype=np.uint64)
+        ms = np.zeros(k, dtype=np.float64)
+        check(self._lib.ja_profile_end(self._h, _u64p(cnt), ms.ctypes.data_as(C.POINTER(C.c_double)), k))
+        return {self._lib.ja_profile_class_name(i).decode(): {"launches": int(cnt[i]), "ms": float(ms[i])}
+                for i in range(k) if cnt[i]}
+
     def bench_kernel(self, which: int, log_n: int, n_polys: int = 1, iters: int = 20) -> float:
         """Average device milliseconds per launch of one kernel on resident synthetic operands."""
         out = C.c_float()

@@ -6,7 +6,57 @@
 static thread_local std::string g_last_error;
 std::string& ja_err_slot() { return g_last_error; }
 
+static const char* const kClassNames[KC_COUNT] = {
+    "bind", "round_eval_split_eq", "round_eval_product", "round_eval_dot", "round_sum", "eq_table", "tensor_fold",
+    "convert_gather", "msm_sort", "msm_accumulate", "msm_reduce", "hkzg_univariate_eval", "hkzg_lincomb", "hkzg_witness",
+    "srs_generate", "sumcheck_fused", "scatter_add", "misc"};
+
+void ja_prof_pre(ja_ctx* c, int cls) {
+  c->launches++;
+  if (!c->prof_on) return;
+  const size_t i = c->prof_cls.size();
+  while (c->prof_events.size() < 2 * (i + 1)) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { c->prof_on = false; return; }
+    c->prof_events.push_back(e);
+  }
+  c->prof_cls.push_back(cls);
+  cudaEventRecord(c->prof_events[2 * i], c->stream);
+}
+void ja_prof_post(ja_ctx* c) {
+  if (!c->prof_on || c->prof_cls.empty()) return;
+  cudaEventRecord(c->prof_events[2 * (c->prof_cls.size() - 1) + 1], c->stream);
+}
+
 extern "C" {
+
+int32_t ja_profile_begin(ja_ctx* c) {
+  JA_REQUIRE(c, "ja_profile_begin: null ctx");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  c->prof_cls.clear();
+  c->prof_on = true;
+  return JA_OK;
+}
+
+int32_t ja_profile_end(ja_ctx* c, uint64_t* out_launches, double* out_ms, size_t n_classes) {
+  JA_REQUIRE(c && out_launches && out_ms, "ja_profile_end: null argument");
+  JA_REQUIRE(n_classes >= (size_t)KC_COUNT, "ja_profile_end: output arrays shorter than ja_profile_class_count()");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  c->prof_on = false;
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t k = 0; k < n_classes; k++) { out_launches[k] = 0; out_ms[k] = 0; }
+  for (size_t i = 0; i < c->prof_cls.size(); i++) {
+    float ms = 0;
+    JA_CUDA(cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]));
+    out_launches[c->prof_cls[i]]++;
+    out_ms[c->prof_cls[i]] += ms;
+  }
+  c->prof_cls.clear();
+  return JA_OK;
+}
+
+int32_t ja_profile_class_count(void) { return KC_COUNT; }
+const char* ja_profile_class_name(int32_t k) { return k >= 0 && k < KC_COUNT ? kClassNames[k] : ""; }
 
 void ja_last_error(char* buf, size_t cap) {
   if (!buf || !cap) return;
@@ -46,6 +96,7 @@ void ja_shutdown(ja_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
   cudaFreeHost(c->h_pinned);
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -92,8 +143,7 @@ int32_t ja_poly_from_i32(ja_ctx* c, const int32_t* z, size_t n, ja_poly** out) {
   st = dev_alloc(c, n * sizeof(int), (void**)&tmp);
   if (st) return st;
   JA_CUDA(cudaMemcpyAsync(tmp, z, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  k_i32_to_fr<<<grid_for(n), kBlock, 0, c->stream>>>(tmp, (*out)->buf[0], n);
-  c->launches++;
+  JA_LAUNCH(c, KC_CONVERT, k_i32_to_fr<<<grid_for(n), kBlock, 0, c->stream>>>(tmp, (*out)->buf[0], n));
   JA_CUDA(cudaGetLastError());
   dev_free(c, tmp);
   JA_CUDA(cudaStreamSynchronize(c->stream));
@@ -112,8 +162,7 @@ int32_t ja_poly_from_lookup(ja_ctx* c, const uint64_t* table, size_t K, const ui
   if ((st = dev_alloc(c, n * sizeof(uint32_t), (void**)&d_idx))) return st;
   JA_CUDA(cudaMemcpyAsync(d_table, table, K * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
   JA_CUDA(cudaMemcpyAsync(d_idx, idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  k_gather_small_table<<<grid_for(n), kBlock, 0, c->stream>>>(d_table, d_idx, n, (*out)->buf[0]);
-  c->launches++;
+  JA_LAUNCH(c, KC_CONVERT, k_gather_small_table<<<grid_for(n), kBlock, 0, c->stream>>>(d_table, d_idx, n, (*out)->buf[0]));
   JA_CUDA(cudaGetLastError());
   dev_free(c, d_table); dev_free(c, d_idx);
   JA_CUDA(cudaStreamSynchronize(c->stream));
@@ -185,9 +234,8 @@ int32_t ja_bind_many(ja_ctx* c, ja_poly* const* polys, size_t n_polys, const uin
       cnt++;
     }
     dim3 grid(grid_for(half), (unsigned)cnt);
-    if (order == JA_LOW_TO_HIGH) k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
-    else                         k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
-    c->launches++;
+    if (order == JA_LOW_TO_HIGH) JA_LAUNCH(c, KC_BIND, k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
+    else                         JA_LAUNCH(c, KC_BIND, k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
     JA_CUDA(cudaGetLastError());
     for (size_t q = 0; q < cnt; q++) {
       ja_poly* p = polys[done + q];
@@ -230,13 +278,11 @@ static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& sca
   EqLevelsArgs a;
   a.w[0] = d_r; a.m[0] = (int)mh; a.rev[0] = 0; a.buf[0] = lv[0]; a.scale[0] = to_dev(scale);
   a.w[1] = d_r + mh; a.m[1] = (int)ml; a.rev[1] = 0; a.buf[1] = lv[1]; a.scale[1] = to_dev(host::FR_ONE);
-  k_eq_levels<<<2, 1024, 0, c->stream>>>(a);
-  c->launches++;
+  JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels<<<2, 1024, 0, c->stream>>>(a));
   JA_CUDA(cudaGetLastError());
   const size_t n = size_t(1) << m;
-  k_eq_expand<<<grid_for(n), kBlock, 0, c->stream>>>(lv[0] + ((size_t(1) << mh) - 1), lv[1] + ((size_t(1) << ml) - 1),
-                                                    (int)ml, n, out);
-  c->launches++;
+  JA_LAUNCH(c, KC_EQ_TABLE, k_eq_expand<<<grid_for(n), kBlock, 0, c->stream>>>(lv[0] + ((size_t(1) << mh) - 1), lv[1] + ((size_t(1) << ml) - 1),
+                                                    (int)ml, n, out));
   JA_CUDA(cudaGetLastError());
   // h_pinned is reused by later calls: make sure the H2D copy has been consumed
   JA_CUDA(cudaStreamSynchronize(c->stream));
@@ -298,8 +344,7 @@ int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, co
   const int rev = order == JA_HIGH_TO_LOW ? 1 : 0;
   a.w[0] = d_w + off_out; a.m[0] = (int)n_out_vars; a.rev[0] = rev; a.buf[0] = s->out_levels; a.scale[0] = to_dev(host::FR_ONE);
   a.w[1] = d_w + off_in;  a.m[1] = (int)n_in_vars;  a.rev[1] = rev; a.buf[1] = s->in_levels;  a.scale[1] = to_dev(host::FR_ONE);
-  k_eq_levels<<<2, 1024, 0, c->stream>>>(a);
-  c->launches++;
+  JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels<<<2, 1024, 0, c->stream>>>(a));
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaStreamSynchronize(c->stream));
   dev_free(c, d_w);
@@ -384,9 +429,8 @@ static void launch_s(ja_ctx* c, const EvalPolys& P, const ja_spliteq* eq, size_t
   size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
   size_t tpb = (tiles + grid - 1) / grid;
   grid = (tiles + tpb - 1) / tpb;
-  k_round_eval_s<KID><<<(unsigned)grid, kBlock, 0, c->stream>>>(P, eq->e_out(), eq->e_in(), bits_in, G, tpb,
-                                                                c->d_partials, c->d_counter, c->d_out);
-  c->launches++;
+  JA_LAUNCH(c, KC_ROUND_EVAL_S, k_round_eval_s<KID><<<(unsigned)grid, kBlock, 0, c->stream>>>(P, eq->e_out(), eq->e_in(), bits_in, G, tpb,
+                                                                c->d_partials, c->d_counter, c->d_out));
 }
 
 extern "C" {
@@ -452,27 +496,24 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
     gx = (tiles + tpb - 1) / tpb;
     dim3 grid((unsigned)gx, chunks);
     if (kernel_id == JA_EVAL_POW)
-      k_round_eval_prod<true><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter);
+      JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod<true><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter));
     else
-      k_round_eval_prod<false><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter);
-    c->launches++;
+      JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod<false><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter));
   } else if (fam == FAM_D) {
     unsigned grid = grid_for(G);
     if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
     if (kernel_id == JA_EVAL_DOT2)
-      k_round_eval_dot<2><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out);
+      JA_LAUNCH(c, KC_ROUND_EVAL_DOT, k_round_eval_dot<2><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out));
     else
-      k_round_eval_dot<3><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out);
-    c->launches++;
+      JA_LAUNCH(c, KC_ROUND_EVAL_DOT, k_round_eval_dot<3><<<grid, kBlock, 0, c->stream>>>(P, G, c->d_partials, c->d_counter, c->d_out));
   } else {
     SumPolys SP;
     for (int i = 0; i < kMaxProdPolys; i++) SP.p[i] = i < (int)n_polys ? polys[i]->data() : nullptr;
     unsigned gx = grid_for(G);
     if (gx > (unsigned)kSMs * 2) gx = kSMs * 2;
     dim3 grid(gx, (unsigned)n_polys);
-    if (kernel_id == JA_EVAL_SUM1) k_round_sum<2><<<grid, kBlock, 0, c->stream>>>(SP, G, c->d_partials, c->d_out, c->d_counter);
-    else                           k_round_sum<1><<<grid, kBlock, 0, c->stream>>>(SP, G, c->d_partials, c->d_out, c->d_counter);
-    c->launches++;
+    if (kernel_id == JA_EVAL_SUM1) JA_LAUNCH(c, KC_ROUND_SUM, k_round_sum<2><<<grid, kBlock, 0, c->stream>>>(SP, G, c->d_partials, c->d_out, c->d_counter));
+    else                           JA_LAUNCH(c, KC_ROUND_SUM, k_round_sum<1><<<grid, kBlock, 0, c->stream>>>(SP, G, c->d_partials, c->d_out, c->d_counter));
     n_dev = n_polys;
     JA_REQUIRE(aux_fr == nullptr || n_aux == n_polys, "ja_round_eval: SUM1 takes one gamma per polynomial");
   }
@@ -504,8 +545,7 @@ int32_t ja_poly_evaluate(ja_ctx* c, const ja_poly* p, const uint64_t* point, siz
   if (st) return st;
   unsigned grid = grid_for(p->len);
   if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
-  k_dot_full<<<grid, kBlock, 0, c->stream>>>(p->data(), eq->data(), p->len, c->d_partials, c->d_counter, c->d_out);
-  c->launches++;
+  JA_LAUNCH(c, KC_ROUND_EVAL_DOT, k_dot_full<<<grid, kBlock, 0, c->stream>>>(p->data(), eq->data(), p->len, c->d_partials, c->d_counter, c->d_out));
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   JA_CUDA(cudaStreamSynchronize(c->stream));
@@ -532,8 +572,7 @@ int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols
   if (st) return st;
   if (transpose) {
     size_t threads = rows * 32;
-    k_fold_rows<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(dA, rows, cols, eq->data(), (*out)->buf[0]);
-    c->launches++;
+    JA_LAUNCH(c, KC_TENSOR_FOLD, k_fold_rows<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(dA, rows, cols, eq->data(), (*out)->buf[0]));
   } else {
     // split rows so that the grid has >= ~4 waves worth of threads
     size_t col_blocks = (cols + kBlock - 1) / kBlock;
@@ -544,9 +583,8 @@ int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols
     st = dev_alloc(c, slices * cols * sizeof(Fr), (void**)&partial);
     if (st) return st;
     dim3 grid((unsigned)col_blocks, (unsigned)slices);
-    k_fold_cols<<<grid, kBlock, 0, c->stream>>>(dA, rows, cols, eq->data(), rps, partial);
-    k_fold_cols_finish<<<(unsigned)col_blocks, kBlock, 0, c->stream>>>(partial, slices, cols, (*out)->buf[0]);
-    c->launches += 2;
+    JA_LAUNCH(c, KC_TENSOR_FOLD, k_fold_cols<<<grid, kBlock, 0, c->stream>>>(dA, rows, cols, eq->data(), rps, partial));
+    JA_LAUNCH(c, KC_TENSOR_FOLD, k_fold_cols_finish<<<(unsigned)col_blocks, kBlock, 0, c->stream>>>(partial, slices, cols, (*out)->buf[0]));
     dev_free(c, partial);
   }
   JA_CUDA(cudaGetLastError());
@@ -586,8 +624,7 @@ int32_t ja_poly_random(ja_ctx* c, size_t n, uint32_t seed, ja_poly** out) {
   int32_t st = ja_poly_alloc(c, n, out);
   if (st) return st;
   std::lock_guard<std::recursive_mutex> lk(c->mu);
-  k_fill_pseudo<<<kSMs * 8, kBlock, 0, c->stream>>>((*out)->buf[0], n, seed);
-  c->launches++;
+  JA_LAUNCH(c, KC_MISC, k_fill_pseudo<<<kSMs * 8, kBlock, 0, c->stream>>>((*out)->buf[0], n, seed));
   JA_CUDA(cudaGetLastError());
   return JA_OK;
 }
@@ -603,7 +640,7 @@ int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys
   int32_t st;
   for (int i = 0; i < np; i++) {
     if ((st = dev_alloc(c, n * sizeof(Fr), (void**)&src[i]))) return st;
-    k_fill_pseudo<<<kSMs * 8, kBlock, 0, c->stream>>>(src[i], n, 17u + i);
+    JA_LAUNCH(c, KC_MISC, k_fill_pseudo<<<kSMs * 8, kBlock, 0, c->stream>>>(src[i], n, 17u + i));
     if (which <= 1) { if ((st = dev_alloc(c, half * sizeof(Fr), (void**)&dst[i]))) return st; }
   }
   JA_CUDA(cudaGetLastError());
@@ -620,9 +657,8 @@ int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys
       BindArgs args;
       for (int i = 0; i < np; i++) { args.in[i] = src[i]; args.out[i] = dst[i]; }
       dim3 grid(grid_for(half), (unsigned)np);
-      if (which == 0) k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
-      else            k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half);
-      c->launches++;
+      if (which == 0) JA_LAUNCH(c, KC_BIND, k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
+      else            JA_LAUNCH(c, KC_BIND, k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
     } else {
       EvalPolys P; P.p[0] = src[0]; P.p[1] = src[1]; P.p[2] = P.p[3] = nullptr;
       if (which == 2) launch_s<2>(c, P, eq, half);
@@ -630,8 +666,7 @@ int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys
       else {
         unsigned grid = grid_for(half);
         if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
-        k_round_eval_dot<2><<<grid, kBlock, 0, c->stream>>>(P, half, c->d_partials, c->d_counter, c->d_out);
-        c->launches++;
+        JA_LAUNCH(c, KC_ROUND_EVAL_DOT, k_round_eval_dot<2><<<grid, kBlock, 0, c->stream>>>(P, half, c->d_partials, c->d_counter, c->d_out));
       }
     }
   };
@@ -660,11 +695,10 @@ int32_t ja_calibrate_fr_mul(ja_ctx* c, int32_t iters, double* out_mul_per_s) {
   cudaEvent_t e0, e1;
   JA_CUDA(cudaEventCreate(&e0)); JA_CUDA(cudaEventCreate(&e1));
   const unsigned grid = kSMs * 8;
-  k_calib_mul<FrParams><<<grid, kBlock, 0, c->stream>>>(d, 16);   // warm-up
+  JA_LAUNCH(c, KC_MISC, k_calib_mul<FrParams><<<grid, kBlock, 0, c->stream>>>(d, 16));   // warm-up
   JA_CUDA(cudaEventRecord(e0, c->stream));
-  k_calib_mul<FrParams><<<grid, kBlock, 0, c->stream>>>(d, iters);
+  JA_LAUNCH(c, KC_MISC, k_calib_mul<FrParams><<<grid, kBlock, 0, c->stream>>>(d, iters));
   JA_CUDA(cudaEventRecord(e1, c->stream));
-  c->launches += 2;
   JA_CUDA(cudaEventSynchronize(e1));
   float ms = 0;
   JA_CUDA(cudaEventElapsedTime(&ms, e0, e1));

@@ -47,7 +47,22 @@ struct ja_ctx {
   uint64_t* h_pinned = nullptr;    // staging for small D2H/H2D
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // per-kernel-class CUDA-event profile (ja_profile_begin / ja_profile_end; bench.py's roofline leg)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;     // pool, two per recorded launch
+  std::vector<int> prof_cls;                // class of launch i (events 2i, 2i+1)
 };
+
+// Kernel classes of the launch profile.  Keep in sync with kClassNames (capi.cu).
+enum {
+  KC_BIND = 0, KC_ROUND_EVAL_S, KC_ROUND_EVAL_PROD, KC_ROUND_EVAL_DOT, KC_ROUND_SUM, KC_EQ_TABLE, KC_TENSOR_FOLD,
+  KC_CONVERT, KC_MSM_SORT, KC_MSM_ACCUMULATE, KC_MSM_REDUCE, KC_HKZG_EVAL, KC_HKZG_LINCOMB, KC_HKZG_WITNESS, KC_SRS,
+  KC_SUMCHECK_FUSED, KC_SCATTER, KC_MISC, KC_COUNT
+};
+void ja_prof_pre(ja_ctx* c, int cls);
+void ja_prof_post(ja_ctx* c);
+// every kernel launch of the library goes through this: counts it and, when profiling, brackets it with events
+#define JA_LAUNCH(c, cls, ...) do { ja_prof_pre((c), (cls)); __VA_ARGS__; ja_prof_post((c)); } while (0)
 static constexpr int kMaxGrid = kSMs * 8;
 static constexpr int kMaxOut = 32;
 static constexpr size_t kPinnedBytes = 1 << 16;

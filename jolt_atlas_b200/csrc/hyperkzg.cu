@@ -56,8 +56,7 @@ int32_t ja_hyperkzg_open_begin(ja_ctx* c, const ja_srs* srs, const ja_poly* poly
     args.in[0] = h->P + poly_off(n, (int)i);
     args.out[0] = h->P + poly_off(n, (int)i + 1);
     const Challenge ch = to_challenge(point + 4 * (ell - i - 1));
-    k_bind<true><<<dim3(grid_for(half), 1), kBlock, 0, c->stream>>>(args, ch, half);
-    c->launches++;
+    JA_LAUNCH(c, KC_BIND, k_bind<true><<<dim3(grid_for(half), 1), kBlock, 0, c->stream>>>(args, ch, half));
   }
   JA_CUDA(cudaGetLastError());
   // commit_variable_batch(polys[1..]) (kzg.rs:227-243): one bucket pipeline for the l-1 folded polynomials
@@ -90,9 +89,8 @@ int32_t ja_hyperkzg_open_evals(ja_ctx* c, ja_hkzg* h, const uint64_t r[4], uint6
     int log_s = 8;
     while (log_s < 18 && (size_t(8) << log_s) < len) log_s++;
     const unsigned grid = 1u << (log_s - 8);
-    k_univariate_eval3<<<grid, kBlock, 0, c->stream>>>(h->P + poly_off(h->n, k), len, d_tab, log_s, c->d_partials,
-                                                      c->d_counter, d_v + 3 * k);
-    c->launches++;
+    JA_LAUNCH(c, KC_HKZG_EVAL, k_univariate_eval3<<<grid, kBlock, 0, c->stream>>>(h->P + poly_off(h->n, k), len, d_tab, log_s, c->d_partials,
+                                                      c->d_counter, d_v + 3 * k));
   }
   JA_CUDA(cudaGetLastError());
   std::vector<FrH> tmp(3 * (size_t)h->ell);
@@ -128,8 +126,7 @@ int32_t ja_hyperkzg_open_witness(ja_ctx* c, ja_hkzg* h, const uint64_t r[4], con
   JA_CUDA(cudaMemcpyAsync(d_tab, stage + ell, 3 * kPowTab * 32, cudaMemcpyHostToDevice, c->stream));
   unsigned grid = grid_for(n);
   if (grid > (unsigned)kSMs * 8) grid = kSMs * 8;
-  k_hkzg_lincomb<<<grid, kBlock, 0, c->stream>>>(h->P, n, ell, d_q, d_B);
-  c->launches++;
+  JA_LAUNCH(c, KC_HKZG_LINCOMB, k_hkzg_lincomb<<<grid, kBlock, 0, c->stream>>>(h->P, n, ell, d_q, d_B));
   // h_i = witness polynomial of B at u_i (mod.rs:213-229), i = 0..2
   int log_l = 5;
   while ((size_t(1) << log_l) > n) log_l--;
@@ -141,10 +138,9 @@ int32_t ja_hyperkzg_open_witness(ja_ctx* c, ja_hkzg* h, const uint64_t r[4], con
   if ((st = dev_alloc(c, (nb + 1) * sizeof(Fr), (void**)&d_C))) return st;
   for (int p = 0; p < 3; p++) {
     const Fr* tab = d_tab + p * kPowTab;
-    k_witness_block_sums<<<(unsigned)nb, kWitBlock, 0, c->stream>>>(d_B, nchunks, log_l, tab, d_F);
-    k_witness_carry<<<1, 1024, 0, c->stream>>>(d_F, nb, log_per, log_l + 8, tab, d_C);
-    k_witness_write<<<(unsigned)nb, kWitBlock, 0, c->stream>>>(d_B, nchunks, log_l, tab, d_C, d_H + (size_t)p * n);
-    c->launches += 3;
+    JA_LAUNCH(c, KC_HKZG_WITNESS, k_witness_block_sums<<<(unsigned)nb, kWitBlock, 0, c->stream>>>(d_B, nchunks, log_l, tab, d_F));
+    JA_LAUNCH(c, KC_HKZG_WITNESS, k_witness_carry<<<1, 1024, 0, c->stream>>>(d_F, nb, log_per, log_l + 8, tab, d_C));
+    JA_LAUNCH(c, KC_HKZG_WITNESS, k_witness_write<<<(unsigned)nb, kWitBlock, 0, c->stream>>>(d_B, nchunks, log_l, tab, d_C, d_H + (size_t)p * n));
   }
   JA_CUDA(cudaGetLastError());
   // commit_batch(h) (kzg.rs:195-223)

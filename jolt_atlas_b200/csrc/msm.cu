@@ -112,35 +112,34 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   JA_CUDA(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nbt + 1), s));
   JA_CUDA(cudaMemsetAsync(d_bigcount, 0, sizeof(uint32_t), s));
   const uint32_t nthreads_n = (uint32_t)total_n;
-  k_msm_digits<false><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_offsets, nullptr);
+  JA_LAUNCH(c, KC_MSM_SORT, k_msm_digits<false><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_offsets, nullptr));
   STAGE("hist");
-  k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles);
-  k_scan_top<<<1, kScanBlock, 0, s>>>(d_tiles, ntiles);
-  k_scan_add<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles);
+  JA_LAUNCH(c, KC_MSM_SORT, k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles));
+  JA_LAUNCH(c, KC_MSM_SORT, k_scan_top<<<1, kScanBlock, 0, s>>>(d_tiles, ntiles));
+  JA_LAUNCH(c, KC_MSM_SORT, k_scan_add<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles));
   JA_CUDA(cudaMemcpyAsync(d_cursor, d_offsets, sizeof(uint32_t) * (nbt + 1), cudaMemcpyDeviceToDevice, s));
   STAGE("scan");
-  k_msm_digits<true><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_cursor, d_entries);
+  JA_LAUNCH(c, KC_MSM_SORT, k_msm_digits<true><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_cursor, d_entries));
   STAGE("scatter");
   {
     int occ = 4;
     if (const char* e = getenv("JA_MSM_OCC")) occ = atoi(e);
     const unsigned g = ceil_div_u32(nruns, 128);
-    if (occ <= 4) k_msm_accumulate<4><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail);
-    else if (occ == 5) k_msm_accumulate<5><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail);
-    else k_msm_accumulate<6><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail);
+    if (occ <= 4) JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<4><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail));
+    else if (occ == 5) JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<5><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail));
+    else JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<6><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail));
   }
   STAGE("accumulate");
-  k_msm_combine<<<ceil_div_u32(nbt, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, T, d_head, d_tail, d_buckets, d_big,
-                                                      d_bigcount);
-  k_msm_combine_big<<<kSMs * 2, 128, 0, s>>>(d_offsets, T, d_head, d_tail, d_buckets, d_big, d_bigcount);
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_combine<<<ceil_div_u32(nbt, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, T, d_head, d_tail, d_buckets, d_big,
+                                                      d_bigcount));
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_combine_big<<<kSMs * 2, 128, 0, s>>>(d_offsets, T, d_head, d_tail, d_buckets, d_big, d_bigcount));
   STAGE("combine");
   dim3 g_red(ceil_div_u32(max_segs, 128), nwins);
-  k_msm_bucket_reduce<<<g_red, 128, 0, s>>>(d_wins, d_buckets, max_segs, d_seg);
-  k_msm_window_sum<<<nwins, 128, 0, s>>>(d_wins, d_seg, max_segs, d_wsum);
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_bucket_reduce<<<g_red, 128, 0, s>>>(d_wins, d_buckets, max_segs, d_seg));
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_window_sum<<<nwins, 128, 0, s>>>(d_wins, d_seg, max_segs, d_wsum));
   STAGE("bucket_reduce");
-  k_msm_final<<<ceil_div_u32(count, 32), 32, 0, s>>>(d_desc, count, d_wsum, d_res);
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_final<<<ceil_div_u32(count, 32), 32, 0, s>>>(d_desc, count, d_wsum, d_res));
   STAGE("final");
-  c->launches += 11;
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaMemcpyAsync(out, d_res, sizeof(MsmResult) * count, cudaMemcpyDeviceToHost, s));
   JA_CUDA(cudaStreamSynchronize(s));
@@ -203,9 +202,8 @@ int32_t ja_srs_generate(ja_ctx* c, const uint64_t g1_xy[8], const uint64_t beta[
   if (st) { cudaFree(s->points); delete s; return st; }
   G1Aff g; memcpy(g.x.l, g1_xy, 32); memcpy(g.y.l, g1_xy + 4, 32);
   Fr b; memcpy(b.l, beta, 32);
-  k_srs_table<<<1, 1, 0, c->stream>>>(g, table);
-  k_srs_powers<<<ceil_div_u32(n_points, 128), 128, 0, c->stream>>>(table, b, (uint32_t)n_points, s->points);
-  c->launches += 2;
+  JA_LAUNCH(c, KC_SRS, k_srs_table<<<1, 1, 0, c->stream>>>(g, table));
+  JA_LAUNCH(c, KC_SRS, k_srs_powers<<<ceil_div_u32(n_points, 128), 128, 0, c->stream>>>(table, b, (uint32_t)n_points, s->points));
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaStreamSynchronize(c->stream));
   dev_free(c, table);

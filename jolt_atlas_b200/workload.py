@@ -159,8 +159,13 @@ def run_device(ctx, srs, inputs, resident=None):
     uploaded from the host arrays inside this call (the end-to-end path)."""
     from . import api as A
     t = A.Blake2bTranscriptState(b"ONNXProof")
-    out = {"commitments": [], "states": [], "finals": []}
+    out = {"commitments": [], "states": [], "finals": [], "msg_bytes": 0}
     claim = inputs["claim"]
+
+    def _sc(*a, **kw):
+        r = A.sumcheck_prove(*a, **kw)
+        out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])     # round polynomials read back from the device
+        return r
     for i, ni in enumerate(inputs["nodes"]):
         spec = ni.spec
         res = resident["nodes"][i] if resident else None
@@ -179,15 +184,15 @@ def run_device(ctx, srs, inputs, resident=None):
             ra = [A.MultilinearPolynomial.from_lookup(ctx, ni.tables[j], ni.hot_k[j]) for j in range(ni.d_hot)]
         # B. lookup read-raf cycle rounds (ps_shout/mod.rs:464-488): [ra0], degree 2
         p = ra[0].clone()
-        r = A.sumcheck_prove(ctx, A.EvalKernel.IDENT, [p], claim, t, eq_w=ni.eq_w)
+        r = _sc(ctx, A.EvalKernel.IDENT, [p], claim, t, eq_w=ni.eq_w)
         out["finals"].append(r["final_claims"]); p.free()
         # C. RA one-hot checks (shout.rs:399-466): Hamming weight over all chunks, then RA virtualisation = product of d
         hw = [q.clone() for q in ra[:D_CLAMP]]
-        r = A.sumcheck_prove(ctx, A.EvalKernel.SUM1, hw, claim, t, gammas=ni.gammas[:D_CLAMP])
+        r = _sc(ctx, A.EvalKernel.SUM1, hw, claim, t, gammas=ni.gammas[:D_CLAMP])
         out["finals"].append(r["final_claims"])
         for q in hw:
             q.free()
-        r = A.sumcheck_prove(ctx, A.EvalKernel.PROD, ra[:D_CLAMP], claim, t, eq_w=ni.eq_w)
+        r = _sc(ctx, A.EvalKernel.PROD, ra[:D_CLAMP], claim, t, eq_w=ni.eq_w)
         out["finals"].append(r["final_claims"])
         # D. the operator's own sumcheck
         if spec.kind == "einsum":
@@ -196,7 +201,7 @@ def run_device(ctx, srs, inputs, resident=None):
             eq_c = A.EqPolynomial.evals(ctx, ni.eq_cols)
             left = A.tensor_fold_i32(ctx, ni.A, eq_r, transpose=False)     # (m x k) folded over rows -> k
             right = A.tensor_fold_i32(ctx, ni.B, eq_c, transpose=True)     # (k x n) folded over columns -> k
-            r = A.sumcheck_prove(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
+            r = _sc(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
             out["finals"].append(r["final_claims"])
             for q in (eq_r, eq_c, left, right):
                 q.free()
@@ -206,16 +211,16 @@ def run_device(ctx, srs, inputs, resident=None):
             else:
                 a, b = A.MultilinearPolynomial.from_i32(ctx, ni.A), A.MultilinearPolynomial.from_i32(ctx, ni.B)
             kind = A.EvalKernel.MUL if spec.kind == "mul" else A.EvalKernel.ADD
-            r = A.sumcheck_prove(ctx, kind, [a, b], claim, t, eq_w=ni.eq_w)
+            r = _sc(ctx, kind, [a, b], claim, t, eq_w=ni.eq_w)
             out["finals"].append(r["final_claims"])
             a.free(); b.free()
         if ni.d_hot > D_CLAMP:
             # E. remainder range check cycle rounds (identity_range_check.rs:332-358)
             p = ra[D_CLAMP].clone()
-            r = A.sumcheck_prove(ctx, A.EvalKernel.IDENT, [p], claim, t, eq_w=ni.eq_w)
+            r = _sc(ctx, A.EvalKernel.IDENT, [p], claim, t, eq_w=ni.eq_w)
             out["finals"].append(r["final_claims"]); p.free()
             # F. remainder RA checks: product of d = 4
-            r = A.sumcheck_prove(ctx, A.EvalKernel.PROD, ra[D_CLAMP:], claim, t, eq_w=ni.eq_w)
+            r = _sc(ctx, A.EvalKernel.PROD, ra[D_CLAMP:], claim, t, eq_w=ni.eq_w)
             out["finals"].append(r["final_claims"])
         for q in ra:
             q.free()
@@ -263,3 +268,100 @@ def count_units(inputs) -> dict:
         rounds += 3 * lt + (2 * lt if ni.d_hot > D_CLAMP else 0)
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
     return {"sumcheck_rounds": rounds, "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"]}
+
+
+# ---- measurement helpers (bench.py) -------------------------------------------------------------------------------
+def sumcheck_list(inputs):
+    """(kernel class of the round evaluation, number of polynomials, initial length) of every sumcheck of one pass, in order."""
+    out = []
+    for ni in inputs["nodes"]:
+        T = 1 << ni.spec.log_t
+        out.append(("round_eval_split_eq", 1, T))
+        out.append(("round_sum", D_CLAMP, T))
+        out.append(("round_eval_product", D_CLAMP, T))
+        if ni.spec.kind == "einsum":
+            out.append(("round_eval_dot", 2, 1 << (ni.spec.k - 1).bit_length()))
+        else:
+            out.append(("round_eval_split_eq", 2, T))
+        if ni.d_hot > D_CLAMP:
+            out.append(("round_eval_split_eq", 1, T))
+            out.append(("round_eval_product", D_REM, T))
+    return out
+
+
+def algorithmic_bytes(inputs) -> dict:
+    """Algorithmic HBM bytes of one pass per kernel class: bind of a length-n polynomial reads 32n and writes
+    16n; a round evaluation reads 32n per participating polynomial (the Hamming-weight sum reads the even half: 16n)."""
+    b = {"bind": 0, "round_eval_split_eq": 0, "round_eval_product": 0, "round_eval_dot": 0, "round_sum": 0}
+    for cls, npoly, n0 in sumcheck_list(inputs):
+        rounds = n0.bit_length() - 1
+        tot = sum(n0 >> j for j in range(rounds))          # sum of the current lengths over the rounds
+        b["bind"] += 48 * tot * npoly
+        b[cls] += (16 if cls == "round_sum" else 32) * tot * npoly
+    n = 1 << inputs["ell"]
+    b["bind"] += 48 * sum(n >> j for j in range(inputs["ell"] - 1))        # HyperKZG folds (hyperkzg/mod.rs:415-428)
+    return b
+
+
+def algorithmic_fieldmuls(inputs) -> dict:
+    """Nominal Fq / Fr multiplications of the compute-bound classes: 10 Fq-mul per mixed addition (XYZZ),
+    d^2 Fr-mul per pair for a product-of-d round."""
+    adds = sum(ni.d_hot * (1 << ni.spec.log_t) for ni in inputs["nodes"])
+    n = 1 << inputs["ell"]
+    msm_pairs = 4 * n
+    nwin = 16                                         # 255 bits / c = 16 signed windows
+    prod = 0
+    for cls, npoly, n0 in sumcheck_list(inputs):
+        if cls == "round_eval_product":
+            prod += npoly * npoly * (n0 - 1)          # sum over rounds of (n/2) pairs = n0 - 1
+    return {"msm_accumulate": 10 * (adds + msm_pairs * nwin), "round_eval_product": prod}
+
+
+def config_dict(config: str, inputs, world: int = 1) -> dict:
+    u = count_units(inputs)
+    return {"workload": "%s-shaped prove pass: %d nodes (one-hot commits K=16, lookup/RA/operator/range-check sumchecks, "
+                        "chained Blake2b transcript) + HyperKZG open ell=%d; synthetic i8-range tensors" %
+                        (config, len(inputs["nodes"]), inputs["ell"]),
+            "sumcheck_rounds": u["sumcheck_rounds"], "onehot_point_additions": u["onehot_point_additions"],
+            "open_msm_pairs": u["open_msm_pairs"],
+            "l2": "no explicit flush: one pass streams %.0f MB of polynomial data through a 126 MB L2" %
+                  (sum(algorithmic_bytes(inputs).values()) / 1e6),
+            "parallelism": "1 GPU" if world == 1 else "%d replicas, one independent proof per GPU (no data-path collective)" % world}
+
+
+def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx) -> dict:
+    """Per-class achieved rates of one profiled pass + a large-n sweep of the streaming kernels."""
+    ab = algorithmic_bytes(inputs)
+    am = algorithmic_fieldmuls(inputs)
+    total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    hbm = float(peaks["hbm_gbs"])
+    mul_peak = ctx.calibrate_fr_mul(2000) / 1e9       # Gmul/s, register-resident Montgomery loop on this GPU
+    classes = {}
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4)}
+        if name in ab and v["ms"] > 0:
+            row["algorithmic_bytes"] = ab[name]
+            row["GBps"] = round(ab[name] / v["ms"] / 1e6, 2)
+        if name in am and v["ms"] > 0:
+            row["field_muls"] = am[name]
+            row["Gmul_per_s"] = round(am[name] / v["ms"] / 1e6, 2)
+        classes[name] = row
+    dom_name = next(iter(classes))
+    dom = classes[dom_name]
+    if dom_name in am:
+        dominant = {"kernel": dom_name, "bound": "int32 field-mul (no tensor cores on this path)", "achieved": dom["Gmul_per_s"],
+                    "peak": round(mul_peak, 2), "unit": "Gmul/s", "frac": round(dom["Gmul_per_s"] / mul_peak, 4),
+                    "traffic": None, "peak_source": "calibrated live: register-resident Montgomery product loop",
+                    "per_launch_ms": round(dom["ms"] / dom["launches"], 5), "share_of_step": dom["share"]}
+    else:
+        gb = dom.get("GBps", 0.0)
+        dominant = {"kernel": dom_name, "bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": round(gb / hbm, 4),
+                    "traffic": None, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peaks_kind,
+                    "per_launch_ms": round(dom["ms"] / dom["launches"], 5), "share_of_step": dom["share"]}
+    sweep = []
+    for which, name, bytes_per_n in ((0, "bind_low_to_high", 48), (1, "bind_high_to_low", 48), (2, "round_eval_mul", 64)):
+        for log_n in (24, 26):
+            ms = ctx.bench_kernel(which, log_n, 1, 10)
+            gb = bytes_per_n * (1 << log_n) / ms / 1e6
+            sweep.append({"kernel": name, "log_n": log_n, "ms": round(ms, 4), "GBps": round(gb, 1), "frac_hbm": round(gb / hbm, 4)})
+    return {"dominant": dominant, "classes": classes, "sweep": sweep, "fr_mul_peak_Gmul_s": mul_peak}
