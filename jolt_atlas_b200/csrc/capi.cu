@@ -8,7 +8,7 @@ std::string& ja_err_slot() { return g_last_error; }
 
 static const char* const kClassNames[KC_COUNT] = {
     "bind", "round_eval_split_eq", "round_eval_product", "round_eval_dot", "round_sum", "eq_table", "tensor_fold",
-    "convert_gather", "msm_sort", "msm_accumulate", "msm_reduce", "hkzg_univariate_eval", "hkzg_lincomb", "hkzg_witness",
+    "convert_gather", "msm_sort", "msm_accumulate", "msm_reduce", "onehot_point_sum", "hkzg_univariate_eval", "hkzg_lincomb", "hkzg_witness",
     "srs_generate", "sumcheck_fused", "scatter_add", "misc"};
 
 void ja_prof_pre(ja_ctx* c, int cls) {
@@ -438,7 +438,22 @@ extern "C" {
 int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
                       const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32,
                       uint64_t* out_evals, size_t n_out) {
-  JA_REQUIRE(c && polys && out_evals, "ja_round_eval: null argument");
+  JA_REQUIRE(c && out_evals, "ja_round_eval: null argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);      // launch + collect share the pinned staging buffer
+  RoundEvalPending pend;
+  int32_t st = ja_round_eval_launch(c, kernel_id, polys, n_polys, eq, aux_fr, n_aux, aux_u32, n_out, &pend);
+  if (st) return st;
+  return ja_round_eval_collect(c, pend, out_evals);
+}
+
+}  // extern "C"
+
+// The asynchronous half: validates, launches the kernel and enqueues the D2H copy of the reduced sums into the
+// context's pinned staging buffer.  The caller may do host work (e.g. the round's field inversion) before collect.
+int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
+                             const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32, size_t n_out,
+                             RoundEvalPending* pend) {
+  JA_REQUIRE(c && polys && pend, "ja_round_eval: null argument");
   JA_REQUIRE(n_polys >= 1 && n_polys <= (size_t)kMaxProdPolys, "ja_round_eval: unsupported number of polynomials");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
@@ -467,6 +482,7 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
   JA_REQUIRE(n_out == want_out, "ja_round_eval: wrong n_out for kernel_id");
   JA_REQUIRE(n_polys == want_polys, "ja_round_eval: wrong n_polys for kernel_id");
   size_t n_dev = n_out;      // Fr values to copy back from d_out
+  int prod_lanes = 0, prod_d = 0;
   if (fam == FAM_S || fam == FAM_PROD) {
     JA_REQUIRE(eq != nullptr, "ja_round_eval: split-eq handle required for family S");
     JA_REQUIRE(eq->order == JA_LOW_TO_HIGH, "ja_round_eval: family S expects a LowToHigh split-eq");
@@ -488,17 +504,40 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
     JA_REQUIRE(d >= 2 && d <= kMaxProdPolys, "ja_round_eval: product degree must be in 2..32");
     ProdPolys PP;
     for (int i = 0; i < kMaxProdPolys; i++) PP.p[i] = i < (int)n_polys ? polys[i]->data() : nullptr;
-    const unsigned chunks = (unsigned)((d + kProdChunk - 1) / kProdChunk);
     const int bits_in = eq->in_len - 1;
-    size_t tiles = (G + kBlock - 1) / kBlock;
-    size_t gx = tiles < (size_t)kSMs * 2 ? tiles : (size_t)kSMs * 2;
-    size_t tpb = (tiles + gx - 1) / gx;
-    gx = (tiles + tpb - 1) / tpb;
-    dim3 grid((unsigned)gx, chunks);
-    if (kernel_id == JA_EVAL_POW)
-      JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod<true><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter));
-    else
-      JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod<false><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter));
+    const bool same = kernel_id == JA_EVAL_POW;
+    if (d <= 16) {
+      // warp-transposed kernel: L lanes per pair, one output point per lane
+      int L = 2; while (L < d) L <<= 1;
+      const size_t gpb = (size_t)kBlock / L;
+      size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
+      ppb = (ppb + gpb - 1) / gpb * gpb;
+      const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
+#define JA_PROD_T(LL)                                                                                                   \
+      if (same) JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod_t<LL, true><<<grid, kBlock, 0, c->stream>>>(       \
+                    PP, d, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_out, c->d_counter));           \
+      else JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod_t<LL, false><<<grid, kBlock, 0, c->stream>>>(            \
+               PP, d, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_out, c->d_counter))
+      switch (L) {
+        case 2: JA_PROD_T(2); break;
+        case 4: JA_PROD_T(4); break;
+        case 8: JA_PROD_T(8); break;
+        default: JA_PROD_T(16); break;
+      }
+#undef JA_PROD_T
+      prod_lanes = L; prod_d = d; n_dev = (size_t)L;
+    } else {
+      const unsigned chunks = (unsigned)((d + kProdChunk - 1) / kProdChunk);
+      size_t tiles = (G + kBlock - 1) / kBlock;
+      size_t gx = tiles < (size_t)kSMs * 2 ? tiles : (size_t)kSMs * 2;
+      size_t tpb = (tiles + gx - 1) / gx;
+      gx = (tiles + tpb - 1) / tpb;
+      dim3 grid(gx, chunks);
+      if (same)
+        JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod<true><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter));
+      else
+        JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod<false><<<grid, kBlock, 0, c->stream>>>(PP, d, eq->e_out(), eq->e_in(), bits_in, G, tpb, c->d_partials, c->d_out, c->d_counter));
+    }
   } else if (fam == FAM_D) {
     unsigned grid = grid_for(G);
     if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
@@ -519,19 +558,31 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
   }
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, n_dev * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  pend->n_dev = n_dev; pend->n_out = n_out; pend->n_polys = n_polys; pend->fam_sum = fam == FAM_SUM; pend->aux_fr = aux_fr;
+  pend->prod_lanes = prod_lanes; pend->prod_d = prod_d;
+  return JA_OK;
+}
+
+int32_t ja_round_eval_collect(ja_ctx* c, const RoundEvalPending& pend, uint64_t* out_evals) {
   JA_CUDA(cudaStreamSynchronize(c->stream));
-  if (fam == FAM_SUM) {
+  if (pend.fam_sum) {
     // hamming_weight.rs:126-133: sum_i gamma_i * (sum_j ra_i[2j]); O(d) scalar glue on the d returned sums
     const FrH* sums = reinterpret_cast<const FrH*>(c->h_pinned);
     FrH acc = host::FR_ZERO;
-    for (size_t i = 0; i < n_polys; i++)
-      acc = host::add(acc, aux_fr ? host::mul(host::from_limbs(aux_fr + 4 * i), sums[i]) : sums[i]);
+    for (size_t i = 0; i < pend.n_polys; i++)
+      acc = host::add(acc, pend.aux_fr ? host::mul(host::from_limbs(pend.aux_fr + 4 * i), sums[i]) : sums[i]);
     memcpy(out_evals, acc.l, 32);
+  } else if (pend.prod_lanes) {
+    // lane j of the transposed kernel holds grid point j: X = j + 1 for j < L - 1, X = inf at j = L - 1
+    memcpy(out_evals, c->h_pinned, (size_t)(pend.prod_d - 1) * sizeof(Fr));
+    memcpy(out_evals + 4 * (pend.prod_d - 1), c->h_pinned + 4 * (pend.prod_lanes - 1), sizeof(Fr));
   } else {
-    memcpy(out_evals, c->h_pinned, n_out * sizeof(Fr));
+    memcpy(out_evals, c->h_pinned, pend.n_out * sizeof(Fr));
   }
   return JA_OK;
 }
+
+extern "C" {
 
 // ---- MLE evaluation ----------------------------------------------------------------------------------
 int32_t ja_poly_evaluate(ja_ctx* c, const ja_poly* p, const uint64_t* point, size_t m, uint64_t out[4]) {

@@ -56,7 +56,7 @@ struct ja_ctx {
 // Kernel classes of the launch profile.  Keep in sync with kClassNames (capi.cu).
 enum {
   KC_BIND = 0, KC_ROUND_EVAL_S, KC_ROUND_EVAL_PROD, KC_ROUND_EVAL_DOT, KC_ROUND_SUM, KC_EQ_TABLE, KC_TENSOR_FOLD,
-  KC_CONVERT, KC_MSM_SORT, KC_MSM_ACCUMULATE, KC_MSM_REDUCE, KC_HKZG_EVAL, KC_HKZG_LINCOMB, KC_HKZG_WITNESS, KC_SRS,
+  KC_CONVERT, KC_MSM_SORT, KC_MSM_ACCUMULATE, KC_MSM_REDUCE, KC_ONEHOT_SUM, KC_HKZG_EVAL, KC_HKZG_LINCOMB, KC_HKZG_WITNESS, KC_SRS,
   KC_SUMCHECK_FUSED, KC_SCATTER, KC_MISC, KC_COUNT
 };
 void ja_prof_pre(ja_ctx* c, int cls);
@@ -104,6 +104,13 @@ struct ja_spliteq {
   const Fr* e_out() const { return out_levels + ((size_t(1) << (out_len - 1)) - 1); }
   const Fr* e_in() const { return in_levels + ((size_t(1) << (in_len - 1)) - 1); }
 };
+
+// ja_round_eval split at its synchronisation point (capi.cu); the sumcheck driver overlaps host math with the kernel
+struct RoundEvalPending { size_t n_dev, n_out, n_polys; bool fam_sum; const uint64_t* aux_fr; int prod_lanes, prod_d; };
+int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
+                             const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32, size_t n_out,
+                             RoundEvalPending* pend);
+int32_t ja_round_eval_collect(ja_ctx* c, const RoundEvalPending& pend, uint64_t* out_evals);
 
 static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
 static inline int log2z(size_t n) { int k = 0; while ((size_t(1) << k) < n) k++; return k; }

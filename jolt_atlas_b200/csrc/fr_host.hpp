@@ -94,9 +94,55 @@ static inline FrH pow(const FrH& a, const uint64_t e[4]) {
   }
   return r;
 }
-static inline FrH inv(const FrH& a) {  // a^(p-2); inverse of 0 is 0
+static inline FrH inv_fermat(const FrH& a) {  // a^(p-2); inverse of 0 is 0
   uint64_t e[4] = {FR_P[0] - 2, FR_P[1], FR_P[2], FR_P[3]};
   return pow(a, e);
+}
+// Inverse by the binary extended Euclidean algorithm on the Montgomery limbs read as a plain integer x = a*R:
+// it yields x^-1 = a^-1 * R^-1 (mod p); one Montgomery product with R^3 turns that into a^-1 * R.
+// ~5x faster than the Fermat ladder; the per-round field division of gruen_poly_deg_2/3 sits on the critical path
+// between two kernel launches.  Inverse of 0 is 0 (as ark's `inverse().unwrap_or(zero)` call sites expect).
+namespace detail {
+static inline bool is_one(const uint64_t* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; }
+static inline bool is_even(const uint64_t* a) { return (a[0] & 1) == 0; }
+static inline void shr1(uint64_t* a, uint64_t top) {
+  a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63);
+  a[2] = (a[2] >> 1) | (a[3] << 63); a[3] = (a[3] >> 1) | (top << 63);
+}
+static inline uint64_t add4(uint64_t* a, const uint64_t* b) {
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; a[i] = (uint64_t)c; c >>= 64; }
+  return (uint64_t)c;
+}
+static inline void sub4(uint64_t* a, const uint64_t* b) {
+  u128 br = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)a[i] - b[i] - (uint64_t)br; a[i] = (uint64_t)t; br = (t >> 64) & 1; }
+}
+static inline bool geq4(const uint64_t* a, const uint64_t* b) {
+  for (int i = 3; i >= 0; i--) { if (a[i] > b[i]) return true; if (a[i] < b[i]) return false; }
+  return true;
+}
+// halve x modulo p (x < p)
+static inline void half_mod(uint64_t* x) {
+  uint64_t top = 0;
+  if (!is_even(x)) top = add4(x, FR_P);
+  shr1(x, top);
+}
+}  // namespace detail
+static inline FrH inv(const FrH& a) {
+  if (a.is_zero()) return a;
+  using namespace detail;
+  uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  memcpy(u, a.l, 32); memcpy(v, FR_P, 32);
+  while (!is_one(u) && !is_one(v)) {
+    while (is_even(u)) { shr1(u, 0); half_mod(x1); }
+    while (is_even(v)) { shr1(v, 0); half_mod(x2); }
+    if (geq4(u, v)) { sub4(u, v); if (geq4(x1, x2)) sub4(x1, x2); else { sub4(x1, x2); add4(x1, FR_P); } }
+    else            { sub4(v, u); if (geq4(x2, x1)) sub4(x2, x1); else { sub4(x2, x1); add4(x2, FR_P); } }
+  }
+  FrH r; memcpy(r.l, is_one(u) ? x1 : x2, 32);            // = a^-1 * R^-1 as a plain integer
+  static const FrH R3 = mul(FR_R2, FR_R2);                // R^2 * R^2 * R^-1
+  return mul(r, R3);
 }
 // challenge limbs {0,0,lo,hi} are already a valid Montgomery representation (mont_ark_u128.rs:79-84)
 static inline FrH from_limbs(const uint64_t* p) { FrH r; memcpy(r.l, p, 32); return r; }

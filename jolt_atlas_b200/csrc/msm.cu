@@ -1,6 +1,7 @@
 // C ABI for the commitment half of the hot path: SRS residency, batched Pippenger MSM, one-hot point sums.
 // Kernels: msm_kernels.cuh.  No CPU fallback.
 #include "common.hpp"
+#include "fq_host.hpp"
 #include "msm_kernels.cuh"
 
 #include <algorithm>
@@ -28,10 +29,53 @@ static uint32_t run_length() {
   return 64;
 }
 
+// Batch of indexed point sums (every job MSM_INDEXED): two launches + one host-side batch normalisation.
+static int32_t indexed_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, MsmResult* out) {
+  const uint32_t count = (uint32_t)jobs.size();
+  std::vector<IdxJob> ij(count);
+  uint64_t blocks = 0;
+  for (uint32_t m = 0; m < count; m++) {
+    JA_REQUIRE(jobs[m].n < (1ull << 32), "indexed sum: list too long");
+    ij[m] = IdxJob{(const unsigned long long*)jobs[m].d_scalars, (uint32_t)jobs[m].n, (uint32_t)blocks};
+    blocks += (jobs[m].n + kIdxBlock * kIdxRun - 1) / (kIdxBlock * kIdxRun);
+    JA_REQUIRE(blocks < (1ull << 31), "indexed sum: batch too large");
+  }
+  auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_jobs = 0, o_part = align(sizeof(IdxJob) * count), o_out = align(o_part + sizeof(G1X) * (blocks ? blocks : 1));
+  const size_t total = align(o_out + sizeof(G1X) * count);
+  char* ws = nullptr;
+  int32_t st = dev_alloc(c, total, (void**)&ws);
+  if (st) return st;
+  IdxJob* d_jobs = (IdxJob*)(ws + o_jobs);
+  G1X* d_part = (G1X*)(ws + o_part);
+  G1X* d_out = (G1X*)(ws + o_out);
+  cudaStream_t s = c->stream;
+  JA_CUDA(cudaMemcpyAsync(d_jobs, ij.data(), sizeof(IdxJob) * count, cudaMemcpyHostToDevice, s));
+  if (blocks) JA_LAUNCH(c, KC_ONEHOT_SUM, k_indexed_partial<<<(unsigned)blocks, kIdxBlock, 0, s>>>(d_jobs, count, srs->points, d_part));
+  JA_LAUNCH(c, KC_ONEHOT_SUM, k_indexed_final<<<count, kIdxBlock, 0, s>>>(d_jobs, count, d_part, (uint32_t)blocks, d_out));
+  JA_CUDA(cudaGetLastError());
+  std::vector<host::G1XH> sums(count);
+  JA_CUDA(cudaMemcpyAsync(sums.data(), d_out, sizeof(G1X) * count, cudaMemcpyDeviceToHost, s));
+  JA_CUDA(cudaStreamSynchronize(s));
+  dev_free(c, ws);
+  std::vector<uint64_t> xy((size_t)count * 8);
+  std::vector<int32_t> inf(count);
+  host::xyzz_batch_to_affine(sums.data(), count, xy.data(), inf.data());
+  for (uint32_t m = 0; m < count; m++) {
+    memcpy(out[m].x.l, xy.data() + 8 * m, 32);
+    memcpy(out[m].y.l, xy.data() + 8 * m + 4, 32);
+    out[m].inf = (uint32_t)inf[m];
+  }
+  return JA_OK;
+}
+
 // Runs the whole pipeline for `jobs` on c->stream; results (count x MsmResult) land in host memory `out`.
 static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, MsmResult* out) {
   const uint32_t count = (uint32_t)jobs.size();
   if (count == 0) return JA_OK;
+  bool all_indexed = true;
+  for (const MsmJob& j : jobs) all_indexed = all_indexed && j.kind == MSM_INDEXED;
+  if (all_indexed) return indexed_engine(c, srs, jobs, out);
   std::vector<MsmDesc> descs(count);
   std::vector<MsmWindow> wins;
   uint64_t total_n = 0, nbt = 0, e_max = 0;

@@ -353,6 +353,60 @@ k_msm_window_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ seg
   if (threadIdx.x == 0) g1x_store(window_sums + blockIdx.x, s_acc[0]);
 }
 
+// ---- indexed point sums (one-hot commitments), dedicated path ---------------------------------------------------
+// HyperKZG::commit_one_hot / batch_commit_one_hot (hyperkzg/mod.rs:520-596): C_j = sum_t G[idx_j[t]], no scalars, no
+// buckets.  Blocks own kIdxBlock * kIdxRun consecutive entries of ONE list: every thread chains kIdxRun mixed
+// additions (strided so the index loads coalesce), the block folds its 128 partial sums in shared memory, and a second
+// launch folds the per-block partials of each list.  The XYZZ results go to the host, which normalises the whole
+// batch with one inversion (fq_host.hpp).
+constexpr int kIdxBlock = 128, kIdxRun = 8;
+struct IdxJob { const unsigned long long* idx; uint32_t n; uint32_t first_block; };
+
+JA_DEV G1X block_point_sum(G1X acc, G1X* s_acc /* kIdxBlock */) {
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t s = kIdxBlock >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { G1X a = s_acc[threadIdx.x]; g1x_add(a, s_acc[threadIdx.x + s]); s_acc[threadIdx.x] = a; }
+    __syncthreads();
+  }
+  return s_acc[0];
+}
+
+static __global__ void __launch_bounds__(kIdxBlock)
+k_indexed_partial(const IdxJob* __restrict__ jobs, uint32_t njobs, const G1Aff* __restrict__ bases, G1X* __restrict__ partial) {
+  __shared__ G1X s_acc[kIdxBlock];
+  uint32_t lo = 0, hi = njobs - 1;
+  while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (jobs[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1; }
+  const IdxJob job = jobs[lo];
+  const uint32_t base = (blockIdx.x - job.first_block) * (kIdxBlock * kIdxRun);
+  G1X acc = g1x_inf();
+  uint32_t e = base + threadIdx.x;
+  G1Aff pt;
+  if (e < job.n) pt = g1aff_load(bases + __ldg(job.idx + e));
+#pragma unroll 1
+  for (int r = 0; r < kIdxRun; r++) {
+    if (e >= job.n) break;
+    const G1Aff cur = pt;
+    e += kIdxBlock;
+    if (r + 1 < kIdxRun && e < job.n) pt = g1aff_load(bases + __ldg(job.idx + e));    // prefetch the next base
+    g1x_madd(acc, cur, false);
+  }
+  const G1X tot = block_point_sum(acc, s_acc);
+  if (threadIdx.x == 0) g1x_store(partial + blockIdx.x, tot);
+}
+// one block per list: fold its per-block partials
+static __global__ void __launch_bounds__(kIdxBlock)
+k_indexed_final(const IdxJob* __restrict__ jobs, uint32_t njobs, const G1X* __restrict__ partial, uint32_t total_blocks,
+                G1X* __restrict__ out) {
+  __shared__ G1X s_acc[kIdxBlock];
+  const IdxJob job = jobs[blockIdx.x];
+  const uint32_t end = blockIdx.x + 1 < njobs ? jobs[blockIdx.x + 1].first_block : total_blocks;
+  G1X acc = g1x_inf();
+  for (uint32_t b = job.first_block + threadIdx.x; b < end; b += kIdxBlock) g1x_add(acc, g1x_load(partial + b));
+  const G1X tot = block_point_sum(acc, s_acc);
+  if (threadIdx.x == 0) g1x_store(out + blockIdx.x, tot);
+}
+
 // ---- final: Horner over windows + affine conversion; one thread per MSM -------------------------------
 struct MsmResult { Fq x, y; uint32_t inf; uint32_t pad[3]; };   // 80 B
 static __global__ void __launch_bounds__(32)

@@ -359,6 +359,124 @@ k_round_eval_prod(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* __
   grid_sum<KC>(outer, partials + (size_t)blockIdx.y * gridDim.x * KC, counters + blockIdx.y, block_out + (size_t)blockIdx.y * KC);
 }
 
+// ---- product of d <= 16 linear factors, warp-transposed --------------------------------------------------------------
+// Same sums as k_round_eval_prod, laid out for latency: a group of L = next_pow2(d) lanes owns one pair g.  Lane i
+// loads factor i (p_i[2g], p_i[2g+1]) and tabulates it on the L grid points with additions only
+// (X = 1..L-1 at indices 0..L-2, X = inf at index L-1).  The d-fold product is then a log2(L)-level exchange in which
+// each lane keeps half of its points and multiplies them with its partner's values at the same points
+// (L-1 products per lane in total, L/2 + L/4 + ... + 1 on the critical path), so lane j ends with the product at grid
+// point j.  The caller reads points 0..d-2 and L-1 (inf).  Lanes >= d carry the constant factor 1.
+JA_DEV Fr fr_select(bool c, const Fr& a, const Fr& b) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+  return r;
+}
+JA_DEV Fr fr_shfl_xor(const Fr& a, int mask) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, a.l[i], mask);
+  return r;
+}
+template <int M> struct LaneProduct {     // M = number of values currently held per lane
+  JA_DEV static void run(Fr (&v)[M], int lane) {
+    constexpr int H = M / 2;
+    const bool hi = (lane & H) != 0;
+    Fr nv[H];
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+      const Fr send = fr_select(hi, v[j], v[j + H]);
+      const Fr keep = fr_select(hi, v[j + H], v[j]);
+      nv[j] = fp_mul<FrParams>(keep, fr_shfl_xor(send, H));
+    }
+    LaneProduct<H>::run(nv, lane);
+    v[0] = nv[0];
+  }
+};
+template <> struct LaneProduct<1> { JA_DEV static void run(Fr (&)[1], int) {} };
+
+// sum of `v` over all threads of the block that share (threadIdx.x % L); valid in threads t < L afterwards
+template <int L>
+JA_DEV Fr block_sum_by_lane(Fr v) {
+  __shared__ Fr s_lane[kBlock / 32][L > 32 ? 32 : L];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int dlt = 16; dlt >= L; dlt >>= 1) v = fp_add<FrParams>(v, fr_shfl_down(v, dlt));
+  __syncthreads();
+  if (lane < L) s_lane[warp][lane] = v;
+  __syncthreads();
+  Fr t = fp_zero<FrParams>();
+  if (threadIdx.x < L)
+    for (int w = 0; w < kBlock / 32; w++) t = fp_add<FrParams>(t, s_lane[w][threadIdx.x]);
+  return t;
+}
+
+template <int L, bool SAME>
+__global__ void __launch_bounds__(kBlock)
+k_round_eval_prod_t(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+                    size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, Fr* out /* [L] */, unsigned int* counter) {
+  constexpr int GPB = kBlock / L;                     // lane groups (pairs in flight) per block
+  const int li = threadIdx.x & (L - 1);
+  const int group = threadIdx.x / L;
+  const bool pad = li >= d;
+  const Fr* __restrict__ z = P.p[(SAME || pad) ? 0 : li];
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  size_t g_end = g_begin + pairs_per_block;
+  if (g_end > G) g_end = G;
+  Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
+  size_t cur_xout = ~size_t(0);
+  for (size_t base = g_begin; base < g_end; base += GPB) {      // uniform trip count: every lane joins the shuffles
+    const size_t g = base + group;
+    const bool active = g < g_end;
+    const size_t gl = active ? g : g_begin;
+    Fr p0, dp;
+    if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
+    else { p0 = fp_load(z + 2 * gl); dp = fp_sub<FrParams>(fp_load(z + 2 * gl + 1), p0); }
+    Fr v[L];
+    Fr cur = p0;
+#pragma unroll
+    for (int k = 0; k < L - 1; k++) { cur = fp_add<FrParams>(cur, dp); v[k] = cur; }
+    v[L - 1] = pad ? p0 : dp;
+    LaneProduct<L>::run(v, li);
+    if (active) {
+      const size_t x_out = g >> bits_in;
+      if (x_out != cur_xout) {
+        if (cur_xout != ~size_t(0)) {
+          outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
+          inner = fp_zero<FrParams>();
+        }
+        cur_xout = x_out;
+      }
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + (g & mask_in)), v[0]));
+    }
+  }
+  if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
+  Fr tot = block_sum_by_lane<L>(outer);
+  if (gridDim.x == 1) {
+    if (threadIdx.x < L) fp_store(out + threadIdx.x, tot);
+    return;
+  }
+  if (threadIdx.x < L) fp_store(partials + (size_t)blockIdx.x * L + threadIdx.x, tot);
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Fr acc = fp_zero<FrParams>();
+  for (unsigned b = threadIdx.x / L; b < gridDim.x; b += GPB) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(partials + (size_t)b * L + li);
+    Fr t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.l[i] = q[i];
+    acc = fp_add<FrParams>(acc, t);
+  }
+  tot = block_sum_by_lane<L>(acc);
+  if (threadIdx.x < L) fp_store(out + threadIdx.x, tot);
+}
+
 // ---- plain sums (no eq): Hamming weight (sum_j p_i[2j], LowToHigh; hamming_weight.rs:118-139) and Sum over an axis
 // (sum_{j<n/2} p[j], HighToLow; ops/sum/axis.rs:220-233).  blockIdx.y = polynomial; out[i] = the sum of poly i.
 // The gamma combination of the Hamming instance is O(d) host work on the returned sums.

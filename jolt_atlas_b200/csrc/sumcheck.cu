@@ -26,25 +26,31 @@ struct Instance {
 int32_t instance_message(ja_ctx* c, Instance& in, const FrH& prev, Coeffs* uni) {
   uint64_t ev[32 * 4];
   const uint64_t* aux = in.gammas.empty() ? nullptr : reinterpret_cast<const uint64_t*>(in.gammas.data());
-  int32_t st = ja_round_eval(c, in.kind, in.polys.data(), in.polys.size(), in.eq, aux, in.gammas.size(), in.pow_d, ev, in.n_out);
+  RoundEvalPending pend;
+  int32_t st = ja_round_eval_launch(c, in.kind, in.polys.data(), in.polys.size(), in.eq, aux, in.gammas.size(), in.pow_d,
+                                    in.n_out, &pend);
   if (st) return st;
-  std::vector<FrH> e(in.n_out);
-  for (size_t k = 0; k < in.n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
-  FrH cs = host::FR_ONE, cw = host::FR_ZERO;
+  // while the kernel runs: the one field division of the round (it depends on the eq state only)
+  FrH cs = host::FR_ONE, cw = host::FR_ZERO, div = host::FR_ZERO;
   if (in.eq) {
     uint64_t t[4];
     ja_spliteq_current_scalar(in.eq, t); cs = host::from_limbs(t);
     if ((st = ja_spliteq_current_w(in.eq, t))) return st;
     cw = host::from_limbs(t);
+    if (in.kind == JA_EVAL_PROD || in.kind == JA_EVAL_POW) div = host::inv(host::sub(host::FR_ONE, cw));
+    else div = host::inv(host::gruen_eq1(cs, cw));
   }
+  if ((st = ja_round_eval_collect(c, pend, ev))) return st;
+  std::vector<FrH> e(in.n_out);
+  for (size_t k = 0; k < in.n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
   switch (in.kind) {
     case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT:
-      *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev); break;                    // ops/add.rs:297-304
+      *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev, div); break;               // ops/add.rs:297-304
     case JA_EVAL_MUL: case JA_EVAL_SQUARE:
-      *uni = host::gruen_poly_deg_3(cs, cw, e[0], e[1], prev); break;              // ops/mul.rs:177
+      *uni = host::gruen_poly_deg_3(cs, cw, e[0], e[1], prev, div); break;         // ops/mul.rs:177
     case JA_EVAL_PROD: case JA_EVAL_POW:
       for (auto& x : e) x = host::mul(x, cs);                                      // mles_product_sum.rs:120-128
-      *uni = host::finish_mles_product_sum_from_evals(e, prev, cw); break;
+      *uni = host::finish_mles_product_sum_from_evals(e, prev, cw, div); break;
     default:
       *uni = host::from_evals_and_hint(prev, e); break;                            // einsum/dot.rs:304,349; hamming_weight.rs:137
   }

@@ -7,6 +7,8 @@
 // as the reference's Gaussian elimination; only the TRIMMING rules change transcript bytes and are kept exactly:
 // from_evals of 3 or 4 values keeps its length, the general path and from_coeff drop trailing zeros.
 #pragma once
+#include <map>
+#include <mutex>
 #include <vector>
 #include "fr_host.hpp"
 
@@ -56,22 +58,56 @@ static inline Coeffs interpolate_0_to_m(const FrH* e, size_t m) {
   return out;
 }
 
+// Interpolation is linear in the evaluations: coeffs = M_n * e.  The matrices depend only on n and are built once
+// (from unit vectors through the routines above) and cached; per round the glue is then n^2 products, no inversion.
+struct InterpCache {
+  std::mutex mu;
+  std::map<size_t, std::vector<FrH>> plain, toom;
+};
+static inline InterpCache& interp_cache() { static InterpCache c; return c; }
+static inline Coeffs from_evals_toom_slow(const std::vector<FrH>& e);
+static inline const std::vector<FrH>& interp_matrix(size_t n, bool toom) {
+  InterpCache& c = interp_cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto& tab = toom ? c.toom : c.plain;
+  auto it = tab.find(n);
+  if (it != tab.end()) return it->second;
+  std::vector<FrH> m(n * n, FR_ZERO);
+  for (size_t i = 0; i < n; i++) {
+    std::vector<FrH> unit(n, FR_ZERO);
+    unit[i] = FR_ONE;
+    const Coeffs col = toom ? from_evals_toom_slow(unit) : interpolate_0_to_m(unit.data(), n);
+    for (size_t k = 0; k < n; k++) m[k * n + i] = col[k];
+  }
+  return tab.emplace(n, std::move(m)).first->second;
+}
+static inline Coeffs apply_matrix(const std::vector<FrH>& m, const std::vector<FrH>& e) {
+  const size_t n = e.size();
+  Coeffs out(n, FR_ZERO);
+  for (size_t k = 0; k < n; k++) {
+    FrH acc = FR_ZERO;
+    for (size_t i = 0; i < n; i++)
+      if (!m[k * n + i].is_zero() && !e[i].is_zero()) acc = add(acc, mul(m[k * n + i], e[i]));
+    out[k] = acc;
+  }
+  return out;
+}
+
 static inline Coeffs from_evals(const std::vector<FrH>& e) {    // unipoly.rs:55-92,136-153
   const size_t n = e.size();
+  static const FrH two_inv = inv(from_u64(2)), six_inv = inv(from_u64(6));
   if (n == 3) {
-    const FrH two_inv = inv(from_u64(2));
     const FrH c2 = mul(add(sub(sub(e[0], e[1]), e[1]), e[2]), two_inv);
     const FrH c1 = sub(sub(e[1], e[0]), c2);
     return Coeffs{e[0], c1, c2};
   }
   if (n == 4) {
-    const FrH two_inv = inv(from_u64(2)), six_inv = inv(from_u64(6));
     const FrH c3 = mul(add(sub(e[3], e[0]), mul(sub(e[1], e[2]), from_u64(3))), six_inv);
     const FrH c2 = sub(sub(sub(mul(add(sub(sub(e[0], e[1]), e[1]), e[2]), two_inv), c3), c3), c3);
     const FrH c1 = sub(sub(sub(e[1], e[0]), c2), c3);
     return Coeffs{e[0], c1, c2, c3};
   }
-  return trim(interpolate_0_to_m(e.data(), n));
+  return trim(apply_matrix(interp_matrix(n, false), e));
 }
 static inline Coeffs from_evals_and_hint(const FrH& hint, const std::vector<FrH>& evals) {   // unipoly.rs:96-101
   std::vector<FrH> e = evals;
@@ -79,7 +115,8 @@ static inline Coeffs from_evals_and_hint(const FrH& hint, const std::vector<FrH>
   return from_evals(e);
 }
 // values at 0..n-2 and the leading coefficient (value "at infinity") -> n coefficients, no trimming (unipoly.rs:104-134)
-static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
+static inline Coeffs from_evals_toom(const std::vector<FrH>& e) { return apply_matrix(interp_matrix(e.size(), true), e); }
+static inline Coeffs from_evals_toom_slow(const std::vector<FrH>& e) {
   const size_t n = e.size();
   const FrH lead = e[n - 1];
   std::vector<FrH> low(n - 1);
@@ -105,23 +142,27 @@ static inline Coeffs compress(const Coeffs& c) {                 // unipoly.rs:3
 }
 
 // split_eq_poly.rs:432-471
-static inline Coeffs gruen_poly_deg_2(const FrH& current_scalar, const FrH& current_w, const FrH& q0, const FrH& prev) {
+// `eq1_inv` = (current_scalar * current_w)^-1: it does not depend on the kernel's sums, so the driver computes it while
+// the round-evaluation kernel is in flight.
+static inline FrH gruen_eq1(const FrH& current_scalar, const FrH& current_w) { return mul(current_scalar, current_w); }
+static inline Coeffs gruen_poly_deg_2(const FrH& current_scalar, const FrH& current_w, const FrH& q0, const FrH& prev,
+                                      const FrH& eq1_inv) {
   const FrH eq1 = mul(current_scalar, current_w);
   const FrH eq0 = sub(current_scalar, eq1);
   const FrH eqm = sub(eq1, eq0), eq2 = add(eq1, eqm);
   const FrH c0 = mul(eq0, q0), c1 = sub(prev, c0);
-  const FrH l1 = mul(c1, inv(eq1));
+  const FrH l1 = mul(c1, eq1_inv);
   const FrH l2 = sub(add(l1, l1), q0);
   return from_evals({c0, c1, mul(eq2, l2)});
 }
 // split_eq_poly.rs:379-426
 static inline Coeffs gruen_poly_deg_3(const FrH& current_scalar, const FrH& current_w, const FrH& q_constant,
-                                      const FrH& q_quadratic, const FrH& s01) {
+                                      const FrH& q_quadratic, const FrH& s01, const FrH& eq1_inv) {
   const FrH eq1 = mul(current_scalar, current_w);
   const FrH eq0 = sub(current_scalar, eq1);
   const FrH eqm = sub(eq1, eq0), eq2 = add(eq1, eqm), eq3 = add(eq2, eqm);
   const FrH c0 = mul(eq0, q_constant), c1 = sub(s01, c0);
-  const FrH q1 = mul(c1, inv(eq1));
+  const FrH q1 = mul(c1, eq1_inv);
   const FrH e2 = add(q_quadratic, q_quadratic);
   const FrH q2 = add(sub(add(q1, q1), q_constant), e2);
   const FrH q3 = add(add(sub(add(q2, q1), q_constant), e2), e2);
@@ -129,10 +170,12 @@ static inline Coeffs gruen_poly_deg_3(const FrH& current_scalar, const FrH& curr
 }
 // mles_product_sum.rs:330-376: sums = values of the eq-free product polynomial on {1..d-1, inf} (already times
 // current_scalar); recover its value at 0 from the claim, interpolate, multiply by the linear eq factor.
-static inline Coeffs finish_mles_product_sum_from_evals(const std::vector<FrH>& sum_evals, const FrH& claim, const FrH& r) {
-  const FrH eq0 = sub(FR_ONE, r), eq1 = r;
+// `eq0_inv` = (1 - r)^-1, precomputable like gruen's eq1_inv.
+static inline Coeffs finish_mles_product_sum_from_evals(const std::vector<FrH>& sum_evals, const FrH& claim, const FrH& r,
+                                                        const FrH& eq0_inv) {
+  const FrH eq1 = r;
   FrH at0 = sub(claim, mul(eq1, sum_evals[0]));
-  if (sum_evals.size() != 1) at0 = mul(at0, inv(eq0));
+  if (sum_evals.size() != 1) at0 = mul(at0, eq0_inv);
   std::vector<FrH> toom; toom.push_back(at0);
   toom.insert(toom.end(), sum_evals.begin(), sum_evals.end());
   const Coeffs tmp = from_evals_toom(toom);
