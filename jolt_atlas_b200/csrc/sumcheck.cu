@@ -9,7 +9,19 @@
 #include "sumcheck_host.hpp"
 #include "transcript_host.hpp"
 
+#include <chrono>
+#include <cstdlib>
 using host::Coeffs;
+
+// JA_SC_TRACE=1: per-phase host wall-clock of the round loop on stderr (tuning aid)
+struct ScTrace {
+  bool on = getenv("JA_SC_TRACE") != nullptr;
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point last;
+  void start() { if (on) last = std::chrono::steady_clock::now(); }
+  void lap(int k) { if (!on) return; auto n = std::chrono::steady_clock::now(); t[k] += std::chrono::duration<double, std::micro>(n - last).count(); last = n; }
+};
+static ScTrace g_trace;
 
 namespace {
 
@@ -30,6 +42,7 @@ int32_t instance_message(ja_ctx* c, Instance& in, const FrH& prev, Coeffs* uni) 
   int32_t st = ja_round_eval_launch(c, in.kind, in.polys.data(), in.polys.size(), in.eq, aux, in.gammas.size(), in.pow_d,
                                     in.n_out, &pend);
   if (st) return st;
+  g_trace.lap(0);
   // while the kernel runs: the one field division of the round (it depends on the eq state only)
   FrH cs = host::FR_ONE, cw = host::FR_ZERO, div = host::FR_ZERO;
   if (in.eq) {
@@ -40,7 +53,9 @@ int32_t instance_message(ja_ctx* c, Instance& in, const FrH& prev, Coeffs* uni) 
     if (in.kind == JA_EVAL_PROD || in.kind == JA_EVAL_POW) div = host::inv(host::sub(host::FR_ONE, cw));
     else div = host::inv(host::gruen_eq1(cs, cw));
   }
+  g_trace.lap(1);
   if ((st = ja_round_eval_collect(c, pend, ev))) return st;
+  g_trace.lap(2);
   std::vector<FrH> e(in.n_out);
   for (size_t k = 0; k < in.n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
   switch (in.kind) {
@@ -101,9 +116,11 @@ int32_t ja_sumcheck_prove(ja_ctx* c, int32_t kind, ja_poly* const* polys, size_t
   host::Blake2bTranscript t(transcript_state, *n_rounds_io);
   FrH prev = host::from_limbs(claim);
   t.append_scalar(prev);                                           // sumcheck.rs:574
+  g_trace.start();
   for (size_t round = 0; round < rounds; round++) {
     Coeffs uni;
     if ((st = instance_message(c, in, prev, &uni))) { ja_spliteq_free(c, in.eq); return st; }
+    g_trace.lap(3);
     const Coeffs cp = host::compress(uni);
     if (cp.size() > max_coeffs) { ja_spliteq_free(c, in.eq); return fail(JA_ERR_INVALID, "ja_sumcheck_prove: max_coeffs too small"); }
     t.append_message("UniPoly_begin");                             // unipoly.rs:550-558
@@ -112,8 +129,10 @@ int32_t ja_sumcheck_prove(ja_ctx* c, int32_t kind, ja_poly* const* polys, size_t
     uint64_t ch[4];
     t.challenge_scalar_optimized(ch);                              // sumcheck.rs:586
     prev = host::evaluate(uni, host::from_limbs(ch));              // sumcheck.rs:589
+    g_trace.lap(4);
     if (in.eq && (st = ja_spliteq_bind(c, in.eq, ch))) { ja_spliteq_free(c, in.eq); return st; }
     if ((st = ja_bind_many(c, in.polys.data(), in.polys.size(), ch, in.order))) { ja_spliteq_free(c, in.eq); return st; }
+    g_trace.lap(5);
     out_ncoeffs[round] = (uint32_t)cp.size();
     for (size_t k = 0; k < cp.size(); k++) memcpy(out_coeffs + 4 * (round * max_coeffs + k), cp[k].l, 32);
     memcpy(out_challenges + 4 * round, ch, 32);
@@ -122,6 +141,9 @@ int32_t ja_sumcheck_prove(ja_ctx* c, int32_t kind, ja_poly* const* polys, size_t
     for (size_t i = 0; i < n_polys; i++)
       if ((st = ja_final_claim(c, polys[i], out_final_claims + 4 * i))) { ja_spliteq_free(c, in.eq); return st; }
   ja_spliteq_free(c, in.eq);
+  if (g_trace.on)
+    fprintf(stderr, "[sc kind=%d n_polys=%zu rounds=%zu] cumulative us: launch=%.0f inv=%.0f wait=%.0f interp=%.0f hash+eval=%.0f bind=%.0f\n",
+            kind, n_polys, rounds, g_trace.t[0], g_trace.t[1], g_trace.t[2], g_trace.t[3], g_trace.t[4], g_trace.t[5]);
   memcpy(transcript_state, t.state, 32);
   *n_rounds_io = t.n_rounds;
   return (int32_t)JA_OK;
