@@ -38,6 +38,7 @@ typedef struct ja_poly ja_poly;       /* device-resident MultilinearPolynomial (
 typedef struct ja_spliteq ja_spliteq; /* device-resident GruenSplitEqPolynomial */
 typedef struct ja_srs ja_srs;         /* device-resident KZG SRS (g1_powers) */
 typedef struct ja_onehot ja_onehot;   /* device-resident batch of one-hot index lists (OneHotPolynomial::nonzero_indices as k*T+t) */
+typedef struct ja_addr ja_addr;       /* device-resident one-hot ADDRESSES of a node: d lists x T entries in [0, K) (u32, 0xFFFFFFFF = None) */
 typedef struct ja_hkzg ja_hkzg;       /* in-flight HyperKZG::open (folded polynomials resident on the device) */
 
 enum { JA_LOW_TO_HIGH = 0, JA_HIGH_TO_LOW = 1 };
@@ -145,6 +146,33 @@ int32_t ja_sumcheck_prove(ja_ctx*, int32_t kind, ja_poly* const* polys, size_t n
                           uint8_t transcript_state[32], uint32_t* n_rounds, size_t max_coeffs, uint64_t* out_coeffs,
                           uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_final_claims);
 
+/* BatchedSumcheck::prove (joltworks/src/subprotocols/sumcheck.rs:30-184, "front-loaded" batching): input claims are
+ * appended, one batching coefficient per instance is drawn (challenge_vector), instances with fewer rounds start late
+ * and contribute 2^k-scaled constants (:58-65, :91-100); per round the instances' univariates are combined, compressed,
+ * appended, and r_j is drawn; every active instance then ingests r_j.  ONE host<->device exchange per round serves all
+ * instances.  An instance is described by: */
+enum { JA_INST_BOOLEANITY = 32,      /* BooleanitySumcheckProver (subprotocols/booleanity.rs:153-372), input claim 0 */
+       JA_INST_HAMMING_TABLES = 33   /* HammingWeightSumcheckProver over the K-entry G tables (hamming_weight.rs:60-160) */ };
+typedef struct ja_sc_instance {
+  int32_t kind;                  /* JA_EVAL_* (device polynomials) or JA_INST_* */
+  uint32_t aux_u32;              /* JA_EVAL_POW: degree d; JA_INST_BOOLEANITY: log_k */
+  size_t n_polys;                /* polynomials / tables of the instance (booleanity: d) */
+  ja_poly* const* polys;         /* JA_EVAL_*: device polynomials, consumed (bound to length 1) */
+  const uint64_t* host_tables;   /* JA_INST_*: n_polys x table_len Fr — the G tables of compute_ra_evals */
+  size_t table_len;              /* K */
+  const ja_addr* addr;           /* JA_INST_BOOLEANITY: the addresses H_i = RaPolynomial(indices, F) is built from */
+  const uint64_t* eq_w;          /* family S / PROD / POW: eq point (one Fr per round); booleanity: r_cycle */
+  size_t eq_m;
+  const uint64_t* aux_fr;        /* SUM1 / HAMMING_TABLES: gammas; booleanity: gammas (d) followed by r_address (log_k) */
+  size_t n_aux;
+  uint64_t claim[4];             /* input claim (ignored for booleanity) */
+  uint64_t* out_final_claims;    /* n_polys x 4 Fr: final_claim of every polynomial / table (may be NULL) */
+} ja_sc_instance;
+/* Outputs as ja_sumcheck_prove; rounds = max over instances of num_rounds. */
+int32_t ja_batched_sumcheck_prove(ja_ctx*, const ja_sc_instance* instances, size_t n_instances, uint8_t transcript_state[32],
+                                  uint32_t* n_rounds, size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs,
+                                  uint64_t* out_challenges);
+
 /* Einsum operand fold / i32 tensor x eq-vector (ops/einsum/mk_kn_mn.rs:47-79):
  *   transpose==0: out[j] = sum_i from_i32(A[i*cols + j]) * eq[i]   (eq has `rows` entries, out has `cols`)
  *   transpose==1: out[i] = sum_j from_i32(A[i*cols + j]) * eq[j]   (eq has `cols` entries, out has `rows`) */
@@ -188,6 +216,21 @@ int32_t ja_g1_sum_indexed_batch(ja_ctx*, const ja_srs*, const uint64_t* indices,
 int32_t ja_onehot_upload(ja_ctx*, const uint64_t* indices, const uint64_t* offsets, size_t count, ja_onehot** out);
 int32_t ja_onehot_commit(ja_ctx*, const ja_srs*, const ja_onehot*, uint64_t* out_xy, int32_t* is_inf);
 void ja_onehot_free(ja_ctx*, ja_onehot*);
+
+/* One-hot address batches: the d chunk-address lists of a node (witness.rs:84-99 build_one_hot_rad_witness ->
+ * OneHotPolynomial::from_indices, one_hot_polynomial.rs:62) uploaded once as d x T u32 (0xFFFFFFFF = None, K <= 65536),
+ * then consumed on the device by the commitment, the RA materialisations and the G-table scatter. */
+int32_t ja_addr_upload(ja_ctx*, const uint32_t* k, size_t d, size_t T, size_t K, ja_addr** out);
+void ja_addr_free(ja_ctx*, ja_addr*);
+size_t ja_addr_len(const ja_addr*);
+size_t ja_addr_count(const ja_addr*);
+/* HyperKZG::batch_commit_one_hot (hyperkzg/mod.rs:558-596): C_i = sum_t g1_powers[k_i[t] * T + t]; out_xy = d x 8 limbs */
+int32_t ja_addr_commit(ja_ctx*, const ja_srs*, const ja_addr*, uint64_t* out_xy, int32_t* is_inf);
+/* RaPolynomial::new(indices, eq_evals) for all d lists in one launch (ra_poly.rs:31-81, ra_virtual.rs:113-134):
+ * tables = d x K Fr, out_polys[i][t] = tables[i][k_i[t]] (None -> 0); T must be a power of two. */
+int32_t ja_addr_gather(ja_ctx*, const ja_addr*, const uint64_t* tables, ja_poly** out_polys);
+/* compute_ra_evals (subprotocols/shout.rs:549-598): out_G[i][k] = sum_{t: k_i[t] == k} eq(r_cycle, t); out_G = d x K Fr */
+int32_t ja_addr_ra_evals(ja_ctx*, const ja_addr*, const uint64_t* r_cycle, size_t log_t, uint64_t* out_G);
 
 /* ---- HyperKZG::open (joltworks/src/poly/commitment/hyperkzg/mod.rs:400-447) --------------------------------------
  * Split at the two transcript interaction points so that a Rust caller keeps its own Blake2bTranscript:

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ja_round_eval": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, u64p, C.c_size_t, C.c_uint32, u64p, C.c_size_t]),
     "ja_sumcheck_prove": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint32, u64p,
                                       C.c_char_p, u32p, C.c_size_t, u64p, u32p, u64p, u64p]),
+    "ja_batched_sumcheck_prove": (C.c_int32, [vp, vp, C.c_size_t, C.c_char_p, u32p, C.c_size_t, u64p, u32p, u64p]),
     "ja_tensor_fold_i32": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vp, C.c_int32, vpp]),
     "ja_srs_upload": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
     "ja_srs_generate": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),
@@ -58,6 +59,13 @@ SIGNATURES = {
     "ja_onehot_upload": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),
     "ja_onehot_commit": (C.c_int32, [vp, vp, vp, u64p, i32p]),
     "ja_onehot_free": (None, [vp, vp]),
+    "ja_addr_upload": (C.c_int32, [vp, u32p, C.c_size_t, C.c_size_t, C.c_size_t, vpp]),
+    "ja_addr_free": (None, [vp, vp]),
+    "ja_addr_len": (C.c_size_t, [vp]),
+    "ja_addr_count": (C.c_size_t, [vp]),
+    "ja_addr_commit": (C.c_int32, [vp, vp, vp, u64p, i32p]),
+    "ja_addr_gather": (C.c_int32, [vp, vp, u64p, vpp]),
+    "ja_addr_ra_evals": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p]),
     "ja_hyperkzg_open_begin": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, vpp, u64p, i32p]),
     "ja_hyperkzg_open_evals": (C.c_int32, [vp, vp, u64p, u64p]),
     "ja_hyperkzg_open_witness": (C.c_int32, [vp, vp, u64p, u64p, u64p, i32p]),
@@ -73,6 +81,16 @@ SIGNATURES = {
     "ja_poly_random": (C.c_int32, [vp, C.c_size_t, C.c_uint32, vpp]),
     "ja_calibrate_fr_mul": (C.c_int32, [vp, C.c_int32, C.POINTER(C.c_double)]),
 }
+
+
+
+class ScInstance(C.Structure):
+    """ja_sc_instance (include/jolt_atlas_b200.h)."""
+    _fields_ = [("kind", C.c_int32), ("aux_u32", C.c_uint32), ("n_polys", C.c_size_t), ("polys", C.c_void_p),
+                ("host_tables", C.c_void_p), ("table_len", C.c_size_t), ("addr", C.c_void_p), ("eq_w", C.c_void_p),
+                ("eq_m", C.c_size_t), ("aux_fr", C.c_void_p), ("n_aux", C.c_size_t), ("claim", C.c_uint64 * 4),
+                ("out_final_claims", C.c_void_p)]
+
 
 _lib = None
 

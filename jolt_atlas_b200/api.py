@@ -455,3 +455,105 @@ def sumcheck_prove(ctx: Context, kind: int, polys, claim, transcript: Blake2bTra
     transcript.state = st.raw
     transcript.n_rounds = nr.value
     return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(rounds)], "challenges": chal, "final_claims": fin}
+
+
+# ---- one-hot address batches (witness.rs:84-99 -> OneHotPolynomial; hyperkzg/mod.rs:558-596; shout.rs:549-598) ----
+class OneHotAddresses:
+    """The d chunk-address lists of a node, resident on the device: (d, T) uint32 in [0, K), 0xFFFFFFFF = None."""
+
+    def __init__(self, ctx: Context, k, K: int):
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        assert k.ndim == 2
+        self.ctx, self.d, self.T, self.K = ctx, k.shape[0], k.shape[1], K
+        h = C.c_void_p()
+        check(ctx._lib.ja_addr_upload(ctx._h, k.ctypes.data_as(_lib.u32p), self.d, self.T, K, C.byref(h)))
+        self._h = h
+
+    def commit(self, srs: SRS):
+        """HyperKZG::batch_commit_one_hot over the resident lists -> ((d, 8) xy limbs, (d,) is_infinity)."""
+        out, inf = _pt_out(self.d)
+        check(self.ctx._lib.ja_addr_commit(self.ctx._h, srs._h, self._h, _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+        return out, inf.astype(bool)
+
+    def gather(self, tables):
+        """RaPolynomial::new(indices, table_i) for every list in one launch: tables (d, K, 4) -> d polynomials."""
+        tables = np.ascontiguousarray(tables, dtype=np.uint64).reshape(self.d, self.K, 4)
+        arr = (C.c_void_p * self.d)()
+        check(self.ctx._lib.ja_addr_gather(self.ctx._h, self._h, _u64p(tables), arr))
+        return [MultilinearPolynomial(self.ctx, C.c_void_p(arr[i])) for i in range(self.d)]
+
+    def ra_evals(self, r_cycle) -> np.ndarray:
+        """compute_ra_evals: G[i][k] = sum_{t: k_i[t] == k} eq(r_cycle, t) -> (d, K, 4)."""
+        r = _fr_arg(r_cycle).reshape(-1, 4)
+        out = np.zeros((self.d, self.K, 4), dtype=np.uint64)
+        check(self.ctx._lib.ja_addr_ra_evals(self.ctx._h, self._h, _u64p(r), r.shape[0], _u64p(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_addr_free(self.ctx._h, self._h)
+            self._h = None
+
+
+class InstanceKind:
+    BOOLEANITY, HAMMING_TABLES = 32, 33
+
+
+def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscriptState, max_coeffs: int = 40):
+    """BatchedSumcheck::prove (sumcheck.rs:30-184).  `instances`: list of dicts
+         device kinds   {"kind": EvalKernel.*, "polys": [MultilinearPolynomial...], "eq_w", "aux_fr", "aux_u32", "claim"}
+         BOOLEANITY     {"kind": 32, "tables": G (d, K, 4), "addr": OneHotAddresses, "eq_w": r_cycle, "gammas", "r_address"}
+         HAMMING_TABLES {"kind": 33, "tables": G (d, K, 4), "aux_fr": gamma powers, "claim"}
+    Device polynomials are consumed.  Returns dict(coeffs, challenges, final_claims=[per instance (n, 4)])."""
+    n = len(instances)
+    arr = (_lib.ScInstance * n)()
+    keep, finals, max_rounds = [], [], 0
+    for i, d in enumerate(instances):
+        kind = int(d["kind"])
+        arr[i].kind = kind
+        arr[i].aux_u32 = int(d.get("aux_u32", 0))
+        if kind in (InstanceKind.BOOLEANITY, InstanceKind.HAMMING_TABLES):
+            tabs = np.ascontiguousarray(d["tables"], dtype=np.uint64)
+            keep.append(tabs)
+            arr[i].n_polys, arr[i].table_len = tabs.shape[0], tabs.shape[1]
+            arr[i].host_tables = tabs.ctypes.data
+            npoly = tabs.shape[0]
+            rounds = tabs.shape[1].bit_length() - 1
+        else:
+            polys = d["polys"]
+            hs = (C.c_void_p * len(polys))(*[p._h for p in polys])
+            keep.append(hs)
+            arr[i].n_polys = len(polys)
+            arr[i].polys = C.cast(hs, C.c_void_p)
+            npoly = len(polys)
+            rounds = len(polys[0]).bit_length() - 1
+        aux = d.get("aux_fr")
+        if kind == InstanceKind.BOOLEANITY:
+            arr[i].addr = d["addr"]._h
+            ra = _fr_arg(d["r_address"]).reshape(-1, 4)
+            aux = np.concatenate([_fr_arg(d["gammas"]).reshape(-1, 4), ra])
+            arr[i].aux_u32 = ra.shape[0]
+            rounds = ra.shape[0] + _fr_arg(d["eq_w"]).reshape(-1, 4).shape[0]
+        for key, val in (("eq_w", d.get("eq_w")), ("aux_fr", aux)):
+            if val is not None:
+                v = np.ascontiguousarray(_fr_arg(val).reshape(-1, 4))
+                keep.append(v)
+                setattr(arr[i], key, v.ctypes.data)
+                setattr(arr[i], "eq_m" if key == "eq_w" else "n_aux", v.shape[0])
+        claim = _fr_arg(d.get("claim", np.zeros(4, dtype=np.uint64)))
+        for k in range(4):
+            arr[i].claim[k] = int(claim[k])
+        fc = np.zeros((npoly, 4), dtype=np.uint64)
+        finals.append(fc)
+        arr[i].out_final_claims = fc.ctypes.data
+        max_rounds = max(max_rounds, rounds)
+    coeffs = np.zeros((max_rounds, max_coeffs, 4), dtype=np.uint64)
+    ncoeffs = np.zeros(max_rounds, dtype=np.uint32)
+    chal = np.zeros((max_rounds, 4), dtype=np.uint64)
+    st = C.create_string_buffer(transcript.state, 32)
+    nr = C.c_uint32(transcript.n_rounds)
+    check(ctx._lib.ja_batched_sumcheck_prove(ctx._h, arr, n, st, C.byref(nr), max_coeffs, _u64p(coeffs),
+                                             ncoeffs.ctypes.data_as(_lib.u32p), _u64p(chal)))
+    transcript.state = st.raw
+    transcript.n_rounds = nr.value
+    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(max_rounds)], "challenges": chal, "final_claims": finals}

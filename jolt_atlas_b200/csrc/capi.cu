@@ -84,6 +84,9 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   JA_CUDA(cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int)));
   JA_CUDA(cudaMalloc(&c->d_out, sizeof(Fr) * kMaxOut));
   JA_CUDA(cudaMallocHost(&c->h_pinned, kPinnedBytes));
+  JA_CUDA(cudaHostAlloc(&c->h_mapped, kSlots * kSlotBytes, cudaHostAllocMapped));
+  memset(c->h_mapped, 0, kSlots * kSlotBytes);
+  JA_CUDA(cudaHostGetDevicePointer(&c->d_mapped, c->h_mapped, 0));
   JA_CUDA(cudaEventCreate(&c->ev0));
   JA_CUDA(cudaEventCreate(&c->ev1));
   *out = c;
@@ -96,6 +99,7 @@ void ja_shutdown(ja_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
   cudaFreeHost(c->h_pinned);
+  cudaFreeHost(c->h_mapped);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -289,6 +293,12 @@ static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& sca
   dev_free(c, d_r); dev_free(c, lv[0]); dev_free(c, lv[1]);
   return JA_OK;
 }
+
+}  // extern "C"
+int32_t eq_evals_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr* out) {
+  return eq_evals_device(c, reinterpret_cast<const FrH*>(r), m, host::FR_ONE, out);
+}
+extern "C" {
 
 int32_t ja_eq_evals(ja_ctx* c, const uint64_t* r, size_t m, const uint64_t* scale_or_null, ja_poly** out) {
   JA_REQUIRE(c && out && (r || m == 0), "ja_eq_evals: null argument");

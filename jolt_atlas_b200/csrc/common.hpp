@@ -45,6 +45,11 @@ struct ja_ctx {
   unsigned int* d_counter = nullptr;
   Fr* d_out = nullptr;             // kMaxOut
   uint64_t* h_pinned = nullptr;    // staging for small D2H/H2D
+  // host-mapped result slots of the sumcheck engine (sumcheck.cu): kSlots x kSlotBytes, sums at 0, sequence word at
+  // kSlotSeqOffset; h_mapped / d_mapped are the host and device addresses of the same pinned allocation
+  void* h_mapped = nullptr;
+  void* d_mapped = nullptr;
+  unsigned int seq = 0;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-kernel-class CUDA-event profile (ja_profile_begin / ja_profile_end; bench.py's roofline leg)
@@ -66,6 +71,8 @@ void ja_prof_post(ja_ctx* c);
 static constexpr int kMaxGrid = kSMs * 8;
 static constexpr int kMaxOut = 32;
 static constexpr size_t kPinnedBytes = 1 << 16;
+static constexpr int kSlots = 16;
+static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
 
 struct ja_poly {
   size_t len = 0;
@@ -84,6 +91,11 @@ struct ja_onehot {
   uint64_t* d_indices = nullptr;        // concatenated base indices k*T + t of every list
   std::vector<uint64_t> offsets;       // count + 1
   uint64_t max_index = 0;
+};
+
+struct ja_addr {
+  uint32_t* d_k = nullptr;   // d lists x T addresses in [0, K), 0xFFFFFFFF = None
+  size_t d = 0, T = 0, K = 0;
 };
 
 // one MSM of a batch (msm.cu): kind/nbits as in msm_kernels.cuh (0 = Fr Montgomery scalars, 254 bits)

@@ -1,0 +1,237 @@
+// Round kernels of the sumcheck engine (sumcheck.cu): "bind the previous challenge, then evaluate the next round" in ONE
+// pass, and publication of the reduced sums straight into host-mapped pinned memory.
+//
+// A sumcheck round on the reference is compute_message (reduce over the hypercube) followed, after the transcript, by
+// ingest_challenge (bind every MLE).  Launched separately that is two passes over each polynomial and two launches per
+// round; fused, round j+1's kernel reads the length-n arrays once, writes the bound length-n/2 arrays and emits the
+// sums over them: 48 n bytes per polynomial and round, the algorithmic minimum, and one launch.
+// Publication: the finishing block writes the sums to mapped host memory, fences at system scope and then stores a
+// sequence number the host spins on - no cudaMemcpyAsync, no cudaStreamSynchronize on the per-round critical path.
+//   LowToHigh (family S, product-of-d):  pair g of the bound array comes from in[4g .. 4g+3]
+//   HighToLow (family D):                pair (i, i+G) of the bound array comes from in[i], in[i+2G], in[i+G], in[i+3G] (in place)
+#pragma once
+#include "poly_kernels.cuh"
+
+namespace ja {
+
+struct Publish {
+  Fr* vals;                      // device address of the mapped host slot (kMaxOut Fr)
+  volatile unsigned int* seq;    // device address of the slot's sequence word
+  unsigned int value;
+};
+// call from every thread of the block that wrote pub.vals
+JA_DEV void publish_flag(const Publish& pub) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) { *pub.seq = pub.value; __threadfence_system(); }
+}
+
+struct FusedPolys {
+  const Fr* in[kMaxProdPolys];
+  Fr* out[kMaxProdPolys];        // FUSED only: bound arrays (LowToHigh: other ping-pong buffer; HighToLow: == in)
+};
+
+// (lo, hi) = elements (2g, 2g+1) of the array the round evaluates
+template <bool FUSED>
+JA_DEV void load_pair_l2h(const Fr* __restrict__ in, Fr* __restrict__ out, size_t g, const Challenge& r, Fr& lo, Fr& hi) {
+  if (FUSED) {
+    const Fr a0 = fp_load(in + 4 * g), a1 = fp_load(in + 4 * g + 1), a2 = fp_load(in + 4 * g + 2), a3 = fp_load(in + 4 * g + 3);
+    lo = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+    hi = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
+    fp_store(out + 2 * g, lo);
+    fp_store(out + 2 * g + 1, hi);
+  } else {
+    lo = fp_load(in + 2 * g);
+    hi = fp_load(in + 2 * g + 1);
+  }
+}
+
+// ---- family S (split-eq weighted, LowToHigh) ----------------------------------------------------------------------
+// KID: 0 ADD, 1 SUB, 2 MUL, 3 SQUARE, 6 IDENT (ids of include/jolt_atlas_b200.h), 7 BOOLEANITY phase 2
+//      (booleanity.rs:254-301: [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] over n_polys one-hot chunks).
+template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 || KID == 7) ? 2 : 1; };
+
+template <int KID, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
+          size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
+  constexpr int NOUT = SOut<KID>::N;
+  Fr outer[NOUT], inner[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)blockIdx.x * tiles_per_block * kBlock;
+  size_t g_end = g_begin + tiles_per_block * kBlock;
+  if (g_end > G) g_end = G;
+  size_t cur_xout = ~size_t(0);
+  for (size_t g = g_begin + threadIdx.x; g < g_end; g += kBlock) {
+    const size_t x_out = g >> bits_in;
+    if (x_out != cur_xout) {
+      if (cur_xout != ~size_t(0)) {
+        const Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) {
+          outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+          inner[k] = fp_zero<FrParams>();
+        }
+      }
+      cur_xout = x_out;
+    }
+    Fr v[NOUT];
+    if (KID == 7) {
+      v[0] = fp_zero<FrParams>(); v[1] = fp_zero<FrParams>();
+      for (int q = 0; q < n_polys; q++) {
+        Fr h0, h1;
+        load_pair_l2h<FUSED>(P.in[q], P.out[q], g, r, h0, h1);
+        const Fr gm = fp_load(gammas + q);
+        const Fr b = fp_sub<FrParams>(h1, h0);
+        v[0] = fp_add<FrParams>(v[0], fp_mul<FrParams>(fp_mul<FrParams>(gm, h0), fp_sub<FrParams>(h0, fp_one<FrParams>())));
+        v[1] = fp_add<FrParams>(v[1], fp_mul<FrParams>(fp_mul<FrParams>(gm, b), b));
+      }
+    } else if (KID == 3 || KID == 6) {
+      Fr o0, o1;
+      load_pair_l2h<FUSED>(P.in[0], P.out[0], g, r, o0, o1);
+      if (KID == 6) v[0] = o0;
+      else { const Fr d = fp_sub<FrParams>(o1, o0); v[0] = fp_sqr<FrParams>(o0); v[NOUT - 1] = fp_sqr<FrParams>(d); }
+    } else {
+      Fr l0, l1, r0, r1;
+      load_pair_l2h<FUSED>(P.in[0], P.out[0], g, r, l0, l1);
+      load_pair_l2h<FUSED>(P.in[1], P.out[1], g, r, r0, r1);
+      if (KID == 0) v[0] = fp_add<FrParams>(l0, r0);
+      else if (KID == 1) v[0] = fp_sub<FrParams>(l0, r0);
+      else { v[0] = fp_mul<FrParams>(l0, r0); v[NOUT - 1] = fp_mul<FrParams>(fp_sub<FrParams>(l1, l0), fp_sub<FrParams>(r1, r0)); }
+    }
+    const Fr ei = fp_load(e_in + (g & mask_in));
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
+  }
+  if (cur_xout != ~size_t(0)) {
+    const Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+  }
+  if (grid_sum<NOUT>(outer, partials, counter, pub.vals)) publish_flag(pub);
+}
+
+// ---- product of d <= 16 linear factors, warp-transposed (see k_round_eval_prod_t), with the fused bind -------------
+template <int L, bool SAME, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub) {
+  constexpr int GPB = kBlock / L;
+  const int li = threadIdx.x & (L - 1);
+  const int group = threadIdx.x / L;
+  const bool pad = li >= d;
+  // SAME (x^d of one MLE): every lane reads polynomial 0; only lane 0 writes the bound array
+  const int pi = (SAME || pad) ? 0 : li;
+  const Fr* __restrict__ zin = P.in[pi];
+  Fr* __restrict__ zout = P.out[pi];
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  size_t g_end = g_begin + pairs_per_block;
+  if (g_end > G) g_end = G;
+  Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
+  size_t cur_xout = ~size_t(0);
+  for (size_t base = g_begin; base < g_end; base += GPB) {
+    const size_t g = base + group;
+    const bool active = g < g_end;
+    const size_t gl = active ? g : g_begin;
+    Fr p0, dp;
+    if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
+    else if (FUSED) {
+      const Fr a0 = fp_load(zin + 4 * gl), a1 = fp_load(zin + 4 * gl + 1), a2 = fp_load(zin + 4 * gl + 2), a3 = fp_load(zin + 4 * gl + 3);
+      p0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+      const Fr p1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
+      if (active && (!SAME || li == 0)) { fp_store(zout + 2 * gl, p0); fp_store(zout + 2 * gl + 1, p1); }
+      dp = fp_sub<FrParams>(p1, p0);
+    } else {
+      p0 = fp_load(zin + 2 * gl);
+      dp = fp_sub<FrParams>(fp_load(zin + 2 * gl + 1), p0);
+    }
+    Fr v[L];
+    Fr cur = p0;
+#pragma unroll
+    for (int k = 0; k < L - 1; k++) { cur = fp_add<FrParams>(cur, dp); v[k] = cur; }
+    v[L - 1] = pad ? p0 : dp;
+    LaneProduct<L>::run(v, li);
+    if (active) {
+      const size_t x_out = g >> bits_in;
+      if (x_out != cur_xout) {
+        if (cur_xout != ~size_t(0)) {
+          outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
+          inner = fp_zero<FrParams>();
+        }
+        cur_xout = x_out;
+      }
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + (g & mask_in)), v[0]));
+    }
+  }
+  if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
+  Fr tot = block_sum_by_lane<L>(outer);
+  if (gridDim.x == 1) {
+    if (threadIdx.x < L) fp_store(pub.vals + threadIdx.x, tot);
+    publish_flag(pub);
+    return;
+  }
+  if (threadIdx.x < L) fp_store(partials + (size_t)blockIdx.x * L + threadIdx.x, tot);
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Fr acc = fp_zero<FrParams>();
+  for (unsigned b = threadIdx.x / L; b < gridDim.x; b += GPB) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(partials + (size_t)b * L + li);
+    Fr t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.l[i] = q[i];
+    acc = fp_add<FrParams>(acc, t);
+  }
+  tot = block_sum_by_lane<L>(acc);
+  if (threadIdx.x < L) fp_store(pub.vals + threadIdx.x, tot);
+  publish_flag(pub);
+}
+
+// ---- family D (plain products at X in {0,2,3}, HighToLow), fused bind in place ------------------------------------------
+template <int NPOLY, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array: it has 2G entries */, Fr* partials,
+            unsigned int* counter, Publish pub) {
+  constexpr int NOUT = NPOLY;
+  Fr acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) acc[k] = fp_zero<FrParams>();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride) {
+    Fr prod[NOUT];
+#pragma unroll
+    for (int q = 0; q < NPOLY; q++) {
+      Fr a, b;
+      if (FUSED) {
+        Fr* z = P.out[q];      // in place
+        const Fr a0 = fp_load(z + i), a1 = fp_load(z + i + 2 * G), b0 = fp_load(z + i + G), b1 = fp_load(z + i + 3 * G);
+        a = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+        b = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
+        fp_store(z + i, a);
+        fp_store(z + i + G, b);
+      } else {
+        a = fp_load(P.in[q] + i);
+        b = fp_load(P.in[q] + i + G);
+      }
+      const Fr m = fp_sub<FrParams>(b, a);
+      const Fr e = fp_add<FrParams>(b, m);   // X = 2
+      if (q == 0) { prod[0] = a; prod[1] = e; } else { prod[0] = fp_mul<FrParams>(prod[0], a); prod[1] = fp_mul<FrParams>(prod[1], e); }
+      if (NOUT == 3) {
+        const Fr e3 = fp_add<FrParams>(e, m);  // X = 3
+        if (q == 0) prod[2] = e3; else prod[2] = fp_mul<FrParams>(prod[2], e3);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) acc[k] = fp_add<FrParams>(acc[k], prod[k]);
+  }
+  if (grid_sum<NOUT>(acc, partials, counter, pub.vals)) publish_flag(pub);
+}
+
+}  // namespace ja

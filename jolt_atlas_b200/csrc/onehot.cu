@@ -1,0 +1,209 @@
+// One-hot address batches resident on the device: the d chunk-address lists of a node (Option<u8/u16> per cycle,
+// K = 2^log_k_chunk = 16) are uploaded ONCE as u32 (0xFFFFFFFF = None, 4 B per entry) and every consumer derives what
+// it needs from them on the device:
+//   ja_addr_commit      HyperKZG::batch_commit_one_hot (hyperkzg/mod.rs:558-596): C_i = sum_t G[k_i[t] * T + t]
+//   ja_addr_gather      RaPolynomial materialisation (poly/ra_poly.rs:31-81): ra_i[t] = table_i[k_i[t]]
+//   ja_addr_ra_evals    compute_ra_evals (subprotocols/shout.rs:549-598): G_i[k] = sum_{t: k_i[t] = k} eq(r_cycle, t)
+// No CPU fallback.
+#include "common.hpp"
+#include "fq_host.hpp"
+#include "msm_kernels.cuh"
+#include "poly_kernels.cuh"
+
+namespace ja {
+
+// point sums straight from the address lists: entry t of list i selects base k*T + t
+static __global__ void __launch_bounds__(kIdxBlock)
+k_addr_partial(const uint32_t* __restrict__ k_all, uint32_t T, uint32_t blocks_per_list, const G1Aff* __restrict__ bases,
+               G1X* __restrict__ partial) {
+  __shared__ G1X s_acc[kIdxBlock];
+  const uint32_t list = blockIdx.x / blocks_per_list, blk = blockIdx.x % blocks_per_list;
+  const uint32_t* __restrict__ k = k_all + (size_t)list * T;
+  const uint32_t base = blk * (kIdxBlock * kIdxRun);
+  G1X acc = g1x_inf();
+  uint32_t e = base + threadIdx.x;
+  uint32_t kk = e < T ? __ldg(k + e) : 0xffffffffu;
+  G1Aff pt;
+  if (kk != 0xffffffffu) pt = g1aff_load(bases + (size_t)kk * T + e);
+#pragma unroll 1
+  for (int r = 0; r < kIdxRun; r++) {
+    if (e >= T) break;
+    const G1Aff cur = pt;
+    const bool have = kk != 0xffffffffu;
+    e += kIdxBlock;
+    if (r + 1 < kIdxRun && e < T) {
+      kk = __ldg(k + e);
+      if (kk != 0xffffffffu) pt = g1aff_load(bases + (size_t)kk * T + e);
+    }
+    if (have) g1x_madd(acc, cur, false);
+  }
+  const G1X tot = block_point_sum(acc, s_acc);
+  if (threadIdx.x == 0) g1x_store(partial + blockIdx.x, tot);
+}
+static __global__ void __launch_bounds__(kIdxBlock)
+k_addr_final(const G1X* __restrict__ partial, uint32_t blocks_per_list, G1X* __restrict__ out) {
+  __shared__ G1X s_acc[kIdxBlock];
+  G1X acc = g1x_inf();
+  for (uint32_t b = threadIdx.x; b < blocks_per_list; b += kIdxBlock) g1x_add(acc, g1x_load(partial + (size_t)blockIdx.x * blocks_per_list + b));
+  const G1X tot = block_point_sum(acc, s_acc);
+  if (threadIdx.x == 0) g1x_store(out + blockIdx.x, tot);
+}
+
+// ra_i[t] = table_i[k_i[t]] for all d lists in one launch (blockIdx.y = list)
+struct GatherOut { Fr* p[kMaxProdPolys]; };
+static __global__ void __launch_bounds__(kBlock)
+k_addr_gather(const uint32_t* __restrict__ k_all, size_t T, const Fr* __restrict__ tables, uint32_t K, GatherOut out) {
+  const uint32_t* __restrict__ k = k_all + (size_t)blockIdx.y * T;
+  const Fr* __restrict__ tab = tables + (size_t)blockIdx.y * K;
+  Fr* __restrict__ dst = out.p[blockIdx.y];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += stride) {
+    const uint32_t kk = __ldg(k + t);
+    fp_store(dst + t, kk == 0xffffffffu ? fp_zero<FrParams>() : fp_load(tab + kk));
+  }
+}
+
+// G_i[k] partial sums.  Block = 16 bins x 16 entry lanes (K <= 16 per pass over bins); grid (tiles, d).
+constexpr int kRaTile = 1024;      // entries per block
+static __global__ void __launch_bounds__(256)
+k_ra_evals_partial(const uint32_t* __restrict__ k_all, size_t T, const Fr* __restrict__ eq, uint32_t K, uint32_t k_base,
+                   Fr* __restrict__ partial /* [d][tiles][16] */) {
+  __shared__ Fr s_bin[16][16];
+  const uint32_t bin = threadIdx.x & 15, lane = threadIdx.x >> 4;
+  const uint32_t* __restrict__ k = k_all + (size_t)blockIdx.y * T;
+  const size_t t0 = (size_t)blockIdx.x * kRaTile;
+  Fr acc = fp_zero<FrParams>();
+  for (size_t t = t0 + lane; t < t0 + kRaTile && t < T; t += 16)
+    if (__ldg(k + t) == k_base + bin) acc = fp_add<FrParams>(acc, fp_load(eq + t));
+  s_bin[lane][bin] = acc;
+  __syncthreads();
+  if (lane == 0) {
+    Fr tot = s_bin[0][bin];
+    for (int l = 1; l < 16; l++) tot = fp_add<FrParams>(tot, s_bin[l][bin]);
+    fp_store(partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + bin, tot);
+  }
+}
+static __global__ void __launch_bounds__(256)
+k_ra_evals_final(const Fr* __restrict__ partial, uint32_t tiles, uint32_t d, uint32_t K, uint32_t k_base, Fr* __restrict__ out /* [d][K] */) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= d * 16) return;
+  const uint32_t i = id >> 4, bin = id & 15;
+  if (k_base + bin >= K) return;
+  Fr tot = fp_zero<FrParams>();
+  for (uint32_t b = 0; b < tiles; b++) tot = fp_add<FrParams>(tot, fp_load(partial + ((size_t)i * tiles + b) * 16 + bin));
+  fp_store(out + (size_t)i * K + k_base + bin, tot);
+}
+
+}  // namespace ja
+
+int32_t eq_evals_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr* out);   // capi.cu
+
+extern "C" {
+
+int32_t ja_addr_upload(ja_ctx* c, const uint32_t* k, size_t d, size_t T, size_t K, ja_addr** out) {
+  JA_REQUIRE(c && k && out && d > 0 && T > 0 && K > 0, "ja_addr_upload: null or empty argument");
+  JA_REQUIRE(d <= (size_t)kMaxProdPolys, "ja_addr_upload: at most 32 lists per batch");
+  JA_REQUIRE(T < (size_t(1) << 31) && K <= 65536, "ja_addr_upload: T or K too large");
+  for (size_t i = 0; i < d * T; i++)
+    JA_REQUIRE(k[i] == 0xffffffffu || k[i] < K, "ja_addr_upload: address outside [0, K)");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  ja_addr* a = new ja_addr();
+  a->d = d; a->T = T; a->K = K;
+  int32_t st = dev_alloc(c, d * T * sizeof(uint32_t), (void**)&a->d_k);
+  if (st) { delete a; return st; }
+  JA_CUDA(cudaMemcpyAsync(a->d_k, k, d * T * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  *out = a;
+  return JA_OK;
+}
+
+void ja_addr_free(ja_ctx* c, ja_addr* a) {
+  if (!c || !a) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  dev_free(c, a->d_k);
+  delete a;
+}
+
+int32_t ja_addr_commit(ja_ctx* c, const ja_srs* srs, const ja_addr* a, uint64_t* out_xy, int32_t* is_inf) {
+  JA_REQUIRE(c && srs && a && out_xy, "ja_addr_commit: null argument");
+  if (a->K * a->T > srs->n)
+    return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, one-hot polynomial needs " +
+                                       std::to_string(a->K * a->T));
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const uint32_t bpl = (uint32_t)((a->T + kIdxBlock * kIdxRun - 1) / (kIdxBlock * kIdxRun));
+  const size_t blocks = (size_t)bpl * a->d;
+  G1X* ws = nullptr;
+  int32_t st = dev_alloc(c, sizeof(G1X) * (blocks + a->d), (void**)&ws);
+  if (st) return st;
+  G1X* d_out = ws + blocks;
+  JA_LAUNCH(c, KC_ONEHOT_SUM, k_addr_partial<<<(unsigned)blocks, kIdxBlock, 0, c->stream>>>(a->d_k, (uint32_t)a->T, bpl, srs->points, ws));
+  JA_LAUNCH(c, KC_ONEHOT_SUM, k_addr_final<<<(unsigned)a->d, kIdxBlock, 0, c->stream>>>(ws, bpl, d_out));
+  JA_CUDA(cudaGetLastError());
+  JA_REQUIRE(a->d * sizeof(G1X) <= kPinnedBytes, "ja_addr_commit: batch too large for the staging buffer");
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, d_out, sizeof(G1X) * a->d, cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  dev_free(c, ws);
+  std::vector<int32_t> inf(a->d);
+  host::xyzz_batch_to_affine(reinterpret_cast<const host::G1XH*>(c->h_pinned), a->d, out_xy, inf.data());
+  if (is_inf) memcpy(is_inf, inf.data(), sizeof(int32_t) * a->d);
+  return JA_OK;
+}
+
+int32_t ja_addr_gather(ja_ctx* c, const ja_addr* a, const uint64_t* tables, ja_poly** out_polys) {
+  JA_REQUIRE(c && a && tables && out_polys, "ja_addr_gather: null argument");
+  JA_REQUIRE(is_pow2(a->T), "ja_addr_gather: T must be a power of two");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const size_t tab_bytes = a->d * a->K * sizeof(Fr);
+  JA_REQUIRE(tab_bytes <= kPinnedBytes, "ja_addr_gather: tables too large for the staging buffer");
+  Fr* d_tab = nullptr;
+  int32_t st = dev_alloc(c, tab_bytes, (void**)&d_tab);
+  if (st) return st;
+  memcpy(c->h_pinned, tables, tab_bytes);
+  JA_CUDA(cudaMemcpyAsync(d_tab, c->h_pinned, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  GatherOut go;
+  for (size_t i = 0; i < a->d; i++) {
+    if ((st = ja_poly_alloc(c, a->T, &out_polys[i]))) return st;
+    go.p[i] = out_polys[i]->buf[0];
+  }
+  unsigned gx = grid_for(a->T);
+  if (gx > (unsigned)kSMs * 2) gx = kSMs * 2;
+  JA_LAUNCH(c, KC_CONVERT, k_addr_gather<<<dim3(gx, (unsigned)a->d), kBlock, 0, c->stream>>>(a->d_k, a->T, d_tab, (uint32_t)a->K, go));
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaStreamSynchronize(c->stream));   // h_pinned is reused by later calls
+  dev_free(c, d_tab);
+  return JA_OK;
+}
+
+int32_t ja_addr_ra_evals(ja_ctx* c, const ja_addr* a, const uint64_t* r_cycle, size_t log_t, uint64_t* out_G) {
+  JA_REQUIRE(c && a && r_cycle && out_G, "ja_addr_ra_evals: null argument");
+  JA_REQUIRE((size_t(1) << log_t) == a->T, "ja_addr_ra_evals: r_cycle length does not match T");
+  JA_REQUIRE(a->d * a->K * sizeof(Fr) <= kPinnedBytes, "ja_addr_ra_evals: result too large for the staging buffer");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  const uint32_t tiles = (uint32_t)((a->T + kRaTile - 1) / kRaTile);
+  Fr* ws = nullptr;
+  const size_t n_part = a->d * (size_t)tiles * 16, n_out = a->d * a->K;
+  int32_t st = dev_alloc(c, (a->T + n_part + n_out) * sizeof(Fr), (void**)&ws);
+  if (st) return st;
+  Fr *d_eq = ws, *d_part = ws + a->T, *d_out = d_part + n_part;
+  if ((st = eq_evals_device_pub(c, r_cycle, log_t, d_eq))) return st;
+  for (uint32_t k_base = 0; k_base < a->K; k_base += 16) {
+    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_partial<<<dim3(tiles, (unsigned)a->d), 256, 0, c->stream>>>(a->d_k, a->T, d_eq, (uint32_t)a->K, k_base, d_part));
+    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_final<<<(unsigned)((a->d * 16 + 255) / 256), 256, 0, c->stream>>>(d_part, tiles, (uint32_t)a->d, (uint32_t)a->K, k_base, d_out));
+  }
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out_G, c->h_pinned, n_out * sizeof(Fr));
+  dev_free(c, ws);
+  return JA_OK;
+}
+
+size_t ja_addr_len(const ja_addr* a) { return a ? a->T : 0; }
+size_t ja_addr_count(const ja_addr* a) { return a ? a->d : 0; }
+
+}  // extern "C"

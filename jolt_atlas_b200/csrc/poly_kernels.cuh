@@ -53,8 +53,9 @@ JA_DEV Fr fr_warp_sum(Fr a) {
 
 // Block-wide exact field sum of NOUT values per thread, then grid-wide via per-block partials and a
 // "last block" pass.  `partials` holds gridDim.x * NOUT Fr; `counter` must be 0 on entry and is reset.
+// Returns true (block-uniform) in the one block that wrote `out`.
 template <int NOUT>
-JA_DEV void grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out) {
+JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out) {
   __shared__ Fr s_part[kBlock / 32][NOUT];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,7 +78,7 @@ JA_DEV void grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
 #pragma unroll
       for (int k = 0; k < NOUT; k++) out[k] = partials[k];
     }
-    return;
+    return true;
   }
   __threadfence();
   __syncthreads();
@@ -86,7 +87,7 @@ JA_DEV void grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
 #pragma unroll
   for (int k = 0; k < NOUT; k++) {
@@ -111,6 +112,7 @@ JA_DEV void grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
       if (lane == 0) fp_store(&out[k], v);
     }
   }
+  return true;
 }
 
 // ---- variable binding (the "fold") ------------------------------------------------------------

@@ -1,74 +1,615 @@
-// Sumcheck::prove (joltworks/src/subprotocols/sumcheck.rs:565-599) with the per-round work on the device:
-//   compute_message  -> ja_round_eval (one kernel, reduced sums back to the host) + O(degree) interpolation
-//   transcript       -> the library's Blake2b transcript (blake2b.rs; UniPoly_begin / coeffs except linear / UniPoly_end,
-//                       unipoly.rs:550-558), challenge_scalar_optimized
-//   ingest_challenge -> ja_bind_many (one kernel for all participating MLEs) + GruenSplitEqPolynomial::bind
-// Built only from the public C ABI above it; a Rust caller that owns the transcript drives the same three calls itself
-// (INTEGRATION.md).  Instance kinds = the JA_EVAL_* bodies of include/jolt_atlas_b200.h.
+// The sumcheck engine: Sumcheck::prove (joltworks/src/subprotocols/sumcheck.rs:565-599) and BatchedSumcheck::prove
+// (:30-184) with the per-round work on the device and the Fiat-Shamir transcript (blake2b.rs) on the host.
+//
+// Round structure (one host<->device exchange per round for ALL instances of a batch):
+//   launch     every active instance enqueues ONE kernel: [bind the previous challenge +] evaluate this round
+//              (fused_kernels.cuh); the finishing block publishes the reduced sums into host-mapped memory
+//   overlap    while the kernels run the host does the round's field inversion (gruen_poly_deg_2/3 divide by
+//              eq(1), finish_mles_product_sum by eq(0): both depend on the eq state only)
+//   collect    the host spins on the slot's sequence word, assembles each instance's univariate (O(degree^2) glue with
+//              cached interpolation matrices), batches them, compresses, appends to the transcript (unipoly.rs:550-558),
+//              draws r_j (challenge_scalar_optimized) and evaluates the claims
+//   ingest     host-side eq state update; the device bind is DEFERRED into the next round's kernel
+// Instance kinds: the JA_EVAL_* round bodies on device polynomials, Booleanity (booleanity.rs; address rounds on the
+// K-entry tables stay on the host, cycle rounds on the device) and the Hamming-weight instance over the G tables
+// (hamming_weight.rs; K entries, host).  A Rust caller that owns the transcript can drive ja_round_eval / ja_bind_many
+// itself; this driver is the same protocol with the library's transcript.
+#include <chrono>
+#include <cstdlib>
+#include <memory>
+
 #include "common.hpp"
+#include "fused_kernels.cuh"
 #include "sumcheck_host.hpp"
 #include "transcript_host.hpp"
 
-#include <chrono>
-#include <cstdlib>
 using host::Coeffs;
+
+namespace {
 
 // JA_SC_TRACE=1: per-phase host wall-clock of the round loop on stderr (tuning aid)
 struct ScTrace {
   bool on = getenv("JA_SC_TRACE") != nullptr;
-  double t[6] = {0, 0, 0, 0, 0, 0};
+  double t[4] = {0, 0, 0, 0};
   std::chrono::steady_clock::time_point last;
   void start() { if (on) last = std::chrono::steady_clock::now(); }
   void lap(int k) { if (!on) return; auto n = std::chrono::steady_clock::now(); t[k] += std::chrono::duration<double, std::micro>(n - last).count(); last = n; }
 };
-static ScTrace g_trace;
+ScTrace g_trace;
 
-namespace {
+// ---- host-mapped result slots ------------------------------------------------------------------------------------
+struct Slot {
+  const uint64_t* host_vals = nullptr;
+  volatile unsigned int* host_seq = nullptr;
+  Publish pub;
+  bool armed = false;
+};
+Slot arm_slot(ja_ctx* c, int s) {
+  Slot r;
+  char* h = reinterpret_cast<char*>(c->h_mapped) + (size_t)s * kSlotBytes;
+  char* d = reinterpret_cast<char*>(c->d_mapped) + (size_t)s * kSlotBytes;
+  r.host_vals = reinterpret_cast<const uint64_t*>(h);
+  r.host_seq = reinterpret_cast<volatile unsigned int*>(h + kSlotSeqOffset);
+  r.pub.vals = reinterpret_cast<Fr*>(d);
+  r.pub.seq = reinterpret_cast<volatile unsigned int*>(d + kSlotSeqOffset);
+  r.pub.value = ++c->seq;
+  r.armed = true;
+  return r;
+}
+int32_t wait_slot(ja_ctx* c, const Slot& s) {
+  uint64_t spins = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  while (*s.host_seq != s.pub.value) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xffff) == 0) {
+      // a failed launch / faulted kernel never publishes: surface the CUDA error instead of spinning forever
+      cudaError_t e = cudaStreamQuery(c->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JA_ERR_CUDA, std::string("sumcheck round kernel: ") + cudaGetErrorString(e));
+      if (e == cudaSuccess && *s.host_seq != s.pub.value) return fail(JA_ERR_CUDA, "sumcheck round kernel finished without publishing its sums");
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
+        return fail(JA_ERR_CUDA, "sumcheck round kernel: timed out waiting for the published sums");
+    }
+  }
+  return JA_OK;
+}
 
-struct Instance {
-  int32_t kind;
+// ---- GruenSplitEqPolynomial on the host for K-entry address rounds (split_eq_poly.rs:86-145,331-372; LowToHigh) ----
+struct HostEq {
+  std::vector<FrH> w;
+  size_t ci = 0;
+  FrH scalar = host::FR_ONE;
+  void init(const uint64_t* limbs, size_t m) { w.resize(m); for (size_t i = 0; i < m; i++) w[i] = host::from_limbs(limbs + 4 * i); ci = m; }
+  FrH current_w() const { return w[ci - 1]; }
+  void bind(const FrH& r) {
+    const FrH wv = current_w(), prod = host::mul(wv, r);
+    FrH f = host::sub(host::sub(host::FR_ONE, wv), r);
+    f = host::add(host::add(f, prod), prod);
+    scalar = host::mul(scalar, f);
+    ci--;
+  }
+  // E_out (x) E_in over the variables still to be bound after the current one: eq(w[0 .. ci-1), .), w[0] = MSB
+  std::vector<FrH> table() const {
+    std::vector<FrH> t{host::FR_ONE};
+    for (size_t j = 0; j + 1 < ci; j++) {
+      std::vector<FrH> n(t.size() * 2);
+      for (size_t i = 0; i < t.size(); i++) { n[2 * i + 1] = host::mul(t[i], w[j]); n[2 * i] = host::sub(t[i], n[2 * i + 1]); }
+      t.swap(n);
+    }
+    return t;
+  }
+};
+
+Coeffs scaled(const Coeffs& c, const FrH& s) {        // &UniPoly * F (unipoly.rs:455-461): from_coeff trims
+  Coeffs o(c.size());
+  for (size_t i = 0; i < c.size(); i++) o[i] = host::mul(c[i], s);
+  return host::trim(o);
+}
+void add_assign(Coeffs& a, const Coeffs& b) {         // unipoly.rs:401-412
+  for (size_t i = 0; i < a.size() && i < b.size(); i++) a[i] = host::add(a[i], b[i]);
+  if (a.size() < b.size()) a.insert(a.end(), b.begin() + a.size(), b.end());
+}
+FrH mul_pow_2(FrH x, size_t k) { for (size_t i = 0; i < k; i++) x = host::dbl(x); return x; }   // field/mod.rs:274-284
+
+// ---- instances -------------------------------------------------------------------------------------------------------
+struct Inst {
+  size_t rounds = 0;
+  FrH claim = host::FR_ZERO;
+  uint64_t* out_final = nullptr;
+  virtual ~Inst() {}
+  virtual int32_t launch(ja_ctx* c, size_t round, int slot) = 0;
+  virtual int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) = 0;
+  virtual int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t round) = 0;
+  // flush deferred work and enqueue the D2H of the final claims into `staging` (pinned); *count = number of Fr written
+  virtual int32_t finalize(ja_ctx* c, uint64_t* staging, size_t* count) = 0;
+  virtual void release(ja_ctx*) {}
+};
+
+// device-resident polynomials, one JA_EVAL_* body (or booleanity phase 2 = body 7)
+struct DevInst : Inst {
+  int32_t kind = 0;
   std::vector<ja_poly*> polys;
-  ja_spliteq* eq = nullptr;        // family S / PROD / POW
-  std::vector<FrH> gammas;         // SUM1
+  ja_spliteq* eq = nullptr;
+  bool own_eq = false;
+  std::vector<FrH> gammas;          // SUM1 (host combination) / body 7 (device copy in d_gammas)
+  Fr* d_gammas = nullptr;
   uint32_t pow_d = 0;
   int order = JA_LOW_TO_HIGH;
   size_t n_out = 0;
+  bool fusable = false, pending = false;
+  uint64_t pend_ch[4] = {0, 0, 0, 0};
+  FrH scale = host::FR_ONE;         // body 7: eq_r_r (booleanity.rs:295-300)
+  bool has_scale = false;
+  FrH scale_inv = host::FR_ONE;
+  // per-round state between launch and message
+  Slot slot;
+  RoundEvalPending pend;
+  bool legacy = false;              // round went through ja_round_eval_launch (pinned staging + stream sync)
+  FrH cs, cw, div;
+  int prod_lanes = 0;
+
+  int32_t setup(ja_ctx* c) {
+    const size_t len = polys[0]->len;
+    for (ja_poly* p : polys) JA_REQUIRE(p && p->len == len, "sumcheck: polynomials of one instance must have equal length");
+    JA_REQUIRE(len >= 2 && is_pow2(len), "sumcheck: polynomial length must be a power of two >= 2");
+    rounds = (size_t)log2z(len);
+    switch (kind) {
+      case JA_EVAL_ADD: case JA_EVAL_SUB: n_out = 1; JA_REQUIRE(polys.size() == 2, "sumcheck: ADD/SUB take two polynomials"); fusable = true; break;
+      case JA_EVAL_IDENT: n_out = 1; JA_REQUIRE(polys.size() == 1, "sumcheck: IDENT takes one polynomial"); fusable = true; break;
+      case JA_EVAL_MUL: n_out = 2; JA_REQUIRE(polys.size() == 2, "sumcheck: MUL takes two polynomials"); fusable = true; break;
+      case JA_EVAL_SQUARE: n_out = 2; JA_REQUIRE(polys.size() == 1, "sumcheck: SQUARE takes one polynomial"); fusable = true; break;
+      case 7: n_out = 2; fusable = true; break;
+      case JA_EVAL_PROD: n_out = polys.size(); fusable = polys.size() <= 16; break;
+      case JA_EVAL_POW: n_out = pow_d; JA_REQUIRE(polys.size() == 1, "sumcheck: POW takes one polynomial"); fusable = pow_d <= 16; break;
+      case JA_EVAL_DOT2: n_out = 2; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 2, "sumcheck: DOT2 takes two polynomials"); fusable = true; break;
+      case JA_EVAL_DOT3: n_out = 3; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 3, "sumcheck: DOT3 takes three polynomials"); fusable = true; break;
+      case JA_EVAL_SUM1: n_out = 1; break;
+      case JA_EVAL_SUMHI: n_out = 1; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 1, "sumcheck: SUMHI takes one polynomial"); break;
+      default: return fail(JA_ERR_UNSUPPORTED, "sumcheck: kind not implemented");
+    }
+    JA_REQUIRE(n_out >= 1 && n_out <= (size_t)kMaxOut && polys.size() <= (size_t)kMaxProdPolys, "sumcheck: too many polynomials / outputs");
+    if (kind == 7) {
+      JA_REQUIRE(gammas.size() == polys.size(), "sumcheck: booleanity takes one gamma per polynomial");
+      int32_t st = dev_alloc(c, gammas.size() * sizeof(Fr), (void**)&d_gammas);
+      if (st) return st;
+      JA_CUDA(cudaMemcpyAsync(d_gammas, gammas.data(), gammas.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+      JA_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return JA_OK;
+  }
+  bool uses_eq() const { return kind <= 7; }
+
+  // fused round kernel (bind pend_ch first when `pending`)
+  int32_t launch_fused(ja_ctx* c) {
+    const bool fz = pending;
+    const size_t len_in = polys[0]->len;
+    const size_t len_eval = fz ? len_in / 2 : len_in;      // length of the arrays this round evaluates
+    const size_t G = len_eval / 2;
+    FusedPolys P;
+    for (size_t q = 0; q < polys.size(); q++) {
+      ja_poly* p = polys[q];
+      P.in[q] = p->data();
+      P.out[q] = p->data();
+      if (fz && order == JA_LOW_TO_HIGH) {
+        const int nxt = 1 - p->cur;
+        if (p->cap[nxt] < len_eval) {
+          dev_free(c, p->buf[nxt]);
+          p->buf[nxt] = nullptr; p->cap[nxt] = 0;
+          int32_t st = dev_alloc(c, len_eval * sizeof(Fr), (void**)&p->buf[nxt]);
+          if (st) return st;
+          p->cap[nxt] = len_eval;
+        }
+        P.out[q] = p->buf[nxt];
+      }
+    }
+    const Challenge ch = to_challenge(pend_ch);
+    int bits_in = 0;
+    const Fr *e_out = nullptr, *e_in = nullptr;
+    if (uses_eq()) {
+      JA_REQUIRE(eq && eq->order == JA_LOW_TO_HIGH, "sumcheck: family S expects a LowToHigh split-eq");
+      const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
+      JA_REQUIRE(cover == G, "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+      bits_in = eq->in_len - 1; e_out = eq->e_out(); e_in = eq->e_in();
+    }
+    cudaStream_t s = c->stream;
+    Fr* part = c->d_partials; unsigned int* ctr = c->d_counter;
+    const Publish pub = slot.pub;
+    if (kind == JA_EVAL_PROD || kind == JA_EVAL_POW) {
+      const int d = kind == JA_EVAL_POW ? (int)pow_d : (int)polys.size();
+      const bool same = kind == JA_EVAL_POW;
+      int L = 2; while (L < d) L <<= 1;
+      const size_t gpb = (size_t)kBlock / L;
+      size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
+      ppb = (ppb + gpb - 1) / gpb * gpb;
+      const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
+#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub))
+#define JA_PROD_L(LL) do { if (same) { if (fz) JA_PROD_F(LL, true, true); else JA_PROD_F(LL, true, false); } \
+                           else { if (fz) JA_PROD_F(LL, false, true); else JA_PROD_F(LL, false, false); } } while (0)
+      switch (L) { case 2: JA_PROD_L(2); break; case 4: JA_PROD_L(4); break; case 8: JA_PROD_L(8); break; default: JA_PROD_L(16); break; }
+#undef JA_PROD_L
+#undef JA_PROD_F
+      prod_lanes = L;
+    } else if (kind == JA_EVAL_DOT2 || kind == JA_EVAL_DOT3) {
+      unsigned grid = grid_for(G);
+      if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub))
+      if (kind == JA_EVAL_DOT2) { if (fz) JA_DOT_F(2, true); else JA_DOT_F(2, false); }
+      else { if (fz) JA_DOT_F(3, true); else JA_DOT_F(3, false); }
+#undef JA_DOT_F
+    } else {
+      size_t tiles = (G + kBlock - 1) / kBlock;
+      size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
+      const size_t tpb = (tiles + grid - 1) / grid;
+      grid = (tiles + tpb - 1) / tpb;
+      const int np = (int)polys.size();
+#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub))
+#define JA_S_K(KID) do { if (fz) JA_S_F(KID, true); else JA_S_F(KID, false); } while (0)
+      switch (kind) {
+        case JA_EVAL_ADD: JA_S_K(0); break;
+        case JA_EVAL_SUB: JA_S_K(1); break;
+        case JA_EVAL_MUL: JA_S_K(2); break;
+        case JA_EVAL_SQUARE: JA_S_K(3); break;
+        case JA_EVAL_IDENT: JA_S_K(6); break;
+        default: JA_S_K(7); break;
+      }
+#undef JA_S_K
+#undef JA_S_F
+    }
+    JA_CUDA(cudaGetLastError());
+    if (fz) {
+      for (ja_poly* p : polys) { if (order == JA_LOW_TO_HIGH) p->cur = 1 - p->cur; p->len = len_eval; }
+      pending = false;
+    }
+    return JA_OK;
+  }
+
+  int32_t launch(ja_ctx* c, size_t, int slot_id) override {
+    int32_t st;
+    legacy = !fusable;
+    if (fusable) {
+      slot = arm_slot(c, slot_id);
+      if ((st = launch_fused(c))) return st;
+    } else {
+      const uint64_t* aux = gammas.empty() ? nullptr : reinterpret_cast<const uint64_t*>(gammas.data());
+      if ((st = ja_round_eval_launch(c, kind, polys.data(), polys.size(), eq, aux, gammas.size(), pow_d, n_out, &pend))) return st;
+    }
+    // while the kernel runs: the round's one field division (depends on the eq state only)
+    cs = host::FR_ONE; cw = host::FR_ZERO; div = host::FR_ZERO;
+    if (eq) {
+      uint64_t t[4];
+      ja_spliteq_current_scalar(eq, t); cs = host::from_limbs(t);
+      if ((st = ja_spliteq_current_w(eq, t))) return st;
+      cw = host::from_limbs(t);
+      if (kind == JA_EVAL_PROD || kind == JA_EVAL_POW) div = host::inv(host::sub(host::FR_ONE, cw));
+      else div = host::inv(host::gruen_eq1(cs, cw));
+    }
+    return JA_OK;
+  }
+
+  int32_t message(ja_ctx* c, size_t, const FrH& prev_in, Coeffs* uni) override {
+    uint64_t ev[kMaxOut * 4];
+    int32_t st;
+    if (legacy) {
+      // this path shares the pinned staging buffer: only one legacy instance may be in flight (the drivers collect
+      // instances in launch order, and ja_round_eval_collect synchronises the stream)
+      if ((st = ja_round_eval_collect(c, pend, ev))) return st;
+    } else {
+      if ((st = wait_slot(c, slot))) return st;
+      if (prod_lanes && (kind == JA_EVAL_PROD || kind == JA_EVAL_POW)) {
+        const size_t d = n_out;
+        memcpy(ev, slot.host_vals, (d - 1) * 32);
+        memcpy(ev + 4 * (d - 1), slot.host_vals + 4 * (prod_lanes - 1), 32);
+      } else {
+        memcpy(ev, slot.host_vals, n_out * 32);
+      }
+    }
+    std::vector<FrH> e(n_out);
+    for (size_t k = 0; k < n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
+    const FrH prev = has_scale ? host::mul(prev_in, scale_inv) : prev_in;
+    switch (kind) {
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT:
+        *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev, div); break;               // ops/add.rs:297-304
+      case JA_EVAL_MUL: case JA_EVAL_SQUARE: case 7:
+        *uni = host::gruen_poly_deg_3(cs, cw, e[0], e[1], prev, div); break;         // ops/mul.rs:177, booleanity.rs:295-300
+      case JA_EVAL_PROD: case JA_EVAL_POW:
+        for (auto& x : e) x = host::mul(x, cs);                                      // mles_product_sum.rs:120-128
+        *uni = host::finish_mles_product_sum_from_evals(e, prev, cw, div); break;
+      default:
+        *uni = host::from_evals_and_hint(prev, e); break;                            // einsum/dot.rs:304,349; hamming_weight.rs:137
+    }
+    if (has_scale) *uni = scaled(*uni, scale);
+    return JA_OK;
+  }
+
+  int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t) override {
+    int32_t st;
+    if (eq && (st = ja_spliteq_bind(c, eq, ch))) return st;
+    if (fusable) { memcpy(pend_ch, ch, 32); pending = true; return JA_OK; }
+    return ja_bind_many(c, polys.data(), polys.size(), ch, order);
+  }
+
+  int32_t finalize(ja_ctx* c, uint64_t* staging, size_t* count) override {
+    int32_t st;
+    if (pending) {
+      if ((st = ja_bind_many(c, polys.data(), polys.size(), pend_ch, order))) return st;
+      pending = false;
+    }
+    for (size_t i = 0; i < polys.size(); i++) {
+      JA_REQUIRE(polys[i]->len == 1, "sumcheck: polynomial not fully bound at the end of the protocol");
+      JA_CUDA(cudaMemcpyAsync(staging + 4 * i, polys[i]->data(), sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+    }
+    *count = polys.size();
+    return JA_OK;
+  }
+  void release(ja_ctx* c) override {
+    if (own_eq && eq) ja_spliteq_free(c, eq);
+    eq = nullptr;
+    if (d_gammas) { dev_free(c, d_gammas); d_gammas = nullptr; }
+  }
 };
 
-int32_t instance_message(ja_ctx* c, Instance& in, const FrH& prev, Coeffs* uni) {
-  uint64_t ev[32 * 4];
-  const uint64_t* aux = in.gammas.empty() ? nullptr : reinterpret_cast<const uint64_t*>(in.gammas.data());
-  RoundEvalPending pend;
-  int32_t st = ja_round_eval_launch(c, in.kind, in.polys.data(), in.polys.size(), in.eq, aux, in.gammas.size(), in.pow_d,
-                                    in.n_out, &pend);
+// HammingWeightSumcheckProver over the K-entry G tables (hamming_weight.rs:60-160): log K rounds, degree 1, host only
+struct HammingHostInst : Inst {
+  std::vector<std::vector<FrH>> ra;
+  std::vector<FrH> gammas;
+  int32_t launch(ja_ctx*, size_t, int) override { return JA_OK; }
+  int32_t message(ja_ctx*, size_t, const FrH& prev, Coeffs* uni) override {
+    FrH acc = host::FR_ZERO;
+    for (size_t i = 0; i < ra.size(); i++) {
+      FrH s = host::FR_ZERO;
+      for (size_t j = 0; j < ra[i].size() / 2; j++) s = host::add(s, ra[i][2 * j]);
+      acc = host::add(acc, host::mul(gammas[i], s));
+    }
+    *uni = host::from_evals_and_hint(prev, {acc});
+    return JA_OK;
+  }
+  int32_t ingest(ja_ctx*, const uint64_t ch[4], size_t) override {
+    const FrH r = host::from_limbs(ch);
+    for (auto& p : ra) {
+      const size_t n = p.size() / 2;
+      for (size_t i = 0; i < n; i++) p[i] = host::add(p[2 * i], host::mul(r, host::sub(p[2 * i + 1], p[2 * i])));
+      p.resize(n);
+    }
+    return JA_OK;
+  }
+  int32_t finalize(ja_ctx*, uint64_t* staging, size_t* count) override {
+    for (size_t i = 0; i < ra.size(); i++) memcpy(staging + 4 * i, ra[i][0].l, 32);
+    *count = ra.size();
+    return JA_OK;
+  }
+};
+
+// BooleanitySumcheckProver (booleanity.rs:153-372): log K address rounds on the host (G tables, expanding table F,
+// split-eq B over r_address), then log T cycle rounds on the device over H_i[t] = F[k_i[t]] (body 7, split-eq D).
+struct BooleanityInst : Inst {
+  size_t d = 0, log_k = 0, log_t = 0;
+  std::vector<FrH> gammas;
+  std::vector<std::vector<FrH>> G;
+  std::vector<FrH> F;
+  HostEq B;
+  const ja_addr* addr = nullptr;
+  std::vector<uint64_t> r_cycle;
+  std::unique_ptr<DevInst> p2;
+  std::vector<ja_poly*> H;
+
+  int32_t launch(ja_ctx* c, size_t round, int slot) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k, slot); }
+  int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
+    if (round >= log_k) return p2->message(c, round - log_k, prev, uni);
+    const size_t m = round + 1;                                       // booleanity.rs:193-252
+    const std::vector<FrH> E = B.table();
+    FrH q0 = host::FR_ZERO, q1 = host::FR_ZERO;
+    for (size_t kp = 0; kp < E.size(); kp++) {
+      FrH c0 = host::FR_ZERO, c1 = host::FR_ZERO;
+      for (size_t i = 0; i < d; i++) {
+        FrH s0 = host::FR_ZERO, s1 = host::FR_ZERO;
+        for (size_t k = 0; k < (size_t(1) << m); k++) {
+          const FrH Gk = G[i][(kp << m) + k];
+          const FrH Fk = F[k % (size_t(1) << (m - 1))];
+          const FrH GF = host::mul(Gk, Fk);
+          const FrH e_inf = host::mul(GF, Fk);
+          if ((k >> (m - 1)) == 0) s0 = host::add(s0, host::sub(e_inf, GF));
+          s1 = host::add(s1, e_inf);
+        }
+        c0 = host::add(c0, host::mul(gammas[i], s0));
+        c1 = host::add(c1, host::mul(gammas[i], s1));
+      }
+      q0 = host::add(q0, host::mul(E[kp], c0));
+      q1 = host::add(q1, host::mul(E[kp], c1));
+    }
+    const FrH cw = B.current_w();
+    *uni = host::gruen_poly_deg_3(B.scalar, cw, q0, q1, prev, host::inv(host::gruen_eq1(B.scalar, cw)));
+    return JA_OK;
+  }
+  int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t round) override {
+    if (round >= log_k) return p2->ingest(c, ch, round - log_k);
+    const FrH r = host::from_limbs(ch);
+    B.bind(r);
+    const size_t len = F.size();                                      // ExpandingTable::update, LowToHigh (expanding_table.rs:62-75)
+    F.resize(2 * len);
+    for (size_t i = 0; i < len; i++) { F[len + i] = host::mul(F[i], r); F[i] = host::sub(F[i], F[len + i]); }
+    if (round + 1 < log_k) return JA_OK;
+    // transition (booleanity.rs:330-347): eq_r_r = B.current_scalar; H_i = RaPolynomial(indices, F)
+    std::vector<uint64_t> tabs(d * addr->K * 4);
+    for (size_t i = 0; i < d; i++) memcpy(tabs.data() + i * addr->K * 4, F.data(), addr->K * 32);
+    H.assign(d, nullptr);
+    int32_t st = ja_addr_gather(c, addr, tabs.data(), H.data());
+    if (st) return st;
+    p2.reset(new DevInst());
+    p2->kind = 7; p2->polys = H; p2->gammas = gammas;
+    if ((st = ja_spliteq_new(c, r_cycle.data(), log_t, JA_LOW_TO_HIGH, nullptr, &p2->eq))) return st;
+    p2->own_eq = true;
+    p2->scale = B.scalar; p2->has_scale = true; p2->scale_inv = host::inv(B.scalar);
+    G.clear();
+    return p2->setup(c);
+  }
+  int32_t finalize(ja_ctx* c, uint64_t* staging, size_t* count) override {
+    JA_REQUIRE(p2 != nullptr, "sumcheck: booleanity never reached its cycle rounds");
+    return p2->finalize(c, staging, count);
+  }
+  void release(ja_ctx* c) override {
+    if (p2) p2->release(c);
+    for (ja_poly* h : H) ja_poly_free(c, h);
+    H.clear();
+  }
+};
+
+int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::unique_ptr<Inst>* out) {
+  int32_t st;
+  if (d.kind == JA_INST_BOOLEANITY) {
+    JA_REQUIRE(d.addr && d.host_tables && d.eq_w && d.aux_fr, "sumcheck: booleanity needs addr, G tables, r_cycle and gammas|r_address");
+    std::unique_ptr<BooleanityInst> b(new BooleanityInst());
+    b->d = d.n_polys; b->log_k = d.aux_u32; b->log_t = d.eq_m; b->addr = d.addr;
+    JA_REQUIRE(b->d == d.addr->d && d.table_len == d.addr->K && (size_t(1) << b->log_k) == d.addr->K && (size_t(1) << b->log_t) == d.addr->T,
+               "sumcheck: booleanity shape mismatch (d, K = 2^log_k, T = 2^log_t)");
+    JA_REQUIRE(d.n_aux == b->d + b->log_k && b->log_k >= 1 && b->log_t >= 1, "sumcheck: booleanity aux_fr = gammas (d) then r_address (log_k)");
+    b->gammas.resize(b->d);
+    for (size_t i = 0; i < b->d; i++) b->gammas[i] = host::from_limbs(d.aux_fr + 4 * i);
+    b->B.init(d.aux_fr + 4 * b->d, b->log_k);
+    b->G.resize(b->d);
+    for (size_t i = 0; i < b->d; i++) {
+      b->G[i].resize(d.table_len);
+      memcpy(b->G[i].data(), d.host_tables + 4 * d.table_len * i, d.table_len * 32);
+    }
+    b->F = {host::FR_ONE};
+    b->r_cycle.assign(d.eq_w, d.eq_w + 4 * d.eq_m);
+    b->rounds = b->log_k + b->log_t;
+    b->claim = host::FR_ZERO;                                        // booleanity.rs:70-72
+    b->out_final = d.out_final_claims;
+    out->reset(b.release());
+    return JA_OK;
+  }
+  if (d.kind == JA_INST_HAMMING_TABLES) {
+    JA_REQUIRE(d.host_tables && is_pow2(d.table_len) && d.table_len >= 2, "sumcheck: hamming-weight instance needs power-of-two G tables");
+    std::unique_ptr<HammingHostInst> h(new HammingHostInst());
+    h->ra.resize(d.n_polys);
+    for (size_t i = 0; i < d.n_polys; i++) {
+      h->ra[i].resize(d.table_len);
+      memcpy(h->ra[i].data(), d.host_tables + 4 * d.table_len * i, d.table_len * 32);
+    }
+    h->gammas.assign(d.n_polys, host::FR_ONE);
+    if (d.aux_fr) {
+      JA_REQUIRE(d.n_aux == d.n_polys, "sumcheck: hamming-weight instance takes one gamma per table");
+      for (size_t i = 0; i < d.n_polys; i++) h->gammas[i] = host::from_limbs(d.aux_fr + 4 * i);
+    }
+    h->rounds = (size_t)log2z(d.table_len);
+    h->claim = host::from_limbs(d.claim);
+    h->out_final = d.out_final_claims;
+    out->reset(h.release());
+    return JA_OK;
+  }
+  JA_REQUIRE(d.polys && d.n_polys, "sumcheck: instance without polynomials");
+  std::unique_ptr<DevInst> v(new DevInst());
+  v->kind = d.kind; v->pow_d = d.aux_u32;
+  v->polys.assign(d.polys, d.polys + d.n_polys);
+  if (d.kind == JA_EVAL_SUM1 && d.aux_fr) {
+    JA_REQUIRE(d.n_aux == d.n_polys, "sumcheck: SUM1 takes one gamma per polynomial");
+    v->gammas.resize(d.n_aux);
+    for (size_t i = 0; i < d.n_aux; i++) v->gammas[i] = host::from_limbs(d.aux_fr + 4 * i);
+  }
+  if ((st = v->setup(c))) return st;
+  if (v->uses_eq()) {
+    JA_REQUIRE(d.eq_w && d.eq_m == v->rounds, "sumcheck: family S needs one eq point coordinate per round");
+    if ((st = ja_spliteq_new(c, d.eq_w, d.eq_m, JA_LOW_TO_HIGH, nullptr, &v->eq))) return st;
+    v->own_eq = true;
+  }
+  v->claim = host::from_limbs(d.claim);
+  v->out_final = d.out_final_claims;
+  out->reset(v.release());
+  return JA_OK;
+}
+
+// the round loop shared by Sumcheck::prove (batched == false, one instance) and BatchedSumcheck::prove
+int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool batched, host::Blake2bTranscript& t,
+                   size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges) {
+  const size_t n = insts.size();
+  JA_REQUIRE(n >= 1 && n <= (size_t)kSlots, "sumcheck: between 1 and 16 instances per batch");
+  size_t max_rounds = 0;
+  for (auto& i : insts) max_rounds = std::max(max_rounds, i->rounds);
+  std::vector<FrH> coeffs(n, host::FR_ONE), claims(n);
+  for (auto& i : insts) t.append_scalar(i->claim);                                         // sumcheck.rs:43-46 / :574
+  if (batched) for (size_t k = 0; k < n; k++) coeffs[k] = t.challenge_scalar();           // :48 challenge_vector
+  for (size_t k = 0; k < n; k++) claims[k] = batched ? mul_pow_2(insts[k]->claim, max_rounds - insts[k]->rounds) : insts[k]->claim;
+  int32_t st;
+  g_trace.start();
+  for (size_t round = 0; round < max_rounds; round++) {
+    const size_t remaining = max_rounds - round;
+    std::vector<Coeffs> unis(n);
+    bool legacy_in_flight = false;
+    for (size_t k = 0; k < n; k++) {
+      if (remaining > insts[k]->rounds) continue;
+      // instances on the pinned-staging path cannot overlap each other: collect before launching the next one
+      DevInst* dv = dynamic_cast<DevInst*>(insts[k].get());
+      const bool is_legacy = dv && !dv->fusable;
+      if (is_legacy && legacy_in_flight) return fail(JA_ERR_UNSUPPORTED, "sumcheck: at most one non-fused instance per batch");
+      if ((st = insts[k]->launch(c, round - (max_rounds - insts[k]->rounds), (int)k))) return st;
+      legacy_in_flight = legacy_in_flight || is_legacy;
+    }
+    g_trace.lap(0);
+    for (size_t k = 0; k < n; k++) {
+      const size_t nr = insts[k]->rounds;
+      if (remaining > nr) unis[k] = host::trim({mul_pow_2(insts[k]->claim, remaining - nr - 1)});    // :96-106
+      else if ((st = insts[k]->message(c, round - (max_rounds - nr), claims[k], &unis[k]))) return st;
+    }
+    g_trace.lap(1);
+    Coeffs uni;
+    if (batched) {
+      uni = host::trim({});
+      for (size_t k = 0; k < n; k++) add_assign(uni, scaled(unis[k], coeffs[k]));          // :113-121
+    } else {
+      uni = unis[0];
+    }
+    const Coeffs cp = host::compress(uni);
+    if (cp.size() > max_coeffs) return fail(JA_ERR_INVALID, "sumcheck: max_coeffs too small");
+    t.append_message("UniPoly_begin");                                                     // unipoly.rs:550-558
+    for (auto& x : cp) t.append_scalar(x);
+    t.append_message("UniPoly_end");
+    uint64_t ch[4];
+    t.challenge_scalar_optimized(ch);                                                      // :126 / :586
+    const FrH r = host::from_limbs(ch);
+    for (size_t k = 0; k < n; k++) claims[k] = host::evaluate(unis[k], r);                 // :130-134 / :589
+    g_trace.lap(2);
+    for (size_t k = 0; k < n; k++)
+      if (remaining <= insts[k]->rounds && (st = insts[k]->ingest(c, ch, round - (max_rounds - insts[k]->rounds)))) return st;
+    g_trace.lap(3);
+    out_ncoeffs[round] = (uint32_t)cp.size();
+    for (size_t k = 0; k < cp.size(); k++) memcpy(out_coeffs + 4 * (round * max_coeffs + k), cp[k].l, 32);
+    memcpy(out_challenges + 4 * round, ch, 32);
+  }
+  // final claims: flush the deferred binds, ONE synchronisation for the whole batch
+  uint64_t* staging = c->h_pinned;
+  std::vector<std::pair<size_t, size_t>> span(n);
+  size_t used = 0;
+  for (size_t k = 0; k < n; k++) {
+    size_t cnt = 0;
+    if ((st = insts[k]->finalize(c, staging + 4 * used, &cnt))) return st;
+    span[k] = {used, cnt};
+    used += cnt;
+    JA_REQUIRE(used * 32 <= kPinnedBytes, "sumcheck: too many final claims for the staging buffer");
+  }
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t k = 0; k < n; k++)
+    if (insts[k]->out_final) memcpy(insts[k]->out_final, staging + 4 * span[k].first, span[k].second * 32);
+  if (g_trace.on)
+    fprintf(stderr, "[sc n=%zu rounds=%zu] cumulative us: launch+inv=%.0f wait+interp=%.0f transcript=%.0f ingest=%.0f\n", n, max_rounds,
+            g_trace.t[0], g_trace.t[1], g_trace.t[2], g_trace.t[3]);
+  return JA_OK;
+}
+
+int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint8_t transcript_state[32], uint32_t* n_rounds_io,
+            size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges) {
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  std::vector<std::unique_ptr<Inst>> insts(n);
+  int32_t st = JA_OK;
+  for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts[k]);
+  host::Blake2bTranscript t(transcript_state, *n_rounds_io);
+  if (!st) st = prove_loop(c, insts, batched, t, max_coeffs, out_coeffs, out_ncoeffs, out_challenges);
+  if (st) cudaStreamSynchronize(c->stream);      // nothing of this call may still be in flight when the handles are released
+  for (auto& i : insts) if (i) i->release(c);
   if (st) return st;
-  g_trace.lap(0);
-  // while the kernel runs: the one field division of the round (it depends on the eq state only)
-  FrH cs = host::FR_ONE, cw = host::FR_ZERO, div = host::FR_ZERO;
-  if (in.eq) {
-    uint64_t t[4];
-    ja_spliteq_current_scalar(in.eq, t); cs = host::from_limbs(t);
-    if ((st = ja_spliteq_current_w(in.eq, t))) return st;
-    cw = host::from_limbs(t);
-    if (in.kind == JA_EVAL_PROD || in.kind == JA_EVAL_POW) div = host::inv(host::sub(host::FR_ONE, cw));
-    else div = host::inv(host::gruen_eq1(cs, cw));
-  }
-  g_trace.lap(1);
-  if ((st = ja_round_eval_collect(c, pend, ev))) return st;
-  g_trace.lap(2);
-  std::vector<FrH> e(in.n_out);
-  for (size_t k = 0; k < in.n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
-  switch (in.kind) {
-    case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT:
-      *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev, div); break;               // ops/add.rs:297-304
-    case JA_EVAL_MUL: case JA_EVAL_SQUARE:
-      *uni = host::gruen_poly_deg_3(cs, cw, e[0], e[1], prev, div); break;         // ops/mul.rs:177
-    case JA_EVAL_PROD: case JA_EVAL_POW:
-      for (auto& x : e) x = host::mul(x, cs);                                      // mles_product_sum.rs:120-128
-      *uni = host::finish_mles_product_sum_from_evals(e, prev, cw, div); break;
-    default:
-      *uni = host::from_evals_and_hint(prev, e); break;                            // einsum/dot.rs:304,349; hamming_weight.rs:137
-  }
+  memcpy(transcript_state, t.state, 32);
+  *n_rounds_io = t.n_rounds;
   return JA_OK;
 }
 
@@ -76,77 +617,27 @@ int32_t instance_message(ja_ctx* c, Instance& in, const FrH& prev, Coeffs* uni) 
 
 extern "C" {
 
+int32_t ja_batched_sumcheck_prove(ja_ctx* c, const ja_sc_instance* instances, size_t n_instances, uint8_t transcript_state[32],
+                                  uint32_t* n_rounds_io, size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs,
+                                  uint64_t* out_challenges) {
+  JA_REQUIRE(c && instances && n_instances && transcript_state && n_rounds_io && out_coeffs && out_ncoeffs && out_challenges,
+             "ja_batched_sumcheck_prove: null argument");
+  return run(c, instances, n_instances, true, transcript_state, n_rounds_io, max_coeffs, out_coeffs, out_ncoeffs, out_challenges);
+}
+
 int32_t ja_sumcheck_prove(ja_ctx* c, int32_t kind, ja_poly* const* polys, size_t n_polys, const uint64_t* eq_w, size_t eq_m,
                           const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32, const uint64_t claim[4],
                           uint8_t transcript_state[32], uint32_t* n_rounds_io, size_t max_coeffs, uint64_t* out_coeffs,
                           uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_final_claims) {
   JA_REQUIRE(c && polys && n_polys && claim && transcript_state && n_rounds_io && out_coeffs && out_ncoeffs && out_challenges,
              "ja_sumcheck_prove: null argument");
-  std::lock_guard<std::recursive_mutex> lk(c->mu);
-  Instance in;
-  in.kind = kind;
-  in.polys.assign(polys, polys + n_polys);
-  in.pow_d = aux_u32;
-  const size_t len = ja_poly_len(polys[0]);
-  JA_REQUIRE(len >= 2 && (len & (len - 1)) == 0, "ja_sumcheck_prove: polynomial length must be a power of two >= 2");
-  size_t rounds = 0;
-  while ((size_t(1) << rounds) < len) rounds++;
-  bool family_s = false;
-  switch (kind) {
-    case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT: in.n_out = 1; family_s = true; break;
-    case JA_EVAL_MUL: case JA_EVAL_SQUARE: in.n_out = 2; family_s = true; break;
-    case JA_EVAL_PROD: in.n_out = n_polys; family_s = true; break;
-    case JA_EVAL_POW: in.n_out = aux_u32; family_s = true; break;
-    case JA_EVAL_DOT2: in.n_out = 2; in.order = JA_HIGH_TO_LOW; break;
-    case JA_EVAL_DOT3: in.n_out = 3; in.order = JA_HIGH_TO_LOW; break;
-    case JA_EVAL_SUM1: in.n_out = 1; break;
-    case JA_EVAL_SUMHI: in.n_out = 1; in.order = JA_HIGH_TO_LOW; break;
-    default: return fail(JA_ERR_UNSUPPORTED, "ja_sumcheck_prove: kind not implemented");
-  }
-  if (kind == JA_EVAL_SUM1 && aux_fr) {
-    JA_REQUIRE(n_aux == n_polys, "ja_sumcheck_prove: SUM1 takes one gamma per polynomial");
-    in.gammas.resize(n_aux);
-    for (size_t i = 0; i < n_aux; i++) in.gammas[i] = host::from_limbs(aux_fr + 4 * i);
-  }
-  int32_t st;
-  if (family_s) {
-    JA_REQUIRE(eq_w && eq_m == rounds, "ja_sumcheck_prove: family S needs one eq point coordinate per round");
-    if ((st = ja_spliteq_new(c, eq_w, eq_m, JA_LOW_TO_HIGH, nullptr, &in.eq))) return st;
-  }
-  host::Blake2bTranscript t(transcript_state, *n_rounds_io);
-  FrH prev = host::from_limbs(claim);
-  t.append_scalar(prev);                                           // sumcheck.rs:574
-  g_trace.start();
-  for (size_t round = 0; round < rounds; round++) {
-    Coeffs uni;
-    if ((st = instance_message(c, in, prev, &uni))) { ja_spliteq_free(c, in.eq); return st; }
-    g_trace.lap(3);
-    const Coeffs cp = host::compress(uni);
-    if (cp.size() > max_coeffs) { ja_spliteq_free(c, in.eq); return fail(JA_ERR_INVALID, "ja_sumcheck_prove: max_coeffs too small"); }
-    t.append_message("UniPoly_begin");                             // unipoly.rs:550-558
-    for (auto& x : cp) t.append_scalar(x);
-    t.append_message("UniPoly_end");
-    uint64_t ch[4];
-    t.challenge_scalar_optimized(ch);                              // sumcheck.rs:586
-    prev = host::evaluate(uni, host::from_limbs(ch));              // sumcheck.rs:589
-    g_trace.lap(4);
-    if (in.eq && (st = ja_spliteq_bind(c, in.eq, ch))) { ja_spliteq_free(c, in.eq); return st; }
-    if ((st = ja_bind_many(c, in.polys.data(), in.polys.size(), ch, in.order))) { ja_spliteq_free(c, in.eq); return st; }
-    g_trace.lap(5);
-    out_ncoeffs[round] = (uint32_t)cp.size();
-    for (size_t k = 0; k < cp.size(); k++) memcpy(out_coeffs + 4 * (round * max_coeffs + k), cp[k].l, 32);
-    memcpy(out_challenges + 4 * round, ch, 32);
-  }
-  if (out_final_claims)
-    for (size_t i = 0; i < n_polys; i++)
-      if ((st = ja_final_claim(c, polys[i], out_final_claims + 4 * i))) { ja_spliteq_free(c, in.eq); return st; }
-  ja_spliteq_free(c, in.eq);
-  if (g_trace.on)
-    fprintf(stderr, "[sc kind=%d n_polys=%zu rounds=%zu] cumulative us: launch=%.0f inv=%.0f wait=%.0f interp=%.0f hash+eval=%.0f bind=%.0f\n",
-            kind, n_polys, rounds, g_trace.t[0], g_trace.t[1], g_trace.t[2], g_trace.t[3], g_trace.t[4], g_trace.t[5]);
-  memcpy(transcript_state, t.state, 32);
-  *n_rounds_io = t.n_rounds;
-  return (int32_t)JA_OK;
+  ja_sc_instance d;
+  memset(&d, 0, sizeof(d));
+  d.kind = kind; d.aux_u32 = aux_u32; d.n_polys = n_polys; d.polys = polys;
+  d.eq_w = eq_w; d.eq_m = eq_m; d.aux_fr = aux_fr; d.n_aux = n_aux;
+  memcpy(d.claim, claim, 32);
+  d.out_final_claims = out_final_claims;
+  return run(c, &d, 1, false, transcript_state, n_rounds_io, max_coeffs, out_coeffs, out_ncoeffs, out_challenges);
 }
 
 }  // extern "C"

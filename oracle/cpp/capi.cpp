@@ -127,6 +127,70 @@ static int sumcheck_prove_t(int family, int kind, unsigned pow_d, const uint64_t
   return (int)pf.compressed_polys.size();
 }
 
+// ---- BatchedSumcheck::prove over a list of instance descriptors (sumcheck.rs:30-184) --------------------------------
+// kind: the JA_EVAL_* ids of include/jolt_atlas_b200.h (0 ADD, 1 SUB, 2 MUL, 3 SQUARE, 4 PROD, 5 POW, 6 IDENT, 16 DOT2, 17 DOT3,
+// 18 SUM1 = Hamming weight with gammas) and 32 = Booleanity (polys = G tables d x K, idx = d x T addresses,
+// eq_w = r_cycle, aux_fr = gammas (d) then r_address (log_k), aux_u32 = log_k).
+struct orc_inst {
+  int32_t kind; uint32_t aux_u32;
+  uint64_t n_polys, poly_len;
+  const uint64_t* polys; const uint32_t* idx;
+  const uint64_t* eq_w; uint64_t eq_m;
+  const uint64_t* aux_fr; uint64_t n_aux;
+  uint64_t claim[4];
+  uint64_t* final_claims;
+};
+static Instance* make_instance(const orc_inst& d) {
+  std::vector<FrVec> ps;
+  for (size_t i = 0; i < d.n_polys; i++) ps.push_back(load_fr(d.polys + 4 * d.poly_len * i, d.poly_len));
+  const Fr claim = Fr::from_raw(d.claim);
+  if (d.kind <= 6) { FrVec w = load_fr(d.eq_w, d.eq_m); return new SplitEqInstance(d.kind, w.data(), d.eq_m, std::move(ps), claim, d.aux_u32); }
+  if (d.kind == 16 || d.kind == 17) return new DotInstance(std::move(ps), claim);
+  if (d.kind == 18) {
+    std::vector<Fr> g(d.n_polys, Fr::one());
+    if (d.aux_fr) for (size_t i = 0; i < d.n_polys; i++) g[i] = Fr::from_raw(d.aux_fr + 4 * i);
+    return new HammingInstance(std::move(ps), g, claim);
+  }
+  if (d.kind == 32) {
+    const size_t log_k = d.aux_u32, dd = d.n_polys, T = size_t(1) << d.eq_m;
+    std::vector<std::vector<uint32_t>> idx(dd);
+    for (size_t i = 0; i < dd; i++) idx[i].assign(d.idx + i * T, d.idx + (i + 1) * T);
+    std::vector<Fr> gam(dd);
+    for (size_t i = 0; i < dd; i++) gam[i] = Fr::from_raw(d.aux_fr + 4 * i);
+    FrVec ra = load_fr(d.aux_fr + 4 * dd, log_k), rc = load_fr(d.eq_w, d.eq_m);
+    return new BooleanityInstance(std::move(ps), std::move(idx), std::move(gam), ra.data(), log_k, rc.data(), d.eq_m);
+  }
+  return nullptr;
+}
+int orc_batched_sumcheck_prove(const orc_inst* descs, size_t n, uint8_t state[32], uint32_t* n_rounds, size_t max_coeffs,
+                               uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges) {
+  std::vector<std::unique_ptr<Instance>> own;
+  std::vector<Instance*> insts;
+  for (size_t i = 0; i < n; i++) { own.emplace_back(make_instance(descs[i])); if (!own.back()) return -2; insts.push_back(own.back().get()); }
+  Transcript t(state, *n_rounds);
+  SumcheckProof pf = batched_sumcheck_prove(insts, t);
+  for (size_t r = 0; r < pf.compressed_polys.size(); r++) {
+    if (pf.compressed_polys[r].size() > max_coeffs) return -1;
+    ncoeffs[r] = (uint32_t)pf.compressed_polys[r].size();
+    for (size_t k = 0; k < pf.compressed_polys[r].size(); k++) store_fr(coeffs + 4 * (r * max_coeffs + k), pf.compressed_polys[r][k]);
+    memcpy(challenges + 4 * r, pf.challenges[r].data(), 32);
+  }
+  for (size_t i = 0; i < n; i++) {
+    std::vector<Fr> fc = insts[i]->final_claims();
+    if (descs[i].final_claims) for (size_t k = 0; k < fc.size(); k++) store_fr(descs[i].final_claims + 4 * k, fc[k]);
+  }
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+  return (int)pf.compressed_polys.size();
+}
+// compute_ra_evals (shout.rs:549-598): idx = d x T addresses, out = d x K Fr
+void orc_compute_ra_evals(const uint32_t* idx, size_t d, size_t T, size_t K, const uint64_t* r_cycle, size_t log_t, uint64_t* out) {
+  std::vector<std::vector<uint32_t>> ix(d);
+  for (size_t i = 0; i < d; i++) ix[i].assign(idx + i * T, idx + (i + 1) * T);
+  FrVec rc = load_fr(r_cycle, log_t);
+  std::vector<FrVec> G = compute_ra_evals(ix, K, rc.data(), log_t);
+  for (size_t i = 0; i < d; i++) memcpy(out + 4 * K * i, G[i].data(), K * 32);
+}
+
 // ---- curve / MSM ----
 void orc_srs_powers(const uint64_t tau_mont[4], size_t n, uint64_t* out_xy) {
   std::vector<G1Affine> s = srs_powers(Fr::from_raw(tau_mont), n);

@@ -244,3 +244,96 @@ inline SumcheckProof batched_sumcheck_prove(std::vector<Instance*>& insts, Trans
 }
 
 }  // namespace orc
+
+// ---- RA one-hot checks: shared set-up + booleanity (TEST INFRASTRUCTURE ONLY, as the rest of this file) ---------------
+namespace orc {
+
+// compute_ra_evals (joltworks/src/subprotocols/shout.rs:549-598): G[i][k] = sum_{j : idx_i[j] == k} eq(r_cycle, j).
+// idx[i][j] == 0xFFFFFFFF (None) contributes nothing.
+inline std::vector<FrVec> compute_ra_evals(const std::vector<std::vector<uint32_t>>& idx, size_t K, const Fr* r_cycle, size_t log_t) {
+  const FrVec eq = eq_evals(r_cycle, log_t);
+  std::vector<FrVec> G(idx.size(), FrVec(K, Fr::zero()));
+#pragma omp parallel for
+  for (size_t i = 0; i < idx.size(); i++)
+    for (size_t j = 0; j < idx[i].size(); j++)
+      if (idx[i][j] != 0xffffffffu) G[i][idx[i][j]] += eq[j];
+  return G;
+}
+
+// RaPolynomial materialisation (poly/ra_poly.rs:31-81): out[j] = table[idx[j]] (None -> 0)
+inline FrVec ra_materialise(const std::vector<uint32_t>& idx, const FrVec& table) {
+  FrVec out(idx.size());
+  for (size_t j = 0; j < idx.size(); j++) out[j] = idx[j] == 0xffffffffu ? Fr::zero() : table[idx[j]];
+  return out;
+}
+
+// BooleanitySumcheckProver (joltworks/src/subprotocols/booleanity.rs:153-372)
+struct BooleanityInstance : Instance {
+  size_t d, log_k, log_t;
+  std::vector<Fr> gammas;
+  GruenSplitEq B, D;
+  std::vector<FrVec> G;
+  std::vector<std::vector<uint32_t>> H_idx;
+  std::vector<FrVec> H;
+  FrVec F;                       // ExpandingTable, LowToHigh (utils/expanding_table.rs:62-75)
+  Fr eq_r_r = Fr::zero();
+  BooleanityInstance(std::vector<FrVec> G_, std::vector<std::vector<uint32_t>> idx, std::vector<Fr> gammas_,
+                     const Fr* r_address, size_t log_k_, const Fr* r_cycle, size_t log_t_)
+      : d(G_.size()), log_k(log_k_), log_t(log_t_), gammas(std::move(gammas_)), B(r_address, log_k_, LOW_TO_HIGH),
+        D(r_cycle, log_t_, LOW_TO_HIGH), G(std::move(G_)), H_idx(std::move(idx)) { F = FrVec{Fr::one()}; }
+  size_t num_rounds() const override { return log_k + log_t; }
+  size_t degree() const override { return 3; }
+  Fr input_claim() const override { return Fr::zero(); }
+  UniPoly compute_message(size_t round, const Fr& prev) override {
+    Fr q[2];
+    if (round < log_k) {                                        // :193-252
+      const size_t m = round + 1;
+      B.fold<2>([&](size_t k_prime, Fr* v) {
+        v[0] = Fr::zero(); v[1] = Fr::zero();
+        for (size_t i = 0; i < d; i++) {
+          Fr s0 = Fr::zero(), s1 = Fr::zero();
+          for (size_t k = 0; k < (size_t(1) << m); k++) {
+            const Fr Gk = G[i][(k_prime << m) + k];
+            const size_t k_m = k >> (m - 1);
+            const Fr Fk = F[k % (size_t(1) << (m - 1))];
+            const Fr GF = Gk * Fk;
+            const Fr e_inf = GF * Fk;
+            if (k_m == 0) s0 += e_inf - GF;
+            s1 += e_inf;
+          }
+          v[0] += gammas[i] * s0; v[1] += gammas[i] * s1;
+        }
+      }, q);
+      return gruen_poly_deg_3(B, q[0], q[1], prev);
+    }
+    D.fold<2>([&](size_t j, Fr* v) {                            // :254-301
+      v[0] = Fr::zero(); v[1] = Fr::zero();
+      for (size_t i = 0; i < d; i++) {
+        const Fr h0 = H[i][2 * j], b = H[i][2 * j + 1] - h0;
+        v[0] += (gammas[i] * h0) * (h0 - Fr::one());
+        v[1] += (gammas[i] * b) * b;
+      }
+    }, q);
+    const Fr adjusted = prev * eq_r_r.inv();
+    return gruen_poly_deg_3(D, q[0], q[1], adjusted).scaled(eq_r_r);
+  }
+  void ingest_challenge(const Fr& r, size_t round) override {   // :321-348
+    if (round < log_k) {
+      B.bind(r);
+      const size_t len = F.size();
+      F.resize(2 * len);
+      for (size_t i = 0; i < len; i++) { F[len + i] = F[i] * r; F[i] -= F[len + i]; }
+      if (round == log_k - 1) {
+        eq_r_r = B.current_scalar;
+        for (auto& ix : H_idx) H.push_back(ra_materialise(ix, F));
+        G.clear();
+      }
+    } else {
+      D.bind(r);
+      for (auto& h : H) bind_poly(h, r, LOW_TO_HIGH);
+    }
+  }
+  std::vector<Fr> final_claims() const override { std::vector<Fr> f; for (auto& h : H) f.push_back(h[0]); return f; }
+};
+
+}  // namespace orc

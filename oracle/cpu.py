@@ -204,3 +204,72 @@ def hyperkzg_open(srs: np.ndarray, poly: np.ndarray, point: np.ndarray, label: b
 
 def bench_kernel(which: int, log_n: int, iters: int = 3) -> float:
     return lib().orc_bench_kernel(which, log_n, iters)
+
+
+# ---- BatchedSumcheck::prove over instance descriptors (oracle/cpp/capi.cpp orc_batched_sumcheck_prove) ----
+class _OrcInst(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("aux_u32", C.c_uint32), ("n_polys", C.c_uint64), ("poly_len", C.c_uint64),
+                ("polys", C.c_void_p), ("idx", C.c_void_p), ("eq_w", C.c_void_p), ("eq_m", C.c_uint64),
+                ("aux_fr", C.c_void_p), ("n_aux", C.c_uint64), ("claim", C.c_uint64 * 4), ("final_claims", C.c_void_p)]
+
+
+def batched_sumcheck_prove(instances, t: TranscriptState):
+    """instances: list of dicts with keys kind, polys ((n_polys, len, 4) uint64; Booleanity: G tables (d, K, 4)),
+    optional eq_w, aux_fr, aux_u32, idx ((d, T) uint32), claim.  Returns dict(coeffs, challenges, final_claims=[per instance])."""
+    n = len(instances)
+    arr = (_OrcInst * n)()
+    keep, finals, max_rounds = [], [], 0
+    for i, d in enumerate(instances):
+        polys = np.ascontiguousarray(d["polys"], dtype=np.uint64)
+        kind = int(d["kind"])
+        arr[i].kind = kind
+        arr[i].aux_u32 = int(d.get("aux_u32", 0))
+        arr[i].n_polys, arr[i].poly_len = polys.shape[0], polys.shape[1]
+        arr[i].polys = polys.ctypes.data
+        keep.append(polys)
+        for key, fld in (("eq_w", "eq_w"), ("aux_fr", "aux_fr")):
+            v = d.get(key)
+            if v is not None:
+                v = np.ascontiguousarray(v, dtype=np.uint64).reshape(-1, 4)
+                keep.append(v)
+                setattr(arr[i], fld, v.ctypes.data)
+                setattr(arr[i], "eq_m" if key == "eq_w" else "n_aux", v.shape[0])
+        if d.get("idx") is not None:
+            ix = np.ascontiguousarray(d["idx"], dtype=np.uint32)
+            keep.append(ix)
+            arr[i].idx = ix.ctypes.data
+        claim = np.ascontiguousarray(d.get("claim", np.zeros(4, dtype=np.uint64)), dtype=np.uint64)
+        for k in range(4):
+            arr[i].claim[k] = int(claim[k])
+        fc = np.zeros((polys.shape[0], 4), dtype=np.uint64)
+        finals.append(fc)
+        arr[i].final_claims = fc.ctypes.data
+        if kind == 32:
+            rounds = int(d["aux_u32"]) + arr[i].eq_m
+        elif kind <= 6:
+            rounds = arr[i].eq_m
+        else:
+            rounds = int(polys.shape[1]).bit_length() - 1
+        max_rounds = max(max_rounds, rounds)
+    maxc = 40
+    coeffs = np.zeros((max_rounds, maxc, 4), dtype=np.uint64)
+    ncoeffs = np.zeros(max_rounds, dtype=np.uint32)
+    chal = np.zeros((max_rounds, 4), dtype=np.uint64)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    fn = lib().orc_batched_sumcheck_prove
+    fn.restype = C.c_int
+    rc = fn(arr, C.c_size_t(n), st, C.byref(nr), C.c_size_t(maxc), _p(coeffs), _p(ncoeffs), _p(chal))
+    assert rc == max_rounds, rc
+    t.state, t.n_rounds = st.raw, nr.value
+    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(max_rounds)], "challenges": chal, "final_claims": finals}
+
+
+def compute_ra_evals(idx: np.ndarray, K: int, r_cycle: np.ndarray) -> np.ndarray:
+    """shout.rs:549-598.  idx: (d, T) uint32; returns (d, K, 4)."""
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    d, T = idx.shape
+    rc = np.ascontiguousarray(r_cycle, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((d, K, 4), dtype=np.uint64)
+    lib().orc_compute_ra_evals(_p(idx), C.c_size_t(d), C.c_size_t(T), C.c_size_t(K), _p(rc), C.c_size_t(rc.shape[0]), _p(out))
+    return out

@@ -245,3 +245,86 @@ def sumcheck_verify(cps, claim, num_rounds, degree_bound, transcript):
         rs.append(c)
         e = cp.eval_from_hint(e, F.challenge_to_fr(c))
     return e, rs
+
+
+# ----------------------------------------------------------------------------- RA one-hot checks
+def compute_ra_evals(idx_lists, K, r_cycle_fr):
+    """compute_ra_evals (joltworks/src/subprotocols/shout.rs:549-598): G[i][k] = sum_{j: idx_i[j]==k} eq(r_cycle, j)."""
+    from .poly import eq_evals
+    eq = eq_evals(r_cycle_fr)
+    G = [[0] * K for _ in idx_lists]
+    for i, idx in enumerate(idx_lists):
+        for j, k in enumerate(idx):
+            if k is not None:
+                G[i][k] = (G[i][k] + eq[j]) % P
+    return G
+
+
+class BooleanityInstance(Instance):
+    """BooleanitySumcheckProver (joltworks/src/subprotocols/booleanity.rs:153-372): log_k address rounds over the G
+    tables with the expanding table F, then log_t cycle rounds over H_i[j] = F[idx_i[j]]; degree 3, input claim 0."""
+    degree = 3
+
+    def __init__(self, G, idx_lists, gammas_fr, r_address_fr, r_cycle_fr):
+        self.G = [list(g) for g in G]
+        self.idx = [list(ix) for ix in idx_lists]
+        self.gammas = list(gammas_fr)
+        self.log_k, self.log_t = len(r_address_fr), len(r_cycle_fr)
+        self.B = GruenSplitEq(r_address_fr, LOW_TO_HIGH)
+        self.D = GruenSplitEq(r_cycle_fr, LOW_TO_HIGH)
+        self.F = [1]
+        self.H = []
+        self.eq_r_r = 0
+
+    def num_rounds(self): return self.log_k + self.log_t
+    def input_claim(self): return 0
+
+    def compute_message(self, rnd, prev):
+        if rnd < self.log_k:
+            m = rnd + 1
+
+            def f(kp):
+                c0 = c1 = 0
+                for Gi, gam in zip(self.G, self.gammas):
+                    s0 = s1 = 0
+                    for k in range(1 << m):
+                        Gk = Gi[(kp << m) + k]
+                        Fk = self.F[k % (1 << (m - 1))]
+                        GF = Gk * Fk % P
+                        e_inf = GF * Fk % P
+                        if (k >> (m - 1)) == 0:
+                            s0 = (s0 + e_inf - GF) % P
+                        s1 = (s1 + e_inf) % P
+                    c0 = (c0 + gam * s0) % P
+                    c1 = (c1 + gam * s1) % P
+                return [c0, c1]
+            q0, q2 = self.B.fold(f, 2)
+            return self.B.gruen_poly_deg_3(q0, q2, prev)
+
+        def f2(j):
+            c0 = c1 = 0
+            for h, gam in zip(self.H, self.gammas):
+                h0 = h[2 * j]
+                b = (h[2 * j + 1] - h0) % P
+                c0 = (c0 + gam * h0 % P * (h0 - 1)) % P
+                c1 = (c1 + gam * b % P * b) % P
+            return [c0, c1]
+        q0, q2 = self.D.fold(f2, 2)
+        adjusted = prev * F.fr_inv(self.eq_r_r) % P
+        return self.D.gruen_poly_deg_3(q0, q2, adjusted).scaled(self.eq_r_r)
+
+    def ingest_challenge(self, c, rnd):
+        r = F.challenge_to_fr(c)
+        if rnd < self.log_k:
+            self.B.bind(r)
+            hi = [x * r % P for x in self.F]
+            self.F = [(x - y) % P for x, y in zip(self.F, hi)] + hi
+            if rnd == self.log_k - 1:
+                self.eq_r_r = self.B.current_scalar
+                self.H = [[0 if k is None else self.F[k] for k in ix] for ix in self.idx]
+        else:
+            self.D.bind(r)
+            self.H = [bind(h, r, LOW_TO_HIGH) for h in self.H]
+
+    def final_claims(self):
+        return [h[0] for h in self.H]

@@ -1,0 +1,116 @@
+"""CPU-only: BatchedSumcheck::prove over the RA one-hot checks [RaVirtual (product of d), HammingWeight over the G tables,
+Booleanity] — the C++ oracle (descriptor API) against the independent Python twin, plus the reference's own per-round
+invariant H(0) + H(1) == batched claim (sumcheck.rs:131-142)."""
+import random
+
+import numpy as np
+
+from oracle import cpu as ORC
+from oracle.pyref import field as F
+from oracle.pyref import poly as PL
+from oracle.pyref import sumcheck as SC
+from oracle.pyref import transcript as TR
+from tests.util import from_mont_array, rand_challenge, to_mont_array
+
+P = F.P
+
+
+def _case(seed, d, log_k, log_t):
+    rng = random.Random(seed)
+    K, T = 1 << log_k, 1 << log_t
+    idx = [[rng.randrange(K) for _ in range(T)] for _ in range(d)]
+    if d > 1:
+        idx[1][3] = None                              # a None entry (Option<u8>::None)
+    r_cycle_c = [rand_challenge(rng) for _ in range(log_t)]
+    r_addr_c = [rand_challenge(rng) for _ in range(log_k)]
+    gam_c = [rand_challenge(rng) for _ in range(d)]
+    hw_gamma = rng.randrange(P)
+    tables = [[rng.randrange(P) for _ in range(K)] for _ in range(d)]     # eq(r_address chunk i, .) stand-ins
+    ra_claim = rng.randrange(P)
+    hw_claim = rng.randrange(P)
+    return dict(idx=idx, r_cycle_c=r_cycle_c, r_addr_c=r_addr_c, gam_c=gam_c, hw_gamma=hw_gamma, tables=tables,
+                ra_claim=ra_claim, hw_claim=hw_claim, K=K, T=T, d=d, log_k=log_k, log_t=log_t)
+
+
+def _python_side(c, label):
+    r_cycle = [F.challenge_to_fr(x) for x in c["r_cycle_c"]]
+    r_addr = [F.challenge_to_fr(x) for x in c["r_addr_c"]]
+    gammas = [F.challenge_to_fr(x) for x in c["gam_c"]]
+    G = SC.compute_ra_evals(c["idx"], c["K"], r_cycle)
+    ra = [[0 if k is None else tab[k] for k in ix] for ix, tab in zip(c["idx"], c["tables"])]
+    hw_pows = [pow(c["hw_gamma"], i, P) for i in range(c["d"])]
+    insts = [SC.SplitEqInstance("prod", r_cycle, ra, c["ra_claim"]),
+             SC.HammingInstance(G, hw_pows, c["hw_claim"]),
+             SC.BooleanityInstance(G, c["idx"], gammas, r_addr, r_cycle)]
+    t = TR.Blake2bTranscript(label)
+    cps, rs, coeffs, claims = SC.batched_sumcheck_prove(insts, t)
+    return G, cps, rs, [i.final_claims() for i in insts], t
+
+
+def _idx_array(c):
+    return np.array([[0xFFFFFFFF if k is None else k for k in ix] for ix in c["idx"]], dtype=np.uint32)
+
+
+def _cpp_side(c, label, G):
+    chal = lambda xs: np.array([F.challenge_limbs(x) for x in xs], dtype=np.uint64)
+    idx = _idx_array(c)
+    r_cycle = chal(c["r_cycle_c"])
+    Gc = ORC.compute_ra_evals(idx, c["K"], r_cycle)
+    assert [from_mont_array(g) for g in Gc] == G
+    ra = np.stack([to_mont_array([0 if k is None else tab[k] for k in ix]) for ix, tab in zip(c["idx"], c["tables"])])
+    hw_pows = to_mont_array([pow(c["hw_gamma"], i, P) for i in range(c["d"])])
+    insts = [
+        {"kind": 4, "polys": ra, "eq_w": r_cycle, "claim": to_mont_array([c["ra_claim"]])[0]},
+        {"kind": 18, "polys": Gc, "aux_fr": hw_pows, "claim": to_mont_array([c["hw_claim"]])[0]},
+        {"kind": 32, "polys": Gc, "idx": idx, "eq_w": r_cycle, "aux_u32": c["log_k"],
+         "aux_fr": np.concatenate([chal(c["gam_c"]), chal(c["r_addr_c"])])},
+    ]
+    t = ORC.TranscriptState(label)
+    return ORC.batched_sumcheck_prove(insts, t), t
+
+
+def test_ra_onehot_batch_cpp_matches_python():
+    for seed, d, log_k, log_t in ((1, 4, 2, 3), (2, 3, 4, 5), (3, 16, 4, 4), (4, 1, 1, 1)):
+        c = _case(seed, d, log_k, log_t)
+        G, cps, rs, finals, tp = _python_side(c, b"ra_onehot")
+        res, tc = _cpp_side(c, b"ra_onehot", G)
+        assert len(res["coeffs"]) == log_k + log_t
+        for cp, got in zip(cps, res["coeffs"]):
+            assert from_mont_array(got) == cp.coeffs_except_linear_term
+        assert [F.from_limbs([int(x) for x in row]) for row in res["challenges"]] == [F.from_limbs(F.challenge_limbs(x)) for x in rs]
+        for want, got in zip(finals, res["final_claims"]):
+            assert from_mont_array(got) == want
+        assert tc.state == tp.state and tc.n_rounds == tp.n_rounds
+
+
+def test_batched_round_invariant_and_late_start():
+    """H(0)+H(1) equals the running batched claim every round; instances with fewer rounds contribute 2^k-scaled constants."""
+    c = _case(7, 4, 2, 4)
+    r_cycle = [F.challenge_to_fr(x) for x in c["r_cycle_c"]]
+    r_addr = [F.challenge_to_fr(x) for x in c["r_addr_c"]]
+    gammas = [F.challenge_to_fr(x) for x in c["gam_c"]]
+    G = SC.compute_ra_evals(c["idx"], c["K"], r_cycle)
+    ra = [[0 if k is None else tab[k] for k in ix] for ix, tab in zip(c["idx"], c["tables"])]
+    # true claims so that the sumcheck identities hold
+    eq = PL.eq_evals(r_cycle)
+    prod_claim = 0
+    for j in range(c["T"]):
+        t = eq[j]
+        for p in ra:
+            t = t * p[j] % P
+        prod_claim = (prod_claim + t) % P
+    hw_pows = [pow(c["hw_gamma"], i, P) for i in range(c["d"])]
+    hw_claim = sum(g * sum(Gi) for g, Gi in zip(hw_pows, G)) % P
+    insts = [SC.SplitEqInstance("prod", r_cycle, ra, prod_claim), SC.HammingInstance(G, hw_pows, hw_claim),
+             SC.BooleanityInstance(G, c["idx"], gammas, r_addr, r_cycle)]
+    t = TR.Blake2bTranscript(b"inv")
+    cps, rs, coeffs, claims = SC.batched_sumcheck_prove(insts, t)
+    max_rounds = c["log_k"] + c["log_t"]
+    batched = sum(cf * F.mul_pow_2(cl, max_rounds - nr) for cf, cl, nr in
+                  zip(coeffs, (prod_claim, hw_claim, 0), (c["log_t"], c["log_k"], max_rounds))) % P
+    for cp, r in zip(cps, rs):
+        uni = cp.decompress(batched)
+        assert (uni.evaluate(0) + uni.evaluate(1)) % P == batched
+        batched = uni.evaluate(F.challenge_to_fr(r))
+    # booleanity is satisfied by one-hot data: its final batched contribution is consistent with claim 0
+    assert batched == sum(cf * cl for cf, cl in zip(coeffs, claims)) % P
