@@ -226,6 +226,10 @@ size_t ja_addr_len(const ja_addr*);
 size_t ja_addr_count(const ja_addr*);
 /* HyperKZG::batch_commit_one_hot (hyperkzg/mod.rs:558-596): C_i = sum_t g1_powers[k_i[t] * T + t]; out_xy = d x 8 limbs */
 int32_t ja_addr_commit(ja_ctx*, const ja_srs*, const ja_addr*, uint64_t* out_xy, int32_t* is_inf);
+/* commit_to_polynomials over every one-hot polynomial of a proof (jolt-atlas-core/src/onnx_proof/prover.rs:236-249): the
+ * lists of all `n_batches` address batches in ONE pair of launches; out_xy = (sum of the batches' d) x 8 limbs, batch-major. */
+int32_t ja_addr_commit_many(ja_ctx*, const ja_srs*, const ja_addr* const* batches, size_t n_batches, uint64_t* out_xy,
+                            int32_t* is_inf);
 /* RaPolynomial::new(indices, eq_evals) for all d lists in one launch (ra_poly.rs:31-81, ra_virtual.rs:113-134):
  * tables = d x K Fr, out_polys[i][t] = tables[i][k_i[t]] (None -> 0); T must be a power of two. */
 int32_t ja_addr_gather(ja_ctx*, const ja_addr*, const uint64_t* tables, ja_poly** out_polys);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "ja_addr_len": (C.c_size_t, [vp]),
     "ja_addr_count": (C.c_size_t, [vp]),
     "ja_addr_commit": (C.c_int32, [vp, vp, vp, u64p, i32p]),
+    "ja_addr_commit_many": (C.c_int32, [vp, vp, vpp, C.c_size_t, u64p, i32p]),
     "ja_addr_gather": (C.c_int32, [vp, vp, u64p, vpp]),
     "ja_addr_ra_evals": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p]),
     "ja_hyperkzg_open_begin": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, vpp, u64p, i32p]),

@@ -495,6 +495,20 @@ class OneHotAddresses:
             self._h = None
 
 
+def commit_one_hot_batches(ctx: Context, srs: SRS, batches):
+    """commit_to_polynomials over every one-hot polynomial of a proof: all address batches in one pair of launches.
+    Returns [(xy (d_i, 8), is_infinity (d_i,)) per batch]."""
+    total = sum(b.d for b in batches)
+    out, inf = _pt_out(total)
+    arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+    check(ctx._lib.ja_addr_commit_many(ctx._h, srs._h, arr, len(batches), _u64p(out), inf.ctypes.data_as(_lib.i32p)))
+    res, o = [], 0
+    for b in batches:
+        res.append((out[o:o + b.d], inf[o:o + b.d].astype(bool)))
+        o += b.d
+    return res
+
+
 class InstanceKind:
     BOOLEANITY, HAMMING_TABLES = 32, 33
 

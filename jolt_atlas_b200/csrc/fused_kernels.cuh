@@ -19,11 +19,14 @@ struct Publish {
   volatile unsigned int* seq;    // device address of the slot's sequence word
   unsigned int value;
 };
-// call from every thread of the block that wrote pub.vals
+// Call from every thread of the block that wrote pub.vals.  Only warp 0 writes the sums (grid_sum: thread 0;
+// block_sum_by_lane: threads < L <= 16), so only warp 0 fences at system scope before lane 0 raises the flag.
 JA_DEV void publish_flag(const Publish& pub) {
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) { *pub.seq = pub.value; __threadfence_system(); }
+  if (threadIdx.x < 32) {
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) *pub.seq = pub.value;
+  }
 }
 
 struct FusedPolys {
@@ -192,6 +195,77 @@ k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
   tot = block_sum_by_lane<L>(acc);
   if (threadIdx.x < L) fp_store(pub.vals + threadIdx.x, tot);
   publish_flag(pub);
+}
+
+// ---- booleanity phase 2, lane-parallel (booleanity.rs:254-301) ---------------------------------------------------------
+// [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] per pair: a group of L = next_pow2(d) lanes owns one pair, lane i
+// loads polynomial i (with the fused bind), forms its two terms (4 products) and the group adds them up with shuffles —
+// d times more threads and d times shorter dependency chains than one thread looping over the d polynomials.
+template <int L, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+             size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
+  constexpr int GPB = kBlock / L;
+  const int li = threadIdx.x & (L - 1);
+  const int group = threadIdx.x / L;
+  const bool pad = li >= d;
+  const Fr* __restrict__ zin = P.in[pad ? 0 : li];
+  Fr* __restrict__ zout = P.out[pad ? 0 : li];
+  const Fr gm = pad ? fp_zero<FrParams>() : fp_load(gammas + li);
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  size_t g_end = g_begin + pairs_per_block;
+  if (g_end > G) g_end = G;
+  Fr outer[2], inner[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
+  size_t cur_xout = ~size_t(0);
+  for (size_t base = g_begin; base < g_end; base += GPB) {      // uniform trip count: every lane joins the shuffles
+    const size_t g = base + group;
+    const bool active = g < g_end;
+    const size_t gl = active ? g : g_begin;
+    Fr v0 = fp_zero<FrParams>(), v1 = fp_zero<FrParams>();
+    if (!pad) {
+      Fr h0, h1;
+      if (FUSED) {
+        const Fr a0 = fp_load(zin + 4 * gl), a1 = fp_load(zin + 4 * gl + 1), a2 = fp_load(zin + 4 * gl + 2), a3 = fp_load(zin + 4 * gl + 3);
+        h0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+        h1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
+        if (active) { fp_store(zout + 2 * gl, h0); fp_store(zout + 2 * gl + 1, h1); }
+      } else {
+        h0 = fp_load(zin + 2 * gl);
+        h1 = fp_load(zin + 2 * gl + 1);
+      }
+      const Fr b = fp_sub<FrParams>(h1, h0);
+      v0 = fp_mul<FrParams>(fp_mul<FrParams>(gm, h0), fp_sub<FrParams>(h0, fp_one<FrParams>()));
+      v1 = fp_mul<FrParams>(fp_mul<FrParams>(gm, b), b);
+    }
+#pragma unroll
+    for (int dlt = L / 2; dlt >= 1; dlt >>= 1) {
+      v0 = fp_add<FrParams>(v0, fr_shfl_xor(v0, dlt));
+      v1 = fp_add<FrParams>(v1, fr_shfl_xor(v1, dlt));
+    }
+    if (active && li == 0) {
+      const size_t x_out = g >> bits_in;
+      if (x_out != cur_xout) {
+        if (cur_xout != ~size_t(0)) {
+          const Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+          for (int k = 0; k < 2; k++) { outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k])); inner[k] = fp_zero<FrParams>(); }
+        }
+        cur_xout = x_out;
+      }
+      const Fr ei = fp_load(e_in + (g & mask_in));
+      inner[0] = fp_add<FrParams>(inner[0], fp_mul<FrParams>(ei, v0));
+      inner[1] = fp_add<FrParams>(inner[1], fp_mul<FrParams>(ei, v1));
+    }
+  }
+  if (cur_xout != ~size_t(0)) {
+    const Fr eo = fp_load(e_out + cur_xout);
+#pragma unroll
+    for (int k = 0; k < 2; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
+  }
+  if (grid_sum<2>(outer, partials, counter, pub.vals)) publish_flag(pub);
 }
 
 // ---- family D (plain products at X in {0,2,3}, HighToLow), fused bind in place ------------------------------------------

@@ -12,14 +12,18 @@
 
 namespace ja {
 
-// point sums straight from the address lists: entry t of list i selects base k*T + t
+// point sums straight from the address lists: entry t of a list selects base k*T + t.  One job per LIST (all lists of
+// all nodes of a proof in one launch: the witness commitments do not depend on the transcript, prover.rs:72-87).
+struct AddrJob { const uint32_t* k; uint32_t T; uint32_t first_block; uint32_t pad; };
 static __global__ void __launch_bounds__(kIdxBlock)
-k_addr_partial(const uint32_t* __restrict__ k_all, uint32_t T, uint32_t blocks_per_list, const G1Aff* __restrict__ bases,
-               G1X* __restrict__ partial) {
+k_addr_partial(const AddrJob* __restrict__ jobs, uint32_t njobs, const G1Aff* __restrict__ bases, G1X* __restrict__ partial) {
   __shared__ G1X s_acc[kIdxBlock];
-  const uint32_t list = blockIdx.x / blocks_per_list, blk = blockIdx.x % blocks_per_list;
-  const uint32_t* __restrict__ k = k_all + (size_t)list * T;
-  const uint32_t base = blk * (kIdxBlock * kIdxRun);
+  uint32_t lo = 0, hi = njobs - 1;
+  while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (jobs[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1; }
+  const AddrJob job = jobs[lo];
+  const uint32_t* __restrict__ k = job.k;
+  const uint32_t T = job.T;
+  const uint32_t base = (blockIdx.x - job.first_block) * (kIdxBlock * kIdxRun);
   G1X acc = g1x_inf();
   uint32_t e = base + threadIdx.x;
   uint32_t kk = e < T ? __ldg(k + e) : 0xffffffffu;
@@ -41,10 +45,12 @@ k_addr_partial(const uint32_t* __restrict__ k_all, uint32_t T, uint32_t blocks_p
   if (threadIdx.x == 0) g1x_store(partial + blockIdx.x, tot);
 }
 static __global__ void __launch_bounds__(kIdxBlock)
-k_addr_final(const G1X* __restrict__ partial, uint32_t blocks_per_list, G1X* __restrict__ out) {
+k_addr_final(const AddrJob* __restrict__ jobs, uint32_t njobs, uint32_t total_blocks, const G1X* __restrict__ partial, G1X* __restrict__ out) {
   __shared__ G1X s_acc[kIdxBlock];
+  const uint32_t first = jobs[blockIdx.x].first_block;
+  const uint32_t end = blockIdx.x + 1 < njobs ? jobs[blockIdx.x + 1].first_block : total_blocks;
   G1X acc = g1x_inf();
-  for (uint32_t b = threadIdx.x; b < blocks_per_list; b += kIdxBlock) g1x_add(acc, g1x_load(partial + (size_t)blockIdx.x * blocks_per_list + b));
+  for (uint32_t b = first + threadIdx.x; b < end; b += kIdxBlock) g1x_add(acc, g1x_load(partial + b));
   const G1X tot = block_point_sum(acc, s_acc);
   if (threadIdx.x == 0) g1x_store(out + blockIdx.x, tot);
 }
@@ -126,30 +132,49 @@ void ja_addr_free(ja_ctx* c, ja_addr* a) {
   delete a;
 }
 
-int32_t ja_addr_commit(ja_ctx* c, const ja_srs* srs, const ja_addr* a, uint64_t* out_xy, int32_t* is_inf) {
-  JA_REQUIRE(c && srs && a && out_xy, "ja_addr_commit: null argument");
-  if (a->K * a->T > srs->n)
-    return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, one-hot polynomial needs " +
-                                       std::to_string(a->K * a->T));
+int32_t ja_addr_commit_many(ja_ctx* c, const ja_srs* srs, const ja_addr* const* batches, size_t n_batches, uint64_t* out_xy,
+                            int32_t* is_inf) {
+  JA_REQUIRE(c && srs && batches && n_batches && out_xy, "ja_addr_commit: null argument");
+  std::vector<AddrJob> jobs;
+  uint64_t blocks = 0;
+  for (size_t b = 0; b < n_batches; b++) {
+    const ja_addr* a = batches[b];
+    JA_REQUIRE(a, "ja_addr_commit: null batch");
+    if (a->K * a->T > srs->n)
+      return fail(JA_ERR_KEY_LENGTH, "KeyLengthError: SRS has " + std::to_string(srs->n) + " powers, one-hot polynomial needs " +
+                                         std::to_string(a->K * a->T));
+    const uint32_t bpl = (uint32_t)((a->T + kIdxBlock * kIdxRun - 1) / (kIdxBlock * kIdxRun));
+    for (size_t i = 0; i < a->d; i++) { jobs.push_back(AddrJob{a->d_k + i * a->T, (uint32_t)a->T, (uint32_t)blocks, 0}); blocks += bpl; }
+    JA_REQUIRE(blocks < (1ull << 31), "ja_addr_commit: batch too large");
+  }
+  const size_t count = jobs.size();
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  const uint32_t bpl = (uint32_t)((a->T + kIdxBlock * kIdxRun - 1) / (kIdxBlock * kIdxRun));
-  const size_t blocks = (size_t)bpl * a->d;
-  G1X* ws = nullptr;
-  int32_t st = dev_alloc(c, sizeof(G1X) * (blocks + a->d), (void**)&ws);
+  auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_part = align(sizeof(AddrJob) * count), o_out = align(o_part + sizeof(G1X) * blocks);
+  char* ws = nullptr;
+  int32_t st = dev_alloc(c, o_out + sizeof(G1X) * count, (void**)&ws);
   if (st) return st;
-  G1X* d_out = ws + blocks;
-  JA_LAUNCH(c, KC_ONEHOT_SUM, k_addr_partial<<<(unsigned)blocks, kIdxBlock, 0, c->stream>>>(a->d_k, (uint32_t)a->T, bpl, srs->points, ws));
-  JA_LAUNCH(c, KC_ONEHOT_SUM, k_addr_final<<<(unsigned)a->d, kIdxBlock, 0, c->stream>>>(ws, bpl, d_out));
+  AddrJob* d_jobs = (AddrJob*)ws;
+  G1X* d_part = (G1X*)(ws + o_part);
+  G1X* d_out = (G1X*)(ws + o_out);
+  JA_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(AddrJob) * count, cudaMemcpyHostToDevice, c->stream));
+  JA_LAUNCH(c, KC_ONEHOT_SUM, k_addr_partial<<<(unsigned)blocks, kIdxBlock, 0, c->stream>>>(d_jobs, (uint32_t)count, srs->points, d_part));
+  JA_LAUNCH(c, KC_ONEHOT_SUM, k_addr_final<<<(unsigned)count, kIdxBlock, 0, c->stream>>>(d_jobs, (uint32_t)count, (uint32_t)blocks, d_part, d_out));
   JA_CUDA(cudaGetLastError());
-  JA_REQUIRE(a->d * sizeof(G1X) <= kPinnedBytes, "ja_addr_commit: batch too large for the staging buffer");
-  JA_CUDA(cudaMemcpyAsync(c->h_pinned, d_out, sizeof(G1X) * a->d, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<host::G1XH> sums(count);
+  JA_CUDA(cudaMemcpyAsync(sums.data(), d_out, sizeof(G1X) * count, cudaMemcpyDeviceToHost, c->stream));
   JA_CUDA(cudaStreamSynchronize(c->stream));
   dev_free(c, ws);
-  std::vector<int32_t> inf(a->d);
-  host::xyzz_batch_to_affine(reinterpret_cast<const host::G1XH*>(c->h_pinned), a->d, out_xy, inf.data());
-  if (is_inf) memcpy(is_inf, inf.data(), sizeof(int32_t) * a->d);
+  std::vector<int32_t> inf(count);
+  host::xyzz_batch_to_affine(sums.data(), count, out_xy, inf.data());
+  if (is_inf) memcpy(is_inf, inf.data(), sizeof(int32_t) * count);
   return JA_OK;
+}
+
+int32_t ja_addr_commit(ja_ctx* c, const ja_srs* srs, const ja_addr* a, uint64_t* out_xy, int32_t* is_inf) {
+  const ja_addr* arr[1] = {a};
+  return ja_addr_commit_many(c, srs, arr, 1, out_xy, is_inf);
 }
 
 int32_t ja_addr_gather(ja_ctx* c, const ja_addr* a, const uint64_t* tables, ja_poly** out_polys) {

@@ -30,7 +30,7 @@ namespace {
 // JA_SC_TRACE=1: per-phase host wall-clock of the round loop on stderr (tuning aid)
 struct ScTrace {
   bool on = getenv("JA_SC_TRACE") != nullptr;
-  double t[4] = {0, 0, 0, 0};
+  double t[6] = {0, 0, 0, 0, 0, 0};
   std::chrono::steady_clock::time_point last;
   void start() { if (on) last = std::chrono::steady_clock::now(); }
   void lap(int k) { if (!on) return; auto n = std::chrono::steady_clock::now(); t[k] += std::chrono::duration<double, std::micro>(n - last).count(); last = n; }
@@ -119,6 +119,9 @@ struct Inst {
   uint64_t* out_final = nullptr;
   virtual ~Inst() {}
   virtual int32_t launch(ja_ctx* c, size_t round, int slot) = 0;
+  // host work that depends on the instance state only (the round's field inversion): runs after EVERY instance of the
+  // batch has enqueued its kernel, i.e. overlapped with the kernels
+  virtual int32_t prework(ja_ctx*, size_t) { return JA_OK; }
   virtual int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) = 0;
   virtual int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t round) = 0;
   // flush deferred work and enqueue the D2H of the final claims into `staging` (pinned); *count = number of Fr written
@@ -237,6 +240,18 @@ struct DevInst : Inst {
       if (kind == JA_EVAL_DOT2) { if (fz) JA_DOT_F(2, true); else JA_DOT_F(2, false); }
       else { if (fz) JA_DOT_F(3, true); else JA_DOT_F(3, false); }
 #undef JA_DOT_F
+    } else if (kind == 7 && polys.size() > 1 && polys.size() <= 16) {
+      const int d = (int)polys.size();
+      int L = 2; while (L < d) L <<= 1;
+      const size_t gpb = (size_t)kBlock / L;
+      size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
+      ppb = (ppb + gpb - 1) / gpb * gpb;
+      const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
+#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub))
+#define JA_BOOL_L(LL) do { if (fz) JA_BOOL_F(LL, true); else JA_BOOL_F(LL, false); } while (0)
+      switch (L) { case 2: JA_BOOL_L(2); break; case 4: JA_BOOL_L(4); break; case 8: JA_BOOL_L(8); break; default: JA_BOOL_L(16); break; }
+#undef JA_BOOL_L
+#undef JA_BOOL_F
     } else {
       size_t tiles = (G + kBlock - 1) / kBlock;
       size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
@@ -274,7 +289,11 @@ struct DevInst : Inst {
       const uint64_t* aux = gammas.empty() ? nullptr : reinterpret_cast<const uint64_t*>(gammas.data());
       if ((st = ja_round_eval_launch(c, kind, polys.data(), polys.size(), eq, aux, gammas.size(), pow_d, n_out, &pend))) return st;
     }
-    // while the kernel runs: the round's one field division (depends on the eq state only)
+    return JA_OK;
+  }
+  // while the kernels run: the round's one field division (depends on the eq state only)
+  int32_t prework(ja_ctx*, size_t) override {
+    int32_t st;
     cs = host::FR_ONE; cw = host::FR_ZERO; div = host::FR_ZERO;
     if (eq) {
       uint64_t t[4];
@@ -394,6 +413,7 @@ struct BooleanityInst : Inst {
   std::vector<ja_poly*> H;
 
   int32_t launch(ja_ctx* c, size_t round, int slot) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k, slot); }
+  int32_t prework(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->prework(c, round - log_k); }
   int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
     if (round >= log_k) return p2->message(c, round - log_k, prev, uni);
     const size_t m = round + 1;                                       // booleanity.rs:193-252
@@ -545,6 +565,13 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
       if ((st = insts[k]->launch(c, round - (max_rounds - insts[k]->rounds), (int)k))) return st;
       legacy_in_flight = legacy_in_flight || is_legacy;
     }
+    if (g_trace.on && getenv("JA_SC_TRACE")[0] == '2') {
+      auto nw = std::chrono::steady_clock::now();
+      fprintf(stderr, "  round %zu launch %.1f us\n", round, std::chrono::duration<double, std::micro>(nw - g_trace.last).count());
+    }
+    g_trace.lap(4);
+    for (size_t k = 0; k < n; k++)
+      if (remaining <= insts[k]->rounds && (st = insts[k]->prework(c, round - (max_rounds - insts[k]->rounds)))) return st;
     g_trace.lap(0);
     for (size_t k = 0; k < n; k++) {
       const size_t nr = insts[k]->rounds;
@@ -591,8 +618,8 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   for (size_t k = 0; k < n; k++)
     if (insts[k]->out_final) memcpy(insts[k]->out_final, staging + 4 * span[k].first, span[k].second * 32);
   if (g_trace.on)
-    fprintf(stderr, "[sc n=%zu rounds=%zu] cumulative us: launch+inv=%.0f wait+interp=%.0f transcript=%.0f ingest=%.0f\n", n, max_rounds,
-            g_trace.t[0], g_trace.t[1], g_trace.t[2], g_trace.t[3]);
+    fprintf(stderr, "[sc n=%zu rounds=%zu] cumulative us: launch=%.0f inv=%.0f wait+interp=%.0f transcript=%.0f ingest=%.0f\n", n, max_rounds,
+            g_trace.t[4], g_trace.t[0], g_trace.t[1], g_trace.t[2], g_trace.t[3]);
   return JA_OK;
 }
 

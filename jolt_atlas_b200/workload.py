@@ -19,6 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 K_CHUNK = 16          # common/src/consts/general.rs:2-3 (LOG_K_CHUNK = 4)
+LOG_K = 4
 D_CLAMP = 16          # 64-bit clamp lookups: 64 / LOG_K_CHUNK one-hot chunks (clamp_lookups/mod.rs:57)
 D_REM = 4             # remainder range check: ceil(14 / 4) chunks (MODEL_SCALE = 14)
 P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
@@ -101,7 +102,8 @@ class NodeInputs:
     hot_k: np.ndarray          # (d_hot, T) uint32 addresses k in [0, 16)
     tables: np.ndarray         # (d_hot, 16, 4) Fr eq tables the RA polynomials are materialised from
     eq_w: np.ndarray           # (log_t, 4) eq point of the node's split-eq sumchecks
-    gammas: np.ndarray         # (d_hot, 4) Hamming-weight batching coefficients
+    gammas: np.ndarray         # (d_hot, 4) batching coefficients (booleanity gammas; Hamming-weight gamma powers stand-ins)
+    r_addr: np.ndarray = None  # (log K, 4) booleanity address point
     A: np.ndarray | None = None    # einsum left operand (m x k) i32 / mul, add: left operand (T,) i32
     B: np.ndarray | None = None
     eq_rows: np.ndarray | None = None   # einsum: eq point over the m rows / the n columns
@@ -120,7 +122,7 @@ def build_inputs(config: str, seed: int | None = None):
         ni = NodeInputs(spec=spec, d_hot=d_hot,
                         hot_k=rng.integers(0, K_CHUNK, size=(d_hot, T), dtype=np.uint32),
                         tables=np.stack([_challenges(rng, K_CHUNK) for _ in range(d_hot)]),
-                        eq_w=_challenges(rng, spec.log_t), gammas=_challenges(rng, d_hot))
+                        eq_w=_challenges(rng, spec.log_t), gammas=_challenges(rng, d_hot), r_addr=_challenges(rng, LOG_K))
         if spec.kind == "einsum":
             ni.A = rng.integers(-128, 128, size=(spec.m, spec.k), dtype=np.int32)
             ni.B = rng.integers(-128, 128, size=(spec.k, spec.n), dtype=np.int32)
@@ -148,13 +150,32 @@ def h2d_bytes(inputs) -> int:
     """Bytes of per-proof inputs that cross host->device in the end-to-end path."""
     total = 0
     for ni in inputs["nodes"]:
-        total += ni.d_hot * ni.hot_k.shape[1] * (8 + 4)            # commit index lists (u64) + RA addresses (u32)
-        total += ni.tables.nbytes + ni.A.nbytes + ni.B.nbytes
+        total += ni.hot_k.nbytes                                   # one-hot addresses, 4 B per entry, uploaded once per node
+        total += 2 * ni.tables.nbytes + ni.A.nbytes + ni.B.nbytes   # RA tables (gather) + G tables (batched instances)
     return total
 
 
+def _ra_checks(A, ctx, addr, ni, lo, hi, claim, t, out, sc):
+    """RaOneHotChecks / RescaleRemainderRaChecks (shout.rs:399-466): BatchedSumcheck[RaVirtual (product of d),
+    HammingWeight over the G tables, Booleanity] sharing one G = compute_ra_evals and one address batch."""
+    G = addr.ra_evals(ni.eq_w)                                                  # shout.rs:549-598
+    ra = addr.gather(ni.tables[lo:hi])                                          # ra_virtual.rs:113-134
+    first = ra[0].clone()
+    r = A.batched_sumcheck_prove(ctx, [
+        {"kind": A.EvalKernel.PROD, "polys": ra, "eq_w": ni.eq_w, "claim": claim},
+        {"kind": A.InstanceKind.HAMMING_TABLES, "tables": G, "aux_fr": ni.gammas[lo:hi], "claim": claim},
+        {"kind": A.InstanceKind.BOOLEANITY, "tables": G, "addr": addr, "eq_w": ni.eq_w, "gammas": ni.gammas[lo:hi],
+         "r_address": ni.r_addr},
+    ], t)
+    out["finals"].extend(r["final_claims"])
+    out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])
+    for q in ra:
+        q.free()
+    return first
+
+
 def run_device(ctx, srs, inputs, resident=None):
-    """One prove-shaped pass on the GPU.  Returns dict(commitments, states, open) for parity checks.
+    """One prove-shaped pass on the GPU.  Returns dict(commitments, states, finals, open) for parity checks.
     `resident` (from make_resident) supplies device-resident copies of the per-proof inputs; without it every input is
     uploaded from the host arrays inside this call (the end-to-end path)."""
     from . import api as A
@@ -165,44 +186,35 @@ def run_device(ctx, srs, inputs, resident=None):
     def _sc(*a, **kw):
         r = A.sumcheck_prove(*a, **kw)
         out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])     # round polynomials read back from the device
+        out["finals"].append(r["final_claims"])
         return r
+    # A. witness commitment of EVERY one-hot polynomial before the IOP, as ONNXProof::prove does
+    #    (mod.rs:152-200 step 4: commit_witness_polynomials -> prover.rs:236-249 -> hyperkzg/mod.rs:558-596)
+    hots = []
+    for i, ni in enumerate(inputs["nodes"]):
+        if resident:
+            hots.append((resident["nodes"][i]["hot16"], resident["nodes"][i]["hot4"]))
+        else:
+            hots.append((A.OneHotAddresses(ctx, ni.hot_k[:D_CLAMP], K_CHUNK),
+                         A.OneHotAddresses(ctx, ni.hot_k[D_CLAMP:], K_CHUNK) if ni.d_hot > D_CLAMP else None))
+    out["commitments"] = A.commit_one_hot_batches(ctx, srs, [h for pair in hots for h in pair if h is not None])
     for i, ni in enumerate(inputs["nodes"]):
         spec = ni.spec
         res = resident["nodes"][i] if resident else None
-        # A. witness commitment: HyperKZG::batch_commit_one_hot (prover.rs:236-249 -> hyperkzg/mod.rs:558-596)
-        if res:
-            com, inf = res["hot"].commit(srs)
-        else:
-            hot = A.OneHotBatch(ctx, onehot_index_lists(ni))
-            com, inf = hot.commit(srs)
-            hot.free()
-        out["commitments"].append((com, inf))
-        # RA polynomials materialised from the addresses (ra_poly.rs; shout.rs:549-598)
-        if res:
-            ra = [p.clone() for p in res["ra"]]
-        else:
-            ra = [A.MultilinearPolynomial.from_lookup(ctx, ni.tables[j], ni.hot_k[j]) for j in range(ni.d_hot)]
+        hot16, hot4 = hots[i]
+        # C. RA one-hot checks of the clamp lookup (batched: product of 16, Hamming weight, booleanity)
+        ra0 = _ra_checks(A, ctx, hot16, ni, 0, D_CLAMP, claim, t, out, _sc)
         # B. lookup read-raf cycle rounds (ps_shout/mod.rs:464-488): [ra0], degree 2
-        p = ra[0].clone()
-        r = _sc(ctx, A.EvalKernel.IDENT, [p], claim, t, eq_w=ni.eq_w)
-        out["finals"].append(r["final_claims"]); p.free()
-        # C. RA one-hot checks (shout.rs:399-466): Hamming weight over all chunks, then RA virtualisation = product of d
-        hw = [q.clone() for q in ra[:D_CLAMP]]
-        r = _sc(ctx, A.EvalKernel.SUM1, hw, claim, t, gammas=ni.gammas[:D_CLAMP])
-        out["finals"].append(r["final_claims"])
-        for q in hw:
-            q.free()
-        r = _sc(ctx, A.EvalKernel.PROD, ra[:D_CLAMP], claim, t, eq_w=ni.eq_w)
-        out["finals"].append(r["final_claims"])
+        _sc(ctx, A.EvalKernel.IDENT, [ra0], claim, t, eq_w=ni.eq_w)
+        ra0.free()
         # D. the operator's own sumcheck
         if spec.kind == "einsum":
-            # EinsumDotProver::initialize (einsum/dot.rs:259-283): fold both operands with the eq tables, then k dot rounds
+            # EinsumDotProver::initialize (einsum/dot.rs:259-283): fold both operands with the eq tables, then log k dot rounds
             eq_r = A.EqPolynomial.evals(ctx, ni.eq_rows)
             eq_c = A.EqPolynomial.evals(ctx, ni.eq_cols)
             left = A.tensor_fold_i32(ctx, ni.A, eq_r, transpose=False)     # (m x k) folded over rows -> k
             right = A.tensor_fold_i32(ctx, ni.B, eq_c, transpose=True)     # (k x n) folded over columns -> k
-            r = _sc(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
-            out["finals"].append(r["final_claims"])
+            _sc(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
             for q in (eq_r, eq_c, left, right):
                 q.free()
         else:
@@ -210,20 +222,18 @@ def run_device(ctx, srs, inputs, resident=None):
                 a, b = res["A"].clone(), res["B"].clone()
             else:
                 a, b = A.MultilinearPolynomial.from_i32(ctx, ni.A), A.MultilinearPolynomial.from_i32(ctx, ni.B)
-            kind = A.EvalKernel.MUL if spec.kind == "mul" else A.EvalKernel.ADD
-            r = _sc(ctx, kind, [a, b], claim, t, eq_w=ni.eq_w)
-            out["finals"].append(r["final_claims"])
+            _sc(ctx, A.EvalKernel.MUL if spec.kind == "mul" else A.EvalKernel.ADD, [a, b], claim, t, eq_w=ni.eq_w)
             a.free(); b.free()
-        if ni.d_hot > D_CLAMP:
-            # E. remainder range check cycle rounds (identity_range_check.rs:332-358)
-            p = ra[D_CLAMP].clone()
-            r = _sc(ctx, A.EvalKernel.IDENT, [p], claim, t, eq_w=ni.eq_w)
-            out["finals"].append(r["final_claims"]); p.free()
-            # F. remainder RA checks: product of d = 4
-            r = _sc(ctx, A.EvalKernel.PROD, ra[D_CLAMP:], claim, t, eq_w=ni.eq_w)
-            out["finals"].append(r["final_claims"])
-        for q in ra:
-            q.free()
+        if hot4 is not None:
+            # F. remainder RA checks (batched: product of d = 4, Hamming weight, booleanity)
+            rem0 = _ra_checks(A, ctx, hot4, ni, D_CLAMP, ni.d_hot, claim, t, out, _sc)
+            # E. remainder range-check cycle rounds (identity_range_check.rs:332-358)
+            _sc(ctx, A.EvalKernel.IDENT, [rem0], claim, t, eq_w=ni.eq_w)
+            rem0.free()
+        if not res:
+            hot16.free()
+            if hot4 is not None:
+                hot4.free()
         out["states"].append(t.state)
     # G. joint opening: HyperKZG::open of a 2^ell polynomial (prover.rs:164-170); the RLC polynomial is synthetic
     rlc = resident["rlc"] if resident else A.MultilinearPolynomial.random(ctx, 1 << inputs["ell"], inputs["rlc_seed"])
@@ -235,12 +245,12 @@ def run_device(ctx, srs, inputs, resident=None):
 
 
 def make_resident(ctx, inputs):
-    """Upload every per-proof input once (the device-resident leg of the bench clones from these)."""
+    """Upload every per-proof input once (the device-resident leg of the bench reuses these)."""
     from . import api as A
     nodes = []
     for ni in inputs["nodes"]:
-        d = {"hot": A.OneHotBatch(ctx, onehot_index_lists(ni)),
-             "ra": [A.MultilinearPolynomial.from_lookup(ctx, ni.tables[j], ni.hot_k[j]) for j in range(ni.d_hot)]}
+        d = {"hot16": A.OneHotAddresses(ctx, ni.hot_k[:D_CLAMP], K_CHUNK),
+             "hot4": A.OneHotAddresses(ctx, ni.hot_k[D_CLAMP:], K_CHUNK) if ni.d_hot > D_CLAMP else None}
         if ni.spec.kind != "einsum":
             d["A"] = A.MultilinearPolynomial.from_i32(ctx, ni.A)
             d["B"] = A.MultilinearPolynomial.from_i32(ctx, ni.B)
@@ -250,9 +260,9 @@ def make_resident(ctx, inputs):
 
 def free_resident(res):
     for d in res["nodes"]:
-        d["hot"].free()
-        for p in d["ra"]:
-            p.free()
+        d["hot16"].free()
+        if d["hot4"] is not None:
+            d["hot4"].free()
         for k in ("A", "B"):
             if k in d:
                 d[k].free()
@@ -265,56 +275,62 @@ def count_units(inputs) -> dict:
     for ni in inputs["nodes"]:
         lt = ni.spec.log_t
         adds += ni.d_hot * (1 << lt)
-        rounds += 3 * lt + (2 * lt if ni.d_hot > D_CLAMP else 0)
+        rounds += (LOG_K + lt) + lt + ((LOG_K + lt) + lt if ni.d_hot > D_CLAMP else 0)     # batched RA checks + cycle rounds
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
     return {"sumcheck_rounds": rounds, "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"]}
 
 
 # ---- measurement helpers (bench.py) -------------------------------------------------------------------------------
 def sumcheck_list(inputs):
-    """(kernel class of the round evaluation, number of polynomials, initial length) of every sumcheck of one pass, in order."""
+    """(round body, number of polynomials, initial length) of every device sumcheck instance of one pass, in order."""
     out = []
     for ni in inputs["nodes"]:
         T = 1 << ni.spec.log_t
-        out.append(("round_eval_split_eq", 1, T))
-        out.append(("round_sum", D_CLAMP, T))
-        out.append(("round_eval_product", D_CLAMP, T))
+        out.append(("product", D_CLAMP, T))       # RaVirtual d = 16
+        out.append(("booleanity", D_CLAMP, T))    # Booleanity phase 2 over 16 H polynomials
+        out.append(("split_eq", 1, T))            # lookup cycle rounds
         if ni.spec.kind == "einsum":
-            out.append(("round_eval_dot", 2, 1 << (ni.spec.k - 1).bit_length()))
+            out.append(("dot", 2, 1 << (ni.spec.k - 1).bit_length()))
         else:
-            out.append(("round_eval_split_eq", 2, T))
+            out.append(("split_eq", 2, T))
         if ni.d_hot > D_CLAMP:
-            out.append(("round_eval_split_eq", 1, T))
-            out.append(("round_eval_product", D_REM, T))
+            out.append(("product", D_REM, T))
+            out.append(("booleanity", D_REM, T))
+            out.append(("split_eq", 1, T))
     return out
 
 
 def algorithmic_bytes(inputs) -> dict:
-    """Algorithmic HBM bytes of one pass per kernel class: bind of a length-n polynomial reads 32n and writes
-    16n; a round evaluation reads 32n per participating polynomial (the Hamming-weight sum reads the even half: 16n)."""
-    b = {"bind": 0, "round_eval_split_eq": 0, "round_eval_product": 0, "round_eval_dot": 0, "round_sum": 0}
-    for cls, npoly, n0 in sumcheck_list(inputs):
+    """Algorithmic HBM bytes of one pass per kernel class.  A fused round kernel over arrays of current length
+    L reads 32 L and writes 16 L per polynomial (bind) and evaluates the bound arrays in the same pass; the first round of
+    an instance only reads (32 n0).  `bind` = the plain bind launches: last bind of every instance + the HyperKZG folds."""
+    b = {"bind": 0, "sumcheck_fused": 0, "onehot_point_sum": 0, "convert_gather": 0, "scatter_add": 0}
+    for body, npoly, n0 in sumcheck_list(inputs):
         rounds = n0.bit_length() - 1
-        tot = sum(n0 >> j for j in range(rounds))          # sum of the current lengths over the rounds
-        b["bind"] += 48 * tot * npoly
-        b[cls] += (16 if cls == "round_sum" else 32) * tot * npoly
+        b["sumcheck_fused"] += npoly * (32 * n0 + 48 * sum(n0 >> (j - 1) for j in range(1, rounds)))
+        b["bind"] += npoly * 48 * 2
     n = 1 << inputs["ell"]
     b["bind"] += 48 * sum(n >> j for j in range(inputs["ell"] - 1))        # HyperKZG folds (hyperkzg/mod.rs:415-428)
+    for ni in inputs["nodes"]:
+        T = 1 << ni.spec.log_t
+        b["onehot_point_sum"] += ni.d_hot * T * (4 + 64)                   # address + gathered affine base
+        b["convert_gather"] += 2 * ni.d_hot * T * (4 + 32)                 # RA + H materialisations
+        b["scatter_add"] += ni.d_hot * T * (4 + 32)                        # G tables: address + eq value per entry
     return b
 
 
 def algorithmic_fieldmuls(inputs) -> dict:
-    """Nominal Fq / Fr multiplications of the compute-bound classes: 10 Fq-mul per mixed addition (XYZZ),
-    d^2 Fr-mul per pair for a product-of-d round."""
+    """Nominal field multiplications of the compute-bound classes (SURVEY §8d): 10 Fq-mul per mixed addition (XYZZ);
+    per pair of a round: d^2 for a product-of-d body (+d for the fused bind), 5 per polynomial for booleanity,
+    4 + 2 for MUL, 2 + npoly for the linear bodies."""
     adds = sum(ni.d_hot * (1 << ni.spec.log_t) for ni in inputs["nodes"])
     n = 1 << inputs["ell"]
-    msm_pairs = 4 * n
-    nwin = 16                                         # 255 bits / c = 16 signed windows
-    prod = 0
-    for cls, npoly, n0 in sumcheck_list(inputs):
-        if cls == "round_eval_product":
-            prod += npoly * npoly * (n0 - 1)          # sum over rounds of (n/2) pairs = n0 - 1
-    return {"msm_accumulate": 10 * (adds + msm_pairs * nwin), "round_eval_product": prod}
+    fused = 0
+    for body, npoly, n0 in sumcheck_list(inputs):
+        pairs = n0 - 1                                # sum over the rounds of the pairs evaluated
+        per_pair = {"product": npoly * npoly + npoly, "booleanity": 5 * npoly, "split_eq": 2 * npoly + 2, "dot": 4}[body]
+        fused += per_pair * pairs
+    return {"onehot_point_sum": 10 * adds, "msm_accumulate": 10 * 4 * n * 16, "sumcheck_fused": fused}
 
 
 def config_dict(config: str, inputs, world: int = 1) -> dict:
@@ -330,7 +346,8 @@ def config_dict(config: str, inputs, world: int = 1) -> dict:
 
 
 def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx) -> dict:
-    """Per-class achieved rates of one profiled pass + a large-n sweep of the streaming kernels."""
+    """Per-class achieved rates of one profiled pass + a large-n sweep of the streaming kernels.  A class that has both an
+    algorithmic byte count and a field-mul count is bound by whichever roofline time is larger."""
     ab = algorithmic_bytes(inputs)
     am = algorithmic_fieldmuls(inputs)
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -339,27 +356,29 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx)
     classes = {}
     for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         row = {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4)}
-        if name in ab and v["ms"] > 0:
+        if ab.get(name) and v["ms"] > 0:
             row["algorithmic_bytes"] = ab[name]
             row["GBps"] = round(ab[name] / v["ms"] / 1e6, 2)
-        if name in am and v["ms"] > 0:
+        if am.get(name) and v["ms"] > 0:
             row["field_muls"] = am[name]
             row["Gmul_per_s"] = round(am[name] / v["ms"] / 1e6, 2)
         classes[name] = row
     dom_name = next(iter(classes))
     dom = classes[dom_name]
-    if dom_name in am:
-        dominant = {"kernel": dom_name, "bound": "int32 field-mul (no tensor cores on this path)", "achieved": dom["Gmul_per_s"],
-                    "peak": round(mul_peak, 2), "unit": "Gmul/s", "frac": round(dom["Gmul_per_s"] / mul_peak, 4),
-                    "traffic": None, "peak_source": "calibrated live: register-resident Montgomery product loop",
-                    "per_launch_ms": round(dom["ms"] / dom["launches"], 5), "share_of_step": dom["share"]}
+    t_hbm = dom.get("algorithmic_bytes", 0) / (hbm * 1e9)
+    t_mul = dom.get("field_muls", 0) / (mul_peak * 1e9)
+    common = {"kernel": dom_name, "traffic": None, "per_launch_ms": round(dom["ms"] / dom["launches"], 5),
+              "share_of_step": dom["share"], "roofline_ms": round(max(t_hbm, t_mul) * 1e3, 4), "measured_ms": dom["ms"]}
+    if t_mul > t_hbm:
+        dominant = dict(common, bound="int32 field-mul (no tensor cores on this path)", achieved=dom["Gmul_per_s"],
+                        peak=round(mul_peak, 2), unit="Gmul/s", frac=round(dom["Gmul_per_s"] / mul_peak, 4),
+                        peak_source="calibrated live: register-resident Montgomery product loop")
     else:
         gb = dom.get("GBps", 0.0)
-        dominant = {"kernel": dom_name, "bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": round(gb / hbm, 4),
-                    "traffic": None, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peaks_kind,
-                    "per_launch_ms": round(dom["ms"] / dom["launches"], 5), "share_of_step": dom["share"]}
+        dominant = dict(common, bound="hbm", achieved=gb, peak=hbm, unit="GB/s", frac=round(gb / hbm, 4),
+                        peak_source="%s (MEASURED_PEAKS.json hbm_gbs)" % peaks_kind)
     sweep = []
-    for which, name, bytes_per_n in ((0, "bind_low_to_high", 48), (1, "bind_high_to_low", 48), (2, "round_eval_mul", 64)):
+    for which, name, bytes_per_n in ((0, "bind_low_to_high", 48), (1, "bind_high_to_low", 48), (4, "round_eval_add", 64), (2, "round_eval_mul", 64)):
         for log_n in (24, 26):
             ms = ctx.bench_kernel(which, log_n, 1, 10)
             gb = bytes_per_n * (1 << log_n) / ms / 1e6

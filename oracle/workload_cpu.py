@@ -16,6 +16,19 @@ def _index_lists(ni):
     return [ni.hot_k[i].astype(np.uint64) * np.uint64(T) + t for i in range(ni.d_hot)]
 
 
+def _ra_checks(ni, lo, hi, claim, t, out):
+    k = np.ascontiguousarray(ni.hot_k[lo:hi])
+    G = ORC.compute_ra_evals(k, 16, ni.eq_w)
+    ra = np.stack([np.ascontiguousarray(ni.tables[j][ni.hot_k[j]]) for j in range(lo, hi)])
+    r = ORC.batched_sumcheck_prove([
+        {"kind": 4, "polys": ra, "eq_w": ni.eq_w, "claim": claim},
+        {"kind": 18, "polys": G, "aux_fr": ni.gammas[lo:hi], "claim": claim},
+        {"kind": 32, "polys": G, "idx": k, "eq_w": ni.eq_w, "aux_u32": 4, "aux_fr": np.concatenate([ni.gammas[lo:hi], ni.r_addr])},
+    ], t)
+    out["finals"].extend(r["final_claims"])
+    return ra[0]
+
+
 def run_cpu(srs_host: np.ndarray, inputs, rlc_host: np.ndarray, node_limit: int | None = None, do_open: bool = True):
     """srs_host: (n, 8) affine Montgomery limbs; rlc_host: (2^ell, 4) Fr of the polynomial to open.
     node_limit bounds the number of nodes processed (bench samples)."""
@@ -25,14 +38,13 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host: np.ndarray, node_limit: int 
     nodes = inputs["nodes"] if node_limit is None else inputs["nodes"][:node_limit]
     for ni in nodes:
         spec = ni.spec
-        coms = [ORC.sum_indexed(srs_host, idx) for idx in _index_lists(ni)]
-        out["commitments"].append((np.stack([c[0] for c in coms]), np.array([c[1] for c in coms])))
-        ra = [np.ascontiguousarray(ni.tables[j][ni.hot_k[j]]) for j in range(ni.d_hot)]
-        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra[0]]), ni.eq_w, claim, t)
-        out["finals"].append(r["final_claims"])
-        r = ORC.sumcheck_prove_st(2, 0, np.stack(ra[:D_CLAMP]), None, claim, t, gammas=ni.gammas[:D_CLAMP])
-        out["finals"].append(r["final_claims"])
-        r = ORC.sumcheck_prove_st(0, 4, np.stack(ra[:D_CLAMP]), ni.eq_w, claim, t)
+        lists = _index_lists(ni)
+        for lo, hi in ((0, D_CLAMP), (D_CLAMP, ni.d_hot)):
+            if hi > lo:
+                coms = [ORC.sum_indexed(srs_host, idx) for idx in lists[lo:hi]]
+                out["commitments"].append((np.stack([c[0] for c in coms]), np.array([c[1] for c in coms])))
+        ra0 = _ra_checks(ni, 0, D_CLAMP, claim, t, out)
+        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra0]), ni.eq_w, claim, t)
         out["finals"].append(r["final_claims"])
         if spec.kind == "einsum":
             left = ORC.tensor_fold_i32(ni.A, ORC.eq_evals(ni.eq_rows), False)
@@ -43,9 +55,8 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host: np.ndarray, node_limit: int 
             r = ORC.sumcheck_prove_st(0, 2 if spec.kind == "mul" else 0, np.stack([a, b]), ni.eq_w, claim, t)
         out["finals"].append(r["final_claims"])
         if ni.d_hot > D_CLAMP:
-            r = ORC.sumcheck_prove_st(0, 6, np.stack([ra[D_CLAMP]]), ni.eq_w, claim, t)
-            out["finals"].append(r["final_claims"])
-            r = ORC.sumcheck_prove_st(0, 4, np.stack(ra[D_CLAMP:]), ni.eq_w, claim, t)
+            rem0 = _ra_checks(ni, D_CLAMP, ni.d_hot, claim, t, out)
+            r = ORC.sumcheck_prove_st(0, 6, np.stack([rem0]), ni.eq_w, claim, t)
             out["finals"].append(r["final_claims"])
         out["states"].append(t.state)
     if do_open:

@@ -20,6 +20,8 @@ with Context(0) as ctx:
     T = 1 << ni.spec.log_t
     hot = A.OneHotBatch(ctx, W.onehot_index_lists(ni))
     ra = [A.MultilinearPolynomial.from_lookup(ctx, ni.tables[j], ni.hot_k[j]) for j in range(ni.d_hot)]
+    hot16 = A.OneHotAddresses(ctx, ni.hot_k[:16], 16)
+    hot4 = A.OneHotAddresses(ctx, ni.hot_k[16:], 16)
     t = A.Blake2bTranscriptState(b"x")
 
     def timeit(name, fn, reps=20):
@@ -33,6 +35,12 @@ with Context(0) as ctx:
         print("%-40s %10.1f us" % (name, dt), flush=True)
 
     timeit("onehot_commit 20x2^14", lambda: hot.commit(srs))
+    timeit("addr16.commit 16x2^14", lambda: hot16.commit(srs))
+    timeit("addr16.ra_evals", lambda: hot16.ra_evals(ni.eq_w))
+    timeit("addr16.gather", lambda: [q.free() for q in hot16.gather(ni.tables[:16])])
+    out_d = {"finals": [], "msg_bytes": 0}
+    timeit("RA checks batch d=16 (18 rounds)", lambda: W._ra_checks(A, ctx, hot16, ni, 0, 16, inputs["claim"], t, out_d, None).free())
+    timeit("RA checks batch d=4 (18 rounds)", lambda: W._ra_checks(A, ctx, hot4, ni, 16, 20, inputs["claim"], t, out_d, None).free())
     timeit("clone 2^14", lambda: ra[0].clone().free())
     timeit("clone x16 2^14", lambda: [q.free() for q in [p.clone() for p in ra[:16]]])
 
