@@ -67,7 +67,10 @@ enum {
   JA_EVAL_DOT2 = 16,    /* [sum l(0)r(0), sum l(2)r(2)]             einsum/dot.rs:292-303   n_out=2 */
   JA_EVAL_DOT3 = 17,    /* [sum l r e at 0,2,3], three MLEs of equal length  dot.rs:330-350   n_out=3 */
   JA_EVAL_SUM1 = 18,    /* [sum_i gamma_i * sum_j p_i[2j]]  LowToHigh one eval  hamming_weight.rs:118-139 (aux = gammas) */
-  JA_EVAL_SUMHI = 19    /* [sum_{j<n/2} p[j]]  HighToLow one eval  ops/sum/axis.rs:220-233 */
+  JA_EVAL_SUMHI = 19,   /* [sum_{j<n/2} p[j]]  HighToLow one eval  ops/sum/axis.rs:220-233 */
+  JA_EVAL_OPEN = 20     /* dense opening reduction: [sum_{j<n/2} eq(r, j) P[j]] HighToLow with a HighToLow split-eq
+                           (DensePolynomialProverOpening, subprotocols/opening_reduction.rs:355-419); n_out=1.
+                           Only through ja_sumcheck_prove / ja_batched_sumcheck_prove. */
 };
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -152,7 +155,11 @@ int32_t ja_sumcheck_prove(ja_ctx*, int32_t kind, ja_poly* const* polys, size_t n
  * appended, and r_j is drawn; every active instance then ingests r_j.  ONE host<->device exchange per round serves all
  * instances.  An instance is described by: */
 enum { JA_INST_BOOLEANITY = 32,      /* BooleanitySumcheckProver (subprotocols/booleanity.rs:153-372), input claim 0 */
-       JA_INST_HAMMING_TABLES = 33   /* HammingWeightSumcheckProver over the K-entry G tables (hamming_weight.rs:60-160) */ };
+       JA_INST_HAMMING_TABLES = 33,  /* HammingWeightSumcheckProver over the K-entry G tables (hamming_weight.rs:60-160) */
+       JA_INST_OPENING_ONEHOT = 34   /* OneHotPolynomialProverOpening (opening_reduction.rs:503-723) for the d polynomials of one
+                                        address batch opened at one point: expands to d instances (d claims, d batching
+                                        coefficients); addr, eq_w = r_cycle, aux_fr = r_address (log K), host_tables = the d
+                                        input claims (table_len = 1), out_final_claims = d x 4 */ };
 typedef struct ja_sc_instance {
   int32_t kind;                  /* JA_EVAL_* (device polynomials) or JA_INST_* */
   uint32_t aux_u32;              /* JA_EVAL_POW: degree d; JA_INST_BOOLEANITY: log_k */
@@ -257,6 +264,28 @@ void ja_hyperkzg_open_free(ja_ctx*, ja_hkzg*);
 int32_t ja_hyperkzg_open(ja_ctx*, const ja_srs*, const ja_poly* poly, const uint64_t* point, size_t ell,
                          uint8_t transcript_state[32], uint32_t* n_rounds, uint64_t* com_xy, int32_t* com_inf,
                          uint64_t* w_xy, int32_t* w_inf, uint64_t* v_out);
+
+/* ---- multi-GPU: one process per GPU; the exchange (an all-gather of <= 17 Fr per round or of one point per
+ * MSM and GPU) belongs to the caller; these are the slice entry points and the host-side combine functions. ------------- */
+/* Restrict every MSM this context runs (ja_hyperkzg_open_*, ja_onehot_commit, ...) to the index range of shard `index` of
+ * `count` (joltworks/src/msm/mod.rs:27-181 pairs split by index; the SRS is resident on every GPU).  Results are PARTIAL
+ * points: all-gather them and add with ja_g1_sum_affine.  count == 1 restores the unsharded behaviour. */
+int32_t ja_set_msm_shard(ja_ctx*, uint32_t index, uint32_t count);
+/* sum_{i in [lo, hi)} Z[i] * g1_powers[i] */
+int32_t ja_msm_fr_range(ja_ctx*, const ja_srs*, const ja_poly* scalars, size_t lo, size_t hi, uint64_t out_xy[8], int32_t* is_inf);
+/* One GPU's share of a round evaluation over contiguous hypercube slices: polys = the slice, eq = the replicated split-eq
+ * of the whole instance, g_offset = slice_start / 2.  Family S / PROD / POW (LowToHigh).  Outputs are partial sums. */
+int32_t ja_round_eval_slice(ja_ctx*, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys, const ja_spliteq* eq,
+                            uint32_t aux_u32, size_t g_offset, uint64_t* out_evals, size_t n_out);
+/* Host-only (no ja_ctx, no GPU): add n affine points (complete addition) / add n_parts vectors of n_vals Fr. */
+int32_t ja_g1_sum_affine(const uint64_t* xy, const int32_t* is_inf, size_t n, uint64_t out_xy[8], int32_t* out_inf);
+int32_t ja_fr_sum(const uint64_t* vals, size_t n_parts, size_t n_vals, uint64_t* out);
+/* The library's Blake2b transcript (joltworks/src/transcripts/blake2b.rs) for callers that own state + round counter. */
+void ja_transcript_new(const char* label, uint8_t state[32], uint32_t* n_rounds);
+void ja_transcript_append_points(uint8_t state[32], uint32_t* n_rounds, const uint64_t* xy, const int32_t* is_inf, size_t n);
+void ja_transcript_append_scalars(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n);
+void ja_transcript_challenge_scalar(uint8_t state[32], uint32_t* n_rounds, uint64_t out[4]);
+void ja_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
 /* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see this stream). */

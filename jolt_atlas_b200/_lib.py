@@ -72,6 +72,16 @@ SIGNATURES = {
     "ja_hyperkzg_open_witness": (C.c_int32, [vp, vp, u64p, u64p, u64p, i32p]),
     "ja_hyperkzg_open_free": (None, [vp, vp]),
     "ja_hyperkzg_open": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, C.c_char_p, u32p, u64p, i32p, u64p, i32p, u64p]),
+    "ja_set_msm_shard": (C.c_int32, [vp, C.c_uint32, C.c_uint32]),
+    "ja_msm_fr_range": (C.c_int32, [vp, vp, vp, C.c_size_t, C.c_size_t, u64p, i32p]),
+    "ja_round_eval_slice": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, C.c_uint32, C.c_size_t, u64p, C.c_size_t]),
+    "ja_g1_sum_affine": (C.c_int32, [u64p, i32p, C.c_size_t, u64p, i32p]),
+    "ja_fr_sum": (C.c_int32, [u64p, C.c_size_t, C.c_size_t, u64p]),
+    "ja_transcript_new": (None, [C.c_char_p, C.c_char_p, u32p]),
+    "ja_transcript_append_points": (None, [C.c_char_p, u32p, u64p, i32p, C.c_size_t]),
+    "ja_transcript_append_scalars": (None, [C.c_char_p, u32p, u64p, C.c_size_t]),
+    "ja_transcript_challenge_scalar": (None, [C.c_char_p, u32p, u64p]),
+    "ja_transcript_challenge_scalar_powers": (None, [C.c_char_p, u32p, C.c_size_t, u64p]),
     "ja_profile_begin": (C.c_int32, [vp]),
     "ja_profile_end": (C.c_int32, [vp, u64p, C.POINTER(C.c_double), C.c_size_t]),
     "ja_profile_class_count": (C.c_int32, []),

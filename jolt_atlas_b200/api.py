@@ -29,7 +29,7 @@ class BindingOrder:
 
 class EvalKernel:
     ADD, SUB, MUL, SQUARE, PROD, POW, IDENT = 0, 1, 2, 3, 4, 5, 6
-    DOT2, DOT3, SUM1, SUMHI = 16, 17, 18, 19
+    DOT2, DOT3, SUM1, SUMHI, OPEN = 16, 17, 18, 19, 20
     N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 16: 2, 17: 3, 18: 1, 19: 1}
     FAMILY_S = (0, 1, 2, 3, 4, 5, 6)
 
@@ -510,7 +510,7 @@ def commit_one_hot_batches(ctx: Context, srs: SRS, batches):
 
 
 class InstanceKind:
-    BOOLEANITY, HAMMING_TABLES = 32, 33
+    BOOLEANITY, HAMMING_TABLES, OPENING_ONEHOT = 32, 33, 34
 
 
 def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscriptState, max_coeffs: int = 40):
@@ -518,6 +518,8 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
          device kinds   {"kind": EvalKernel.*, "polys": [MultilinearPolynomial...], "eq_w", "aux_fr", "aux_u32", "claim"}
          BOOLEANITY     {"kind": 32, "tables": G (d, K, 4), "addr": OneHotAddresses, "eq_w": r_cycle, "gammas", "r_address"}
          HAMMING_TABLES {"kind": 33, "tables": G (d, K, 4), "aux_fr": gamma powers, "claim"}
+         OPENING_ONEHOT {"kind": 34, "addr": OneHotAddresses (d lists), "eq_w": r_cycle, "r_address", "claims": (d, 4)}
+                        expands to d instances; its final_claims entry is (d, 4)
     Device polynomials are consumed.  Returns dict(coeffs, challenges, final_claims=[per instance (n, 4)])."""
     n = len(instances)
     arr = (_lib.ScInstance * n)()
@@ -526,7 +528,11 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
         kind = int(d["kind"])
         arr[i].kind = kind
         arr[i].aux_u32 = int(d.get("aux_u32", 0))
-        if kind in (InstanceKind.BOOLEANITY, InstanceKind.HAMMING_TABLES):
+        if kind == InstanceKind.OPENING_ONEHOT:
+            d = dict(d)
+            d["tables"] = _fr_arg(d["claims"]).reshape(-1, 1, 4)
+            d["aux_fr"] = d["r_address"]
+        if kind in (InstanceKind.BOOLEANITY, InstanceKind.HAMMING_TABLES, InstanceKind.OPENING_ONEHOT):
             tabs = np.ascontiguousarray(d["tables"], dtype=np.uint64)
             keep.append(tabs)
             arr[i].n_polys, arr[i].table_len = tabs.shape[0], tabs.shape[1]
@@ -542,6 +548,9 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
             npoly = len(polys)
             rounds = len(polys[0]).bit_length() - 1
         aux = d.get("aux_fr")
+        if kind == InstanceKind.OPENING_ONEHOT:
+            arr[i].addr = d["addr"]._h
+            rounds = _fr_arg(aux).reshape(-1, 4).shape[0] + _fr_arg(d["eq_w"]).reshape(-1, 4).shape[0]
         if kind == InstanceKind.BOOLEANITY:
             arr[i].addr = d["addr"]._h
             ra = _fr_arg(d["r_address"]).reshape(-1, 4)

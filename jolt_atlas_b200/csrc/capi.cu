@@ -440,10 +440,27 @@ static void launch_s(ja_ctx* c, const EvalPolys& P, const ja_spliteq* eq, size_t
   size_t tpb = (tiles + grid - 1) / grid;
   grid = (tiles + tpb - 1) / tpb;
   JA_LAUNCH(c, KC_ROUND_EVAL_S, k_round_eval_s<KID><<<(unsigned)grid, kBlock, 0, c->stream>>>(P, eq->e_out(), eq->e_in(), bits_in, G, tpb,
-                                                                c->d_partials, c->d_counter, c->d_out));
+                                                                c->d_partials, c->d_counter, c->d_out,
+                                                                c->slice_on ? c->slice_g_offset : 0));
 }
 
 extern "C" {
+
+// One GPU's share of a round evaluation when every MLE is sharded into contiguous hypercube slices (shard.cu):
+// `polys` hold the slice, `eq` is the replicated split-eq of the WHOLE instance, g_offset = slice_start / 2.
+// Family S and PROD/POW only (LowToHigh).  out_evals are PARTIAL sums: all-gather them and add (ja_fr_sum).
+int32_t ja_round_eval_slice(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
+                            const ja_spliteq* eq, uint32_t aux_u32, size_t g_offset, uint64_t* out_evals, size_t n_out) {
+  JA_REQUIRE(c && eq, "ja_round_eval_slice: null argument");
+  JA_REQUIRE(kernel_id <= JA_EVAL_IDENT, "ja_round_eval_slice: only the split-eq (LowToHigh) round bodies shard by contiguous slices");
+  JA_REQUIRE(kernel_id != JA_EVAL_PROD && kernel_id != JA_EVAL_POW ? true : (kernel_id == JA_EVAL_POW ? aux_u32 : n_polys) <= 16,
+             "ja_round_eval_slice: product degree must be <= 16");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  c->slice_on = true; c->slice_g_offset = g_offset;
+  const int32_t st = ja_round_eval(c, kernel_id, polys, n_polys, eq, nullptr, 0, aux_u32, out_evals, n_out);
+  c->slice_on = false;
+  return st;
+}
 
 int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
                       const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32,
@@ -497,7 +514,8 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
     JA_REQUIRE(eq != nullptr, "ja_round_eval: split-eq handle required for family S");
     JA_REQUIRE(eq->order == JA_LOW_TO_HIGH, "ja_round_eval: family S expects a LowToHigh split-eq");
     const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
-    JA_REQUIRE(cover == G, "ja_round_eval: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+    if (c->slice_on) JA_REQUIRE(c->slice_g_offset + G <= cover, "ja_round_eval_slice: slice outside the split-eq tables");
+    else JA_REQUIRE(cover == G, "ja_round_eval: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
   } else {
     JA_REQUIRE(eq == nullptr, "ja_round_eval: this kernel_id takes no split-eq handle");
   }
@@ -525,9 +543,10 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
 #define JA_PROD_T(LL)                                                                                                   \
       if (same) JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod_t<LL, true><<<grid, kBlock, 0, c->stream>>>(       \
-                    PP, d, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_out, c->d_counter));           \
+                    PP, d, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_out, c->d_counter, g_off));    \
       else JA_LAUNCH(c, KC_ROUND_EVAL_PROD, k_round_eval_prod_t<LL, false><<<grid, kBlock, 0, c->stream>>>(            \
-               PP, d, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_out, c->d_counter))
+               PP, d, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_out, c->d_counter, g_off))
+      const size_t g_off = c->slice_on ? c->slice_g_offset : 0;
       switch (L) {
         case 2: JA_PROD_T(2); break;
         case 4: JA_PROD_T(4); break;

@@ -50,6 +50,10 @@ struct ja_ctx {
   void* h_mapped = nullptr;
   void* d_mapped = nullptr;
   unsigned int seq = 0;
+  // MSM index-range shard of this context (shard.cu): ja_msm_run restricts every job to its slice when count > 1
+  uint32_t msm_shard_index = 0, msm_shard_count = 1;
+  bool slice_on = false;           // ja_round_eval_slice in progress: eq tables are indexed with g + slice_g_offset
+  size_t slice_g_offset = 0;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-kernel-class CUDA-event profile (ja_profile_begin / ja_profile_end; bench.py's roofline leg)
@@ -71,7 +75,7 @@ void ja_prof_post(ja_ctx* c);
 static constexpr int kMaxGrid = kSMs * 8;
 static constexpr int kMaxOut = 32;
 static constexpr size_t kPinnedBytes = 1 << 16;
-static constexpr int kSlots = 16;
+static constexpr int kSlots = 48;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
 
 struct ja_poly {

@@ -52,7 +52,48 @@ static inline FqH inv(const FqH& a) {                   // a^(q-2); inverse of 0
 }
 }  // namespace fq
 
+namespace fq {
+static inline FqH add(const FqH& a, const FqH& b) {
+  FqH r; u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a.l[i] + b.l[i]; r.l[i] = (uint64_t)c; c >>= 64; }
+  if (geq_p(r.l)) sub_p(r.l);
+  return r;
+}
+static inline FqH sub(const FqH& a, const FqH& b) {
+  FqH r; u128 br = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)a.l[i] - b.l[i] - (uint64_t)br; r.l[i] = (uint64_t)t; br = (t >> 64) & 1; }
+  if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r.l[i] + P[i]; r.l[i] = (uint64_t)c; c >>= 64; } }
+  return r;
+}
+static inline FqH dbl(const FqH& a) { return add(a, a); }
+static const FqH ZERO = {{0, 0, 0, 0}};
+}  // namespace fq
+
 struct G1XH { FqH X, Y, ZZ, ZZZ; };                      // mirrors the device G1X (128 B)
+
+// acc += (x, y) affine, complete (EFD xyzz madd-2008-s / dbl-2008-s-1 with a = 0): combining the per-GPU partial points
+// of a sharded MSM is a handful of additions, done where the transcript lives.
+static inline void xyzz_madd(G1XH& acc, const FqH& x, const FqH& y) {
+  using namespace fq;
+  if (acc.ZZ.is_zero()) { acc.X = x; acc.Y = y; acc.ZZ = ONE; acc.ZZZ = ONE; return; }
+  const FqH U2 = mul(x, acc.ZZ), S2 = mul(y, acc.ZZZ);
+  const FqH Pp = sub(U2, acc.X), R = sub(S2, acc.Y);
+  if (Pp.is_zero()) {
+    if (!R.is_zero()) { acc.X = ZERO; acc.Y = ZERO; acc.ZZ = ZERO; acc.ZZZ = ZERO; return; }   // P + (-P)
+    const FqH U = dbl(y), V = mul(U, U), W = mul(U, V), S = mul(x, V), XX = mul(x, x);          // 2P from affine
+    const FqH M = add(dbl(XX), XX);
+    acc.X = sub(sub(mul(M, M), S), S);
+    acc.Y = sub(mul(M, sub(S, acc.X)), mul(W, y));
+    acc.ZZ = V; acc.ZZZ = W;
+    return;
+  }
+  const FqH PP = mul(Pp, Pp), PPP = mul(Pp, PP), Q = mul(acc.X, PP);
+  const FqH X3 = sub(sub(sub(mul(R, R), PPP), Q), Q);
+  const FqH Y3 = sub(mul(R, sub(Q, X3)), mul(acc.Y, PPP));
+  acc.X = X3; acc.Y = Y3;
+  acc.ZZ = mul(acc.ZZ, PP);
+  acc.ZZZ = mul(acc.ZZZ, PPP);
+}
 
 // Affine coordinates of `n` XYZZ points with one inversion.  out_xy = n x 8 limbs, is_inf[i] = 1 for ZZ == 0.
 static inline void xyzz_batch_to_affine(const G1XH* pts, size_t n, uint64_t* out_xy, int32_t* is_inf) {

@@ -308,4 +308,80 @@ k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array:
   if (grid_sum<NOUT>(acc, partials, counter, pub.vals)) publish_flag(pub);
 }
 
+// ---- opening reduction, HighToLow (opening_reduction.rs:355-403 dense, :630-673 one-hot cycle rounds) --------------------
+// q_i(0) = sum_{j < half} E_in[j >> bits_out] * E_out[j & mask] * P_i[j] for d polynomials that share one opening point
+// (blockIdx.y = polynomial; one sum per polynomial: each is its own sumcheck instance).  FUSED: bind the previous
+// challenge in place first (P[j] <- P[j] + r (P[j + 2 half] - P[j]) for j < 2 half).
+// counters: [0, d) per-row block counters, [63] rows finished.
+template <bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_open(FusedPolys P, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_out, size_t half,
+             Fr* partials /* [gridDim.y][gridDim.x] */, unsigned int* counters, Publish pub) {
+  const int row = blockIdx.y;
+  Fr* __restrict__ z = P.out[row];
+  const size_t mask_out = (size_t(1) << bits_out) - 1;
+  Fr acc[1];
+  acc[0] = fp_zero<FrParams>();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+    Fr h;
+    if (FUSED) {
+      const Fr a0 = fp_load(z + j), a1 = fp_load(z + j + 2 * half), b0 = fp_load(z + j + half), b1 = fp_load(z + j + 3 * half);
+      h = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+      const Fr h2 = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
+      fp_store(z + j, h);
+      fp_store(z + j + half, h2);
+    } else {
+      h = fp_load(P.in[row] + j);
+    }
+    const Fr w = fp_mul<FrParams>(fp_load(e_in + (j >> bits_out)), fp_load(e_out + (j & mask_out)));
+    acc[0] = fp_add<FrParams>(acc[0], fp_mul<FrParams>(w, h));
+  }
+  // row-level reduction: the row's blocks behave like a 1-D grid of their own
+  __shared__ Fr s_part[kBlock / 32];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Fr v = fr_warp_sum(acc[0]);
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  Fr tot = fp_zero<FrParams>();
+  if (warp == 0) {
+    tot = lane < (kBlock >> 5) ? s_part[lane] : fp_zero<FrParams>();
+    tot = fr_warp_sum(tot);
+  }
+  Fr* row_part = partials + (size_t)row * gridDim.x;
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) fp_store(row_part + blockIdx.x, tot);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicInc(counters + row, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Fr a = fp_zero<FrParams>();
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+      const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(row_part + b);
+      Fr t;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t.l[i] = q[i];
+      a = fp_add<FrParams>(a, t);
+    }
+    a = fr_warp_sum(a);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+      tot = lane < (kBlock >> 5) ? s_part[lane] : fp_zero<FrParams>();
+      tot = fr_warp_sum(tot);
+    }
+  }
+  // publish the row's sum; the last row to finish raises the flag
+  if (threadIdx.x == 0) {
+    fp_store(pub.vals + row, tot);
+    __threadfence_system();
+    const bool all_done = gridDim.y == 1 || atomicInc(counters + 63, gridDim.y - 1) == gridDim.y - 1;
+    if (all_done) { __threadfence_system(); *pub.seq = pub.value; }
+  }
+}
+
 }  // namespace ja

@@ -204,7 +204,25 @@ static void store_result(const MsmResult& r, uint64_t* out_xy, int32_t* is_inf) 
   if (is_inf) *is_inf = (int32_t)r.inf;
 }
 
-int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, uint64_t* out_xy, int32_t* is_inf) {
+static inline size_t kKindBytesFwd(uint32_t kind) { const size_t b[8] = {32, 1, 2, 4, 8, 4, 8, 8}; return b[kind & 7]; }
+// index-range slice [lo, hi) of a job of n pairs for shard i of k (shard.cu): balanced, contiguous
+static inline void shard_range(size_t n, uint32_t i, uint32_t k, size_t* lo, size_t* hi) {
+  *lo = n * i / k; *hi = n * (i + 1) / k;
+}
+
+int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs_in, uint64_t* out_xy, int32_t* is_inf) {
+  std::vector<MsmJob> jobs = jobs_in;
+  if (c->msm_shard_count > 1) {
+    // every GPU multiplies its index range only; the results are PARTIAL points the caller all-gathers and adds
+    for (MsmJob& j : jobs) {
+      size_t lo, hi;
+      shard_range(j.n, c->msm_shard_index, c->msm_shard_count, &lo, &hi);
+      const size_t bytes = j.kind == 7 ? 8 : kKindBytesFwd(j.kind);
+      j.d_scalars = (const char*)j.d_scalars + lo * bytes;
+      if (j.kind != 7) j.base_offset += lo;
+      j.n = hi - lo;
+    }
+  }
   std::vector<MsmResult> res(jobs.size());
   int32_t st = msm_engine(c, srs, jobs, res.data());
   if (st) return st;

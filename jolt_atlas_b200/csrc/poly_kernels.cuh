@@ -258,7 +258,9 @@ template <> struct SBody<6> {  // IDENT  ps_shout/mod.rs:464-488, opening_reduct
 template <int KID>
 __global__ void __launch_bounds__(kBlock)
 k_round_eval_s(EvalPolys P, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-               size_t tiles_per_block, Fr* partials, unsigned int* counter, Fr* out) {
+               size_t tiles_per_block, Fr* partials, unsigned int* counter, Fr* out, size_t g_off = 0) {
+  // g_off: global index of this GPU's first pair when the arrays are one hypercube slice of a sharded MLE (shard.cu);
+  // the polynomials are indexed locally, the replicated eq tables globally
   constexpr int NOUT = SBody<KID>::NOUT;
   Fr outer[NOUT], inner[NOUT];
 #pragma unroll
@@ -269,7 +271,7 @@ k_round_eval_s(EvalPolys P, const Fr* __restrict__ e_out, const Fr* __restrict__
   if (g_end > G) g_end = G;
   size_t cur_xout = ~size_t(0);
   for (size_t g = g_begin + threadIdx.x; g < g_end; g += kBlock) {
-    const size_t x_out = g >> bits_in;
+    const size_t x_out = (g + g_off) >> bits_in;
     if (x_out != cur_xout) {
       if (cur_xout != ~size_t(0)) {
         Fr eo = fp_load(e_out + cur_xout);
@@ -283,7 +285,7 @@ k_round_eval_s(EvalPolys P, const Fr* __restrict__ e_out, const Fr* __restrict__
     }
     Fr v[NOUT];
     SBody<KID>::eval(P, g, v);
-    Fr ei = fp_load(e_in + (g & mask_in));
+    Fr ei = fp_load(e_in + ((g + g_off) & mask_in));
 #pragma unroll
     for (int k = 0; k < NOUT; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
   }
@@ -416,7 +418,8 @@ JA_DEV Fr block_sum_by_lane(Fr v) {
 template <int L, bool SAME>
 __global__ void __launch_bounds__(kBlock)
 k_round_eval_prod_t(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-                    size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, Fr* out /* [L] */, unsigned int* counter) {
+                    size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, Fr* out /* [L] */, unsigned int* counter,
+                    size_t g_off = 0) {
   constexpr int GPB = kBlock / L;                     // lane groups (pairs in flight) per block
   const int li = threadIdx.x & (L - 1);
   const int group = threadIdx.x / L;
@@ -442,7 +445,7 @@ k_round_eval_prod_t(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* 
     v[L - 1] = pad ? p0 : dp;
     LaneProduct<L>::run(v, li);
     if (active) {
-      const size_t x_out = g >> bits_in;
+      const size_t x_out = (g + g_off) >> bits_in;
       if (x_out != cur_xout) {
         if (cur_xout != ~size_t(0)) {
           outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
@@ -450,7 +453,7 @@ k_round_eval_prod_t(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* 
         }
         cur_xout = x_out;
       }
-      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + (g & mask_in)), v[0]));
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), v[0]));
     }
   }
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));

@@ -117,8 +117,10 @@ struct Inst {
   size_t rounds = 0;
   FrH claim = host::FR_ZERO;
   uint64_t* out_final = nullptr;
+  int slot_id = -1;                 // host-mapped result slot (assigned by run() to the instances that publish from a kernel)
+  virtual bool needs_slot() const { return false; }
   virtual ~Inst() {}
-  virtual int32_t launch(ja_ctx* c, size_t round, int slot) = 0;
+  virtual int32_t launch(ja_ctx* c, size_t round) = 0;
   // host work that depends on the instance state only (the round's field inversion): runs after EVERY instance of the
   // batch has enqueued its kernel, i.e. overlapped with the kernels
   virtual int32_t prework(ja_ctx*, size_t) { return JA_OK; }
@@ -167,6 +169,7 @@ struct DevInst : Inst {
       case JA_EVAL_POW: n_out = pow_d; JA_REQUIRE(polys.size() == 1, "sumcheck: POW takes one polynomial"); fusable = pow_d <= 16; break;
       case JA_EVAL_DOT2: n_out = 2; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 2, "sumcheck: DOT2 takes two polynomials"); fusable = true; break;
       case JA_EVAL_DOT3: n_out = 3; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 3, "sumcheck: DOT3 takes three polynomials"); fusable = true; break;
+      case JA_EVAL_OPEN: n_out = 1; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 1, "sumcheck: OPEN takes one polynomial"); fusable = true; break;
       case JA_EVAL_SUM1: n_out = 1; break;
       case JA_EVAL_SUMHI: n_out = 1; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 1, "sumcheck: SUMHI takes one polynomial"); break;
       default: return fail(JA_ERR_UNSUPPORTED, "sumcheck: kind not implemented");
@@ -181,7 +184,8 @@ struct DevInst : Inst {
     }
     return JA_OK;
   }
-  bool uses_eq() const { return kind <= 7; }
+  bool uses_eq() const { return kind <= 7 || kind == JA_EVAL_OPEN; }
+  bool needs_slot() const override { return fusable; }
 
   // fused round kernel (bind pend_ch first when `pending`)
   int32_t launch_fused(ja_ctx* c) {
@@ -210,7 +214,7 @@ struct DevInst : Inst {
     int bits_in = 0;
     const Fr *e_out = nullptr, *e_in = nullptr;
     if (uses_eq()) {
-      JA_REQUIRE(eq && eq->order == JA_LOW_TO_HIGH, "sumcheck: family S expects a LowToHigh split-eq");
+      JA_REQUIRE(eq && eq->order == order, "sumcheck: split-eq binding order does not match the round body");
       const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
       JA_REQUIRE(cover == G, "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
       bits_in = eq->in_len - 1; e_out = eq->e_out(); e_in = eq->e_in();
@@ -233,6 +237,12 @@ struct DevInst : Inst {
 #undef JA_PROD_L
 #undef JA_PROD_F
       prod_lanes = L;
+    } else if (kind == JA_EVAL_OPEN) {
+      unsigned grid = grid_for(G);
+      if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+      const int bits_out = eq->out_len - 1;
+      if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<true><<<dim3(grid, 1), kBlock, 0, s>>>(P, ch, e_out, e_in, bits_out, G, part, ctr, pub));
+      else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<false><<<dim3(grid, 1), kBlock, 0, s>>>(P, ch, e_out, e_in, bits_out, G, part, ctr, pub));
     } else if (kind == JA_EVAL_DOT2 || kind == JA_EVAL_DOT3) {
       unsigned grid = grid_for(G);
       if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
@@ -279,7 +289,7 @@ struct DevInst : Inst {
     return JA_OK;
   }
 
-  int32_t launch(ja_ctx* c, size_t, int slot_id) override {
+  int32_t launch(ja_ctx* c, size_t) override {
     int32_t st;
     legacy = !fusable;
     if (fusable) {
@@ -327,8 +337,8 @@ struct DevInst : Inst {
     for (size_t k = 0; k < n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
     const FrH prev = has_scale ? host::mul(prev_in, scale_inv) : prev_in;
     switch (kind) {
-      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT:
-        *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev, div); break;               // ops/add.rs:297-304
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT: case JA_EVAL_OPEN:
+        *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev, div); break;               // ops/add.rs:297-304, opening_reduction.rs:402
       case JA_EVAL_MUL: case JA_EVAL_SQUARE: case 7:
         *uni = host::gruen_poly_deg_3(cs, cw, e[0], e[1], prev, div); break;         // ops/mul.rs:177, booleanity.rs:295-300
       case JA_EVAL_PROD: case JA_EVAL_POW:
@@ -372,7 +382,7 @@ struct DevInst : Inst {
 struct HammingHostInst : Inst {
   std::vector<std::vector<FrH>> ra;
   std::vector<FrH> gammas;
-  int32_t launch(ja_ctx*, size_t, int) override { return JA_OK; }
+  int32_t launch(ja_ctx*, size_t) override { return JA_OK; }
   int32_t message(ja_ctx*, size_t, const FrH& prev, Coeffs* uni) override {
     FrH acc = host::FR_ZERO;
     for (size_t i = 0; i < ra.size(); i++) {
@@ -412,7 +422,8 @@ struct BooleanityInst : Inst {
   std::unique_ptr<DevInst> p2;
   std::vector<ja_poly*> H;
 
-  int32_t launch(ja_ctx* c, size_t round, int slot) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k, slot); }
+  bool needs_slot() const override { return true; }
+  int32_t launch(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k); }
   int32_t prework(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->prework(c, round - log_k); }
   int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
     if (round >= log_k) return p2->message(c, round - log_k, prev, uni);
@@ -460,6 +471,7 @@ struct BooleanityInst : Inst {
     if ((st = ja_spliteq_new(c, r_cycle.data(), log_t, JA_LOW_TO_HIGH, nullptr, &p2->eq))) return st;
     p2->own_eq = true;
     p2->scale = B.scalar; p2->has_scale = true; p2->scale_inv = host::inv(B.scalar);
+    p2->slot_id = slot_id;
     G.clear();
     return p2->setup(c);
   }
@@ -474,7 +486,158 @@ struct BooleanityInst : Inst {
   }
 };
 
-int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::unique_ptr<Inst>* out) {
+// OneHotPolynomialProverOpening (opening_reduction.rs:503-723) for the d one-hot polynomials of one address batch that are
+// opened at the same point (they share EqAddressState / EqCycleState in the reference, :207-258).  Every polynomial is
+// its own sumcheck instance (own claim, own batching coefficient); the group does the shared work once per round:
+// log K address rounds on the host (B = eq(r_address, .) bound HighToLow, expanding table F HighToLow, G_i), then log T
+// cycle rounds on the device: ONE launch evaluates all d polynomials H_i[j] = F[k_i[j]] (k_round_open, d rows).
+struct OpenGroup {
+  size_t d = 0, log_k = 0, log_t = 0;
+  const ja_addr* addr = nullptr;
+  std::vector<FrH> B, F;
+  std::vector<std::vector<FrH>> G;
+  std::vector<ja_poly*> H;
+  ja_spliteq* D = nullptr;
+  std::vector<uint64_t> r_cycle;
+  FrH ea = host::FR_ONE, ea_inv = host::FR_ONE;       // eq(r_address, r') and its inverse (:667-672)
+  bool pending = false;
+  uint64_t pend_ch[4] = {0, 0, 0, 0};
+  int slot_id = -1;
+  Slot slot;
+  size_t launched_for = ~size_t(0), pre_for = ~size_t(0), waited_for = ~size_t(0), ingested_for = ~size_t(0);
+  bool finalized = false;
+  FrH cs, cw, div;
+  std::vector<FrH> vals;
+
+  int32_t launch(ja_ctx* c, size_t round) {
+    if (round < log_k || launched_for == round) return JA_OK;
+    launched_for = round;
+    const bool fz = pending;
+    const size_t len_in = H[0]->len, len_eval = fz ? len_in / 2 : len_in, half = len_eval / 2;
+    FusedPolys P;
+    for (size_t q = 0; q < d; q++) { P.in[q] = H[q]->data(); P.out[q] = H[q]->data(); }
+    const size_t cover = size_t(1) << ((D->out_len - 1) + (D->in_len - 1));
+    JA_REQUIRE(cover == half, "sumcheck: opening split-eq tables do not cover len/2");
+    slot = arm_slot(c, slot_id);
+    unsigned gx = grid_for(half);
+    const unsigned cap = (unsigned)std::max<size_t>(1, (size_t)kSMs * 4 / d);
+    if (gx > cap) gx = cap;
+    const Challenge ch = to_challenge(pend_ch);
+    const int bits_out = D->out_len - 1;
+    if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<true><<<dim3(gx, (unsigned)d), kBlock, 0, c->stream>>>(P, ch, D->e_out(), D->e_in(), bits_out, half, c->d_partials, c->d_counter, slot.pub));
+    else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<false><<<dim3(gx, (unsigned)d), kBlock, 0, c->stream>>>(P, ch, D->e_out(), D->e_in(), bits_out, half, c->d_partials, c->d_counter, slot.pub));
+    JA_CUDA(cudaGetLastError());
+    if (fz) { for (ja_poly* p : H) p->len = len_eval; pending = false; }
+    return JA_OK;
+  }
+  int32_t prework(ja_ctx*, size_t round) {
+    if (round < log_k || pre_for == round) return JA_OK;
+    pre_for = round;
+    uint64_t t[4];
+    int32_t st;
+    ja_spliteq_current_scalar(D, t); cs = host::from_limbs(t);
+    if ((st = ja_spliteq_current_w(D, t))) return st;
+    cw = host::from_limbs(t);
+    div = host::inv(host::gruen_eq1(cs, cw));
+    return JA_OK;
+  }
+  int32_t wait(ja_ctx* c, size_t round) {
+    if (waited_for == round) return JA_OK;
+    waited_for = round;
+    int32_t st = wait_slot(c, slot);
+    if (st) return st;
+    vals.resize(d);
+    for (size_t i = 0; i < d; i++) vals[i] = host::from_limbs(slot.host_vals + 4 * i);
+    return JA_OK;
+  }
+  int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t round) {
+    if (ingested_for == round) return JA_OK;
+    ingested_for = round;
+    int32_t st;
+    if (round >= log_k) {
+      if ((st = ja_spliteq_bind(c, D, ch))) return st;
+      memcpy(pend_ch, ch, 32); pending = true;
+      return JA_OK;
+    }
+    const FrH r = host::from_limbs(ch);
+    const size_t half = B.size() / 2;                               // B.bind_parallel(r, HighToLow)
+    for (size_t i = 0; i < half; i++) B[i] = host::add(B[i], host::mul(r, host::sub(B[i + half], B[i])));
+    B.resize(half);
+    std::vector<FrH> nf(F.size() * 2);                              // ExpandingTable::update, HighToLow (expanding_table.rs:76-86)
+    for (size_t i = 0; i < F.size(); i++) { const FrH e1 = host::mul(r, F[i]); nf[2 * i] = host::sub(F[i], e1); nf[2 * i + 1] = e1; }
+    F.swap(nf);
+    if (round + 1 < log_k) return JA_OK;
+    ea = B[0]; ea_inv = host::inv(ea);                              // B.final_claim()
+    std::vector<uint64_t> tabs(d * addr->K * 4);
+    for (size_t i = 0; i < d; i++) memcpy(tabs.data() + i * addr->K * 4, F.data(), addr->K * 32);
+    H.assign(d, nullptr);
+    if ((st = ja_addr_gather(c, addr, tabs.data(), H.data()))) return st;
+    G.clear();
+    return ja_spliteq_new(c, r_cycle.data(), log_t, JA_HIGH_TO_LOW, nullptr, &D);
+  }
+  int32_t finalize(ja_ctx* c) {
+    if (finalized) return JA_OK;
+    finalized = true;
+    JA_REQUIRE(D != nullptr, "sumcheck: one-hot opening never reached its cycle rounds");
+    if (pending) {
+      int32_t st = ja_bind_many(c, H.data(), H.size(), pend_ch, JA_HIGH_TO_LOW);
+      if (st) return st;
+      pending = false;
+    }
+    return JA_OK;
+  }
+  void release(ja_ctx* c) {
+    if (D) ja_spliteq_free(c, D);
+    D = nullptr;
+    for (ja_poly* h : H) ja_poly_free(c, h);
+    H.clear();
+  }
+};
+
+struct OpenMember : Inst {
+  std::shared_ptr<OpenGroup> g;
+  size_t i = 0;
+  bool needs_slot() const override { return i == 0; }
+  int32_t launch(ja_ctx* c, size_t round) override { g->slot_id = g->slot_id < 0 ? slot_id : g->slot_id; return g->launch(c, round); }
+  int32_t prework(ja_ctx* c, size_t round) override { return g->prework(c, round); }
+  int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
+    if (round < g->log_k) {                                         // opening_reduction.rs:579-629
+      const size_t nu = g->log_k - round, half = g->B.size() / 2;
+      const std::vector<FrH>& Gi = g->G[i];
+      FrH e0 = host::FR_ZERO, e2 = host::FR_ZERO;
+      for (size_t kp = 0; kp < half; kp++) {
+        const FrH b0 = g->B[kp], b1 = g->B[kp + half];
+        const FrH b2 = host::add(b1, host::sub(b1, b0));
+        FrH i0 = host::FR_ZERO, i2 = host::FR_ZERO;
+        for (size_t k = kp; k < Gi.size(); k += half) {
+          const FrH GF = host::mul(Gi[k], g->F[k >> nu]);
+          if (((k >> (nu - 1)) & 1) == 0) { i0 = host::add(i0, GF); i2 = host::sub(i2, GF); }
+          else i2 = host::add(i2, host::add(GF, GF));
+        }
+        e0 = host::add(e0, host::mul(b0, i0));
+        e2 = host::add(e2, host::mul(b2, i2));
+      }
+      *uni = host::from_evals_and_hint(prev, {e0, e2});
+      return JA_OK;
+    }
+    int32_t st = g->wait(c, round);
+    if (st) return st;
+    *uni = scaled(host::gruen_poly_deg_2(g->cs, g->cw, g->vals[i], host::mul(prev, g->ea_inv), g->div), g->ea);   // :667-672
+    return JA_OK;
+  }
+  int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t round) override { return g->ingest(c, ch, round); }
+  int32_t finalize(ja_ctx* c, uint64_t* staging, size_t* count) override {
+    int32_t st = g->finalize(c);
+    if (st) return st;
+    JA_REQUIRE(g->H[i]->len == 1, "sumcheck: one-hot opening not fully bound");
+    JA_CUDA(cudaMemcpyAsync(staging, g->H[i]->data(), sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+    *count = 1;
+    return JA_OK;
+  }
+  void release(ja_ctx* c) override { if (i == 0) g->release(c); }
+};
+
+int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::vector<std::unique_ptr<Inst>>* out) {
   int32_t st;
   if (d.kind == JA_INST_BOOLEANITY) {
     JA_REQUIRE(d.addr && d.host_tables && d.eq_w && d.aux_fr, "sumcheck: booleanity needs addr, G tables, r_cycle and gammas|r_address");
@@ -496,7 +659,38 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::unique_ptr<Inst>
     b->rounds = b->log_k + b->log_t;
     b->claim = host::FR_ZERO;                                        // booleanity.rs:70-72
     b->out_final = d.out_final_claims;
-    out->reset(b.release());
+    out->emplace_back(b.release());
+    return JA_OK;
+  }
+  if (d.kind == JA_INST_OPENING_ONEHOT) {
+    JA_REQUIRE(d.addr && d.eq_w && d.aux_fr && d.host_tables, "sumcheck: one-hot opening needs addr, r_cycle, r_address and the d claims");
+    std::shared_ptr<OpenGroup> g(new OpenGroup());
+    g->d = d.addr->d; g->log_k = d.n_aux; g->log_t = d.eq_m; g->addr = d.addr;
+    JA_REQUIRE(d.n_polys == g->d && (size_t(1) << g->log_k) == d.addr->K && (size_t(1) << g->log_t) == d.addr->T && g->log_k >= 1 && g->log_t >= 1,
+               "sumcheck: one-hot opening shape mismatch (d, K = 2^|r_address|, T = 2^|r_cycle|)");
+    g->r_cycle.assign(d.eq_w, d.eq_w + 4 * d.eq_m);
+    // B = eq(r_address, .) (EqAddressState::new, :207-226), G_i over D.merge() = eq(r_cycle, .) (:541-566)
+    g->B = {host::FR_ONE};
+    for (size_t j = 0; j < g->log_k; j++) {
+      const FrH wj = host::from_limbs(d.aux_fr + 4 * j);
+      std::vector<FrH> nb(g->B.size() * 2);
+      for (size_t i = 0; i < g->B.size(); i++) { nb[2 * i + 1] = host::mul(g->B[i], wj); nb[2 * i] = host::sub(g->B[i], nb[2 * i + 1]); }
+      g->B.swap(nb);
+    }
+    g->F = {host::FR_ONE};
+    std::vector<uint64_t> Gt(g->d * d.addr->K * 4);
+    int32_t st2 = ja_addr_ra_evals(c, d.addr, d.eq_w, d.eq_m, Gt.data());
+    if (st2) return st2;
+    g->G.resize(g->d);
+    for (size_t i = 0; i < g->d; i++) { g->G[i].resize(d.addr->K); memcpy(g->G[i].data(), Gt.data() + i * d.addr->K * 4, d.addr->K * 32); }
+    for (size_t i = 0; i < g->d; i++) {
+      std::unique_ptr<OpenMember> m(new OpenMember());
+      m->g = g; m->i = i;
+      m->rounds = g->log_k + g->log_t;
+      m->claim = host::from_limbs(d.host_tables + 4 * i);
+      m->out_final = d.out_final_claims ? d.out_final_claims + 4 * i : nullptr;
+      out->emplace_back(m.release());
+    }
     return JA_OK;
   }
   if (d.kind == JA_INST_HAMMING_TABLES) {
@@ -515,7 +709,7 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::unique_ptr<Inst>
     h->rounds = (size_t)log2z(d.table_len);
     h->claim = host::from_limbs(d.claim);
     h->out_final = d.out_final_claims;
-    out->reset(h.release());
+    out->emplace_back(h.release());
     return JA_OK;
   }
   JA_REQUIRE(d.polys && d.n_polys, "sumcheck: instance without polynomials");
@@ -530,12 +724,12 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::unique_ptr<Inst>
   if ((st = v->setup(c))) return st;
   if (v->uses_eq()) {
     JA_REQUIRE(d.eq_w && d.eq_m == v->rounds, "sumcheck: family S needs one eq point coordinate per round");
-    if ((st = ja_spliteq_new(c, d.eq_w, d.eq_m, JA_LOW_TO_HIGH, nullptr, &v->eq))) return st;
+    if ((st = ja_spliteq_new(c, d.eq_w, d.eq_m, v->order, nullptr, &v->eq))) return st;
     v->own_eq = true;
   }
   v->claim = host::from_limbs(d.claim);
   v->out_final = d.out_final_claims;
-  out->reset(v.release());
+  out->emplace_back(v.release());
   return JA_OK;
 }
 
@@ -543,7 +737,7 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::unique_ptr<Inst>
 int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool batched, host::Blake2bTranscript& t,
                    size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges) {
   const size_t n = insts.size();
-  JA_REQUIRE(n >= 1 && n <= (size_t)kSlots, "sumcheck: between 1 and 16 instances per batch");
+  JA_REQUIRE(n >= 1, "sumcheck: empty batch");
   size_t max_rounds = 0;
   for (auto& i : insts) max_rounds = std::max(max_rounds, i->rounds);
   std::vector<FrH> coeffs(n, host::FR_ONE), claims(n);
@@ -562,7 +756,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
       DevInst* dv = dynamic_cast<DevInst*>(insts[k].get());
       const bool is_legacy = dv && !dv->fusable;
       if (is_legacy && legacy_in_flight) return fail(JA_ERR_UNSUPPORTED, "sumcheck: at most one non-fused instance per batch");
-      if ((st = insts[k]->launch(c, round - (max_rounds - insts[k]->rounds), (int)k))) return st;
+      if ((st = insts[k]->launch(c, round - (max_rounds - insts[k]->rounds)))) return st;
       legacy_in_flight = legacy_in_flight || is_legacy;
     }
     if (g_trace.on && getenv("JA_SC_TRACE")[0] == '2') {
@@ -627,9 +821,12 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
             size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges) {
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  std::vector<std::unique_ptr<Inst>> insts(n);
+  std::vector<std::unique_ptr<Inst>> insts;
   int32_t st = JA_OK;
-  for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts[k]);
+  for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts);
+  int next_slot = 0;
+  for (auto& i : insts) if (i->needs_slot()) i->slot_id = next_slot++;
+  if (!st && next_slot > kSlots) st = fail(JA_ERR_UNSUPPORTED, "sumcheck: more than " + std::to_string(kSlots) + " kernel-backed instances / groups in one batch");
   host::Blake2bTranscript t(transcript_state, *n_rounds_io);
   if (!st) st = prove_loop(c, insts, batched, t, max_coeffs, out_coeffs, out_ncoeffs, out_challenges);
   if (st) cudaStreamSynchronize(c->stream);      // nothing of this call may still be in flight when the handles are released

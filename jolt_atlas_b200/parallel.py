@@ -1,0 +1,204 @@
+"""Multi-GPU layer: one process per GPU, `torch.distributed` (NCCL on GPUs, gloo on CPU) as plumbing.
+
+The reference is single-process rayon (no distributed code to mirror); what shards is dictated by the algorithms:
+  * MSM (joltworks/src/msm/mod.rs:27-181, hyperkzg commit/open): split the (scalar, base) pairs by INDEX RANGE, every GPU
+    keeps the SRS resident; one all-gather of a partial POINT per GPU and MSM, then world-1 additions.
+  * sumcheck fold / round evaluation with LowToHigh binding (dense_mlpoly.rs:219-239): contiguous hypercube slices; binds
+    are local, a round exchanges <= 17 partial field sums per GPU.
+The exchange is tiny (<= 544 B per GPU and step): it is latency, not bandwidth, so nothing is fused into kernels.
+Independent proofs need no exchange at all — that is what `bench.py --gpus N` measures (weak scaling).
+
+Host-side combine goes through the C ABI's GPU-free functions (ja_g1_sum_affine, ja_fr_sum, ja_transcript_*), so the
+world_size-2 gloo tests run this logic on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Which part of an index space / hypercube this rank owns."""
+    rank: int
+    world: int
+
+    def index_range(self, n: int) -> tuple[int, int]:
+        """Balanced contiguous range of [0, n) — the MSM split (same rule as the library's ja_set_msm_shard)."""
+        return n * self.rank // self.world, n * (self.rank + 1) // self.world
+
+    def slice_range(self, n: int) -> tuple[int, int]:
+        """Contiguous hypercube slice of a length-n MLE for LowToHigh binding: n / world coefficients (pairs 2i, 2i+1 stay
+        local for log2(n / world) rounds).  n and world must be powers of two with n >= 2 * world."""
+        assert n & (n - 1) == 0 and self.world & (self.world - 1) == 0 and n >= 2 * self.world
+        per = n // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def local_rounds(self, n: int) -> int:
+        """Rounds a length-n instance can run before its slices shrink to one element per rank."""
+        return (n // self.world).bit_length() - 1
+
+
+class Comm:
+    """all_gather of small numpy arrays over torch.distributed (backend nccl -> staged through a CUDA tensor)."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device
+        self.plan = ShardPlan(self.rank, self.world)
+
+    def all_gather(self, a: np.ndarray) -> np.ndarray:
+        """(world,) + a.shape, identical on every rank, rank-major."""
+        import torch
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in out])
+
+
+class LocalComm:
+    """world == 1 stand-in (and the shape tests use it to run the sharded code path in one process)."""
+    rank, world = 0, 1
+    plan = ShardPlan(0, 1)
+
+    def all_gather(self, a: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(a)[None]
+
+
+# ---- host-side combine (GPU-free C ABI) -----------------------------------------------------------------------------
+def g1_sum_affine(xy: np.ndarray, is_inf: np.ndarray):
+    """Sum of affine points ((n, 8) Montgomery limbs + (n,) infinity flags) -> (xy (8,), is_infinity)."""
+    lib = _lib.load()
+    xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 8)
+    inf = np.ascontiguousarray(is_inf, dtype=np.int32).reshape(-1)
+    out = np.zeros(8, dtype=np.uint64)
+    oinf = C.c_int32()
+    check(lib.ja_g1_sum_affine(xy.ctypes.data_as(_lib.u64p), inf.ctypes.data_as(_lib.i32p), xy.shape[0],
+                               out.ctypes.data_as(_lib.u64p), C.byref(oinf)))
+    return out, bool(oinf.value)
+
+
+def fr_sum(parts: np.ndarray) -> np.ndarray:
+    """(n_parts, n_vals, 4) partial field sums -> (n_vals, 4)."""
+    lib = _lib.load()
+    parts = np.ascontiguousarray(parts, dtype=np.uint64)
+    n_parts, n_vals = parts.shape[0], parts.shape[1]
+    out = np.zeros((n_vals, 4), dtype=np.uint64)
+    check(lib.ja_fr_sum(parts.ctypes.data_as(_lib.u64p), n_parts, n_vals, out.ctypes.data_as(_lib.u64p)))
+    return out
+
+
+def combine_points(comm, xy: np.ndarray, inf: np.ndarray):
+    """All-gather this rank's partial points ((k, 8), (k,)) and add them point-wise -> ((k, 8), (k,) bool)."""
+    xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 8)
+    inf = np.ascontiguousarray(inf, dtype=np.int32).reshape(-1)
+    packed = np.concatenate([xy, inf.astype(np.uint64)[:, None]], axis=1)          # one exchange for points + flags
+    allp = comm.all_gather(packed)                                                 # (world, k, 9)
+    out = np.zeros_like(xy)
+    oinf = np.zeros(xy.shape[0], dtype=bool)
+    for j in range(xy.shape[0]):
+        out[j], oinf[j] = g1_sum_affine(allp[:, j, :8], allp[:, j, 8].astype(np.int32))
+    return out, oinf
+
+
+class Transcript:
+    """Blake2bTranscript state driven through the library (blake2b.rs) for callers that own the transcript."""
+
+    def __init__(self, label: bytes = None, state: bytes = None, n_rounds: int = 0):
+        self._lib = _lib.load()
+        self._st = C.create_string_buffer(32)
+        self._nr = C.c_uint32(n_rounds)
+        if state is not None:
+            self._st.raw = state
+        else:
+            self._lib.ja_transcript_new(label, self._st, C.byref(self._nr))
+
+    @property
+    def state(self) -> bytes:
+        return self._st.raw
+
+    @property
+    def n_rounds(self) -> int:
+        return self._nr.value
+
+    def append_points(self, xy, inf):
+        xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 8)
+        inf = np.ascontiguousarray(inf, dtype=np.int32).reshape(-1)
+        self._lib.ja_transcript_append_points(self._st, C.byref(self._nr), xy.ctypes.data_as(_lib.u64p),
+                                              inf.ctypes.data_as(_lib.i32p), xy.shape[0])
+
+    def append_scalars(self, fr):
+        fr = np.ascontiguousarray(fr, dtype=np.uint64).reshape(-1, 4)
+        self._lib.ja_transcript_append_scalars(self._st, C.byref(self._nr), fr.ctypes.data_as(_lib.u64p), fr.shape[0])
+
+    def challenge_scalar(self) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        self._lib.ja_transcript_challenge_scalar(self._st, C.byref(self._nr), out.ctypes.data_as(_lib.u64p))
+        return out
+
+    def challenge_scalar_powers(self, n: int) -> np.ndarray:
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self._lib.ja_transcript_challenge_scalar_powers(self._st, C.byref(self._nr), n, out.ctypes.data_as(_lib.u64p))
+        return out
+
+
+# ---- sharded device operations ---------------------------------------------------------------------------------------------
+def sharded_msm_fr(ctx, srs, scalars, comm):
+    """UnivariateKZG::commit_as_univariate with the pairs split by index range over the ranks.  `scalars` is the FULL
+    device polynomial on every rank (replicated streaming data, sharded group arithmetic)."""
+    from . import api as A
+    lo, hi = comm.plan.index_range(len(scalars))
+    out = np.zeros((1, 8), dtype=np.uint64)
+    inf = np.zeros(1, dtype=np.int32)
+    check(ctx._lib.ja_msm_fr_range(ctx._h, srs._h, scalars._h, lo, hi, A._u64p(out), inf.ctypes.data_as(_lib.i32p)))
+    xy, oinf = combine_points(comm, out, inf)
+    return xy[0], bool(oinf[0])
+
+
+def sharded_hyperkzg_open(ctx, srs, poly, point, transcript_state, comm):
+    """HyperKZG::open (hyperkzg/mod.rs:400-447) with every MSM split by index range over the ranks: the folds, the
+    univariate evaluations and the quotient recurrence are replicated (HBM streaming, no exchange), the commitments are
+    partial points combined by two all-gathers (l-1 points, then 3).  `transcript_state` is api.Blake2bTranscriptState.
+    Every rank returns the same proof and ends with the same transcript."""
+    from . import api as A
+    check(ctx._lib.ja_set_msm_shard(ctx._h, comm.rank, comm.world))
+    try:
+        op = A.HyperKZGOpening(ctx, srs, poly, point)                                   # phase 1: folds + partial commitments
+        com, com_inf = combine_points(comm, op.com, op.com_inf)
+        t = Transcript(state=transcript_state.state, n_rounds=transcript_state.n_rounds)
+        t.append_points(com, com_inf)                                                   # mod.rs:439
+        r = t.challenge_scalar()                                                        # mod.rs:440
+        v = op.evals(r)
+        t.append_scalars(v.reshape(-1, 4))                                              # mod.rs:258
+        q = t.challenge_scalar_powers(op.ell)                                           # mod.rs:260
+        w_part, w_inf_part = op.witness(r, q)
+        w, w_inf = combine_points(comm, w_part, w_inf_part)
+        t.append_points(w, w_inf)                                                       # mod.rs:276
+        t.challenge_scalar()                                                            # mod.rs:277
+        op.free()
+    finally:
+        check(ctx._lib.ja_set_msm_shard(ctx._h, 0, 1))
+    transcript_state.state, transcript_state.n_rounds = t.state, t.n_rounds
+    return {"com": com, "com_inf": com_inf.astype(np.int32), "w": w, "w_inf": w_inf.astype(np.int32), "v": v}
+
+
+def sharded_round_eval(ctx, kernel_id, slice_polys, eq, comm, n_out, aux_u32=0):
+    """One round's reduced sums when every MLE lives as contiguous hypercube slices (this rank holds `slice_polys`,
+    `eq` is the replicated split-eq of the whole instance): local partial sums, one all-gather, field addition."""
+    from . import api as A
+    n_local = len(slice_polys[0])
+    g_offset = comm.rank * (n_local // 2)
+    arr = (C.c_void_p * len(slice_polys))(*[p._h for p in slice_polys])
+    part = np.zeros((n_out, 4), dtype=np.uint64)
+    check(ctx._lib.ja_round_eval_slice(ctx._h, kernel_id, arr, len(slice_polys), eq._h, aux_u32, g_offset, A._u64p(part), n_out))
+    return fr_sum(comm.all_gather(part))

@@ -142,7 +142,7 @@ struct orc_inst {
 };
 static Instance* make_instance(const orc_inst& d) {
   std::vector<FrVec> ps;
-  for (size_t i = 0; i < d.n_polys; i++) ps.push_back(load_fr(d.polys + 4 * d.poly_len * i, d.poly_len));
+  if (d.polys) for (size_t i = 0; i < d.n_polys; i++) ps.push_back(load_fr(d.polys + 4 * d.poly_len * i, d.poly_len));
   const Fr claim = Fr::from_raw(d.claim);
   if (d.kind <= 6) { FrVec w = load_fr(d.eq_w, d.eq_m); return new SplitEqInstance(d.kind, w.data(), d.eq_m, std::move(ps), claim, d.aux_u32); }
   if (d.kind == 16 || d.kind == 17) return new DotInstance(std::move(ps), claim);
@@ -150,6 +150,16 @@ static Instance* make_instance(const orc_inst& d) {
     std::vector<Fr> g(d.n_polys, Fr::one());
     if (d.aux_fr) for (size_t i = 0; i < d.n_polys; i++) g[i] = Fr::from_raw(d.aux_fr + 4 * i);
     return new HammingInstance(std::move(ps), g, claim);
+  }
+  if (d.kind == 20) {   // dense opening (HighToLow): eq_w = opening point
+    FrVec w = load_fr(d.eq_w, d.eq_m);
+    return new DenseOpeningInstance(w.data(), d.eq_m, std::move(ps[0]), claim);
+  }
+  if (d.kind == 34) {   // one-hot opening: idx = T addresses, eq_w = r_cycle, aux_fr = r_address (log_k), aux_u32 = log_k
+    const size_t log_k = d.aux_u32, T = size_t(1) << d.eq_m;
+    std::vector<uint32_t> idx(d.idx, d.idx + T);
+    FrVec ra = load_fr(d.aux_fr, log_k), rc = load_fr(d.eq_w, d.eq_m);
+    return new OneHotOpeningInstance(std::move(idx), ra.data(), log_k, rc.data(), d.eq_m, claim);
   }
   if (d.kind == 32) {
     const size_t log_k = d.aux_u32, dd = d.n_polys, T = size_t(1) << d.eq_m;

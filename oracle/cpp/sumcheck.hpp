@@ -337,3 +337,88 @@ struct BooleanityInstance : Instance {
 };
 
 }  // namespace orc
+
+// ---- batched opening reduction instances (TEST INFRASTRUCTURE ONLY) ---------------------------------------------------
+namespace orc {
+
+// gruen q(0) for HighToLow binding (opening_reduction.rs:355-403, :630-673): sum over the FIRST half j < len/2 with
+// j = (x_in << out_bits) | x_out, weights E_in[x_in] * E_out[x_out]
+inline Fr open_q0(const GruenSplitEq& D, const FrVec& z) {
+  const FrVec& eo = D.E_out(); const FrVec& ei = D.E_in();
+  int out_bits = 0; while ((size_t(1) << out_bits) < eo.size()) out_bits++;
+  Fr tot = Fr::zero();
+  for (size_t xi = 0; xi < ei.size(); xi++) {
+    Fr inner = Fr::zero();
+    for (size_t xo = 0; xo < eo.size(); xo++) inner += eo[xo] * z[(xi << out_bits) | xo];
+    tot += ei[xi] * inner;
+  }
+  return tot;
+}
+
+// DensePolynomialProverOpening (opening_reduction.rs:337-424): sum_j eq(r, j) P[j], HighToLow, degree 2
+struct DenseOpeningInstance : Instance {
+  GruenSplitEq D; FrVec poly; Fr claim;
+  DenseOpeningInstance(const Fr* r, size_t m, FrVec p, Fr c) : D(r, m, HIGH_TO_LOW), poly(std::move(p)), claim(c) {}
+  size_t num_rounds() const override { return D.w.size(); }
+  size_t degree() const override { return 2; }
+  Fr input_claim() const override { return claim; }
+  UniPoly compute_message(size_t, const Fr& prev) override { return gruen_poly_deg_2(D, open_q0(D, poly), prev); }
+  void ingest_challenge(const Fr& r, size_t) override { D.bind(r); bind_poly(poly, r, HIGH_TO_LOW); }
+  std::vector<Fr> final_claims() const override { return {poly[0]}; }
+};
+
+// OneHotPolynomialProverOpening (opening_reduction.rs:503-723): log K address rounds (B = eq(r_address, .) bound
+// HighToLow, expanding table F HighToLow, G as in compute_ra_evals over D.merge()), then log T cycle rounds over
+// H[j] = F[idx[j]] scaled by eq(r_address, r'_address).
+struct OneHotOpeningInstance : Instance {
+  size_t log_k, log_t; Fr claim;
+  FrVec B, F, G, H;
+  std::vector<uint32_t> idx;
+  GruenSplitEq D;
+  OneHotOpeningInstance(std::vector<uint32_t> idx_, const Fr* r_address, size_t log_k_, const Fr* r_cycle, size_t log_t_, Fr c)
+      : log_k(log_k_), log_t(log_t_), claim(c), idx(std::move(idx_)), D(r_cycle, log_t_, HIGH_TO_LOW) {
+    B = eq_evals(r_address, log_k);
+    F = FrVec{Fr::one()};
+    const FrVec dm = D.merge();                                   // :541 D_coeffs_for_G
+    G.assign(size_t(1) << log_k, Fr::zero());
+    for (size_t j = 0; j < idx.size(); j++) if (idx[j] != 0xffffffffu) G[idx[j]] += dm[j];
+  }
+  size_t num_rounds() const override { return log_k + log_t; }
+  size_t degree() const override { return 2; }
+  Fr input_claim() const override { return claim; }
+  UniPoly compute_message(size_t round, const Fr& prev) override {
+    if (round < log_k) {                                          // :579-629
+      const size_t nu = log_k - round, half = B.size() / 2;
+      Fr e0 = Fr::zero(), e2 = Fr::zero();
+      for (size_t kp = 0; kp < half; kp++) {
+        const Fr b0 = B[kp], b1 = B[kp + half];
+        const Fr b2 = b1 + (b1 - b0);                             // sumcheck_evals_array::<2>: evals at 0 and 2
+        Fr i0 = Fr::zero(), i2 = Fr::zero();
+        for (size_t k = kp; k < G.size(); k += half) {
+          const size_t k_m = (k >> (nu - 1)) & 1;
+          const Fr GF = G[k] * F[k >> nu];
+          if (k_m == 0) { i0 += GF; i2 -= GF; } else { i2 += GF + GF; }
+        }
+        e0 += b0 * i0; e2 += b2 * i2;
+      }
+      return UniPoly::from_evals_and_hint(prev, {e0, e2});
+    }
+    const Fr ea = B[0];                                           // B.final_claim()
+    return gruen_poly_deg_2(D, open_q0(D, H), prev * ea.inv()).scaled(ea);   // :667-672
+  }
+  void ingest_challenge(const Fr& r, size_t round) override {   // :677-718
+    if (round < log_k) {
+      bind_poly(B, r, HIGH_TO_LOW);
+      FrVec nf(F.size() * 2);                                     // ExpandingTable::update HighToLow (expanding_table.rs:76-86)
+      for (size_t i = 0; i < F.size(); i++) { const Fr e1 = r * F[i]; nf[2 * i] = F[i] - e1; nf[2 * i + 1] = e1; }
+      F.swap(nf);
+      if (round == log_k - 1) { H = ra_materialise(idx, F); G.clear(); }
+    } else {
+      D.bind(r);
+      bind_poly(H, r, HIGH_TO_LOW);
+    }
+  }
+  std::vector<Fr> final_claims() const override { return {H[0]}; }
+};
+
+}  // namespace orc

@@ -220,8 +220,8 @@ def batched_sumcheck_prove(instances, t: TranscriptState):
     arr = (_OrcInst * n)()
     keep, finals, max_rounds = [], [], 0
     for i, d in enumerate(instances):
-        polys = np.ascontiguousarray(d["polys"], dtype=np.uint64)
         kind = int(d["kind"])
+        polys = np.ascontiguousarray(d["polys"] if kind != 34 else np.zeros((1, 1, 4)), dtype=np.uint64)
         arr[i].kind = kind
         arr[i].aux_u32 = int(d.get("aux_u32", 0))
         arr[i].n_polys, arr[i].poly_len = polys.shape[0], polys.shape[1]
@@ -244,8 +244,13 @@ def batched_sumcheck_prove(instances, t: TranscriptState):
         fc = np.zeros((polys.shape[0], 4), dtype=np.uint64)
         finals.append(fc)
         arr[i].final_claims = fc.ctypes.data
-        if kind == 32:
+        if kind == 34:
+            arr[i].polys = None
+            arr[i].n_polys = 1
+        if kind in (32, 34):
             rounds = int(d["aux_u32"]) + arr[i].eq_m
+        elif kind == 20:
+            rounds = arr[i].eq_m
         elif kind <= 6:
             rounds = arr[i].eq_m
         else:

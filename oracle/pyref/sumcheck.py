@@ -328,3 +328,100 @@ class BooleanityInstance(Instance):
 
     def final_claims(self):
         return [h[0] for h in self.H]
+
+
+# ----------------------------------------------------------------------------- batched opening reduction
+def _open_q0(D, z):
+    """opening_reduction.rs:355-403 / :630-673: first half only, j = (x_in << out_bits) | x_out."""
+    eo, ei = D.E_out(), D.E_in()
+    out_bits = len(eo).bit_length() - 1
+    tot = 0
+    for xi, e_in in enumerate(ei):
+        inner = 0
+        for xo, e_out in enumerate(eo):
+            inner = (inner + e_out * z[(xi << out_bits) | xo]) % P
+        tot = (tot + e_in * inner) % P
+    return tot
+
+
+class DenseOpeningInstance(Instance):
+    """DensePolynomialProverOpening (opening_reduction.rs:337-424): sum_j eq(r, j) P[j], HighToLow, degree 2."""
+    degree = 2
+
+    def __init__(self, r_fr, poly, claim):
+        self.D = GruenSplitEq(r_fr, HIGH_TO_LOW)
+        self.poly = list(poly)
+        self.claim = claim % P
+
+    def num_rounds(self): return len(self.D.w)
+    def input_claim(self): return self.claim
+    def compute_message(self, rnd, prev): return self.D.gruen_poly_deg_2(_open_q0(self.D, self.poly), prev)
+
+    def ingest_challenge(self, c, rnd):
+        r = F.challenge_to_fr(c)
+        self.D.bind(r)
+        self.poly = bind(self.poly, r, HIGH_TO_LOW)
+
+    def final_claims(self): return [self.poly[0]]
+
+
+class OneHotOpeningInstance(Instance):
+    """OneHotPolynomialProverOpening (opening_reduction.rs:503-723)."""
+    degree = 2
+
+    def __init__(self, idx, r_address_fr, r_cycle_fr, claim):
+        from .poly import eq_evals
+        self.idx = list(idx)
+        self.log_k, self.log_t = len(r_address_fr), len(r_cycle_fr)
+        self.D = GruenSplitEq(r_cycle_fr, HIGH_TO_LOW)
+        self.B = eq_evals(r_address_fr)
+        self.F = [1]
+        dm = self.D.merge()
+        self.G = [0] * (1 << self.log_k)
+        for j, k in enumerate(self.idx):
+            if k is not None:
+                self.G[k] = (self.G[k] + dm[j]) % P
+        self.H = []
+        self.claim = claim % P
+
+    def num_rounds(self): return self.log_k + self.log_t
+    def input_claim(self): return self.claim
+
+    def compute_message(self, rnd, prev):
+        if rnd < self.log_k:
+            nu = self.log_k - rnd
+            half = len(self.B) // 2
+            e0 = e2 = 0
+            for kp in range(half):
+                b0, b1 = self.B[kp], self.B[kp + half]
+                b2 = (2 * b1 - b0) % P
+                i0 = i2 = 0
+                for k in range(kp, len(self.G), half):
+                    GF = self.G[k] * self.F[k >> nu] % P
+                    if ((k >> (nu - 1)) & 1) == 0:
+                        i0 = (i0 + GF) % P
+                        i2 = (i2 - GF) % P
+                    else:
+                        i2 = (i2 + 2 * GF) % P
+                e0 = (e0 + b0 * i0) % P
+                e2 = (e2 + b2 * i2) % P
+            return UniPoly.from_evals_and_hint(prev, [e0, e2])
+        ea = self.B[0]
+        return self.D.gruen_poly_deg_2(_open_q0(self.D, self.H), prev * F.fr_inv(ea) % P).scaled(ea)
+
+    def ingest_challenge(self, c, rnd):
+        r = F.challenge_to_fr(c)
+        if rnd < self.log_k:
+            self.B = bind(self.B, r, HIGH_TO_LOW)
+            nf = []
+            for v in self.F:
+                e1 = r * v % P
+                nf += [(v - e1) % P, e1]
+            self.F = nf
+            if rnd == self.log_k - 1:
+                self.H = [0 if k is None else self.F[k] for k in self.idx]
+        else:
+            self.D.bind(r)
+            self.H = bind(self.H, r, HIGH_TO_LOW)
+
+    def final_claims(self): return [self.H[0]]

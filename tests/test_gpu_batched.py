@@ -116,3 +116,48 @@ def test_addr_commit_matches_indexed_sums(ctx):
         assert not winf and np.array_equal(xy[i], w)
     addr.free()
     srs.free()
+
+
+def test_opening_reduction_batch(ctx):
+    """Batched opening reduction (opening_proof.rs:500-532): two one-hot groups (16 and 4 polynomials, different T) and
+    three dense polynomials of different sizes in ONE BatchedSumcheck, against the C++ oracle."""
+    from jolt_atlas_b200 import (Blake2bTranscriptState, EvalKernel, InstanceKind, MultilinearPolynomial, OneHotAddresses,
+                                 batched_sumcheck_prove)
+    rng = np.random.default_rng(404)
+    log_k, K = 4, 16
+    dev, cpu, keep = [], [], []
+    for d, log_t in ((16, 9), (4, 11)):
+        T = 1 << log_t
+        k = rng.integers(0, K, size=(d, T), dtype=np.uint32)
+        k[0, 5] = 0xFFFFFFFF
+        r_cycle, r_addr = _chal(rng, log_t), _chal(rng, log_k)
+        claims = _rand_fr(rng, (d,))
+        addr = OneHotAddresses(ctx, k, K)
+        keep.append(addr)
+        dev.append({"kind": InstanceKind.OPENING_ONEHOT, "addr": addr, "eq_w": r_cycle, "r_address": r_addr, "claims": claims})
+        for i in range(d):
+            cpu.append({"kind": 34, "polys": None, "idx": k[i:i + 1], "eq_w": r_cycle, "aux_fr": r_addr, "aux_u32": log_k, "claim": claims[i]})
+    for lg in (13, 6, 1):
+        host = _rand_fr(rng, (1, 1 << lg))
+        w = _chal(rng, lg)
+        claim = _rand_fr(rng, (1,))[0]
+        dev.append({"kind": EvalKernel.OPEN, "polys": [MultilinearPolynomial.from_fr(ctx, host[0])], "eq_w": w, "claim": claim})
+        cpu.append({"kind": 20, "polys": host, "eq_w": w, "claim": claim})
+    t_dev, t_cpu = Blake2bTranscriptState(b"opening"), ORC.TranscriptState(b"opening")
+    got = batched_sumcheck_prove(ctx, dev, t_dev)
+    want = ORC.batched_sumcheck_prove(cpu, t_cpu)
+    flat = []
+    for f in got["final_claims"]:
+        flat.extend([f[i:i + 1] for i in range(f.shape[0])])
+    assert len(flat) == len(want["final_claims"])
+    for a, b in zip(got["coeffs"], want["coeffs"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got["challenges"], want["challenges"])
+    for a, b in zip(flat, want["final_claims"]):
+        assert np.array_equal(a, b)
+    assert t_dev.state == t_cpu.state
+    for a in keep:
+        a.free()
+    for d in dev:
+        for p in d.get("polys", []):
+            p.free()

@@ -114,3 +114,50 @@ def test_batched_round_invariant_and_late_start():
         batched = uni.evaluate(F.challenge_to_fr(r))
     # booleanity is satisfied by one-hot data: its final batched contribution is consistent with claim 0
     assert batched == sum(cf * cl for cf, cl in zip(coeffs, claims)) % P
+
+
+def test_opening_reduction_batch_cpp_matches_python():
+    """Batched opening reduction (opening_proof.rs:500-532): dense and one-hot openings of different sizes in ONE
+    BatchedSumcheck; true claims, so the per-round invariant H(0)+H(1) == claim holds and is asserted."""
+    rng = random.Random(31)
+    log_k = 2
+    specs = [("dense", 5), ("onehot", 4), ("dense", 3), ("onehot", 2)]
+    py_insts, cpp_descs, true_claims, rounds = [], [], [], []
+    chal = lambda xs: np.array([F.challenge_limbs(x) for x in xs], dtype=np.uint64)
+    for kind, m in specs:
+        if kind == "dense":
+            rc = [rand_challenge(rng) for _ in range(m)]
+            r = [F.challenge_to_fr(x) for x in rc]
+            z = [rng.randrange(P) for _ in range(1 << m)]
+            claim = PL.evaluate(z, r)
+            py_insts.append(SC.DenseOpeningInstance(r, z, claim))
+            cpp_descs.append({"kind": 20, "polys": to_mont_array(z)[None], "eq_w": chal(rc), "claim": to_mont_array([claim])[0]})
+            rounds.append(m)
+        else:
+            rac, rcc = [rand_challenge(rng) for _ in range(log_k)], [rand_challenge(rng) for _ in range(m)]
+            ra, rc = [F.challenge_to_fr(x) for x in rac], [F.challenge_to_fr(x) for x in rcc]
+            idx = [rng.randrange(1 << log_k) for _ in range(1 << m)]
+            idx[1] = None
+            # claim = sum_{k,j} eq(ra,k) eq(rc,j) [idx[j] == k]
+            ea, ec = PL.eq_evals(ra), PL.eq_evals(rc)
+            claim = sum(ea[k] * ec[j] for j, k in enumerate(idx) if k is not None) % P
+            py_insts.append(SC.OneHotOpeningInstance(idx, ra, rc, claim))
+            cpp_descs.append({"kind": 34, "polys": None, "idx": np.array([[0xFFFFFFFF if k is None else k for k in idx]], dtype=np.uint32),
+                              "eq_w": chal(rcc), "aux_fr": chal(rac), "aux_u32": log_k, "claim": to_mont_array([claim])[0]})
+            rounds.append(log_k + m)
+        true_claims.append(claim)
+    tp = TR.Blake2bTranscript(b"opening")
+    cps, rs, coeffs, claims = SC.batched_sumcheck_prove(py_insts, tp)
+    mx = max(rounds)
+    batched = sum(cf * F.mul_pow_2(cl, mx - nr) for cf, cl, nr in zip(coeffs, true_claims, rounds)) % P
+    for cp, r in zip(cps, rs):
+        uni = cp.decompress(batched)
+        assert (uni.evaluate(0) + uni.evaluate(1)) % P == batched
+        batched = uni.evaluate(F.challenge_to_fr(r))
+    tc = ORC.TranscriptState(b"opening")
+    res = ORC.batched_sumcheck_prove(cpp_descs, tc)
+    for cp, got in zip(cps, res["coeffs"]):
+        assert from_mont_array(got) == cp.coeffs_except_linear_term
+    for inst, got in zip(py_insts, res["final_claims"]):
+        assert from_mont_array(got) == inst.final_claims()
+    assert tc.state == tp.state
