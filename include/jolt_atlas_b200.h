@@ -243,6 +243,13 @@ int32_t ja_addr_gather(ja_ctx*, const ja_addr*, const uint64_t* tables, ja_poly*
 /* compute_ra_evals (subprotocols/shout.rs:549-598): out_G[i][k] = sum_{t: k_i[t] == k} eq(r_cycle, t); out_G = d x K Fr */
 int32_t ja_addr_ra_evals(ja_ctx*, const ja_addr*, const uint64_t* r_cycle, size_t log_t, uint64_t* out_G);
 
+/* build_materialized_rlc (joltworks/src/poly/rlc_polynomial.rs:13-78): the joint polynomial sum_i gamma^i P_i of the single
+ * HyperKZG opening, built in HBM.  ja_poly_zeros(2^max_num_vars); one ja_rlc_add_onehot per address batch
+ * (joint[k_i[t] * T + t] += coeffs[i], :59-74) and one ja_rlc_add_dense per dense polynomial (joint[i] += coeff * P[i], :42-57). */
+int32_t ja_poly_zeros(ja_ctx*, size_t n, ja_poly** out);
+int32_t ja_rlc_add_onehot(ja_ctx*, ja_poly* joint, const ja_addr*, const uint64_t* coeffs /* d Fr */);
+int32_t ja_rlc_add_dense(ja_ctx*, ja_poly* joint, const ja_poly* poly, const uint64_t coeff[4]);
+
 /* ---- HyperKZG::open (joltworks/src/poly/commitment/hyperkzg/mod.rs:400-447) --------------------------------------
  * Split at the two transcript interaction points so that a Rust caller keeps its own Blake2bTranscript:
  *   begin    Phase 1: l-1 folds Pi[j] = point[l-i-1]*(prev[2j+1]-prev[2j]) + prev[2j] (:413-428) and

@@ -140,6 +140,22 @@ class MultilinearPolynomial:
         check(ctx._lib.ja_poly_random(ctx._h, n, seed, C.byref(h)))
         return MultilinearPolynomial(ctx, h)
 
+    @staticmethod
+    def zeros(ctx: Context, n: int) -> "MultilinearPolynomial":
+        h = C.c_void_p()
+        check(ctx._lib.ja_poly_zeros(ctx._h, n, C.byref(h)))
+        return MultilinearPolynomial(ctx, h)
+
+    def rlc_add_onehot(self, addr, coeffs):
+        """build_materialized_rlc, sparse half: self[k_i[t] * T + t] += coeffs[i] for the batch's d one-hot polynomials."""
+        co = np.ascontiguousarray(_fr_arg(coeffs).reshape(-1, 4))
+        assert co.shape[0] == addr.d
+        check(self.ctx._lib.ja_rlc_add_onehot(self.ctx._h, self._h, addr._h, _u64p(co)))
+
+    def rlc_add_dense(self, poly, coeff):
+        """build_materialized_rlc, dense half: self[i] += coeff * poly[i]."""
+        check(self.ctx._lib.ja_rlc_add_dense(self.ctx._h, self._h, poly._h, _u64p(np.ascontiguousarray(_fr_arg(coeff)))))
+
     def clone(self) -> "MultilinearPolynomial":
         h = C.c_void_p()
         check(self.ctx._lib.ja_poly_clone(self.ctx._h, self._h, C.byref(h)))

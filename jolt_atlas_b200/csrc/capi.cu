@@ -97,6 +97,7 @@ void ja_shutdown(ja_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  dev_cache_release(c);
   cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
   cudaFreeHost(c->h_pinned);
   cudaFreeHost(c->h_mapped);

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/jolt_atlas_b200.h"
@@ -54,6 +55,12 @@ struct ja_ctx {
   uint32_t msm_shard_index = 0, msm_shard_count = 1;
   bool slice_on = false;           // ja_round_eval_slice in progress: eq tables are indexed with g + slice_g_offset
   size_t slice_g_offset = 0;
+  // Size-class cache of device buffers (dev_alloc / dev_free below).  Every buffer of a context is used on its one
+  // stream, so a freed block can be handed out again immediately (stream order serialises the users).  A proof pass
+  // allocates and frees thousands of polynomial buffers; in steady state none of that reaches the driver allocator,
+  // whose pool growth showed up as sporadic 100-500 ms stalls (profiles/r1_pass_time_distribution.txt).
+  std::unordered_map<void*, size_t> alloc_class;
+  std::unordered_map<size_t, std::vector<void*>> free_blocks;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-kernel-class CUDA-event profile (ja_profile_begin / ja_profile_end; bench.py's roofline leg)
@@ -75,7 +82,7 @@ void ja_prof_post(ja_ctx* c);
 static constexpr int kMaxGrid = kSMs * 8;
 static constexpr int kMaxOut = 32;
 static constexpr size_t kPinnedBytes = 1 << 16;
-static constexpr int kSlots = 48;
+static constexpr int kSlots = 128;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
 
 struct ja_poly {
@@ -144,9 +151,42 @@ static inline unsigned grid_for(size_t work) {
   return (unsigned)b;
 }
 
+static inline size_t dev_size_class(size_t bytes) {
+  size_t s = 256;
+  while (s < bytes) s <<= 1;
+  if (s > (size_t(1) << 24)) {                 // above 16 MiB: 1/8-octave steps instead of powers of two (HBM is not free)
+    const size_t step = s >> 4;
+    s = (bytes + step - 1) / step * step;
+  }
+  return s;
+}
+static inline void dev_cache_release(ja_ctx* c) {
+  for (auto& kv : c->free_blocks)
+    for (void* p : kv.second) { c->alloc_class.erase(p); cudaFree(p); }
+  c->free_blocks.clear();
+}
 static inline int32_t dev_alloc(ja_ctx* c, size_t bytes, void** out) {
-  JA_CUDA(cudaMallocAsync(out, bytes ? bytes : 32, c->stream));
+  const size_t cls = dev_size_class(bytes ? bytes : 32);
+  auto it = c->free_blocks.find(cls);
+  if (it != c->free_blocks.end() && !it->second.empty()) {
+    *out = it->second.back();
+    it->second.pop_back();
+    return JA_OK;
+  }
+  cudaError_t e = cudaMalloc(out, cls);
+  if (e != cudaSuccess) {                      // out of memory: give the cached blocks back and retry once
+    cudaGetLastError();
+    cudaStreamSynchronize(c->stream);
+    dev_cache_release(c);
+    e = cudaMalloc(out, cls);
+  }
+  if (e != cudaSuccess) return fail(JA_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(cls) + "): " + cudaGetErrorString(e));
+  c->alloc_class[*out] = cls;
   return JA_OK;
 }
-static inline void dev_free(ja_ctx* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
-
+static inline void dev_free(ja_ctx* c, void* p) {
+  if (!p) return;
+  auto it = c->alloc_class.find(p);
+  if (it == c->alloc_class.end()) { cudaFreeAsync(p, c->stream); return; }
+  c->free_blocks[it->second].push_back(p);
+}

@@ -100,6 +100,38 @@ k_ra_evals_final(const Fr* __restrict__ partial, uint32_t tiles, uint32_t d, uin
   fp_store(out + (size_t)i * K + k_base + bin, tot);
 }
 
+// build_materialized_rlc, sparse half (poly/rlc_polynomial.rs:59-74): joint[k_i[t] * T + t] += coeff_i for the d one-hot
+// polynomials of an address batch.  Thread t owns column t (all its targets are congruent to t mod T), so the d updates
+// of a column are sequential in one thread and no atomics are needed; different batches are separate launches.
+static __global__ void __launch_bounds__(kBlock)
+k_rlc_add_onehot(const uint32_t* __restrict__ k_all, size_t T, uint32_t d, const Fr* __restrict__ coeffs, Fr* __restrict__ joint) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += stride) {
+    for (uint32_t i = 0; i < d; i++) {
+      const uint32_t kk = __ldg(k_all + (size_t)i * T + t);
+      if (kk == 0xffffffffu) continue;
+      Fr* dst = joint + (size_t)kk * T + t;
+      Fr cur;                                  // plain loads: the same thread may have just written this element
+      const uint4* q = reinterpret_cast<const uint4*>(dst);
+      const uint4 lo = q[0], hi = q[1];
+      cur.l[0] = lo.x; cur.l[1] = lo.y; cur.l[2] = lo.z; cur.l[3] = lo.w; cur.l[4] = hi.x; cur.l[5] = hi.y; cur.l[6] = hi.z; cur.l[7] = hi.w;
+      fp_store(dst, fp_add<FrParams>(cur, fp_load(coeffs + i)));
+    }
+  }
+}
+// dense half (:42-57): joint[i] += coeff * poly[i] for i < len
+static __global__ void __launch_bounds__(kBlock)
+k_rlc_add_dense(const Fr* __restrict__ poly, size_t len, Fr coeff, Fr* __restrict__ joint) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    Fr cur;
+    const uint4* q = reinterpret_cast<const uint4*>(joint + i);
+    const uint4 lo = q[0], hi = q[1];
+    cur.l[0] = lo.x; cur.l[1] = lo.y; cur.l[2] = lo.z; cur.l[3] = lo.w; cur.l[4] = hi.x; cur.l[5] = hi.y; cur.l[6] = hi.z; cur.l[7] = hi.w;
+    fp_store(joint + i, fp_add<FrParams>(cur, fp_mul<FrParams>(coeff, fp_load(poly + i))));
+  }
+}
+
 }  // namespace ja
 
 int32_t eq_evals_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr* out);   // capi.cu
@@ -225,6 +257,42 @@ int32_t ja_addr_ra_evals(ja_ctx* c, const ja_addr* a, const uint64_t* r_cycle, s
   JA_CUDA(cudaStreamSynchronize(c->stream));
   memcpy(out_G, c->h_pinned, n_out * sizeof(Fr));
   dev_free(c, ws);
+  return JA_OK;
+}
+
+int32_t ja_poly_zeros(ja_ctx* c, size_t n, ja_poly** out) {
+  int32_t st = ja_poly_alloc(c, n, out);
+  if (st) return st;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaMemsetAsync((*out)->buf[0], 0, n * sizeof(Fr), c->stream));
+  return JA_OK;
+}
+
+int32_t ja_rlc_add_onehot(ja_ctx* c, ja_poly* joint, const ja_addr* a, const uint64_t* coeffs) {
+  JA_REQUIRE(c && joint && a && coeffs, "ja_rlc_add_onehot: null argument");
+  JA_REQUIRE(a->K * a->T <= joint->len, "ja_rlc_add_onehot: joint polynomial shorter than K * T");
+  JA_REQUIRE(a->d * sizeof(Fr) <= kPinnedBytes, "ja_rlc_add_onehot: too many coefficients");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  Fr* d_co = nullptr;
+  int32_t st = dev_alloc(c, a->d * sizeof(Fr), (void**)&d_co);
+  if (st) return st;
+  JA_CUDA(cudaMemcpyAsync(d_co, coeffs, a->d * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));   // pageable source: staged synchronously
+  unsigned gx = grid_for(a->T);
+  JA_LAUNCH(c, KC_SCATTER, k_rlc_add_onehot<<<gx, kBlock, 0, c->stream>>>(a->d_k, a->T, (uint32_t)a->d, d_co, joint->data()));
+  JA_CUDA(cudaGetLastError());
+  dev_free(c, d_co);
+  return JA_OK;
+}
+
+int32_t ja_rlc_add_dense(ja_ctx* c, ja_poly* joint, const ja_poly* poly, const uint64_t coeff[4]) {
+  JA_REQUIRE(c && joint && poly && coeff, "ja_rlc_add_dense: null argument");
+  JA_REQUIRE(poly->len <= joint->len, "ja_rlc_add_dense: joint polynomial shorter than the summand");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  Fr co; memcpy(co.l, coeff, 32);
+  JA_LAUNCH(c, KC_SCATTER, k_rlc_add_dense<<<grid_for(poly->len), kBlock, 0, c->stream>>>(poly->data(), poly->len, co, joint->data()));
+  JA_CUDA(cudaGetLastError());
   return JA_OK;
 }
 

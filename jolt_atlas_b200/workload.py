@@ -230,16 +230,38 @@ def run_device(ctx, srs, inputs, resident=None):
             # E. remainder range-check cycle rounds (identity_range_check.rs:332-358)
             _sc(ctx, A.EvalKernel.IDENT, [rem0], claim, t, eq_w=ni.eq_w)
             rem0.free()
-        if not res:
-            hot16.free()
-            if hot4 is not None:
-                hot4.free()
         out["states"].append(t.state)
-    # G. joint opening: HyperKZG::open of a 2^ell polynomial (prover.rs:164-170); the RLC polynomial is synthetic
-    rlc = resident["rlc"] if resident else A.MultilinearPolynomial.random(ctx, 1 << inputs["ell"], inputs["rlc_seed"])
-    out["open"] = A.hyperkzg_open(ctx, srs, rlc, inputs["open_point"], t)
+    # G. prove_reduced_openings (prover.rs:141-176): ONE BatchedSumcheck over every committed polynomial
+    #    (opening_proof.rs:500-532), gamma powers (:611-643), the materialised RLC (rlc_polynomial.rs:13-78) and the
+    #    single HyperKZG opening at r_sumcheck.  Every polynomial is opened at its node's (r_address, r_cycle).
+    from . import parallel as PAR
+    groups, batches = [], []
+    for (hot16, hot4), ni in zip(hots, inputs["nodes"]):
+        for h, lo, hi in ((hot16, 0, D_CLAMP), (hot4, D_CLAMP, ni.d_hot)):
+            if h is not None:
+                groups.append({"kind": A.InstanceKind.OPENING_ONEHOT, "addr": h, "eq_w": ni.eq_w, "r_address": ni.r_addr,
+                               "claims": np.broadcast_to(claim, (hi - lo, 4))})
+                batches.append(h)
+    r = A.batched_sumcheck_prove(ctx, groups, t)
+    out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])
+    claims = np.concatenate(r["final_claims"])
+    out["finals"].append(claims)
+    tr = PAR.Transcript(state=t.state, n_rounds=t.n_rounds)
+    tr.append_scalars(claims)                                            # opening_proof.rs:628
+    gammas = tr.challenge_scalar_powers(claims.shape[0])                 # :630
+    t.state, t.n_rounds = tr.state, tr.n_rounds
+    rlc = A.MultilinearPolynomial.zeros(ctx, 1 << inputs["ell"])
+    o = 0
+    for h in batches:
+        rlc.rlc_add_onehot(h, gammas[o:o + h.d])
+        o += h.d
+    out["open"] = A.hyperkzg_open(ctx, srs, rlc, r["challenges"], t)    # PCS::prove(rlc, r_sumcheck), prover.rs:164-170
+    rlc.free()
     if not resident:
-        rlc.free()
+        for pair in hots:
+            for h in pair:
+                if h is not None:
+                    h.free()
     out["states"].append(t.state)
     return out
 
@@ -255,7 +277,7 @@ def make_resident(ctx, inputs):
             d["A"] = A.MultilinearPolynomial.from_i32(ctx, ni.A)
             d["B"] = A.MultilinearPolynomial.from_i32(ctx, ni.B)
         nodes.append(d)
-    return {"nodes": nodes, "rlc": A.MultilinearPolynomial.random(ctx, 1 << inputs["ell"], inputs["rlc_seed"])}
+    return {"nodes": nodes}
 
 
 def free_resident(res):
@@ -266,7 +288,6 @@ def free_resident(res):
         for k in ("A", "B"):
             if k in d:
                 d[k].free()
-    res["rlc"].free()
 
 
 def count_units(inputs) -> dict:
@@ -277,6 +298,7 @@ def count_units(inputs) -> dict:
         adds += ni.d_hot * (1 << lt)
         rounds += (LOG_K + lt) + lt + ((LOG_K + lt) + lt if ni.d_hot > D_CLAMP else 0)     # batched RA checks + cycle rounds
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
+    rounds += inputs["ell"]                                             # the batched opening reduction
     return {"sumcheck_rounds": rounds, "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"]}
 
 
@@ -297,6 +319,8 @@ def sumcheck_list(inputs):
             out.append(("product", D_REM, T))
             out.append(("booleanity", D_REM, T))
             out.append(("split_eq", 1, T))
+    for ni in inputs["nodes"]:
+        out.append(("opening", ni.d_hot, 1 << ni.spec.log_t))      # batched opening reduction, cycle rounds
     return out
 
 
@@ -328,7 +352,8 @@ def algorithmic_fieldmuls(inputs) -> dict:
     fused = 0
     for body, npoly, n0 in sumcheck_list(inputs):
         pairs = n0 - 1                                # sum over the rounds of the pairs evaluated
-        per_pair = {"product": npoly * npoly + npoly, "booleanity": 5 * npoly, "split_eq": 2 * npoly + 2, "dot": 4}[body]
+        per_pair = {"product": npoly * npoly + npoly, "booleanity": 5 * npoly, "split_eq": 2 * npoly + 2, "dot": 4,
+                    "opening": 3 * npoly}[body]
         fused += per_pair * pairs
     return {"onehot_point_sum": 10 * adds, "msm_accumulate": 10 * 4 * n * 16, "sumcheck_fused": fused}
 

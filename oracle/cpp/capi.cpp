@@ -201,6 +201,34 @@ void orc_compute_ra_evals(const uint32_t* idx, size_t d, size_t T, size_t K, con
   for (size_t i = 0; i < d; i++) memcpy(out + 4 * K * i, G[i].data(), K * 32);
 }
 
+// build_materialized_rlc (poly/rlc_polynomial.rs:13-78), in place on `joint` (n Fr):
+//   one-hot batch: joint[idx[i][t] * T + t] += coeffs[i];   dense: joint[i] += coeff * poly[i]
+void orc_rlc_add_onehot(uint64_t* joint, const uint32_t* idx, size_t d, size_t T, const uint64_t* coeffs) {
+  Fr* J = reinterpret_cast<Fr*>(joint);
+  for (size_t i = 0; i < d; i++) {
+    const Fr c = Fr::from_raw(coeffs + 4 * i);
+    for (size_t t = 0; t < T; t++) { const uint32_t k = idx[i * T + t]; if (k != 0xffffffffu) J[(size_t)k * T + t] += c; }
+  }
+}
+void orc_rlc_add_dense(uint64_t* joint, const uint64_t* poly, size_t len, const uint64_t coeff[4]) {
+  Fr* J = reinterpret_cast<Fr*>(joint);
+  const Fr c = Fr::from_raw(coeff);
+#pragma omp parallel for if (len >= 4096)
+  for (size_t i = 0; i < len; i++) J[i] += c * Fr::from_raw(poly + 4 * i);
+}
+
+void orc_transcript_append_scalars(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n) {
+  Transcript t(state, *n_rounds);
+  t.append_scalars(load_fr(fr, n));
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+void orc_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out) {
+  Transcript t(state, *n_rounds);
+  std::vector<Fr> q = t.challenge_scalar_powers(n);
+  for (size_t i = 0; i < n; i++) store_fr(out + 4 * i, q[i]);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+
 // ---- curve / MSM ----
 void orc_srs_powers(const uint64_t tau_mont[4], size_t n, uint64_t* out_xy) {
   std::vector<G1Affine> s = srs_powers(Fr::from_raw(tau_mont), n);

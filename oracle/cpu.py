@@ -278,3 +278,33 @@ def compute_ra_evals(idx: np.ndarray, K: int, r_cycle: np.ndarray) -> np.ndarray
     out = np.zeros((d, K, 4), dtype=np.uint64)
     lib().orc_compute_ra_evals(_p(idx), C.c_size_t(d), C.c_size_t(T), C.c_size_t(K), _p(rc), C.c_size_t(rc.shape[0]), _p(out))
     return out
+
+
+def rlc_add_onehot(joint: np.ndarray, idx: np.ndarray, coeffs: np.ndarray):
+    """rlc_polynomial.rs:59-74, in place: joint[idx[i][t] * T + t] += coeffs[i]."""
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    co = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    assert joint.flags["C_CONTIGUOUS"] and joint.dtype == np.uint64
+    lib().orc_rlc_add_onehot(_p(joint), _p(idx), C.c_size_t(idx.shape[0]), C.c_size_t(idx.shape[1]), _p(co))
+
+
+def rlc_add_dense(joint: np.ndarray, poly: np.ndarray, coeff: np.ndarray):
+    poly = np.ascontiguousarray(poly, dtype=np.uint64)
+    lib().orc_rlc_add_dense(_p(joint), _p(poly), C.c_size_t(poly.shape[0]), _p(np.ascontiguousarray(coeff, dtype=np.uint64)))
+
+
+def transcript_append_scalars(t: TranscriptState, fr: np.ndarray):
+    fr = np.ascontiguousarray(fr, dtype=np.uint64).reshape(-1, 4)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    lib().orc_transcript_append_scalars(st, C.byref(nr), _p(fr), C.c_size_t(fr.shape[0]))
+    t.state, t.n_rounds = st.raw, nr.value
+
+
+def transcript_challenge_scalar_powers(t: TranscriptState, n: int) -> np.ndarray:
+    out = np.zeros((n, 4), dtype=np.uint64)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    lib().orc_transcript_challenge_scalar_powers(st, C.byref(nr), C.c_size_t(n), _p(out))
+    t.state, t.n_rounds = st.raw, nr.value
+    return out

@@ -29,14 +29,14 @@ def _ra_checks(ni, lo, hi, claim, t, out):
     return ra[0]
 
 
-def run_cpu(srs_host: np.ndarray, inputs, rlc_host: np.ndarray, node_limit: int | None = None, do_open: bool = True):
-    """srs_host: (n, 8) affine Montgomery limbs; rlc_host: (2^ell, 4) Fr of the polynomial to open.
-    node_limit bounds the number of nodes processed (bench samples)."""
+def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None = None, do_open: bool = True, iop: bool = True):
+    """srs_host: (n, 8) affine Montgomery limbs.  node_limit bounds the number of nodes processed, iop=False skips the
+    per-node stage (bench samples time the stages separately); rlc_host is unused (the joint polynomial is built here)."""
     t = ORC.TranscriptState(b"ONNXProof")
     out = {"commitments": [], "states": [], "finals": []}
     claim = inputs["claim"]
     nodes = inputs["nodes"] if node_limit is None else inputs["nodes"][:node_limit]
-    for ni in nodes:
+    for ni in (nodes if iop else []):
         spec = ni.spec
         lists = _index_lists(ni)
         for lo, hi in ((0, D_CLAMP), (D_CLAMP, ni.d_hot)):
@@ -60,7 +60,24 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host: np.ndarray, node_limit: int 
             out["finals"].append(r["final_claims"])
         out["states"].append(t.state)
     if do_open:
+        # prove_reduced_openings: batched opening reduction over every one-hot polynomial, gamma powers, RLC, HyperKZG open
         n = 1 << inputs["ell"]
-        out["open"] = ORC.hyperkzg_open_st(srs_host[:n], rlc_host, inputs["open_point"], t)
+        descs = []
+        for ni in nodes:
+            for j in range(ni.d_hot):
+                descs.append({"kind": 34, "polys": None, "idx": ni.hot_k[j:j + 1], "eq_w": ni.eq_w, "aux_fr": ni.r_addr, "aux_u32": 4,
+                              "claim": claim})
+        r = ORC.batched_sumcheck_prove(descs, t)
+        claims = np.concatenate(r["final_claims"])
+        out["finals"].append(claims)
+        ORC.transcript_append_scalars(t, claims)
+        gammas = ORC.transcript_challenge_scalar_powers(t, claims.shape[0])
+        joint = np.zeros((n, 4), dtype=np.uint64)
+        o = 0
+        for ni in nodes:
+            ORC.rlc_add_onehot(joint, ni.hot_k, gammas[o:o + ni.d_hot])
+            o += ni.d_hot
+        out["rlc"] = joint
+        out["open"] = ORC.hyperkzg_open_st(srs_host[:n], joint, r["challenges"], t)
         out["states"].append(t.state)
     return out

@@ -18,11 +18,8 @@ def test_microgpt_pipeline_bit_exact(ctx):
     n = 1 << inputs["ell"]
     srs_host = ORC.srs_powers(to_mont_array([TAU])[0], n)
     srs = SRS(ctx, srs_host)
-    rlc = MultilinearPolynomial.random(ctx, n, inputs["rlc_seed"])
-    rlc_host = rlc.to_host()
-    rlc.free()
     got = W.run_device(ctx, srs, inputs)
-    want = WC.run_cpu(srs_host, inputs, rlc_host)
+    want = WC.run_cpu(srs_host, inputs)
     assert len(got["states"]) == len(want["states"]) == len(inputs["nodes"]) + 1
     for i, ((gc, gi), (wc, wi)) in enumerate(zip(got["commitments"], want["commitments"])):
         assert np.array_equal(np.asarray(gi, dtype=bool), np.asarray(wi, dtype=bool)), i
