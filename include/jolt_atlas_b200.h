@@ -180,6 +180,13 @@ int32_t ja_batched_sumcheck_prove(ja_ctx*, const ja_sc_instance* instances, size
                                   uint32_t* n_rounds, size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs,
                                   uint64_t* out_challenges);
 
+/* NodeEvalReduction::prove -> compute_h (joltworks/src/subprotocols/evaluation_reduction.rs:91-148, :223-249): the
+ * univariate h = mle o l for the degree n-1 curve l through the n opening points (points = n x m Fr, point-major, l(i) =
+ * point i).  out_coeffs holds up to m (n-1) + 1 coefficients, trailing zeros trimmed (UniPoly::from_coeff); the caller
+ * appends h ("UncompressedUniPoly_begin" ... "_end", unipoly.rs:540-548), draws x' and opens at l(x'). */
+int32_t ja_eval_reduction_h(ja_ctx*, const ja_poly* mle, const uint64_t* points, size_t n, size_t m, uint64_t* out_coeffs,
+                            size_t* out_ncoeffs);
+
 /* Einsum operand fold / i32 tensor x eq-vector (ops/einsum/mk_kn_mn.rs:47-79):
  *   transpose==0: out[j] = sum_i from_i32(A[i*cols + j]) * eq[i]   (eq has `rows` entries, out has `cols`)
  *   transpose==1: out[i] = sum_j from_i32(A[i*cols + j]) * eq[j]   (eq has `cols` entries, out has `rows`) */

@@ -261,6 +261,16 @@ def round_eval(ctx: Context, kernel_id: int, polys, eq: GruenSplitEqPolynomial |
     return out
 
 
+def eval_reduction_h(ctx: Context, mle: MultilinearPolynomial, points) -> np.ndarray:
+    """compute_h (evaluation_reduction.rs:223-249): coefficients of h = mle o l for the curve l through `points` (n, m, 4)."""
+    pts = np.ascontiguousarray(_fr_arg(points))
+    n, m = pts.shape[0], pts.shape[1]
+    out = np.zeros((m * (n - 1) + 1, 4), dtype=np.uint64)
+    cnt = C.c_size_t()
+    check(ctx._lib.ja_eval_reduction_h(ctx._h, mle._h, _u64p(pts), n, m, _u64p(out), C.byref(cnt)))
+    return out[: cnt.value]
+
+
 def tensor_fold_i32(ctx: Context, A, eq: MultilinearPolynomial, transpose: bool) -> MultilinearPolynomial:
     A = np.ascontiguousarray(A, dtype=np.int32)
     rows, cols = A.shape

@@ -9,6 +9,7 @@
 // which need no GPU (the world_size-2 gloo tests exercise them on CPU).
 #include "common.hpp"
 #include "fq_host.hpp"
+#include "sumcheck_host.hpp"
 #include "transcript_host.hpp"
 
 extern "C" {
@@ -65,6 +66,41 @@ void ja_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds
   FrH p = host::FR_ONE;
   for (size_t i = 0; i < n; i++) { memcpy(out + 4 * i, p.l, 32); p = host::mul(p, q); }
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+
+// ---- evaluation reduction (joltworks/src/subprotocols/evaluation_reduction.rs:91-148, :223-249) --------------------------
+// h = mle o l, where l is the degree n-1 curve through the n opening points (l(i) = point i, one UniPoly::from_evals per
+// variable, :213-221).  The reference folds the table with POLYNOMIAL-valued entries, serially; h is the unique polynomial
+// of degree <= m (n-1) with h(t) = mle(l(t)), so here it is m (n-1) + 1 ordinary MLE evaluations on the device
+// (ja_poly_evaluate: eq table + dot) followed by one interpolation on the host (cached matrix).  Coefficients are trimmed
+// like UniPoly::from_coeff (the reference's Mul trims every intermediate product, unipoly.rs:463-476).
+int32_t ja_eval_reduction_h(ja_ctx* c, const ja_poly* mle, const uint64_t* points, size_t n, size_t m, uint64_t* out_coeffs,
+                            size_t* out_ncoeffs) {
+  JA_REQUIRE(c && mle && points && out_coeffs && out_ncoeffs && n >= 1, "ja_eval_reduction_h: null argument");
+  JA_REQUIRE((size_t(1) << m) == mle->len, "ja_eval_reduction_h: points must have log2(len) coordinates");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  const size_t D = m * (n - 1);
+  // l_k(t): per-variable interpolation through (j, points[j][k])
+  std::vector<host::Coeffs> var(m);
+  for (size_t k = 0; k < m; k++) {
+    std::vector<FrH> e(n);
+    for (size_t j = 0; j < n; j++) e[j] = host::from_limbs(points + 4 * (j * m + k));
+    var[k] = n == 1 ? host::Coeffs{e[0]} : host::apply_matrix(host::interp_matrix(n, false), e);
+  }
+  std::vector<FrH> evals(D + 1);
+  std::vector<uint64_t> pt(4 * (m ? m : 1));
+  for (size_t t = 0; t <= D; t++) {
+    const FrH ft = host::from_u64(t);
+    for (size_t k = 0; k < m; k++) { const FrH v = host::evaluate(var[k], ft); memcpy(pt.data() + 4 * k, v.l, 32); }
+    uint64_t out[4];
+    int32_t st = ja_poly_evaluate(c, mle, pt.data(), m, out);
+    if (st) return st;
+    evals[t] = host::from_limbs(out);
+  }
+  const host::Coeffs h = D == 0 ? host::Coeffs{evals[0]} : host::trim(host::apply_matrix(host::interp_matrix(D + 1, false), evals));
+  for (size_t i = 0; i < h.size(); i++) memcpy(out_coeffs + 4 * i, h[i].l, 32);
+  *out_ncoeffs = h.size();
+  return JA_OK;
 }
 
 // ---- device-side slice entry points --------------------------------------------------------------------------------------

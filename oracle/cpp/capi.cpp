@@ -217,6 +217,28 @@ void orc_rlc_add_dense(uint64_t* joint, const uint64_t* poly, size_t len, const 
   for (size_t i = 0; i < len; i++) J[i] += c * Fr::from_raw(poly + 4 * i);
 }
 
+// compute_h (subprotocols/evaluation_reduction.rs:223-249), restated as the reference does it: fold the coefficient
+// table variable by variable with polynomial-valued entries (Add / Sub keep lengths, Mul trims: unipoly.rs:401-476).
+int orc_eval_reduction_h(const uint64_t* mle, size_t len, const uint64_t* points, size_t n, size_t m, uint64_t* out, size_t cap) {
+  typedef std::vector<Fr> Poly;
+  auto trim = [](Poly p) { while (!p.empty() && p.back().is_zero()) p.pop_back(); if (p.empty()) p.push_back(Fr::zero()); return p; };
+  auto addp = [](const Poly& a, const Poly& b) { Poly c(std::max(a.size(), b.size()), Fr::zero()); for (size_t i = 0; i < a.size(); i++) c[i] += a[i]; for (size_t i = 0; i < b.size(); i++) c[i] += b[i]; return c; };
+  auto subp = [](const Poly& a, const Poly& b) { Poly c(std::max(a.size(), b.size()), Fr::zero()); for (size_t i = 0; i < a.size(); i++) c[i] += a[i]; for (size_t i = 0; i < b.size(); i++) c[i] -= b[i]; return c; };
+  auto mulp = [&](const Poly& a, const Poly& b) { Poly c(a.size() + b.size() - 1, Fr::zero()); for (size_t i = 0; i < a.size(); i++) for (size_t j = 0; j < b.size(); j++) c[i + j] += a[i] * b[j]; return trim(c); };
+  std::vector<Poly> tab(len);
+  for (size_t i = 0; i < len; i++) tab[i] = trim(Poly{Fr::from_raw(mle + 4 * i)});
+  for (size_t i = 0; i < m; i++) {
+    const size_t half = size_t(1) << (m - i - 1);
+    std::vector<Fr> e(n);
+    for (size_t j = 0; j < n; j++) e[j] = Fr::from_raw(points + 4 * (j * m + i));
+    const Poly var = UniPoly::from_evals(e).coeffs;
+    for (size_t j = 0; j < half; j++) tab[j] = addp(tab[j], mulp(var, subp(tab[j + half], tab[j])));
+  }
+  if (tab[0].size() > cap) return -1;
+  for (size_t i = 0; i < tab[0].size(); i++) store_fr(out + 4 * i, tab[0][i]);
+  return (int)tab[0].size();
+}
+
 void orc_transcript_append_scalars(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n) {
   Transcript t(state, *n_rounds);
   t.append_scalars(load_fr(fr, n));

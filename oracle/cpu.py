@@ -308,3 +308,16 @@ def transcript_challenge_scalar_powers(t: TranscriptState, n: int) -> np.ndarray
     lib().orc_transcript_challenge_scalar_powers(st, C.byref(nr), C.c_size_t(n), _p(out))
     t.state, t.n_rounds = st.raw, nr.value
     return out
+
+
+def eval_reduction_h(mle: np.ndarray, points: np.ndarray) -> np.ndarray:
+    """compute_h (evaluation_reduction.rs:223-249) by the reference's polynomial-valued fold.  points: (n, m, 4)."""
+    mle = np.ascontiguousarray(mle, dtype=np.uint64)
+    pts = np.ascontiguousarray(points, dtype=np.uint64)
+    n, m = pts.shape[0], pts.shape[1]
+    out = np.zeros((m * max(n - 1, 1) + 2, 4), dtype=np.uint64)
+    fn = lib().orc_eval_reduction_h
+    fn.restype = C.c_int
+    k = fn(_p(mle), C.c_size_t(mle.shape[0]), _p(pts), C.c_size_t(n), C.c_size_t(m), _p(out), C.c_size_t(out.shape[0]))
+    assert k > 0
+    return out[:k]

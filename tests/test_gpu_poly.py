@@ -9,6 +9,7 @@ import random
 import numpy as np
 import pytest
 
+from oracle import cpu as ORC
 from oracle.pyref import field as F
 from oracle.pyref import poly as PL
 from tests.util import challenge_array, from_mont_array, rand_challenge, rand_fr, to_mont_array
@@ -243,3 +244,19 @@ def test_large_bind_linearity_property(ctx):
         q2.bind_parallel(challenge_array(c), 1)
     assert from_mont_array(q2.final_claim()) == from_mont_array(p.final_claim())
     p.free(); q.free(); q2.free()
+
+
+@pytest.mark.parametrize("n,m", [(2, 10), (3, 6), (1, 5), (2, 1), (5, 3)])
+def test_eval_reduction_h(ctx, n, m):
+    """NodeEvalReduction / compute_h (evaluation_reduction.rs:223-249): device evaluate-and-interpolate against the oracle's
+    polynomial-valued fold, on an i32 node output (EvalReductionWitness::from_tensor)."""
+    from jolt_atlas_b200 import MultilinearPolynomial, eval_reduction_h
+    rng = np.random.default_rng(n * 100 + m)
+    z = rng.integers(-128, 128, size=1 << m, dtype=np.int32)
+    pts = rng.integers(0, 1 << 63, size=(n, m, 4), dtype=np.uint64)
+    pts[..., 3] &= np.uint64((1 << 60) - 1)
+    p = MultilinearPolynomial.from_i32(ctx, z)
+    got = eval_reduction_h(ctx, p, pts)
+    want = ORC.eval_reduction_h(ORC.fr_from_i64(z), pts)
+    assert np.array_equal(got, want)
+    p.free()

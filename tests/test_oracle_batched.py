@@ -161,3 +161,26 @@ def test_opening_reduction_batch_cpp_matches_python():
     for inst, got in zip(py_insts, res["final_claims"]):
         assert from_mont_array(got) == inst.final_claims()
     assert tc.state == tp.state
+
+
+def _py_compute_h(mle, points):
+    """Independent Python restatement of compute_h (evaluation_reduction.rs:223-249): h(t) = MLE(l(t)) evaluated point-wise
+    and interpolated (the other route is the C++ oracle's polynomial-valued fold)."""
+    from oracle.pyref.unipoly import UniPoly
+    n, m = len(points), len(points[0])
+    var = [UniPoly.from_evals([points[j][k] for j in range(n)]) for k in range(m)]
+    D = m * (n - 1)
+    evals = [PL.evaluate(mle, [v.evaluate(t) for v in var]) for t in range(D + 1)]
+    return UniPoly.from_evals(evals) if D + 1 not in (3, 4) else UniPoly.from_coeff(UniPoly.from_evals(evals).coeffs)
+
+
+def test_eval_reduction_h_fold_equals_pointwise():
+    rng = random.Random(99)
+    for n, m in ((2, 4), (3, 3), (2, 1), (4, 2), (5, 2)):
+        mle = [rng.randrange(-128, 128) % P for _ in range(1 << m)]
+        pts = [[rng.randrange(P) for _ in range(m)] for _ in range(n)]
+        h = _py_compute_h(mle, pts)
+        got = ORC.eval_reduction_h(to_mont_array(mle), np.stack([to_mont_array(p) for p in pts]))
+        assert from_mont_array(got) == h.coeffs
+        for i, p in enumerate(pts):                                   # h(i) == claim_i (evaluation_reduction.rs:127-133)
+            assert h.evaluate(i) == PL.evaluate(mle, p)
