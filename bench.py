@@ -236,7 +236,7 @@ def run_device_arm(args):
     # independent proofs per rank (weak scaling: the path has no cross-proof exchange); see DESIGN.md §Multi-GPU
     inputs = W.build_inputs(args.config, seed=None if rank == 0 else W.CONFIGS[args.config]["seed"] + rank)
     n = 1 << inputs["ell"]
-    srs = SRS.generate(ctx, g1_generator_mont(), tau_mont(), n)
+    srs = SRS.generate(ctx, g1_generator_mont(), tau_mont(), n).precompute()
     resident = W.make_resident(ctx, inputs)
     pin_inputs(inputs)
     ctx.sync()
@@ -301,6 +301,20 @@ def run_device_arm(args):
                 "wall_ms_per_step": wall_ms / args.steps,
                 "units_per_step": units,
                 "roofline": roof["dominant"], "kernel_classes": roof["classes"], "kernel_sweep": roof["sweep"]}
+        # MSM sweep (BASELINE.json config 5: Mscalar/s on random 254-bit scalars, one GPU)
+        msm = []
+        big = SRS.generate(ctx, g1_generator_mont(), tau_mont(), 1 << 22).precompute()
+        for log_n in (18, 20, 22):
+            p = MultilinearPolynomial.random(ctx, 1 << log_n, 7)
+            from jolt_atlas_b200 import msm_fr
+            msm_fr(ctx, big, p)
+            best = 1e9
+            for _ in range(3):
+                ctx.timer_begin(); msm_fr(ctx, big, p); best = min(best, ctx.timer_end())
+            msm.append({"log_n": log_n, "ms": round(best, 3), "Mscalar_per_s": round((1 << log_n) / best / 1e3, 1)})
+            p.free()
+        big.free()
+        line["msm_sweep"] = msm
         if world == 1 and not args.no_cpu:
             from oracle import cpu as ORC
             secs, sample = cpu_pass_seconds(srs.to_host(), inputs, None, 30.0)

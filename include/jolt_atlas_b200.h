@@ -202,6 +202,10 @@ int32_t ja_srs_upload(ja_ctx*, const uint64_t* g1_affine_xy, size_t n_points, ja
 /* SRS::setup's fixed-base loop on device (hyperkzg/kzg.rs:45-66): g1_powers[i] = beta^i * g1.  The caller samples
  * beta and g1 (arkworks UniformRand over ChaCha20 stays on the host, kzg.rs:34-36). */
 int32_t ja_srs_generate(ja_ctx*, const uint64_t g1_xy[8], const uint64_t beta[4], size_t n_points, ja_srs** out);
+/* Fixed-base window table for full-width MSMs against this SRS: 2^(16 w) * g1_powers[i] for w = 0..15 resident in HBM
+ * (16x the SRS: 256 MB at nanoGPT scale, 16 GiB at GPT-2 scale).  Every later MSM of Fr scalars then fills ONE bucket set
+ * (no per-window bucket reduction, no doubling tail).  Part of setup_prover; results are unchanged (same group element). */
+int32_t ja_srs_precompute(ja_ctx*, ja_srs*);
 int32_t ja_srs_to_host(ja_ctx*, const ja_srs*, size_t first, size_t count, uint64_t* out_xy);
 size_t ja_srs_len(const ja_srs*);
 void ja_srs_free(ja_ctx*, ja_srs*);
@@ -318,6 +322,10 @@ const char* ja_profile_class_name(int32_t k);
  *          2 = round eval MUL (split-eq, 2 polys), 3 = round eval DOT2, 4 = round eval ADD
  * Returns the average device time per launch in *out_ms. */
 int32_t ja_bench_kernel(ja_ctx*, int32_t which, int32_t log_n, int32_t n_polys, int32_t iters, float* out_ms);
+/* The same for ONE fused round kernel (bind previous challenge + evaluate; fused_kernels.cuh): which = 0 ADD (2 polys),
+ * 1 MUL (2), 2 IDENT (1), 3 product of 4, 4 product of 16, 5 booleanity over 16, 6 opening reduction HighToLow (1).
+ * Algorithmic bytes per launch = 48 * 2^log_n per polynomial. */
+int32_t ja_bench_fused(ja_ctx*, int32_t which, int32_t log_n, int32_t iters, float* out_ms);
 /* device-side pseudo-random canonical Fr (xorshift of the index; synthetic bench operands) */
 int32_t ja_poly_random(ja_ctx*, size_t n, uint32_t seed, ja_poly** out);
 /* register-resident Montgomery-product loop; returns achieved Fr-mul/s in *out_mul_per_s */

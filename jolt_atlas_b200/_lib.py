@@ -49,6 +49,7 @@ SIGNATURES = {
     "ja_tensor_fold_i32": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vp, C.c_int32, vpp]),
     "ja_srs_upload": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
     "ja_srs_generate": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),
+    "ja_srs_precompute": (C.c_int32, [vp, vp]),
     "ja_srs_to_host": (C.c_int32, [vp, vp, C.c_size_t, C.c_size_t, u64p]),
     "ja_srs_len": (C.c_size_t, [vp]),
     "ja_srs_free": (None, [vp, vp]),
@@ -93,6 +94,7 @@ SIGNATURES = {
     "ja_timer_begin": (C.c_int32, [vp]),
     "ja_timer_end": (C.c_int32, [vp, C.POINTER(C.c_float)]),
     "ja_bench_kernel": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    "ja_bench_fused": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "ja_poly_random": (C.c_int32, [vp, C.c_size_t, C.c_uint32, vpp]),
     "ja_calibrate_fr_mul": (C.c_int32, [vp, C.c_int32, C.POINTER(C.c_double)]),
 }

@@ -97,6 +97,12 @@ class Context:
         check(self._lib.ja_bench_kernel(self._h, which, log_n, n_polys, iters, C.byref(out)))
         return out.value
 
+    def bench_fused(self, which: int, log_n: int, iters: int = 10) -> float:
+        """Average device milliseconds per launch of one fused bind+eval round kernel (ja_bench_fused)."""
+        out = C.c_float()
+        check(self._lib.ja_bench_fused(self._h, which, log_n, iters, C.byref(out)))
+        return out.value
+
     def calibrate_fr_mul(self, iters: int = 2000) -> float:
         out = C.c_double()
         check(self._lib.ja_calibrate_fr_mul(self._h, iters, C.byref(out)))
@@ -304,6 +310,11 @@ class SRS:
         g = np.ascontiguousarray(g1_xy, dtype=np.uint64).reshape(8)
         check(ctx._lib.ja_srs_generate(ctx._h, _u64p(g), _u64p(_fr_arg(beta)), n, C.byref(h)))
         self._h = h
+        return self
+
+    def precompute(self) -> "SRS":
+        """Build the fixed-base window table (16x the SRS in HBM): later Fr MSMs use one bucket set and no doubling tail."""
+        check(self.ctx._lib.ja_srs_precompute(self.ctx._h, self._h))
         return self
 
     def to_host(self, first: int = 0, count: int | None = None) -> np.ndarray:

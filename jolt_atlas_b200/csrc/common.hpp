@@ -96,7 +96,11 @@ struct ja_poly {
 struct ja_srs {
   G1Aff* points = nullptr;   // g1_powers, affine Montgomery (kzg.rs:108-143 KZGProverKey)
   size_t n = 0;
+  // Fixed-base window table (ja_srs_precompute): table[w * n + i] = 2^(16 w) * g1_powers[i], w = 0..15 (table[0..n) is a
+  // copy of the SRS).  With it a full-width MSM needs ONE bucket set instead of one per window and no doubling tail.
+  G1Aff* table = nullptr;
 };
+constexpr uint32_t kFixedWindowBits = 16, kFixedWindows = 16;
 
 struct ja_onehot {
   uint64_t* d_indices = nullptr;        // concatenated base indices k*T + t of every list

@@ -24,6 +24,14 @@ static uint32_t pick_window(size_t n, uint32_t nbits) {
   return best_c;
 }
 
+// Jobs shorter than this keep per-window buckets: with c = 16 their 2^15 buckets would hold < ~1 entry each and the
+// accumulate pass degenerates into bucket flushes (measured: HyperKZG phase-1 batch 1.3 -> 5 ms when every folded
+// polynomial went through the table).
+static size_t table_min_n() {
+  if (const char* e = getenv("JA_MSM_TABLE_MIN_LOG")) { int v = atoi(e); if (v >= 0 && v <= 40) return size_t(1) << v; }
+  return size_t(1) << 15;
+}
+
 static uint32_t run_length() {
   if (const char* e = getenv("JA_MSM_T")) { int v = atoi(e); if (v >= 4 && v <= 4096) return (uint32_t)v; }
   return 64;
@@ -83,19 +91,24 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   for (uint32_t m = 0; m < count; m++) {
     const MsmJob& j = jobs[m];
     MsmDesc& d = descs[m];
-    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.pad = 0;
+    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.fixed_stride = 0;
     if (j.kind == MSM_INDEXED) { d.c = 1; d.nwin = 1; d.nb = 1; }
-    else {
+    else if (j.kind == MSM_FR && srs->table && j.n >= table_min_n()) {
+      // fixed-base window table: c = 16, 16 windows, ONE bucket set
+      d.c = kFixedWindowBits; d.nwin = kFixedWindows; d.nb = 1u << (kFixedWindowBits - 1);
+      d.fixed_stride = (uint32_t)srs->n;
+    } else {
       d.c = pick_window(j.n, j.nbits);
       d.nwin = (j.nbits + 1 + d.c - 1) / d.c;
       d.nb = 1u << (d.c - 1);
     }
     d.bucket_base = (uint32_t)nbt; d.win_base = (uint32_t)wins.size();
     d.entry_base = (uint32_t)total_n; d.base_offset = (uint32_t)j.base_offset;
-    for (uint32_t w = 0; w < d.nwin; w++) wins.push_back(MsmWindow{(uint32_t)(nbt + (uint64_t)w * d.nb), d.nb, d.c, m});
+    const uint32_t nsets = d.fixed_stride ? 1u : d.nwin;       // bucket sets (= window sums) of this job
+    for (uint32_t w = 0; w < nsets; w++) wins.push_back(MsmWindow{(uint32_t)(nbt + (uint64_t)w * d.nb), d.nb, d.c, m});
     max_segs = std::max(max_segs, ceil_div_u32(d.nb, kSegBuckets));
     max_nwin = std::max(max_nwin, d.nwin);
-    nbt += (uint64_t)d.nwin * d.nb;
+    nbt += (uint64_t)nsets * d.nb;
     total_n += j.n;
     e_max += (uint64_t)j.n * d.nwin;
   }
@@ -145,6 +158,7 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   MsmResult* d_res = (MsmResult*)(ws + o_res);
 
   cudaStream_t s = c->stream;
+  const G1Aff* bases = srs->table ? srs->table : srs->points;     // table[0 .. n) is the SRS itself
   // JA_MSM_PROFILE=1: per-stage CUDA-event timings on stderr (tuning aid; adds synchronisation)
   const bool prof = getenv("JA_MSM_PROFILE") != nullptr;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
@@ -169,9 +183,9 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
     int occ = 4;
     if (const char* e = getenv("JA_MSM_OCC")) occ = atoi(e);
     const unsigned g = ceil_div_u32(nruns, 128);
-    if (occ <= 4) JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<4><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail));
-    else if (occ == 5) JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<5><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail));
-    else JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<6><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, srs->points, T, d_buckets, d_head, d_tail));
+    if (occ <= 4) JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<4><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, bases, T, d_buckets, d_head, d_tail));
+    else if (occ == 5) JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<5><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, bases, T, d_buckets, d_head, d_tail));
+    else JA_LAUNCH(c, KC_MSM_ACCUMULATE, k_msm_accumulate<6><<<g, 128, 0, s>>>(d_offsets, (uint32_t)nbt, d_entries, bases, T, d_buckets, d_head, d_tail));
   }
   STAGE("accumulate");
   JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_combine<<<ceil_div_u32(nbt, 128), 128, 0, s>>>(d_offsets, (uint32_t)nbt, T, d_head, d_tail, d_buckets, d_big,
@@ -285,11 +299,26 @@ int32_t ja_srs_to_host(ja_ctx* c, const ja_srs* s, size_t first, size_t count, u
 
 size_t ja_srs_len(const ja_srs* s) { return s ? s->n : 0; }
 
+int32_t ja_srs_precompute(ja_ctx* c, ja_srs* s) {
+  JA_REQUIRE(c && s, "ja_srs_precompute: null argument");
+  if (s->table) return JA_OK;
+  JA_REQUIRE((uint64_t)s->n * kFixedWindows < (1ull << 31), "ja_srs_precompute: SRS too large for 31-bit table indices");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->n * kFixedWindows * sizeof(G1Aff));
+  if (e != cudaSuccess) { s->table = nullptr; cudaGetLastError(); return fail(JA_ERR_CUDA, std::string("ja_srs_precompute: ") + cudaGetErrorString(e)); }
+  JA_LAUNCH(c, KC_SRS, k_srs_window_table<<<ceil_div_u32(s->n, 128), 128, 0, c->stream>>>(s->points, (uint32_t)s->n, s->table));
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  return JA_OK;
+}
+
 void ja_srs_free(ja_ctx* c, ja_srs* s) {
   if (!c || !s) return;
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  cudaFree(s->table);
   cudaFree(s->points);
   delete s;
 }

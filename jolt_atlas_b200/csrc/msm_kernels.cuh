@@ -47,7 +47,8 @@ struct MsmDesc {
   uint32_t win_base;     // first global window id of this MSM
   uint32_t entry_base;   // prefix sum of n over the batch (thread -> msm lookup)
   uint32_t base_offset;  // SRS index of base 0 (ignored for MSM_INDEXED)
-  uint32_t pad;
+  uint32_t fixed_stride; // != 0: fixed-base window table in use (stride = SRS length): every window shares ONE bucket set and
+                         // digit w of scalar j selects base w * stride + j (= 2^(c w) * G_j); 0: classic per-window buckets
 };
 
 constexpr uint32_t kSignBit = 0x80000000u;
@@ -122,8 +123,8 @@ JA_DEV bool msm_digit(const MsmDesc& d, MsmDigitIter& it, uint32_t w, uint32_t& 
   bool dneg = false;
   if (raw > nb) { raw = full - raw; it.carry = 1; dneg = true; } else it.carry = 0;
   if (!raw) return false;
-  key = d.bucket_base + w * nb + (raw - 1);
-  payload = it.base | ((dneg != it.neg) ? kSignBit : 0u);
+  key = d.bucket_base + (d.fixed_stride ? 0u : w * nb) + (raw - 1);
+  payload = (it.base + w * d.fixed_stride) | ((dneg != it.neg) ? kSignBit : 0u);
   return true;
 }
 
@@ -416,7 +417,7 @@ k_msm_final(const MsmDesc* __restrict__ descs, uint32_t count, const G1X* __rest
   if (m >= count) return;
   const MsmDesc d = descs[m];
   G1X acc = g1x_inf();
-  for (uint32_t w = d.nwin; w-- > 0;) {
+  for (uint32_t w = d.fixed_stride ? 1u : d.nwin; w-- > 0;) {
     if (!g1x_is_inf(acc)) for (uint32_t k = 0; k < d.c; k++) acc = g1x_dbl(acc);
     g1x_add(acc, g1x_load(window_sums + d.win_base + w));
   }
@@ -451,6 +452,41 @@ JA_DEV Fr fr_pow_u32(const Fr& b, uint32_t e) {
     if ((e >> bit) & 1) r = fp_mul<FrParams>(r, b);
   }
   return r;
+}
+
+// Fixed-base window table: table[w * n + i] = 2^(16 w) * P_i.  One thread per point: 15 x 16 doublings in XYZZ, then the
+// 15 multiples are normalised with one shared inversion (Montgomery's trick).
+static __global__ void __launch_bounds__(128)
+k_srs_window_table(const G1Aff* __restrict__ points, uint32_t n, G1Aff* __restrict__ table) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G1Aff p = g1aff_load(points + i);
+  fp_store(&table[i].x, p.x); fp_store(&table[i].y, p.y);
+  G1X cur = g1x_from_aff(p);
+  // pass 1: walk the doubling chain, keeping the running product of the denominators ZZ * ZZZ in global scratch-free form:
+  // store the XYZZ multiples temporarily in the table slots (x <- X, y <- Y) and their denominators' prefix products in regs
+  Fq pre[15], den[15];
+  Fq run = fp_one<FqParams>();
+#pragma unroll 1
+  for (int w = 1; w < 16; w++) {
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) cur = g1x_dbl(cur);
+    // X / ZZ and Y / ZZZ need 1 / (ZZ * ZZZ): x = X * ZZZ * inv, y = Y * ZZ * inv
+    fp_store(&table[(size_t)w * n + i].x, fq_mul(cur.X, cur.ZZZ));
+    fp_store(&table[(size_t)w * n + i].y, fq_mul(cur.Y, cur.ZZ));
+    den[w - 1] = fq_mul(cur.ZZ, cur.ZZZ);
+    pre[w - 1] = run;
+    run = fq_mul(run, den[w - 1]);
+  }
+  Fq inv = fq_inv(run);
+#pragma unroll 1
+  for (int w = 15; w >= 1; w--) {
+    const Fq di = fq_mul(inv, pre[w - 1]);
+    inv = fq_mul(inv, den[w - 1]);
+    G1Aff* dst = table + (size_t)w * n + i;
+    const Fq x = fq_mul(fp_load(&dst->x), di), y = fq_mul(fp_load(&dst->y), di);
+    fp_store(&dst->x, x); fp_store(&dst->y, y);
+  }
 }
 
 static __global__ void __launch_bounds__(128)

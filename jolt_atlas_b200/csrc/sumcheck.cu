@@ -841,6 +841,77 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
 
 extern "C" {
 
+// bench hook: ONE fused round kernel (bind the previous challenge + evaluate) re-run `iters` times on resident synthetic
+// operands of 2^log_n Fr per polynomial.  which: 0 ADD (2 polys), 1 MUL (2), 2 IDENT (1), 3 product of 4, 4 product of 16,
+// 5 booleanity over 16, 6 opening reduction HighToLow (1 poly, in place).  Algorithmic bytes per launch: 48 * 2^log_n per
+// polynomial (32 n read + 16 n written).
+int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, float* out_ms) {
+  JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 3 && log_n <= 28 && which >= 0 && which <= 6, "ja_bench_fused: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  static const int kNp[7] = {2, 2, 1, 4, 16, 16, 1};
+  const int np = kNp[which];
+  const size_t n = size_t(1) << log_n, G = n / 4;
+  std::vector<ja_poly*> src(np, nullptr);
+  std::vector<Fr*> dst(np, nullptr);
+  int32_t st;
+  for (int i = 0; i < np; i++) {
+    if ((st = ja_poly_random(c, n, 31u + i, &src[i]))) return st;
+    if ((st = dev_alloc(c, (n / 2) * sizeof(Fr), (void**)&dst[i]))) return st;
+  }
+  std::vector<uint64_t> w((size_t)log_n * 4, 0);
+  for (int i = 0; i < log_n; i++) { w[4 * i + 2] = 0x9e3779b97f4a7c15ull * (i + 1); w[4 * i + 3] = 0x0123456789abcdefull + i; }
+  ja_spliteq* eq = nullptr;
+  if ((st = ja_spliteq_new(c, w.data(), (size_t)log_n - 1, which == 6 ? JA_HIGH_TO_LOW : JA_LOW_TO_HIGH, nullptr, &eq))) return st;
+  Fr* d_gam = nullptr;
+  if ((st = dev_alloc(c, 16 * sizeof(Fr), (void**)&d_gam))) return st;
+  JA_CUDA(cudaMemcpyAsync(d_gam, src[0]->data(), 16 * sizeof(Fr), cudaMemcpyDeviceToDevice, c->stream));
+  const uint64_t rr[4] = {0, 0, 0x0123456789abcdefull, 0x0fedcba987654321ull};
+  const Challenge ch = to_challenge(rr);
+  FusedPolys P;
+  for (int i = 0; i < np; i++) { P.in[i] = src[i]->data(); P.out[i] = which == 6 ? src[i]->data() : dst[i]; }
+  const int bits_in = eq->in_len - 1, bits_out = eq->out_len - 1;
+  Slot slot = arm_slot(c, 0);
+  auto launch = [&]() {
+    cudaStream_t s = c->stream;
+    if (which <= 2) {
+      size_t tiles = (G + kBlock - 1) / kBlock;
+      size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
+      const size_t tpb = (tiles + grid - 1) / grid;
+      grid = (tiles + tpb - 1) / tpb;
+      if (which == 0) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<0, true><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, tpb, d_gam, c->d_partials, c->d_counter, slot.pub));
+      else if (which == 1) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<2, true><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, tpb, d_gam, c->d_partials, c->d_counter, slot.pub));
+      else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<6, true><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, tpb, d_gam, c->d_partials, c->d_counter, slot.pub));
+    } else if (which <= 5) {
+      const int L = np;
+      const size_t gpb = (size_t)kBlock / L;
+      size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
+      ppb = (ppb + gpb - 1) / gpb * gpb;
+      const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
+      if (which == 3) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<4, false, true><<<grid, kBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_counter, slot.pub));
+      else if (which == 4) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<16, false, true><<<grid, kBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, ppb, c->d_partials, c->d_counter, slot.pub));
+      else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<16, true><<<grid, kBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, ppb, d_gam, c->d_partials, c->d_counter, slot.pub));
+    } else {
+      unsigned grid = grid_for(G);
+      if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+      JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<true><<<dim3(grid, 1), kBlock, 0, s>>>(P, ch, eq->e_out(), eq->e_in(), bits_out, G, c->d_partials, c->d_counter, slot.pub));
+    }
+  };
+  for (int i = 0; i < 3; i++) launch();
+  JA_CUDA(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < iters; i++) launch();
+  JA_CUDA(cudaEventRecord(c->ev1, c->stream));
+  JA_CUDA(cudaEventSynchronize(c->ev1));
+  JA_CUDA(cudaGetLastError());
+  float ms = 0;
+  JA_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  *out_ms = ms / iters;
+  for (int i = 0; i < np; i++) { ja_poly_free(c, src[i]); dev_free(c, dst[i]); }
+  dev_free(c, d_gam);
+  ja_spliteq_free(c, eq);
+  return JA_OK;
+}
+
 int32_t ja_batched_sumcheck_prove(ja_ctx* c, const ja_sc_instance* instances, size_t n_instances, uint8_t transcript_state[32],
                                   uint32_t* n_rounds_io, size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs,
                                   uint64_t* out_challenges) {

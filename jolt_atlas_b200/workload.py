@@ -408,4 +408,15 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx)
             ms = ctx.bench_kernel(which, log_n, 1, 10)
             gb = bytes_per_n * (1 << log_n) / ms / 1e6
             sweep.append({"kernel": name, "log_n": log_n, "ms": round(ms, 4), "GBps": round(gb, 1), "frac_hbm": round(gb / hbm, 4)})
+    # fused bind + evaluate round kernels: 48 n bytes per polynomial and launch; the mul-bound bodies also as Gmul/s
+    fused = ((0, "fused_round_add", 2, 24, 2 * 2 + 2), (1, "fused_round_mul", 2, 24, 4 + 2 * 2), (2, "fused_round_ident", 1, 24, 1 + 2),
+             (6, "fused_round_open_h2l", 1, 24, 2 + 2), (3, "fused_round_product4", 4, 22, 16 + 4 + 4), (4, "fused_round_product16", 16, 20, 256 + 16 + 16),
+             (5, "fused_round_booleanity16", 16, 20, 16 * 5 + 16 + 2))
+    for which, name, npoly, log_n, muls_per_pair in fused:
+        ms = ctx.bench_fused(which, log_n, 10)
+        n = 1 << log_n
+        gb = 48 * n * npoly / ms / 1e6
+        gm = muls_per_pair * (n // 4) / ms / 1e6
+        sweep.append({"kernel": name, "log_n": log_n, "n_polys": npoly, "ms": round(ms, 4), "GBps": round(gb, 1),
+                      "frac_hbm": round(gb / hbm, 4), "Gmul_per_s": round(gm, 2), "frac_mul": round(gm / mul_peak, 4)})
     return {"dominant": dominant, "classes": classes, "sweep": sweep, "fr_mul_peak_Gmul_s": mul_peak}

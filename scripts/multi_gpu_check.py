@@ -24,7 +24,7 @@ comm = PAR.Comm(device=torch.device("cuda", local))
 rng = np.random.default_rng(9)           # same seed on every rank: replicated inputs
 with A.Context(local) as ctx:
     n = 1 << ell
-    srs = A.SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), n)
+    srs = A.SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), n).precompute()
     poly = A.MultilinearPolynomial.random(ctx, n, 21)
     # 1. MSM split by index range
     want, winf = A.msm_fr(ctx, srs, poly)

@@ -11,7 +11,7 @@ config = sys.argv[1] if len(sys.argv) > 1 else "nanoGPT"
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 with Context(0) as ctx:
     inputs = W.build_inputs(config)
-    srs = SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), 1 << inputs["ell"])
+    srs = SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), 1 << inputs["ell"]).precompute()
     res = W.make_resident(ctx, inputs)
     ctx.sync()
     l0 = ctx.launch_count()

@@ -21,7 +21,7 @@ for n in ("ra_evals", "gather"):
 if len(sys.argv) > 2: gc.disable()
 with Context(0) as ctx:
     inputs = W.build_inputs("nanoGPT")
-    srs = SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), 1 << inputs["ell"])
+    srs = SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), 1 << inputs["ell"]).precompute()
     res = W.make_resident(ctx, inputs)
     for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 20):
         acc.clear()

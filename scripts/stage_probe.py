@@ -15,7 +15,7 @@ out = {}
 with Context(0) as ctx:
     inputs = W.build_inputs("nanoGPT")
     ell = inputs["ell"]
-    srs = SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), 1 << ell)
+    srs = SRS.generate(ctx, bench.g1_generator_mont(), bench.tau_mont(), 1 << ell).precompute()
     ni = inputs["nodes"][0]
     T = 1 << ni.spec.log_t
     hot = A.OneHotBatch(ctx, W.onehot_index_lists(ni))

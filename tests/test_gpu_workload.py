@@ -17,7 +17,7 @@ def test_microgpt_pipeline_bit_exact(ctx):
     inputs = W.build_inputs("microgpt")
     n = 1 << inputs["ell"]
     srs_host = ORC.srs_powers(to_mont_array([TAU])[0], n)
-    srs = SRS(ctx, srs_host)
+    srs = SRS(ctx, srs_host).precompute()
     got = W.run_device(ctx, srs, inputs)
     want = WC.run_cpu(srs_host, inputs)
     assert len(got["states"]) == len(want["states"]) == len(inputs["nodes"]) + 1
