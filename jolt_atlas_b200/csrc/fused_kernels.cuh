@@ -55,7 +55,7 @@ JA_DEV void load_pair_l2h(const Fr* __restrict__ in, Fr* __restrict__ out, size_
 template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 || KID == 7) ? 2 : 1; };
 
 template <int KID, bool FUSED>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, (KID == 0 || KID == 1 || KID == 6) ? 4 : 2)
 k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
           size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
   constexpr int NOUT = SOut<KID>::N;
