@@ -138,7 +138,9 @@ def cpu_pass_seconds(srs_host, inputs, rlc_host, budget_s: float):
     """Time the C++ oracle (OpenMP, all host threads) on the workload.  Full pass when it fits the budget, else
     layer 0 x (number of identical layers) + lm_head + the opening stage (reduction sumcheck, RLC, HyperKZG open),
     each timed once."""
+    from oracle import cpu as ORC
     from oracle import workload_cpu as WC
+    ORC.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1
     nodes = inputs["nodes"]
     per_layer = 10
     t0 = time.perf_counter()
@@ -178,6 +180,7 @@ def run_reference(args):
     from oracle import cpu as ORC
     from oracle import workload_cpu as WC
     from jolt_atlas_b200 import workload as W
+    ORC.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1
     inputs = W.build_inputs(args.config)
     n = 1 << inputs["ell"]
     srs_host = ORC.srs_powers(tau_mont(), n)

@@ -36,6 +36,11 @@ def num_threads() -> int:
     return lib().orc_num_threads()
 
 
+def set_threads(n: int):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs ask for every host core explicitly."""
+    lib().orc_set_threads(C.c_int(n))
+
+
 def blake2b256(data: bytes) -> bytes:
     out = C.create_string_buffer(32)
     lib().orc_blake2b256(data, C.c_size_t(len(data)), out)
