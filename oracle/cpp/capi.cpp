@@ -174,9 +174,11 @@ static Instance* make_instance(const orc_inst& d) {
 }
 int orc_batched_sumcheck_prove(const orc_inst* descs, size_t n, uint8_t state[32], uint32_t* n_rounds, size_t max_coeffs,
                                uint64_t* coeffs, uint32_t* ncoeffs, uint64_t* challenges) {
-  std::vector<std::unique_ptr<Instance>> own;
-  std::vector<Instance*> insts;
-  for (size_t i = 0; i < n; i++) { own.emplace_back(make_instance(descs[i])); if (!own.back()) return -2; insts.push_back(own.back().get()); }
+  std::vector<std::unique_ptr<Instance>> own(n);
+  std::vector<Instance*> insts(n);
+#pragma omp parallel for schedule(dynamic, 1) if (n >= 8)
+  for (size_t i = 0; i < n; i++) own[i].reset(make_instance(descs[i]));
+  for (size_t i = 0; i < n; i++) { if (!own[i]) return -2; insts[i] = own[i].get(); }
   Transcript t(state, *n_rounds);
   SumcheckProof pf = batched_sumcheck_prove(insts, t);
   for (size_t r = 0; r < pf.compressed_polys.size(); r++) {

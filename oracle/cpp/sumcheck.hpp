@@ -216,13 +216,18 @@ inline SumcheckProof batched_sumcheck_prove(std::vector<Instance*>& insts, Trans
   std::vector<Fr> coeffs = t.challenge_vector(insts.size());
   std::vector<Fr> claims;
   for (auto* i : insts) claims.push_back(i->input_claim().mul_pow_2((unsigned)(max_rounds - i->num_rounds())));
+  // The reference walks the instances sequentially and parallelises INSIDE each one (rayon).  With hundreds of small
+  // instances (the opening reduction) that leaves the cores idle, so this CPU baseline additionally spreads the
+  // instances of a round over the threads (nested regions then run serially) - it only makes the baseline faster.
+  const bool par_inst = insts.size() >= 8;
   for (size_t round = 0; round < max_rounds; round++) {
     const size_t remaining = max_rounds - round;
-    std::vector<UniPoly> unis;
+    std::vector<UniPoly> unis(insts.size());
+#pragma omp parallel for schedule(dynamic, 1) if (par_inst)
     for (size_t k = 0; k < insts.size(); k++) {
       const size_t nr = insts[k]->num_rounds();
-      if (remaining > nr) unis.push_back(UniPoly::from_coeff({insts[k]->input_claim().mul_pow_2((unsigned)(remaining - nr - 1))}));
-      else unis.push_back(insts[k]->compute_message(round - (max_rounds - nr), claims[k]));
+      if (remaining > nr) unis[k] = UniPoly::from_coeff({insts[k]->input_claim().mul_pow_2((unsigned)(remaining - nr - 1))});
+      else unis[k] = insts[k]->compute_message(round - (max_rounds - nr), claims[k]);
     }
     UniPoly batched = UniPoly::from_coeff({});
     for (size_t k = 0; k < insts.size(); k++) batched.add_assign(unis[k].scaled(coeffs[k]));
@@ -231,6 +236,7 @@ inline SumcheckProof batched_sumcheck_prove(std::vector<Instance*>& insts, Trans
     std::array<uint64_t, 4> c; t.challenge_optimized(c.data());
     const Fr r = Fr::from_raw(c.data());
     for (size_t k = 0; k < insts.size(); k++) claims[k] = unis[k].evaluate(r);
+#pragma omp parallel for schedule(dynamic, 1) if (par_inst)
     for (size_t k = 0; k < insts.size(); k++) {
       const size_t nr = insts[k]->num_rounds();
       if (remaining <= nr) insts[k]->ingest_challenge(r, round - (max_rounds - nr));
