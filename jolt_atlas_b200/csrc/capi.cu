@@ -87,6 +87,9 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   JA_CUDA(cudaHostAlloc(&c->h_mapped, kSlots * kSlotBytes, cudaHostAllocMapped));
   memset(c->h_mapped, 0, kSlots * kSlotBytes);
   JA_CUDA(cudaHostGetDevicePointer(&c->d_mapped, c->h_mapped, 0));
+  JA_CUDA(cudaHostAlloc(&c->h_rowvals, kRowSeqOffset + 64, cudaHostAllocMapped));
+  memset(c->h_rowvals, 0, kRowSeqOffset + 64);
+  JA_CUDA(cudaHostGetDevicePointer(&c->d_rowvals, c->h_rowvals, 0));
   JA_CUDA(cudaEventCreate(&c->ev0));
   JA_CUDA(cudaEventCreate(&c->ev1));
   *out = c;
@@ -101,6 +104,7 @@ void ja_shutdown(ja_ctx* c) {
   cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
   cudaFreeHost(c->h_pinned);
   cudaFreeHost(c->h_mapped);
+  cudaFreeHost(c->h_rowvals);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;

@@ -51,6 +51,9 @@ struct ja_ctx {
   void* h_mapped = nullptr;
   void* d_mapped = nullptr;
   unsigned int seq = 0;
+  // flat host-mapped value array of the batched opening reduction (kMaxRowVals Fr + a sequence word at kRowSeqOffset)
+  void* h_rowvals = nullptr;
+  void* d_rowvals = nullptr;
   // MSM index-range shard of this context (shard.cu): ja_msm_run restricts every job to its slice when count > 1
   uint32_t msm_shard_index = 0, msm_shard_count = 1;
   bool slice_on = false;           // ja_round_eval_slice in progress: eq tables are indexed with g + slice_g_offset
@@ -84,6 +87,7 @@ static constexpr int kMaxOut = 32;
 static constexpr size_t kPinnedBytes = 1 << 16;
 static constexpr int kSlots = 128;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
+static constexpr size_t kMaxRowVals = 8192, kRowSeqOffset = kMaxRowVals * 32;
 
 struct ja_poly {
   size_t len = 0;

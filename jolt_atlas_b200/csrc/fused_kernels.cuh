@@ -384,4 +384,89 @@ k_round_open(FusedPolys P, Challenge r, const Fr* __restrict__ e_out, const Fr* 
   }
 }
 
+// ---- opening reduction, every group of a batch in ONE launch -----------------------------------------------------------
+// The batched opening reduction runs hundreds of one-hot instances (opening_proof.rs:500-532): one k_round_open launch per
+// group and round would be launch-bound (74 groups x 18 rounds for a nanoGPT proof).  Here blockIdx.y walks a device
+// table of rows (one polynomial each, with its own eq tables and length); every row is the same HighToLow body as
+// k_round_open.  Row sums go to a flat host-mapped array; the last row to finish raises the flag.
+struct OpenRow {
+  Fr* z;
+  const Fr* e_out;
+  const Fr* e_in;
+  unsigned long long half;       // pairs evaluated: j < half
+  unsigned int bits_out;
+  unsigned int fused;            // bind the previous challenge first
+  unsigned int out_index;        // slot of the row's sum in the host-mapped array
+  unsigned int pad;
+};
+static __global__ void __launch_bounds__(kBlock)
+k_round_open_rows(const OpenRow* __restrict__ rows, unsigned int n_rows, Challenge r, Fr* partials /* [n_rows][gridDim.x] */,
+                  unsigned int* counters /* [n_rows] + 1 */, Fr* host_vals, volatile unsigned int* host_seq, unsigned int seq_value) {
+  const OpenRow row = rows[blockIdx.y];
+  const size_t half = (size_t)row.half;
+  unsigned int nblk = (unsigned int)((half + kBlock - 1) / kBlock);
+  if (nblk > gridDim.x) nblk = gridDim.x;
+  if (blockIdx.x >= nblk) return;
+  Fr* __restrict__ z = row.z;
+  const size_t mask_out = (size_t(1) << row.bits_out) - 1;
+  Fr acc = fp_zero<FrParams>();
+  const size_t stride = (size_t)nblk * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+    Fr h;
+    if (row.fused) {
+      const Fr a0 = fp_load(z + j), a1 = fp_load(z + j + 2 * half), b0 = fp_load(z + j + half), b1 = fp_load(z + j + 3 * half);
+      h = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+      const Fr h2 = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
+      fp_store(z + j, h);
+      fp_store(z + j + half, h2);
+    } else {
+      h = fp_load(z + j);
+    }
+    const Fr w = fp_mul<FrParams>(fp_load(row.e_in + (j >> row.bits_out)), fp_load(row.e_out + (j & mask_out)));
+    acc = fp_add<FrParams>(acc, fp_mul<FrParams>(w, h));
+  }
+  __shared__ Fr s_part[kBlock / 32];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Fr v = fr_warp_sum(acc);
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  Fr tot = fp_zero<FrParams>();
+  if (warp == 0) {
+    tot = lane < (kBlock >> 5) ? s_part[lane] : fp_zero<FrParams>();
+    tot = fr_warp_sum(tot);
+  }
+  if (nblk > 1) {
+    Fr* row_part = partials + (size_t)blockIdx.y * gridDim.x;
+    if (threadIdx.x == 0) fp_store(row_part + blockIdx.x, tot);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicInc(counters + blockIdx.y, nblk - 1) == nblk - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Fr a = fp_zero<FrParams>();
+    for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x) {
+      const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(row_part + b);
+      Fr t;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t.l[i] = q[i];
+      a = fp_add<FrParams>(a, t);
+    }
+    a = fr_warp_sum(a);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+      tot = lane < (kBlock >> 5) ? s_part[lane] : fp_zero<FrParams>();
+      tot = fr_warp_sum(tot);
+    }
+  }
+  if (threadIdx.x == 0) {
+    fp_store(host_vals + row.out_index, tot);
+    __threadfence_system();
+    if (n_rows == 1 || atomicInc(counters + n_rows, n_rows - 1) == n_rows - 1) { __threadfence_system(); *host_seq = seq_value; }
+  }
+}
+
 }  // namespace ja

@@ -502,54 +502,13 @@ struct OpenGroup {
   FrH ea = host::FR_ONE, ea_inv = host::FR_ONE;       // eq(r_address, r') and its inverse (:667-672)
   bool pending = false;
   uint64_t pend_ch[4] = {0, 0, 0, 0};
-  int slot_id = -1;
-  Slot slot;
-  size_t launched_for = ~size_t(0), pre_for = ~size_t(0), waited_for = ~size_t(0), ingested_for = ~size_t(0);
+  size_t ingested_for = ~size_t(0);
   bool finalized = false;
   FrH cs, cw, div;
   std::vector<FrH> vals;
 
-  int32_t launch(ja_ctx* c, size_t round) {
-    if (round < log_k || launched_for == round) return JA_OK;
-    launched_for = round;
-    const bool fz = pending;
-    const size_t len_in = H[0]->len, len_eval = fz ? len_in / 2 : len_in, half = len_eval / 2;
-    FusedPolys P;
-    for (size_t q = 0; q < d; q++) { P.in[q] = H[q]->data(); P.out[q] = H[q]->data(); }
-    const size_t cover = size_t(1) << ((D->out_len - 1) + (D->in_len - 1));
-    JA_REQUIRE(cover == half, "sumcheck: opening split-eq tables do not cover len/2");
-    slot = arm_slot(c, slot_id);
-    unsigned gx = grid_for(half);
-    const unsigned cap = (unsigned)std::max<size_t>(1, (size_t)kSMs * 4 / d);
-    if (gx > cap) gx = cap;
-    const Challenge ch = to_challenge(pend_ch);
-    const int bits_out = D->out_len - 1;
-    if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<true><<<dim3(gx, (unsigned)d), kBlock, 0, c->stream>>>(P, ch, D->e_out(), D->e_in(), bits_out, half, c->d_partials, c->d_counter, slot.pub));
-    else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open<false><<<dim3(gx, (unsigned)d), kBlock, 0, c->stream>>>(P, ch, D->e_out(), D->e_in(), bits_out, half, c->d_partials, c->d_counter, slot.pub));
-    JA_CUDA(cudaGetLastError());
-    if (fz) { for (ja_poly* p : H) p->len = len_eval; pending = false; }
-    return JA_OK;
-  }
-  int32_t prework(ja_ctx*, size_t round) {
-    if (round < log_k || pre_for == round) return JA_OK;
-    pre_for = round;
-    uint64_t t[4];
-    int32_t st;
-    ja_spliteq_current_scalar(D, t); cs = host::from_limbs(t);
-    if ((st = ja_spliteq_current_w(D, t))) return st;
-    cw = host::from_limbs(t);
-    div = host::inv(host::gruen_eq1(cs, cw));
-    return JA_OK;
-  }
-  int32_t wait(ja_ctx* c, size_t round) {
-    if (waited_for == round) return JA_OK;
-    waited_for = round;
-    int32_t st = wait_slot(c, slot);
-    if (st) return st;
-    vals.resize(d);
-    for (size_t i = 0; i < d; i++) vals[i] = host::from_limbs(slot.host_vals + 4 * i);
-    return JA_OK;
-  }
+  struct OpenBatch* batch = nullptr;
+  size_t row_base = 0;                                  // first row of this group in the batch's value array
   int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t round) {
     if (ingested_for == round) return JA_OK;
     ingested_for = round;
@@ -594,12 +553,126 @@ struct OpenGroup {
   }
 };
 
+// All one-hot opening groups of a batched sumcheck: ONE launch per round for every group in its cycle phase
+// (k_round_open_rows), ONE shared inversion per round (Montgomery's trick over the groups' eq(1) values).
+struct OpenBatch {
+  std::vector<OpenGroup*> groups;
+  size_t total_rows = 0;
+  OpenRow* d_rows = nullptr;
+  Fr* d_partials = nullptr;
+  unsigned int* d_counters = nullptr;
+  unsigned int gx = 1;
+  std::vector<OpenRow> rows;
+  std::vector<OpenGroup*> active;
+  size_t launched_round = ~size_t(0), pre_round = ~size_t(0), waited_round = ~size_t(0);
+  unsigned int seq = 0;
+
+  int32_t init(ja_ctx* c) {
+    total_rows = 0;
+    for (OpenGroup* g : groups) { g->row_base = total_rows; total_rows += g->d; }
+    JA_REQUIRE(total_rows <= (size_t)kMaxRowVals, "sumcheck: too many one-hot opening instances in one batch");
+    gx = (unsigned int)std::max<size_t>(1, std::min<size_t>(32, (size_t)kSMs * 8 / std::max<size_t>(1, total_rows)));
+    int32_t st;
+    if ((st = dev_alloc(c, total_rows * sizeof(OpenRow), (void**)&d_rows))) return st;
+    if ((st = dev_alloc(c, total_rows * gx * sizeof(Fr), (void**)&d_partials))) return st;
+    if ((st = dev_alloc(c, (total_rows + 1) * sizeof(unsigned int), (void**)&d_counters))) return st;
+    JA_CUDA(cudaMemsetAsync(d_counters, 0, (total_rows + 1) * sizeof(unsigned int), c->stream));
+    return JA_OK;
+  }
+  // local round of group g at batch round `round`, or -1 when it has not started / is in its address phase
+  static long cycle_round(const OpenGroup* g, size_t round, size_t max_rounds) {
+    const size_t nr = g->log_k + g->log_t;
+    if (max_rounds - round > nr) return -1;
+    const size_t local = round - (max_rounds - nr);
+    return local >= g->log_k ? (long)local : -1;
+  }
+  int32_t launch(ja_ctx* c, size_t round, size_t max_rounds) {
+    if (launched_round == round) return JA_OK;
+    launched_round = round;
+    rows.clear(); active.clear();
+    uint64_t ch_limbs[4] = {0, 0, 0, 0};
+    for (OpenGroup* g : groups) {
+      if (cycle_round(g, round, max_rounds) < 0) continue;
+      active.push_back(g);
+      const bool fz = g->pending;
+      const size_t len_in = g->H[0]->len, len_eval = fz ? len_in / 2 : len_in, half = len_eval / 2;
+      const size_t cover = size_t(1) << ((g->D->out_len - 1) + (g->D->in_len - 1));
+      JA_REQUIRE(cover == half, "sumcheck: opening split-eq tables do not cover len/2");
+      if (fz) memcpy(ch_limbs, g->pend_ch, 32);
+      for (size_t i = 0; i < g->d; i++) {
+        OpenRow r;
+        r.z = g->H[i]->data(); r.e_out = g->D->e_out(); r.e_in = g->D->e_in();
+        r.half = half; r.bits_out = (unsigned int)(g->D->out_len - 1); r.fused = fz ? 1u : 0u;
+        r.out_index = (unsigned int)(g->row_base + i); r.pad = 0;
+        rows.push_back(r);
+      }
+      if (fz) { for (ja_poly* p : g->H) p->len = len_eval; g->pending = false; }
+    }
+    if (rows.empty()) return JA_OK;
+    // the counters wrap back to zero by themselves (atomicInc), except the "rows done" word whose modulus changes with
+    // the number of active rows: it sits right after the active rows' counters, freshly zeroed territory each time
+    JA_REQUIRE(rows.size() * sizeof(OpenRow) <= kPinnedBytes, "sumcheck: opening row table too large for the staging buffer");
+    memcpy(c->h_pinned, rows.data(), rows.size() * sizeof(OpenRow));
+    JA_CUDA(cudaMemcpyAsync(d_rows, c->h_pinned, rows.size() * sizeof(OpenRow), cudaMemcpyHostToDevice, c->stream));
+    seq = ++c->seq;
+    Fr* hv = reinterpret_cast<Fr*>(c->d_rowvals);
+    volatile unsigned int* hs = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<char*>(c->d_rowvals) + kRowSeqOffset);
+    JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open_rows<<<dim3(gx, (unsigned int)rows.size()), kBlock, 0, c->stream>>>(
+                  d_rows, (unsigned int)rows.size(), to_challenge(ch_limbs), d_partials, d_counters, hv, hs, seq));
+    JA_CUDA(cudaGetLastError());
+    return JA_OK;
+  }
+  int32_t prework(ja_ctx*, size_t round) {
+    if (pre_round == round || active.empty()) return JA_OK;
+    pre_round = round;
+    // one inversion for all groups: inv(eq1_g) = inv(prod) * prod of the others
+    std::vector<FrH> eq1(active.size()), pre(active.size());
+    FrH run = host::FR_ONE;
+    for (size_t k = 0; k < active.size(); k++) {
+      OpenGroup* g = active[k];
+      uint64_t t[4];
+      ja_spliteq_current_scalar(g->D, t); g->cs = host::from_limbs(t);
+      int32_t st = ja_spliteq_current_w(g->D, t);
+      if (st) return st;
+      g->cw = host::from_limbs(t);
+      eq1[k] = host::gruen_eq1(g->cs, g->cw);
+      pre[k] = run;
+      run = host::mul(run, eq1[k]);
+    }
+    FrH inv = host::inv(run);
+    for (size_t k = active.size(); k-- > 0;) {
+      active[k]->div = host::mul(inv, pre[k]);
+      inv = host::mul(inv, eq1[k]);
+    }
+    return JA_OK;
+  }
+  int32_t wait(ja_ctx* c, size_t round) {
+    if (waited_round == round) return JA_OK;
+    waited_round = round;
+    if (rows.empty()) return JA_OK;
+    Slot s;
+    s.host_vals = reinterpret_cast<const uint64_t*>(c->h_rowvals);
+    s.host_seq = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<char*>(c->h_rowvals) + kRowSeqOffset);
+    s.pub.value = seq;
+    int32_t st = wait_slot(c, s);
+    if (st) return st;
+    for (OpenGroup* g : active) {
+      g->vals.resize(g->d);
+      for (size_t i = 0; i < g->d; i++) g->vals[i] = host::from_limbs(s.host_vals + 4 * (g->row_base + i));
+    }
+    return JA_OK;
+  }
+  void release(ja_ctx* c) {
+    dev_free(c, d_rows); dev_free(c, d_partials); dev_free(c, d_counters);
+    d_rows = nullptr; d_partials = nullptr; d_counters = nullptr;
+  }
+};
+
 struct OpenMember : Inst {
   std::shared_ptr<OpenGroup> g;
   size_t i = 0;
-  bool needs_slot() const override { return i == 0; }
-  int32_t launch(ja_ctx* c, size_t round) override { g->slot_id = g->slot_id < 0 ? slot_id : g->slot_id; return g->launch(c, round); }
-  int32_t prework(ja_ctx* c, size_t round) override { return g->prework(c, round); }
+  size_t batch_round = 0;                               // set by the driver before launch / message
+  int32_t launch(ja_ctx*, size_t) override { return JA_OK; }     // the batch launches once for every group (prove_loop)
   int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
     if (round < g->log_k) {                                         // opening_reduction.rs:579-629
       const size_t nu = g->log_k - round, half = g->B.size() / 2;
@@ -620,7 +693,7 @@ struct OpenMember : Inst {
       *uni = host::from_evals_and_hint(prev, {e0, e2});
       return JA_OK;
     }
-    int32_t st = g->wait(c, round);
+    int32_t st = g->batch->wait(c, batch_round);
     if (st) return st;
     *uni = scaled(host::gruen_poly_deg_2(g->cs, g->cw, g->vals[i], host::mul(prev, g->ea_inv), g->div), g->ea);   // :667-672
     return JA_OK;
@@ -735,7 +808,7 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::vector<std::uniq
 
 // the round loop shared by Sumcheck::prove (batched == false, one instance) and BatchedSumcheck::prove
 int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool batched, host::Blake2bTranscript& t,
-                   size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges) {
+                   size_t max_coeffs, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges, OpenBatch* ob) {
   const size_t n = insts.size();
   JA_REQUIRE(n >= 1, "sumcheck: empty batch");
   size_t max_rounds = 0;
@@ -750,6 +823,10 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     const size_t remaining = max_rounds - round;
     std::vector<Coeffs> unis(n);
     bool legacy_in_flight = false;
+    if (ob) {
+      for (size_t k = 0; k < n; k++) if (OpenMember* om = dynamic_cast<OpenMember*>(insts[k].get())) om->batch_round = round;
+      if ((st = ob->launch(c, round, max_rounds))) return st;
+    }
     for (size_t k = 0; k < n; k++) {
       if (remaining > insts[k]->rounds) continue;
       // instances on the pinned-staging path cannot overlap each other: collect before launching the next one
@@ -764,6 +841,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
       fprintf(stderr, "  round %zu launch %.1f us\n", round, std::chrono::duration<double, std::micro>(nw - g_trace.last).count());
     }
     g_trace.lap(4);
+    if (ob && (st = ob->prework(c, round))) return st;
     for (size_t k = 0; k < n; k++)
       if (remaining <= insts[k]->rounds && (st = insts[k]->prework(c, round - (max_rounds - insts[k]->rounds)))) return st;
     g_trace.lap(0);
@@ -827,10 +905,16 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
   int next_slot = 0;
   for (auto& i : insts) if (i->needs_slot()) i->slot_id = next_slot++;
   if (!st && next_slot > kSlots) st = fail(JA_ERR_UNSUPPORTED, "sumcheck: more than " + std::to_string(kSlots) + " kernel-backed instances / groups in one batch");
+  OpenBatch ob;
+  for (auto& i : insts)
+    if (OpenMember* om = dynamic_cast<OpenMember*>(i.get()))
+      if (om->i == 0) { ob.groups.push_back(om->g.get()); om->g->batch = &ob; }
+  if (!st && !ob.groups.empty()) st = ob.init(c);
   host::Blake2bTranscript t(transcript_state, *n_rounds_io);
-  if (!st) st = prove_loop(c, insts, batched, t, max_coeffs, out_coeffs, out_ncoeffs, out_challenges);
+  if (!st) st = prove_loop(c, insts, batched, t, max_coeffs, out_coeffs, out_ncoeffs, out_challenges, ob.groups.empty() ? nullptr : &ob);
   if (st) cudaStreamSynchronize(c->stream);      // nothing of this call may still be in flight when the handles are released
   for (auto& i : insts) if (i) i->release(c);
+  ob.release(c);
   if (st) return st;
   memcpy(transcript_state, t.state, 32);
   *n_rounds_io = t.n_rounds;
