@@ -118,9 +118,9 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
 
 // ---- product of d <= 16 linear factors, warp-transposed (see k_round_eval_prod_t), with the fused bind -------------
 template <int L, bool SAME, bool FUSED>
-__global__ void __launch_bounds__(kBlock)
-k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub) {
+JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+                            int bits_in, size_t G, size_t pairs_per_block, Fr* partials /* [nb][L] */, unsigned int* counter,
+                            const Publish& pub, unsigned int bx, unsigned int nb) {
   constexpr int GPB = kBlock / L;
   const int li = threadIdx.x & (L - 1);
   const int group = threadIdx.x / L;
@@ -130,7 +130,7 @@ k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
   const Fr* __restrict__ zin = P.in[pi];
   Fr* __restrict__ zout = P.out[pi];
   const size_t mask_in = (size_t(1) << bits_in) - 1;
-  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  const size_t g_begin = (size_t)bx * pairs_per_block;
   size_t g_end = g_begin + pairs_per_block;
   if (g_end > G) g_end = G;
   Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
@@ -171,21 +171,21 @@ k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
   }
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
   Fr tot = block_sum_by_lane<L>(outer);
-  if (gridDim.x == 1) {
+  if (nb == 1) {
     if (threadIdx.x < L) fp_store(pub.vals + threadIdx.x, tot);
     publish_flag(pub);
     return;
   }
-  if (threadIdx.x < L) fp_store(partials + (size_t)blockIdx.x * L + threadIdx.x, tot);
+  if (threadIdx.x < L) fp_store(partials + (size_t)bx * L + threadIdx.x, tot);
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  if (threadIdx.x == 0) s_last = atomicInc(counter, nb - 1) == nb - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   Fr acc = fp_zero<FrParams>();
-  for (unsigned b = threadIdx.x / L; b < gridDim.x; b += GPB) {
+  for (unsigned b = threadIdx.x / L; b < nb; b += GPB) {
     const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(partials + (size_t)b * L + li);
     Fr t;
 #pragma unroll
@@ -197,14 +197,21 @@ k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
   publish_flag(pub);
 }
 
+template <int L, bool SAME, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub) {
+  round_prod_body<L, SAME, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x);
+}
+
 // ---- booleanity phase 2, lane-parallel (booleanity.rs:254-301) ---------------------------------------------------------
 // [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] per pair: a group of L = next_pow2(d) lanes owns one pair, lane i
 // loads polynomial i (with the fused bind), forms its two terms (4 products) and the group adds them up with shuffles —
 // d times more threads and d times shorter dependency chains than one thread looping over the d polynomials.
 template <int L, bool FUSED>
-__global__ void __launch_bounds__(kBlock)
-k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-             size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
+JA_DEV void round_bool_body(const FusedPolys& P, int d, const Challenge& r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+                            int bits_in, size_t G, size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials,
+                            unsigned int* counter, const Publish& pub, unsigned int bx, unsigned int nb) {
   constexpr int GPB = kBlock / L;
   const int li = threadIdx.x & (L - 1);
   const int group = threadIdx.x / L;
@@ -213,7 +220,7 @@ k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
   Fr* __restrict__ zout = P.out[pad ? 0 : li];
   const Fr gm = pad ? fp_zero<FrParams>() : fp_load(gammas + li);
   const size_t mask_in = (size_t(1) << bits_in) - 1;
-  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  const size_t g_begin = (size_t)bx * pairs_per_block;
   size_t g_end = g_begin + pairs_per_block;
   if (g_end > G) g_end = G;
   Fr outer[2], inner[2];
@@ -265,7 +272,40 @@ k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
 #pragma unroll
     for (int k = 0; k < 2; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
   }
-  if (grid_sum<2>(outer, partials, counter, pub.vals)) publish_flag(pub);
+  if (grid_sum_ex<2>(outer, partials, counter, pub.vals, bx, nb)) publish_flag(pub);
+}
+
+template <int L, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+             size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
+  round_bool_body<L, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
+}
+
+// ---- RA one-hot checks: RaVirtual (product of d) and Booleanity phase 2 of the same batch in ONE launch -------------------
+// The two instances of a round are independent; launched back to back on one stream they serialise two latency-bound
+// kernels.  blockIdx.y selects the body, each with its own sub-grid, scratch and result slot.
+struct PairArgs {
+  FusedPolys P;
+  int d;
+  const Fr* e_out; const Fr* e_in;
+  int bits_in;
+  unsigned int nb;               // blocks of this body
+  unsigned long long G, ppb;
+  const Fr* gammas;
+  Fr* partials; unsigned int* counter;
+  Publish pub;
+};
+template <int L, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_prod_bool(PairArgs A, PairArgs B, Challenge r) {
+  if (blockIdx.y == 0) {
+    if (blockIdx.x < A.nb)
+      round_prod_body<L, false, FUSED>(A.P, A.d, r, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
+  } else {
+    if (blockIdx.x < B.nb)
+      round_bool_body<L, FUSED>(B.P, B.d, r, B.e_out, B.e_in, B.bits_in, (size_t)B.G, (size_t)B.ppb, B.gammas, B.partials, B.counter, B.pub, blockIdx.x, B.nb);
+  }
 }
 
 // ---- family D (plain products at X in {0,2,3}, HighToLow), fused bind in place ------------------------------------------

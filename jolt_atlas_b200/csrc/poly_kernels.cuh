@@ -53,9 +53,10 @@ JA_DEV Fr fr_warp_sum(Fr a) {
 
 // Block-wide exact field sum of NOUT values per thread, then grid-wide via per-block partials and a
 // "last block" pass.  `partials` holds gridDim.x * NOUT Fr; `counter` must be 0 on entry and is reset.
-// Returns true (block-uniform) in the one block that wrote `out`.
+// Returns true (block-uniform) in the one block that wrote `out`.  bx / nb = index of this block and number of blocks
+// taking part (a kernel that hosts several independent reductions passes its own sub-grid).
 template <int NOUT>
-JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out) {
+JA_DEV bool grid_sum_ex(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out, unsigned int bx, unsigned int nb) {
   __shared__ Fr s_part[kBlock / 32][NOUT];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -70,10 +71,10 @@ JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
     for (int k = 0; k < NOUT; k++) {
       Fr v = lane < (blockDim.x >> 5) ? s_part[lane][k] : fp_zero<FrParams>();
       v = fr_warp_sum(v);
-      if (lane == 0) fp_store(&partials[(size_t)blockIdx.x * NOUT + k], v);
+      if (lane == 0) fp_store(&partials[(size_t)bx * NOUT + k], v);
     }
   }
-  if (gridDim.x == 1) {
+  if (nb == 1) {
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int k = 0; k < NOUT; k++) out[k] = partials[k];
@@ -83,8 +84,8 @@ JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int t = atomicInc(counter, gridDim.x - 1);   // wraps back to 0 after the last block
-    s_last = (t == gridDim.x - 1);
+    unsigned int t = atomicInc(counter, nb - 1);   // wraps back to 0 after the last block
+    s_last = (t == nb - 1);
   }
   __syncthreads();
   if (!s_last) return false;
@@ -92,7 +93,7 @@ JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
 #pragma unroll
   for (int k = 0; k < NOUT; k++) {
     Fr v = fp_zero<FrParams>();
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) {
       const volatile uint32_t* p = reinterpret_cast<const volatile uint32_t*>(&partials[(size_t)b * NOUT + k]);
       Fr t;
 #pragma unroll
@@ -113,6 +114,11 @@ JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* o
     }
   }
   return true;
+}
+
+template <int NOUT>
+JA_DEV bool grid_sum(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out) {
+  return grid_sum_ex<NOUT>(acc, partials, counter, out, blockIdx.x, gridDim.x);
 }
 
 // ---- variable binding (the "fold") ------------------------------------------------------------

@@ -117,6 +117,7 @@ struct Inst {
   size_t rounds = 0;
   FrH claim = host::FR_ZERO;
   uint64_t* out_final = nullptr;
+  virtual struct DevInst* pair_candidate(size_t /*local round*/) { return nullptr; }
   int slot_id = -1;                 // host-mapped result slot (assigned by run() to the instances that publish from a kernel)
   virtual bool needs_slot() const { return false; }
   virtual ~Inst() {}
@@ -187,13 +188,22 @@ struct DevInst : Inst {
   bool uses_eq() const { return kind <= 7 || kind == JA_EVAL_OPEN; }
   bool needs_slot() const override { return fusable; }
 
-  // fused round kernel (bind pend_ch first when `pending`)
-  int32_t launch_fused(ja_ctx* c) {
+  // everything a fused round launch needs, computed before the launch (shared by the single and the paired launch)
+  struct Prep {
+    FusedPolys P;
+    bool fz = false;
+    size_t len_eval = 0, G = 0;
+    Challenge ch;
+    int bits_in = 0;
+    const Fr* e_out = nullptr;
+    const Fr* e_in = nullptr;
+  };
+  int32_t prepare(ja_ctx* c, Prep* pr) {
     const bool fz = pending;
     const size_t len_in = polys[0]->len;
     const size_t len_eval = fz ? len_in / 2 : len_in;      // length of the arrays this round evaluates
     const size_t G = len_eval / 2;
-    FusedPolys P;
+    FusedPolys& P = pr->P;
     for (size_t q = 0; q < polys.size(); q++) {
       ja_poly* p = polys[q];
       P.in[q] = p->data();
@@ -210,15 +220,58 @@ struct DevInst : Inst {
         P.out[q] = p->buf[nxt];
       }
     }
-    const Challenge ch = to_challenge(pend_ch);
-    int bits_in = 0;
-    const Fr *e_out = nullptr, *e_in = nullptr;
+    pr->ch = to_challenge(pend_ch);
     if (uses_eq()) {
       JA_REQUIRE(eq && eq->order == order, "sumcheck: split-eq binding order does not match the round body");
       const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
       JA_REQUIRE(cover == G, "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
-      bits_in = eq->in_len - 1; e_out = eq->e_out(); e_in = eq->e_in();
+      pr->bits_in = eq->in_len - 1; pr->e_out = eq->e_out(); pr->e_in = eq->e_in();
     }
+    pr->fz = fz; pr->len_eval = len_eval; pr->G = G;
+    return JA_OK;
+  }
+  void commit_round(const Prep& pr) {
+    if (pr.fz) {
+      for (ja_poly* p : polys) { if (order == JA_LOW_TO_HIGH) p->cur = 1 - p->cur; p->len = pr.len_eval; }
+      pending = false;
+    }
+  }
+  bool pairable() const {
+    return fusable && polys.size() >= 2 && polys.size() <= 16 && (kind == JA_EVAL_PROD || kind == 7);
+  }
+  // this instance's half of a paired launch (k_round_prod_bool): slot armed, buffers ready, state advanced
+  int32_t prepare_pair(ja_ctx* c, PairArgs* a, Prep* pr, int scratch_half) {
+    int32_t st = prepare(c, pr);
+    if (st) return st;
+    slot = arm_slot(c, slot_id);
+    legacy = false;
+    const int d = (int)polys.size();
+    int L = 2; while (L < d) L <<= 1;
+    const size_t gpb = (size_t)kBlock / L;
+    size_t ppb = (pr->G + (size_t)kSMs * 2 - 1) / ((size_t)kSMs * 2);
+    ppb = (ppb + gpb - 1) / gpb * gpb;
+    a->P = pr->P; a->d = d; a->e_out = pr->e_out; a->e_in = pr->e_in; a->bits_in = pr->bits_in;
+    a->nb = (unsigned int)((pr->G + ppb - 1) / ppb); a->G = pr->G; a->ppb = ppb;
+    a->gammas = d_gammas;
+    a->partials = c->d_partials + (size_t)scratch_half * (kMaxGrid * kMaxOut / 2);
+    a->counter = c->d_counter + scratch_half;
+    a->pub = slot.pub;
+    if (kind == JA_EVAL_PROD) prod_lanes = L;
+    commit_round(*pr);
+    return JA_OK;
+  }
+
+  // fused round kernel (bind pend_ch first when `pending`)
+  int32_t launch_fused(ja_ctx* c) {
+    Prep pr;
+    int32_t pst = prepare(c, &pr);
+    if (pst) return pst;
+    const bool fz = pr.fz;
+    const size_t G = pr.G;
+    const FusedPolys& P = pr.P;
+    const Challenge ch = pr.ch;
+    const int bits_in = pr.bits_in;
+    const Fr *e_out = pr.e_out, *e_in = pr.e_in;
     cudaStream_t s = c->stream;
     Fr* part = c->d_partials; unsigned int* ctr = c->d_counter;
     const Publish pub = slot.pub;
@@ -282,15 +335,15 @@ struct DevInst : Inst {
 #undef JA_S_F
     }
     JA_CUDA(cudaGetLastError());
-    if (fz) {
-      for (ja_poly* p : polys) { if (order == JA_LOW_TO_HIGH) p->cur = 1 - p->cur; p->len = len_eval; }
-      pending = false;
-    }
+    commit_round(pr);
     return JA_OK;
   }
 
+  bool paired_this_round = false;    // the driver already launched this round's kernel together with a partner
+  DevInst* pair_candidate(size_t) override { return pairable() ? this : nullptr; }
   int32_t launch(ja_ctx* c, size_t) override {
     int32_t st;
+    if (paired_this_round) { paired_this_round = false; return JA_OK; }
     legacy = !fusable;
     if (fusable) {
       slot = arm_slot(c, slot_id);
@@ -423,6 +476,7 @@ struct BooleanityInst : Inst {
   std::vector<ja_poly*> H;
 
   bool needs_slot() const override { return true; }
+  DevInst* pair_candidate(size_t round) override { return round >= log_k && p2 && p2->pairable() ? p2.get() : nullptr; }
   int32_t launch(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k); }
   int32_t prework(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->prework(c, round - log_k); }
   int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
@@ -826,6 +880,32 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     if (ob) {
       for (size_t k = 0; k < n; k++) if (OpenMember* om = dynamic_cast<OpenMember*>(insts[k].get())) om->batch_round = round;
       if ((st = ob->launch(c, round, max_rounds))) return st;
+    }
+    // RA one-hot checks: RaVirtual (product of d) + Booleanity phase 2 of the same shape go out as ONE launch
+    if (n <= 8) {
+      DevInst *pa = nullptr, *pb = nullptr;
+      for (size_t k = 0; k < n; k++) {
+        if (remaining > insts[k]->rounds) continue;
+        DevInst* cand = insts[k]->pair_candidate(round - (max_rounds - insts[k]->rounds));
+        if (!cand) continue;
+        if (cand->kind == JA_EVAL_PROD && !pa) pa = cand;
+        else if (cand->kind == 7 && !pb) pb = cand;
+      }
+      if (pa && pb && pa->polys.size() == pb->polys.size() && pa->polys[0]->len == pb->polys[0]->len && pa->pending == pb->pending &&
+          (!pa->pending || memcmp(pa->pend_ch, pb->pend_ch, 32) == 0)) {
+        PairArgs A, B;
+        DevInst::Prep ra, rb;
+        if ((st = pa->prepare_pair(c, &A, &ra, 0))) return st;
+        if ((st = pb->prepare_pair(c, &B, &rb, 1))) return st;
+        const unsigned int gx = std::max(A.nb, B.nb);
+        int L = 2; while (L < A.d) L <<= 1;
+#define JA_PAIR(LL) do { if (ra.fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, true><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); \
+                         else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, false><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); } while (0)
+        switch (L) { case 2: JA_PAIR(2); break; case 4: JA_PAIR(4); break; case 8: JA_PAIR(8); break; default: JA_PAIR(16); break; }
+#undef JA_PAIR
+        JA_CUDA(cudaGetLastError());
+        pa->paired_this_round = true; pb->paired_this_round = true;
+      }
     }
     for (size_t k = 0; k < n; k++) {
       if (remaining > insts[k]->rounds) continue;
