@@ -84,6 +84,7 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   JA_CUDA(cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int)));
   JA_CUDA(cudaMalloc(&c->d_out, sizeof(Fr) * kMaxOut));
   JA_CUDA(cudaMallocHost(&c->h_pinned, kPinnedBytes));
+  JA_CUDA(cudaMallocHost((void**)&c->h_ring, kRingBytes));
   JA_CUDA(cudaHostAlloc(&c->h_mapped, kSlots * kSlotBytes, cudaHostAllocMapped));
   memset(c->h_mapped, 0, kSlots * kSlotBytes);
   JA_CUDA(cudaHostGetDevicePointer(&c->d_mapped, c->h_mapped, 0));
@@ -103,6 +104,7 @@ void ja_shutdown(ja_ctx* c) {
   dev_cache_release(c);
   cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
   cudaFreeHost(c->h_pinned);
+  cudaFreeHost(c->h_ring);
   cudaFreeHost(c->h_mapped);
   cudaFreeHost(c->h_rowvals);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
@@ -275,11 +277,7 @@ static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& sca
   Fr* lv[2] = {nullptr, nullptr};
   int32_t st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_r);
   if (st) return st;
-  if (m) {
-    JA_REQUIRE(m * 32 <= kPinnedBytes, "eq_evals: too many variables");
-    memcpy(c->h_pinned, r, m * 32);
-    JA_CUDA(cudaMemcpyAsync(d_r, c->h_pinned, m * 32, cudaMemcpyHostToDevice, c->stream));
-  }
+  if (m && (st = stage_h2d(c, d_r, r, m * 32))) return st;
   st = dev_alloc(c, (size_t(2) << mh) * sizeof(Fr), (void**)&lv[0]);
   if (st) return st;
   st = dev_alloc(c, (size_t(2) << ml) * sizeof(Fr), (void**)&lv[1]);
@@ -293,9 +291,7 @@ static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& sca
   JA_LAUNCH(c, KC_EQ_TABLE, k_eq_expand<<<grid_for(n), kBlock, 0, c->stream>>>(lv[0] + ((size_t(1) << mh) - 1), lv[1] + ((size_t(1) << ml) - 1),
                                                     (int)ml, n, out));
   JA_CUDA(cudaGetLastError());
-  // h_pinned is reused by later calls: make sure the H2D copy has been consumed
-  JA_CUDA(cudaStreamSynchronize(c->stream));
-  dev_free(c, d_r); dev_free(c, lv[0]); dev_free(c, lv[1]);
+  dev_free(c, d_r); dev_free(c, lv[0]); dev_free(c, lv[1]);     // stream-ordered reuse (one stream per context)
   return JA_OK;
 }
 
@@ -346,11 +342,7 @@ int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, co
   Fr* d_w = nullptr;
   int32_t st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_w);
   if (st) { delete s; return st; }
-  if (m) {
-    JA_REQUIRE(m * 32 <= kPinnedBytes, "ja_spliteq_new: too many variables");
-    memcpy(c->h_pinned, w, m * 32);
-    JA_CUDA(cudaMemcpyAsync(d_w, c->h_pinned, m * 32, cudaMemcpyHostToDevice, c->stream));
-  }
+  if (m && (st = stage_h2d(c, d_w, w, m * 32))) { delete s; return st; }
   st = dev_alloc(c, (size_t(2) << n_out_vars) * sizeof(Fr), (void**)&s->out_levels);
   if (st) { delete s; return st; }
   st = dev_alloc(c, (size_t(2) << n_in_vars) * sizeof(Fr), (void**)&s->in_levels);
@@ -361,8 +353,7 @@ int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, co
   a.w[1] = d_w + off_in;  a.m[1] = (int)n_in_vars;  a.rev[1] = rev; a.buf[1] = s->in_levels;  a.scale[1] = to_dev(host::FR_ONE);
   JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels<<<2, 1024, 0, c->stream>>>(a));
   JA_CUDA(cudaGetLastError());
-  JA_CUDA(cudaStreamSynchronize(c->stream));
-  dev_free(c, d_w);
+  dev_free(c, d_w);                 // stream-ordered reuse (one stream per context)
   *out = s;
   return JA_OK;
 }

@@ -46,6 +46,11 @@ struct ja_ctx {
   unsigned int* d_counter = nullptr;
   Fr* d_out = nullptr;             // kMaxOut
   uint64_t* h_pinned = nullptr;    // staging for small D2H/H2D
+  // Ring of pinned staging memory for small host->device uploads (eq points, tables, gammas): the copy is enqueued and
+  // the call returns without synchronising.  A slot is only reused after kRingBytes of further uploads, by which time
+  // the stream has long consumed it (every sumcheck round and every API call that returns data synchronises).
+  char* h_ring = nullptr;
+  size_t ring_off = 0;
   // host-mapped result slots of the sumcheck engine (sumcheck.cu): kSlots x kSlotBytes, sums at 0, sequence word at
   // kSlotSeqOffset; h_mapped / d_mapped are the host and device addresses of the same pinned allocation
   void* h_mapped = nullptr;
@@ -85,6 +90,7 @@ void ja_prof_post(ja_ctx* c);
 static constexpr int kMaxGrid = kSMs * 8;
 static constexpr int kMaxOut = 32;
 static constexpr size_t kPinnedBytes = 1 << 16;
+static constexpr size_t kRingBytes = 1 << 20;
 static constexpr int kSlots = 128;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
 static constexpr size_t kMaxRowVals = 8192, kRowSeqOffset = kMaxRowVals * 32;
@@ -157,6 +163,19 @@ static inline unsigned grid_for(size_t work) {
   if (b < 1) b = 1;
   if (b > (size_t)kSMs * 8) b = (size_t)kSMs * 8;
   return (unsigned)b;
+}
+
+// enqueue an H2D copy of a small host buffer through the pinned ring; no synchronisation
+static inline int32_t stage_h2d(ja_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return JA_OK;
+  JA_REQUIRE(bytes <= kRingBytes / 4, "stage_h2d: buffer too large for the staging ring");
+  const size_t need = (bytes + 255) & ~size_t(255);
+  if (c->ring_off + need > kRingBytes) c->ring_off = 0;
+  char* slot = c->h_ring + c->ring_off;
+  c->ring_off += need;
+  memcpy(slot, src, bytes);
+  JA_CUDA(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, c->stream));
+  return JA_OK;
 }
 
 static inline size_t dev_size_class(size_t bytes) {

@@ -215,12 +215,11 @@ int32_t ja_addr_gather(ja_ctx* c, const ja_addr* a, const uint64_t* tables, ja_p
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   const size_t tab_bytes = a->d * a->K * sizeof(Fr);
-  JA_REQUIRE(tab_bytes <= kPinnedBytes, "ja_addr_gather: tables too large for the staging buffer");
+  JA_REQUIRE(tab_bytes <= kRingBytes / 4, "ja_addr_gather: tables too large for the staging ring");
   Fr* d_tab = nullptr;
   int32_t st = dev_alloc(c, tab_bytes, (void**)&d_tab);
   if (st) return st;
-  memcpy(c->h_pinned, tables, tab_bytes);
-  JA_CUDA(cudaMemcpyAsync(d_tab, c->h_pinned, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((st = stage_h2d(c, d_tab, tables, tab_bytes))) return st;
   GatherOut go;
   for (size_t i = 0; i < a->d; i++) {
     if ((st = ja_poly_alloc(c, a->T, &out_polys[i]))) return st;
@@ -230,8 +229,7 @@ int32_t ja_addr_gather(ja_ctx* c, const ja_addr* a, const uint64_t* tables, ja_p
   if (gx > (unsigned)kSMs * 2) gx = kSMs * 2;
   JA_LAUNCH(c, KC_CONVERT, k_addr_gather<<<dim3(gx, (unsigned)a->d), kBlock, 0, c->stream>>>(a->d_k, a->T, d_tab, (uint32_t)a->K, go));
   JA_CUDA(cudaGetLastError());
-  JA_CUDA(cudaStreamSynchronize(c->stream));   // h_pinned is reused by later calls
-  dev_free(c, d_tab);
+  dev_free(c, d_tab);                          // stream-ordered reuse (one stream per context)
   return JA_OK;
 }
 
@@ -277,7 +275,7 @@ int32_t ja_rlc_add_onehot(ja_ctx* c, ja_poly* joint, const ja_addr* a, const uin
   Fr* d_co = nullptr;
   int32_t st = dev_alloc(c, a->d * sizeof(Fr), (void**)&d_co);
   if (st) return st;
-  JA_CUDA(cudaMemcpyAsync(d_co, coeffs, a->d * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));   // pageable source: staged synchronously
+  if ((st = stage_h2d(c, d_co, coeffs, a->d * sizeof(Fr)))) return st;
   unsigned gx = grid_for(a->T);
   JA_LAUNCH(c, KC_SCATTER, k_rlc_add_onehot<<<gx, kBlock, 0, c->stream>>>(a->d_k, a->T, (uint32_t)a->d, d_co, joint->data()));
   JA_CUDA(cudaGetLastError());

@@ -180,8 +180,7 @@ struct DevInst : Inst {
       JA_REQUIRE(gammas.size() == polys.size(), "sumcheck: booleanity takes one gamma per polynomial");
       int32_t st = dev_alloc(c, gammas.size() * sizeof(Fr), (void**)&d_gammas);
       if (st) return st;
-      JA_CUDA(cudaMemcpyAsync(d_gammas, gammas.data(), gammas.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-      JA_CUDA(cudaStreamSynchronize(c->stream));
+      if ((st = stage_h2d(c, d_gammas, gammas.data(), gammas.size() * sizeof(Fr)))) return st;
     }
     return JA_OK;
   }
