@@ -142,8 +142,9 @@ int32_t ja_addr_upload(ja_ctx* c, const uint32_t* k, size_t d, size_t T, size_t 
   JA_REQUIRE(c && k && out && d > 0 && T > 0 && K > 0, "ja_addr_upload: null or empty argument");
   JA_REQUIRE(d <= (size_t)kMaxProdPolys, "ja_addr_upload: at most 32 lists per batch");
   JA_REQUIRE(T < (size_t(1) << 31) && K <= 65536, "ja_addr_upload: T or K too large");
-  for (size_t i = 0; i < d * T; i++)
-    JA_REQUIRE(k[i] == 0xffffffffu || k[i] < K, "ja_addr_upload: address outside [0, K)");
+  uint32_t bad = 0;                                   // branch-free so the compiler vectorises the scan
+  for (size_t i = 0; i < d * T; i++) bad |= (uint32_t)(k[i] != 0xffffffffu) & (uint32_t)(k[i] >= (uint32_t)K);
+  JA_REQUIRE(!bad, "ja_addr_upload: address outside [0, K)");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   ja_addr* a = new ja_addr();
