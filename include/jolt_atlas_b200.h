@@ -295,6 +295,14 @@ int32_t ja_msm_fr_range(ja_ctx*, const ja_srs*, const ja_poly* scalars, size_t l
  * of the whole instance, g_offset = slice_start / 2.  Family S / PROD / POW (LowToHigh).  Outputs are partial sums. */
 int32_t ja_round_eval_slice(ja_ctx*, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys, const ja_spliteq* eq,
                             uint32_t aux_u32, size_t g_offset, uint64_t* out_evals, size_t n_out);
+/* Sharded Sumcheck::prove / BatchedSumcheck::prove: after this call the device polynomials handed to ja_sumcheck_prove /
+ * ja_batched_sumcheck_prove are this GPU's contiguous slice (len / world coefficients, rank-major) of each MLE; eq points,
+ * claims and the transcript are replicated.  Every round the partial sums (<= 17 Fr) go through `allgather` (send `bytes`,
+ * receive world x bytes, rank-major; return 0) and are added; binds stay local; once a slice is down to one coefficient
+ * the world remaining coefficients are gathered and the last log2(world) rounds run replicated.  Every rank returns the same
+ * proof.  Split-eq (LowToHigh) bodies and PROD / POW only; world == 1 (or a NULL callback) restores the normal mode. */
+typedef int32_t (*ja_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
+int32_t ja_set_sumcheck_shard(ja_ctx*, uint32_t rank, uint32_t world, ja_allgather_fn allgather, void* user);
 /* Host-only (no ja_ctx, no GPU): add n affine points (complete addition) / add n_parts vectors of n_vals Fr. */
 int32_t ja_g1_sum_affine(const uint64_t* xy, const int32_t* is_inf, size_t n, uint64_t out_xy[8], int32_t* out_inf);
 int32_t ja_fr_sum(const uint64_t* vals, size_t n_parts, size_t n_vals, uint64_t* out);

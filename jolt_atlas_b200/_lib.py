@@ -77,6 +77,7 @@ SIGNATURES = {
     "ja_hyperkzg_open_witness": (C.c_int32, [vp, vp, u64p, u64p, u64p, i32p]),
     "ja_hyperkzg_open_free": (None, [vp, vp]),
     "ja_hyperkzg_open": (C.c_int32, [vp, vp, vp, u64p, C.c_size_t, C.c_char_p, u32p, u64p, i32p, u64p, i32p, u64p]),
+    "ja_set_sumcheck_shard": (C.c_int32, [vp, C.c_uint32, C.c_uint32, vp, vp]),
     "ja_set_msm_shard": (C.c_int32, [vp, C.c_uint32, C.c_uint32]),
     "ja_msm_fr_range": (C.c_int32, [vp, vp, vp, C.c_size_t, C.c_size_t, u64p, i32p]),
     "ja_round_eval_slice": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, C.c_uint32, C.c_size_t, u64p, C.c_size_t]),

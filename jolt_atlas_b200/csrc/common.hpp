@@ -61,6 +61,11 @@ struct ja_ctx {
   void* d_rowvals = nullptr;
   // MSM index-range shard of this context (shard.cu): ja_msm_run restricts every job to its slice when count > 1
   uint32_t msm_shard_index = 0, msm_shard_count = 1;
+  // sharded sumcheck (ja_set_sumcheck_shard): device polynomials are contiguous hypercube slices, partial round sums
+  // are all-gathered through the caller's callback
+  uint32_t sc_rank = 0, sc_world = 1;
+  ja_allgather_fn sc_allgather = nullptr;
+  void* sc_user = nullptr;
   bool slice_on = false;           // ja_round_eval_slice in progress: eq tables are indexed with g + slice_g_offset
   size_t slice_g_offset = 0;
   // Size-class cache of device buffers (dev_alloc / dev_free below).  Every buffer of a context is used on its one

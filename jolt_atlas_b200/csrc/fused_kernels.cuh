@@ -57,7 +57,8 @@ template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 
 template <int KID, bool FUSED>
 __global__ void __launch_bounds__(kBlock, (KID == 0 || KID == 1 || KID == 6) ? 4 : 2)
 k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
-          size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
+          size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
+          size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */) {
   constexpr int NOUT = SOut<KID>::N;
   Fr outer[NOUT], inner[NOUT];
 #pragma unroll
@@ -68,7 +69,7 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
   if (g_end > G) g_end = G;
   size_t cur_xout = ~size_t(0);
   for (size_t g = g_begin + threadIdx.x; g < g_end; g += kBlock) {
-    const size_t x_out = g >> bits_in;
+    const size_t x_out = (g + g_off) >> bits_in;
     if (x_out != cur_xout) {
       if (cur_xout != ~size_t(0)) {
         const Fr eo = fp_load(e_out + cur_xout);
@@ -104,7 +105,7 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       else if (KID == 1) v[0] = fp_sub<FrParams>(l0, r0);
       else { v[0] = fp_mul<FrParams>(l0, r0); v[NOUT - 1] = fp_mul<FrParams>(fp_sub<FrParams>(l1, l0), fp_sub<FrParams>(r1, r0)); }
     }
-    const Fr ei = fp_load(e_in + (g & mask_in));
+    const Fr ei = fp_load(e_in + ((g + g_off) & mask_in));
 #pragma unroll
     for (int k = 0; k < NOUT; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
   }
@@ -120,7 +121,7 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
 template <int L, bool SAME, bool FUSED>
 JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
                             int bits_in, size_t G, size_t pairs_per_block, Fr* partials /* [nb][L] */, unsigned int* counter,
-                            const Publish& pub, unsigned int bx, unsigned int nb) {
+                            const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off = 0) {
   constexpr int GPB = kBlock / L;
   const int li = threadIdx.x & (L - 1);
   const int group = threadIdx.x / L;
@@ -158,7 +159,7 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, cons
     v[L - 1] = pad ? p0 : dp;
     LaneProduct<L>::run(v, li);
     if (active) {
-      const size_t x_out = g >> bits_in;
+      const size_t x_out = (g + g_off) >> bits_in;
       if (x_out != cur_xout) {
         if (cur_xout != ~size_t(0)) {
           outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
@@ -166,7 +167,7 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, cons
         }
         cur_xout = x_out;
       }
-      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + (g & mask_in)), v[0]));
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), v[0]));
     }
   }
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
@@ -200,8 +201,8 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, cons
 template <int L, bool SAME, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub) {
-  round_prod_body<L, SAME, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x);
+             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0) {
+  round_prod_body<L, SAME, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 
 // ---- booleanity phase 2, lane-parallel (booleanity.rs:254-301) ---------------------------------------------------------

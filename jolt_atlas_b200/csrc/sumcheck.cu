@@ -154,6 +154,9 @@ struct DevInst : Inst {
   bool legacy = false;              // round went through ja_round_eval_launch (pinned staging + stream sync)
   FrH cs, cw, div;
   int prod_lanes = 0;
+  // multi-GPU: the polynomials are this rank's contiguous hypercube slices (ja_set_sumcheck_shard)
+  bool sharded = false, round_sharded = false;
+  uint32_t sc_rank = 0, sc_world = 1;
 
   int32_t setup(ja_ctx* c) {
     const size_t len = polys[0]->len;
@@ -176,6 +179,11 @@ struct DevInst : Inst {
       default: return fail(JA_ERR_UNSUPPORTED, "sumcheck: kind not implemented");
     }
     JA_REQUIRE(n_out >= 1 && n_out <= (size_t)kMaxOut && polys.size() <= (size_t)kMaxProdPolys, "sumcheck: too many polynomials / outputs");
+    if (c->sc_world > 1 && c->sc_allgather && kind != 7) {
+      JA_REQUIRE(fusable && order == JA_LOW_TO_HIGH, "sumcheck: only the LowToHigh split-eq / product bodies run on hypercube slices");
+      sharded = true; sc_rank = c->sc_rank; sc_world = c->sc_world;
+      rounds += (size_t)log2z(sc_world);
+    }
     if (kind == 7) {
       JA_REQUIRE(gammas.size() == polys.size(), "sumcheck: booleanity takes one gamma per polynomial");
       int32_t st = dev_alloc(c, gammas.size() * sizeof(Fr), (void**)&d_gammas);
@@ -196,6 +204,7 @@ struct DevInst : Inst {
     int bits_in = 0;
     const Fr* e_out = nullptr;
     const Fr* e_in = nullptr;
+    size_t g_off = 0;
   };
   int32_t prepare(ja_ctx* c, Prep* pr) {
     const bool fz = pending;
@@ -223,9 +232,10 @@ struct DevInst : Inst {
     if (uses_eq()) {
       JA_REQUIRE(eq && eq->order == order, "sumcheck: split-eq binding order does not match the round body");
       const size_t cover = size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1));
-      JA_REQUIRE(cover == G, "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+      JA_REQUIRE(cover == G * (sharded ? sc_world : 1), "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
       pr->bits_in = eq->in_len - 1; pr->e_out = eq->e_out(); pr->e_in = eq->e_in();
     }
+    pr->g_off = sharded ? (size_t)sc_rank * G : 0;
     pr->fz = fz; pr->len_eval = len_eval; pr->G = G;
     return JA_OK;
   }
@@ -236,7 +246,7 @@ struct DevInst : Inst {
     }
   }
   bool pairable() const {
-    return fusable && polys.size() >= 2 && polys.size() <= 16 && (kind == JA_EVAL_PROD || kind == 7);
+    return !sharded && fusable && polys.size() >= 2 && polys.size() <= 16 && (kind == JA_EVAL_PROD || kind == 7);
   }
   // this instance's half of a paired launch (k_round_prod_bool): slot armed, buffers ready, state advanced
   int32_t prepare_pair(ja_ctx* c, PairArgs* a, Prep* pr, int scratch_half) {
@@ -257,6 +267,40 @@ struct DevInst : Inst {
     a->pub = slot.pub;
     if (kind == JA_EVAL_PROD) prod_lanes = L;
     commit_round(*pr);
+    return JA_OK;
+  }
+
+  // Every slice is down to one coefficient: gather the sc_world remaining coefficients of each MLE onto every rank and
+  // run the last log2(world) rounds replicated ("the last log2 g rounds run after gathering g elements per poly").
+  int32_t unshard(ja_ctx* c) {
+    int32_t st;
+    if (pending) {
+      if ((st = ja_bind_many(c, polys.data(), polys.size(), pend_ch, order))) return st;
+      pending = false;
+    }
+    const size_t np = polys.size();
+    std::vector<uint64_t> mine(4 * np), all(4 * np * sc_world);
+    for (size_t q = 0; q < np; q++) {
+      JA_REQUIRE(polys[q]->len == 1, "sumcheck: slice not reduced to one coefficient at the hand-over");
+      JA_CUDA(cudaMemcpyAsync(c->h_pinned + 4 * q, polys[q]->data(), sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+    }
+    JA_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(mine.data(), c->h_pinned, 32 * np);
+    if (c->sc_allgather(c->sc_user, mine.data(), 32 * np, all.data()) != 0) return fail(JA_ERR_INVALID, "sumcheck: allgather callback failed");
+    std::vector<uint64_t> col(4 * sc_world);
+    for (size_t q = 0; q < np; q++) {
+      ja_poly* p = polys[q];
+      for (uint32_t r = 0; r < sc_world; r++) memcpy(col.data() + 4 * r, all.data() + 4 * (r * np + q), 32);
+      if (p->cap[p->cur] < sc_world) {
+        dev_free(c, p->buf[p->cur]);
+        p->buf[p->cur] = nullptr; p->cap[p->cur] = 0;
+        if ((st = dev_alloc(c, sc_world * sizeof(Fr), (void**)&p->buf[p->cur]))) return st;
+        p->cap[p->cur] = sc_world;
+      }
+      if ((st = stage_h2d(c, p->buf[p->cur], col.data(), 32 * sc_world))) return st;
+      p->len = sc_world;
+    }
+    sharded = false;
     return JA_OK;
   }
 
@@ -282,7 +326,7 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub))
+#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off))
 #define JA_PROD_L(LL) do { if (same) { if (fz) JA_PROD_F(LL, true, true); else JA_PROD_F(LL, true, false); } \
                            else { if (fz) JA_PROD_F(LL, false, true); else JA_PROD_F(LL, false, false); } } while (0)
       switch (L) { case 2: JA_PROD_L(2); break; case 4: JA_PROD_L(4); break; case 8: JA_PROD_L(8); break; default: JA_PROD_L(16); break; }
@@ -320,7 +364,7 @@ struct DevInst : Inst {
       const size_t tpb = (tiles + grid - 1) / grid;
       grid = (tiles + tpb - 1) / tpb;
       const int np = (int)polys.size();
-#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub))
+#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off))
 #define JA_S_K(KID) do { if (fz) JA_S_F(KID, true); else JA_S_F(KID, false); } while (0)
       switch (kind) {
         case JA_EVAL_ADD: JA_S_K(0); break;
@@ -343,7 +387,9 @@ struct DevInst : Inst {
   int32_t launch(ja_ctx* c, size_t) override {
     int32_t st;
     if (paired_this_round) { paired_this_round = false; return JA_OK; }
+    if (sharded && (pending ? polys[0]->len / 2 : polys[0]->len) < 2 && (st = unshard(c))) return st;
     legacy = !fusable;
+    round_sharded = sharded;
     if (fusable) {
       slot = arm_slot(c, slot_id);
       if ((st = launch_fused(c))) return st;
@@ -377,12 +423,26 @@ struct DevInst : Inst {
       if ((st = ja_round_eval_collect(c, pend, ev))) return st;
     } else {
       if ((st = wait_slot(c, slot))) return st;
-      if (prod_lanes && (kind == JA_EVAL_PROD || kind == JA_EVAL_POW)) {
+      const bool lanes = prod_lanes && (kind == JA_EVAL_PROD || kind == JA_EVAL_POW);
+      const size_t n_raw = lanes ? (size_t)prod_lanes : n_out;
+      uint64_t raw[kMaxOut * 4];
+      memcpy(raw, slot.host_vals, n_raw * 32);
+      if (round_sharded) {
+        // partial sums of this rank's slice: all-gather (<= 17 Fr per rank) and add as field elements
+        std::vector<uint64_t> all(4 * n_raw * sc_world);
+        if (c->sc_allgather(c->sc_user, raw, 32 * n_raw, all.data()) != 0) return fail(JA_ERR_INVALID, "sumcheck: allgather callback failed");
+        for (size_t k = 0; k < n_raw; k++) {
+          FrH acc = host::FR_ZERO;
+          for (uint32_t r = 0; r < sc_world; r++) acc = host::add(acc, host::from_limbs(all.data() + 4 * (r * n_raw + k)));
+          memcpy(raw + 4 * k, acc.l, 32);
+        }
+      }
+      if (lanes) {
         const size_t d = n_out;
-        memcpy(ev, slot.host_vals, (d - 1) * 32);
-        memcpy(ev + 4 * (d - 1), slot.host_vals + 4 * (prod_lanes - 1), 32);
+        memcpy(ev, raw, (d - 1) * 32);
+        memcpy(ev + 4 * (d - 1), raw + 4 * (prod_lanes - 1), 32);
       } else {
-        memcpy(ev, slot.host_vals, n_out * 32);
+        memcpy(ev, raw, n_out * 32);
       }
     }
     std::vector<FrH> e(n_out);
@@ -1072,6 +1132,13 @@ int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, f
   for (int i = 0; i < np; i++) { ja_poly_free(c, src[i]); dev_free(c, dst[i]); }
   dev_free(c, d_gam);
   ja_spliteq_free(c, eq);
+  return JA_OK;
+}
+
+int32_t ja_set_sumcheck_shard(ja_ctx* c, uint32_t rank, uint32_t world, ja_allgather_fn allgather, void* user) {
+  JA_REQUIRE(c && world >= 1 && rank < world && is_pow2(world), "ja_set_sumcheck_shard: world must be a power of two and rank < world");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  c->sc_rank = rank; c->sc_world = allgather ? world : 1; c->sc_allgather = allgather; c->sc_user = user;
   return JA_OK;
 }
 

@@ -202,3 +202,71 @@ def sharded_round_eval(ctx, kernel_id, slice_polys, eq, comm, n_out, aux_u32=0):
     part = np.zeros((n_out, 4), dtype=np.uint64)
     check(ctx._lib.ja_round_eval_slice(ctx._h, kernel_id, arr, len(slice_polys), eq._h, aux_u32, g_offset, A._u64p(part), n_out))
     return fr_sum(comm.all_gather(part))
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+def _allgather_callback(comm):
+    """ja_allgather_fn over a Comm: send `nbytes`, receive world x nbytes (rank-major)."""
+    def cb(user, send, nbytes, recv):
+        try:
+            buf = np.frombuffer((C.c_uint8 * nbytes).from_address(send), dtype=np.uint8).copy()
+            allp = np.ascontiguousarray(comm.all_gather(buf))
+            C.memmove(recv, allp.ctypes.data, comm.world * nbytes)
+            return 0
+        except Exception:       # noqa: BLE001 - nothing may unwind into the C caller
+            return -1
+    return ALLGATHER_FN(cb)
+
+
+def sharded_sumcheck_prove(ctx, kind, slice_polys, claim, transcript, comm, eq_w, aux_u32=0, max_coeffs=40):
+    """Sumcheck::prove (sumcheck.rs:565-599) with every MLE sharded into contiguous hypercube slices: `slice_polys` hold
+    this rank's len / world coefficients, eq point / claim / transcript are replicated.  Split-eq (LowToHigh) bodies and
+    PROD / POW.  Returns the same dict as api.sumcheck_prove, identical on every rank."""
+    from . import api as A
+    n_local = len(slice_polys[0])
+    rounds = (n_local * comm.world).bit_length() - 1
+    cb = _allgather_callback(comm)
+    check(ctx._lib.ja_set_sumcheck_shard(ctx._h, comm.rank, comm.world, C.cast(cb, C.c_void_p), None))
+    try:
+        arr = (C.c_void_p * len(slice_polys))(*[p._h for p in slice_polys])
+        w = A._fr_arg(eq_w).reshape(-1, 4)
+        assert w.shape[0] == rounds
+        coeffs = np.zeros((rounds, max_coeffs, 4), dtype=np.uint64)
+        ncoeffs = np.zeros(rounds, dtype=np.uint32)
+        chal = np.zeros((rounds, 4), dtype=np.uint64)
+        fin = np.zeros((len(slice_polys), 4), dtype=np.uint64)
+        st = C.create_string_buffer(transcript.state, 32)
+        nr = C.c_uint32(transcript.n_rounds)
+        check(ctx._lib.ja_sumcheck_prove(ctx._h, kind, arr, len(slice_polys), A._u64p(w), w.shape[0], None, 0, aux_u32,
+                                         A._u64p(A._fr_arg(claim)), st, C.byref(nr), max_coeffs, A._u64p(coeffs),
+                                         ncoeffs.ctypes.data_as(_lib.u32p), A._u64p(chal), A._u64p(fin)))
+    finally:
+        check(ctx._lib.ja_set_sumcheck_shard(ctx._h, 0, 1, None, None))
+    transcript.state, transcript.n_rounds = st.raw, nr.value
+    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(rounds)], "challenges": chal, "final_claims": fin}
+
+
+class ThreadComm:
+    """In-process all-gather between `world` threads (one Context per thread on the same GPU): lets the sharded code
+    paths run on a 1-GPU box.  Create one shared ThreadComm.Group and one ThreadComm(rank) per thread."""
+
+    class Group:
+        def __init__(self, world):
+            import threading
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, group, rank):
+        self.group, self.rank, self.world = group, rank, group.world
+        self.plan = ShardPlan(rank, group.world)
+
+    def all_gather(self, a: np.ndarray) -> np.ndarray:
+        g = self.group
+        g.slots[self.rank] = np.ascontiguousarray(a).copy()
+        g.barrier.wait(timeout=60)
+        out = np.stack(g.slots)
+        g.barrier.wait(timeout=60)
+        return out

@@ -108,3 +108,52 @@ def test_two_gpu_nccl_job():
                         "--master-port", "29533", os.path.join(ROOT, "scripts", "multi_gpu_check.py")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "multi-gpu ok" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("kind,npoly,world,m", [(2, 2, 2, 10), (6, 1, 4, 9), (4, 4, 2, 8), (0, 2, 8, 5), (4, 16, 2, 7)])
+def test_sharded_sumcheck_prove_equals_single(kind, npoly, world, m):
+    """The full sharded Sumcheck::prove loop (local fused rounds on hypercube slices, partial sums all-gathered through the
+    callback, hand-over to replicated rounds when a slice reaches one coefficient) equals the unsharded proof on every
+    rank.  Ranks are threads with their own Context on this GPU (tests the engine path; NCCL run: scripts/multi_gpu_check.py)."""
+    import threading
+    from jolt_atlas_b200 import Blake2bTranscriptState, Context, MultilinearPolynomial, sumcheck_prove
+    from jolt_atlas_b200 import parallel as PAR
+    rng = np.random.default_rng(kind * 100 + world)
+    N = 1 << m
+    host = rng.integers(0, 1 << 63, size=(npoly, N, 4), dtype=np.uint64)
+    host[..., 3] &= np.uint64((1 << 60) - 1)
+    w, claim = _chal(rng, m), _chal(rng, 1)[0]
+    with Context(0) as c0:
+        t0 = Blake2bTranscriptState(b"shard")
+        want = sumcheck_prove(c0, kind, [MultilinearPolynomial.from_fr(c0, host[i]) for i in range(npoly)], claim, t0, eq_w=w)
+    group = PAR.ThreadComm.Group(world)
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            comm = PAR.ThreadComm(group, rank)
+            lo, hi = comm.plan.slice_range(N)
+            with Context(0) as c:
+                t = Blake2bTranscriptState(b"shard")
+                polys = [MultilinearPolynomial.from_fr(c, host[i, lo:hi]) for i in range(npoly)]
+                results[rank] = (PAR.sharded_sumcheck_prove(c, kind, polys, claim, t, comm, w), t.state)
+        except Exception as e:   # noqa: BLE001
+            errors.append((rank, repr(e)))
+            try:
+                group.barrier.abort()
+            except Exception:    # noqa: BLE001
+                pass
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errors, errors
+    for rank in range(world):
+        got, state = results[rank]
+        assert len(got["coeffs"]) == m
+        for a, b in zip(got["coeffs"], want["coeffs"]):
+            assert np.array_equal(a, b), rank
+        assert np.array_equal(got["challenges"], want["challenges"])
+        assert np.array_equal(got["final_claims"], want["final_claims"])
+        assert state == t0.state
