@@ -68,12 +68,12 @@ with A.Context(local) as ctx:
     host2[..., 3] &= np.uint64((1 << 60) - 1)
     w2, claim2 = W._challenges(rng, m), W._challenges(rng, 1)[0]
     for kind, npoly in ((2, 2), (4, 4)):
-        t_one, t_sh = A.Blake2bTranscriptState(b"sc"), A.Blake2bTranscriptState(b"sc")
-        want = A.sumcheck_prove(ctx, kind, [A.MultilinearPolynomial.from_fr(ctx, host2[i]) for i in range(npoly)], claim2, t_one, eq_w=w2)
+        tr_one, tr_sh = A.Blake2bTranscriptState(b"sc"), A.Blake2bTranscriptState(b"sc")
+        want = A.sumcheck_prove(ctx, kind, [A.MultilinearPolynomial.from_fr(ctx, host2[i]) for i in range(npoly)], claim2, tr_one, eq_w=w2)
         got = PAR.sharded_sumcheck_prove(ctx, kind, [A.MultilinearPolynomial.from_fr(ctx, host2[i, lo:hi]) for i in range(npoly)],
-                                         claim2, t_sh, comm, w2)
+                                         claim2, tr_sh, comm, w2)
         assert all(np.array_equal(a, b) for a, b in zip(got["coeffs"], want["coeffs"])), "sharded sumcheck differs"
-        assert np.array_equal(got["final_claims"], want["final_claims"]) and t_one.state == t_sh.state
+        assert np.array_equal(got["final_claims"], want["final_claims"]) and tr_one.state == tr_sh.state
     if comm.rank == 0:
         print("multi-gpu ok: world=%d ell=%d  open sharded %.2f ms vs single-GPU %.2f ms" % (comm.world, ell, t_sh * 1e3, t_one * 1e3), flush=True)
 dist.barrier()
