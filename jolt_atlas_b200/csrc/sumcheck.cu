@@ -20,6 +20,7 @@
 
 #include "common.hpp"
 #include "fused_kernels.cuh"
+#include "tma_round.cuh"
 #include "sumcheck_host.hpp"
 #include "transcript_host.hpp"
 
@@ -36,6 +37,67 @@ struct ScTrace {
   void lap(int k) { if (!on) return; auto n = std::chrono::steady_clock::now(); t[k] += std::chrono::duration<double, std::micro>(n - last).count(); last = n; }
 };
 ScTrace g_trace;
+
+// ---- TMA-staged streaming round kernels (tma_round.cuh) -------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query: nothing links libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// a polynomial of n Fr as [n/4 rows][32 x u32], 32-row boxes (one warp's slab), SWIZZLE_128B
+int32_t make_row_map(CUtensorMap* tm, const Fr* base, size_t n) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(JA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {32, (cuuint64_t)(n / 4)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<Fr*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(JA_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return JA_OK;
+}
+constexpr size_t kTmaMinPairs = size_t(1) << 16;     // below this the slabs live in L2 and the register-staged kernel is as fast
+bool tma_eligible(int kind, bool fused, size_t G) {
+  const bool off = getenv("JA_NO_TMA") != nullptr;      // read per call: tests flip it to compare the two kernels
+  return !off && fused && (kind == JA_EVAL_ADD || kind == JA_EVAL_SUB || kind == JA_EVAL_IDENT) && G >= kTmaMinPairs && G % kTmaRows == 0;
+}
+// in[q]: current arrays of 4G Fr, out[q]: bound arrays of 2G Fr
+int32_t launch_round_s_tma(ja_ctx* c, int kind, const FusedPolys& P, const Challenge& ch, const Fr* e_out, const Fr* e_in, int bits_in,
+                           size_t G, Fr* part, unsigned int* ctr, const Publish& pub, size_t g_off) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    JA_CUDA(cudaFuncSetAttribute(k_round_s_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    JA_CUDA(cudaFuncSetAttribute(k_round_s_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    JA_CUDA(cudaFuncSetAttribute(k_round_s_tma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    attr_set = true;
+  }
+  const int np = kind == JA_EVAL_IDENT ? 1 : 2;
+  CUtensorMap tm[2];
+  int32_t st;
+  for (int q = 0; q < 2; q++)
+    if ((st = make_row_map(&tm[q], P.in[q < np ? q : 0], 4 * G))) return st;
+  const size_t slabs = G / kTmaRows;
+  size_t grid = slabs < (size_t)kSMs * 2 ? slabs : (size_t)kSMs * 2;
+  const size_t spb = (slabs + grid - 1) / grid;
+  grid = (slabs + spb - 1) / spb;
+  cudaStream_t s = c->stream;
+#define JA_TMA_K(KID) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s_tma<KID><<<(unsigned)grid, kTmaRows, kTmaSmemBytes, s>>>( \
+    tm[0], tm[1], P.out[0], P.out[np - 1], ch, e_out, e_in, bits_in, G, spb, part, ctr, pub, g_off))
+  if (kind == JA_EVAL_ADD) JA_TMA_K(0);
+  else if (kind == JA_EVAL_SUB) JA_TMA_K(1);
+  else JA_TMA_K(6);
+#undef JA_TMA_K
+  return JA_OK;
+}
 
 // ---- host-mapped result slots ------------------------------------------------------------------------------------
 struct Slot {
@@ -358,6 +420,9 @@ struct DevInst : Inst {
       switch (L) { case 2: JA_BOOL_L(2); break; case 4: JA_BOOL_L(4); break; case 8: JA_BOOL_L(8); break; default: JA_BOOL_L(16); break; }
 #undef JA_BOOL_L
 #undef JA_BOOL_F
+    } else if (tma_eligible(kind, fz, G)) {
+      int32_t tst = launch_round_s_tma(c, kind, P, ch, e_out, e_in, bits_in, G, part, ctr, pub, pr.g_off);
+      if (tst) return tst;
     } else {
       size_t tiles = (G + kBlock - 1) / kBlock;
       size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
@@ -1066,13 +1131,13 @@ extern "C" {
 
 // bench hook: ONE fused round kernel (bind the previous challenge + evaluate) re-run `iters` times on resident synthetic
 // operands of 2^log_n Fr per polynomial.  which: 0 ADD (2 polys), 1 MUL (2), 2 IDENT (1), 3 product of 4, 4 product of 16,
-// 5 booleanity over 16, 6 opening reduction HighToLow (1 poly, in place).  Algorithmic bytes per launch: 48 * 2^log_n per
+// 5 booleanity over 16, 6 opening reduction HighToLow (1 poly, in place), 7 / 8 = ADD / IDENT through the TMA-staged kernel.  Algorithmic bytes per launch: 48 * 2^log_n per
 // polynomial (32 n read + 16 n written).
 int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, float* out_ms) {
-  JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 3 && log_n <= 28 && which >= 0 && which <= 6, "ja_bench_fused: bad argument");
+  JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 3 && log_n <= 28 && which >= 0 && which <= 8, "ja_bench_fused: bad argument");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  static const int kNp[7] = {2, 2, 1, 4, 16, 16, 1};
+  static const int kNp[9] = {2, 2, 1, 4, 16, 16, 1, 2, 1};
   const int np = kNp[which];
   const size_t n = size_t(1) << log_n, G = n / 4;
   std::vector<ja_poly*> src(np, nullptr);
@@ -1095,9 +1160,14 @@ int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, f
   for (int i = 0; i < np; i++) { P.in[i] = src[i]->data(); P.out[i] = which == 6 ? src[i]->data() : dst[i]; }
   const int bits_in = eq->in_len - 1, bits_out = eq->out_len - 1;
   Slot slot = arm_slot(c, 0);
+  int32_t lst = JA_OK;
   auto launch = [&]() {
     cudaStream_t s = c->stream;
-    if (which <= 2) {
+    if (which >= 7) {
+      const int32_t e = launch_round_s_tma(c, which == 7 ? JA_EVAL_ADD : JA_EVAL_IDENT, P, ch, eq->e_out(), eq->e_in(), bits_in, G,
+                                           c->d_partials, c->d_counter, slot.pub, 0);
+      if (e) lst = e;
+    } else if (which <= 2) {
       size_t tiles = (G + kBlock - 1) / kBlock;
       size_t grid = tiles < (size_t)kSMs * 4 ? tiles : (size_t)kSMs * 4;
       const size_t tpb = (tiles + grid - 1) / grid;
@@ -1121,6 +1191,7 @@ int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, f
     }
   };
   for (int i = 0; i < 3; i++) launch();
+  if (lst) return lst;
   JA_CUDA(cudaEventRecord(c->ev0, c->stream));
   for (int i = 0; i < iters; i++) launch();
   JA_CUDA(cudaEventRecord(c->ev1, c->stream));

@@ -409,7 +409,8 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx)
             gb = bytes_per_n * (1 << log_n) / ms / 1e6
             sweep.append({"kernel": name, "log_n": log_n, "ms": round(ms, 4), "GBps": round(gb, 1), "frac_hbm": round(gb / hbm, 4)})
     # fused bind + evaluate round kernels: 48 n bytes per polynomial and launch; the mul-bound bodies also as Gmul/s
-    fused = ((0, "fused_round_add", 2, 24, 2 * 2 + 2), (1, "fused_round_mul", 2, 24, 4 + 2 * 2), (2, "fused_round_ident", 1, 24, 1 + 2),
+    fused = ((7, "fused_round_add_tma", 2, 24, 2 * 2 + 2), (7, "fused_round_add_tma", 2, 26, 2 * 2 + 2), (8, "fused_round_ident_tma", 1, 26, 1 + 2),
+             (0, "fused_round_add", 2, 24, 2 * 2 + 2), (1, "fused_round_mul", 2, 24, 4 + 2 * 2), (2, "fused_round_ident", 1, 24, 1 + 2),
              (6, "fused_round_open_h2l", 1, 24, 2 + 2), (3, "fused_round_product4", 4, 22, 16 + 4 + 4), (4, "fused_round_product16", 16, 20, 256 + 16 + 16),
              (5, "fused_round_booleanity16", 16, 20, 16 * 5 + 16 + 2))
     for which, name, npoly, log_n, muls_per_pair in fused:

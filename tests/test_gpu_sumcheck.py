@@ -105,3 +105,38 @@ def test_round_eval_prod_and_sums(ctx):
     assert got == [sum(zs[0][: n // 2]) % P]
     for p in ps:
         p.free()
+
+
+@pytest.mark.parametrize("kind_id,fam_ok,npoly,m", [(0, (0, 0), 2, 19), (1, (0, 1), 2, 18), (6, (0, 6), 1, 19)])
+def test_tma_staged_round_kernels_match_oracle(ctx, kind_id, fam_ok, npoly, m):
+    """Slabs of >= 2^16 pairs go through the TMA-staged kernel (csrc/tma_round.cuh): same proof as the C++ oracle and as
+    the register-staged kernel (JA_NO_TMA=1) on the same inputs."""
+    from jolt_atlas_b200 import Blake2bTranscriptState, MultilinearPolynomial, sumcheck_prove
+    rng = np.random.default_rng(kind_id * 100 + m)
+    polys = rng.integers(0, 1 << 63, size=(npoly, 1 << m, 4), dtype=np.uint64)
+    polys[..., 3] &= np.uint64((1 << 60) - 1)                                       # canonical: top limb < 2^60 < p's top limb
+    w = np.zeros((m, 4), dtype=np.uint64)
+    w[:, 2] = rng.integers(0, 1 << 63, size=m, dtype=np.uint64)
+    w[:, 3] = rng.integers(0, 1 << 61, size=m, dtype=np.uint64)
+    claim = polys[0, 0].copy()
+    want = ORC.sumcheck_prove(fam_ok[0], fam_ok[1], polys, w, claim, b"tma")
+    outs = []
+    for no_tma in (False, True):
+        if no_tma:
+            os.environ["JA_NO_TMA"] = "1"
+        try:
+            ps = [MultilinearPolynomial.from_fr(ctx, z) for z in polys]
+            t = Blake2bTranscriptState(b"tma")
+            res = sumcheck_prove(ctx, kind_id, ps, claim, t, eq_w=w)
+            for p in ps:
+                p.free()
+        finally:
+            os.environ.pop("JA_NO_TMA", None)
+        outs.append((res, t.state))
+    for res, state in outs:
+        assert len(res["coeffs"]) == m
+        for r in range(m):
+            assert np.array_equal(res["coeffs"][r], want["coeffs"][r]), r
+        assert np.array_equal(res["challenges"], want["challenges"])
+        assert np.array_equal(res["final_claims"], want["final_claims"])
+        assert state == want["state"]
