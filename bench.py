@@ -338,7 +338,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="nanoGPT", choices=["nanoGPT", "microgpt"])
+    ap.add_argument("--config", default="nanoGPT", choices=["nanoGPT", "microgpt", "gpt2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

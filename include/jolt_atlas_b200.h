@@ -192,6 +192,12 @@ int32_t ja_eval_reduction_h(ja_ctx*, const ja_poly* mle, const uint64_t* points,
  *   transpose==1: out[i] = sum_j from_i32(A[i*cols + j]) * eq[j]   (eq has `cols` entries, out has `rows`) */
 int32_t ja_tensor_fold_i32(ja_ctx*, const int32_t* A, size_t rows, size_t cols, const ja_poly* eq,
                            int32_t transpose, ja_poly** out);
+/* The same fold on a tensor kept on the device: model weights (and the node inputs the tracer hands to several provers,
+ * jolt-atlas-core/src/onnx_proof/ops/einsum/dot.rs:259-283) are uploaded once per proof / per preprocessing. */
+typedef struct ja_tensor_i32 ja_tensor_i32;
+int32_t ja_tensor_i32_upload(ja_ctx*, const int32_t* A, size_t rows, size_t cols, ja_tensor_i32** out);
+void ja_tensor_i32_free(ja_ctx*, ja_tensor_i32*);
+int32_t ja_tensor_fold_resident(ja_ctx*, const ja_tensor_i32* t, const ja_poly* eq, int32_t transpose, ja_poly** out);
 
 /* ---- SRS residency + MSM (commitment half) ---------------------------------------------------------
  * Scalar width tags of ja_msm_host == the variants VariableBaseMSM::msm dispatches on (joltworks/src/msm/mod.rs:27-181). */

@@ -47,6 +47,9 @@ SIGNATURES = {
     "ja_batched_sumcheck_prove": (C.c_int32, [vp, vp, C.c_size_t, C.c_char_p, u32p, C.c_size_t, u64p, u32p, u64p]),
     "ja_eval_reduction_h": (C.c_int32, [vp, vp, u64p, C.c_size_t, C.c_size_t, u64p, C.POINTER(C.c_size_t)]),
     "ja_tensor_fold_i32": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vp, C.c_int32, vpp]),
+    "ja_tensor_i32_upload": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vpp]),
+    "ja_tensor_i32_free": (None, [vp, vp]),
+    "ja_tensor_fold_resident": (C.c_int32, [vp, vp, vp, C.c_int32, vpp]),
     "ja_srs_upload": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
     "ja_srs_generate": (C.c_int32, [vp, u64p, u64p, C.c_size_t, vpp]),
     "ja_srs_precompute": (C.c_int32, [vp, vp]),

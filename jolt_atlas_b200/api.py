@@ -285,6 +285,28 @@ def tensor_fold_i32(ctx: Context, A, eq: MultilinearPolynomial, transpose: bool)
     return MultilinearPolynomial(ctx, h)
 
 
+class TensorI32:
+    """An i32 tensor (rows x cols) resident on the device: fold it with eq tables any number of times."""
+
+    def __init__(self, ctx: Context, A):
+        A = np.ascontiguousarray(A, dtype=np.int32)
+        assert A.ndim == 2
+        self.ctx, self.shape = ctx, A.shape
+        h = C.c_void_p()
+        check(ctx._lib.ja_tensor_i32_upload(ctx._h, A.ctypes.data_as(_lib.i32p), A.shape[0], A.shape[1], C.byref(h)))
+        self._h = h
+
+    def fold(self, eq: MultilinearPolynomial, transpose: bool) -> MultilinearPolynomial:
+        h = C.c_void_p()
+        check(self.ctx._lib.ja_tensor_fold_resident(self.ctx._h, self._h, eq._h, int(transpose), C.byref(h)))
+        return MultilinearPolynomial(self.ctx, h)
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_tensor_i32_free(self.ctx._h, self._h)
+            self._h = None
+
+
 # ---- commitment half: SRS residency, MSM, one-hot point sums (joltworks/src/msm/mod.rs, hyperkzg/) ----
 class MsmWidth:
     FR, U8, U16, U32, U64, I32, I64 = range(7)

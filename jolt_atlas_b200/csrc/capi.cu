@@ -1,5 +1,6 @@
 // C ABI implementation (include/jolt_atlas_b200.h): handle management, launch geometry, error mapping.
 // Kernels live in poly_kernels.cuh / msm_kernels.cuh.  No CPU fallback anywhere in this file.
+#include <memory>
 #include "common.hpp"
 #include "poly_kernels.cuh"
 
@@ -631,20 +632,10 @@ int32_t ja_poly_evaluate(ja_ctx* c, const ja_poly* p, const uint64_t* point, siz
 }
 
 // ---- tensor fold ---------------------------------------------------------------------------------------
-int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols, const ja_poly* eq,
-                           int32_t transpose, ja_poly** out) {
-  JA_REQUIRE(c && A && eq && out, "ja_tensor_fold_i32: null argument");
-  JA_REQUIRE(rows && cols, "ja_tensor_fold_i32: empty tensor");
-  JA_REQUIRE(eq->len >= (transpose ? cols : rows), "ja_tensor_fold_i32: eq table shorter than the folded axis");
+// core of the einsum operand fold on a device-resident tensor
+static int32_t tensor_fold_dev(ja_ctx* c, const int* dA, size_t rows, size_t cols, const ja_poly* eq, int32_t transpose, ja_poly** out) {
   const size_t out_n = transpose ? rows : cols;
-  JA_REQUIRE(is_pow2(out_n), "ja_tensor_fold_i32: output length must be a power of two");
-  std::lock_guard<std::recursive_mutex> lk(c->mu);
-  JA_CUDA(cudaSetDevice(c->device));
-  int* dA = nullptr;
-  int32_t st = dev_alloc(c, rows * cols * sizeof(int), (void**)&dA);
-  if (st) return st;
-  JA_CUDA(cudaMemcpyAsync(dA, A, rows * cols * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  st = ja_poly_alloc(c, out_n, out);
+  int32_t st = ja_poly_alloc(c, out_n, out);
   if (st) return st;
   if (transpose) {
     size_t threads = rows * 32;
@@ -664,9 +655,61 @@ int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols
     dev_free(c, partial);
   }
   JA_CUDA(cudaGetLastError());
-  dev_free(c, dA);
-  JA_CUDA(cudaStreamSynchronize(c->stream));
   return JA_OK;
+}
+
+int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols, const ja_poly* eq,
+                           int32_t transpose, ja_poly** out) {
+  JA_REQUIRE(c && A && eq && out, "ja_tensor_fold_i32: null argument");
+  JA_REQUIRE(rows && cols, "ja_tensor_fold_i32: empty tensor");
+  JA_REQUIRE(eq->len >= (transpose ? cols : rows), "ja_tensor_fold_i32: eq table shorter than the folded axis");
+  JA_REQUIRE(is_pow2(transpose ? rows : cols), "ja_tensor_fold_i32: output length must be a power of two");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  int* dA = nullptr;
+  int32_t st = dev_alloc(c, rows * cols * sizeof(int), (void**)&dA);
+  if (st) return st;
+  JA_CUDA(cudaMemcpyAsync(dA, A, rows * cols * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  st = tensor_fold_dev(c, dA, rows, cols, eq, transpose, out);
+  dev_free(c, dA);
+  if (st) return st;
+  JA_CUDA(cudaStreamSynchronize(c->stream));      // the host tensor is borrowed for the duration of the call only
+  return JA_OK;
+}
+
+// Model weights / activations of a node live on the device for the whole proof (they are inputs of several stages):
+// upload once, fold any number of times.
+struct ja_tensor_i32 {
+  int* data = nullptr;
+  size_t rows = 0, cols = 0;
+};
+int32_t ja_tensor_i32_upload(ja_ctx* c, const int32_t* A, size_t rows, size_t cols, ja_tensor_i32** out) {
+  JA_REQUIRE(c && A && out && rows && cols, "ja_tensor_i32_upload: null or empty argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  std::unique_ptr<ja_tensor_i32> t(new ja_tensor_i32());
+  t->rows = rows; t->cols = cols;
+  int32_t st = dev_alloc(c, rows * cols * sizeof(int), (void**)&t->data);
+  if (st) return st;
+  JA_CUDA(cudaMemcpyAsync(t->data, A, rows * cols * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  *out = t.release();
+  return JA_OK;
+}
+void ja_tensor_i32_free(ja_ctx* c, ja_tensor_i32* t) {
+  if (!c || !t) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  dev_free(c, t->data);
+  delete t;
+}
+int32_t ja_tensor_fold_resident(ja_ctx* c, const ja_tensor_i32* t, const ja_poly* eq, int32_t transpose, ja_poly** out) {
+  JA_REQUIRE(c && t && eq && out, "ja_tensor_fold_resident: null argument");
+  JA_REQUIRE(eq->len >= (transpose ? t->cols : t->rows), "ja_tensor_fold_resident: eq table shorter than the folded axis");
+  JA_REQUIRE(is_pow2(transpose ? t->rows : t->cols), "ja_tensor_fold_resident: output length must be a power of two");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  return tensor_fold_dev(c, t->data, t->rows, t->cols, eq, transpose, out);
 }
 
 // ---- measurement hooks ------------------------------------------------------------------------------------

@@ -441,9 +441,11 @@ struct OpenRow {
   unsigned int pad;
 };
 static __global__ void __launch_bounds__(kBlock)
-k_round_open_rows(const OpenRow* __restrict__ rows, unsigned int n_rows, Challenge r, Fr* partials /* [n_rows][gridDim.x] */,
+k_round_open_rows(const OpenRow* __restrict__ rows, unsigned int n_rows /* active rows of the round, all launches */,
+                  unsigned int row_off /* first row of this launch */, Challenge r, Fr* partials /* [gridDim.y][gridDim.x] */,
                   unsigned int* counters /* [n_rows] + 1 */, Fr* host_vals, volatile unsigned int* host_seq, unsigned int seq_value) {
-  const OpenRow row = rows[blockIdx.y];
+  const unsigned int ri = row_off + blockIdx.y;
+  const OpenRow row = rows[ri];
   const size_t half = (size_t)row.half;
   unsigned int nblk = (unsigned int)((half + kBlock - 1) / kBlock);
   if (nblk > gridDim.x) nblk = gridDim.x;
@@ -482,7 +484,7 @@ k_round_open_rows(const OpenRow* __restrict__ rows, unsigned int n_rows, Challen
     if (threadIdx.x == 0) fp_store(row_part + blockIdx.x, tot);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicInc(counters + blockIdx.y, nblk - 1) == nblk - 1;
+    if (threadIdx.x == 0) s_last = atomicInc(counters + ri, nblk - 1) == nblk - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();

@@ -14,6 +14,7 @@
 // K-entry tables stay on the host, cycle rounds on the device) and the Hamming-weight instance over the G tables
 // (hamming_weight.rs; K entries, host).  A Rust caller that owns the transcript can drive ja_round_eval / ja_bind_many
 // itself; this driver is the same protocol with the library's transcript.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <memory>
@@ -739,7 +740,7 @@ struct OpenBatch {
   OpenRow* d_rows = nullptr;
   Fr* d_partials = nullptr;
   unsigned int* d_counters = nullptr;
-  unsigned int gx = 1;
+  static constexpr unsigned long long kBigRowPairs = 1ull << 13;
   std::vector<OpenRow> rows;
   std::vector<OpenGroup*> active;
   size_t launched_round = ~size_t(0), pre_round = ~size_t(0), waited_round = ~size_t(0);
@@ -749,10 +750,10 @@ struct OpenBatch {
     total_rows = 0;
     for (OpenGroup* g : groups) { g->row_base = total_rows; total_rows += g->d; }
     JA_REQUIRE(total_rows <= (size_t)kMaxRowVals, "sumcheck: too many one-hot opening instances in one batch");
-    gx = (unsigned int)std::max<size_t>(1, std::min<size_t>(32, (size_t)kSMs * 8 / std::max<size_t>(1, total_rows)));
     int32_t st;
     if ((st = dev_alloc(c, total_rows * sizeof(OpenRow), (void**)&d_rows))) return st;
-    if ((st = dev_alloc(c, total_rows * gx * sizeof(Fr), (void**)&d_partials))) return st;
+    // partial sums of the two launches of a round (large rows, small rows): each has at most kSMs * 8 + rows entries
+    if ((st = dev_alloc(c, 2 * ((size_t)kSMs * 8 + total_rows) * sizeof(Fr), (void**)&d_partials))) return st;
     if ((st = dev_alloc(c, (total_rows + 1) * sizeof(unsigned int), (void**)&d_counters))) return st;
     JA_CUDA(cudaMemsetAsync(d_counters, 0, (total_rows + 1) * sizeof(unsigned int), c->stream));
     return JA_OK;
@@ -787,6 +788,12 @@ struct OpenBatch {
       if (fz) { for (ja_poly* p : g->H) p->len = len_eval; g->pending = false; }
     }
     if (rows.empty()) return JA_OK;
+    // Rows of very different lengths share a batch (GPT-2: 2^12 ... 2^20 per polynomial): the long rows go out first with
+    // many blocks each, the short ones in a second launch with few, so that neither idles the GPU nor floods it with
+    // blocks that have nothing to do.
+    std::stable_partition(rows.begin(), rows.end(), [](const OpenRow& r) { return r.half >= kBigRowPairs; });
+    size_t n_big = 0;
+    while (n_big < rows.size() && rows[n_big].half >= kBigRowPairs) n_big++;
     // the counters wrap back to zero by themselves (atomicInc), except the "rows done" word whose modulus changes with
     // the number of active rows: it sits right after the active rows' counters, freshly zeroed territory each time
     JA_REQUIRE(rows.size() * sizeof(OpenRow) <= kPinnedBytes, "sumcheck: opening row table too large for the staging buffer");
@@ -795,8 +802,26 @@ struct OpenBatch {
     seq = ++c->seq;
     Fr* hv = reinterpret_cast<Fr*>(c->d_rowvals);
     volatile unsigned int* hs = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<char*>(c->d_rowvals) + kRowSeqOffset);
-    JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open_rows<<<dim3(gx, (unsigned int)rows.size()), kBlock, 0, c->stream>>>(
-                  d_rows, (unsigned int)rows.size(), to_challenge(ch_limbs), d_partials, d_counters, hv, hs, seq));
+    const unsigned int n_all = (unsigned int)rows.size();
+    auto blocks_per_row = [](size_t n_rows, size_t max_half) {
+      size_t g = ((size_t)kSMs * 8 + n_rows - 1) / n_rows;
+      const size_t need = (max_half + kBlock - 1) / kBlock;
+      g = std::min(g, need);
+      return (unsigned int)std::max<size_t>(1, std::min<size_t>(g, 65535));
+    };
+    if (n_big) {
+      size_t max_half = 0;
+      for (size_t i = 0; i < n_big; i++) max_half = std::max(max_half, (size_t)rows[i].half);
+      const unsigned int gxa = blocks_per_row(n_big, max_half);
+      JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open_rows<<<dim3(gxa, (unsigned int)n_big), kBlock, 0, c->stream>>>(
+                    d_rows, n_all, 0u, to_challenge(ch_limbs), d_partials, d_counters, hv, hs, seq));
+    }
+    if (n_big < rows.size()) {
+      const size_t n_small = rows.size() - n_big;
+      const unsigned int gxb = blocks_per_row(n_small, (size_t)kBigRowPairs);
+      JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open_rows<<<dim3(gxb, (unsigned int)n_small), kBlock, 0, c->stream>>>(
+                    d_rows, n_all, (unsigned int)n_big, to_challenge(ch_limbs), d_partials + ((size_t)kSMs * 8 + total_rows), d_counters, hv, hs, seq));
+    }
     JA_CUDA(cudaGetLastError());
     return JA_OK;
   }

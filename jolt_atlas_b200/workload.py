@@ -72,9 +72,30 @@ def microgpt_nodes() -> list[NodeSpec]:
     ]
 
 
+def gpt2_nodes() -> list[NodeSpec]:
+    """GPT-2 125M at seq_len 16 (n_embd 768, 12 heads, 12 layers, vocab 50257 -> 65536; jolt-atlas-core/examples/gpt2.rs:86-112,
+    README.md:139).  Output counts are padded to powers of two as the tracer does (atlas-onnx-tracer/src/model/mod.rs:273-300):
+    16 x 2304 -> 2^16, 16 x 768 -> 2^14, 16 x 3072 -> 2^16, logits 16 x 65536 = 2^20 (=> committed polynomials up to 2^24).
+    Contraction lengths 768 / 3072 are zero-padded to 1024 / 4096."""
+    layer = [
+        NodeSpec("einsum", 16, 16, 768, 2304),    # qkv projection
+        NodeSpec("einsum", 12, 192, 64, 16),      # 12 heads x (16x64 . 64x16) scores
+        NodeSpec("mul", 12),                      # softmax-side elementwise product
+        NodeSpec("einsum", 14, 192, 16, 64),      # 12 heads x (16x16 . 16x64)
+        NodeSpec("einsum", 14, 16, 768, 768),     # output projection
+        NodeSpec("add", 14),                      # residual
+        NodeSpec("einsum", 16, 16, 768, 3072),    # MLP up
+        NodeSpec("mul", 16),                      # activation-side product
+        NodeSpec("einsum", 14, 16, 3072, 768),    # MLP down
+        NodeSpec("add", 14),                      # residual
+    ]
+    return layer * 12 + [NodeSpec("einsum", 20, 16, 768, 65536)]   # lm_head
+
+
 CONFIGS = {
     "microgpt": {"nodes": microgpt_nodes, "ell": 14, "seed": 0x42},
     "nanoGPT": {"nodes": nanogpt_nodes, "ell": 18, "seed": 0x1096},
+    "gpt2": {"nodes": gpt2_nodes, "ell": 24, "seed": 42},
 }
 
 
@@ -124,8 +145,11 @@ def build_inputs(config: str, seed: int | None = None):
                         tables=np.stack([_challenges(rng, K_CHUNK) for _ in range(d_hot)]),
                         eq_w=_challenges(rng, spec.log_t), gammas=_challenges(rng, d_hot), r_addr=_challenges(rng, LOG_K))
         if spec.kind == "einsum":
-            ni.A = rng.integers(-128, 128, size=(spec.m, spec.k), dtype=np.int32)
-            ni.B = rng.integers(-128, 128, size=(spec.k, spec.n), dtype=np.int32)
+            kp = 1 << (spec.k - 1).bit_length()            # contraction axis zero-padded to a power of two (MLE length)
+            ni.A = np.zeros((spec.m, kp), dtype=np.int32)
+            ni.B = np.zeros((kp, spec.n), dtype=np.int32)
+            ni.A[:, :spec.k] = rng.integers(-128, 128, size=(spec.m, spec.k), dtype=np.int32)
+            ni.B[:spec.k] = rng.integers(-128, 128, size=(spec.k, spec.n), dtype=np.int32)
             ni.eq_rows = _challenges(rng, (spec.m - 1).bit_length())
             ni.eq_cols = _challenges(rng, (spec.n - 1).bit_length())
         else:
@@ -212,8 +236,11 @@ def run_device(ctx, srs, inputs, resident=None):
             # EinsumDotProver::initialize (einsum/dot.rs:259-283): fold both operands with the eq tables, then log k dot rounds
             eq_r = A.EqPolynomial.evals(ctx, ni.eq_rows)
             eq_c = A.EqPolynomial.evals(ctx, ni.eq_cols)
-            left = A.tensor_fold_i32(ctx, ni.A, eq_r, transpose=False)     # (m x k) folded over rows -> k
-            right = A.tensor_fold_i32(ctx, ni.B, eq_c, transpose=True)     # (k x n) folded over columns -> k
+            if res:                                                        # weights / node inputs resident on the device
+                left, right = res["A"].fold(eq_r, transpose=False), res["B"].fold(eq_c, transpose=True)
+            else:
+                left = A.tensor_fold_i32(ctx, ni.A, eq_r, transpose=False)     # (m x k) folded over rows -> k
+                right = A.tensor_fold_i32(ctx, ni.B, eq_c, transpose=True)     # (k x n) folded over columns -> k
             _sc(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
             for q in (eq_r, eq_c, left, right):
                 q.free()
@@ -276,6 +303,9 @@ def make_resident(ctx, inputs):
         if ni.spec.kind != "einsum":
             d["A"] = A.MultilinearPolynomial.from_i32(ctx, ni.A)
             d["B"] = A.MultilinearPolynomial.from_i32(ctx, ni.B)
+        else:
+            d["A"] = A.TensorI32(ctx, ni.A)
+            d["B"] = A.TensorI32(ctx, ni.B)
         nodes.append(d)
     return {"nodes": nodes}
 
