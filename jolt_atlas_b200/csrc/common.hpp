@@ -111,11 +111,18 @@ struct ja_poly {
 struct ja_srs {
   G1Aff* points = nullptr;   // g1_powers, affine Montgomery (kzg.rs:108-143 KZGProverKey)
   size_t n = 0;
-  // Fixed-base window table (ja_srs_precompute): table[w * n + i] = 2^(16 w) * g1_powers[i], w = 0..15 (table[0..n) is a
+  // Fixed-base window table (ja_srs_precompute): table[w * n + i] = 2^(c w) * g1_powers[i], w = 0..nwin-1 (table[0..n) is a
   // copy of the SRS).  With it a full-width MSM needs ONE bucket set instead of one per window and no doubling tail.
+  // c = table_c is chosen per SRS size: wider windows mean fewer additions per scalar (nwin = ceil(255 / c)) but need
+  // jobs long enough to fill 2^(c-1) buckets.
   G1Aff* table = nullptr;
+  uint32_t table_c = 16, table_nwin = 16;
+  // Large SRS (>= 2^21 points): a second, wider-window table for the long jobs, stored right behind the first one
+  // (table[table2_off + w * n + i] = 2^(table2_c w) * g1_powers[i]); 0 = absent.  Measured on B200 (profiles/
+  // r1_msm_table_probe_*.json): c = 20 takes a 2^24 MSM from 57.7 to 44.1 ms, but a 2^18 job is faster with c = 16.
+  uint32_t table2_off = 0, table2_c = 0, table2_nwin = 0;
 };
-constexpr uint32_t kFixedWindowBits = 16, kFixedWindows = 16;
+constexpr uint32_t kMaxFixedWindows = 22;
 
 struct ja_onehot {
   uint64_t* d_indices = nullptr;        // concatenated base indices k*T + t of every list

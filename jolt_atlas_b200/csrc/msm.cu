@@ -24,12 +24,21 @@ static uint32_t pick_window(size_t n, uint32_t nbits) {
   return best_c;
 }
 
-// Jobs shorter than this keep per-window buckets: with c = 16 their 2^15 buckets would hold < ~1 entry each and the
+// Jobs shorter than the table's bucket count keep per-window buckets: their buckets would hold < ~1 entry each and the
 // accumulate pass degenerates into bucket flushes (measured: HyperKZG phase-1 batch 1.3 -> 5 ms when every folded
 // polynomial went through the table).
-static size_t table_min_n() {
+static size_t table_min_n(const ja_srs* srs) {
   if (const char* e = getenv("JA_MSM_TABLE_MIN_LOG")) { int v = atoi(e); if (v >= 0 && v <= 40) return size_t(1) << v; }
-  return size_t(1) << 15;
+  return size_t(1) << (srs->table_c - 1);
+}
+// the wider second table: window bits (JA_MSM_TABLE2_C overrides, 0 disables) and the shortest job that uses it
+static uint32_t table2_window_bits(size_t n) {
+  if (const char* e = getenv("JA_MSM_TABLE2_C")) { int v = atoi(e); if (v == 0 || (v >= 12 && v <= 22)) return (uint32_t)v; }
+  return n >= (size_t(1) << 21) ? 20u : 0u;
+}
+static size_t table2_min_n(const ja_srs* srs) {
+  if (const char* e = getenv("JA_MSM_TABLE2_MIN_LOG")) { int v = atoi(e); if (v >= 0 && v <= 40) return size_t(1) << v; }
+  return size_t(1) << (srs->table2_c + 1);
 }
 
 static uint32_t run_length() {
@@ -91,11 +100,14 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   for (uint32_t m = 0; m < count; m++) {
     const MsmJob& j = jobs[m];
     MsmDesc& d = descs[m];
-    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.fixed_stride = 0;
+    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.fixed_stride = 0; d.table_off = 0;
     if (j.kind == MSM_INDEXED) { d.c = 1; d.nwin = 1; d.nb = 1; }
-    else if (j.kind == MSM_FR && srs->table && j.n >= table_min_n()) {
-      // fixed-base window table: c = 16, 16 windows, ONE bucket set
-      d.c = kFixedWindowBits; d.nwin = kFixedWindows; d.nb = 1u << (kFixedWindowBits - 1);
+    else if (j.kind == MSM_FR && srs->table && srs->table2_c && j.n >= table2_min_n(srs)) {
+      d.c = srs->table2_c; d.nwin = srs->table2_nwin; d.nb = 1u << (srs->table2_c - 1);
+      d.fixed_stride = (uint32_t)srs->n; d.table_off = srs->table2_off;
+    } else if (j.kind == MSM_FR && srs->table && j.n >= table_min_n(srs)) {
+      // fixed-base window table: nwin windows of c bits, ONE bucket set
+      d.c = srs->table_c; d.nwin = srs->table_nwin; d.nb = 1u << (srs->table_c - 1);
       d.fixed_stride = (uint32_t)srs->n;
     } else {
       d.c = pick_window(j.n, j.nbits);
@@ -302,12 +314,20 @@ size_t ja_srs_len(const ja_srs* s) { return s ? s->n : 0; }
 int32_t ja_srs_precompute(ja_ctx* c, ja_srs* s) {
   JA_REQUIRE(c && s, "ja_srs_precompute: null argument");
   if (s->table) return JA_OK;
-  JA_REQUIRE((uint64_t)s->n * kFixedWindows < (1ull << 31), "ja_srs_precompute: SRS too large for 31-bit table indices");
+  const uint32_t tc = 16, tw = (254 + 1 + tc - 1) / tc;
+  const uint32_t tc2 = table2_window_bits(s->n), tw2 = tc2 ? (254 + 1 + tc2 - 1) / tc2 : 0;
+  JA_REQUIRE(tw <= kMaxFixedWindows && tw2 <= kMaxFixedWindows && (uint64_t)s->n * (tw + tw2) < (1ull << 31),
+             "ja_srs_precompute: SRS too large for 31-bit table indices");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->n * kFixedWindows * sizeof(G1Aff));
+  cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->n * (tw + tw2) * sizeof(G1Aff));
   if (e != cudaSuccess) { s->table = nullptr; cudaGetLastError(); return fail(JA_ERR_CUDA, std::string("ja_srs_precompute: ") + cudaGetErrorString(e)); }
-  JA_LAUNCH(c, KC_SRS, k_srs_window_table<<<ceil_div_u32(s->n, 128), 128, 0, c->stream>>>(s->points, (uint32_t)s->n, s->table));
+  s->table_c = tc; s->table_nwin = tw;
+  JA_LAUNCH(c, KC_SRS, k_srs_window_table<<<ceil_div_u32(s->n, 128), 128, 0, c->stream>>>(s->points, (uint32_t)s->n, s->table, (int)tc, (int)tw));
+  if (tc2) {
+    s->table2_c = tc2; s->table2_nwin = tw2; s->table2_off = (uint32_t)(s->n * tw);
+    JA_LAUNCH(c, KC_SRS, k_srs_window_table<<<ceil_div_u32(s->n, 128), 128, 0, c->stream>>>(s->points, (uint32_t)s->n, s->table + s->table2_off, (int)tc2, (int)tw2));
+  }
   JA_CUDA(cudaGetLastError());
   JA_CUDA(cudaStreamSynchronize(c->stream));
   return JA_OK;

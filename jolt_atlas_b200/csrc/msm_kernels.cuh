@@ -48,7 +48,8 @@ struct MsmDesc {
   uint32_t entry_base;   // prefix sum of n over the batch (thread -> msm lookup)
   uint32_t base_offset;  // SRS index of base 0 (ignored for MSM_INDEXED)
   uint32_t fixed_stride; // != 0: fixed-base window table in use (stride = SRS length): every window shares ONE bucket set and
-                         // digit w of scalar j selects base w * stride + j (= 2^(c w) * G_j); 0: classic per-window buckets
+                         // digit w of scalar j selects base table_off + w * stride + j (= 2^(c w) * G_j); 0: classic per-window buckets
+  uint32_t table_off;    // first entry of the window table this job uses (0 unless fixed_stride != 0)
 };
 
 constexpr uint32_t kSignBit = 0x80000000u;
@@ -124,7 +125,7 @@ JA_DEV bool msm_digit(const MsmDesc& d, MsmDigitIter& it, uint32_t w, uint32_t& 
   if (raw > nb) { raw = full - raw; it.carry = 1; dneg = true; } else it.carry = 0;
   if (!raw) return false;
   key = d.bucket_base + (d.fixed_stride ? 0u : w * nb) + (raw - 1);
-  payload = (it.base + w * d.fixed_stride) | ((dneg != it.neg) ? kSignBit : 0u);
+  payload = (it.base + d.table_off + w * d.fixed_stride) | ((dneg != it.neg) ? kSignBit : 0u);
   return true;
 }
 
@@ -454,23 +455,23 @@ JA_DEV Fr fr_pow_u32(const Fr& b, uint32_t e) {
   return r;
 }
 
-// Fixed-base window table: table[w * n + i] = 2^(16 w) * P_i.  One thread per point: 15 x 16 doublings in XYZZ, then the
-// 15 multiples are normalised with one shared inversion (Montgomery's trick).
+// Fixed-base window table: table[w * n + i] = 2^(c w) * P_i, w < nwin <= 22.  One thread per point: (nwin - 1) x c doublings
+// in XYZZ, then the multiples are normalised with one shared inversion (Montgomery's trick).
 static __global__ void __launch_bounds__(128)
-k_srs_window_table(const G1Aff* __restrict__ points, uint32_t n, G1Aff* __restrict__ table) {
+k_srs_window_table(const G1Aff* __restrict__ points, uint32_t n, G1Aff* __restrict__ table, int c, int nwin) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const G1Aff p = g1aff_load(points + i);
   fp_store(&table[i].x, p.x); fp_store(&table[i].y, p.y);
   G1X cur = g1x_from_aff(p);
-  // pass 1: walk the doubling chain, keeping the running product of the denominators ZZ * ZZZ in global scratch-free form:
-  // store the XYZZ multiples temporarily in the table slots (x <- X, y <- Y) and their denominators' prefix products in regs
-  Fq pre[15], den[15];
+  // pass 1: walk the doubling chain; the XYZZ multiples wait in their table slots (x <- X * ZZZ, y <- Y * ZZ) and the prefix
+  // products of their denominators ZZ * ZZZ in local arrays
+  Fq pre[21], den[21];
   Fq run = fp_one<FqParams>();
 #pragma unroll 1
-  for (int w = 1; w < 16; w++) {
+  for (int w = 1; w < nwin; w++) {
 #pragma unroll 1
-    for (int k = 0; k < 16; k++) cur = g1x_dbl(cur);
+    for (int k = 0; k < c; k++) cur = g1x_dbl(cur);
     // X / ZZ and Y / ZZZ need 1 / (ZZ * ZZZ): x = X * ZZZ * inv, y = Y * ZZ * inv
     fp_store(&table[(size_t)w * n + i].x, fq_mul(cur.X, cur.ZZZ));
     fp_store(&table[(size_t)w * n + i].y, fq_mul(cur.Y, cur.ZZ));
@@ -480,7 +481,7 @@ k_srs_window_table(const G1Aff* __restrict__ points, uint32_t n, G1Aff* __restri
   }
   Fq inv = fq_inv(run);
 #pragma unroll 1
-  for (int w = 15; w >= 1; w--) {
+  for (int w = nwin - 1; w >= 1; w--) {
     const Fq di = fq_mul(inv, pre[w - 1]);
     inv = fq_mul(inv, den[w - 1]);
     G1Aff* dst = table + (size_t)w * n + i;
