@@ -84,7 +84,7 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   JA_CUDA(cudaMalloc(&c->d_counter, 64 * sizeof(unsigned int)));
   JA_CUDA(cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int)));
   JA_CUDA(cudaMalloc(&c->d_out, sizeof(Fr) * kMaxOut));
-  JA_CUDA(cudaMallocHost(&c->h_pinned, kPinnedBytes));
+  JA_CUDA(cudaHostAlloc((void**)&c->h_pinned, kPinnedBytes, cudaHostAllocMapped));   // device-addressable: k_collect_finals stores into it
   JA_CUDA(cudaMallocHost((void**)&c->h_ring, kRingBytes));
   JA_CUDA(cudaHostAlloc(&c->h_mapped, kSlots * kSlotBytes, cudaHostAllocMapped));
   memset(c->h_mapped, 0, kSlots * kSlotBytes);

@@ -74,6 +74,9 @@ struct ja_ctx {
   // whose pool growth showed up as sporadic 100-500 ms stalls (profiles/r1_pass_time_distribution.txt).
   std::unordered_map<void*, size_t> alloc_class;
   std::unordered_map<size_t, std::vector<void*>> free_blocks;
+  // final-claim collector of the sumcheck engine: (device source, pinned host destination) of single field elements,
+  // flushed by ONE small kernel per 32 entries that stores straight into the pinned staging buffer
+  std::vector<std::pair<const void*, void*>> collect;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-kernel-class CUDA-event profile (ja_profile_begin / ja_profile_end; bench.py's roofline leg)

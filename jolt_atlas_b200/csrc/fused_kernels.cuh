@@ -29,6 +29,17 @@ JA_DEV void publish_flag(const Publish& pub) {
   }
 }
 
+// Final MLE claims of a batch: up to 32 single field elements scattered over device buffers -> pinned host memory
+// (device-addressable under unified addressing) in one launch instead of one 32-byte cudaMemcpyAsync each.
+struct CollectArgs {
+  const Fr* src[32];
+  Fr* dst[32];
+};
+static __global__ void __launch_bounds__(64) k_collect_finals(CollectArgs a, int n) {
+  const int i = threadIdx.x >> 1, h = threadIdx.x & 1;
+  if (i < n) reinterpret_cast<uint4*>(a.dst[i])[h] = __ldg(reinterpret_cast<const uint4*>(a.src[i]) + h);
+}
+
 struct FusedPolys {
   const Fr* in[kMaxProdPolys];
   Fr* out[kMaxProdPolys];        // FUSED only: bound arrays (LowToHigh: other ping-pong buffer; HighToLow: == in)

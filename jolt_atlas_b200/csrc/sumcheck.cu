@@ -100,6 +100,22 @@ int32_t launch_round_s_tma(ja_ctx* c, int kind, const FusedPolys& P, const Chall
   return JA_OK;
 }
 
+// final-claim collector (ja_ctx::collect): one launch per 32 (source, pinned destination) pairs
+int32_t flush_collect(ja_ctx* c) {
+  for (size_t base = 0; base < c->collect.size(); base += 32) {
+    CollectArgs a;
+    const int n = (int)std::min<size_t>(32, c->collect.size() - base);
+    for (int i = 0; i < 32; i++) {
+      a.src[i] = i < n ? reinterpret_cast<const Fr*>(c->collect[base + i].first) : nullptr;
+      a.dst[i] = i < n ? reinterpret_cast<Fr*>(c->collect[base + i].second) : nullptr;
+    }
+    JA_LAUNCH(c, KC_BIND, k_collect_finals<<<1, 64, 0, c->stream>>>(a, n));
+  }
+  c->collect.clear();
+  JA_CUDA(cudaGetLastError());
+  return JA_OK;
+}
+
 // ---- host-mapped result slots ------------------------------------------------------------------------------------
 struct Slot {
   const uint64_t* host_vals = nullptr;
@@ -544,7 +560,7 @@ struct DevInst : Inst {
     }
     for (size_t i = 0; i < polys.size(); i++) {
       JA_REQUIRE(polys[i]->len == 1, "sumcheck: polynomial not fully bound at the end of the protocol");
-      JA_CUDA(cudaMemcpyAsync(staging + 4 * i, polys[i]->data(), sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+      c->collect.push_back({polys[i]->data(), staging + 4 * i});
     }
     *count = polys.size();
     return JA_OK;
@@ -906,7 +922,7 @@ struct OpenMember : Inst {
     int32_t st = g->finalize(c);
     if (st) return st;
     JA_REQUIRE(g->H[i]->len == 1, "sumcheck: one-hot opening not fully bound");
-    JA_CUDA(cudaMemcpyAsync(staging, g->H[i]->data(), sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+    c->collect.push_back({g->H[i]->data(), staging});
     *count = 1;
     return JA_OK;
   }
@@ -1106,6 +1122,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   }
   // final claims: flush the deferred binds, ONE synchronisation for the whole batch
   uint64_t* staging = c->h_pinned;
+  c->collect.clear();
   std::vector<std::pair<size_t, size_t>> span(n);
   size_t used = 0;
   for (size_t k = 0; k < n; k++) {
@@ -1115,6 +1132,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     used += cnt;
     JA_REQUIRE(used * 32 <= kPinnedBytes, "sumcheck: too many final claims for the staging buffer");
   }
+  if ((st = flush_collect(c))) return st;
   JA_CUDA(cudaStreamSynchronize(c->stream));
   for (size_t k = 0; k < n; k++)
     if (insts[k]->out_final) memcpy(insts[k]->out_final, staging + 4 * span[k].first, span[k].second * 32);
@@ -1130,6 +1148,7 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
   JA_CUDA(cudaSetDevice(c->device));
   std::vector<std::unique_ptr<Inst>> insts;
   int32_t st = JA_OK;
+  const auto t_enter = std::chrono::steady_clock::now();
   for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts);
   int next_slot = 0;
   for (auto& i : insts) if (i->needs_slot()) i->slot_id = next_slot++;
@@ -1140,10 +1159,17 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
       if (om->i == 0) { ob.groups.push_back(om->g.get()); om->g->batch = &ob; }
   if (!st && !ob.groups.empty()) st = ob.init(c);
   host::Blake2bTranscript t(transcript_state, *n_rounds_io);
+  const auto t_built = std::chrono::steady_clock::now();
   if (!st) st = prove_loop(c, insts, batched, t, max_coeffs, out_coeffs, out_ncoeffs, out_challenges, ob.groups.empty() ? nullptr : &ob);
+  const auto t_proved = std::chrono::steady_clock::now();
   if (st) cudaStreamSynchronize(c->stream);      // nothing of this call may still be in flight when the handles are released
   for (auto& i : insts) if (i) i->release(c);
   ob.release(c);
+  if (g_trace.on) {
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    fprintf(stderr, "[sc-call n=%zu] build=%.0f us loop=%.0f us release=%.0f us\n", n, us(t_enter, t_built), us(t_built, t_proved),
+            us(t_proved, std::chrono::steady_clock::now()));
+  }
   if (st) return st;
   memcpy(transcript_state, t.state, 32);
   *n_rounds_io = t.n_rounds;
