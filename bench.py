@@ -235,6 +235,8 @@ def run_device_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # host worker threads of the library (large-batch glue): split the box's cores between the ranks
+    os.environ.setdefault("JA_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // world))))
     ctx = Context(local)
     # independent proofs per rank (weak scaling: the path has no cross-proof exchange); see DESIGN.md §Multi-GPU
     inputs = W.build_inputs(args.config, seed=None if rank == 0 else W.CONFIGS[args.config]["seed"] + rank)

@@ -19,7 +19,7 @@ LIB = os.path.join(LIBDIR, "libjolt_atlas_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fopenmp",
     "--expt-relaxed-constexpr",
 ]
 
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {cu}:\n{out}")
         if verbose and out:
             print(out, file=sys.stderr)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lgomp"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

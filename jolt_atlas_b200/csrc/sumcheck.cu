@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 
 #include "common.hpp"
 #include "fused_kernels.cuh"
@@ -28,6 +29,16 @@
 using host::Coeffs;
 
 namespace {
+
+// worker threads for the host-side glue of large batches: JA_HOST_THREADS, else min(8, hardware threads)
+int host_threads() {
+  static const int n = [] {
+    if (const char* e = getenv("JA_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 256) return v; }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+  }();
+  return n;
+}
 
 // JA_SC_TRACE=1: per-phase host wall-clock of the round loop on stderr (tuning aid)
 struct ScTrace {
@@ -756,6 +767,7 @@ struct OpenBatch {
   OpenRow* d_rows = nullptr;
   Fr* d_partials = nullptr;
   unsigned int* d_counters = nullptr;
+  Fr* d_vals = nullptr;                                 // row sums of the round on the device (shipped to the host in one burst)
   static constexpr unsigned long long kBigRowPairs = 1ull << 13;
   std::vector<OpenRow> rows;
   std::vector<OpenGroup*> active;
@@ -771,6 +783,8 @@ struct OpenBatch {
     // partial sums of the two launches of a round (large rows, small rows): each has at most kSMs * 8 + rows entries
     if ((st = dev_alloc(c, 2 * ((size_t)kSMs * 8 + total_rows) * sizeof(Fr), (void**)&d_partials))) return st;
     if ((st = dev_alloc(c, (total_rows + 1) * sizeof(unsigned int), (void**)&d_counters))) return st;
+    if ((st = dev_alloc(c, total_rows * sizeof(Fr), (void**)&d_vals))) return st;
+    JA_CUDA(cudaMemsetAsync(d_vals, 0, total_rows * sizeof(Fr), c->stream));
     JA_CUDA(cudaMemsetAsync(d_counters, 0, (total_rows + 1) * sizeof(unsigned int), c->stream));
     return JA_OK;
   }
@@ -830,13 +844,14 @@ struct OpenBatch {
       for (size_t i = 0; i < n_big; i++) max_half = std::max(max_half, (size_t)rows[i].half);
       const unsigned int gxa = blocks_per_row(n_big, max_half);
       JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open_rows<<<dim3(gxa, (unsigned int)n_big), kBlock, 0, c->stream>>>(
-                    d_rows, n_all, 0u, to_challenge(ch_limbs), d_partials, d_counters, hv, hs, seq));
+                    d_rows, n_all, 0u, to_challenge(ch_limbs), d_partials, d_counters, d_vals, (unsigned int)total_rows, hv, hs, seq));
     }
     if (n_big < rows.size()) {
       const size_t n_small = rows.size() - n_big;
       const unsigned int gxb = blocks_per_row(n_small, (size_t)kBigRowPairs);
       JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_open_rows<<<dim3(gxb, (unsigned int)n_small), kBlock, 0, c->stream>>>(
-                    d_rows, n_all, (unsigned int)n_big, to_challenge(ch_limbs), d_partials + ((size_t)kSMs * 8 + total_rows), d_counters, hv, hs, seq));
+                    d_rows, n_all, (unsigned int)n_big, to_challenge(ch_limbs), d_partials + ((size_t)kSMs * 8 + total_rows), d_counters, d_vals,
+                    (unsigned int)total_rows, hv, hs, seq));
     }
     JA_CUDA(cudaGetLastError());
     return JA_OK;
@@ -882,8 +897,8 @@ struct OpenBatch {
     return JA_OK;
   }
   void release(ja_ctx* c) {
-    dev_free(c, d_rows); dev_free(c, d_partials); dev_free(c, d_counters);
-    d_rows = nullptr; d_partials = nullptr; d_counters = nullptr;
+    dev_free(c, d_rows); dev_free(c, d_partials); dev_free(c, d_counters); dev_free(c, d_vals);
+    d_rows = nullptr; d_partials = nullptr; d_counters = nullptr; d_vals = nullptr;
   }
 };
 
@@ -1037,6 +1052,13 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   if (batched) for (size_t k = 0; k < n; k++) coeffs[k] = t.challenge_scalar();           // :48 challenge_vector
   for (size_t k = 0; k < n; k++) claims[k] = batched ? mul_pow_2(insts[k]->claim, max_rounds - insts[k]->rounds) : insts[k]->claim;
   int32_t st;
+  // Host threads for the per-instance glue of LARGE batches (the opening reduction has one instance per committed
+  // polynomial: 756 for nanoGPT, 2340 for GPT-2; ~20 field products per instance and round).  Only the one-hot opening
+  // members run in parallel: their message() reads shared group state and nothing else.
+  std::vector<char> is_open(n, 0);
+  size_t n_open = 0;
+  for (size_t k = 0; k < n; k++) if (dynamic_cast<OpenMember*>(insts[k].get())) { is_open[k] = 1; n_open++; }
+  const int nth = n_open >= 128 ? host_threads() : 1;
   g_trace.start();
   for (size_t round = 0; round < max_rounds; round++) {
     const size_t remaining = max_rounds - round;
@@ -1091,17 +1113,48 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
       if (remaining <= insts[k]->rounds && (st = insts[k]->prework(c, round - (max_rounds - insts[k]->rounds)))) return st;
     g_trace.lap(0);
     for (size_t k = 0; k < n; k++) {
+      if (nth > 1 && is_open[k]) continue;
       const size_t nr = insts[k]->rounds;
       if (remaining > nr) unis[k] = host::trim({mul_pow_2(insts[k]->claim, remaining - nr - 1)});    // :96-106
       else if ((st = insts[k]->message(c, round - (max_rounds - nr), claims[k], &unis[k]))) return st;
     }
-    g_trace.lap(1);
     Coeffs uni;
-    if (batched) {
+    if (nth > 1) {
+      if (ob && (st = ob->wait(c, round))) return st;          // the members below only read the collected row sums
+      int32_t first_err = JA_OK;
       uni = host::trim({});
-      for (size_t k = 0; k < n; k++) add_assign(uni, scaled(unis[k], coeffs[k]));          // :113-121
+#pragma omp parallel num_threads(nth)
+      {
+        Coeffs local = host::trim({});
+#pragma omp for schedule(static)
+        for (long k = 0; k < (long)n; k++) {
+          if (is_open[k]) {
+            const size_t nr = insts[k]->rounds;
+            int32_t e = JA_OK;
+            if (remaining > nr) unis[k] = host::trim({mul_pow_2(insts[k]->claim, remaining - nr - 1)});
+            else e = insts[k]->message(c, round - (max_rounds - nr), claims[k], &unis[k]);
+            if (e) {
+#pragma omp critical(ja_sc_err)
+              first_err = e;
+              continue;
+            }
+          }
+          if (batched) add_assign(local, scaled(unis[k], coeffs[k]));                      // :113-121
+        }
+#pragma omp critical(ja_sc_sum)
+        add_assign(uni, local);
+      }
+      if (first_err) return fail(first_err, "sumcheck: a one-hot opening instance failed in a worker thread");
+      g_trace.lap(1);
+      if (!batched) uni = unis[0];
     } else {
-      uni = unis[0];
+      g_trace.lap(1);
+      if (batched) {
+        uni = host::trim({});
+        for (size_t k = 0; k < n; k++) add_assign(uni, scaled(unis[k], coeffs[k]));        // :113-121
+      } else {
+        uni = unis[0];
+      }
     }
     const Coeffs cp = host::compress(uni);
     if (cp.size() > max_coeffs) return fail(JA_ERR_INVALID, "sumcheck: max_coeffs too small");
@@ -1111,7 +1164,8 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     uint64_t ch[4];
     t.challenge_scalar_optimized(ch);                                                      // :126 / :586
     const FrH r = host::from_limbs(ch);
-    for (size_t k = 0; k < n; k++) claims[k] = host::evaluate(unis[k], r);                 // :130-134 / :589
+#pragma omp parallel for schedule(static) num_threads(nth) if (nth > 1)
+    for (long k = 0; k < (long)n; k++) claims[k] = host::evaluate(unis[k], r);             // :130-134 / :589
     g_trace.lap(2);
     for (size_t k = 0; k < n; k++)
       if (remaining <= insts[k]->rounds && (st = insts[k]->ingest(c, ch, round - (max_rounds - insts[k]->rounds)))) return st;
