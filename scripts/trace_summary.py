@@ -1,7 +1,7 @@
 """Summarise a JA_SC_TRACE=1 log of scripts/pass_times.py: per sumcheck shape, where the host time of the LAST pass went."""
 import collections, re, sys
 lines = open(sys.argv[1]).read().splitlines()
-idx = [i for i, l in enumerate(lines) if l.startswith('pass')]
+idx = [i for i, l in enumerate(lines) if l.startswith('pass') or l.startswith("{'pass'")]
 seg = lines[idx[-2] + 1:idx[-1]]
 pat = re.compile(r'\[sc n=(\d+) rounds=(\d+)\] cumulative us: launch=(\d+) inv=(\d+) wait\+interp=(\d+) transcript=(\d+) ingest=(\d+)')
 pc = re.compile(r'\[sc-call n=(\d+)\] build=(\d+) us loop=(\d+) us release=(\d+) us')
