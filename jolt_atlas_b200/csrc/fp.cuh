@@ -214,6 +214,65 @@ JA_DEV void fp_mont_rows(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]));
 }
 
+// ---- delayed reduction (the reference's mul_unreduced::<9> + from_montgomery_reduce, field/mod.rs:286-310) ----------------
+// A 512-bit accumulator takes up to 16 unreduced products of canonical elements (16 p^2 < 2^512); one reduction per flush
+// instead of one per product: 64 IMAD.WIDE per accumulated product instead of 128.
+struct FpWide { uint32_t l[16]; };
+JA_DEV FpWide fpw_zero() { FpWide w;
+#pragma unroll
+  for (int i = 0; i < 16; i++) w.l[i] = 0; return w; }
+// acc += a * b as integers (a, b < p)
+template <class M> JA_DEV void fpw_mul_acc(FpWide& acc, const Fp<M>& a, const Fp<M>& b) {
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+  // partial product a[j] * b[i] sits at limb i + j: even positions accumulate in E (64-bit slots at limbs 0, 2, ...), odd
+  // positions in O (the same slots shifted by one limb), so every mad.lo.cc / madc.hi.cc pair is one IMAD.WIDE
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    JA_ROW_ACC((E + i), a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+    JA_ROW_ACC((O + i), a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+    JA_ROW_ACC((O + i), a.l[0], a.l[2], a.l[4], a.l[6], b.l[i + 1]);
+    JA_ROW_ACC((E + i + 2), a.l[1], a.l[3], a.l[5], a.l[7], b.l[i + 1]);
+  }
+  // T = E + (O << 32); acc += T
+  uint32_t T[16];
+  asm("add.cc.u32 %0, %16, 0;\n\t"
+      "addc.cc.u32 %1, %17, %32;\n\t"  "addc.cc.u32 %2, %18, %33;\n\t"  "addc.cc.u32 %3, %19, %34;\n\t"
+      "addc.cc.u32 %4, %20, %35;\n\t"  "addc.cc.u32 %5, %21, %36;\n\t"  "addc.cc.u32 %6, %22, %37;\n\t"
+      "addc.cc.u32 %7, %23, %38;\n\t"  "addc.cc.u32 %8, %24, %39;\n\t"  "addc.cc.u32 %9, %25, %40;\n\t"
+      "addc.cc.u32 %10, %26, %41;\n\t" "addc.cc.u32 %11, %27, %42;\n\t" "addc.cc.u32 %12, %28, %43;\n\t"
+      "addc.cc.u32 %13, %29, %44;\n\t" "addc.cc.u32 %14, %30, %45;\n\t" "addc.u32 %15, %31, %46;"
+      : "=r"(T[0]), "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9]),
+        "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+      : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]),
+        "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
+        "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+  asm("add.cc.u32 %0, %0, %16;\n\t"
+      "addc.cc.u32 %1, %1, %17;\n\t"   "addc.cc.u32 %2, %2, %18;\n\t"   "addc.cc.u32 %3, %3, %19;\n\t"
+      "addc.cc.u32 %4, %4, %20;\n\t"   "addc.cc.u32 %5, %5, %21;\n\t"   "addc.cc.u32 %6, %6, %22;\n\t"
+      "addc.cc.u32 %7, %7, %23;\n\t"   "addc.cc.u32 %8, %8, %24;\n\t"   "addc.cc.u32 %9, %9, %25;\n\t"
+      "addc.cc.u32 %10, %10, %26;\n\t" "addc.cc.u32 %11, %11, %27;\n\t" "addc.cc.u32 %12, %12, %28;\n\t"
+      "addc.cc.u32 %13, %13, %29;\n\t" "addc.cc.u32 %14, %14, %30;\n\t" "addc.u32 %15, %15, %31;"
+      : "+r"(acc.l[0]), "+r"(acc.l[1]), "+r"(acc.l[2]), "+r"(acc.l[3]), "+r"(acc.l[4]), "+r"(acc.l[5]), "+r"(acc.l[6]), "+r"(acc.l[7]),
+        "+r"(acc.l[8]), "+r"(acc.l[9]), "+r"(acc.l[10]), "+r"(acc.l[11]), "+r"(acc.l[12]), "+r"(acc.l[13]), "+r"(acc.l[14]), "+r"(acc.l[15])
+      : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]), "r"(T[8]), "r"(T[9]), "r"(T[10]),
+        "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+}
+// acc * 2^-256 mod p, canonical: (lo + hi 2^256) 2^-256 = mont(lo, 1) + mont(hi, R)   (both operands < 2^256 are fine for the
+// row reduction: its output is < (2^256 p + 2^256 p) / 2^256 = 2p)
+template <class M> JA_DEV Fp<M> fpw_reduce(const FpWide& acc) {
+  const uint32_t one_raw[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  const Fp<M> r_one = fp_one<M>();
+  Fp<M> lo, hi;
+  fp_mont_rows<M, 8>(lo.l, acc.l, one_raw);
+  fp_final_sub<M>(lo.l);
+  fp_mont_rows<M, 8>(hi.l, acc.l + 8, r_one.l);
+  fp_final_sub<M>(hi.l);
+  return fp_add<M>(lo, hi);
+}
+
 template <class M> JA_DEV Fp<M> fp_mul(const Fp<M>& a, const Fp<M>& b) {
   Fp<M> r;
   fp_mont_rows<M, 8>(r.l, a.l, b.l);

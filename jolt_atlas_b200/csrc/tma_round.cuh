@@ -66,8 +66,7 @@ JA_DEV Fr slab_fr(const uint8_t* slab, int t, int e) {
   return r;
 }
 
-// KID: 0 ADD, 1 SUB, 6 IDENT.  G (pairs of the bound array) must be a multiple of 256; block b owns the contiguous
-// slabs [b * slabs_per_block, ...) so that the split-eq outer index changes rarely per thread (as in k_round_s).
+// KID: 0 ADD, 1 SUB, 6 IDENT.  G (pairs of the bound array) must be a multiple of 256.
 template <int KID>
 __global__ void __launch_bounds__(kTmaRows, 2)
 k_round_s_tma(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, Fr* __restrict__ out0,
@@ -81,11 +80,17 @@ k_round_s_tma(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ C
                    (size_t)warp * kTmaSlots * kTmaSlabBytes;
   __shared__ __align__(8) uint64_t full_all[kTmaWarps][kTmaSlots];
   uint64_t* full = full_all[warp];
-  const size_t n_slabs = G / kTmaRows;
+  // Work split: block b owns the contiguous steps [s_begin, s_end) of 256 rows; inside it warp w owns a CONTIGUOUS run of
+  // 32-row slabs, so that consecutive rows of a thread are 32 apart and stay under one split-eq outer index for
+  // 2^bits_in / 32 iterations: the eq-weighted sum accumulates unreduced (delayed Montgomery reduction) and is only
+  // reduced every 16 products or when the outer index changes.
+  const size_t n_steps = G / kTmaRows;
   const size_t s_begin = (size_t)blockIdx.x * slabs_per_block;
   size_t s_end = s_begin + slabs_per_block;
-  if (s_end > n_slabs) s_end = n_slabs;
-  const int n_items = s_begin < s_end ? (int)(s_end - s_begin) * NP : 0;     // (step, polynomial) units, in consumption order
+  if (s_end > n_steps) s_end = n_steps;
+  const size_t my_steps = s_begin < s_end ? s_end - s_begin : 0;       // this warp: my_steps slabs of 32 rows
+  const size_t row_first = s_begin * kTmaRows + (size_t)warp * my_steps * 32;
+  const int n_items = (int)my_steps * NP;                              // (slab, polynomial) units, in consumption order
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kTmaSlots; s++) mbar_init(&full[s], 1);
@@ -95,19 +100,20 @@ k_round_s_tma(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ C
   __syncwarp();
   auto issue = [&](int q) {
     const int slot = q % kTmaSlots;
-    const size_t step = s_begin + (size_t)(q / NP);
     mbar_expect_tx(&full[slot], kTmaSlabBytes);
-    tma_load_slab(slabs + (size_t)slot * kTmaSlabBytes, (NP == 2 && (q % NP) == 1) ? &tm1 : &tm0, (int)(step * kTmaRows + warp * 32), &full[slot]);
+    tma_load_slab(slabs + (size_t)slot * kTmaSlabBytes, (NP == 2 && (q % NP) == 1) ? &tm1 : &tm0, (int)(row_first + (size_t)(q / NP) * 32), &full[slot]);
   };
   if (lane == 0)
     for (int q = 0; q < kTmaSlots && q < n_items; q++) issue(q);
 
   Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
+  FpWide wide = fpw_zero();
+  int pending = 0;
   const size_t mask_in = (size_t(1) << bits_in) - 1;
   size_t cur_xout = ~size_t(0);
   int q = 0;
-  for (size_t slab = s_begin; slab < s_end; slab++) {
-    const size_t g = slab * kTmaRows + tid;
+  for (size_t it = 0; it < my_steps; it++) {
+    const size_t g = row_first + it * 32 + lane;
     Fr lo[NP];
 #pragma unroll
     for (int p = 0; p < NP; p++, q++) {
@@ -124,19 +130,24 @@ k_round_s_tma(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ C
       fp_store(o + 1, hi);
     }
     const size_t x_out = (g + g_off) >> bits_in;
-    if (x_out != cur_xout) {
-      if (cur_xout != ~size_t(0)) {
-        outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
-        inner = fp_zero<FrParams>();
+    if (x_out != cur_xout || pending == 16) {
+      if (pending) { inner = fp_add<FrParams>(inner, fpw_reduce<FrParams>(wide)); wide = fpw_zero(); pending = 0; }
+      if (x_out != cur_xout) {
+        if (cur_xout != ~size_t(0)) {
+          outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
+          inner = fp_zero<FrParams>();
+        }
+        cur_xout = x_out;
       }
-      cur_xout = x_out;
     }
     Fr v;
     if (KID == 6) v = lo[0];
     else if (KID == 0) v = fp_add<FrParams>(lo[0], lo[NP - 1]);
     else v = fp_sub<FrParams>(lo[0], lo[NP - 1]);
-    inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), v));
+    fpw_mul_acc<FrParams>(wide, fp_load(e_in + ((g + g_off) & mask_in)), v);
+    pending++;
   }
+  if (pending) inner = fp_add<FrParams>(inner, fpw_reduce<FrParams>(wide));
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
   Fr acc[1] = {outer};
   if (grid_sum<1>(acc, partials, counter, pub.vals)) publish_flag(pub);
