@@ -239,7 +239,13 @@ def run_device_arm(args):
     os.environ.setdefault("JA_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // world))))
     ctx = Context(local)
     # independent proofs per rank (weak scaling: the path has no cross-proof exchange); see DESIGN.md §Multi-GPU
-    inputs = W.build_inputs(args.config, seed=None if rank == 0 else W.CONFIGS[args.config]["seed"] + rank)
+    # --shard: ONE proof on all ranks (same inputs everywhere; commitments and opening MSMs sharded, strong scaling)
+    shard = bool(args.shard) and world > 1
+    comm = None
+    if shard:
+        from jolt_atlas_b200 import parallel as PAR
+        comm = PAR.Comm(device=torch.device("cuda", local))
+    inputs = W.build_inputs(args.config, seed=None if (rank == 0 or shard) else W.CONFIGS[args.config]["seed"] + rank)
     n = 1 << inputs["ell"]
     srs = SRS.generate(ctx, g1_generator_mont(), tau_mont(), n).precompute()
     resident = W.make_resident(ctx, inputs)
@@ -248,7 +254,7 @@ def run_device_arm(args):
 
     # ---- device-resident leg ----
     for _ in range(args.warmup):
-        W.run_device(ctx, srs, inputs, resident=resident)
+        W.run_device(ctx, srs, inputs, resident=resident, comm=comm)
     sampler = ClockSampler(local)
     barrier()
     if not os.environ.get("JA_BENCH_NO_CLOCKS"):
@@ -257,7 +263,7 @@ def run_device_arm(args):
     ctx.timer_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        W.run_device(ctx, srs, inputs, resident=resident)
+        W.run_device(ctx, srs, inputs, resident=resident, comm=comm)
     dev_ms = ctx.timer_end()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -271,12 +277,12 @@ def run_device_arm(args):
     ms_per_step = ms / args.steps
 
     # ---- end-to-end leg: host buffers in, proof data out, every step ----
-    W.run_device(ctx, srs, inputs)          # warm the upload path
+    W.run_device(ctx, srs, inputs, comm=comm)          # warm the upload path
     barrier()
     ctx.timer_begin()
     last = None
     for _ in range(args.steps):
-        last = W.run_device(ctx, srs, inputs)
+        last = W.run_device(ctx, srs, inputs, comm=comm)
     e2e_ms = ctx.timer_end()
     barrier()
     if world > 1:
@@ -294,22 +300,23 @@ def run_device_arm(args):
         W.run_device(ctx, srs, inputs, resident=resident)
         prof = ctx.profile_end()
         pk, pk_kind = peaks()
-        roof = W.roofline_from_profile(prof, inputs, pk, pk_kind, ctx)
+        roof = W.roofline_from_profile(prof, inputs, pk, pk_kind, ctx, sweep=not args.no_sweep)
         units = W.count_units(inputs)
-        line = {"metric": metric_name(args.config), "value": ms_per_step / 1e3 / world, "unit": "s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+        div = 1 if shard else world        # replicas: world proofs per step; --shard: one proof per step
+        line = {"metric": metric_name(args.config), "value": ms_per_step / 1e3 / div, "unit": "s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong" if shard else "weak",
                 "vs_baseline": None, "dtype": "u64x4 Montgomery (BN254 Fr/Fq)", "data": "synthetic",
-                "config": W.config_dict(args.config, inputs, world),
+                "config": W.config_dict(args.config, inputs, world, shard),
                 "clocks": clocks,
-                "e2e": {"value": e2e_per_step / 1e3 / world, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_per_step / 1e3 / div, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "wall_ms_per_step": wall_ms / args.steps,
                 "units_per_step": units,
                 "roofline": roof["dominant"], "kernel_classes": roof["classes"], "kernel_sweep": roof["sweep"]}
         # MSM sweep (BASELINE.json config 5: Mscalar/s on random 254-bit scalars, one GPU)
         msm = []
-        big = SRS.generate(ctx, g1_generator_mont(), tau_mont(), 1 << 22).precompute()
-        for log_n in (18, 20, 22):
+        big = SRS.generate(ctx, g1_generator_mont(), tau_mont(), 1 << (10 if args.no_sweep else 22)).precompute()
+        for log_n in (() if args.no_sweep else (18, 20, 22)):
             p = MultilinearPolynomial.random(ctx, 1 << log_n, 7)
             from jolt_atlas_b200 import msm_fr
             msm_fr(ctx, big, p)
@@ -342,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="nanoGPT", choices=["nanoGPT", "microgpt", "gpt2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", action="store_true", help="N > 1: one proof on all GPUs (sharded commitments / opening MSMs) instead of N replicas")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the large-n kernel sweep and the MSM sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -165,6 +165,28 @@ def sharded_msm_fr(ctx, srs, scalars, comm):
     return xy[0], bool(oinf[0])
 
 
+def sharded_commit_one_hot_batches(ctx, srs, batches, comm):
+    """commit_to_polynomials (prover.rs:236-249) with the address batches dealt round-robin to the ranks: the commitments
+    of a proof are independent of each other and of the transcript, so a rank commits batches rank, rank + world, ...
+    (all its lists in one pair of launches) and ONE all-gather of the affine points makes every rank hold all of them.
+    Same return value as api.commit_one_hot_batches, identical on every rank."""
+    from . import api as A
+    mine = [b for i, b in enumerate(batches) if i % comm.world == comm.rank]
+    res = A.commit_one_hot_batches(ctx, srs, mine) if mine else []
+    per_rank = (len(batches) + comm.world - 1) // comm.world
+    dmax = max(b.d for b in batches)
+    packed = np.zeros((per_rank, dmax, 9), dtype=np.uint64)                # x||y limbs + infinity flag, padded
+    for j, (xy, inf) in enumerate(res):
+        packed[j, : xy.shape[0], :8] = xy
+        packed[j, : xy.shape[0], 8] = np.asarray(inf, dtype=np.uint64)
+    allp = comm.all_gather(packed)                                         # (world, per_rank, dmax, 9)
+    out = []
+    for i, b in enumerate(batches):
+        blk = allp[i % comm.world, i // comm.world]
+        out.append((np.ascontiguousarray(blk[: b.d, :8]), blk[: b.d, 8].astype(bool)))
+    return out
+
+
 def sharded_hyperkzg_open(ctx, srs, poly, point, transcript_state, comm):
     """HyperKZG::open (hyperkzg/mod.rs:400-447) with every MSM split by index range over the ranks: the folds, the
     univariate evaluations and the quotient recurrence are replicated (HBM streaming, no exchange), the commitments are

@@ -198,10 +198,14 @@ def _ra_checks(A, ctx, addr, ni, lo, hi, claim, t, out, sc):
     return first
 
 
-def run_device(ctx, srs, inputs, resident=None):
+def run_device(ctx, srs, inputs, resident=None, comm=None):
     """One prove-shaped pass on the GPU.  Returns dict(commitments, states, finals, open) for parity checks.
     `resident` (from make_resident) supplies device-resident copies of the per-proof inputs; without it every input is
-    uploaded from the host arrays inside this call (the end-to-end path)."""
+    uploaded from the host arrays inside this call (the end-to-end path).
+    `comm` (parallel.Comm, world > 1): ONE proof on several GPUs — every rank holds the same inputs and runs the
+    (latency-bound, strictly sequential) sumchecks replicated, while the group arithmetic is sharded: the witness
+    commitments by polynomial, every MSM of the HyperKZG opening by index range (parallel.py).  All ranks end with the
+    same transcript and the same proof."""
     from . import api as A
     t = A.Blake2bTranscriptState(b"ONNXProof")
     out = {"commitments": [], "states": [], "finals": [], "msg_bytes": 0}
@@ -221,7 +225,13 @@ def run_device(ctx, srs, inputs, resident=None):
         else:
             hots.append((A.OneHotAddresses(ctx, ni.hot_k[:D_CLAMP], K_CHUNK),
                          A.OneHotAddresses(ctx, ni.hot_k[D_CLAMP:], K_CHUNK) if ni.d_hot > D_CLAMP else None))
-    out["commitments"] = A.commit_one_hot_batches(ctx, srs, [h for pair in hots for h in pair if h is not None])
+    sharded = comm is not None and comm.world > 1
+    all_hots = [h for pair in hots for h in pair if h is not None]
+    if sharded:
+        from . import parallel as PAR0
+        out["commitments"] = PAR0.sharded_commit_one_hot_batches(ctx, srs, all_hots, comm)
+    else:
+        out["commitments"] = A.commit_one_hot_batches(ctx, srs, all_hots)
     for i, ni in enumerate(inputs["nodes"]):
         spec = ni.spec
         res = resident["nodes"][i] if resident else None
@@ -282,7 +292,10 @@ def run_device(ctx, srs, inputs, resident=None):
     for h in batches:
         rlc.rlc_add_onehot(h, gammas[o:o + h.d])
         o += h.d
-    out["open"] = A.hyperkzg_open(ctx, srs, rlc, r["challenges"], t)    # PCS::prove(rlc, r_sumcheck), prover.rs:164-170
+    if sharded:
+        out["open"] = PAR.sharded_hyperkzg_open(ctx, srs, rlc, r["challenges"], t, comm)
+    else:
+        out["open"] = A.hyperkzg_open(ctx, srs, rlc, r["challenges"], t)    # PCS::prove(rlc, r_sumcheck), prover.rs:164-170
     rlc.free()
     if not resident:
         for pair in hots:
@@ -388,7 +401,7 @@ def algorithmic_fieldmuls(inputs) -> dict:
     return {"onehot_point_sum": 10 * adds, "msm_accumulate": 10 * 4 * n * 16, "sumcheck_fused": fused}
 
 
-def config_dict(config: str, inputs, world: int = 1) -> dict:
+def config_dict(config: str, inputs, world: int = 1, shard: bool = False) -> dict:
     u = count_units(inputs)
     return {"workload": "%s-shaped prove pass: %d nodes (one-hot commits K=16, lookup/RA/operator/range-check sumchecks, "
                         "chained Blake2b transcript) + HyperKZG open ell=%d; synthetic i8-range tensors" %
@@ -397,10 +410,13 @@ def config_dict(config: str, inputs, world: int = 1) -> dict:
             "open_msm_pairs": u["open_msm_pairs"],
             "l2": "no explicit flush: one pass streams %.0f MB of polynomial data through a 126 MB L2" %
                   (sum(algorithmic_bytes(inputs).values()) / 1e6),
-            "parallelism": "1 GPU" if world == 1 else "%d replicas, one independent proof per GPU (no data-path collective)" % world}
+            "parallelism": "1 GPU" if world == 1 else
+                           ("one proof on %d GPUs: commitments sharded by polynomial, opening MSMs by index range (3 all-gathers of points), "
+                            "sumchecks replicated" % world if shard else
+                            "%d replicas, one independent proof per GPU (no data-path collective)" % world)}
 
 
-def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx) -> dict:
+def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx, sweep: bool = True) -> dict:
     """Per-class achieved rates of one profiled pass + a large-n sweep of the streaming kernels.  A class that has both an
     algorithmic byte count and a field-mul count is bound by whichever roofline time is larger."""
     ab = algorithmic_bytes(inputs)
@@ -432,7 +448,9 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx)
         gb = dom.get("GBps", 0.0)
         dominant = dict(common, bound="hbm", achieved=gb, peak=hbm, unit="GB/s", frac=round(gb / hbm, 4),
                         peak_source="%s (MEASURED_PEAKS.json hbm_gbs)" % peaks_kind)
-    sweep = []
+    do_sweep, sweep = sweep, []
+    if not do_sweep:
+        return {"dominant": dominant, "classes": classes, "sweep": sweep, "fr_mul_peak_Gmul_s": mul_peak}
     for which, name, bytes_per_n in ((0, "bind_low_to_high", 48), (1, "bind_high_to_low", 48), (4, "round_eval_add", 64), (2, "round_eval_mul", 64)):
         for log_n in (24, 26):
             ms = ctx.bench_kernel(which, log_n, 1, 10)

@@ -157,3 +157,49 @@ def test_sharded_sumcheck_prove_equals_single(kind, npoly, world, m):
         assert np.array_equal(got["challenges"], want["challenges"])
         assert np.array_equal(got["final_claims"], want["final_claims"])
         assert state == t0.state
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_prove_pass_equals_single_gpu(world):
+    """One microgpt-shaped proof on `world` ranks (threads, one Context each): commitments sharded by polynomial, opening
+    MSMs by index range, sumchecks replicated -> every rank produces the single-GPU commitments, opening and transcript."""
+    import threading
+    import bench
+    from jolt_atlas_b200 import SRS, Context
+    from jolt_atlas_b200 import parallel as PAR
+    from jolt_atlas_b200 import workload as W
+    inputs = W.build_inputs("microgpt")
+    with Context(0) as c0:
+        srs0 = SRS.generate(c0, bench.g1_generator_mont(), bench.tau_mont(), 1 << inputs["ell"]).precompute()
+        want = W.run_device(c0, srs0, inputs)
+        srs0.free()
+    group = PAR.ThreadComm.Group(world)
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            comm = PAR.ThreadComm(group, rank)
+            with Context(0) as c:
+                srs = SRS.generate(c, bench.g1_generator_mont(), bench.tau_mont(), 1 << inputs["ell"]).precompute()
+                results[rank] = W.run_device(c, srs, inputs, comm=comm)
+                srs.free()
+        except Exception as e:   # noqa: BLE001
+            errors.append((rank, repr(e)))
+            try:
+                group.barrier.abort()
+            except Exception:    # noqa: BLE001
+                pass
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errors, errors
+    for rank in range(world):
+        got = results[rank]
+        assert got["states"] == want["states"], rank
+        assert len(got["commitments"]) == len(want["commitments"])
+        for (gxy, ginf), (wxy, winf) in zip(got["commitments"], want["commitments"]):
+            assert np.array_equal(gxy, wxy) and np.array_equal(np.asarray(ginf, dtype=bool), np.asarray(winf, dtype=bool)), rank
+        for k in ("com", "w", "v"):
+            assert np.array_equal(got["open"][k], want["open"][k]), (rank, k)
