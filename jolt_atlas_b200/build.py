@@ -19,7 +19,7 @@ LIB = os.path.join(LIBDIR, "libjolt_atlas_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fopenmp",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fopenmp,-mbmi2,-madx",   # mulx / adcx / adox for the host-side Montgomery glue (every x86-64 server CPU since 2015)
     "--expt-relaxed-constexpr",
 ]
 

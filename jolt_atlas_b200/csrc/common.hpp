@@ -56,6 +56,15 @@ struct ja_ctx {
   void* h_mapped = nullptr;
   void* d_mapped = nullptr;
   unsigned int seq = 0;
+  // challenge mailboxes of the pre-launched round kernels (fused_kernels.cuh: MailRef): ring of kMailEntries x 32 B in
+  // host-mapped memory; ahead_p / ahead_seq are non-null only while the engine enqueues the NEXT round's kernels
+  void* h_mail = nullptr;
+  void* d_mail = nullptr;
+  uint32_t* d_mail_dev = nullptr;       // device-memory twin of the ring (relay target of block (0, 0))
+  volatile uint32_t* ahead_dev = nullptr;
+  uint32_t mail_seq = 0;
+  const volatile uint32_t* ahead_p = nullptr;
+  uint32_t ahead_seq = 0;
   // flat host-mapped value array of the batched opening reduction (kMaxRowVals Fr + a sequence word at kRowSeqOffset)
   void* h_rowvals = nullptr;
   void* d_rowvals = nullptr;
@@ -102,6 +111,7 @@ static constexpr size_t kRingBytes = 1 << 20;
 static constexpr int kSlots = 128;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
 static constexpr size_t kMaxRowVals = 8192, kRowSeqOffset = kMaxRowVals * 32;
+static constexpr uint32_t kMailEntries = 64;
 
 struct ja_poly {
   size_t len = 0;

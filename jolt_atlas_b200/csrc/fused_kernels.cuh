@@ -40,6 +40,49 @@ static __global__ void __launch_bounds__(64) k_collect_finals(CollectArgs a, int
   if (i < n) reinterpret_cast<uint4*>(a.dst[i])[h] = __ldg(reinterpret_cast<const uint4*>(a.src[i]) + h);
 }
 
+// ---- challenge mailbox --------------------------------------------------------------------------------------------------
+// The kernel of round j+1 is enqueued BEFORE the host has derived r_j (right behind round j's kernel), so that the
+// launch overhead and latency are off the Fiat-Shamir critical path: it starts as soon as round j's kernel retires and its
+// thread 0 polls a 32-byte entry in host-mapped memory until the host has written r_j and the expected sequence number
+// (challenge words first, sequence word last).  Bit 31 of the sequence word = abort (the host hit an error): the block
+// returns without touching anything.  p == nullptr: no mailbox, the challenge is the kernel parameter.
+struct MailRef {
+  const volatile uint32_t* p;    // device address of the host-mapped entry: c[0..3], seq
+  volatile uint32_t* dev;        // the same entry in device memory: block (0, 0) relays the challenge to the other blocks
+  uint32_t seq;
+};
+// Only block (0, 0) polls the host entry (a PCIe round trip per poll; hundreds of blocks doing that congest the link and
+// cost > 100 us per round); it republishes challenge + sequence word in device memory, which the other blocks poll in L2.
+JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
+  if (!m.p) return true;
+  __shared__ uint32_t s_mail[5];
+  if (threadIdx.x == 0) {
+    const bool relay = blockIdx.x == 0 && blockIdx.y == 0;
+    const volatile uint32_t* src = relay ? m.p : m.dev;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t v;
+    for (unsigned int it = 0;; it++) {
+      v = src[4];
+      if ((v & 0x7fffffffu) == m.seq) break;
+      if ((it & 255u) == 255u) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) asm volatile("trap;");        // 20 s: the host is gone
+      }
+    }
+    const uint32_t c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
+    if (relay) {
+      m.dev[0] = c0; m.dev[1] = c1; m.dev[2] = c2; m.dev[3] = c3;
+      __threadfence();
+      m.dev[4] = v;
+    }
+    s_mail[0] = c0; s_mail[1] = c1; s_mail[2] = c2; s_mail[3] = c3; s_mail[4] = v >> 31;
+  }
+  __syncthreads();
+  r.c[0] = s_mail[0]; r.c[1] = s_mail[1]; r.c[2] = s_mail[2]; r.c[3] = s_mail[3];
+  return s_mail[4] == 0;
+}
+
 struct FusedPolys {
   const Fr* in[kMaxProdPolys];
   Fr* out[kMaxProdPolys];        // FUSED only: bound arrays (LowToHigh: other ping-pong buffer; HighToLow: == in)
@@ -69,7 +112,9 @@ template <int KID, bool FUSED>
 __global__ void __launch_bounds__(kBlock, (KID == 0 || KID == 1 || KID == 6) ? 4 : 2)
 k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
           size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
-          size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */) {
+          size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */,
+          MailRef mail = MailRef{nullptr, nullptr, 0}) {
+  if (FUSED && !mail_wait(r, mail)) return;
   constexpr int NOUT = SOut<KID>::N;
   Fr outer[NOUT], inner[NOUT];
 #pragma unroll
@@ -212,7 +257,9 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, cons
 template <int L, bool SAME, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0) {
+             size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0,
+             MailRef mail = MailRef{nullptr, nullptr, 0}) {
+  if (FUSED && !mail_wait(r, mail)) return;
   round_prod_body<L, SAME, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 
@@ -290,7 +337,9 @@ JA_DEV void round_bool_body(const FusedPolys& P, int d, const Challenge& r, cons
 template <int L, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-             size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub) {
+             size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
+             MailRef mail = MailRef{nullptr, nullptr, 0}) {
+  if (FUSED && !mail_wait(r, mail)) return;
   round_bool_body<L, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
 }
 
@@ -310,7 +359,8 @@ struct PairArgs {
 };
 template <int L, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
-k_round_prod_bool(PairArgs A, PairArgs B, Challenge r) {
+k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{nullptr, nullptr, 0}) {
+  if (FUSED && !mail_wait(r, mail)) return;
   if (blockIdx.y == 0) {
     if (blockIdx.x < A.nb)
       round_prod_body<L, false, FUSED>(A.P, A.d, r, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
@@ -324,7 +374,8 @@ k_round_prod_bool(PairArgs A, PairArgs B, Challenge r) {
 template <int NPOLY, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array: it has 2G entries */, Fr* partials,
-            unsigned int* counter, Publish pub) {
+            unsigned int* counter, Publish pub, MailRef mail = MailRef{nullptr, nullptr, 0}) {
+  if (FUSED && !mail_wait(r, mail)) return;
   constexpr int NOUT = NPOLY;
   Fr acc[NOUT];
 #pragma unroll

@@ -220,6 +220,14 @@ struct Inst {
   // flush deferred work and enqueue the D2H of the final claims into `staging` (pinned); *count = number of Fr written
   virtual int32_t finalize(ja_ctx* c, uint64_t* staging, size_t* count) = 0;
   virtual void release(ja_ctx*) {}
+  // Pre-launch protocol (prove_loop): the kernels of local round `next` are enqueued while round next-1 is still in flight
+  // and receive its challenge through the context's mailbox.  can_ahead: this instance's round `next` may be enqueued
+  // that way (host-only instances: always).  ahead_begin / ahead_end bracket the early launch (state as if the missing
+  // challenge had been ingested, then back); ahead_commit runs at the top of the next iteration instead of launch().
+  virtual bool can_ahead(size_t /*next local round*/) { return false; }
+  virtual int32_t ahead_begin(ja_ctx*) { return JA_OK; }
+  virtual void ahead_end(ja_ctx*) {}
+  virtual void ahead_commit() {}
 };
 
 // device-resident polynomials, one JA_EVAL_* body (or booleanity phase 2 = body 7)
@@ -240,6 +248,11 @@ struct DevInst : Inst {
   FrH scale_inv = host::FR_ONE;
   // per-round state between launch and message
   Slot slot;
+  // pre-launch: slot armed for the NEXT round's kernel, eq level saved across the early launch, "the pending bind of the
+  // next ingest has already been consumed"
+  Slot slot_next, slot_keep;
+  bool ahead_consumed = false;
+  struct EqSave { int current_index = 0; size_t in_len = 0, out_len = 0; FrH scalar; } eq_save;
   RoundEvalPending pend;
   bool legacy = false;              // round went through ja_round_eval_launch (pinned staging + stream sync)
   FrH cs, cw, div;
@@ -394,6 +407,36 @@ struct DevInst : Inst {
     return JA_OK;
   }
 
+  bool can_ahead(size_t next) override {
+    if (!fusable || sharded || next < 1 || next >= rounds) return false;
+    switch (kind) {
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_MUL: case JA_EVAL_SQUARE: case JA_EVAL_IDENT: case 7:
+      case JA_EVAL_PROD: case JA_EVAL_POW: case JA_EVAL_DOT2: case JA_EVAL_DOT3: break;
+      default: return false;
+    }
+    // large rounds gain nothing (and would put hundreds of blocks on the mailbox): pairs of the next round <= 2^15
+    const size_t len_now = pending ? polys[0]->len / 2 : polys[0]->len;        // length this round evaluates
+    return len_now >= 4 && len_now / 4 <= (size_t(1) << 15);
+  }
+  int32_t ahead_begin(ja_ctx* c) override {
+    if (eq) {
+      eq_save.current_index = (int)eq->current_index; eq_save.in_len = eq->in_len; eq_save.out_len = eq->out_len; eq_save.scalar = eq->current_scalar;
+      const uint64_t zero[4] = {0, 0, 0, 0};
+      int32_t st = ja_spliteq_bind(c, eq, zero);                      // advances the table level; the scalar is restored below
+      if (st) return st;
+    }
+    pending = true;
+    memset(pend_ch, 0, 32);                                          // the kernel takes the challenge from the mailbox
+    slot_keep = slot;
+    return JA_OK;
+  }
+  void ahead_end(ja_ctx*) override {
+    slot_next = slot; slot = slot_keep;
+    if (eq) { eq->current_index = eq_save.current_index; eq->in_len = eq_save.in_len; eq->out_len = eq_save.out_len; eq->current_scalar = eq_save.scalar; }
+    ahead_consumed = true;
+  }
+  void ahead_commit() override { slot = slot_next; }
+
   // fused round kernel (bind pend_ch first when `pending`)
   int32_t launch_fused(ja_ctx* c) {
     Prep pr;
@@ -416,7 +459,7 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off))
+#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
 #define JA_PROD_L(LL) do { if (same) { if (fz) JA_PROD_F(LL, true, true); else JA_PROD_F(LL, true, false); } \
                            else { if (fz) JA_PROD_F(LL, false, true); else JA_PROD_F(LL, false, false); } } while (0)
       switch (L) { case 2: JA_PROD_L(2); break; case 4: JA_PROD_L(4); break; case 8: JA_PROD_L(8); break; default: JA_PROD_L(16); break; }
@@ -432,7 +475,7 @@ struct DevInst : Inst {
     } else if (kind == JA_EVAL_DOT2 || kind == JA_EVAL_DOT3) {
       unsigned grid = grid_for(G);
       if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
-#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub))
+#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
       if (kind == JA_EVAL_DOT2) { if (fz) JA_DOT_F(2, true); else JA_DOT_F(2, false); }
       else { if (fz) JA_DOT_F(3, true); else JA_DOT_F(3, false); }
 #undef JA_DOT_F
@@ -443,12 +486,12 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub))
+#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
 #define JA_BOOL_L(LL) do { if (fz) JA_BOOL_F(LL, true); else JA_BOOL_F(LL, false); } while (0)
       switch (L) { case 2: JA_BOOL_L(2); break; case 4: JA_BOOL_L(4); break; case 8: JA_BOOL_L(8); break; default: JA_BOOL_L(16); break; }
 #undef JA_BOOL_L
 #undef JA_BOOL_F
-    } else if (tma_eligible(kind, fz, G)) {
+    } else if (!c->ahead_p && tma_eligible(kind, fz, G)) {
       int32_t tst = launch_round_s_tma(c, kind, P, ch, e_out, e_in, bits_in, G, part, ctr, pub, pr.g_off);
       if (tst) return tst;
     } else {
@@ -457,7 +500,7 @@ struct DevInst : Inst {
       const size_t tpb = (tiles + grid - 1) / grid;
       grid = (tiles + tpb - 1) / tpb;
       const int np = (int)polys.size();
-#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off))
+#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
 #define JA_S_K(KID) do { if (fz) JA_S_F(KID, true); else JA_S_F(KID, false); } while (0)
       switch (kind) {
         case JA_EVAL_ADD: JA_S_K(0); break;
@@ -559,6 +602,7 @@ struct DevInst : Inst {
   int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t) override {
     int32_t st;
     if (eq && (st = ja_spliteq_bind(c, eq, ch))) return st;
+    if (ahead_consumed) { ahead_consumed = false; return JA_OK; }   // the pre-launched kernel of the next round binds this challenge
     if (fusable) { memcpy(pend_ch, ch, 32); pending = true; return JA_OK; }
     return ja_bind_many(c, polys.data(), polys.size(), ch, order);
   }
@@ -588,6 +632,7 @@ struct HammingHostInst : Inst {
   std::vector<std::vector<FrH>> ra;
   std::vector<FrH> gammas;
   int32_t launch(ja_ctx*, size_t) override { return JA_OK; }
+  bool can_ahead(size_t) override { return true; }                 // no kernels
   int32_t message(ja_ctx*, size_t, const FrH& prev, Coeffs* uni) override {
     FrH acc = host::FR_ZERO;
     for (size_t i = 0; i < ra.size(); i++) {
@@ -628,6 +673,11 @@ struct BooleanityInst : Inst {
   std::vector<ja_poly*> H;
 
   bool needs_slot() const override { return true; }
+  // pre-launch only between two cycle rounds (p2 exists and has launched the round before `next`)
+  bool can_ahead(size_t next) override { return next > log_k && p2 && p2->can_ahead(next - log_k); }
+  int32_t ahead_begin(ja_ctx* c) override { return p2->ahead_begin(c); }
+  void ahead_end(ja_ctx* c) override { p2->ahead_end(c); }
+  void ahead_commit() override { p2->ahead_commit(); }
   DevInst* pair_candidate(size_t round) override { return round >= log_k && p2 && p2->pairable() ? p2.get() : nullptr; }
   int32_t launch(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k); }
   int32_t prework(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->prework(c, round - log_k); }
@@ -1060,48 +1110,96 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   for (size_t k = 0; k < n; k++) if (dynamic_cast<OpenMember*>(insts[k].get())) { is_open[k] = 1; n_open++; }
   const int nth = n_open >= 128 ? host_threads() : 1;
   g_trace.start();
+  // the launch phase of one round: every active instance enqueues its kernel (pairs / row batches share launches)
+  auto launch_round = [&](size_t rnd) -> int32_t {
+    const size_t rem = max_rounds - rnd;
+    int32_t st = JA_OK;
+      bool legacy_in_flight = false;
+      if (ob) {
+        for (size_t k = 0; k < n; k++) if (OpenMember* om = dynamic_cast<OpenMember*>(insts[k].get())) om->batch_round = rnd;
+        if ((st = ob->launch(c, rnd, max_rounds))) return st;
+      }
+      // RA one-hot checks: RaVirtual (product of d) + Booleanity phase 2 of the same shape go out as ONE launch
+      if (n <= 8) {
+        DevInst *pa = nullptr, *pb = nullptr;
+        for (size_t k = 0; k < n; k++) {
+          if (rem > insts[k]->rounds) continue;
+          DevInst* cand = insts[k]->pair_candidate(rnd - (max_rounds - insts[k]->rounds));
+          if (!cand) continue;
+          if (cand->kind == JA_EVAL_PROD && !pa) pa = cand;
+          else if (cand->kind == 7 && !pb) pb = cand;
+        }
+        if (pa && pb && pa->polys.size() == pb->polys.size() && pa->polys[0]->len == pb->polys[0]->len && pa->pending == pb->pending &&
+            (!pa->pending || memcmp(pa->pend_ch, pb->pend_ch, 32) == 0)) {
+          PairArgs A, B;
+          DevInst::Prep ra, rb;
+          if ((st = pa->prepare_pair(c, &A, &ra, 0))) return st;
+          if ((st = pb->prepare_pair(c, &B, &rb, 1))) return st;
+          const unsigned int gx = std::max(A.nb, B.nb);
+          int L = 2; while (L < A.d) L <<= 1;
+#define JA_PAIR(LL) do { if (ra.fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, true><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq})); \
+                           else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, false><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); } while (0)
+          switch (L) { case 2: JA_PAIR(2); break; case 4: JA_PAIR(4); break; case 8: JA_PAIR(8); break; default: JA_PAIR(16); break; }
+#undef JA_PAIR
+          JA_CUDA(cudaGetLastError());
+          pa->paired_this_round = true; pb->paired_this_round = true;
+        }
+      }
+      for (size_t k = 0; k < n; k++) {
+        if (rem > insts[k]->rounds) continue;
+        // instances on the pinned-staging path cannot overlap each other: collect before launching the next one
+        DevInst* dv = dynamic_cast<DevInst*>(insts[k].get());
+        const bool is_legacy = dv && !dv->fusable;
+        if (is_legacy && legacy_in_flight) return fail(JA_ERR_UNSUPPORTED, "sumcheck: at most one non-fused instance per batch");
+        if ((st = insts[k]->launch(c, rnd - (max_rounds - insts[k]->rounds)))) return st;
+        legacy_in_flight = legacy_in_flight || is_legacy;
+      }
+    return JA_OK;
+  };
+  // Pre-launch (fused_kernels.cuh: MailRef): right behind round j's kernels the engine enqueues round j+1's, which wait on
+  // the device for r_j; launch overhead and latency leave the Fiat-Shamir critical path.  JA_NO_AHEAD=1 disables it.
+  const bool ahead_on = !ob && c->h_mail && getenv("JA_NO_AHEAD") == nullptr;
+  size_t prelaunched = ~size_t(0);
+  struct MailGuard {                       // an enqueued kernel must never be left waiting: errors abort it
+    volatile uint32_t* entry = nullptr; uint32_t seq = 0;
+    void post(const uint64_t ch[4]) {
+      const Challenge cc = to_challenge(ch);
+      entry[0] = cc.c[0]; entry[1] = cc.c[1]; entry[2] = cc.c[2]; entry[3] = cc.c[3];
+      __atomic_thread_fence(__ATOMIC_RELEASE);
+      entry[4] = seq;
+      entry = nullptr;
+    }
+    ~MailGuard() { if (entry) { __atomic_thread_fence(__ATOMIC_RELEASE); entry[4] = seq | 0x80000000u; } }
+  } mail;
   for (size_t round = 0; round < max_rounds; round++) {
     const size_t remaining = max_rounds - round;
     std::vector<Coeffs> unis(n);
-    bool legacy_in_flight = false;
-    if (ob) {
-      for (size_t k = 0; k < n; k++) if (OpenMember* om = dynamic_cast<OpenMember*>(insts[k].get())) om->batch_round = round;
-      if ((st = ob->launch(c, round, max_rounds))) return st;
+    if (prelaunched == round) {
+      for (size_t k = 0; k < n; k++) if (remaining <= insts[k]->rounds) insts[k]->ahead_commit();
+    } else if ((st = launch_round(round))) {
+      return st;
     }
-    // RA one-hot checks: RaVirtual (product of d) + Booleanity phase 2 of the same shape go out as ONE launch
-    if (n <= 8) {
-      DevInst *pa = nullptr, *pb = nullptr;
-      for (size_t k = 0; k < n; k++) {
-        if (remaining > insts[k]->rounds) continue;
-        DevInst* cand = insts[k]->pair_candidate(round - (max_rounds - insts[k]->rounds));
-        if (!cand) continue;
-        if (cand->kind == JA_EVAL_PROD && !pa) pa = cand;
-        else if (cand->kind == 7 && !pb) pb = cand;
+    if (ahead_on && round + 1 < max_rounds) {
+      bool ok = true, any = false;
+      for (size_t k = 0; k < n && ok; k++) {
+        const bool now = remaining <= insts[k]->rounds, next = remaining - 1 <= insts[k]->rounds;
+        if (next && !now) ok = false;                                // an instance starts next round: plain launch
+        else if (next) { ok = insts[k]->can_ahead(round + 1 - (max_rounds - insts[k]->rounds)); any = true; }
       }
-      if (pa && pb && pa->polys.size() == pb->polys.size() && pa->polys[0]->len == pb->polys[0]->len && pa->pending == pb->pending &&
-          (!pa->pending || memcmp(pa->pend_ch, pb->pend_ch, 32) == 0)) {
-        PairArgs A, B;
-        DevInst::Prep ra, rb;
-        if ((st = pa->prepare_pair(c, &A, &ra, 0))) return st;
-        if ((st = pb->prepare_pair(c, &B, &rb, 1))) return st;
-        const unsigned int gx = std::max(A.nb, B.nb);
-        int L = 2; while (L < A.d) L <<= 1;
-#define JA_PAIR(LL) do { if (ra.fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, true><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); \
-                         else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, false><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); } while (0)
-        switch (L) { case 2: JA_PAIR(2); break; case 4: JA_PAIR(4); break; case 8: JA_PAIR(8); break; default: JA_PAIR(16); break; }
-#undef JA_PAIR
-        JA_CUDA(cudaGetLastError());
-        pa->paired_this_round = true; pb->paired_this_round = true;
+      if (ok && any) {
+        if (++c->mail_seq >= 0x7fffffffu) c->mail_seq = 1;
+        const uint32_t seq = c->mail_seq, idx = seq % kMailEntries;
+        c->ahead_seq = seq;
+        c->ahead_p = reinterpret_cast<const volatile uint32_t*>(c->d_mail) + 8 * idx;
+        c->ahead_dev = c->d_mail_dev + 8 * idx;
+        for (size_t k = 0; k < n && !st; k++) if (remaining <= insts[k]->rounds) st = insts[k]->ahead_begin(c);
+        if (!st) st = launch_round(round + 1);
+        for (size_t k = 0; k < n; k++) if (remaining <= insts[k]->rounds) insts[k]->ahead_end(c);
+        c->ahead_p = nullptr; c->ahead_dev = nullptr; c->ahead_seq = 0;
+        mail.entry = reinterpret_cast<volatile uint32_t*>(c->h_mail) + 8 * idx; mail.seq = seq;
+        if (st) return st;
+        prelaunched = round + 1;
       }
-    }
-    for (size_t k = 0; k < n; k++) {
-      if (remaining > insts[k]->rounds) continue;
-      // instances on the pinned-staging path cannot overlap each other: collect before launching the next one
-      DevInst* dv = dynamic_cast<DevInst*>(insts[k].get());
-      const bool is_legacy = dv && !dv->fusable;
-      if (is_legacy && legacy_in_flight) return fail(JA_ERR_UNSUPPORTED, "sumcheck: at most one non-fused instance per batch");
-      if ((st = insts[k]->launch(c, round - (max_rounds - insts[k]->rounds)))) return st;
-      legacy_in_flight = legacy_in_flight || is_legacy;
     }
     if (g_trace.on && getenv("JA_SC_TRACE")[0] == '2') {
       auto nw = std::chrono::steady_clock::now();
@@ -1163,6 +1261,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     t.append_message("UniPoly_end");
     uint64_t ch[4];
     t.challenge_scalar_optimized(ch);                                                      // :126 / :586
+    if (mail.entry) mail.post(ch);                                                         // releases the pre-launched kernels of the next round
     const FrH r = host::from_limbs(ch);
 #pragma omp parallel for schedule(static) num_threads(nth) if (nth > 1)
     for (long k = 0; k < (long)n; k++) claims[k] = host::evaluate(unis[k], r);             // :130-134 / :589
