@@ -67,7 +67,7 @@ JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
       if ((v & 0x7fffffffu) == m.seq) break;
       if ((it & 255u) == 255u) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) asm volatile("trap;");        // 20 s: the host is gone
+        if (t1 - t0 > 5000000000ull) asm volatile("trap;");         // 5 s: the host is gone
       }
     }
     const uint32_t c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];

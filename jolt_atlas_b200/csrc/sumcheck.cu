@@ -28,6 +28,8 @@
 
 using host::Coeffs;
 
+extern "C" char** environ;      // tool-injection scan (ahead_allowed)
+
 namespace {
 
 // worker threads for the host-side glue of large batches: JA_HOST_THREADS, else min(8, hardware threads)
@@ -38,6 +40,24 @@ int host_threads() {
     return (int)std::max(1u, std::min(8u, hc ? hc : 1u));
   }();
   return n;
+}
+
+// Pre-launching a kernel that waits for the host deadlocks under anything that makes launches synchronous (ncu and
+// compute-sanitizer serialise kernels, CUDA_LAUNCH_BLOCKING=1): detect tool injection / blocking launches once and
+// fall back to plain launches.  JA_NO_AHEAD=1 forces the fallback, JA_AHEAD_TRACE=1 says on stderr which mode is on.
+bool ahead_allowed() {
+  static const bool ok = [] {
+    bool allow = true;
+    if (const char* e = getenv("CUDA_LAUNCH_BLOCKING")) if (atoi(e) != 0) allow = false;
+    for (char** e = environ; allow && e && *e; e++) {
+      static const char* const kTool[] = {"CUDA_INJECTION", "NV_NSIGHT_INJECTION", "NV_COMPUTE_PROFILER", "NV_TPS_LAUNCH", "NV_SANITIZER",
+                                         "NVTX_INJECTION", "CUPTI_", "NSIGHT_"};
+      for (const char* t : kTool) if (strncmp(*e, t, strlen(t)) == 0) { allow = false; break; }
+    }
+    if (getenv("JA_AHEAD_TRACE")) fprintf(stderr, "[jolt_atlas_b200] pre-launched round kernels: %s\n", allow ? "on" : "off (tool injection / blocking launches detected)");
+    return allow;
+  }();
+  return ok;
 }
 
 // JA_SC_TRACE=1: per-phase host wall-clock of the round loop on stderr (tuning aid)
@@ -1158,7 +1178,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   };
   // Pre-launch (fused_kernels.cuh: MailRef): right behind round j's kernels the engine enqueues round j+1's, which wait on
   // the device for r_j; launch overhead and latency leave the Fiat-Shamir critical path.  JA_NO_AHEAD=1 disables it.
-  const bool ahead_on = !ob && c->h_mail && getenv("JA_NO_AHEAD") == nullptr;
+  const bool ahead_on = !ob && c->h_mail && getenv("JA_NO_AHEAD") == nullptr && ahead_allowed();
   size_t prelaunched = ~size_t(0);
   struct MailGuard {                       // an enqueued kernel must never be left waiting: errors abort it
     volatile uint32_t* entry = nullptr; uint32_t seq = 0;
