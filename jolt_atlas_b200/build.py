@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fopenmp,-mbmi2,-madx",   # mulx / adcx / adox for the host-side Montgomery glue (every x86-64 server CPU since 2015)
     "--expt-relaxed-constexpr",
-]
+] + (["-DJA_MUL_CALL"] if os.environ.get("JA_MUL_CALL") else [])
 
 
 def _newer(target: str, sources: list[str]) -> bool:

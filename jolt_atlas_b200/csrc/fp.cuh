@@ -50,6 +50,14 @@ using Fr = Fp<FrParams>;
 using Fq = Fp<FqParams>;
 
 #define JA_DEV __device__ __forceinline__
+// Montgomery products stay force-inlined: making them real calls (one code copy per kernel, -DJA_MUL_CALL) to relieve the
+// instruction cache of the latency-bound small launches was measured SLOWER everywhere (ABI spills around the calls:
+// single-instance rounds 16.9 -> 19.6 us, fused ADD at 2^24 0.63 -> 0.40 of HBM).
+#ifdef JA_MUL_CALL
+#define JA_MUL_DEV __device__ __noinline__
+#else
+#define JA_MUL_DEV __device__ __forceinline__
+#endif
 
 template <class M> JA_DEV Fp<M> fp_zero() { Fp<M> r;
 #pragma unroll
@@ -273,7 +281,7 @@ template <class M> JA_DEV Fp<M> fpw_reduce(const FpWide& acc) {
   return fp_add<M>(lo, hi);
 }
 
-template <class M> JA_DEV Fp<M> fp_mul(const Fp<M>& a, const Fp<M>& b) {
+template <class M> JA_MUL_DEV Fp<M> fp_mul(const Fp<M>& a, const Fp<M>& b) {
   Fp<M> r;
   fp_mont_rows<M, 8>(r.l, a.l, b.l);
   fp_final_sub<M>(r.l);
@@ -285,7 +293,7 @@ template <class M> JA_DEV Fp<M> fp_sqr(const Fp<M>& a) { return fp_mul<M>(a, a);
 // [0,0,0,0,c0,c1,c2,c3]:  a*c*2^-256 == a*c'*2^-128, i.e. only 4 of the 8 rows are needed.
 // (field/challenge/macros.rs:274-286 `mul_hi_bigint_u128`)
 struct Challenge { uint32_t c[4]; };
-template <class M> JA_DEV Fp<M> fp_mul_challenge(const Fp<M>& a, const Challenge& ch) {
+template <class M> JA_MUL_DEV Fp<M> fp_mul_challenge(const Fp<M>& a, const Challenge& ch) {
   Fp<M> r;
   fp_mont_rows<M, 4>(r.l, a.l, ch.c);
   fp_final_sub<M>(r.l);

@@ -109,7 +109,7 @@ JA_DEV void load_pair_l2h(const Fr* __restrict__ in, Fr* __restrict__ out, size_
 template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 || KID == 7) ? 2 : 1; };
 
 template <int KID, bool FUSED>
-__global__ void __launch_bounds__(kBlock, (KID == 0 || KID == 1 || KID == 6) ? 4 : 2)
+__global__ void __launch_bounds__(kBlock, 2)
 k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
           size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
           size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */,
@@ -137,6 +137,7 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       }
       cur_xout = x_out;
     }
+    const Fr ei = fp_load(e_in + ((g + g_off) & mask_in));          // issued with the polynomial loads, not after the stores
     Fr v[NOUT];
     if (KID == 7) {
       v[0] = fp_zero<FrParams>(); v[1] = fp_zero<FrParams>();
@@ -154,14 +155,28 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       if (KID == 6) v[0] = o0;
       else { const Fr d = fp_sub<FrParams>(o1, o0); v[0] = fp_sqr<FrParams>(o0); v[NOUT - 1] = fp_sqr<FrParams>(d); }
     } else {
+      // every global load of the pair (both polynomials) is issued before the first store: the bound arrays may alias
+      // nothing the compiler can prove, and a load -> bind -> store -> load chain costs ~2 us per polynomial on a small slab
       Fr l0, l1, r0, r1;
-      load_pair_l2h<FUSED>(P.in[0], P.out[0], g, r, l0, l1);
-      load_pair_l2h<FUSED>(P.in[1], P.out[1], g, r, r0, r1);
+      if (FUSED) {
+        const Fr* __restrict__ za = P.in[0] + 4 * g;
+        const Fr* __restrict__ zb = P.in[1] + 4 * g;
+        const Fr a0 = fp_load(za), a1 = fp_load(za + 1), a2 = fp_load(za + 2), a3 = fp_load(za + 3);
+        const Fr b0 = fp_load(zb), b1 = fp_load(zb + 1), b2 = fp_load(zb + 2), b3 = fp_load(zb + 3);
+        l0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+        l1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
+        r0 = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
+        r1 = fp_add<FrParams>(b2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b3, b2), r));
+        fp_store(P.out[0] + 2 * g, l0); fp_store(P.out[0] + 2 * g + 1, l1);
+        fp_store(P.out[1] + 2 * g, r0); fp_store(P.out[1] + 2 * g + 1, r1);
+      } else {
+        l0 = fp_load(P.in[0] + 2 * g); l1 = fp_load(P.in[0] + 2 * g + 1);
+        r0 = fp_load(P.in[1] + 2 * g); r1 = fp_load(P.in[1] + 2 * g + 1);
+      }
       if (KID == 0) v[0] = fp_add<FrParams>(l0, r0);
       else if (KID == 1) v[0] = fp_sub<FrParams>(l0, r0);
       else { v[0] = fp_mul<FrParams>(l0, r0); v[NOUT - 1] = fp_mul<FrParams>(fp_sub<FrParams>(l1, l0), fp_sub<FrParams>(r1, r0)); }
     }
-    const Fr ei = fp_load(e_in + ((g + g_off) & mask_in));
 #pragma unroll
     for (int k = 0; k < NOUT; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
   }
