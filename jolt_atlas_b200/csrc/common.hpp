@@ -56,15 +56,17 @@ struct ja_ctx {
   void* h_mapped = nullptr;
   void* d_mapped = nullptr;
   unsigned int seq = 0;
-  // challenge mailboxes of the pre-launched round kernels (fused_kernels.cuh: MailRef): ring of kMailEntries x 32 B in
-  // host-mapped memory; ahead_p / ahead_seq are non-null only while the engine enqueues the NEXT round's kernels
+  // challenge mailboxes of the pre-launched round kernels (fused_kernels.cuh: MailRef): ring of kMailEntries 16-byte
+  // entries in host-mapped memory + its device-memory twin; ahead_p / ahead_dev / ahead_tag are set only while the engine
+  // enqueues the NEXT round's kernels
   void* h_mail = nullptr;
   void* d_mail = nullptr;
-  uint32_t* d_mail_dev = nullptr;       // device-memory twin of the ring (relay target of block (0, 0))
-  volatile uint32_t* ahead_dev = nullptr;
+  void* d_mail_dev = nullptr;
   uint32_t mail_seq = 0;
-  const volatile uint32_t* ahead_p = nullptr;
-  uint32_t ahead_seq = 0;
+  uint8_t mail_uses[64] = {0};
+  const void* ahead_p = nullptr;
+  void* ahead_dev = nullptr;
+  uint32_t ahead_tag = 0;
   // flat host-mapped value array of the batched opening reduction (kMaxRowVals Fr + a sequence word at kRowSeqOffset)
   void* h_rowvals = nullptr;
   void* d_rowvals = nullptr;

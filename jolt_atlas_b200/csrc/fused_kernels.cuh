@@ -42,45 +42,51 @@ static __global__ void __launch_bounds__(64) k_collect_finals(CollectArgs a, int
 
 // ---- challenge mailbox --------------------------------------------------------------------------------------------------
 // The kernel of round j+1 is enqueued BEFORE the host has derived r_j (right behind round j's kernel), so that the
-// launch overhead and latency are off the Fiat-Shamir critical path: it starts as soon as round j's kernel retires and its
-// thread 0 polls a 32-byte entry in host-mapped memory until the host has written r_j and the expected sequence number
-// (challenge words first, sequence word last).  Bit 31 of the sequence word = abort (the host hit an error): the block
-// returns without touching anything.  p == nullptr: no mailbox, the challenge is the kernel parameter.
+// launch overhead and latency are off the Fiat-Shamir critical path: it starts as soon as round j's kernel retires and
+// waits on the device for the challenge.  A mailbox entry is ONE 16-byte vector in host-mapped memory: the 125-bit
+// challenge in words 0..3 and a 3-bit tag in the free top bits of word 3 (bits 29-30: use counter of the entry, cycling
+// 1,2,3 so that consecutive uses differ and zeroed memory never matches; bit 31: abort, the host hit an error).  One
+// aligned 16-byte load both polls and delivers the challenge: a read of host memory is a PCIe round trip of ~1 us and
+// they do NOT overlap (measured: 16 blocks reading the entry 17 us, 128 blocks 117 us; five 4-byte reads 5 us), so only
+// thread 0 of block (0, 0) polls the host entry; it republishes the vector in device memory, where the other blocks pick
+// it up from L2.  p == nullptr: no mailbox, the challenge is the kernel parameter.
 struct MailRef {
-  const volatile uint32_t* p;    // device address of the host-mapped entry: c[0..3], seq
-  volatile uint32_t* dev;        // the same entry in device memory: block (0, 0) relays the challenge to the other blocks
-  uint32_t seq;
+  const uint4* p;                // device address of the host-mapped entry
+  uint4* dev;                    // the entry's twin in device memory (relay target of block (0, 0))
+  uint32_t tag;                  // 1..3
 };
-// Only block (0, 0) polls the host entry (a PCIe round trip per poll; hundreds of blocks doing that congest the link and
-// cost > 100 us per round); it republishes challenge + sequence word in device memory, which the other blocks poll in L2.
+JA_DEV uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+JA_DEV void st_volatile_v4(uint4* p, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
   if (!m.p) return true;
-  __shared__ uint32_t s_mail[5];
+  __shared__ uint4 s_mail;
   if (threadIdx.x == 0) {
     const bool relay = blockIdx.x == 0 && blockIdx.y == 0;
-    const volatile uint32_t* src = relay ? m.p : m.dev;
+    const uint4* src = relay ? m.p : m.dev;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    uint32_t v;
+    uint4 v;
     for (unsigned int it = 0;; it++) {
-      v = src[4];
-      if ((v & 0x7fffffffu) == m.seq) break;
+      v = ld_volatile_v4(src);
+      if (((v.w >> 29) & 3u) == m.tag) break;
       if ((it & 255u) == 255u) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 5000000000ull) asm volatile("trap;");         // 5 s: the host is gone
       }
     }
-    const uint32_t c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
-    if (relay) {
-      m.dev[0] = c0; m.dev[1] = c1; m.dev[2] = c2; m.dev[3] = c3;
-      __threadfence();
-      m.dev[4] = v;
-    }
-    s_mail[0] = c0; s_mail[1] = c1; s_mail[2] = c2; s_mail[3] = c3; s_mail[4] = v >> 31;
+    if (relay) st_volatile_v4(m.dev, v);
+    s_mail = v;
   }
   __syncthreads();
-  r.c[0] = s_mail[0]; r.c[1] = s_mail[1]; r.c[2] = s_mail[2]; r.c[3] = s_mail[3];
-  return s_mail[4] == 0;
+  const uint4 v = s_mail;
+  r.c[0] = v.x; r.c[1] = v.y; r.c[2] = v.z; r.c[3] = v.w & 0x1fffffffu;
+  return (v.w >> 31) == 0;
 }
 
 struct FusedPolys {

@@ -479,7 +479,7 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
+#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
 #define JA_PROD_L(LL) do { if (same) { if (fz) JA_PROD_F(LL, true, true); else JA_PROD_F(LL, true, false); } \
                            else { if (fz) JA_PROD_F(LL, false, true); else JA_PROD_F(LL, false, false); } } while (0)
       switch (L) { case 2: JA_PROD_L(2); break; case 4: JA_PROD_L(4); break; case 8: JA_PROD_L(8); break; default: JA_PROD_L(16); break; }
@@ -495,7 +495,7 @@ struct DevInst : Inst {
     } else if (kind == JA_EVAL_DOT2 || kind == JA_EVAL_DOT3) {
       unsigned grid = grid_for(G);
       if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
-#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
+#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
       if (kind == JA_EVAL_DOT2) { if (fz) JA_DOT_F(2, true); else JA_DOT_F(2, false); }
       else { if (fz) JA_DOT_F(3, true); else JA_DOT_F(3, false); }
 #undef JA_DOT_F
@@ -506,7 +506,7 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
+#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
 #define JA_BOOL_L(LL) do { if (fz) JA_BOOL_F(LL, true); else JA_BOOL_F(LL, false); } while (0)
       switch (L) { case 2: JA_BOOL_L(2); break; case 4: JA_BOOL_L(4); break; case 8: JA_BOOL_L(8); break; default: JA_BOOL_L(16); break; }
 #undef JA_BOOL_L
@@ -520,7 +520,7 @@ struct DevInst : Inst {
       const size_t tpb = (tiles + grid - 1) / grid;
       grid = (tiles + tpb - 1) / tpb;
       const int np = (int)polys.size();
-#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq}))
+#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
 #define JA_S_K(KID) do { if (fz) JA_S_F(KID, true); else JA_S_F(KID, false); } while (0)
       switch (kind) {
         case JA_EVAL_ADD: JA_S_K(0); break;
@@ -1157,7 +1157,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
           if ((st = pb->prepare_pair(c, &B, &rb, 1))) return st;
           const unsigned int gx = std::max(A.nb, B.nb);
           int L = 2; while (L < A.d) L <<= 1;
-#define JA_PAIR(LL) do { if (ra.fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, true><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch, MailRef{c->ahead_p, c->ahead_dev, c->ahead_seq})); \
+#define JA_PAIR(LL) do { if (ra.fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, true><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag})); \
                            else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, false><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); } while (0)
           switch (L) { case 2: JA_PAIR(2); break; case 4: JA_PAIR(4); break; case 8: JA_PAIR(8); break; default: JA_PAIR(16); break; }
 #undef JA_PAIR
@@ -1181,15 +1181,15 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   const bool ahead_on = !ob && c->h_mail && getenv("JA_NO_AHEAD") == nullptr && ahead_allowed();
   size_t prelaunched = ~size_t(0);
   struct MailGuard {                       // an enqueued kernel must never be left waiting: errors abort it
-    volatile uint32_t* entry = nullptr; uint32_t seq = 0;
-    void post(const uint64_t ch[4]) {
+    volatile uint32_t* entry = nullptr; uint32_t tag = 0;
+    void post(const uint64_t ch[4]) {      // words 0..2 first, the tagged word 3 last (one 16-byte read on the device sees a prefix of these stores)
       const Challenge cc = to_challenge(ch);
-      entry[0] = cc.c[0]; entry[1] = cc.c[1]; entry[2] = cc.c[2]; entry[3] = cc.c[3];
+      entry[0] = cc.c[0]; entry[1] = cc.c[1]; entry[2] = cc.c[2];
       __atomic_thread_fence(__ATOMIC_RELEASE);
-      entry[4] = seq;
+      entry[3] = (cc.c[3] & 0x1fffffffu) | (tag << 29);
       entry = nullptr;
     }
-    ~MailGuard() { if (entry) { __atomic_thread_fence(__ATOMIC_RELEASE); entry[4] = seq | 0x80000000u; } }
+    ~MailGuard() { if (entry) { __atomic_thread_fence(__ATOMIC_RELEASE); entry[3] = (tag | 4u) << 29; } }
   } mail;
   for (size_t round = 0; round < max_rounds; round++) {
     const size_t remaining = max_rounds - round;
@@ -1207,16 +1207,16 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
         else if (next) { ok = insts[k]->can_ahead(round + 1 - (max_rounds - insts[k]->rounds)); any = true; }
       }
       if (ok && any) {
-        if (++c->mail_seq >= 0x7fffffffu) c->mail_seq = 1;
-        const uint32_t seq = c->mail_seq, idx = seq % kMailEntries;
-        c->ahead_seq = seq;
-        c->ahead_p = reinterpret_cast<const volatile uint32_t*>(c->d_mail) + 8 * idx;
-        c->ahead_dev = c->d_mail_dev + 8 * idx;
+        const uint32_t idx = (++c->mail_seq) % kMailEntries;
+        const uint32_t tag = c->mail_uses[idx] = (uint8_t)(c->mail_uses[idx] % 3 + 1);   // last tag of the entry -> 1, 2, 3, 1, ...: consecutive uses always differ
+        c->ahead_tag = tag;
+        c->ahead_p = reinterpret_cast<const char*>(c->d_mail) + 16 * idx;
+        c->ahead_dev = reinterpret_cast<char*>(c->d_mail_dev) + 16 * idx;
         for (size_t k = 0; k < n && !st; k++) if (remaining <= insts[k]->rounds) st = insts[k]->ahead_begin(c);
         if (!st) st = launch_round(round + 1);
         for (size_t k = 0; k < n; k++) if (remaining <= insts[k]->rounds) insts[k]->ahead_end(c);
-        c->ahead_p = nullptr; c->ahead_dev = nullptr; c->ahead_seq = 0;
-        mail.entry = reinterpret_cast<volatile uint32_t*>(c->h_mail) + 8 * idx; mail.seq = seq;
+        c->ahead_p = nullptr; c->ahead_dev = nullptr; c->ahead_tag = 0;
+        mail.entry = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<char*>(c->h_mail) + 16 * idx); mail.tag = tag;
         if (st) return st;
         prelaunched = round + 1;
       }

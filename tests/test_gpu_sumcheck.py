@@ -140,3 +140,34 @@ def test_tma_staged_round_kernels_match_oracle(ctx, kind_id, fam_ok, npoly, m):
         assert np.array_equal(res["challenges"], want["challenges"])
         assert np.array_equal(res["final_claims"], want["final_claims"])
         assert state == want["state"]
+
+
+def test_prelaunched_rounds_survive_mailbox_reuse(ctx):
+    """The engine enqueues round j+1 ahead of its challenge and hands it over through a ring of 64 tagged mailbox
+    entries (csrc/fused_kernels.cuh: MailRef).  Thousands of rounds on one context wrap every counter involved; every
+    proof must equal the first one (a stale-tag match would bind a stale challenge or clobber the result slot)."""
+    from jolt_atlas_b200 import Blake2bTranscriptState, MultilinearPolynomial, sumcheck_prove
+    rng = np.random.default_rng(77)
+    m = 5
+    z = rng.integers(0, 1 << 63, size=(2, 1 << m, 4), dtype=np.uint64)
+    z[..., 3] &= np.uint64((1 << 60) - 1)
+    w = np.zeros((m, 4), dtype=np.uint64)
+    w[:, 2] = rng.integers(0, 1 << 63, size=m, dtype=np.uint64)
+    w[:, 3] = rng.integers(0, 1 << 61, size=m, dtype=np.uint64)
+    claim = z[0, 0].copy()
+    want = ORC.sumcheck_prove(0, 2, z, w, claim, b"ring")
+    first = None
+    for it in range(5000):                       # 4 pre-launched rounds each: 20000 mailbox uses, > 256 per entry
+        ps = [MultilinearPolynomial.from_fr(ctx, z[0]), MultilinearPolynomial.from_fr(ctx, z[1])]
+        t = Blake2bTranscriptState(b"ring")
+        res = sumcheck_prove(ctx, 2, ps, claim, t, eq_w=w)
+        for p in ps:
+            p.free()
+        key = (b"".join(c.tobytes() for c in res["coeffs"]), res["final_claims"].tobytes(), t.state)
+        if first is None:
+            first = key
+            for r in range(m):
+                assert np.array_equal(res["coeffs"][r], want["coeffs"][r]), r
+            assert t.state == want["state"]
+        else:
+            assert key == first, it
