@@ -259,6 +259,11 @@ int32_t ja_addr_commit_many(ja_ctx*, const ja_srs*, const ja_addr* const* batche
 int32_t ja_addr_gather(ja_ctx*, const ja_addr*, const uint64_t* tables, ja_poly** out_polys);
 /* compute_ra_evals (subprotocols/shout.rs:549-598): out_G[i][k] = sum_{t: k_i[t] == k} eq(r_cycle, t); out_G = d x K Fr */
 int32_t ja_addr_ra_evals(ja_ctx*, const ja_addr*, const uint64_t* r_cycle, size_t log_t, uint64_t* out_G);
+/* The same for many address batches whose points are all known at once (OneHotPolynomialProverOpening::initialize for every
+ * committed polynomial of the opening reduction, joltworks/src/subprotocols/opening_reduction.rs:532-571): one
+ * synchronisation for all of them.  out_G[j] receives d_j x K_j Fr. */
+int32_t ja_addr_ra_evals_many(ja_ctx*, const ja_addr* const* addrs, const uint64_t* const* r_cycles, const size_t* log_ts, size_t n,
+                              uint64_t* const* out_G);
 
 /* build_materialized_rlc (joltworks/src/poly/rlc_polynomial.rs:13-78): the joint polynomial sum_i gamma^i P_i of the single
  * HyperKZG opening, built in HBM.  ja_poly_zeros(2^max_num_vars); one ja_rlc_add_onehot per address batch

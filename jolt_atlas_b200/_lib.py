@@ -72,6 +72,7 @@ SIGNATURES = {
     "ja_addr_commit_many": (C.c_int32, [vp, vp, vpp, C.c_size_t, u64p, i32p]),
     "ja_addr_gather": (C.c_int32, [vp, vp, u64p, vpp]),
     "ja_addr_ra_evals": (C.c_int32, [vp, vp, u64p, C.c_size_t, u64p]),
+    "ja_addr_ra_evals_many": (C.c_int32, [vp, vp, vp, vp, C.c_size_t, vp]),
     "ja_poly_zeros": (C.c_int32, [vp, C.c_size_t, vpp]),
     "ja_rlc_add_onehot": (C.c_int32, [vp, vp, vp, u64p]),
     "ja_rlc_add_dense": (C.c_int32, [vp, vp, vp, u64p]),

@@ -108,7 +108,7 @@ void ja_prof_post(ja_ctx* c);
 #define JA_LAUNCH(c, cls, ...) do { ja_prof_pre((c), (cls)); __VA_ARGS__; ja_prof_post((c)); } while (0)
 static constexpr int kMaxGrid = kSMs * 8;
 static constexpr int kMaxOut = 32;
-static constexpr size_t kPinnedBytes = 1 << 20;
+static constexpr size_t kPinnedBytes = 1 << 22;
 static constexpr size_t kRingBytes = 1 << 20;
 static constexpr int kSlots = 128;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;

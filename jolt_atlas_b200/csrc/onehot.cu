@@ -262,27 +262,82 @@ int32_t ja_addr_gather(ja_ctx* c, const ja_addr* a, const uint64_t* tables, ja_p
   return JA_OK;
 }
 
+// workspace of one compute_ra_evals job (Fr elements): eq table + per-tile partial bins
+static size_t ra_evals_ws(const ja_addr* a) {
+  const size_t tiles = (a->T + kRaTile - 1) / kRaTile;
+  return a->T + a->d * tiles * 16;
+}
+// enqueue one job on the context's stream; results (d x K Fr) go to d_out
+static int32_t ra_evals_enqueue(ja_ctx* c, const ja_addr* a, const uint64_t* r_cycle, size_t log_t, Fr* ws, Fr* d_out) {
+  const uint32_t tiles = (uint32_t)((a->T + kRaTile - 1) / kRaTile);
+  Fr *d_eq = ws, *d_part = ws + a->T;
+  int32_t st = eq_evals_device_pub(c, r_cycle, log_t, d_eq);
+  if (st) return st;
+  for (uint32_t k_base = 0; k_base < a->K; k_base += 16) {
+    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_partial<<<dim3(tiles, (unsigned)a->d), 256, 0, c->stream>>>(a->d_k, a->T, d_eq, (uint32_t)a->K, k_base, d_part));
+    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_final<<<(unsigned)((a->d * 16 + 255) / 256), 256, 0, c->stream>>>(d_part, tiles, (uint32_t)a->d, (uint32_t)a->K, k_base, d_out));
+  }
+  JA_CUDA(cudaGetLastError());
+  return JA_OK;
+}
+
 int32_t ja_addr_ra_evals(ja_ctx* c, const ja_addr* a, const uint64_t* r_cycle, size_t log_t, uint64_t* out_G) {
   JA_REQUIRE(c && a && r_cycle && out_G, "ja_addr_ra_evals: null argument");
   JA_REQUIRE((size_t(1) << log_t) == a->T, "ja_addr_ra_evals: r_cycle length does not match T");
   JA_REQUIRE(a->d * a->K * sizeof(Fr) <= kPinnedBytes, "ja_addr_ra_evals: result too large for the staging buffer");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  const uint32_t tiles = (uint32_t)((a->T + kRaTile - 1) / kRaTile);
   Fr* ws = nullptr;
-  const size_t n_part = a->d * (size_t)tiles * 16, n_out = a->d * a->K;
-  int32_t st = dev_alloc(c, (a->T + n_part + n_out) * sizeof(Fr), (void**)&ws);
+  const size_t n_out = a->d * a->K;
+  int32_t st = dev_alloc(c, (ra_evals_ws(a) + n_out) * sizeof(Fr), (void**)&ws);
   if (st) return st;
-  Fr *d_eq = ws, *d_part = ws + a->T, *d_out = d_part + n_part;
-  if ((st = eq_evals_device_pub(c, r_cycle, log_t, d_eq))) return st;
-  for (uint32_t k_base = 0; k_base < a->K; k_base += 16) {
-    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_partial<<<dim3(tiles, (unsigned)a->d), 256, 0, c->stream>>>(a->d_k, a->T, d_eq, (uint32_t)a->K, k_base, d_part));
-    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_final<<<(unsigned)((a->d * 16 + 255) / 256), 256, 0, c->stream>>>(d_part, tiles, (uint32_t)a->d, (uint32_t)a->K, k_base, d_out));
-  }
-  JA_CUDA(cudaGetLastError());
+  Fr* d_out = ws + ra_evals_ws(a);
+  if ((st = ra_evals_enqueue(c, a, r_cycle, log_t, ws, d_out))) return st;
   JA_CUDA(cudaMemcpyAsync(c->h_pinned, d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   JA_CUDA(cudaStreamSynchronize(c->stream));
   memcpy(out_G, c->h_pinned, n_out * sizeof(Fr));
+  dev_free(c, ws);
+  return JA_OK;
+}
+
+// compute_ra_evals for MANY address batches whose points are all known (the opening reduction initialises every one-hot
+// opening at once, opening_reduction.rs:532-571): the jobs are enqueued back to back and synchronised ONCE
+// (218 separate calls cost ~77 us each at GPT-2 size, most of it the per-call synchronisation and copy).
+// out_G[j] receives d_j x K_j Fr.
+int32_t ja_addr_ra_evals_many(ja_ctx* c, const ja_addr* const* addrs, const uint64_t* const* r_cycles, const size_t* log_ts, size_t n,
+                              uint64_t* const* out_G) {
+  JA_REQUIRE(c && addrs && r_cycles && log_ts && out_G, "ja_addr_ra_evals_many: null argument");
+  if (n == 0) return JA_OK;
+  size_t ws_total = 0, out_total = 0;
+  for (size_t j = 0; j < n; j++) {
+    JA_REQUIRE(addrs[j] && r_cycles[j] && out_G[j], "ja_addr_ra_evals_many: null job");
+    JA_REQUIRE((size_t(1) << log_ts[j]) == addrs[j]->T, "ja_addr_ra_evals_many: r_cycle length does not match T");
+    ws_total += ra_evals_ws(addrs[j]);
+    out_total += addrs[j]->d * addrs[j]->K;
+  }
+  JA_REQUIRE(out_total * sizeof(Fr) <= kPinnedBytes, "ja_addr_ra_evals_many: results too large for the staging buffer");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  Fr* ws = nullptr;
+  int32_t st = dev_alloc(c, (ws_total + out_total) * sizeof(Fr), (void**)&ws);
+  if (st) return st;
+  Fr* d_all = ws + ws_total;                     // every job's d x K results, contiguous: ONE copy back
+  size_t off = 0, ooff = 0, staged = 0;
+  for (size_t j = 0; j < n; j++) {
+    if (staged + 64 * 32 > kRingBytes / 2) { JA_CUDA(cudaStreamSynchronize(c->stream)); staged = 0; }   // never lap the upload ring
+    if ((st = ra_evals_enqueue(c, addrs[j], r_cycles[j], log_ts[j], ws + off, d_all + ooff))) return st;
+    off += ra_evals_ws(addrs[j]);
+    ooff += addrs[j]->d * addrs[j]->K;
+    staged += 64 * 32;
+  }
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, d_all, out_total * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  JA_CUDA(cudaStreamSynchronize(c->stream));
+  ooff = 0;
+  for (size_t j = 0; j < n; j++) {
+    const size_t cnt = addrs[j]->d * addrs[j]->K;
+    memcpy(out_G[j], c->h_pinned + 4 * ooff, cnt * sizeof(Fr));
+    ooff += cnt;
+  }
   dev_free(c, ws);
   return JA_OK;
 }

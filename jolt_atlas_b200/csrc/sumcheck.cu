@@ -1014,7 +1014,7 @@ struct OpenMember : Inst {
   void release(ja_ctx* c) override { if (i == 0) g->release(c); }
 };
 
-int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::vector<std::unique_ptr<Inst>>* out) {
+int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::vector<std::unique_ptr<Inst>>* out, const uint64_t* pre_G = nullptr) {
   int32_t st;
   if (d.kind == JA_INST_BOOLEANITY) {
     JA_REQUIRE(d.addr && d.host_tables && d.eq_w && d.aux_fr, "sumcheck: booleanity needs addr, G tables, r_cycle and gammas|r_address");
@@ -1055,9 +1055,15 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::vector<std::uniq
       g->B.swap(nb);
     }
     g->F = {host::FR_ONE};
-    std::vector<uint64_t> Gt(g->d * d.addr->K * 4);
-    int32_t st2 = ja_addr_ra_evals(c, d.addr, d.eq_w, d.eq_m, Gt.data());
-    if (st2) return st2;
+    std::vector<uint64_t> Gt_own;
+    const uint64_t* Gt_data = pre_G;                                // run() computes the G tables of all groups in one batch
+    if (!Gt_data) {
+      Gt_own.resize(g->d * d.addr->K * 4);
+      int32_t st2 = ja_addr_ra_evals(c, d.addr, d.eq_w, d.eq_m, Gt_own.data());
+      if (st2) return st2;
+      Gt_data = Gt_own.data();
+    }
+    struct { const uint64_t* p; const uint64_t* data() const { return p; } } Gt{Gt_data};
     g->G.resize(g->d);
     for (size_t i = 0; i < g->d; i++) { g->G[i].resize(d.addr->K); memcpy(g->G[i].data(), Gt.data() + i * d.addr->K * 4, d.addr->K * 32); }
     for (size_t i = 0; i < g->d; i++) {
@@ -1322,7 +1328,20 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
   std::vector<std::unique_ptr<Inst>> insts;
   int32_t st = JA_OK;
   const auto t_enter = std::chrono::steady_clock::now();
-  for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts);
+  // G tables (compute_ra_evals) of every one-hot opening group in ONE batch: their points are all known here
+  std::vector<std::vector<uint64_t>> pre(n);
+  {
+    std::vector<const ja_addr*> addrs; std::vector<const uint64_t*> pts; std::vector<size_t> lts; std::vector<uint64_t*> outs;
+    for (size_t k = 0; k < n; k++) {
+      const ja_sc_instance& d = descs[k];
+      if (d.kind != JA_INST_OPENING_ONEHOT || !d.addr || !d.eq_w || (size_t(1) << d.eq_m) != d.addr->T) continue;
+      pre[k].resize(d.addr->d * d.addr->K * 4);
+      addrs.push_back(d.addr); pts.push_back(d.eq_w); lts.push_back(d.eq_m); outs.push_back(pre[k].data());
+    }
+    if (addrs.size() >= 2) st = ja_addr_ra_evals_many(c, addrs.data(), pts.data(), lts.data(), addrs.size(), outs.data());
+    else for (auto& v : pre) v.clear();
+  }
+  for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts, pre[k].empty() ? nullptr : pre[k].data());
   int next_slot = 0;
   for (auto& i : insts) if (i->needs_slot()) i->slot_id = next_slot++;
   if (!st && next_slot > kSlots) st = fail(JA_ERR_UNSUPPORTED, "sumcheck: more than " + std::to_string(kSlots) + " kernel-backed instances / groups in one batch");
