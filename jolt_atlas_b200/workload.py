@@ -398,7 +398,12 @@ def algorithmic_fieldmuls(inputs) -> dict:
         per_pair = {"product": npoly * npoly + npoly, "booleanity": 5 * npoly, "split_eq": 2 * npoly + 2, "dot": 4,
                     "opening": 3 * npoly}[body]
         fused += per_pair * pairs
-    return {"onehot_point_sum": 10 * adds, "msm_accumulate": 10 * 4 * n * 16, "sumcheck_fused": fused}
+    # HyperKZG open: MSMs of 2^(ell-1), ..., 2 pairs (phase 1) and 3 x 2^ell (witness); one mixed addition per scalar and
+    # window: 13 windows of 20 bits through the wide fixed-base table (SRS >= 2^21 points, job >= 2^21), else 16 of 16 bits
+    def windows(size):
+        return 13 if (n >= (1 << 21) and size >= (1 << 21)) else 16
+    msm_adds = 3 * n * windows(n) + sum((n >> j) * windows(n >> j) for j in range(1, inputs["ell"]))
+    return {"onehot_point_sum": 10 * adds, "msm_accumulate": 10 * msm_adds, "sumcheck_fused": fused}
 
 
 def config_dict(config: str, inputs, world: int = 1, shard: bool = False) -> dict:
