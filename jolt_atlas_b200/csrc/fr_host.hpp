@@ -4,6 +4,7 @@
 // (unipoly.rs), transcript scalar serialisation (blake2b.rs:138-146).
 // This is product code (tiny scalar math between kernel launches), not a CPU fallback for any kernel.
 #pragma once
+#include <alloca.h>
 #include <cstdint>
 #include <cstring>
 
@@ -143,6 +144,21 @@ static inline FrH inv(const FrH& a) {
   FrH r; memcpy(r.l, is_one(u) ? x1 : x2, 32);            // = a^-1 * R^-1 as a plain integer
   static const FrH R3 = mul(FR_R2, FR_R2);                // R^2 * R^2 * R^-1
   return mul(r, R3);
+}
+// Montgomery's trick: every element of v replaced by its inverse with ONE inversion and 3 (n - 1) products; zeros stay
+// zero (same convention as inv).
+static inline void batch_inv(FrH* v, size_t n) {
+  if (n == 0) return;
+  FrH* pre = static_cast<FrH*>(alloca(n * sizeof(FrH)));
+  FrH run = FR_ONE;
+  for (size_t i = 0; i < n; i++) { pre[i] = run; if (!v[i].is_zero()) run = mul(run, v[i]); }
+  FrH iv = inv(run);
+  for (size_t i = n; i-- > 0;) {
+    if (v[i].is_zero()) continue;
+    const FrH t = mul(iv, pre[i]);
+    iv = mul(iv, v[i]);
+    v[i] = t;
+  }
 }
 // challenge limbs {0,0,lo,hi} are already a valid Montgomery representation (mont_ark_u128.rs:79-84)
 static inline FrH from_limbs(const uint64_t* p) { FrH r; memcpy(r.l, p, 32); return r; }

@@ -15,12 +15,13 @@
 namespace ja {
 
 struct Publish {
-  Fr* vals;                      // device address of the mapped host slot (kMaxOut Fr)
-  volatile unsigned int* seq;    // device address of the slot's sequence word
-  unsigned int value;
+  Fr* vals;                      // device address of the mapped host slot (kMaxOut elements, 48 bytes each when tagged)
+  volatile unsigned int* seq;    // device address of the slot's sequence word (fence + flag protocol: k_round_open only)
+  unsigned int value;            // the round's tag / sequence value (never 0)
 };
-// Call from every thread of the block that wrote pub.vals.  Only warp 0 writes the sums (grid_sum: thread 0;
-// block_sum_by_lane: threads < L <= 16), so only warp 0 fences at system scope before lane 0 raises the flag.
+// Two publication protocols.  Tagged (every round kernel but k_round_open): store_tagged (poly_kernels.cuh), no fence.
+// Fence + flag (k_round_open, k_round_open_rows): plain stores, __threadfence_system, then the sequence word.
+// publish_flag: call from every thread of the block that wrote pub.vals; only warp 0 writes the sums.
 JA_DEV void publish_flag(const Publish& pub) {
   if (threadIdx.x < 32) {
     __threadfence_system();
@@ -120,15 +121,35 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
           size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
           size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */,
           MailRef mail = MailRef{nullptr, nullptr, 0}) {
-  if (FUSED && !mail_wait(r, mail)) return;
   constexpr int NOUT = SOut<KID>::N;
-  Fr outer[NOUT], inner[NOUT];
-#pragma unroll
-  for (int k = 0; k < NOUT; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
+  constexpr int NP = KID == 7 ? 0 : ((KID == 3 || KID == 6) ? 1 : 2);      // polynomials with register-staged operands
   const size_t mask_in = (size_t(1) << bits_in) - 1;
   const size_t g_begin = (size_t)blockIdx.x * tiles_per_block * kBlock;
   size_t g_end = g_begin + tiles_per_block * kBlock;
   if (g_end > G) g_end = G;
+  // The operands of the thread's first pair (and its eq weight) do not depend on the challenge: a pre-launched kernel
+  // issues these loads BEFORE it waits on the mailbox, so their latency is spent while the host is still hashing.
+  Fr a[NP > 0 ? NP : 1][4];
+  Fr ei = fp_zero<FrParams>();
+  {
+    const size_t g = g_begin + threadIdx.x;
+    if (g < g_end) {
+      ei = fp_load(e_in + ((g + g_off) & mask_in));
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        if (FUSED) {
+          const Fr* __restrict__ z = P.in[q] + 4 * g;
+          a[q][0] = fp_load(z); a[q][1] = fp_load(z + 1); a[q][2] = fp_load(z + 2); a[q][3] = fp_load(z + 3);
+        } else {
+          a[q][0] = fp_load(P.in[q] + 2 * g); a[q][1] = fp_load(P.in[q] + 2 * g + 1);
+        }
+      }
+    }
+  }
+  if (FUSED && !mail_wait(r, mail)) return;
+  Fr outer[NOUT], inner[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
   size_t cur_xout = ~size_t(0);
   for (size_t g = g_begin + threadIdx.x; g < g_end; g += kBlock) {
     const size_t x_out = (g + g_off) >> bits_in;
@@ -143,7 +164,20 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       }
       cur_xout = x_out;
     }
-    const Fr ei = fp_load(e_in + ((g + g_off) & mask_in));          // issued with the polynomial loads, not after the stores
+    if (g != g_begin + threadIdx.x) {
+      // every global load of the pair (both polynomials) is issued before the first store: the bound arrays may alias
+      // nothing the compiler can prove, and a load -> bind -> store -> load chain costs ~2 us per polynomial on a small slab
+      ei = fp_load(e_in + ((g + g_off) & mask_in));
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        if (FUSED) {
+          const Fr* __restrict__ z = P.in[q] + 4 * g;
+          a[q][0] = fp_load(z); a[q][1] = fp_load(z + 1); a[q][2] = fp_load(z + 2); a[q][3] = fp_load(z + 3);
+        } else {
+          a[q][0] = fp_load(P.in[q] + 2 * g); a[q][1] = fp_load(P.in[q] + 2 * g + 1);
+        }
+      }
+    }
     Fr v[NOUT];
     if (KID == 7) {
       v[0] = fp_zero<FrParams>(); v[1] = fp_zero<FrParams>();
@@ -155,33 +189,23 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
         v[0] = fp_add<FrParams>(v[0], fp_mul<FrParams>(fp_mul<FrParams>(gm, h0), fp_sub<FrParams>(h0, fp_one<FrParams>())));
         v[1] = fp_add<FrParams>(v[1], fp_mul<FrParams>(fp_mul<FrParams>(gm, b), b));
       }
-    } else if (KID == 3 || KID == 6) {
-      Fr o0, o1;
-      load_pair_l2h<FUSED>(P.in[0], P.out[0], g, r, o0, o1);
-      if (KID == 6) v[0] = o0;
-      else { const Fr d = fp_sub<FrParams>(o1, o0); v[0] = fp_sqr<FrParams>(o0); v[NOUT - 1] = fp_sqr<FrParams>(d); }
     } else {
-      // every global load of the pair (both polynomials) is issued before the first store: the bound arrays may alias
-      // nothing the compiler can prove, and a load -> bind -> store -> load chain costs ~2 us per polynomial on a small slab
-      Fr l0, l1, r0, r1;
-      if (FUSED) {
-        const Fr* __restrict__ za = P.in[0] + 4 * g;
-        const Fr* __restrict__ zb = P.in[1] + 4 * g;
-        const Fr a0 = fp_load(za), a1 = fp_load(za + 1), a2 = fp_load(za + 2), a3 = fp_load(za + 3);
-        const Fr b0 = fp_load(zb), b1 = fp_load(zb + 1), b2 = fp_load(zb + 2), b3 = fp_load(zb + 3);
-        l0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
-        l1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
-        r0 = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
-        r1 = fp_add<FrParams>(b2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b3, b2), r));
-        fp_store(P.out[0] + 2 * g, l0); fp_store(P.out[0] + 2 * g + 1, l1);
-        fp_store(P.out[1] + 2 * g, r0); fp_store(P.out[1] + 2 * g + 1, r1);
-      } else {
-        l0 = fp_load(P.in[0] + 2 * g); l1 = fp_load(P.in[0] + 2 * g + 1);
-        r0 = fp_load(P.in[1] + 2 * g); r1 = fp_load(P.in[1] + 2 * g + 1);
+      Fr lo[NP > 0 ? NP : 1], hi[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        if (FUSED) {
+          lo[q] = fp_add<FrParams>(a[q][0], fp_mul_challenge<FrParams>(fp_sub<FrParams>(a[q][1], a[q][0]), r));
+          hi[q] = fp_add<FrParams>(a[q][2], fp_mul_challenge<FrParams>(fp_sub<FrParams>(a[q][3], a[q][2]), r));
+          fp_store(P.out[q] + 2 * g, lo[q]); fp_store(P.out[q] + 2 * g + 1, hi[q]);
+        } else {
+          lo[q] = a[q][0]; hi[q] = a[q][1];
+        }
       }
-      if (KID == 0) v[0] = fp_add<FrParams>(l0, r0);
-      else if (KID == 1) v[0] = fp_sub<FrParams>(l0, r0);
-      else { v[0] = fp_mul<FrParams>(l0, r0); v[NOUT - 1] = fp_mul<FrParams>(fp_sub<FrParams>(l1, l0), fp_sub<FrParams>(r1, r0)); }
+      if (KID == 6) v[0] = lo[0];
+      else if (KID == 3) { const Fr d = fp_sub<FrParams>(hi[0], lo[0]); v[0] = fp_sqr<FrParams>(lo[0]); v[NOUT - 1] = fp_sqr<FrParams>(d); }
+      else if (KID == 0) v[0] = fp_add<FrParams>(lo[0], lo[NP - 1]);
+      else if (KID == 1) v[0] = fp_sub<FrParams>(lo[0], lo[NP - 1]);
+      else { v[0] = fp_mul<FrParams>(lo[0], lo[NP - 1]); v[NOUT - 1] = fp_mul<FrParams>(fp_sub<FrParams>(hi[0], lo[0]), fp_sub<FrParams>(hi[NP - 1], lo[NP - 1])); }
     }
 #pragma unroll
     for (int k = 0; k < NOUT; k++) inner[k] = fp_add<FrParams>(inner[k], fp_mul<FrParams>(ei, v[k]));
@@ -191,15 +215,49 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
 #pragma unroll
     for (int k = 0; k < NOUT; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
   }
-  if (grid_sum<NOUT>(outer, partials, counter, pub.vals)) publish_flag(pub);
+  grid_sum_ex<NOUT>(outer, partials, counter, pub.vals, blockIdx.x, gridDim.x, pub.value);
 }
 
 // ---- product of d <= 16 linear factors, warp-transposed (see k_round_eval_prod_t), with the fused bind -------------
-template <int L, bool SAME, bool FUSED>
-JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+// Operand loads of a thread's FIRST pair are issued before the mailbox wait (they do not depend on the challenge): on a
+// pre-launched kernel the L2 / HBM latency is then spent while the host is still hashing.
+// BLOCK = 128 on small slabs (one warp per scheduler: a dependent chain of Montgomery products issues at one IMAD.WIDE
+// per 4 cycles per scheduler, so two resident warps double the latency of the chain).
+
+// cross-block tail shared by the product bodies: L per-block sums -> partials -> last block -> tagged publication
+template <int L, int BLOCK>
+JA_DEV void prod_tail(Fr tot /* valid in threads < L */, Fr* partials, unsigned int* counter, const Publish& pub, unsigned int bx, unsigned int nb) {
+  constexpr int GPB = BLOCK / L;
+  const int li = threadIdx.x & (L - 1);
+  if (nb == 1) {
+    if (threadIdx.x < L) store_tagged(pub.vals, threadIdx.x, tot, pub.value);
+    return;
+  }
+  if (threadIdx.x < L) fp_store(partials + (size_t)bx * L + threadIdx.x, tot);
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(counter, nb - 1) == nb - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Fr acc = fp_zero<FrParams>();
+  for (unsigned b = threadIdx.x / L; b < nb; b += GPB) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(partials + (size_t)b * L + li);
+    Fr t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.l[i] = q[i];
+    acc = fp_add<FrParams>(acc, t);
+  }
+  tot = block_sum_by_lane<L, BLOCK>(acc);
+  if (threadIdx.x < L) store_tagged(pub.vals, threadIdx.x, tot, pub.value);
+}
+
+template <int L, bool SAME, bool FUSED, int BLOCK = kBlock>
+JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
                             int bits_in, size_t G, size_t pairs_per_block, Fr* partials /* [nb][L] */, unsigned int* counter,
                             const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off = 0) {
-  constexpr int GPB = kBlock / L;
+  constexpr int GPB = BLOCK / L;
   const int li = threadIdx.x & (L - 1);
   const int group = threadIdx.x / L;
   const bool pad = li >= d;
@@ -211,23 +269,34 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, cons
   const size_t g_begin = (size_t)bx * pairs_per_block;
   size_t g_end = g_begin + pairs_per_block;
   if (g_end > G) g_end = G;
+  Fr a0, a1, a2, a3;
+  {
+    const size_t g = g_begin + group;
+    const size_t gl = g < g_end ? g : g_begin;
+    if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+    else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
+  }
+  if (FUSED && !mail_wait(r, mail)) return;
   Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
   size_t cur_xout = ~size_t(0);
   for (size_t base = g_begin; base < g_end; base += GPB) {
     const size_t g = base + group;
     const bool active = g < g_end;
     const size_t gl = active ? g : g_begin;
+    if (base != g_begin) {
+      if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+      else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); }
+    }
     Fr p0, dp;
     if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
     else if (FUSED) {
-      const Fr a0 = fp_load(zin + 4 * gl), a1 = fp_load(zin + 4 * gl + 1), a2 = fp_load(zin + 4 * gl + 2), a3 = fp_load(zin + 4 * gl + 3);
       p0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
       const Fr p1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
       if (active && (!SAME || li == 0)) { fp_store(zout + 2 * gl, p0); fp_store(zout + 2 * gl + 1, p1); }
       dp = fp_sub<FrParams>(p1, p0);
     } else {
-      p0 = fp_load(zin + 2 * gl);
-      dp = fp_sub<FrParams>(fp_load(zin + 2 * gl + 1), p0);
+      p0 = a0;
+      dp = fp_sub<FrParams>(a1, p0);
     }
     Fr v[L];
     Fr cur = p0;
@@ -248,31 +317,70 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, const Challenge& r, cons
     }
   }
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
-  Fr tot = block_sum_by_lane<L>(outer);
-  if (nb == 1) {
-    if (threadIdx.x < L) fp_store(pub.vals + threadIdx.x, tot);
-    publish_flag(pub);
-    return;
+  const Fr tot = block_sum_by_lane<L, BLOCK>(outer);
+  prod_tail<L, BLOCK>(tot, partials, counter, pub, bx, nb);
+}
+
+// Latency variant for small slabs of a product of 9..16 factors: 64 threads per pair, thread (li, s) = (polynomial, quarter of
+// the 16 evaluation points X = 1..15 and "infinity").  Each thread forms its polynomial's 4 values, then the 16 lanes of a
+// quarter multiply across polynomials: exchange on bit 3 (4 values -> 2, two products), on bit 2 (2 -> 1, one product) and a
+// multiplying butterfly on bits 1, 0: 5 dependent products per thread instead of 15, at 1.3x the total work and 4x the
+// (L2-resident) loads.  Block = 128 threads = 2 pairs; the launcher uses it while the whole grid fits the SMs once or twice.
+constexpr int kWideBlock = 128;
+constexpr size_t kWideMaxPairs = 256;      // measured on B200: 64 threads per pair wins up to 2^8 pairs, loses from 2^10 (scripts/small_probe.py)
+constexpr size_t kSmallMaxPairs = 1024;    // 128-thread blocks up to here
+template <bool FUSED>
+JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out,
+                                   const Fr* __restrict__ e_in, int bits_in, size_t G, Fr* partials /* [nb][16] */, unsigned int* counter,
+                                   const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off = 0) {
+  constexpr int L = 16, PPB = kWideBlock / 64;
+  const int t = threadIdx.x & 63, li = t & 15, s = t >> 4, group = threadIdx.x >> 6;
+  const bool pad = li >= d;
+  const size_t g = (size_t)bx * PPB + group;
+  const bool active = g < G;
+  const size_t gl = active ? g : (size_t)bx * PPB;
+  const Fr* __restrict__ zin = P.in[pad ? 0 : li];
+  Fr* __restrict__ zout = P.out[pad ? 0 : li];
+  Fr a0, a1, a2, a3;
+  if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+  else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
+  // the pair's eq weight, formed while the challenge is still on its way
+  const Fr ew = fp_mul<FrParams>(fp_load(e_out + ((gl + g_off) >> bits_in)), fp_load(e_in + ((gl + g_off) & ((size_t(1) << bits_in) - 1))));
+  if (FUSED && !mail_wait(r, mail)) return;
+  Fr p0, dp;
+  if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
+  else if (FUSED) {
+    p0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+    const Fr p1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
+    if (active && s == 0) { fp_store(zout + 2 * gl, p0); fp_store(zout + 2 * gl + 1, p1); }
+    dp = fp_sub<FrParams>(p1, p0);
+  } else {
+    p0 = a0;
+    dp = fp_sub<FrParams>(a1, p0);
   }
-  if (threadIdx.x < L) fp_store(partials + (size_t)bx * L + threadIdx.x, tot);
-  __shared__ bool s_last;
-  __threadfence();
+  // my points k = 4 s + j: X = k + 1 for k < 15, k = 15 the leading coefficient (pad lanes: the constant 1)
+  const Fr dp4 = fp_dbl<FrParams>(fp_dbl<FrParams>(dp));
+  Fr off = (s & 1) ? dp4 : fp_zero<FrParams>();
+  if (s & 2) off = fp_add<FrParams>(off, fp_dbl<FrParams>(dp4));
+  const Fr v0 = fp_add<FrParams>(fp_add<FrParams>(p0, dp), off);
+  const Fr v1 = fp_add<FrParams>(v0, dp), v2 = fp_add<FrParams>(v1, dp);
+  const Fr v3 = s == 3 ? (pad ? p0 : dp) : fp_add<FrParams>(v2, dp);
+  const bool hi8 = (li & 8) != 0, hi4 = (li & 4) != 0;
+  const Fr n0 = fp_mul<FrParams>(fr_select(hi8, v2, v0), fr_shfl_xor(fr_select(hi8, v0, v2), 8));
+  const Fr n1 = fp_mul<FrParams>(fr_select(hi8, v3, v1), fr_shfl_xor(fr_select(hi8, v1, v3), 8));
+  Fr w = fp_mul<FrParams>(fr_select(hi4, n1, n0), fr_shfl_xor(fr_select(hi4, n0, n1), 4));
+  w = fp_mul<FrParams>(w, fr_shfl_xor(w, 2));
+  w = fp_mul<FrParams>(w, fr_shfl_xor(w, 1));
+  // point k = 4 s + 2 hi8 + hi4 is complete in all four lanes that share (s, hi8, hi4); lane (li & 3) == 0 weighs it
+  __shared__ Fr s_red[PPB][L];
+  if ((li & 3) == 0) s_red[group][4 * s + (hi8 ? 2 : 0) + (hi4 ? 1 : 0)] = active ? fp_mul<FrParams>(ew, w) : fp_zero<FrParams>();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicInc(counter, nb - 1) == nb - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  Fr acc = fp_zero<FrParams>();
-  for (unsigned b = threadIdx.x / L; b < nb; b += GPB) {
-    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(partials + (size_t)b * L + li);
-    Fr t;
+  Fr tot = fp_zero<FrParams>();
+  if (threadIdx.x < L) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) t.l[i] = q[i];
-    acc = fp_add<FrParams>(acc, t);
+    for (int gp = 0; gp < PPB; gp++) tot = fp_add<FrParams>(tot, s_red[gp][threadIdx.x]);
   }
-  tot = block_sum_by_lane<L>(acc);
-  if (threadIdx.x < L) fp_store(pub.vals + threadIdx.x, tot);
-  publish_flag(pub);
+  prod_tail<L, kWideBlock>(tot, partials, counter, pub, bx, nb);
 }
 
 template <int L, bool SAME, bool FUSED>
@@ -280,19 +388,25 @@ __global__ void __launch_bounds__(kBlock)
 k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0,
              MailRef mail = MailRef{nullptr, nullptr, 0}) {
-  if (FUSED && !mail_wait(r, mail)) return;
-  round_prod_body<L, SAME, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
+  round_prod_body<L, SAME, FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
+}
+template <bool FUSED>
+__global__ void __launch_bounds__(kWideBlock)
+k_round_prod16_wide(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
+                    Fr* partials /* [gridDim.x][16] */, unsigned int* counter, Publish pub, size_t g_off = 0,
+                    MailRef mail = MailRef{nullptr, nullptr, 0}) {
+  round_prod16_wide_body<FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 
 // ---- booleanity phase 2, lane-parallel (booleanity.rs:254-301) ---------------------------------------------------------
 // [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] per pair: a group of L = next_pow2(d) lanes owns one pair, lane i
 // loads polynomial i (with the fused bind), forms its two terms (4 products) and the group adds them up with shuffles —
 // d times more threads and d times shorter dependency chains than one thread looping over the d polynomials.
-template <int L, bool FUSED>
-JA_DEV void round_bool_body(const FusedPolys& P, int d, const Challenge& r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+template <int L, bool FUSED, int BLOCK = kBlock>
+JA_DEV void round_bool_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
                             int bits_in, size_t G, size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials,
                             unsigned int* counter, const Publish& pub, unsigned int bx, unsigned int nb) {
-  constexpr int GPB = kBlock / L;
+  constexpr int GPB = BLOCK / L;
   const int li = threadIdx.x & (L - 1);
   const int group = threadIdx.x / L;
   const bool pad = li >= d;
@@ -303,6 +417,14 @@ JA_DEV void round_bool_body(const FusedPolys& P, int d, const Challenge& r, cons
   const size_t g_begin = (size_t)bx * pairs_per_block;
   size_t g_end = g_begin + pairs_per_block;
   if (g_end > G) g_end = G;
+  Fr a0, a1, a2, a3;
+  {
+    const size_t g = g_begin + group;
+    const size_t gl = g < g_end ? g : g_begin;
+    if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+    else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
+  }
+  if (FUSED && !mail_wait(r, mail)) return;
   Fr outer[2], inner[2];
 #pragma unroll
   for (int k = 0; k < 2; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
@@ -311,17 +433,20 @@ JA_DEV void round_bool_body(const FusedPolys& P, int d, const Challenge& r, cons
     const size_t g = base + group;
     const bool active = g < g_end;
     const size_t gl = active ? g : g_begin;
+    if (base != g_begin) {
+      if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+      else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); }
+    }
     Fr v0 = fp_zero<FrParams>(), v1 = fp_zero<FrParams>();
     if (!pad) {
       Fr h0, h1;
       if (FUSED) {
-        const Fr a0 = fp_load(zin + 4 * gl), a1 = fp_load(zin + 4 * gl + 1), a2 = fp_load(zin + 4 * gl + 2), a3 = fp_load(zin + 4 * gl + 3);
         h0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
         h1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
         if (active) { fp_store(zout + 2 * gl, h0); fp_store(zout + 2 * gl + 1, h1); }
       } else {
-        h0 = fp_load(zin + 2 * gl);
-        h1 = fp_load(zin + 2 * gl + 1);
+        h0 = a0;
+        h1 = a1;
       }
       const Fr b = fp_sub<FrParams>(h1, h0);
       v0 = fp_mul<FrParams>(fp_mul<FrParams>(gm, h0), fp_sub<FrParams>(h0, fp_one<FrParams>()));
@@ -352,7 +477,7 @@ JA_DEV void round_bool_body(const FusedPolys& P, int d, const Challenge& r, cons
 #pragma unroll
     for (int k = 0; k < 2; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
   }
-  if (grid_sum_ex<2>(outer, partials, counter, pub.vals, bx, nb)) publish_flag(pub);
+  grid_sum_ex<2>(outer, partials, counter, pub.vals, bx, nb, pub.value);
 }
 
 template <int L, bool FUSED>
@@ -360,13 +485,14 @@ __global__ void __launch_bounds__(kBlock)
 k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
              MailRef mail = MailRef{nullptr, nullptr, 0}) {
-  if (FUSED && !mail_wait(r, mail)) return;
-  round_bool_body<L, FUSED>(P, d, r, e_out, e_in, bits_in, G, pairs_per_block, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
+  round_bool_body<L, FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
 }
 
 // ---- RA one-hot checks: RaVirtual (product of d) and Booleanity phase 2 of the same batch in ONE launch -------------------
 // The two instances of a round are independent; launched back to back on one stream they serialise two latency-bound
-// kernels.  blockIdx.y selects the body, each with its own sub-grid, scratch and result slot.
+// kernels.  blockIdx.y selects the body, each with its own sub-grid, scratch and result slot.  Blocks beyond a body's
+// sub-grid exit at once (block (0, 0), the mailbox relay, always belongs to body A).
+// BLOCK = kWideBlock: the small-slab variant (128-thread blocks); WIDE: the product of 9..16 factors runs 64 threads per pair.
 struct PairArgs {
   FusedPolys P;
   int d;
@@ -378,16 +504,18 @@ struct PairArgs {
   Fr* partials; unsigned int* counter;
   Publish pub;
 };
-template <int L, bool FUSED>
-__global__ void __launch_bounds__(kBlock)
+template <int L, bool FUSED, int BLOCK = kBlock, bool WIDE = false>
+__global__ void __launch_bounds__(BLOCK)
 k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{nullptr, nullptr, 0}) {
-  if (FUSED && !mail_wait(r, mail)) return;
   if (blockIdx.y == 0) {
-    if (blockIdx.x < A.nb)
-      round_prod_body<L, false, FUSED>(A.P, A.d, r, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
+    if (blockIdx.x >= A.nb) return;
+    if constexpr (L == 16 && BLOCK == kWideBlock && WIDE)
+      round_prod16_wide_body<FUSED>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
+    else
+      round_prod_body<L, false, FUSED, BLOCK>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
   } else {
-    if (blockIdx.x < B.nb)
-      round_bool_body<L, FUSED>(B.P, B.d, r, B.e_out, B.e_in, B.bits_in, (size_t)B.G, (size_t)B.ppb, B.gammas, B.partials, B.counter, B.pub, blockIdx.x, B.nb);
+    if (blockIdx.x >= B.nb) return;
+    round_bool_body<L, FUSED, BLOCK>(B.P, B.d, r, mail, B.e_out, B.e_in, B.bits_in, (size_t)B.G, (size_t)B.ppb, B.gammas, B.partials, B.counter, B.pub, blockIdx.x, B.nb);
   }
 }
 
@@ -429,7 +557,7 @@ k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array:
 #pragma unroll
     for (int k = 0; k < NOUT; k++) acc[k] = fp_add<FrParams>(acc[k], prod[k]);
   }
-  if (grid_sum<NOUT>(acc, partials, counter, pub.vals)) publish_flag(pub);
+  grid_sum_ex<NOUT>(acc, partials, counter, pub.vals, blockIdx.x, gridDim.x, pub.value);
 }
 
 // ---- opening reduction, HighToLow (opening_reduction.rs:355-403 dense, :630-673 one-hot cycle rounds) --------------------

@@ -51,12 +51,25 @@ JA_DEV Fr fr_warp_sum(Fr a) {
   return a;  // lane 0 holds the sum
 }
 
+// Publication of a field element into host-mapped memory WITHOUT a system-scope fence (the fence + flag protocol costs
+// ~2 us per round: scripts/micro/latency_probe.cu).  Element k of a slot is three 16-byte vectors
+// [l0 l1 l2 tag] [l3 l4 l5 tag] [l6 l7 0 tag]; an aligned 16-byte store reaches host memory as a unit, so every vector
+// validates itself and the host waits until all vectors it expects carry the round's tag (sumcheck.cu: wait_slot).
+JA_DEV void store_tagged(Fr* slot_base, int k, const Fr& v, unsigned int tag) {
+  uint4* p = reinterpret_cast<uint4*>(slot_base) + 3 * k;
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(tag) : "memory");
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 1), "r"(v.l[3]), "r"(v.l[4]), "r"(v.l[5]), "r"(tag) : "memory");
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 2), "r"(v.l[6]), "r"(v.l[7]), "r"(0u), "r"(tag) : "memory");
+}
+
 // Block-wide exact field sum of NOUT values per thread, then grid-wide via per-block partials and a
 // "last block" pass.  `partials` holds gridDim.x * NOUT Fr; `counter` must be 0 on entry and is reset.
 // Returns true (block-uniform) in the one block that wrote `out`.  bx / nb = index of this block and number of blocks
 // taking part (a kernel that hosts several independent reductions passes its own sub-grid).
+// tag != 0: `out` is a host-mapped result slot and the sums are published with store_tagged.
 template <int NOUT>
-JA_DEV bool grid_sum_ex(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out, unsigned int bx, unsigned int nb) {
+JA_DEV bool grid_sum_ex(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr* out, unsigned int bx, unsigned int nb,
+                        unsigned int tag = 0) {
   __shared__ Fr s_part[kBlock / 32][NOUT];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,16 +84,14 @@ JA_DEV bool grid_sum_ex(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr
     for (int k = 0; k < NOUT; k++) {
       Fr v = lane < (blockDim.x >> 5) ? s_part[lane][k] : fp_zero<FrParams>();
       v = fr_warp_sum(v);
-      if (lane == 0) fp_store(&partials[(size_t)bx * NOUT + k], v);
+      if (lane == 0) {
+        if (nb != 1) fp_store(&partials[(size_t)bx * NOUT + k], v);
+        else if (tag) store_tagged(out, k, v, tag);
+        else fp_store(&out[k], v);
+      }
     }
   }
-  if (nb == 1) {
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < NOUT; k++) out[k] = partials[k];
-    }
-    return true;
-  }
+  if (nb == 1) return true;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -110,7 +121,10 @@ JA_DEV bool grid_sum_ex(Fr (&acc)[NOUT], Fr* partials, unsigned int* counter, Fr
     for (int k = 0; k < NOUT; k++) {
       Fr v = lane < (blockDim.x >> 5) ? s_part[lane][k] : fp_zero<FrParams>();
       v = fr_warp_sum(v);
-      if (lane == 0) fp_store(&out[k], v);
+      if (lane == 0) {
+        if (tag) store_tagged(out, k, v, tag);
+        else fp_store(&out[k], v);
+      }
     }
   }
   return true;
@@ -406,9 +420,9 @@ template <int M> struct LaneProduct {     // M = number of values currently held
 template <> struct LaneProduct<1> { JA_DEV static void run(Fr (&)[1], int) {} };
 
 // sum of `v` over all threads of the block that share (threadIdx.x % L); valid in threads t < L afterwards
-template <int L>
+template <int L, int BLOCK = kBlock>
 JA_DEV Fr block_sum_by_lane(Fr v) {
-  __shared__ Fr s_lane[kBlock / 32][L > 32 ? 32 : L];
+  __shared__ Fr s_lane[BLOCK / 32][L > 32 ? 32 : L];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int dlt = 16; dlt >= L; dlt >>= 1) v = fp_add<FrParams>(v, fr_shfl_down(v, dlt));
@@ -417,7 +431,7 @@ JA_DEV Fr block_sum_by_lane(Fr v) {
   __syncthreads();
   Fr t = fp_zero<FrParams>();
   if (threadIdx.x < L)
-    for (int w = 0; w < kBlock / 32; w++) t = fp_add<FrParams>(t, s_lane[w][threadIdx.x]);
+    for (int w = 0; w < BLOCK / 32; w++) t = fp_add<FrParams>(t, s_lane[w][threadIdx.x]);
   return t;
 }
 

@@ -162,7 +162,8 @@ Slot arm_slot(ja_ctx* c, int s) {
   r.host_seq = reinterpret_cast<volatile unsigned int*>(h + kSlotSeqOffset);
   r.pub.vals = reinterpret_cast<Fr*>(d);
   r.pub.seq = reinterpret_cast<volatile unsigned int*>(d + kSlotSeqOffset);
-  r.pub.value = ++c->seq;
+  if (++c->seq == 0) ++c->seq;                                     // 0 = "no tag" on the device side
+  r.pub.value = c->seq;
   r.armed = true;
   return r;
 }
@@ -181,6 +182,37 @@ int32_t wait_slot(ja_ctx* c, const Slot& s) {
       if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
         return fail(JA_ERR_CUDA, "sumcheck round kernel: timed out waiting for the published sums");
     }
+  }
+  return JA_OK;
+}
+
+// Tagged protocol (store_tagged, poly_kernels.cuh): element k of the slot is three self-validating 16-byte vectors; wait
+// until all 3 n of them carry the round's tag, then unpack n field elements into `out` (4 n limbs).
+int32_t wait_slot_tagged(ja_ctx* c, const Slot& s, size_t n, uint64_t* out) {
+  const volatile uint32_t* h = reinterpret_cast<const volatile uint32_t*>(s.host_vals);
+  const uint32_t tag = s.pub.value;
+  uint64_t spins = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  uint32_t* o = reinterpret_cast<uint32_t*>(out);
+  for (size_t v = 0; v < 3 * n; v++) {
+    const volatile uint32_t* q = h + 4 * v;
+    while (q[3] != tag) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((++spins & 0xffff) == 0) {
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JA_ERR_CUDA, std::string("sumcheck round kernel: ") + cudaGetErrorString(e));
+        if (e == cudaSuccess && q[3] != tag) return fail(JA_ERR_CUDA, "sumcheck round kernel finished without publishing its sums");
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
+          return fail(JA_ERR_CUDA, "sumcheck round kernel: timed out waiting for the published sums");
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);                       // payload words are read after the tag (same 16-byte store)
+    const size_t k = v / 3, part = v % 3;
+    uint32_t* dst = o + 8 * k + 3 * part;
+    dst[0] = q[0]; dst[1] = q[1];
+    if (part < 2) dst[2] = q[2];
   }
   return JA_OK;
 }
@@ -276,6 +308,13 @@ struct DevInst : Inst {
   RoundEvalPending pend;
   bool legacy = false;              // round went through ja_round_eval_launch (pinned staging + stream sync)
   FrH cs, cw, div;
+  // Division without a per-round inversion: w_inv[i] = 1 / w_i (split-eq bodies) or 1 / (1 - w_i) (product bodies) for every
+  // coordinate of the eq point, ONE batch inversion at the instance's first round; the split-eq bodies also carry
+  // nclaim = claim / current_scalar = q(r) of the eq-free polynomial q of the previous round (gruen_poly_deg_*_q1).
+  std::vector<FrH> w_inv;
+  FrH nclaim = host::FR_ZERO;
+  bool nclaim_valid = false;
+  FrH qc0 = host::FR_ZERO, qc1 = host::FR_ZERO, qc2 = host::FR_ZERO;   // q(X) = qc0 + qc1 X + qc2 X^2 of the last message
   int prod_lanes = 0;
   // multi-GPU: the polynomials are this rank's contiguous hypercube slices (ja_set_sumcheck_shard)
   bool sharded = false, round_sharded = false;
@@ -379,9 +418,18 @@ struct DevInst : Inst {
     legacy = false;
     const int d = (int)polys.size();
     int L = 2; while (L < d) L <<= 1;
-    const size_t gpb = (size_t)kBlock / L;
-    size_t ppb = (pr->G + (size_t)kSMs * 2 - 1) / ((size_t)kSMs * 2);
-    ppb = (ppb + gpb - 1) / gpb * gpb;
+    // small slabs: 128-thread blocks, one pass per block (the product of 9..16 factors on 64 threads per pair)
+    const bool no_small = getenv("JA_NO_WIDE") != nullptr;                     // JA_NO_WIDE=1: tests compare the variants
+    small_round = !no_small && pr->G <= kSmallMaxPairs;
+    wide_round = small_round && L == 16 && pr->G <= kWideMaxPairs;
+    size_t ppb;
+    if (small_round) {
+      ppb = (kind == JA_EVAL_PROD && wide_round) ? (size_t)kWideBlock / 64 : (size_t)kWideBlock / L;
+    } else {
+      const size_t gpb = (size_t)kBlock / L;
+      ppb = (pr->G + (size_t)kSMs * 2 - 1) / ((size_t)kSMs * 2);
+      ppb = (ppb + gpb - 1) / gpb * gpb;
+    }
     a->P = pr->P; a->d = d; a->e_out = pr->e_out; a->e_in = pr->e_in; a->bits_in = pr->bits_in;
     a->nb = (unsigned int)((pr->G + ppb - 1) / ppb); a->G = pr->G; a->ppb = ppb;
     a->gammas = d_gammas;
@@ -475,6 +523,16 @@ struct DevInst : Inst {
       const int d = kind == JA_EVAL_POW ? (int)pow_d : (int)polys.size();
       const bool same = kind == JA_EVAL_POW;
       int L = 2; while (L < d) L <<= 1;
+      if (!same && L == 16 && G <= kWideMaxPairs && getenv("JA_NO_WIDE") == nullptr) {
+        const unsigned grid = (unsigned)((G + 1) / 2);
+        const MailRef mref{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag};
+        if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, part, ctr, pub, pr.g_off, mref));
+        else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<false><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, part, ctr, pub, pr.g_off, mref));
+        prod_lanes = L;
+        JA_CUDA(cudaGetLastError());
+        commit_round(pr);
+        return JA_OK;
+      }
       const size_t gpb = (size_t)kBlock / L;
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
@@ -538,6 +596,7 @@ struct DevInst : Inst {
     return JA_OK;
   }
 
+  bool small_round = false, wide_round = false;   // prepare_pair chose the small-slab variants of the paired kernel
   bool paired_this_round = false;    // the driver already launched this round's kernel together with a partner
   DevInst* pair_candidate(size_t) override { return pairable() ? this : nullptr; }
   int32_t launch(ja_ctx* c, size_t) override {
@@ -564,10 +623,20 @@ struct DevInst : Inst {
       ja_spliteq_current_scalar(eq, t); cs = host::from_limbs(t);
       if ((st = ja_spliteq_current_w(eq, t))) return st;
       cw = host::from_limbs(t);
-      if (kind == JA_EVAL_PROD || kind == JA_EVAL_POW) div = host::inv(host::sub(host::FR_ONE, cw));
-      else div = host::inv(host::gruen_eq1(cs, cw));
+      if (w_inv.empty()) {
+        const bool prod = kind == JA_EVAL_PROD || kind == JA_EVAL_POW;
+        w_inv.resize(eq->w.size());
+        for (size_t i = 0; i < w_inv.size(); i++) w_inv[i] = prod ? host::sub(host::FR_ONE, eq->w[i]) : eq->w[i];
+        host::batch_inv(w_inv.data(), w_inv.size());
+      }
+      div = w_inv[order == JA_LOW_TO_HIGH ? eq->current_index - 1 : eq->current_index];
     }
     return JA_OK;
+  }
+  // q(1) of the eq-free polynomial from the running normalised claim (split-eq bodies)
+  FrH gruen_q1(const FrH& prev, const FrH& q0) {
+    if (!nclaim_valid) { nclaim = cs == host::FR_ONE ? prev : host::mul(prev, host::inv(cs)); nclaim_valid = true; }
+    return host::mul(host::sub(nclaim, host::mul(host::sub(host::FR_ONE, cw), q0)), div);
   }
 
   int32_t message(ja_ctx* c, size_t, const FrH& prev_in, Coeffs* uni) override {
@@ -578,11 +647,15 @@ struct DevInst : Inst {
       // instances in launch order, and ja_round_eval_collect synchronises the stream)
       if ((st = ja_round_eval_collect(c, pend, ev))) return st;
     } else {
-      if ((st = wait_slot(c, slot))) return st;
       const bool lanes = prod_lanes && (kind == JA_EVAL_PROD || kind == JA_EVAL_POW);
       const size_t n_raw = lanes ? (size_t)prod_lanes : n_out;
       uint64_t raw[kMaxOut * 4];
-      memcpy(raw, slot.host_vals, n_raw * 32);
+      if (kind == JA_EVAL_OPEN) {                                    // k_round_open: fence + flag protocol
+        if ((st = wait_slot(c, slot))) return st;
+        memcpy(raw, slot.host_vals, n_raw * 32);
+      } else if ((st = wait_slot_tagged(c, slot, n_raw, raw))) {
+        return st;
+      }
       if (round_sharded) {
         // partial sums of this rank's slice: all-gather (<= 17 Fr per rank) and add as field elements
         std::vector<uint64_t> all(4 * n_raw * sc_world);
@@ -605,10 +678,16 @@ struct DevInst : Inst {
     for (size_t k = 0; k < n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
     const FrH prev = has_scale ? host::mul(prev_in, scale_inv) : prev_in;
     switch (kind) {
-      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT: case JA_EVAL_OPEN:
-        *uni = host::gruen_poly_deg_2(cs, cw, e[0], prev, div); break;               // ops/add.rs:297-304, opening_reduction.rs:402
-      case JA_EVAL_MUL: case JA_EVAL_SQUARE: case 7:
-        *uni = host::gruen_poly_deg_3(cs, cw, e[0], e[1], prev, div); break;         // ops/mul.rs:177, booleanity.rs:295-300
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT: case JA_EVAL_OPEN: {
+        const FrH q1 = gruen_q1(prev, e[0]);
+        qc0 = e[0]; qc1 = host::sub(q1, e[0]); qc2 = host::FR_ZERO;
+        *uni = host::gruen_poly_deg_2_q1(cs, cw, e[0], prev, q1); break;             // ops/add.rs:297-304, opening_reduction.rs:402
+      }
+      case JA_EVAL_MUL: case JA_EVAL_SQUARE: case 7: {
+        const FrH q1 = gruen_q1(prev, e[0]);
+        qc0 = e[0]; qc1 = host::sub(host::sub(q1, e[0]), e[1]); qc2 = e[1];
+        *uni = host::gruen_poly_deg_3_q1(cs, cw, e[0], e[1], prev, q1); break;       // ops/mul.rs:177, booleanity.rs:295-300
+      }
       case JA_EVAL_PROD: case JA_EVAL_POW:
         for (auto& x : e) x = host::mul(x, cs);                                      // mles_product_sum.rs:120-128
         *uni = host::finish_mles_product_sum_from_evals(e, prev, cw, div); break;
@@ -622,6 +701,10 @@ struct DevInst : Inst {
   int32_t ingest(ja_ctx* c, const uint64_t ch[4], size_t) override {
     int32_t st;
     if (eq && (st = ja_spliteq_bind(c, eq, ch))) return st;
+    if (nclaim_valid) {                                            // n' = q(r)
+      const FrH r = host::from_limbs(ch);
+      nclaim = host::add(qc0, host::mul(r, host::add(qc1, host::mul(r, qc2))));
+    }
     if (ahead_consumed) { ahead_consumed = false; return JA_OK; }   // the pre-launched kernel of the next round binds this challenge
     if (fusable) { memcpy(pend_ch, ch, 32); pending = true; return JA_OK; }
     return ja_bind_many(c, polys.data(), polys.size(), ch, order);
@@ -1163,10 +1246,14 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
           if ((st = pb->prepare_pair(c, &B, &rb, 1))) return st;
           const unsigned int gx = std::max(A.nb, B.nb);
           int L = 2; while (L < A.d) L <<= 1;
-#define JA_PAIR(LL) do { if (ra.fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, true><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag})); \
-                           else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, false><<<dim3(gx, 2), kBlock, 0, c->stream>>>(A, B, ra.ch)); } while (0)
-          switch (L) { case 2: JA_PAIR(2); break; case 4: JA_PAIR(4); break; case 8: JA_PAIR(8); break; default: JA_PAIR(16); break; }
+          const MailRef mref{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag};
+#define JA_PAIR_B(LL, FZ, BLK, WD) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, FZ, BLK, WD><<<dim3(gx, 2), BLK, 0, c->stream>>>(A, B, ra.ch, mref))
+#define JA_PAIR(LL) do { if (pa->small_round) { if (ra.fz) JA_PAIR_B(LL, true, kWideBlock, false); else JA_PAIR_B(LL, false, kWideBlock, false); } \
+                           else { if (ra.fz) JA_PAIR_B(LL, true, kBlock, false); else JA_PAIR_B(LL, false, kBlock, false); } } while (0)
+          if (pa->wide_round) { if (ra.fz) JA_PAIR_B(16, true, kWideBlock, true); else JA_PAIR_B(16, false, kWideBlock, true); }
+          else switch (L) { case 2: JA_PAIR(2); break; case 4: JA_PAIR(4); break; case 8: JA_PAIR(8); break; default: JA_PAIR(16); break; }
 #undef JA_PAIR
+#undef JA_PAIR_B
           JA_CUDA(cudaGetLastError());
           pa->paired_this_round = true; pb->paired_this_round = true;
         }
@@ -1374,13 +1461,15 @@ extern "C" {
 
 // bench hook: ONE fused round kernel (bind the previous challenge + evaluate) re-run `iters` times on resident synthetic
 // operands of 2^log_n Fr per polynomial.  which: 0 ADD (2 polys), 1 MUL (2), 2 IDENT (1), 3 product of 4, 4 product of 16,
-// 5 booleanity over 16, 6 opening reduction HighToLow (1 poly, in place), 7 / 8 = ADD / IDENT through the TMA-staged kernel.  Algorithmic bytes per launch: 48 * 2^log_n per
-// polynomial (32 n read + 16 n written).
+// 5 booleanity over 16, 6 opening reduction HighToLow (1 poly, in place), 7 / 8 = ADD / IDENT through the TMA-staged kernel,
+// 9 product of 16 on 64 threads per pair (small-slab variant), 10 / 11 = the paired RA-check launch (product of 16 +
+// booleanity over 16) in its 256-thread / 64-threads-per-pair form, 12 = the same in 128-thread blocks.  Algorithmic bytes per launch: 48 * 2^log_n per polynomial
+// (32 n read + 16 n written).
 int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, float* out_ms) {
-  JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 3 && log_n <= 28 && which >= 0 && which <= 8, "ja_bench_fused: bad argument");
+  JA_REQUIRE(c && out_ms && iters > 0 && log_n >= 3 && log_n <= 28 && which >= 0 && which <= 12, "ja_bench_fused: bad argument");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  static const int kNp[9] = {2, 2, 1, 4, 16, 16, 1, 2, 1};
+  static const int kNp[13] = {2, 2, 1, 4, 16, 16, 1, 2, 1, 16, 32, 32, 32};
   const int np = kNp[which];
   const size_t n = size_t(1) << log_n, G = n / 4;
   std::vector<ja_poly*> src(np, nullptr);
@@ -1402,11 +1491,30 @@ int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, f
   FusedPolys P;
   for (int i = 0; i < np; i++) { P.in[i] = src[i]->data(); P.out[i] = which == 6 ? src[i]->data() : dst[i]; }
   const int bits_in = eq->in_len - 1, bits_out = eq->out_len - 1;
-  Slot slot = arm_slot(c, 0);
+  Slot slot = arm_slot(c, 0), slot2 = arm_slot(c, 1);
   int32_t lst = JA_OK;
   auto launch = [&]() {
     cudaStream_t s = c->stream;
-    if (which >= 7) {
+    if (which == 9) {
+      JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<(unsigned)((G + 1) / 2), kWideBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, c->d_partials, c->d_counter, slot.pub));
+    } else if (which >= 10) {
+      const bool wide = which == 11;
+      PairArgs A, B;
+      for (int q = 0; q < 16; q++) { A.P.in[q] = P.in[q]; A.P.out[q] = P.out[q]; B.P.in[q] = P.in[16 + q]; B.P.out[q] = P.out[16 + q]; }
+      A.d = B.d = 16; A.e_out = B.e_out = eq->e_out(); A.e_in = B.e_in = eq->e_in(); A.bits_in = B.bits_in = bits_in; A.G = B.G = G;
+      if (wide) { A.ppb = 2; B.ppb = kWideBlock / 16; }
+      else if (which == 12) { A.ppb = B.ppb = kWideBlock / 16; }
+      else { size_t ppb = (G + (size_t)kSMs * 2 - 1) / ((size_t)kSMs * 2); ppb = (ppb + 15) / 16 * 16; A.ppb = B.ppb = ppb; }
+      A.nb = (unsigned)((G + A.ppb - 1) / A.ppb); B.nb = (unsigned)((G + B.ppb - 1) / B.ppb);
+      A.gammas = B.gammas = d_gam;
+      A.partials = c->d_partials; B.partials = c->d_partials + kMaxGrid * kMaxOut / 2;
+      A.counter = c->d_counter; B.counter = c->d_counter + 1;
+      A.pub = slot.pub; B.pub = slot2.pub;
+      const unsigned gx = std::max(A.nb, B.nb);
+      if (wide) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<16, true, kWideBlock, true><<<dim3(gx, 2), kWideBlock, 0, s>>>(A, B, ch));
+      else if (which == 12) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<16, true, kWideBlock, false><<<dim3(gx, 2), kWideBlock, 0, s>>>(A, B, ch));
+      else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<16, true, kBlock><<<dim3(gx, 2), kBlock, 0, s>>>(A, B, ch));
+    } else if (which >= 7) {
       const int32_t e = launch_round_s_tma(c, which == 7 ? JA_EVAL_ADD : JA_EVAL_IDENT, P, ch, eq->e_out(), eq->e_in(), bits_in, G,
                                            c->d_partials, c->d_counter, slot.pub, 0);
       if (e) lst = e;

@@ -155,6 +155,29 @@ static inline Coeffs gruen_poly_deg_2(const FrH& current_scalar, const FrH& curr
   const FrH l2 = sub(add(l1, l1), q0);
   return from_evals({c0, c1, mul(eq2, l2)});
 }
+// The same round polynomial from q(1) directly.  The engine carries the eq-free polynomial's own running claim
+// n = claim / current_scalar (n' = q(r): s(r) = current_scalar' * q(r) exactly), so q(1) = (n - (1 - w) q(0)) / w needs
+// 1/w only - known for every round when the instance is built (one batch inversion) - instead of one inversion of
+// current_scalar * w per round on the Fiat-Shamir critical path.  Field arithmetic is exact: same coefficients.
+static inline Coeffs gruen_poly_deg_2_q1(const FrH& current_scalar, const FrH& current_w, const FrH& q0, const FrH& prev, const FrH& l1) {
+  const FrH eq1 = mul(current_scalar, current_w);
+  const FrH eq0 = sub(current_scalar, eq1);
+  const FrH eqm = sub(eq1, eq0), eq2 = add(eq1, eqm);
+  const FrH c0 = mul(eq0, q0), c1 = sub(prev, c0);
+  const FrH l2 = sub(add(l1, l1), q0);
+  return from_evals({c0, c1, mul(eq2, l2)});
+}
+static inline Coeffs gruen_poly_deg_3_q1(const FrH& current_scalar, const FrH& current_w, const FrH& q_constant,
+                                         const FrH& q_quadratic, const FrH& s01, const FrH& q1) {
+  const FrH eq1 = mul(current_scalar, current_w);
+  const FrH eq0 = sub(current_scalar, eq1);
+  const FrH eqm = sub(eq1, eq0), eq2 = add(eq1, eqm), eq3 = add(eq2, eqm);
+  const FrH c0 = mul(eq0, q_constant), c1 = sub(s01, c0);
+  const FrH e2 = add(q_quadratic, q_quadratic);
+  const FrH q2 = add(sub(add(q1, q1), q_constant), e2);
+  const FrH q3 = add(add(sub(add(q2, q1), q_constant), e2), e2);
+  return from_evals({c0, c1, mul(eq2, q2), mul(eq3, q3)});
+}
 // split_eq_poly.rs:379-426
 static inline Coeffs gruen_poly_deg_3(const FrH& current_scalar, const FrH& current_w, const FrH& q_constant,
                                       const FrH& q_quadratic, const FrH& s01, const FrH& eq1_inv) {

@@ -150,7 +150,7 @@ k_round_s_tma(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ C
   if (pending) inner = fp_add<FrParams>(inner, fpw_reduce<FrParams>(wide));
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
   Fr acc[1] = {outer};
-  if (grid_sum<1>(acc, partials, counter, pub.vals)) publish_flag(pub);
+  grid_sum_ex<1>(acc, partials, counter, pub.vals, blockIdx.x, gridDim.x, pub.value);
 }
 
 }  // namespace ja
