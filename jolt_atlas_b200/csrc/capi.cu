@@ -283,17 +283,26 @@ static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& sca
   const size_t mh = m / 2, ml = m - mh;
   Fr* d_r = nullptr;
   Fr* lv[2] = {nullptr, nullptr};
-  int32_t st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_r);
-  if (st) return st;
-  if (m && (st = stage_h2d(c, d_r, r, m * 32))) return st;
-  st = dev_alloc(c, (size_t(2) << mh) * sizeof(Fr), (void**)&lv[0]);
+  int32_t st = dev_alloc(c, (size_t(2) << mh) * sizeof(Fr), (void**)&lv[0]);
   if (st) return st;
   st = dev_alloc(c, (size_t(2) << ml) * sizeof(Fr), (void**)&lv[1]);
   if (st) return st;
-  EqLevelsArgs a;
-  a.w[0] = d_r; a.m[0] = (int)mh; a.rev[0] = 0; a.buf[0] = lv[0]; a.scale[0] = to_dev(scale);
-  a.w[1] = d_r + mh; a.m[1] = (int)ml; a.rev[1] = 0; a.buf[1] = lv[1]; a.scale[1] = to_dev(host::FR_ONE);
-  JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels<<<2, 1024, 0, c->stream>>>(a));
+  if (ml <= (size_t)kEqValMax) {
+    EqLevelsValArgs v;
+    for (size_t i = 0; i < mh; i++) v.w[0][i] = to_dev(r[i]);
+    for (size_t i = 0; i < ml; i++) v.w[1][i] = to_dev(r[mh + i]);
+    v.m[0] = (int)mh; v.rev[0] = 0; v.buf[0] = lv[0]; v.scale[0] = to_dev(scale);
+    v.m[1] = (int)ml; v.rev[1] = 0; v.buf[1] = lv[1]; v.scale[1] = to_dev(host::FR_ONE);
+    JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels_val<<<2, kBlock, 0, c->stream>>>(v));
+  } else {
+    st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_r);
+    if (st) return st;
+    if (m && (st = stage_h2d(c, d_r, r, m * 32))) return st;
+    EqLevelsArgs a;
+    a.w[0] = d_r; a.m[0] = (int)mh; a.rev[0] = 0; a.buf[0] = lv[0]; a.scale[0] = to_dev(scale);
+    a.w[1] = d_r + mh; a.m[1] = (int)ml; a.rev[1] = 0; a.buf[1] = lv[1]; a.scale[1] = to_dev(host::FR_ONE);
+    JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels<<<2, 1024, 0, c->stream>>>(a));
+  }
   JA_CUDA(cudaGetLastError());
   const size_t n = size_t(1) << m;
   JA_LAUNCH(c, KC_EQ_TABLE, k_eq_expand<<<grid_for(n), kBlock, 0, c->stream>>>(lv[0] + ((size_t(1) << mh) - 1), lv[1] + ((size_t(1) << ml) - 1),
@@ -347,16 +356,28 @@ int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, co
     s->current_index = 0;
   }
   s->out_len = (int)n_out_vars + 1; s->in_len = (int)n_in_vars + 1;
-  Fr* d_w = nullptr;
-  int32_t st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_w);
-  if (st) { delete s; return st; }
-  if (m && (st = stage_h2d(c, d_w, w, m * 32))) { delete s; return st; }
-  st = dev_alloc(c, (size_t(2) << n_out_vars) * sizeof(Fr), (void**)&s->out_levels);
+  int32_t st = dev_alloc(c, (size_t(2) << n_out_vars) * sizeof(Fr), (void**)&s->out_levels);
   if (st) { delete s; return st; }
   st = dev_alloc(c, (size_t(2) << n_in_vars) * sizeof(Fr), (void**)&s->in_levels);
   if (st) { delete s; return st; }
-  EqLevelsArgs a;
   const int rev = order == JA_HIGH_TO_LOW ? 1 : 0;
+  if (n_out_vars <= (size_t)kEqValMax && n_in_vars <= (size_t)kEqValMax) {
+    // the point travels in the kernel parameters: no staged copy ahead of the launch
+    EqLevelsValArgs v;
+    for (size_t i = 0; i < n_out_vars; i++) v.w[0][i] = to_dev(s->w[off_out + i]);
+    for (size_t i = 0; i < n_in_vars; i++) v.w[1][i] = to_dev(s->w[off_in + i]);
+    v.m[0] = (int)n_out_vars; v.rev[0] = rev; v.buf[0] = s->out_levels; v.scale[0] = to_dev(host::FR_ONE);
+    v.m[1] = (int)n_in_vars;  v.rev[1] = rev; v.buf[1] = s->in_levels;  v.scale[1] = to_dev(host::FR_ONE);
+    JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels_val<<<2, kBlock, 0, c->stream>>>(v));
+    JA_CUDA(cudaGetLastError());
+    *out = s;
+    return JA_OK;
+  }
+  Fr* d_w = nullptr;
+  st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_w);
+  if (st) { delete s; return st; }
+  if (m && (st = stage_h2d(c, d_w, w, m * 32))) { delete s; return st; }
+  EqLevelsArgs a;
   a.w[0] = d_w + off_out; a.m[0] = (int)n_out_vars; a.rev[0] = rev; a.buf[0] = s->out_levels; a.scale[0] = to_dev(host::FR_ONE);
   a.w[1] = d_w + off_in;  a.m[1] = (int)n_in_vars;  a.rev[1] = rev; a.buf[1] = s->in_levels;  a.scale[1] = to_dev(host::FR_ONE);
   JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels<<<2, 1024, 0, c->stream>>>(a));

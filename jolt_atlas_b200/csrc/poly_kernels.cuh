@@ -225,6 +225,43 @@ static __global__ void __launch_bounds__(1024) k_eq_levels(EqLevelsArgs a) {
   }
 }
 
+// The same tables with the point passed BY VALUE in the kernel parameters (no staged H2D copy of w ahead of the launch: a
+// copy is one more ~3 us operation on the stream, and every sumcheck instance starts with one of these) and the previous
+// level read from shared memory instead of through L2 (levels up to 2^9 entries; larger ones fall back to global).
+constexpr int kEqValMax = 16;
+struct EqLevelsValArgs {
+  Fr w[2][kEqValMax];
+  int m[2];
+  int rev[2];
+  Fr* buf[2];
+  Fr scale[2];
+};
+static __global__ void __launch_bounds__(kBlock) k_eq_levels_val(const __grid_constant__ EqLevelsValArgs a) {
+  __shared__ Fr sm[2][512];
+  const int t = blockIdx.x;
+  const int m = a.m[t], rev = a.rev[t];
+  Fr* buf = a.buf[t];
+  if (threadIdx.x == 0) { fp_store(buf, a.scale[t]); sm[0][0] = a.scale[t]; }
+  __syncthreads();
+  for (int j = 0; j < m; j++) {
+    const Fr wj = rev ? a.w[t][m - 1 - j] : a.w[t][j];
+    const size_t n = size_t(1) << j;
+    const Fr* prev = buf + (n - 1);
+    Fr* cur = buf + (2 * n - 1);
+    const Fr* sp = sm[j & 1];
+    Fr* sc = sm[(j + 1) & 1];
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const Fr s = n <= 512 ? sp[i] : prev[i];
+      const Fr hi = fp_mul<FrParams>(s, wj);
+      const Fr lo = fp_sub<FrParams>(s, hi);
+      const size_t ih = rev ? i + n : 2 * i + 1, il = rev ? i : 2 * i;
+      fp_store(cur + ih, hi); fp_store(cur + il, lo);
+      if (2 * n <= 512) { sc[ih] = hi; sc[il] = lo; }
+    }
+    __syncthreads();
+  }
+}
+
 // out[x] = hi[x >> bits_lo] * lo[x & mask]   — EqPolynomial::evals (eq_poly.rs:77-101) as an outer product
 static __global__ void __launch_bounds__(kBlock) k_eq_expand(const Fr* __restrict__ hi, const Fr* __restrict__ lo,
                                                      int bits_lo, size_t n, Fr* __restrict__ out) {

@@ -7,6 +7,7 @@
 // as the reference's Gaussian elimination; only the TRIMMING rules change transcript bytes and are kept exactly:
 // from_evals of 3 or 4 values keeps its length, the general path and from_coeff drop trailing zeros.
 #pragma once
+#include <climits>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -114,8 +115,117 @@ static inline Coeffs from_evals_and_hint(const FrH& hint, const std::vector<FrH>
   e.insert(e.begin() + 1, sub(hint, e[0]));
   return from_evals(e);
 }
+// Toom interpolation with a SMALL-INTEGER matrix.  p(x) = lead * prod_{j<m} (x - j) + (interpolant of e[0..m) on 0..m-1), so
+//   c_k = (1 / (m-1)!) * sum_i N[k][i] e[i] + s_k * lead,   N[k][i] = (-1)^(m-1-i) C(m-1, i) [x^k] prod_{j != i} (x - j),
+// s_k = [x^k] prod_j (x - j): N fits in 64 bits for m <= 17, so a row is m products of 256 x 64 bits accumulated in 320-bit
+// integers (positive and negative entries apart) and three Montgomery products (two fold the 320-bit sum times 1/(m-1)!
+// back into the field: lo * K + hi * K R; one is s_k * lead) instead of m + 1 of them.  The degree-17 round polynomial of
+// a product of 16 MLEs drops from 289 to ~100 product-equivalents; this sits on the Fiat-Shamir critical path of every
+// RA-check round.  Same unique polynomial, exact field arithmetic: same coefficients.
+struct ToomInt {
+  size_t m = 0;
+  bool ok = false;
+  std::vector<int64_t> N;          // m x m
+  std::vector<FrH> s;              // s_k, Montgomery form
+  FrH k_lo, k_hi;                  // Mont(1 / (m-1)!) and the same times R
+};
+static inline const ToomInt& toom_int(size_t n /* values: m = n - 1 points and the leading coefficient */) {
+  static std::mutex mu;
+  static std::map<size_t, ToomInt> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(n);
+  if (it != cache.end()) return it->second;
+  ToomInt t;
+  t.m = n - 1;
+  const size_t m = t.m;
+  if (m >= 2 && m <= 17) {
+    typedef __int128 i128;
+    bool ok = true;
+    t.N.assign(m * m, 0);
+    std::vector<i128> binom(m, 1);                       // C(m-1, i)
+    for (size_t i = 1; i < m; i++) binom[i] = binom[i - 1] * (i128)(m - i) / (i128)i;
+    for (size_t i = 0; i < m && ok; i++) {
+      std::vector<i128> poly(1, 1);                      // prod_{j != i} (x - j)
+      for (size_t j = 0; j < m; j++) {
+        if (j == i) continue;
+        std::vector<i128> nx(poly.size() + 1, 0);
+        for (size_t k = 0; k < poly.size(); k++) { nx[k + 1] += poly[k]; nx[k] -= poly[k] * (i128)j; }
+        poly.swap(nx);
+      }
+      for (size_t k = 0; k < m; k++) {
+        i128 v = poly[k] * binom[i];
+        if ((m - 1 - i) & 1) v = -v;
+        if (v > (i128)INT64_MAX / 2 || v < -((i128)INT64_MAX / 2)) { ok = false; break; }
+        t.N[k * m + i] = (int64_t)v;
+      }
+    }
+    if (ok) {
+      std::vector<i128> full(1, 1);                      // prod_j (x - j)
+      for (size_t j = 0; j < m; j++) {
+        std::vector<i128> nx(full.size() + 1, 0);
+        for (size_t k = 0; k < full.size(); k++) { nx[k + 1] += full[k]; nx[k] -= full[k] * (i128)j; }
+        full.swap(nx);
+      }
+      t.s.resize(m);
+      for (size_t k = 0; k < m && ok; k++) {
+        const i128 v = full[k];
+        if (v > (i128)INT64_MAX || v < -(i128)INT64_MAX) { ok = false; break; }
+        t.s[k] = from_i64((int64_t)v);
+      }
+      FrH fact = FR_ONE;
+      for (size_t i = 2; i < m; i++) fact = mul(fact, from_u64(i));
+      t.k_lo = inv(fact);
+      t.k_hi = mul(t.k_lo, FR_R2);                       // K * R (Montgomery form of K R)
+    }
+    t.ok = ok;
+  }
+  return cache.emplace(n, std::move(t)).first->second;
+}
+// acc (5 limbs) += a (4 limbs) * w
+static inline void mac_256x64(uint64_t acc[5], const uint64_t a[4], uint64_t w) {
+  u128 c = 0;
+  for (int j = 0; j < 4; j++) { c += (u128)a[j] * w + acc[j]; acc[j] = (uint64_t)c; c >>= 64; }
+  acc[4] += (uint64_t)c;
+}
+// (320-bit integer X) * K mod p for the Montgomery constants k_lo = Mont(K), k_hi = Mont(K R): X = lo + hi 2^256 and the
+// CIOS product takes an unreduced first operand < 2^256 (result < 2 p before its final subtraction)
+static inline FrH fold320(const uint64_t x[5], const FrH& k_lo, const FrH& k_hi) {
+  const FrH lo = {{x[0], x[1], x[2], x[3]}}, hi = {{x[4], 0, 0, 0}};
+  return add(mul(lo, k_lo), mul(hi, k_hi));
+}
 // values at 0..n-2 and the leading coefficient (value "at infinity") -> n coefficients, no trimming (unipoly.rs:104-134)
-static inline Coeffs from_evals_toom(const std::vector<FrH>& e) { return apply_matrix(interp_matrix(e.size(), true), e); }
+static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
+  const size_t n = e.size();
+  const ToomInt& t = toom_int(n);
+  if (!t.ok) return apply_matrix(interp_matrix(n, true), e);
+  const size_t m = t.m;
+  const FrH& lead = e[m];
+  Coeffs out(n);
+  for (size_t k = 0; k < m; k++) {
+    uint64_t pos[5] = {0, 0, 0, 0, 0}, ngt[5] = {0, 0, 0, 0, 0};
+    const int64_t* row = t.N.data() + k * m;
+    for (size_t i = 0; i < m; i++) {
+      const int64_t w = row[i];
+      if (w > 0) mac_256x64(pos, e[i].l, (uint64_t)w);
+      else if (w < 0) mac_256x64(ngt, e[i].l, (uint64_t)(-w));
+    }
+    // |pos - ngt| as a 320-bit integer, one fold, sign applied in the field
+    bool ge = true;
+    for (int j = 4; j >= 0; j--) if (pos[j] != ngt[j]) { ge = pos[j] > ngt[j]; break; }
+    const uint64_t* hi_v = ge ? pos : ngt;
+    const uint64_t* lo_v = ge ? ngt : pos;
+    uint64_t df[5];
+    unsigned char br = 0;
+    for (int j = 0; j < 5; j++) {
+      const u128 d = (u128)hi_v[j] - lo_v[j] - br;
+      df[j] = (uint64_t)d; br = (unsigned char)((d >> 64) & 1);
+    }
+    const FrH f = fold320(df, t.k_lo, t.k_hi);
+    out[k] = add(ge ? f : neg(f), mul(t.s[k], lead));
+  }
+  out[m] = lead;
+  return out;
+}
 static inline Coeffs from_evals_toom_slow(const std::vector<FrH>& e) {
   const size_t n = e.size();
   const FrH lead = e[n - 1];
@@ -130,8 +240,8 @@ static inline Coeffs from_evals_toom_slow(const std::vector<FrH>& e) {
   return c;
 }
 static inline FrH evaluate(const Coeffs& c, const FrH& r) {    // unipoly.rs:219-245
-  FrH acc = c[0], pw = r;
-  for (size_t i = 1; i < c.size(); i++) { acc = add(acc, mul(pw, c[i])); pw = mul(pw, r); }
+  FrH acc = c.back();                                            // Horner: one product per coefficient, same field value
+  for (size_t i = c.size() - 1; i-- > 0;) acc = add(mul(acc, r), c[i]);
   return acc;
 }
 static inline Coeffs compress(const Coeffs& c) {                 // unipoly.rs:307-318: everything but the linear term
@@ -202,11 +312,12 @@ static inline Coeffs finish_mles_product_sum_from_evals(const std::vector<FrH>& 
   std::vector<FrH> toom; toom.push_back(at0);
   toom.insert(toom.end(), sum_evals.begin(), sum_evals.end());
   const Coeffs tmp = from_evals_toom(toom);
-  const FrH cc = sub(FR_ONE, r), xc = sub(add(r, r), FR_ONE);
+  // times the linear eq factor (1 - r) + (2 r - 1) X: t (1 - r) = t - t r and t (2 r - 1) = 2 t r - t, one product per coefficient
   Coeffs coeffs(tmp.size() + 1, FR_ZERO);
   for (size_t i = 0; i < tmp.size(); i++) {
-    coeffs[i] = add(coeffs[i], mul(tmp[i], cc));
-    coeffs[i + 1] = add(coeffs[i + 1], mul(tmp[i], xc));
+    const FrH tr = mul(tmp[i], r);
+    coeffs[i] = add(coeffs[i], sub(tmp[i], tr));
+    coeffs[i + 1] = add(coeffs[i + 1], sub(add(tr, tr), tmp[i]));
   }
   return trim(coeffs);
 }
