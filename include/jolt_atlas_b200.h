@@ -245,6 +245,10 @@ void ja_onehot_free(ja_ctx*, ja_onehot*);
  * OneHotPolynomial::from_indices, one_hot_polynomial.rs:62) uploaded once as d x T u32 (0xFFFFFFFF = None, K <= 65536),
  * then consumed on the device by the commitment, the RA materialisations and the G-table scatter. */
 int32_t ja_addr_upload(ja_ctx*, const uint32_t* k, size_t d, size_t T, size_t K, ja_addr** out);
+/* n batches in one call (all index arrays of a proof: witness.rs:142-214 produces them together): copies and device-side
+ * validation enqueued back to back, one synchronisation; on error no handle is returned. */
+int32_t ja_addr_upload_many(ja_ctx*, const uint32_t* const* ks, const size_t* ds, const size_t* Ts, const size_t* Ks, size_t n,
+                            ja_addr** outs);
 void ja_addr_free(ja_ctx*, ja_addr*);
 size_t ja_addr_len(const ja_addr*);
 size_t ja_addr_count(const ja_addr*);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "ja_onehot_commit": (C.c_int32, [vp, vp, vp, u64p, i32p]),
     "ja_onehot_free": (None, [vp, vp]),
     "ja_addr_upload": (C.c_int32, [vp, u32p, C.c_size_t, C.c_size_t, C.c_size_t, vpp]),
+    "ja_addr_upload_many": (C.c_int32, [vp, vp, vp, vp, vp, C.c_size_t, vp]),
     "ja_addr_free": (None, [vp, vp]),
     "ja_addr_len": (C.c_size_t, [vp]),
     "ja_addr_count": (C.c_size_t, [vp]),

@@ -528,6 +528,26 @@ class OneHotAddresses:
         check(ctx._lib.ja_addr_upload(ctx._h, k.ctypes.data_as(_lib.u32p), self.d, self.T, K, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def upload_many(cls, ctx: Context, ks, K: int):
+        """All address batches of a proof in one call (ja_addr_upload_many): copies and device-side validation enqueued back
+        to back, one synchronisation.  ks: list of (d_i, T_i) uint32 arrays -> list of OneHotAddresses."""
+        ks = [np.ascontiguousarray(k, dtype=np.uint32) for k in ks]
+        n = len(ks)
+        assert n and all(k.ndim == 2 for k in ks)
+        ptrs = (C.c_void_p * n)(*[k.ctypes.data for k in ks])
+        ds = (C.c_size_t * n)(*[k.shape[0] for k in ks])
+        ts = (C.c_size_t * n)(*[k.shape[1] for k in ks])
+        kk = (C.c_size_t * n)(*([K] * n))
+        outs = (C.c_void_p * n)()
+        check(ctx._lib.ja_addr_upload_many(ctx._h, ptrs, ds, ts, kk, n, outs))
+        res = []
+        for i, k in enumerate(ks):
+            o = cls.__new__(cls)
+            o.ctx, o.d, o.T, o.K, o._h = ctx, k.shape[0], k.shape[1], K, C.c_void_p(outs[i])
+            res.append(o)
+        return res
+
     def commit(self, srs: SRS):
         """HyperKZG::batch_commit_one_hot over the resident lists -> ((d, 8) xy limbs, (d,) is_infinity)."""
         out, inf = _pt_out(self.d)

@@ -160,29 +160,69 @@ k_rlc_add_dense(const Fr* __restrict__ poly, size_t len, Fr coeff, Fr* __restric
   }
 }
 
+// address validation on the device (every entry must be None = 0xFFFFFFFF or < K): flags[slot] |= 1 on a violation.
+// The host-side scan it replaces read the whole index array a second time on one core (1.1 GB for a GPT-2-shaped proof).
+static __global__ void __launch_bounds__(kBlock)
+k_addr_validate(const uint32_t* __restrict__ k, size_t n, uint32_t K, unsigned int* flags, unsigned int slot) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned int bad = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t v = k[i];
+    bad |= (v != 0xffffffffu) & (v >= K);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + slot, 1u);
+}
+
 }  // namespace ja
 
 int32_t eq_evals_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr* out);   // capi.cu
 
 extern "C" {
 
-int32_t ja_addr_upload(ja_ctx* c, const uint32_t* k, size_t d, size_t T, size_t K, ja_addr** out) {
-  JA_REQUIRE(c && k && out && d > 0 && T > 0 && K > 0, "ja_addr_upload: null or empty argument");
-  JA_REQUIRE(d <= (size_t)kMaxProdPolys, "ja_addr_upload: at most 32 lists per batch");
-  JA_REQUIRE(T < (size_t(1) << 31) && K <= 65536, "ja_addr_upload: T or K too large");
-  uint32_t bad = 0;                                   // branch-free so the compiler vectorises the scan
-  for (size_t i = 0; i < d * T; i++) bad |= (uint32_t)(k[i] != 0xffffffffu) & (uint32_t)(k[i] >= (uint32_t)K);
-  JA_REQUIRE(!bad, "ja_addr_upload: address outside [0, K)");
+// Upload n address batches back to back: every copy and its validation kernel are enqueued, then ONE synchronisation
+// (the source buffers may be reused when the call returns).  A proof uploads all of its one-hot index arrays at once
+// (commit_witness_polynomials runs before the IOP), so this replaces one blocking copy + host scan per node.
+int32_t ja_addr_upload_many(ja_ctx* c, const uint32_t* const* ks, const size_t* ds, const size_t* Ts, const size_t* Ks, size_t n,
+                            ja_addr** outs) {
+  JA_REQUIRE(c && ks && ds && Ts && Ks && outs && n > 0, "ja_addr_upload: null or empty argument");
+  JA_REQUIRE(n * sizeof(unsigned int) <= kPinnedBytes, "ja_addr_upload: too many batches in one call");
+  for (size_t b = 0; b < n; b++) {
+    JA_REQUIRE(ks[b] && ds[b] > 0 && Ts[b] > 0 && Ks[b] > 0, "ja_addr_upload: null or empty argument");
+    JA_REQUIRE(ds[b] <= (size_t)kMaxProdPolys, "ja_addr_upload: at most 32 lists per batch");
+    JA_REQUIRE(Ts[b] < (size_t(1) << 31) && Ks[b] <= 65536, "ja_addr_upload: T or K too large");
+  }
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
-  ja_addr* a = new ja_addr();
-  a->d = d; a->T = T; a->K = K;
-  int32_t st = dev_alloc(c, d * T * sizeof(uint32_t), (void**)&a->d_k);
-  if (st) { delete a; return st; }
-  JA_CUDA(cudaMemcpyAsync(a->d_k, k, d * T * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  JA_CUDA(cudaStreamSynchronize(c->stream));
-  *out = a;
+  unsigned int* d_flags = nullptr;
+  int32_t st = dev_alloc(c, n * sizeof(unsigned int), (void**)&d_flags);
+  if (st) return st;
+  JA_CUDA(cudaMemsetAsync(d_flags, 0, n * sizeof(unsigned int), c->stream));
+  for (size_t b = 0; b < n; b++) outs[b] = nullptr;
+  for (size_t b = 0; b < n && !st; b++) {
+    ja_addr* a = new ja_addr();
+    a->d = ds[b]; a->T = Ts[b]; a->K = Ks[b];
+    outs[b] = a;
+    const size_t cnt = ds[b] * Ts[b];
+    if ((st = dev_alloc(c, cnt * sizeof(uint32_t), (void**)&a->d_k))) break;
+    if (cudaMemcpyAsync(a->d_k, ks[b], cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { st = fail(JA_ERR_CUDA, "ja_addr_upload: copy failed"); break; }
+    JA_LAUNCH(c, KC_CONVERT, k_addr_validate<<<grid_for(cnt), kBlock, 0, c->stream>>>(a->d_k, cnt, (uint32_t)Ks[b], d_flags, (unsigned int)b));
+  }
+  unsigned int* h_flags = reinterpret_cast<unsigned int*>(c->h_pinned);
+  if (!st && cudaMemcpyAsync(h_flags, d_flags, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) st = fail(JA_ERR_CUDA, "ja_addr_upload: copy failed");
+  const cudaError_t se = cudaStreamSynchronize(c->stream);
+  if (!st && se != cudaSuccess) st = fail(JA_ERR_CUDA, std::string("ja_addr_upload: ") + cudaGetErrorString(se));
+  if (!st) for (size_t b = 0; b < n; b++) if (h_flags[b]) { st = fail(JA_ERR_INVALID, "ja_addr_upload: address outside [0, K)"); break; }
+  dev_free(c, d_flags);
+  if (st) {
+    for (size_t b = 0; b < n; b++) if (outs[b]) { dev_free(c, outs[b]->d_k); delete outs[b]; outs[b] = nullptr; }
+    return st;
+  }
   return JA_OK;
+}
+
+int32_t ja_addr_upload(ja_ctx* c, const uint32_t* k, size_t d, size_t T, size_t K, ja_addr** out) {
+  JA_REQUIRE(out, "ja_addr_upload: null or empty argument");
+  return ja_addr_upload_many(c, &k, &d, &T, &K, 1, out);
 }
 
 void ja_addr_free(ja_ctx* c, ja_addr* a) {

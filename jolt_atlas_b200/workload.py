@@ -219,12 +219,19 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
     # A. witness commitment of EVERY one-hot polynomial before the IOP, as ONNXProof::prove does
     #    (mod.rs:152-200 step 4: commit_witness_polynomials -> prover.rs:236-249 -> hyperkzg/mod.rs:558-596)
     hots = []
-    for i, ni in enumerate(inputs["nodes"]):
-        if resident:
+    if resident:
+        for i, ni in enumerate(inputs["nodes"]):
             hots.append((resident["nodes"][i]["hot16"], resident["nodes"][i]["hot4"]))
-        else:
-            hots.append((A.OneHotAddresses(ctx, ni.hot_k[:D_CLAMP], K_CHUNK),
-                         A.OneHotAddresses(ctx, ni.hot_k[D_CLAMP:], K_CHUNK) if ni.d_hot > D_CLAMP else None))
+    else:
+        # every index array of the proof in ONE upload call (copies + device-side validation back to back, one synchronisation)
+        parts, where = [], []
+        for ni in inputs["nodes"]:
+            where.append((len(parts), len(parts) + 1 if ni.d_hot > D_CLAMP else None))
+            parts.append(ni.hot_k[:D_CLAMP])
+            if ni.d_hot > D_CLAMP:
+                parts.append(ni.hot_k[D_CLAMP:])
+        up = A.OneHotAddresses.upload_many(ctx, parts, K_CHUNK)
+        hots = [(up[a], up[b] if b is not None else None) for a, b in where]
     sharded = comm is not None and comm.world > 1
     all_hots = [h for pair in hots for h in pair if h is not None]
     if sharded:

@@ -96,6 +96,19 @@ def test_rlc_commitment_is_combination_of_commitments(ctx):
         k[0, :7] = 0xFFFFFFFF
         batches.append(OneHotAddresses(ctx, k, K))
     coms = commit_one_hot_batches(ctx, srs, batches)
+    # the batched upload gives the same resident lists as one upload per batch
+    ks2 = []
+    rng2 = np.random.default_rng(7)
+    for d, log_t in ((16, 14), (4, 14), (16, 12), (4, 12)):
+        k = rng2.integers(0, K, size=(d, 1 << log_t), dtype=np.uint32)
+        k[0, :7] = 0xFFFFFFFF
+        ks2.append(k)
+    many = OneHotAddresses.upload_many(ctx, ks2, K)
+    coms2 = commit_one_hot_batches(ctx, srs, many)
+    for (a, ai), (b, bi) in zip(coms, coms2):
+        assert np.array_equal(a, b) and np.array_equal(ai, bi)
+    for h in many:
+        h.free()
     n_poly = sum(b.d for b in batches)
     gammas = np.ascontiguousarray(rng.integers(0, 1 << 63, size=(n_poly, 4), dtype=np.uint64))
     gammas[:, 3] &= np.uint64((1 << 60) - 1)
@@ -131,6 +144,13 @@ def test_engine_error_paths(ctx):
         sumcheck_prove(ctx, EvalKernel.ADD, [p, q], claim, t, eq_w=_chal(rng, 6))
     with pytest.raises(JoltAtlasError):                               # address outside [0, K)
         OneHotAddresses(ctx, np.full((2, 8), 16, dtype=np.uint32), 16)
+    good = rng.integers(0, 16, size=(3, 64), dtype=np.uint32)
+    bad = good.copy(); bad[2, 63] = 16
+    with pytest.raises(JoltAtlasError):                               # one bad batch fails the whole batched upload (device-side validation)
+        OneHotAddresses.upload_many(ctx, [good, bad, good], 16)
+    none_ok = good.copy(); none_ok[1, 5] = 0xFFFFFFFF                 # None entries are valid
+    for h in OneHotAddresses.upload_many(ctx, [good, none_ok], 16):
+        h.free()
     addr = OneHotAddresses(ctx, rng.integers(0, 16, size=(2, 8), dtype=np.uint32), 16)
     with pytest.raises(JoltAtlasError):                               # booleanity: r_cycle does not match T
         batched_sumcheck_prove(ctx, [{"kind": InstanceKind.BOOLEANITY, "tables": _chal(rng, 32).reshape(2, 16, 4), "addr": addr,
