@@ -100,7 +100,7 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   for (uint32_t m = 0; m < count; m++) {
     const MsmJob& j = jobs[m];
     MsmDesc& d = descs[m];
-    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.fixed_stride = 0; d.table_off = 0;
+    d.scalars = j.d_scalars; d.n = (uint32_t)j.n; d.kind = j.kind; d.fixed_stride = 0; d.table_off = 0; d.sub = 1;
     if (j.kind == MSM_INDEXED) { d.c = 1; d.nwin = 1; d.nb = 1; }
     else if (j.kind == MSM_FR && srs->table && srs->table2_c && j.n >= table2_min_n(srs)) {
       d.c = srs->table2_c; d.nwin = srs->table2_nwin; d.nb = 1u << (srs->table2_c - 1);
@@ -109,6 +109,15 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
       // fixed-base window table: nwin windows of c bits, ONE bucket set
       d.c = srs->table_c; d.nwin = srs->table_nwin; d.nb = 1u << (srs->table_c - 1);
       d.fixed_stride = (uint32_t)srs->n;
+    } else if (j.kind == MSM_FR && srs->table && srs->table_c == 16 && getenv("JA_MSM_NO_SUB") == nullptr) {
+      // SHORT job on the window table: sub-windows of c = 16 / sub bits, sub bucket sets, (sub - 1) c doublings at the end
+      // (a classic windowed MSM ends in one doubling per scalar bit on ONE thread: 1.6 ms for the short folded
+      // polynomials of every HyperKZG opening)
+      d.c = j.n >= 256 ? 8u : 4u;
+      d.sub = 16u / d.c;
+      d.nwin = srs->table_nwin * d.sub;
+      d.nb = 1u << (d.c - 1);
+      d.fixed_stride = (uint32_t)srs->n;
     } else {
       d.c = pick_window(j.n, j.nbits);
       d.nwin = (j.nbits + 1 + d.c - 1) / d.c;
@@ -116,7 +125,7 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
     }
     d.bucket_base = (uint32_t)nbt; d.win_base = (uint32_t)wins.size();
     d.entry_base = (uint32_t)total_n; d.base_offset = (uint32_t)j.base_offset;
-    const uint32_t nsets = d.fixed_stride ? 1u : d.nwin;       // bucket sets (= window sums) of this job
+    const uint32_t nsets = d.fixed_stride ? d.sub : d.nwin;    // bucket sets (= window sums) of this job
     for (uint32_t w = 0; w < nsets; w++) wins.push_back(MsmWindow{(uint32_t)(nbt + (uint64_t)w * d.nb), d.nb, d.c, m});
     max_segs = std::max(max_segs, ceil_div_u32(d.nb, kSegBuckets));
     max_nwin = std::max(max_nwin, d.nwin);
@@ -149,6 +158,8 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   const size_t o_head = off; off = align(off + sizeof(G1X) * nruns);
   const size_t o_tail = off; off = align(off + sizeof(G1X) * nruns);
   const size_t o_seg = off; off = align(off + sizeof(G1X) * (size_t)nwins * max_segs);
+  const uint32_t max_chunks = ceil_div_u32(max_segs, kSegSpan);
+  const size_t o_chunk = off; off = align(off + sizeof(G1X) * (size_t)nwins * max_chunks);
   const size_t o_wsum = off; off = align(off + sizeof(G1X) * nwins);
   const size_t o_res = off; off = align(off + sizeof(MsmResult) * count);
   char* ws = nullptr;
@@ -166,6 +177,7 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   G1X* d_head = (G1X*)(ws + o_head);
   G1X* d_tail = (G1X*)(ws + o_tail);
   G1X* d_seg = (G1X*)(ws + o_seg);
+  G1X* d_chunk = (G1X*)(ws + o_chunk);
   G1X* d_wsum = (G1X*)(ws + o_wsum);
   MsmResult* d_res = (MsmResult*)(ws + o_res);
 
@@ -206,7 +218,8 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   STAGE("combine");
   dim3 g_red(ceil_div_u32(max_segs, 128), nwins);
   JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_bucket_reduce<<<g_red, 128, 0, s>>>(d_wins, d_buckets, max_segs, d_seg));
-  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_window_sum<<<nwins, 128, 0, s>>>(d_wins, d_seg, max_segs, d_wsum));
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_part_sum<<<dim3(max_chunks, nwins), 128, 0, s>>>(d_wins, d_seg, max_segs, kSegBuckets, kSegSpan, d_chunk, max_chunks));
+  JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_part_sum<<<dim3(1, nwins), 128, 0, s>>>(d_wins, d_chunk, max_chunks, kSegBuckets * kSegSpan, 0xffffffffu, d_wsum, 1));
   STAGE("bucket_reduce");
   JA_LAUNCH(c, KC_MSM_REDUCE, k_msm_final<<<ceil_div_u32(count, 32), 32, 0, s>>>(d_desc, count, d_wsum, d_res));
   STAGE("final");

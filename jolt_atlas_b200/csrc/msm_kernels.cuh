@@ -18,8 +18,8 @@
 //                      partial per run (head / tail).
 //   5  k_msm_combine   per bucket: add the partials of the runs it spans (wide buckets go to a
 //                      block-cooperative kernel, k_msm_combine_big)
-//   6  k_msm_bucket_reduce / k_msm_window_sum   sum_b (b+1) * B_b per window: per-thread running sums over
-//                      segments of buckets + one small scalar multiple, then a block tree per window
+//   6  k_msm_bucket_reduce / k_msm_part_sum   sum_b (b+1) * B_b per window: per-thread running sums over
+//                      segments of buckets + one small scalar multiple, then a two-stage block tree per window
 //   7  k_msm_final     Horner over the windows (c doublings each) and conversion to affine
 // Integer-throughput bound (8M+2S per pair and window); the 64 B base gathers are hidden behind it.
 #pragma once
@@ -50,6 +50,9 @@ struct MsmDesc {
   uint32_t fixed_stride; // != 0: fixed-base window table in use (stride = SRS length): every window shares ONE bucket set and
                          // digit w of scalar j selects base table_off + w * stride + j (= 2^(c w) * G_j); 0: classic per-window buckets
   uint32_t table_off;    // first entry of the window table this job uses (0 unless fixed_stride != 0)
+  uint32_t sub;          // fixed_stride != 0: sub-windows per table window (table window bits / c), >= 1.  sub > 1 = a SHORT job
+                         // on the table: digit v uses base table window v / sub and bucket set v % sub, so the final Horner
+                         // runs (sub - 1) * c doublings instead of one doubling per scalar bit
 };
 
 constexpr uint32_t kSignBit = 0x80000000u;
@@ -124,8 +127,8 @@ JA_DEV bool msm_digit(const MsmDesc& d, MsmDigitIter& it, uint32_t w, uint32_t& 
   bool dneg = false;
   if (raw > nb) { raw = full - raw; it.carry = 1; dneg = true; } else it.carry = 0;
   if (!raw) return false;
-  key = d.bucket_base + (d.fixed_stride ? 0u : w * nb) + (raw - 1);
-  payload = (it.base + d.table_off + w * d.fixed_stride) | ((dneg != it.neg) ? kSignBit : 0u);
+  key = d.bucket_base + (d.fixed_stride ? (w % d.sub) * nb : w * nb) + (raw - 1);
+  payload = (it.base + d.table_off + (d.fixed_stride ? w / d.sub : 0u) * d.fixed_stride) | ((dneg != it.neg) ? kSignBit : 0u);
   return true;
 }
 
@@ -318,7 +321,8 @@ k_msm_combine_big(const uint32_t* __restrict__ offsets, uint32_t T, const G1X* _
 
 // ---- bucket reduction: W = sum_b (b+1) * B_b per window ------------------------------------------------
 struct MsmWindow { uint32_t bucket_base, nb, c, msm; };
-constexpr uint32_t kSegBuckets = 32;
+constexpr uint32_t kSegBuckets = 8;       // buckets per thread: the running sums are ONE dependent chain of 2 x kSegBuckets full additions
+constexpr uint32_t kSegSpan = 1024;       // segment partials summed per block of k_msm_part_sum (stage A)
 // grid (ceil(max_segs/128), n_windows); seg_part[w * max_segs + seg]
 static __global__ void __launch_bounds__(128)
 k_msm_bucket_reduce(const MsmWindow* __restrict__ wins, const G1X* __restrict__ bucket_sums, uint32_t max_segs,
@@ -337,22 +341,29 @@ k_msm_bucket_reduce(const MsmWindow* __restrict__ wins, const G1X* __restrict__ 
   if (lo) g1x_add(tot, g1x_mul_small(run, lo));
   g1x_store(seg_part + (size_t)blockIdx.y * max_segs + seg, tot);
 }
-// one block per window: tree sum of its segment partials
+// Tree sum of partial points, two stages so that a window of 2^19 buckets is not summed by one block:
+//   A  grid (ceil(max_in / span), n_windows): block (x, w) sums inputs [x span, (x+1) span) of window w -> out[w * out_stride + x]
+//   B  grid (1, n_windows) with span >= the number of stage-A blocks -> the window sum
+// `per` = buckets covered by one input element (kSegBuckets for the segment partials, kSegBuckets * span for stage A's output).
 static __global__ void __launch_bounds__(128)
-k_msm_window_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ seg_part, uint32_t max_segs,
-                 G1X* __restrict__ window_sums) {
+k_msm_part_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ in, uint32_t in_stride, uint32_t per, uint32_t span,
+               G1X* __restrict__ out, uint32_t out_stride) {
   __shared__ G1X s_acc[128];
-  const MsmWindow w = wins[blockIdx.x];
-  const uint32_t nsegs = (w.nb + kSegBuckets - 1) / kSegBuckets;
+  const MsmWindow w = wins[blockIdx.y];
+  const uint32_t n_in = (w.nb + per - 1) / per;
+  const uint32_t lo = blockIdx.x * span;
+  if (lo >= n_in) return;
+  const uint32_t hi = lo + span < n_in ? lo + span : n_in;
   G1X acc = g1x_inf();
-  for (uint32_t s = threadIdx.x; s < nsegs; s += blockDim.x) g1x_add(acc, g1x_load(seg_part + (size_t)blockIdx.x * max_segs + s));
+  for (uint32_t s = lo + threadIdx.x; s < hi; s += blockDim.x) g1x_add(acc, g1x_load(in + (size_t)blockIdx.y * in_stride + s));
   s_acc[threadIdx.x] = acc;
   __syncthreads();
+  const uint32_t cnt = hi - lo;
   for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (threadIdx.x < s && threadIdx.x + s < nsegs) { G1X a = s_acc[threadIdx.x]; g1x_add(a, s_acc[threadIdx.x + s]); s_acc[threadIdx.x] = a; }
+    if (threadIdx.x < s && threadIdx.x + s < cnt) { G1X a = s_acc[threadIdx.x]; g1x_add(a, s_acc[threadIdx.x + s]); s_acc[threadIdx.x] = a; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) g1x_store(window_sums + blockIdx.x, s_acc[0]);
+  if (threadIdx.x == 0) g1x_store(out + (size_t)blockIdx.y * out_stride + blockIdx.x, s_acc[0]);
 }
 
 // ---- indexed point sums (one-hot commitments), dedicated path ---------------------------------------------------
@@ -418,7 +429,7 @@ k_msm_final(const MsmDesc* __restrict__ descs, uint32_t count, const G1X* __rest
   if (m >= count) return;
   const MsmDesc d = descs[m];
   G1X acc = g1x_inf();
-  for (uint32_t w = d.fixed_stride ? 1u : d.nwin; w-- > 0;) {
+  for (uint32_t w = d.fixed_stride ? d.sub : d.nwin; w-- > 0;) {
     if (!g1x_is_inf(acc)) for (uint32_t k = 0; k < d.c; k++) acc = g1x_dbl(acc);
     g1x_add(acc, g1x_load(window_sums + d.win_base + w));
   }
