@@ -98,6 +98,7 @@ size_t ja_poly_len(const ja_poly*);
 /* copy current (bound) coefficients to the host as Fr; cap >= len */
 int32_t ja_poly_to_host(ja_ctx*, const ja_poly*, uint64_t* out, size_t cap);
 void ja_poly_free(ja_ctx*, ja_poly*);
+void ja_poly_free_many(ja_ctx*, ja_poly* const* polys, size_t n);   /* the d RA polynomials of a node in one call */
 
 /* PolynomialBinding::bind_parallel (multilinear_polynomial.rs:728-742) ->
  * DensePolynomial::bound_poly_var_top_zero_optimized (dense_mlpoly.rs:126-141, HighToLow) /

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libjolt_atlas_b200.so")
 
-u64p = C.POINTER(C.c_uint64)
+u64p = C.c_void_p     # Fr / Fq limb arrays travel as plain addresses (ndarray.ctypes.data): POINTER(c_uint64) conversion costs ~1.3 us per argument
 i32p = C.POINTER(C.c_int32)
 u32p = C.POINTER(C.c_uint32)
 vp = C.c_void_p
@@ -30,6 +30,7 @@ SIGNATURES = {
     "ja_poly_len": (C.c_size_t, [vp]),
     "ja_poly_to_host": (C.c_int32, [vp, vp, u64p, C.c_size_t]),
     "ja_poly_free": (None, [vp, vp]),
+    "ja_poly_free_many": (None, [vp, vp, C.c_size_t]),
     "ja_bind": (C.c_int32, [vp, vp, u64p, C.c_int32]),
     "ja_bind_many": (C.c_int32, [vp, vpp, C.c_size_t, u64p, C.c_int32]),
     "ja_final_claim": (C.c_int32, [vp, vp, u64p]),

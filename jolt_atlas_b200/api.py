@@ -34,9 +34,16 @@ class EvalKernel:
     FAMILY_S = (0, 1, 2, 3, 4, 5, 6)
 
 
+class _Addr(C.c_void_p):
+    """Address of an ndarray's buffer that keeps the array alive for the duration of the call it is passed to."""
+    __slots__ = ("_keep",)
+
+
 def _u64p(a: np.ndarray):
     assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
-    return a.ctypes.data_as(_lib.u64p)
+    p = _Addr(a.ctypes.data)
+    p._keep = a
+    return p
 
 
 def _fr_arg(x) -> np.ndarray:
@@ -171,6 +178,17 @@ class MultilinearPolynomial:
         if self._h:
             self.ctx._lib.ja_poly_free(self.ctx._h, self._h)
             self._h = None
+
+    @staticmethod
+    def free_many(polys):
+        """Release several polynomials of one context in one call (ja_poly_free_many)."""
+        live = [p for p in polys if p._h]
+        if not live:
+            return
+        arr = (C.c_void_p * len(live))(*[p._h for p in live])
+        live[0].ctx._lib.ja_poly_free_many(live[0].ctx._h, arr, len(live))
+        for p in live:
+            p._h = None
 
     def __len__(self):
         return int(self.ctx._lib.ja_poly_len(self._h))
@@ -513,7 +531,8 @@ def sumcheck_prove(ctx: Context, kind: int, polys, claim, transcript: Blake2bTra
                                      max_coeffs, _u64p(coeffs), ncoeffs.ctypes.data_as(_lib.u32p), _u64p(chal), _u64p(fin)))
     transcript.state = st.raw
     transcript.n_rounds = nr.value
-    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(rounds)], "challenges": chal, "final_claims": fin}
+    nc = ncoeffs.tolist()
+    return {"coeffs": [coeffs[i, : nc[i]] for i in range(rounds)], "challenges": chal, "final_claims": fin, "msg_bytes": 32 * sum(nc)}
 
 
 # ---- one-hot address batches (witness.rs:84-99 -> OneHotPolynomial; hyperkzg/mod.rs:558-596; shout.rs:549-598) ----
@@ -658,4 +677,6 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
                                              ncoeffs.ctypes.data_as(_lib.u32p), _u64p(chal)))
     transcript.state = st.raw
     transcript.n_rounds = nr.value
-    return {"coeffs": [coeffs[i, : ncoeffs[i]].copy() for i in range(max_rounds)], "challenges": chal, "final_claims": finals}
+    nc = ncoeffs.tolist()
+    return {"coeffs": [coeffs[i, : nc[i]] for i in range(max_rounds)], "challenges": chal, "final_claims": finals,
+            "msg_bytes": 32 * sum(nc)}

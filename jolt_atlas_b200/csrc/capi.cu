@@ -218,6 +218,19 @@ void ja_poly_free(ja_ctx* c, ja_poly* p) {
   delete p;
 }
 
+void ja_poly_free_many(ja_ctx* c, ja_poly* const* polys, size_t n) {
+  if (!c || !polys) return;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  for (size_t i = 0; i < n; i++) {
+    ja_poly* p = polys[i];
+    if (!p) continue;
+    dev_free(c, p->buf[0]);
+    dev_free(c, p->buf[1]);
+    delete p;
+  }
+}
+
 int32_t ja_bind_many(ja_ctx* c, ja_poly* const* polys, size_t n_polys, const uint64_t r[4], int32_t order) {
   JA_REQUIRE(c && polys && r, "ja_bind: null argument");
   JA_REQUIRE(order == JA_LOW_TO_HIGH || order == JA_HIGH_TO_LOW, "ja_bind: bad binding order");

@@ -192,9 +192,8 @@ def _ra_checks(A, ctx, addr, ni, lo, hi, claim, t, out, sc):
          "r_address": ni.r_addr},
     ], t)
     out["finals"].extend(r["final_claims"])
-    out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])
-    for q in ra:
-        q.free()
+    out["msg_bytes"] += r["msg_bytes"]
+    A.MultilinearPolynomial.free_many(ra)
     return first
 
 
@@ -213,7 +212,7 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
 
     def _sc(*a, **kw):
         r = A.sumcheck_prove(*a, **kw)
-        out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])     # round polynomials read back from the device
+        out["msg_bytes"] += r["msg_bytes"]                         # round polynomials read back from the device
         out["finals"].append(r["final_claims"])
         return r
     # A. witness commitment of EVERY one-hot polynomial before the IOP, as ONNXProof::prove does
@@ -259,15 +258,14 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
                 left = A.tensor_fold_i32(ctx, ni.A, eq_r, transpose=False)     # (m x k) folded over rows -> k
                 right = A.tensor_fold_i32(ctx, ni.B, eq_c, transpose=True)     # (k x n) folded over columns -> k
             _sc(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
-            for q in (eq_r, eq_c, left, right):
-                q.free()
+            A.MultilinearPolynomial.free_many([eq_r, eq_c, left, right])
         else:
             if res:
                 a, b = res["A"].clone(), res["B"].clone()
             else:
                 a, b = A.MultilinearPolynomial.from_i32(ctx, ni.A), A.MultilinearPolynomial.from_i32(ctx, ni.B)
             _sc(ctx, A.EvalKernel.MUL if spec.kind == "mul" else A.EvalKernel.ADD, [a, b], claim, t, eq_w=ni.eq_w)
-            a.free(); b.free()
+            A.MultilinearPolynomial.free_many([a, b])
         if hot4 is not None:
             # F. remainder RA checks (batched: product of d = 4, Hamming weight, booleanity)
             rem0 = _ra_checks(A, ctx, hot4, ni, D_CLAMP, ni.d_hot, claim, t, out, _sc)
@@ -287,7 +285,7 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
                                "claims": np.broadcast_to(claim, (hi - lo, 4))})
                 batches.append(h)
     r = A.batched_sumcheck_prove(ctx, groups, t)
-    out["msg_bytes"] += sum(c.nbytes for c in r["coeffs"])
+    out["msg_bytes"] += r["msg_bytes"]
     claims = np.concatenate(r["final_claims"])
     out["finals"].append(claims)
     tr = PAR.Transcript(state=t.state, n_rounds=t.n_rounds)
