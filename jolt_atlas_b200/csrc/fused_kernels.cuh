@@ -243,10 +243,10 @@ JA_DEV void prod_tail(Fr tot /* valid in threads < L */, Fr* partials, unsigned 
   __threadfence();
   Fr acc = fp_zero<FrParams>();
   for (unsigned b = threadIdx.x / L; b < nb; b += GPB) {
-    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(partials + (size_t)b * L + li);
+    const uint4* q = reinterpret_cast<const uint4*>(partials + (size_t)b * L + li);
+    const uint4 lo = __ldcg(q), hi = __ldcg(q + 1);               // L2 (coherent after the fence), two 16-byte loads
     Fr t;
-#pragma unroll
-    for (int i = 0; i < 8; i++) t.l[i] = q[i];
+    t.l[0] = lo.x; t.l[1] = lo.y; t.l[2] = lo.z; t.l[3] = lo.w; t.l[4] = hi.x; t.l[5] = hi.y; t.l[6] = hi.z; t.l[7] = hi.w;
     acc = fp_add<FrParams>(acc, t);
   }
   tot = block_sum_by_lane<L, BLOCK>(acc);
@@ -325,55 +325,88 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const MailR
 // the 16 evaluation points X = 1..15 and "infinity").  Each thread forms its polynomial's 4 values, then the 16 lanes of a
 // quarter multiply across polynomials: exchange on bit 3 (4 values -> 2, two products), on bit 2 (2 -> 1, one product) and a
 // multiplying butterfly on bits 1, 0: 5 dependent products per thread instead of 15, at 1.3x the total work and 4x the
-// (L2-resident) loads.  Block = 128 threads = 2 pairs; the launcher uses it while the whole grid fits the SMs once or twice.
+// (L2-resident) loads.  Block = 128 threads = 2 pairs per pass of its loop.  It is a LATENCY form: on large slabs both forms reach
+// ~0.72 of the field-mul peak and this one does 1.6x the products (600 vs 394 us at 2^16 pairs), so the launcher uses it up
+// to kWideMaxPairs only (JA_BIGWIDE=1 enables it on large slabs for experiments).
 constexpr int kWideBlock = 128;
 constexpr size_t kWideMaxPairs = 256;      // measured on B200: 64 threads per pair wins up to 2^8 pairs, loses from 2^10 (scripts/small_probe.py)
 constexpr size_t kSmallMaxPairs = 1024;    // 128-thread blocks up to here
+constexpr size_t kBigWideMinPairs = 2048;  // JA_BIGWIDE=1 only: the 64-threads-per-pair form with several pairs per block
+// sub-grids of the large-slab form: product blocks (3 of the 4 resident blocks per SM) and booleanity blocks
+static inline __host__ __device__ size_t big_wide_ppb_prod(size_t G) { size_t p = (G + (size_t)kSMs * 3 - 1) / ((size_t)kSMs * 3); return (p + 1) & ~size_t(1); }
+static inline __host__ __device__ size_t big_wide_ppb_bool(size_t G) { size_t p = (G + (size_t)kSMs - 1) / (size_t)kSMs; return (p + 7) & ~size_t(7); }
 template <bool FUSED>
 JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out,
-                                   const Fr* __restrict__ e_in, int bits_in, size_t G, Fr* partials /* [nb][16] */, unsigned int* counter,
+                                   const Fr* __restrict__ e_in, int bits_in, size_t G, size_t pairs_per_block /* multiple of 2 */,
+                                   Fr* partials /* [nb][16] */, unsigned int* counter,
                                    const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off = 0) {
   constexpr int L = 16, PPB = kWideBlock / 64;
   const int t = threadIdx.x & 63, li = t & 15, s = t >> 4, group = threadIdx.x >> 6;
   const bool pad = li >= d;
-  const size_t g = (size_t)bx * PPB + group;
-  const bool active = g < G;
-  const size_t gl = active ? g : (size_t)bx * PPB;
+  const bool hi8 = (li & 8) != 0, hi4 = (li & 4) != 0;
+  const size_t mask_in = (size_t(1) << bits_in) - 1;
+  const size_t g_begin = (size_t)bx * pairs_per_block;
+  size_t g_end = g_begin + pairs_per_block;
+  if (g_end > G) g_end = G;
   const Fr* __restrict__ zin = P.in[pad ? 0 : li];
   Fr* __restrict__ zout = P.out[pad ? 0 : li];
   Fr a0, a1, a2, a3;
-  if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-  else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
-  // the pair's eq weight, formed while the challenge is still on its way
-  const Fr ew = fp_mul<FrParams>(fp_load(e_out + ((gl + g_off) >> bits_in)), fp_load(e_in + ((gl + g_off) & ((size_t(1) << bits_in) - 1))));
-  if (FUSED && !mail_wait(r, mail)) return;
-  Fr p0, dp;
-  if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
-  else if (FUSED) {
-    p0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
-    const Fr p1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
-    if (active && s == 0) { fp_store(zout + 2 * gl, p0); fp_store(zout + 2 * gl + 1, p1); }
-    dp = fp_sub<FrParams>(p1, p0);
-  } else {
-    p0 = a0;
-    dp = fp_sub<FrParams>(a1, p0);
+  {
+    const size_t g = g_begin + group;
+    const size_t gl = g < g_end ? g : g_begin;
+    if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+    else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
   }
-  // my points k = 4 s + j: X = k + 1 for k < 15, k = 15 the leading coefficient (pad lanes: the constant 1)
-  const Fr dp4 = fp_dbl<FrParams>(fp_dbl<FrParams>(dp));
-  Fr off = (s & 1) ? dp4 : fp_zero<FrParams>();
-  if (s & 2) off = fp_add<FrParams>(off, fp_dbl<FrParams>(dp4));
-  const Fr v0 = fp_add<FrParams>(fp_add<FrParams>(p0, dp), off);
-  const Fr v1 = fp_add<FrParams>(v0, dp), v2 = fp_add<FrParams>(v1, dp);
-  const Fr v3 = s == 3 ? (pad ? p0 : dp) : fp_add<FrParams>(v2, dp);
-  const bool hi8 = (li & 8) != 0, hi4 = (li & 4) != 0;
-  const Fr n0 = fp_mul<FrParams>(fr_select(hi8, v2, v0), fr_shfl_xor(fr_select(hi8, v0, v2), 8));
-  const Fr n1 = fp_mul<FrParams>(fr_select(hi8, v3, v1), fr_shfl_xor(fr_select(hi8, v1, v3), 8));
-  Fr w = fp_mul<FrParams>(fr_select(hi4, n1, n0), fr_shfl_xor(fr_select(hi4, n0, n1), 4));
-  w = fp_mul<FrParams>(w, fr_shfl_xor(w, 2));
-  w = fp_mul<FrParams>(w, fr_shfl_xor(w, 1));
-  // point k = 4 s + 2 hi8 + hi4 is complete in all four lanes that share (s, hi8, hi4); lane (li & 3) == 0 weighs it
+  if (FUSED && !mail_wait(r, mail)) return;
+  Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
+  size_t cur_xout = ~size_t(0);
+  for (size_t base = g_begin; base < g_end; base += PPB) {      // uniform trip count: every lane joins the shuffles
+    const size_t g = base + group;
+    const bool active = g < g_end;
+    const size_t gl = active ? g : g_begin;
+    if (base != g_begin) {
+      if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
+      else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); }
+    }
+    Fr p0, dp;
+    if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
+    else if (FUSED) {
+      p0 = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
+      const Fr p1 = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
+      if (active && s == 0) { fp_store(zout + 2 * gl, p0); fp_store(zout + 2 * gl + 1, p1); }
+      dp = fp_sub<FrParams>(p1, p0);
+    } else {
+      p0 = a0;
+      dp = fp_sub<FrParams>(a1, p0);
+    }
+    // my points k = 4 s + j: X = k + 1 for k < 15, k = 15 the leading coefficient (pad lanes: the constant 1)
+    const Fr dp4 = fp_dbl<FrParams>(fp_dbl<FrParams>(dp));
+    Fr off = (s & 1) ? dp4 : fp_zero<FrParams>();
+    if (s & 2) off = fp_add<FrParams>(off, fp_dbl<FrParams>(dp4));
+    const Fr v0 = fp_add<FrParams>(fp_add<FrParams>(p0, dp), off);
+    const Fr v1 = fp_add<FrParams>(v0, dp), v2 = fp_add<FrParams>(v1, dp);
+    const Fr v3 = s == 3 ? (pad ? p0 : dp) : fp_add<FrParams>(v2, dp);
+    const Fr n0 = fp_mul<FrParams>(fr_select(hi8, v2, v0), fr_shfl_xor(fr_select(hi8, v0, v2), 8));
+    const Fr n1 = fp_mul<FrParams>(fr_select(hi8, v3, v1), fr_shfl_xor(fr_select(hi8, v1, v3), 8));
+    Fr w = fp_mul<FrParams>(fr_select(hi4, n1, n0), fr_shfl_xor(fr_select(hi4, n0, n1), 4));
+    w = fp_mul<FrParams>(w, fr_shfl_xor(w, 2));
+    w = fp_mul<FrParams>(w, fr_shfl_xor(w, 1));
+    // point k = 4 s + 2 hi8 + hi4 is complete in all four lanes that share (s, hi8, hi4); lane (li & 3) == 0 weighs it
+    if (active && (li & 3) == 0) {
+      const size_t x_out = (g + g_off) >> bits_in;
+      if (x_out != cur_xout) {
+        if (cur_xout != ~size_t(0)) {
+          outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
+          inner = fp_zero<FrParams>();
+        }
+        cur_xout = x_out;
+      }
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), w));
+    }
+  }
+  if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));
   __shared__ Fr s_red[PPB][L];
-  if ((li & 3) == 0) s_red[group][4 * s + (hi8 ? 2 : 0) + (hi4 ? 1 : 0)] = active ? fp_mul<FrParams>(ew, w) : fp_zero<FrParams>();
+  if ((li & 3) == 0) s_red[group][4 * s + (hi8 ? 2 : 0) + (hi4 ? 1 : 0)] = outer;
   __syncthreads();
   Fr tot = fp_zero<FrParams>();
   if (threadIdx.x < L) {
@@ -393,9 +426,9 @@ k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, con
 template <bool FUSED>
 __global__ void __launch_bounds__(kWideBlock)
 k_round_prod16_wide(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
-                    Fr* partials /* [gridDim.x][16] */, unsigned int* counter, Publish pub, size_t g_off = 0,
+                    size_t pairs_per_block, Fr* partials /* [gridDim.x][16] */, unsigned int* counter, Publish pub, size_t g_off = 0,
                     MailRef mail = MailRef{nullptr, nullptr, 0}) {
-  round_prod16_wide_body<FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
+  round_prod16_wide_body<FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 
 // ---- booleanity phase 2, lane-parallel (booleanity.rs:254-301) ---------------------------------------------------------
@@ -510,7 +543,7 @@ k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{nu
   if (blockIdx.y == 0) {
     if (blockIdx.x >= A.nb) return;
     if constexpr (L == 16 && BLOCK == kWideBlock && WIDE)
-      round_prod16_wide_body<FUSED>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
+      round_prod16_wide_body<FUSED>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
     else
       round_prod_body<L, false, FUSED, BLOCK>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
   } else {

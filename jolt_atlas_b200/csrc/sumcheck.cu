@@ -420,10 +420,15 @@ struct DevInst : Inst {
     int L = 2; while (L < d) L <<= 1;
     // small slabs: 128-thread blocks, one pass per block (the product of 9..16 factors on 64 threads per pair)
     const bool no_small = getenv("JA_NO_WIDE") != nullptr;                     // JA_NO_WIDE=1: tests compare the variants
-    small_round = !no_small && pr->G <= kSmallMaxPairs;
-    wide_round = small_round && L == 16 && pr->G <= kWideMaxPairs;
+    // JA_BIGWIDE=1 (experiment, off): the 64-threads-per-pair form on LARGE slabs too.  Measured on B200 it loses - 600 vs 394 us at
+    // 2^16 pairs: both forms sit at ~0.72 of the field-mul peak there, and the wide one does 1.6x the products.
+    const bool big_wide = !no_small && L == 16 && pr->G >= kBigWideMinPairs && getenv("JA_BIGWIDE") != nullptr;
+    small_round = big_wide || (!no_small && pr->G <= kSmallMaxPairs);
+    wide_round = big_wide || (small_round && L == 16 && pr->G <= kWideMaxPairs);
     size_t ppb;
-    if (small_round) {
+    if (big_wide) {
+      ppb = kind == JA_EVAL_PROD ? big_wide_ppb_prod(pr->G) : big_wide_ppb_bool(pr->G);
+    } else if (small_round) {
       ppb = (kind == JA_EVAL_PROD && wide_round) ? (size_t)kWideBlock / 64 : (size_t)kWideBlock / L;
     } else {
       const size_t gpb = (size_t)kBlock / L;
@@ -523,11 +528,14 @@ struct DevInst : Inst {
       const int d = kind == JA_EVAL_POW ? (int)pow_d : (int)polys.size();
       const bool same = kind == JA_EVAL_POW;
       int L = 2; while (L < d) L <<= 1;
-      if (!same && L == 16 && G <= kWideMaxPairs && getenv("JA_NO_WIDE") == nullptr) {
-        const unsigned grid = (unsigned)((G + 1) / 2);
+      const bool big_wide = G >= kBigWideMinPairs && getenv("JA_BIGWIDE") != nullptr;
+      if (!same && L == 16 && (G <= kWideMaxPairs || big_wide) && getenv("JA_NO_WIDE") == nullptr) {
+        size_t wppb = 2;
+        if (big_wide) { wppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4); wppb = (wppb + 1) & ~size_t(1); }
+        const unsigned grid = (unsigned)((G + wppb - 1) / wppb);
         const MailRef mref{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag};
-        if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, part, ctr, pub, pr.g_off, mref));
-        else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<false><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, part, ctr, pub, pr.g_off, mref));
+        if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, wppb, part, ctr, pub, pr.g_off, mref));
+        else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<false><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, wppb, part, ctr, pub, pr.g_off, mref));
         prod_lanes = L;
         JA_CUDA(cudaGetLastError());
         commit_round(pr);
@@ -1496,13 +1504,16 @@ int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, f
   auto launch = [&]() {
     cudaStream_t s = c->stream;
     if (which == 9) {
-      JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<(unsigned)((G + 1) / 2), kWideBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, c->d_partials, c->d_counter, slot.pub));
+      size_t wppb = 2;
+      if (G > kWideMaxPairs) { wppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4); wppb = (wppb + 1) & ~size_t(1); }
+      JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<(unsigned)((G + wppb - 1) / wppb), kWideBlock, 0, s>>>(P, np, ch, eq->e_out(), eq->e_in(), bits_in, G, wppb, c->d_partials, c->d_counter, slot.pub));
     } else if (which >= 10) {
       const bool wide = which == 11;
       PairArgs A, B;
       for (int q = 0; q < 16; q++) { A.P.in[q] = P.in[q]; A.P.out[q] = P.out[q]; B.P.in[q] = P.in[16 + q]; B.P.out[q] = P.out[16 + q]; }
       A.d = B.d = 16; A.e_out = B.e_out = eq->e_out(); A.e_in = B.e_in = eq->e_in(); A.bits_in = B.bits_in = bits_in; A.G = B.G = G;
-      if (wide) { A.ppb = 2; B.ppb = kWideBlock / 16; }
+      if (wide && G > kWideMaxPairs) { A.ppb = big_wide_ppb_prod(G); B.ppb = big_wide_ppb_bool(G); }
+      else if (wide) { A.ppb = 2; B.ppb = kWideBlock / 16; }
       else if (which == 12) { A.ppb = B.ppb = kWideBlock / 16; }
       else { size_t ppb = (G + (size_t)kSMs * 2 - 1) / ((size_t)kSMs * 2); ppb = (ppb + 15) / 16 * 16; A.ppb = B.ppb = ppb; }
       A.nb = (unsigned)((G + A.ppb - 1) / A.ppb); B.nb = (unsigned)((G + B.ppb - 1) / B.ppb);

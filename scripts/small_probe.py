@@ -7,8 +7,6 @@ names = {0: "add", 1: "mul", 2: "ident", 3: "prod4", 4: "prod16", 5: "bool16", 6
 with Context(0) as ctx:
     for which in (2, 0, 1, 3, 4, 9, 5, 10, 11, 12):
         row = []
-        for log_n in (6, 8, 10, 11, 12, 13, 14):
-            if which in (9, 11) and log_n > 12:      # the small-slab variants run up to 2^10 pairs
-                continue
+        for log_n in (6, 8, 10, 11, 12, 13, 14, 15, 16, 18):
             row.append("%5.1f" % (ctx.bench_fused(which, log_n, 200) * 1e3))
-        print("%-8s us/launch at log_n 6,8,10,11,12,13,14: %s" % (names[which], " ".join(row)), flush=True)
+        print("%-8s us/launch at log_n 6,8,10,11,12,13,14,15,16,18: %s" % (names[which], " ".join(row)), flush=True)

@@ -70,6 +70,18 @@ def test_ra_onehot_checks_batch(ctx, d, log_k, log_t, none_frac):
     addr.free()
 
 
+@pytest.mark.parametrize("d,log_t", [(13, 9), (9, 7), (16, 11)])
+@pytest.mark.parametrize("no_wide", [False, True])
+def test_ra_checks_small_slab_variants(ctx, monkeypatch, d, log_t, no_wide):
+    """The RA-check launch has three forms (256-thread blocks, 128-thread blocks, product of 9..16 factors on 64 threads per
+    pair with padded lanes for d < 16): each must give the oracle's transcript.  JA_NO_WIDE=1 forces the 256-thread form."""
+    if no_wide:
+        monkeypatch.setenv("JA_NO_WIDE", "1")
+    else:
+        monkeypatch.delenv("JA_NO_WIDE", raising=False)
+    test_ra_onehot_checks_batch(ctx, d, 4, log_t, 0.02)
+
+
 def test_mixed_batch_different_lengths(ctx):
     """MUL (2^9), DOT2 (2^6, HighToLow), ADD (2^11), IDENT (2^3), POW d=3 (2^7) in one batch: late starts, one exchange per round."""
     from jolt_atlas_b200 import Blake2bTranscriptState, EvalKernel, MultilinearPolynomial, batched_sumcheck_prove
