@@ -303,6 +303,18 @@ def run_device_arm(args):
         os.environ.pop("JA_NO_AHEAD", None)
         pk, pk_kind = peaks()
         roof = W.roofline_from_profile(prof, inputs, pk, pk_kind, ctx, sweep=not args.no_sweep)
+        # `traffic` of the class is an average over thousands of launches of different sizes and stays null; the committed
+        # `ncu --set full` captures of single launches of the dominant kernel (profiles/r1_ncu_pair_v14.*) ride along instead.
+        probe_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_pair_v14.json")
+        if os.path.exists(probe_file):
+            try:
+                forms = json.load(open(probe_file))["forms"]
+                roof["dominant"]["traffic_probe"] = {
+                    "source": "profiles/r1_ncu_pair_v14.json (ncu --set full, one launch per form, cold-cache replay)",
+                    "launches": [{"kernel": f["kernel"], "pairs": f["pairs"], "dram_bytes": f["dram_read"] + f["dram_write"],
+                                  "algorithmic_bytes": f["algorithmic_read"] + f["algorithmic_write"]} for f in forms.values()]}
+            except (OSError, KeyError, ValueError):
+                pass
         units = W.count_units(inputs)
         div = 1 if shard else world        # replicas: world proofs per step; --shard: one proof per step
         line = {"metric": metric_name(args.config), "value": ms_per_step / 1e3 / div, "unit": "s", "n_gpus": world, "steps": args.steps,
