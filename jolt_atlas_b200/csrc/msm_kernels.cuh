@@ -372,7 +372,10 @@ k_msm_part_sum(const MsmWindow* __restrict__ wins, const G1X* __restrict__ in, u
 // additions (strided so the index loads coalesce), the block folds its 128 partial sums in shared memory, and a second
 // launch folds the per-block partials of each list.  The XYZZ results go to the host, which normalises the whole
 // batch with one inversion (fq_host.hpp).
-constexpr int kIdxBlock = 128, kIdxRun = 8;
+// kIdxRun: the block's closing tree is 7 levels of FULL additions (~98 products on the critical path, most threads idle), as
+// much as a chain of 8 mixed additions (80 products): at kIdxRun = 8 the kernel ran at 0.46 of the field-mul peak.  32 puts
+// 320 products of useful chain against the same tree.
+constexpr int kIdxBlock = 128, kIdxRun = 32;
 struct IdxJob { const unsigned long long* idx; uint32_t n; uint32_t first_block; };
 
 JA_DEV G1X block_point_sum(G1X acc, G1X* s_acc /* kIdxBlock */) {
