@@ -326,6 +326,27 @@ static int32_t eq_evals_device(ja_ctx* c, const FrH* r, size_t m, const FrH& sca
 }
 
 }  // extern "C"
+// the two half tables of eq(r, .) without the outer product: eq[x] = hi[x >> bits_lo] * lo[x & mask]; lv_* are the level
+// buffers to release (dev_free) once the consumer has been enqueued
+int32_t eq_halves_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr** lv_hi, Fr** lv_lo, const Fr** hi, const Fr** lo, int* bits_lo) {
+  const size_t mh = m / 2, ml = m - mh;
+  if (ml > (size_t)kEqValMax) return fail(JA_ERR_UNSUPPORTED, "eq tables: too many variables for the by-value kernel");
+  const FrH* rr = reinterpret_cast<const FrH*>(r);
+  int32_t st = dev_alloc(c, (size_t(2) << mh) * sizeof(Fr), (void**)lv_hi);
+  if (st) return st;
+  if ((st = dev_alloc(c, (size_t(2) << ml) * sizeof(Fr), (void**)lv_lo))) return st;
+  EqLevelsValArgs v;
+  for (size_t i = 0; i < mh; i++) v.w[0][i] = to_dev(rr[i]);
+  for (size_t i = 0; i < ml; i++) v.w[1][i] = to_dev(rr[mh + i]);
+  v.m[0] = (int)mh; v.rev[0] = 0; v.buf[0] = *lv_hi; v.scale[0] = to_dev(host::FR_ONE);
+  v.m[1] = (int)ml; v.rev[1] = 0; v.buf[1] = *lv_lo; v.scale[1] = to_dev(host::FR_ONE);
+  JA_LAUNCH(c, KC_EQ_TABLE, k_eq_levels_val<<<2, kBlock, 0, c->stream>>>(v));
+  JA_CUDA(cudaGetLastError());
+  *hi = *lv_hi + ((size_t(1) << mh) - 1);
+  *lo = *lv_lo + ((size_t(1) << ml) - 1);
+  *bits_lo = (int)ml;
+  return JA_OK;
+}
 int32_t eq_evals_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr* out) {
   return eq_evals_device(c, reinterpret_cast<const FrH*>(r), m, host::FR_ONE, out);
 }

@@ -128,6 +128,74 @@ k_ra_evals_final(const Fr* __restrict__ partial, uint32_t tiles, uint32_t d, uin
   fp_store(out + (size_t)i * K + k_base + bin, tot);
 }
 
+// One-launch form for a single job whose results the host is waiting for (the RA checks of a node call compute_ra_evals
+// right before their sumcheck): eq(r_cycle, t) is formed on the fly from the two half tables (eq[t] = hi[t >> bits_lo] *
+// lo[t & mask], the same product k_eq_expand stores), the block that finishes the LAST tile of a list adds the list's tile
+// partials, and the sums go to the host with store_tagged (no D2H copy, no stream synchronisation).  K <= 16.
+static __global__ void __launch_bounds__(256)
+k_ra_evals_fused(const uint32_t* __restrict__ k_all, size_t T, const Fr* __restrict__ eq_hi, const Fr* __restrict__ eq_lo, int bits_lo,
+                 uint32_t K, Fr* __restrict__ partial /* [d][tiles][16] */, unsigned int* counters /* [d], zero on entry, reset on exit */,
+                 Fr* host_slot /* d x K tagged elements */, unsigned int tag) {
+  __shared__ Fr s_eq[kRaTile];            // the tile's eq values: 4 products per thread, all lanes busy (forming them at the hits
+  __shared__ Fr s_bin[16][16];            // would run the product once per ENTRY per warp: every entry hits exactly one bin lane)
+  __shared__ bool s_last;
+  const uint32_t bin = threadIdx.x & 15, lane = threadIdx.x >> 4;
+  const uint32_t* __restrict__ k = k_all + (size_t)blockIdx.y * T;
+  const size_t tile0 = (size_t)blockIdx.x * kRaTile;
+  const size_t t0 = tile0 + (size_t)lane * kRaRun;
+  const size_t mask_lo = (size_t(1) << bits_lo) - 1;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kRaTile; i += blockDim.x) {
+    const size_t t = tile0 + i;
+    if (t < T) s_eq[i] = fp_mul<FrParams>(fp_load(eq_hi + (t >> bits_lo)), fp_load(eq_lo + (t & mask_lo)));
+  }
+  __syncthreads();
+  Fr acc = fp_zero<FrParams>();
+  for (size_t t = t0; t < t0 + kRaRun && t < T; t += 4) {
+    uint32_t kk[4];
+    if (t + 4 <= T && (T & 3) == 0) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(k + t));
+      kk[0] = v.x; kk[1] = v.y; kk[2] = v.z; kk[3] = v.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++) kk[q] = t + q < T ? __ldg(k + t + q) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (kk[q] == bin) acc = fp_add<FrParams>(acc, s_eq[t + q - tile0]);
+  }
+  s_bin[lane][bin] = acc;
+  __syncthreads();
+  const uint32_t tiles = gridDim.x;
+  if (lane == 0) {
+    Fr tot = s_bin[0][bin];
+    for (int l = 1; l < 16; l++) tot = fp_add<FrParams>(tot, s_bin[l][bin]);
+    if (tiles == 1) { if (bin < K) store_tagged(host_slot, (int)(blockIdx.y * K + bin), tot, tag); }
+    else fp_store(partial + ((size_t)blockIdx.y * tiles + blockIdx.x) * 16 + bin, tot);
+  }
+  if (tiles == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(counters + blockIdx.y, tiles - 1) == tiles - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  acc = fp_zero<FrParams>();
+  for (uint32_t b = lane; b < tiles; b += 16) {
+    const uint4* q = reinterpret_cast<const uint4*>(partial + ((size_t)blockIdx.y * tiles + b) * 16 + bin);
+    const uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    Fr v;
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w; v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+    acc = fp_add<FrParams>(acc, v);
+  }
+  s_bin[lane][bin] = acc;
+  __syncthreads();
+  if (lane == 0 && bin < K) {
+    Fr tot = s_bin[0][bin];
+    for (int l = 1; l < 16; l++) tot = fp_add<FrParams>(tot, s_bin[l][bin]);
+    store_tagged(host_slot, (int)(blockIdx.y * K + bin), tot, tag);
+  }
+}
+
 // build_materialized_rlc, sparse half (poly/rlc_polynomial.rs:59-74): joint[k_i[t] * T + t] += coeff_i for the d one-hot
 // polynomials of an address batch.  Thread t owns column t (all its targets are congruent to t mod T), so the d updates
 // of a column are sequential in one thread and no atomics are needed; different batches are separate launches.
@@ -176,6 +244,7 @@ k_addr_validate(const uint32_t* __restrict__ k, size_t n, uint32_t K, unsigned i
 }  // namespace ja
 
 int32_t eq_evals_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr* out);   // capi.cu
+int32_t eq_halves_device_pub(ja_ctx* c, const uint64_t* r, size_t m, Fr** lv_hi, Fr** lv_lo, const Fr** hi, const Fr** lo, int* bits_lo);   // capi.cu
 
 extern "C" {
 
@@ -329,6 +398,26 @@ int32_t ja_addr_ra_evals(ja_ctx* c, const ja_addr* a, const uint64_t* r_cycle, s
   JA_CUDA(cudaSetDevice(c->device));
   Fr* ws = nullptr;
   const size_t n_out = a->d * a->K;
+  if (a->K <= 16 && log_t <= 32 && n_out * 48 <= kRowSeqOffset && getenv("JA_NO_RA_FUSED") == nullptr) {
+    // two launches (half tables, scatter + per-list reduction) and a tagged publication through the mapped value buffer
+    const uint32_t tiles = (uint32_t)((a->T + kRaTile - 1) / kRaTile);
+    Fr *lv_hi = nullptr, *lv_lo = nullptr;
+    const Fr *hi = nullptr, *lo = nullptr;
+    int bits_lo = 0;
+    int32_t st = eq_halves_device_pub(c, r_cycle, log_t, &lv_hi, &lv_lo, &hi, &lo, &bits_lo);
+    if (st) return st;
+    unsigned int* d_ctr = nullptr;
+    if ((st = dev_alloc(c, a->d * tiles * 16 * sizeof(Fr) + a->d * sizeof(unsigned int), (void**)&ws))) return st;
+    d_ctr = reinterpret_cast<unsigned int*>(ws + a->d * tiles * 16);
+    JA_CUDA(cudaMemsetAsync(d_ctr, 0, a->d * sizeof(unsigned int), c->stream));
+    const uint32_t tag = next_tag(c);
+    JA_LAUNCH(c, KC_SCATTER, k_ra_evals_fused<<<dim3(tiles, (unsigned)a->d), 256, 0, c->stream>>>(a->d_k, a->T, hi, lo, bits_lo, (uint32_t)a->K, ws, d_ctr,
+                                                                                             reinterpret_cast<Fr*>(c->d_rowvals), tag));
+    JA_CUDA(cudaGetLastError());
+    st = wait_tagged(c, c->h_rowvals, tag, n_out, out_G, "compute_ra_evals kernel");
+    dev_free(c, ws); dev_free(c, lv_hi); dev_free(c, lv_lo);
+    return st;
+  }
   int32_t st = dev_alloc(c, (ra_evals_ws(a) + n_out) * sizeof(Fr), (void**)&ws);
   if (st) return st;
   Fr* d_out = ws + ra_evals_ws(a);

@@ -189,32 +189,7 @@ int32_t wait_slot(ja_ctx* c, const Slot& s) {
 // Tagged protocol (store_tagged, poly_kernels.cuh): element k of the slot is three self-validating 16-byte vectors; wait
 // until all 3 n of them carry the round's tag, then unpack n field elements into `out` (4 n limbs).
 int32_t wait_slot_tagged(ja_ctx* c, const Slot& s, size_t n, uint64_t* out) {
-  const volatile uint32_t* h = reinterpret_cast<const volatile uint32_t*>(s.host_vals);
-  const uint32_t tag = s.pub.value;
-  uint64_t spins = 0;
-  auto t0 = std::chrono::steady_clock::now();
-  uint32_t* o = reinterpret_cast<uint32_t*>(out);
-  for (size_t v = 0; v < 3 * n; v++) {
-    const volatile uint32_t* q = h + 4 * v;
-    while (q[3] != tag) {
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-      if ((++spins & 0xffff) == 0) {
-        cudaError_t e = cudaStreamQuery(c->stream);
-        if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JA_ERR_CUDA, std::string("sumcheck round kernel: ") + cudaGetErrorString(e));
-        if (e == cudaSuccess && q[3] != tag) return fail(JA_ERR_CUDA, "sumcheck round kernel finished without publishing its sums");
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
-          return fail(JA_ERR_CUDA, "sumcheck round kernel: timed out waiting for the published sums");
-      }
-    }
-    __atomic_thread_fence(__ATOMIC_ACQUIRE);                       // payload words are read after the tag (same 16-byte store)
-    const size_t k = v / 3, part = v % 3;
-    uint32_t* dst = o + 8 * k + 3 * part;
-    dst[0] = q[0]; dst[1] = q[1];
-    if (part < 2) dst[2] = q[2];
-  }
-  return JA_OK;
+  return wait_tagged(c, s.host_vals, s.pub.value, n, out, "sumcheck round kernel");
 }
 
 // ---- GruenSplitEqPolynomial on the host for K-entry address rounds (split_eq_poly.rs:86-145,331-372; LowToHigh) ----
