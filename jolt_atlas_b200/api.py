@@ -510,6 +510,19 @@ class HyperKZGOpening:
 
 
 # ---- Sumcheck::prove (subprotocols/sumcheck.rs:565-599) ----
+class _ScResult(dict):
+    """Result of a sumcheck call; the per-round coefficient views (`coeffs`) are built on first access (a proof makes
+    hundreds of calls and only tests / serialisation look at them)."""
+
+    def __missing__(self, key):
+        if key == "coeffs":
+            buf, nc = self["_coeffs"], self["_ncoeffs"]
+            v = [buf[i, :n] for i, n in enumerate(nc)]
+            self["coeffs"] = v
+            return v
+        raise KeyError(key)
+
+
 def sumcheck_prove(ctx: Context, kind: int, polys, claim, transcript: Blake2bTranscriptState, eq_w=None, gammas=None,
                    pow_d: int = 0, max_coeffs: int = 40):
     """One instance through the device kernels + the library transcript.  Consumes `polys`.
@@ -519,7 +532,7 @@ def sumcheck_prove(ctx: Context, kind: int, polys, claim, transcript: Blake2bTra
     arr = (C.c_void_p * len(polys))(*[p._h for p in polys])
     w = _fr_arg(eq_w).reshape(-1, 4) if eq_w is not None else None
     g = _fr_arg(gammas).reshape(-1, 4) if gammas is not None else None
-    coeffs = np.zeros((rounds, max_coeffs, 4), dtype=np.uint64)
+    coeffs = np.empty((rounds, max_coeffs, 4), dtype=np.uint64)       # the library writes ncoeffs[i] entries of row i
     ncoeffs = np.zeros(rounds, dtype=np.uint32)
     chal = np.zeros((rounds, 4), dtype=np.uint64)
     fin = np.zeros((len(polys), 4), dtype=np.uint64)
@@ -532,7 +545,7 @@ def sumcheck_prove(ctx: Context, kind: int, polys, claim, transcript: Blake2bTra
     transcript.state = st.raw
     transcript.n_rounds = nr.value
     nc = ncoeffs.tolist()
-    return {"coeffs": [coeffs[i, : nc[i]] for i in range(rounds)], "challenges": chal, "final_claims": fin, "msg_bytes": 32 * sum(nc)}
+    return _ScResult(_coeffs=coeffs, _ncoeffs=nc, challenges=chal, final_claims=fin, msg_bytes=32 * sum(nc))
 
 
 # ---- one-hot address batches (witness.rs:84-99 -> OneHotPolynomial; hyperkzg/mod.rs:558-596; shout.rs:549-598) ----
@@ -622,10 +635,12 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
     n = len(instances)
     arr = (_lib.ScInstance * n)()
     keep, finals, max_rounds = [], [], 0
+    zero_claim = np.zeros(4, dtype=np.uint64)
     for i, d in enumerate(instances):
         kind = int(d["kind"])
-        arr[i].kind = kind
-        arr[i].aux_u32 = int(d.get("aux_u32", 0))
+        ai = arr[i]                                   # one struct view per instance (every arr[i] builds a new one)
+        ai.kind = kind
+        ai.aux_u32 = int(d.get("aux_u32", 0))
         if kind == InstanceKind.OPENING_ONEHOT:
             d = dict(d)
             d["tables"] = _fr_arg(d["claims"]).reshape(-1, 1, 4)
@@ -633,42 +648,41 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
         if kind in (InstanceKind.BOOLEANITY, InstanceKind.HAMMING_TABLES, InstanceKind.OPENING_ONEHOT):
             tabs = np.ascontiguousarray(d["tables"], dtype=np.uint64)
             keep.append(tabs)
-            arr[i].n_polys, arr[i].table_len = tabs.shape[0], tabs.shape[1]
-            arr[i].host_tables = tabs.ctypes.data
+            ai.n_polys, ai.table_len = tabs.shape[0], tabs.shape[1]
+            ai.host_tables = tabs.ctypes.data
             npoly = tabs.shape[0]
             rounds = tabs.shape[1].bit_length() - 1
         else:
             polys = d["polys"]
             hs = (C.c_void_p * len(polys))(*[p._h for p in polys])
             keep.append(hs)
-            arr[i].n_polys = len(polys)
-            arr[i].polys = C.cast(hs, C.c_void_p)
+            ai.n_polys = len(polys)
+            ai.polys = C.cast(hs, C.c_void_p)
             npoly = len(polys)
             rounds = len(polys[0]).bit_length() - 1
         aux = d.get("aux_fr")
         if kind == InstanceKind.OPENING_ONEHOT:
-            arr[i].addr = d["addr"]._h
+            ai.addr = d["addr"]._h
             rounds = _fr_arg(aux).reshape(-1, 4).shape[0] + _fr_arg(d["eq_w"]).reshape(-1, 4).shape[0]
         if kind == InstanceKind.BOOLEANITY:
-            arr[i].addr = d["addr"]._h
+            ai.addr = d["addr"]._h
             ra = _fr_arg(d["r_address"]).reshape(-1, 4)
             aux = np.concatenate([_fr_arg(d["gammas"]).reshape(-1, 4), ra])
-            arr[i].aux_u32 = ra.shape[0]
+            ai.aux_u32 = ra.shape[0]
             rounds = ra.shape[0] + _fr_arg(d["eq_w"]).reshape(-1, 4).shape[0]
         for key, val in (("eq_w", d.get("eq_w")), ("aux_fr", aux)):
             if val is not None:
                 v = np.ascontiguousarray(_fr_arg(val).reshape(-1, 4))
                 keep.append(v)
-                setattr(arr[i], key, v.ctypes.data)
-                setattr(arr[i], "eq_m" if key == "eq_w" else "n_aux", v.shape[0])
-        claim = _fr_arg(d.get("claim", np.zeros(4, dtype=np.uint64)))
-        for k in range(4):
-            arr[i].claim[k] = int(claim[k])
+                setattr(ai, key, v.ctypes.data)
+                setattr(ai, "eq_m" if key == "eq_w" else "n_aux", v.shape[0])
+        claim = _fr_arg(d.get("claim", zero_claim))
+        C.memmove(ai.claim, claim.ctypes.data, 32)
         fc = np.zeros((npoly, 4), dtype=np.uint64)
         finals.append(fc)
-        arr[i].out_final_claims = fc.ctypes.data
+        ai.out_final_claims = fc.ctypes.data
         max_rounds = max(max_rounds, rounds)
-    coeffs = np.zeros((max_rounds, max_coeffs, 4), dtype=np.uint64)
+    coeffs = np.empty((max_rounds, max_coeffs, 4), dtype=np.uint64)   # the library writes ncoeffs[i] entries of row i
     ncoeffs = np.zeros(max_rounds, dtype=np.uint32)
     chal = np.zeros((max_rounds, 4), dtype=np.uint64)
     st = C.create_string_buffer(transcript.state, 32)
@@ -678,5 +692,4 @@ def batched_sumcheck_prove(ctx: Context, instances, transcript: Blake2bTranscrip
     transcript.state = st.raw
     transcript.n_rounds = nr.value
     nc = ncoeffs.tolist()
-    return {"coeffs": [coeffs[i, : nc[i]] for i in range(max_rounds)], "challenges": chal, "final_claims": finals,
-            "msg_bytes": 32 * sum(nc)}
+    return _ScResult(_coeffs=coeffs, _ncoeffs=nc, challenges=chal, final_claims=finals, msg_bytes=32 * sum(nc))
