@@ -62,7 +62,7 @@ int32_t ja_hyperkzg_open_begin(ja_ctx* c, const ja_srs* srs, const ja_poly* poly
   // commit_variable_batch(polys[1..]) (kzg.rs:227-243): one bucket pipeline for the l-1 folded polynomials
   if (ell > 1) {
     std::vector<MsmJob> jobs;
-    for (size_t k = 1; k < ell; k++) jobs.push_back(MsmJob{h->P + poly_off(n, (int)k), n >> k, 0, 254, 0});
+    for (size_t k = 1; k < ell; k++) jobs.push_back(MsmJob{h->P + poly_off(n, (int)k), n >> k, 0, 254, 0, 1});
     st = ja_msm_run(c, srs, jobs, com_xy, com_inf);
     if (st) { ja_hyperkzg_open_free(c, h); return st; }
   }
@@ -145,7 +145,7 @@ int32_t ja_hyperkzg_open_witness(ja_ctx* c, ja_hkzg* h, const uint64_t r[4], con
   JA_CUDA(cudaGetLastError());
   // commit_batch(h) (kzg.rs:195-223)
   std::vector<MsmJob> jobs;
-  for (int p = 0; p < 3; p++) jobs.push_back(MsmJob{d_H + (size_t)p * n, n, 0, 254, 0});
+  for (int p = 0; p < 3; p++) jobs.push_back(MsmJob{d_H + (size_t)p * n, n, 0, 254, 0, 1});
   st = ja_msm_run(c, h->srs, jobs, w_xy, w_inf);
   dev_free(c, d_q); dev_free(c, d_B); dev_free(c, d_H); dev_free(c, d_tab); dev_free(c, d_F); dev_free(c, d_C);
   return st;

@@ -194,14 +194,19 @@ static int32_t msm_engine(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob
   JA_CUDA(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nbt + 1), s));
   JA_CUDA(cudaMemsetAsync(d_bigcount, 0, sizeof(uint32_t), s));
   const uint32_t nthreads_n = (uint32_t)total_n;
-  JA_LAUNCH(c, KC_MSM_SORT, k_msm_digits<false><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_offsets, nullptr));
+  // plain atomics in the digit passes when every job is declared pseudo-random (MsmJob::dense_random); JA_MSM_AGG=1 forces
+  // the aggregated form, JA_MSM_PLAIN=1 the plain one for any all-MSM_FR batch
+  bool plain = getenv("JA_MSM_AGG") == nullptr;
+  const bool force_plain = getenv("JA_MSM_PLAIN") != nullptr;
+  for (const MsmJob& j : jobs) plain = plain && j.kind == MSM_FR && (j.dense_random || force_plain);
+  JA_LAUNCH(c, KC_MSM_SORT, k_msm_digits<false><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_offsets, nullptr, plain));
   STAGE("hist");
   JA_LAUNCH(c, KC_MSM_SORT, k_scan_tiles<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles));
   JA_LAUNCH(c, KC_MSM_SORT, k_scan_top<<<1, kScanBlock, 0, s>>>(d_tiles, ntiles));
   JA_LAUNCH(c, KC_MSM_SORT, k_scan_add<<<(unsigned)ntiles, kScanBlock, 0, s>>>(d_offsets, nbt + 1, d_tiles));
   JA_CUDA(cudaMemcpyAsync(d_cursor, d_offsets, sizeof(uint32_t) * (nbt + 1), cudaMemcpyDeviceToDevice, s));
   STAGE("scan");
-  JA_LAUNCH(c, KC_MSM_SORT, k_msm_digits<true><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_cursor, d_entries));
+  JA_LAUNCH(c, KC_MSM_SORT, k_msm_digits<true><<<ceil_div_u32(nthreads_n, 256), 256, 0, s>>>(d_desc, count, nthreads_n, max_nwin, d_cursor, d_entries, plain));
   STAGE("scatter");
   {
     int occ = 4;

@@ -137,7 +137,8 @@ JA_DEV bool msm_digit(const MsmDesc& d, MsmDigitIter& it, uint32_t w, uint32_t& 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_msm_digits(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n, uint32_t max_nwin,
-             uint32_t* __restrict__ ctr, uint32_t* __restrict__ entries) {
+             uint32_t* __restrict__ ctr, uint32_t* __restrict__ entries, bool plain = false /* full-width field scalars only:
+             digits of random 254-bit scalars almost never collide inside a warp, so the match_any aggregation is pure overhead */) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = g < total_n;
   MsmDesc d; d.kind = MSM_INDEXED; d.nwin = 0; d.entry_base = 0; d.bucket_base = 0;
@@ -165,8 +166,15 @@ k_msm_digits(const MsmDesc* __restrict__ descs, uint32_t count, uint32_t total_n
   for (uint32_t w = 0; w < max_nwin; w++) {
     uint32_t key = 0, payload = 0;
     const bool has = digits && w < d.nwin && msm_digit(d, it, w, key, payload);
-    const uint32_t slot = warp_agg_atomic_add(ctr, key, has);
-    if (SCATTER && has) entries[slot] = payload;
+    if (plain) {
+      if (has) {
+        if (SCATTER) entries[atomicAdd(ctr + key, 1u)] = payload;
+        else atomicAdd(ctr + key, 1u);                 // result unused: a reduction
+      }
+    } else {
+      const uint32_t slot = warp_agg_atomic_add(ctr, key, has);
+      if (SCATTER && has) entries[slot] = payload;
+    }
   }
 }
 

@@ -598,6 +598,38 @@ static __global__ void __launch_bounds__(kBlock) k_dot_full(const Fr* __restrict
 // ---- i32 tensor folds (einsum operand fold, ops/einsum/mk_kn_mn.rs:47-79) ------------------------
 // transpose == 0: out[j] = sum_i from_i32(A[i*cols+j]) * eq[i]; thread per column, rows split over grid.y,
 //                 partial[y][j] summed by k_fold_cols_finish.
+// Delayed reduction: from_i32(v) * e = v * e (e is a Montgomery residue, so v * e is the Montgomery form of the product) is
+// accumulated as a plain 320-bit integer, positive and negative v apart - 8 IMAD.WIDE per element instead of a Montgomery
+// row for from_i32 plus a full product (~150) - and folded back into the field ONCE per output:
+//   X mod p = mont(1_mont, lo) + mont(R^2, hi)   for X = lo + hi 2^256
+// (the unreduced value is the per-row multiplier of fp_mont_rows, whose bound "< 2p" needs only the OTHER operand < p).
+// |v| <= 2^31 and < 2^32 terms keep X below 2^317.
+struct Acc320 { uint32_t w[10]; };
+JA_DEV Acc320 acc320_zero() { Acc320 a;
+#pragma unroll
+  for (int i = 0; i < 10; i++) a.w[i] = 0; return a; }
+JA_DEV void acc320_mad(Acc320& a, const Fr& e, uint32_t v) {
+  unsigned long long c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (unsigned long long)e.l[i] * v + a.w[i];       // <= (2^32-1)^2 + 2 (2^32-1) = 2^64 - 1
+    a.w[i] = (uint32_t)c; c >>= 32;
+  }
+  c += a.w[8]; a.w[8] = (uint32_t)c; c >>= 32;
+  a.w[9] += (uint32_t)c;
+}
+JA_DEV Fr acc320_reduce(const Acc320& a) {
+  Fr lo, hi = fp_zero<FrParams>();
+#pragma unroll
+  for (int i = 0; i < 8; i++) lo.l[i] = a.w[i];
+  hi.l[0] = a.w[8]; hi.l[1] = a.w[9];
+  return fp_add<FrParams>(fp_mul<FrParams>(fp_one<FrParams>(), lo), fp_mul<FrParams>(fp_r2<FrParams>(), hi));
+}
+JA_DEV void acc320_mad_i32(Acc320& pos, Acc320& neg, const Fr& e, int v) {
+  if (v > 0) acc320_mad(pos, e, (uint32_t)v);
+  else if (v < 0) acc320_mad(neg, e, (uint32_t)(-(long long)v));
+}
+
 static __global__ void __launch_bounds__(kBlock)
 k_fold_cols(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __restrict__ eq,
             size_t rows_per_slice, Fr* __restrict__ partial) {
@@ -605,12 +637,12 @@ k_fold_cols(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __res
   if (j >= cols) return;
   size_t i0 = (size_t)blockIdx.y * rows_per_slice, i1 = i0 + rows_per_slice;
   if (i1 > rows) i1 = rows;
-  Fr acc = fp_zero<FrParams>();
+  Acc320 pos = acc320_zero(), neg = acc320_zero();
   for (size_t i = i0; i < i1; i++) {
-    int v = __ldg(A + i * cols + j);
-    if (v != 0) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(fr_from_i32(v), fp_load(eq + i)));
+    const int v = __ldg(A + i * cols + j);
+    if (v != 0) acc320_mad_i32(pos, neg, fp_load(eq + i), v);
   }
-  fp_store(partial + (size_t)blockIdx.y * cols + j, acc);
+  fp_store(partial + (size_t)blockIdx.y * cols + j, fp_sub<FrParams>(acc320_reduce(pos), acc320_reduce(neg)));
 }
 static __global__ void __launch_bounds__(kBlock)
 k_fold_cols_finish(const Fr* __restrict__ partial, size_t slices, size_t cols, Fr* __restrict__ out) {
@@ -626,11 +658,12 @@ k_fold_rows(const int* __restrict__ A, size_t rows, size_t cols, const Fr* __res
   const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  Fr acc = fp_zero<FrParams>();
+  Acc320 pos = acc320_zero(), neg = acc320_zero();
   for (size_t j = lane; j < cols; j += 32) {
-    int v = __ldg(A + row * cols + j);
-    if (v != 0) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(fr_from_i32(v), fp_load(eq + j)));
+    const int v = __ldg(A + row * cols + j);
+    if (v != 0) acc320_mad_i32(pos, neg, fp_load(eq + j), v);
   }
+  Fr acc = fp_sub<FrParams>(acc320_reduce(pos), acc320_reduce(neg));
   acc = fr_warp_sum(acc);
   if (lane == 0) fp_store(out + row, acc);
 }
