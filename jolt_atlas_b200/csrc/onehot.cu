@@ -135,7 +135,7 @@ k_ra_evals_final(const Fr* __restrict__ partial, uint32_t tiles, uint32_t d, uin
 static __global__ void __launch_bounds__(256)
 k_ra_evals_fused(const uint32_t* __restrict__ k_all, size_t T, const Fr* __restrict__ eq_hi, const Fr* __restrict__ eq_lo, int bits_lo,
                  uint32_t K, Fr* __restrict__ partial /* [d][tiles][16] */, unsigned int* counters /* [d], zero on entry, reset on exit */,
-                 Fr* host_slot /* d x K tagged elements */, unsigned int tag) {
+                 Fr* out /* d x K: tagged host-mapped elements (tag != 0) or plain device elements (tag == 0) */, unsigned int tag) {
   __shared__ Fr s_eq[kRaTile];            // the tile's eq values: 4 products per thread, all lanes busy (forming them at the hits
   __shared__ Fr s_bin[16][16];            // would run the product once per ENTRY per warp: every entry hits exactly one bin lane)
   __shared__ bool s_last;
@@ -169,7 +169,9 @@ k_ra_evals_fused(const uint32_t* __restrict__ k_all, size_t T, const Fr* __restr
   if (lane == 0) {
     Fr tot = s_bin[0][bin];
     for (int l = 1; l < 16; l++) tot = fp_add<FrParams>(tot, s_bin[l][bin]);
-    if (tiles == 1) { if (bin < K) store_tagged(host_slot, (int)(blockIdx.y * K + bin), tot, tag); }
+    if (tiles == 1) {
+      if (bin < K) { if (tag) store_tagged(out, (int)(blockIdx.y * K + bin), tot, tag); else fp_store(out + (size_t)blockIdx.y * K + bin, tot); }
+    }
     else fp_store(partial + ((size_t)blockIdx.y * tiles + blockIdx.x) * 16 + bin, tot);
   }
   if (tiles == 1) return;
@@ -192,7 +194,7 @@ k_ra_evals_fused(const uint32_t* __restrict__ k_all, size_t T, const Fr* __restr
   if (lane == 0 && bin < K) {
     Fr tot = s_bin[0][bin];
     for (int l = 1; l < 16; l++) tot = fp_add<FrParams>(tot, s_bin[l][bin]);
-    store_tagged(host_slot, (int)(blockIdx.y * K + bin), tot, tag);
+    if (tag) store_tagged(out, (int)(blockIdx.y * K + bin), tot, tag); else fp_store(out + (size_t)blockIdx.y * K + bin, tot);
   }
 }
 
@@ -213,6 +215,38 @@ k_rlc_add_onehot(const uint32_t* __restrict__ k_all, size_t T, uint32_t d, const
       cur.l[0] = lo.x; cur.l[1] = lo.y; cur.l[2] = lo.z; cur.l[3] = lo.w; cur.l[4] = hi.x; cur.l[5] = hi.y; cur.l[6] = hi.z; cur.l[7] = hi.w;
       fp_store(dst, fp_add<FrParams>(cur, fp_load(coeffs + i)));
     }
+  }
+}
+// The same for d <= 16 lists with a group of 16 lanes per column: lane i owns list i; lanes of a column that hit the same row
+// (equal k) elect a leader, which adds their coefficients and performs ONE read-modify-write.  All read-modify-writes of a
+// column go to distinct rows and are independent (one memory round trip instead of d dependent ones: 15 -> ~4 us per launch
+// at T = 2^14), and the coefficients travel in the kernel parameters (no staged copy per call).
+struct RlcCoeffs { Fr c[16]; };
+static __global__ void __launch_bounds__(kBlock)
+k_rlc_add_onehot_lanes(const uint32_t* __restrict__ k_all, size_t T, uint32_t d, const __grid_constant__ RlcCoeffs co, Fr* __restrict__ joint) {
+  const uint32_t lane = threadIdx.x & 31, li = threadIdx.x & 15;
+  const size_t col = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  uint32_t kk = 0xffffffffu;
+  if (col < T && li < d) kk = __ldg(k_all + (size_t)li * T + col);
+  const bool act = kk != 0xffffffffu;
+  // match key: the row within this column's half-warp; idle lanes get keys that match nothing
+  const uint32_t key = act ? (kk | ((lane & 16u) << 16)) : (0x80000000u | lane);
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
+  const bool leader = act && (uint32_t)(__ffs(peers) - 1) == lane;
+  Fr mine = fp_zero<FrParams>();
+  if (act) mine = co.c[li];
+  Fr acc = mine;
+#pragma unroll 1
+  for (uint32_t o = 1; o < 16; o++) {
+    const uint32_t src = (lane & 16u) | ((li + o) & 15u);
+    Fr v;
+#pragma unroll
+    for (int q = 0; q < 8; q++) v.l[q] = __shfl_sync(0xffffffffu, mine.l[q], src);
+    if (leader && ((peers >> src) & 1u)) acc = fp_add<FrParams>(acc, v);
+  }
+  if (leader) {
+    Fr* dst = joint + (size_t)kk * T + col;
+    fp_store(dst, fp_add<FrParams>(fp_load(dst), acc));
   }
 }
 // dense half (:42-57): joint[i] += coeff * poly[i] for i < len
@@ -452,7 +486,30 @@ int32_t ja_addr_ra_evals_many(ja_ctx* c, const ja_addr* const* addrs, const uint
   if (st) return st;
   Fr* d_all = ws + ws_total;                     // every job's d x K results, contiguous: ONE copy back
   size_t off = 0, ooff = 0, staged = 0;
+  size_t d_total = 0;
+  for (size_t j = 0; j < n; j++) d_total += addrs[j]->d;
+  unsigned int* d_ctr = nullptr;                 // per-list tile counters of the one-kernel form
+  if ((st = dev_alloc(c, d_total * sizeof(unsigned int), (void**)&d_ctr))) return st;
+  JA_CUDA(cudaMemsetAsync(d_ctr, 0, d_total * sizeof(unsigned int), c->stream));
+  const bool fused_ok = getenv("JA_NO_RA_FUSED") == nullptr;
+  size_t coff = 0;
   for (size_t j = 0; j < n; j++) {
+    if (fused_ok && addrs[j]->K <= 16 && log_ts[j] <= 32) {
+      // half eq tables + ONE scatter kernel per job (k_ra_evals_fused, plain device output)
+      const ja_addr* a = addrs[j];
+      const uint32_t tiles = (uint32_t)((a->T + kRaTile - 1) / kRaTile);
+      Fr *lv_hi = nullptr, *lv_lo = nullptr;
+      const Fr *hi = nullptr, *lo = nullptr;
+      int bits_lo = 0;
+      if ((st = eq_halves_device_pub(c, r_cycles[j], log_ts[j], &lv_hi, &lv_lo, &hi, &lo, &bits_lo))) return st;
+      JA_LAUNCH(c, KC_SCATTER, k_ra_evals_fused<<<dim3(tiles, (unsigned)a->d), 256, 0, c->stream>>>(a->d_k, a->T, hi, lo, bits_lo, (uint32_t)a->K, ws + off + a->T,
+                                                                                               d_ctr + coff, d_all + ooff, 0u));
+      JA_CUDA(cudaGetLastError());
+      dev_free(c, lv_hi); dev_free(c, lv_lo);
+      off += ra_evals_ws(a); ooff += a->d * a->K; coff += a->d;
+      continue;
+    }
+    coff += addrs[j]->d;
     if (staged + 64 * 32 > kRingBytes / 2) { JA_CUDA(cudaStreamSynchronize(c->stream)); staged = 0; }   // never lap the upload ring
     if ((st = ra_evals_enqueue(c, addrs[j], r_cycles[j], log_ts[j], ws + off, d_all + ooff))) return st;
     off += ra_evals_ws(addrs[j]);
@@ -468,6 +525,7 @@ int32_t ja_addr_ra_evals_many(ja_ctx* c, const ja_addr* const* addrs, const uint
     ooff += cnt;
   }
   dev_free(c, ws);
+  dev_free(c, d_ctr);
   return JA_OK;
 }
 
@@ -488,6 +546,16 @@ int32_t ja_rlc_add_onehot(ja_ctx* c, ja_poly* joint, const ja_addr* a, const uin
   Fr* d_co = nullptr;
   int32_t st = dev_alloc(c, a->d * sizeof(Fr), (void**)&d_co);
   if (st) return st;
+  if (a->d <= 16 && getenv("JA_NO_RLC_LANES") == nullptr) {
+    dev_free(c, d_co);
+    RlcCoeffs co;
+    memset(&co, 0, sizeof(co));
+    memcpy(co.c, coeffs, a->d * sizeof(Fr));
+    const size_t threads = a->T * 16;
+    JA_LAUNCH(c, KC_SCATTER, k_rlc_add_onehot_lanes<<<(unsigned)((threads + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(a->d_k, a->T, (uint32_t)a->d, co, joint->data()));
+    JA_CUDA(cudaGetLastError());
+    return JA_OK;
+  }
   if ((st = stage_h2d(c, d_co, coeffs, a->d * sizeof(Fr)))) return st;
   unsigned gx = grid_for(a->T);
   JA_LAUNCH(c, KC_SCATTER, k_rlc_add_onehot<<<gx, kBlock, 0, c->stream>>>(a->d_k, a->T, (uint32_t)a->d, d_co, joint->data()));
