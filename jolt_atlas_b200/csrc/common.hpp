@@ -184,32 +184,36 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
 int32_t ja_round_eval_collect(ja_ctx* c, const RoundEvalPending& pend, uint64_t* out_evals);
 
 // Host side of the tagged publication protocol (store_tagged, poly_kernels.cuh): element k of a host-mapped buffer is three
-// self-validating 16-byte vectors [l0 l1 l2 tag] [l3 l4 l5 tag] [l6 l7 0 tag]; wait until all 3 n of them carry `tag`, then
-// unpack n field elements into `out` (4 n limbs).  Bounded: a failed or finished stream and a 20 s timeout end the spin.
+// self-validating 16-byte vectors [l0 l1 l2 tag] [l3 l4 l5 tag] [l6 l7 chk tag]; wait until all 3 n of them carry `tag` (and the
+// element's xor checksum holds), then unpack n field elements into `out` (4 n limbs).  Bounded: a failed or finished stream and a 20 s timeout end the spin.
 static inline int32_t wait_tagged(ja_ctx* c, const void* host_base, uint32_t tag, size_t n, uint64_t* out, const char* what) {
   const volatile uint32_t* h = reinterpret_cast<const volatile uint32_t*>(host_base);
   uint64_t spins = 0;
   const auto t0 = std::chrono::steady_clock::now();
   uint32_t* o = reinterpret_cast<uint32_t*>(out);
-  for (size_t v = 0; v < 3 * n; v++) {
-    const volatile uint32_t* q = h + 4 * v;
-    while (q[3] != tag) {
+  for (size_t k = 0; k < n; k++) {
+    const volatile uint32_t* q = h + 12 * k;
+    uint32_t* dst = o + 8 * k;
+    for (;;) {
+      bool ok = q[3] == tag && q[7] == tag && q[11] == tag;
+      if (ok) {
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);                   // payload words are read after the tags
+        dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[4]; dst[4] = q[5]; dst[5] = q[6]; dst[6] = q[8]; dst[7] = q[9];
+        ok = (dst[0] ^ dst[1] ^ dst[2] ^ dst[3] ^ dst[4] ^ dst[5] ^ dst[6] ^ dst[7] ^ tag) == q[10];
+      }
+      if (ok) break;
 #if defined(__x86_64__)
       __builtin_ia32_pause();
 #endif
       if ((++spins & 0xffff) == 0) {
         cudaError_t e = cudaStreamQuery(c->stream);
         if (e != cudaSuccess && e != cudaErrorNotReady) return fail(JA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-        if (e == cudaSuccess && q[3] != tag) return fail(JA_ERR_CUDA, std::string(what) + " finished without publishing its results");
+        if (e == cudaSuccess && !(q[3] == tag && q[7] == tag && q[11] == tag))
+          return fail(JA_ERR_CUDA, std::string(what) + " finished without publishing its results");
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
           return fail(JA_ERR_CUDA, std::string(what) + ": timed out waiting for the published results");
       }
     }
-    __atomic_thread_fence(__ATOMIC_ACQUIRE);                       // payload words are read after the tag (same 16-byte store)
-    const size_t k = v / 3, part = v % 3;
-    uint32_t* dst = o + 8 * k + 3 * part;
-    dst[0] = q[0]; dst[1] = q[1];
-    if (part < 2) dst[2] = q[2];
   }
   return JA_OK;
 }

@@ -53,13 +53,15 @@ JA_DEV Fr fr_warp_sum(Fr a) {
 
 // Publication of a field element into host-mapped memory WITHOUT a system-scope fence (the fence + flag protocol costs
 // ~2 us per round: scripts/micro/latency_probe.cu).  Element k of a slot is three 16-byte vectors
-// [l0 l1 l2 tag] [l3 l4 l5 tag] [l6 l7 0 tag]; an aligned 16-byte store reaches host memory as a unit, so every vector
-// validates itself and the host waits until all vectors it expects carry the round's tag (sumcheck.cu: wait_slot).
+// [l0 l1 l2 tag] [l3 l4 l5 tag] [l6 l7 chk tag]; an aligned 16-byte store reaches host memory as a unit, so every vector
+// validates itself and the host waits until all vectors it expects carry the round's tag (common.hpp: wait_tagged).  chk = xor of
+// the limbs and the tag: belt and braces - an element that fails it is simply read again.
 JA_DEV void store_tagged(Fr* slot_base, int k, const Fr& v, unsigned int tag) {
   uint4* p = reinterpret_cast<uint4*>(slot_base) + 3 * k;
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(tag) : "memory");
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 1), "r"(v.l[3]), "r"(v.l[4]), "r"(v.l[5]), "r"(tag) : "memory");
-  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 2), "r"(v.l[6]), "r"(v.l[7]), "r"(0u), "r"(tag) : "memory");
+  const unsigned int chk = v.l[0] ^ v.l[1] ^ v.l[2] ^ v.l[3] ^ v.l[4] ^ v.l[5] ^ v.l[6] ^ v.l[7] ^ tag;   // the host re-reads an element whose checksum fails
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 2), "r"(v.l[6]), "r"(v.l[7]), "r"(chk), "r"(tag) : "memory");
 }
 
 // Block-wide exact field sum of NOUT values per thread, then grid-wide via per-block partials and a
