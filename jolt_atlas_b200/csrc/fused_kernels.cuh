@@ -90,6 +90,17 @@ JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
   return (v.w >> 31) == 0;
 }
 
+// The same collection with tagged publication (store_tagged) into the context's mapped value buffer: the host picks the claims
+// up as soon as they land, without a stream synchronisation at the end of every sumcheck call.
+struct CollectIdxArgs {
+  const Fr* src[32];
+  unsigned int idx[32];
+};
+static __global__ void __launch_bounds__(32) k_collect_finals_tagged(CollectIdxArgs a, int n, Fr* mapped, unsigned int tag) {
+  const int i = threadIdx.x;
+  if (i < n) store_tagged(mapped, (int)a.idx[i], fp_load(a.src[i]), tag);
+}
+
 struct FusedPolys {
   const Fr* in[kMaxProdPolys];
   Fr* out[kMaxProdPolys];        // FUSED only: bound arrays (LowToHigh: other ping-pong buffer; HighToLow: == in)

@@ -1381,10 +1381,36 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     used += cnt;
     JA_REQUIRE(used * 32 <= kPinnedBytes, "sumcheck: too many final claims for the staging buffer");
   }
-  if ((st = flush_collect(c))) return st;
-  JA_CUDA(cudaStreamSynchronize(c->stream));
-  for (size_t k = 0; k < n; k++)
-    if (insts[k]->out_final) memcpy(insts[k]->out_final, staging + 4 * span[k].first, span[k].second * 32);
+  if (used * 48 <= kRowSeqOffset && getenv("JA_NO_TAGGED_FINALS") == nullptr) {
+    // tagged publication of the final claims: no stream synchronisation at the end of the call (everything the caller
+    // does next with these buffers is stream-ordered behind the kernels of this call)
+    const uint32_t tag = next_tag(c);
+    std::vector<uint64_t> got(4 * (used ? used : 1));
+    memcpy(got.data(), staging, used * 32);                 // host-only instances wrote their claims into the staging area directly
+    std::vector<unsigned int> published;
+    published.reserve(c->collect.size());
+    for (size_t base = 0; base < c->collect.size(); base += 32) {
+      CollectIdxArgs a;
+      const int m = (int)std::min<size_t>(32, c->collect.size() - base);
+      for (int i = 0; i < 32; i++) {
+        a.src[i] = i < m ? reinterpret_cast<const Fr*>(c->collect[base + i].first) : nullptr;
+        a.idx[i] = i < m ? (unsigned int)((reinterpret_cast<const uint64_t*>(c->collect[base + i].second) - staging) / 4) : 0u;
+        if (i < m) published.push_back(a.idx[i]);
+      }
+      JA_LAUNCH(c, KC_BIND, k_collect_finals_tagged<<<1, 32, 0, c->stream>>>(a, m, reinterpret_cast<Fr*>(c->d_rowvals), tag));
+    }
+    c->collect.clear();
+    JA_CUDA(cudaGetLastError());
+    for (unsigned int idx : published)
+      if ((st = wait_tagged(c, reinterpret_cast<const char*>(c->h_rowvals) + (size_t)idx * 48, tag, 1, got.data() + 4 * (size_t)idx, "final-claim collection"))) return st;
+    for (size_t k = 0; k < n; k++)
+      if (insts[k]->out_final) memcpy(insts[k]->out_final, got.data() + 4 * span[k].first, span[k].second * 32);
+  } else {
+    if ((st = flush_collect(c))) return st;
+    JA_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < n; k++)
+      if (insts[k]->out_final) memcpy(insts[k]->out_final, staging + 4 * span[k].first, span[k].second * 32);
+  }
   if (g_trace.on)
     fprintf(stderr, "[sc n=%zu rounds=%zu] cumulative us: launch=%.0f inv=%.0f wait+interp=%.0f transcript=%.0f ingest=%.0f\n", n, max_rounds,
             g_trace.t[4], g_trace.t[0], g_trace.t[1], g_trace.t[2], g_trace.t[3]);
