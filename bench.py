@@ -134,6 +134,23 @@ def d2h_bytes(result) -> int:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+LAST_CPU_PASS = {"out": None}      # result of the last FULL oracle pass (parity check of the device arm)
+
+
+def parity_with_cpu_pass(dev_out, cpu_out) -> bool:
+    """The device pass and the oracle pass of the same inputs agree bit for bit: every commitment, every final claim, the
+    transcript state after every node (which pins every round polynomial and challenge) and the HyperKZG opening."""
+    if cpu_out is None or dev_out is None:
+        return False
+    ok = dev_out["states"] == cpu_out["states"] and len(dev_out["finals"]) == len(cpu_out["finals"])
+    ok = ok and all(np.array_equal(a, b) for a, b in zip(dev_out["finals"], cpu_out["finals"]))
+    ok = ok and len(dev_out["commitments"]) == len(cpu_out["commitments"])
+    ok = ok and all(np.array_equal(a[0], b[0]) and np.array_equal(np.asarray(a[1], dtype=bool), np.asarray(b[1], dtype=bool))
+                    for a, b in zip(dev_out["commitments"], cpu_out["commitments"]))
+    ok = ok and all(np.array_equal(dev_out["open"][k], cpu_out["open"][k]) for k in ("com", "v", "w"))
+    return bool(ok)
+
+
 def cpu_pass_seconds(srs_host, inputs, rlc_host, budget_s: float):
     """Time the C++ oracle (OpenMP, all host threads) on the workload.  Full pass when it fits the budget, else
     layer 0 x (number of identical layers) + lm_head + the opening stage (reduction sumcheck, RLC, HyperKZG open),
@@ -149,7 +166,8 @@ def cpu_pass_seconds(srs_host, inputs, rlc_host, budget_s: float):
     n_layers = (len(nodes) - 1) // per_layer
     if t_layer * n_layers * 1.6 <= budget_s:
         t0 = time.perf_counter()
-        WC.run_cpu(srs_host, inputs)
+        full_out = WC.run_cpu(srs_host, inputs)
+        LAST_CPU_PASS["out"] = full_out
         return time.perf_counter() - t0, "full pass: %d nodes + opening reduction + HyperKZG open ell=%d" % (len(nodes), inputs["ell"])
     head = dict(inputs)
     head["nodes"] = nodes[n_layers * per_layer:]
@@ -345,6 +363,13 @@ def run_device_arm(args):
             from oracle import cpu as ORC
             secs, sample = cpu_pass_seconds(srs.to_host(), inputs, None, 30.0)
             line["cpu_baseline"] = {"value": secs, "unit": "s", "cores": ORC.num_threads(), "kind": "port", "sample": sample}
+            if LAST_CPU_PASS["out"] is not None:
+                # the timed device pass (last end-to-end step) against the oracle's full pass of the same inputs, bit for bit
+                line["parity_checked"] = parity_with_cpu_pass(last, LAST_CPU_PASS["out"])
+                if not line["parity_checked"]:
+                    raise SystemExit("bench.py: the device pass differs from the CPU oracle pass (transcript states / claims / commitments / opening)")
+            else:
+                line["parity_checked"] = False   # the oracle only ran a bounded sample of this workload
     W.free_resident(resident)
     srs.free()
     ctx.close()

@@ -355,6 +355,15 @@ int32_t ja_poly_random(ja_ctx*, size_t n, uint32_t seed, ja_poly** out);
 /* register-resident Montgomery-product loop; returns achieved Fr-mul/s in *out_mul_per_s */
 int32_t ja_calibrate_fr_mul(ja_ctx*, int32_t iters, double* out_mul_per_s);
 
+/* ---- test hooks (tests/test_gpu_field.py) ------------------------------------------------------- */
+/* The device field arithmetic applied element-wise to host arrays of n Fr (Montgomery limbs), so that golden edge vectors reach
+ * fp.cuh directly: joltworks/src/field/ark.rs:76-297 (mul / add / sub / neg / square / from_i64), field/challenge/macros.rs:274-286
+ * (F * MontU128Challenge; b = {0,0,lo,hi}), field/mod.rs:286-310 (delayed reduction: MUL_WIDE returns 16 * a * b through
+ * fpw_mul_acc x 16 + one fpw_reduce).  FROM_I64 reads the i64 from limb 0 of a. */
+enum { JA_TEST_FR_MUL = 0, JA_TEST_FR_ADD = 1, JA_TEST_FR_SUB = 2, JA_TEST_FR_MUL_CHALLENGE = 3, JA_TEST_FR_FROM_I64 = 4,
+       JA_TEST_FR_MUL_WIDE = 5, JA_TEST_FR_NEG = 6, JA_TEST_FR_SQR = 7 };
+int32_t ja_test_field_ops(ja_ctx*, int32_t op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

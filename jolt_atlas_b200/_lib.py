@@ -104,6 +104,7 @@ SIGNATURES = {
     "ja_bench_fused": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "ja_poly_random": (C.c_int32, [vp, C.c_size_t, C.c_uint32, vpp]),
     "ja_calibrate_fr_mul": (C.c_int32, [vp, C.c_int32, C.POINTER(C.c_double)]),
+    "ja_test_field_ops": (C.c_int32, [vp, C.c_int32, u64p, u64p, C.c_size_t, u64p]),
 }
 
 

@@ -115,6 +115,14 @@ class Context:
         check(self._lib.ja_calibrate_fr_mul(self._h, iters, C.byref(out)))
         return out.value
 
+    def test_field_ops(self, op: int, a, b) -> np.ndarray:
+        """ja_test_field_ops: the device field arithmetic element-wise on host arrays (n, 4) of Montgomery limbs."""
+        a, b = _fr_arg(a), _fr_arg(b)
+        assert a.shape == b.shape
+        out = np.empty_like(a)
+        check(self._lib.ja_test_field_ops(self._h, op, _u64p(a), _u64p(b), a.shape[0], _u64p(out)))
+        return out
+
 
 class MultilinearPolynomial:
     def __init__(self, ctx: Context, handle):

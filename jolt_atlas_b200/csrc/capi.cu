@@ -92,8 +92,8 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   JA_CUDA(cudaHostAlloc(&c->h_mail, kMailEntries * 16, cudaHostAllocMapped));
   memset(c->h_mail, 0, kMailEntries * 16);
   JA_CUDA(cudaHostGetDevicePointer(&c->d_mail, c->h_mail, 0));
-  JA_CUDA(cudaMalloc((void**)&c->d_mail_dev, kMailEntries * 16));
-  JA_CUDA(cudaMemset(c->d_mail_dev, 0, kMailEntries * 16));
+  JA_CUDA(cudaMalloc((void**)&c->d_mail_dev, kMailEntries * 20));      // 16-byte twins, then one relay-election word per entry
+  JA_CUDA(cudaMemset(c->d_mail_dev, 0, kMailEntries * 20));
   JA_CUDA(cudaHostAlloc(&c->h_rowvals, kRowSeqOffset + 64, cudaHostAllocMapped));
   memset(c->h_rowvals, 0, kRowSeqOffset + 64);
   JA_CUDA(cudaHostGetDevicePointer(&c->d_rowvals, c->h_rowvals, 0));

@@ -68,6 +68,8 @@ struct ja_ctx {
   const void* ahead_p = nullptr;
   void* ahead_dev = nullptr;
   uint32_t ahead_tag = 0;
+  unsigned int* ahead_ticket = nullptr;   // relay-election word of the entry (behind the twins in d_mail_dev)
+  uint32_t ahead_use = 0;
   // flat host-mapped value array of the batched opening reduction (kMaxRowVals Fr + a sequence word at kRowSeqOffset)
   void* h_rowvals = nullptr;
   void* d_rowvals = nullptr;

@@ -327,6 +327,16 @@ template <class M> JA_DEV Fp<M> fp_load(const Fp<M>* p) {
   r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
   return r;
 }
+// Coherent variant (plain ld.global) for operands that alias an OUTPUT of the same kernel (the in-place HighToLow binds):
+// PTX requires memory read through ld.global.nc to stay read-only for the whole kernel.
+template <class M> JA_DEV Fp<M> fp_load_rw(const Fp<M>* p) {
+  Fp<M> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 lo = q[0], hi = q[1];
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+  r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
 template <class M> JA_DEV void fp_store(Fp<M>* p, const Fp<M>& v) {
   uint4* q = reinterpret_cast<uint4*>(p);
   q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);

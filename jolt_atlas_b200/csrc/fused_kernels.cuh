@@ -52,9 +52,11 @@ static __global__ void __launch_bounds__(64) k_collect_finals(CollectArgs a, int
 // thread 0 of block (0, 0) polls the host entry; it republishes the vector in device memory, where the other blocks pick
 // it up from L2.  p == nullptr: no mailbox, the challenge is the kernel parameter.
 struct MailRef {
-  const uint4* p;                // device address of the host-mapped entry
-  uint4* dev;                    // the entry's twin in device memory (relay target of block (0, 0))
-  uint32_t tag;                  // 1..3
+  const uint4* p = nullptr;      // device address of the host-mapped entry
+  uint4* dev = nullptr;          // the entry's twin in device memory (relay target)
+  uint32_t tag = 0;              // 1..3
+  unsigned int* ticket = nullptr;// relay election word of the entry (device memory)
+  uint32_t use = 0;              // unique id of this use of the entry (the context's mailbox sequence number, never 0)
 };
 JA_DEV uint4 ld_volatile_v4(const uint4* p) {
   uint4 v;
@@ -64,11 +66,18 @@ JA_DEV uint4 ld_volatile_v4(const uint4* p) {
 JA_DEV void st_volatile_v4(uint4* p, const uint4& v) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Relay election: the FIRST block that reaches the mailbox (atomic exchange of the entry's ticket word with this use's id)
+// polls the host entry and republishes it in device memory; every later block reads the twin.  No block waits on a block
+// that may not be resident yet (CUDA gives no ordering between the blocks of a grid), so a grid larger than the resident
+// capacity, MPS time-slicing or a debugger cannot wedge it.  Give-up path: after kMailTimeoutNs (longer than the host's own
+// 20 s wait) the waiting block treats the round as aborted and returns without publishing - no trap, the context survives
+// and the host reports the missing publication as an error.
+constexpr unsigned long long kMailTimeoutNs = 30000000000ull;
 JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
   if (!m.p) return true;
   __shared__ uint4 s_mail;
   if (threadIdx.x == 0) {
-    const bool relay = blockIdx.x == 0 && blockIdx.y == 0;
+    const bool relay = atomicExch(m.ticket, m.use) != m.use;
     const uint4* src = relay ? m.p : m.dev;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -78,7 +87,7 @@ JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
       if (((v.w >> 29) & 3u) == m.tag) break;
       if ((it & 255u) == 255u) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 5000000000ull) asm volatile("trap;");         // 5 s: the host is gone
+        if (t1 - t0 > kMailTimeoutNs) { v = make_uint4(0u, 0u, 0u, (m.tag << 29) | 0x80000000u); break; }   // the host is gone: abort
       }
     }
     if (relay) st_volatile_v4(m.dev, v);
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(kBlock, 2)
 k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
           size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
           size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */,
-          MailRef mail = MailRef{nullptr, nullptr, 0}) {
+          MailRef mail = MailRef{}) {
   constexpr int NOUT = SOut<KID>::N;
   constexpr int NP = KID == 7 ? 0 : ((KID == 3 || KID == 6) ? 1 : 2);      // polynomials with register-staged operands
   const size_t mask_in = (size_t(1) << bits_in) - 1;
@@ -431,14 +440,14 @@ template <int L, bool SAME, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0,
-             MailRef mail = MailRef{nullptr, nullptr, 0}) {
+             MailRef mail = MailRef{}) {
   round_prod_body<L, SAME, FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 template <bool FUSED>
 __global__ void __launch_bounds__(kWideBlock)
 k_round_prod16_wide(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
                     size_t pairs_per_block, Fr* partials /* [gridDim.x][16] */, unsigned int* counter, Publish pub, size_t g_off = 0,
-                    MailRef mail = MailRef{nullptr, nullptr, 0}) {
+                    MailRef mail = MailRef{}) {
   round_prod16_wide_body<FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 
@@ -528,7 +537,7 @@ template <int L, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
-             MailRef mail = MailRef{nullptr, nullptr, 0}) {
+             MailRef mail = MailRef{}) {
   round_bool_body<L, FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
 }
 
@@ -550,7 +559,7 @@ struct PairArgs {
 };
 template <int L, bool FUSED, int BLOCK = kBlock, bool WIDE = false>
 __global__ void __launch_bounds__(BLOCK)
-k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{nullptr, nullptr, 0}) {
+k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{}) {
   if (blockIdx.y == 0) {
     if (blockIdx.x >= A.nb) return;
     if constexpr (L == 16 && BLOCK == kWideBlock && WIDE)
@@ -567,7 +576,7 @@ k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{nu
 template <int NPOLY, bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array: it has 2G entries */, Fr* partials,
-            unsigned int* counter, Publish pub, MailRef mail = MailRef{nullptr, nullptr, 0}) {
+            unsigned int* counter, Publish pub, MailRef mail = MailRef{}) {
   if (FUSED && !mail_wait(r, mail)) return;
   constexpr int NOUT = NPOLY;
   Fr acc[NOUT];
@@ -581,7 +590,7 @@ k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array:
       Fr a, b;
       if (FUSED) {
         Fr* z = P.out[q];      // in place
-        const Fr a0 = fp_load(z + i), a1 = fp_load(z + i + 2 * G), b0 = fp_load(z + i + G), b1 = fp_load(z + i + 3 * G);
+        const Fr a0 = fp_load_rw(z + i), a1 = fp_load_rw(z + i + 2 * G), b0 = fp_load_rw(z + i + G), b1 = fp_load_rw(z + i + 3 * G);
         a = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
         b = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
         fp_store(z + i, a);
@@ -622,7 +631,7 @@ k_round_open(FusedPolys P, Challenge r, const Fr* __restrict__ e_out, const Fr* 
   for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
     Fr h;
     if (FUSED) {
-      const Fr a0 = fp_load(z + j), a1 = fp_load(z + j + 2 * half), b0 = fp_load(z + j + half), b1 = fp_load(z + j + 3 * half);
+      const Fr a0 = fp_load_rw(z + j), a1 = fp_load_rw(z + j + 2 * half), b0 = fp_load_rw(z + j + half), b1 = fp_load_rw(z + j + 3 * half);
       h = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
       const Fr h2 = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
       fp_store(z + j, h);
@@ -713,13 +722,13 @@ k_round_open_rows(const OpenRow* __restrict__ rows, unsigned int n_rows /* activ
   for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
     Fr h;
     if (row.fused) {
-      const Fr a0 = fp_load(z + j), a1 = fp_load(z + j + 2 * half), b0 = fp_load(z + j + half), b1 = fp_load(z + j + 3 * half);
+      const Fr a0 = fp_load_rw(z + j), a1 = fp_load_rw(z + j + 2 * half), b0 = fp_load_rw(z + j + half), b1 = fp_load_rw(z + j + 3 * half);
       h = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
       const Fr h2 = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
       fp_store(z + j, h);
       fp_store(z + j + half, h2);
     } else {
-      h = fp_load(z + j);
+      h = fp_load_rw(z + j);
     }
     const Fr w = fp_mul<FrParams>(fp_load(row.e_in + (j >> row.bits_out)), fp_load(row.e_out + (j & mask_out)));
     acc = fp_add<FrParams>(acc, fp_mul<FrParams>(w, h));

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kBlock) k_bind(BindArgs args, Challenge r, siz
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
     Fr a, b;
     if (LOW_TO_HIGH) { a = fp_load(in + 2 * i); b = fp_load(in + 2 * i + 1); }
-    else             { a = fp_load(in + i);     b = fp_load(in + i + half); }
+    else             { a = fp_load_rw(in + i);  b = fp_load_rw(in + i + half); }   // HighToLow binds run in place
     Fr m = fp_sub<FrParams>(b, a);
     fp_store(out + i, fp_add<FrParams>(a, fp_mul_challenge<FrParams>(m, r)));
   }

@@ -60,6 +60,14 @@ bool ahead_allowed() {
   return ok;
 }
 
+// mailbox reference of the round being pre-launched (null reference outside a pre-launch)
+static inline MailRef mail_ref(const ja_ctx* c) {
+  MailRef m;
+  m.p = reinterpret_cast<const uint4*>(c->ahead_p); m.dev = reinterpret_cast<uint4*>(c->ahead_dev); m.tag = c->ahead_tag;
+  m.ticket = c->ahead_ticket; m.use = c->ahead_use;
+  return m;
+}
+
 // JA_SC_TRACE=1: per-phase host wall-clock of the round loop on stderr (tuning aid)
 struct ScTrace {
   bool on = getenv("JA_SC_TRACE") != nullptr;
@@ -508,7 +516,7 @@ struct DevInst : Inst {
         size_t wppb = 2;
         if (big_wide) { wppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4); wppb = (wppb + 1) & ~size_t(1); }
         const unsigned grid = (unsigned)((G + wppb - 1) / wppb);
-        const MailRef mref{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag};
+        const MailRef mref = mail_ref(c);
         if (fz) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<true><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, wppb, part, ctr, pub, pr.g_off, mref));
         else JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod16_wide<false><<<grid, kWideBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, wppb, part, ctr, pub, pr.g_off, mref));
         prod_lanes = L;
@@ -520,7 +528,7 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
+#define JA_PROD_F(LL, SM, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod<LL, SM, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, part, ctr, pub, pr.g_off, mail_ref(c)))
 #define JA_PROD_L(LL) do { if (same) { if (fz) JA_PROD_F(LL, true, true); else JA_PROD_F(LL, true, false); } \
                            else { if (fz) JA_PROD_F(LL, false, true); else JA_PROD_F(LL, false, false); } } while (0)
       switch (L) { case 2: JA_PROD_L(2); break; case 4: JA_PROD_L(4); break; case 8: JA_PROD_L(8); break; default: JA_PROD_L(16); break; }
@@ -536,7 +544,7 @@ struct DevInst : Inst {
     } else if (kind == JA_EVAL_DOT2 || kind == JA_EVAL_DOT3) {
       unsigned grid = grid_for(G);
       if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
-#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
+#define JA_DOT_F(NP, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_dot<NP, FZ><<<grid, kBlock, 0, s>>>(P, ch, G, part, ctr, pub, mail_ref(c)))
       if (kind == JA_EVAL_DOT2) { if (fz) JA_DOT_F(2, true); else JA_DOT_F(2, false); }
       else { if (fz) JA_DOT_F(3, true); else JA_DOT_F(3, false); }
 #undef JA_DOT_F
@@ -547,7 +555,7 @@ struct DevInst : Inst {
       size_t ppb = (G + (size_t)kSMs * 4 - 1) / ((size_t)kSMs * 4);
       ppb = (ppb + gpb - 1) / gpb * gpb;
       const unsigned grid = (unsigned)((G + ppb - 1) / ppb);
-#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
+#define JA_BOOL_F(LL, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_bool<LL, FZ><<<grid, kBlock, 0, s>>>(P, d, ch, e_out, e_in, bits_in, G, ppb, d_gammas, part, ctr, pub, mail_ref(c)))
 #define JA_BOOL_L(LL) do { if (fz) JA_BOOL_F(LL, true); else JA_BOOL_F(LL, false); } while (0)
       switch (L) { case 2: JA_BOOL_L(2); break; case 4: JA_BOOL_L(4); break; case 8: JA_BOOL_L(8); break; default: JA_BOOL_L(16); break; }
 #undef JA_BOOL_L
@@ -561,7 +569,7 @@ struct DevInst : Inst {
       const size_t tpb = (tiles + grid - 1) / grid;
       grid = (tiles + tpb - 1) / tpb;
       const int np = (int)polys.size();
-#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off, MailRef{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag}))
+#define JA_S_F(KID, FZ) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_s<KID, FZ><<<(unsigned)grid, kBlock, 0, s>>>(P, np, ch, e_out, e_in, bits_in, G, tpb, d_gammas, part, ctr, pub, pr.g_off, mail_ref(c)))
 #define JA_S_K(KID) do { if (fz) JA_S_F(KID, true); else JA_S_F(KID, false); } while (0)
       switch (kind) {
         case JA_EVAL_ADD: JA_S_K(0); break;
@@ -610,6 +618,8 @@ struct DevInst : Inst {
         const bool prod = kind == JA_EVAL_PROD || kind == JA_EVAL_POW;
         w_inv.resize(eq->w.size());
         for (size_t i = 0; i < w_inv.size(); i++) w_inv[i] = prod ? host::sub(host::FR_ONE, eq->w[i]) : eq->w[i];
+        for (const FrH& x : w_inv)
+          if (x.is_zero()) return fail(JA_ERR_INVALID, "sumcheck: eq point coordinate is 0 (split-eq bodies) or 1 (product bodies): the round polynomial division is undefined");
         host::batch_inv(w_inv.data(), w_inv.size());
       }
       div = w_inv[order == JA_LOW_TO_HIGH ? eq->current_index - 1 : eq->current_index];
@@ -1006,6 +1016,9 @@ struct OpenBatch {
       if (st) return st;
       g->cw = host::from_limbs(t);
       eq1[k] = host::gruen_eq1(g->cs, g->cw);
+      // a zero divisor (a 0 coordinate of the opening point, or an eq scalar that hit 0) would zero the SHARED inverse and
+      // silently corrupt every group of the batch; the reference divides per instance and fails loudly: so do we
+      if (eq1[k].is_zero()) return fail(JA_ERR_INVALID, "sumcheck: opening reduction: eq(1) = current_scalar * w is zero (zero coordinate in an opening point)");
       pre[k] = run;
       run = host::mul(run, eq1[k]);
     }
@@ -1229,7 +1242,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
           if ((st = pb->prepare_pair(c, &B, &rb, 1))) return st;
           const unsigned int gx = std::max(A.nb, B.nb);
           int L = 2; while (L < A.d) L <<= 1;
-          const MailRef mref{reinterpret_cast<const uint4*>(c->ahead_p), reinterpret_cast<uint4*>(c->ahead_dev), c->ahead_tag};
+          const MailRef mref = mail_ref(c);
 #define JA_PAIR_B(LL, FZ, BLK, WD) JA_LAUNCH(c, KC_SUMCHECK_FUSED, k_round_prod_bool<LL, FZ, BLK, WD><<<dim3(gx, 2), BLK, 0, c->stream>>>(A, B, ra.ch, mref))
 #define JA_PAIR(LL) do { if (pa->small_round) { if (ra.fz) JA_PAIR_B(LL, true, kWideBlock, false); else JA_PAIR_B(LL, false, kWideBlock, false); } \
                            else { if (ra.fz) JA_PAIR_B(LL, true, kBlock, false); else JA_PAIR_B(LL, false, kBlock, false); } } while (0)
@@ -1288,10 +1301,12 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
         c->ahead_tag = tag;
         c->ahead_p = reinterpret_cast<const char*>(c->d_mail) + 16 * idx;
         c->ahead_dev = reinterpret_cast<char*>(c->d_mail_dev) + 16 * idx;
+        c->ahead_ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(c->d_mail_dev) + 16 * kMailEntries) + idx;
+        c->ahead_use = c->mail_seq ? c->mail_seq : (c->mail_seq = kMailEntries);      // never 0 (tickets start zeroed)
         for (size_t k = 0; k < n && !st; k++) if (remaining <= insts[k]->rounds) st = insts[k]->ahead_begin(c);
         if (!st) st = launch_round(round + 1);
         for (size_t k = 0; k < n; k++) if (remaining <= insts[k]->rounds) insts[k]->ahead_end(c);
-        c->ahead_p = nullptr; c->ahead_dev = nullptr; c->ahead_tag = 0;
+        c->ahead_p = nullptr; c->ahead_dev = nullptr; c->ahead_tag = 0; c->ahead_ticket = nullptr; c->ahead_use = 0;
         mail.entry = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<char*>(c->h_mail) + 16 * idx); mail.tag = tag;
         if (st) return st;
         prelaunched = round + 1;
@@ -1376,10 +1391,10 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   size_t used = 0;
   for (size_t k = 0; k < n; k++) {
     size_t cnt = 0;
+    JA_REQUIRE((used + kMaxProdPolys) * 32 <= kPinnedBytes, "sumcheck: too many final claims for the staging buffer");   // before finalize() writes
     if ((st = insts[k]->finalize(c, staging + 4 * used, &cnt))) return st;
     span[k] = {used, cnt};
     used += cnt;
-    JA_REQUIRE(used * 32 <= kPinnedBytes, "sumcheck: too many final claims for the staging buffer");
   }
   if (used * 48 <= kRowSeqOffset && getenv("JA_NO_TAGGED_FINALS") == nullptr) {
     // tagged publication of the final claims: no stream synchronisation at the end of the call (everything the caller

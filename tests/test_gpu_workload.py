@@ -1,4 +1,5 @@
-"""BASELINE.json configs[0]: the microgpt-shaped prove pipeline on the GPU against the CPU oracle twin, stage by stage —
+"""BASELINE.json configs[0] (microgpt) and configs[1] (nanoGPT — the shape bench.py's headline is measured on): the
+prove-shaped pipeline on the GPU against the CPU oracle twin, stage by stage —
 every one-hot commitment, every sumcheck's final claims, the transcript state after each node (which pins every round
 polynomial and challenge, since they are all absorbed), and the final HyperKZG opening.  Bit-exact."""
 import numpy as np
@@ -12,9 +13,10 @@ pytestmark = pytest.mark.gpu
 TAU = 0x1234567890abcdef1122334455667788
 
 
-def test_microgpt_pipeline_bit_exact(ctx):
+@pytest.mark.parametrize("config", ["microgpt", "nanoGPT"])
+def test_pipeline_bit_exact(ctx, config):
     from jolt_atlas_b200 import SRS, MultilinearPolynomial, workload as W
-    inputs = W.build_inputs("microgpt")
+    inputs = W.build_inputs(config)
     n = 1 << inputs["ell"]
     srs_host = ORC.srs_powers(to_mont_array([TAU])[0], n)
     srs = SRS(ctx, srs_host).precompute()
