@@ -94,6 +94,11 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
   JA_CUDA(cudaHostGetDevicePointer(&c->d_mail, c->h_mail, 0));
   JA_CUDA(cudaMalloc((void**)&c->d_mail_dev, kMailEntries * 20));      // 16-byte twins, then one relay-election word per entry
   JA_CUDA(cudaMemset(c->d_mail_dev, 0, kMailEntries * 20));
+  JA_CUDA(cudaHostAlloc(&c->h_rrmail, kRrEntries * 16, cudaHostAllocMapped));
+  memset(c->h_rrmail, 0, kRrEntries * 16);
+  JA_CUDA(cudaHostGetDevicePointer(&c->d_rrmail, c->h_rrmail, 0));
+  JA_CUDA(cudaMalloc((void**)&c->d_rrrelay, kRrEntries * 16));
+  JA_CUDA(cudaMemset(c->d_rrrelay, 0, kRrEntries * 16));
   JA_CUDA(cudaHostAlloc(&c->h_rowvals, kRowSeqOffset + 64, cudaHostAllocMapped));
   memset(c->h_rowvals, 0, kRowSeqOffset + 64);
   JA_CUDA(cudaHostGetDevicePointer(&c->d_rowvals, c->h_rowvals, 0));
@@ -115,6 +120,8 @@ void ja_shutdown(ja_ctx* c) {
   cudaFreeHost(c->h_rowvals);
   cudaFreeHost(c->h_mail);
   cudaFree(c->d_mail_dev);
+  cudaFreeHost(c->h_rrmail);
+  cudaFree(c->d_rrrelay);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;

@@ -70,6 +70,15 @@ struct ja_ctx {
   uint32_t ahead_tag = 0;
   unsigned int* ahead_ticket = nullptr;   // relay-election word of the entry (behind the twins in d_mail_dev)
   uint32_t ahead_use = 0;
+  // challenge channel of the round-resident kernels (persist_kernels.cuh): ring of kRrEntries 16-byte entries in host-mapped
+  // memory (a call takes one entry per round, zeroed before its launch) + device-memory twins (block 0 relays into them)
+  void* h_rrmail = nullptr;
+  void* d_rrmail = nullptr;
+  void* d_rrrelay = nullptr;
+  uint32_t rr_off = 0;
+  // A round-resident kernel occupies the stream until its last round: a call may run ONE of them (its only device-backed
+  // instance, or the RaVirtual + Booleanity pair of an RA one-hot check); set per call by the sumcheck driver
+  bool rr_call_ok = false, rr_call_pair = false;
   // flat host-mapped value array of the batched opening reduction (kMaxRowVals Fr + a sequence word at kRowSeqOffset)
   void* h_rowvals = nullptr;
   void* d_rowvals = nullptr;
@@ -117,6 +126,7 @@ static constexpr int kSlots = 128;
 static constexpr size_t kSlotBytes = 2048, kSlotSeqOffset = 1024;
 static constexpr size_t kMaxRowVals = 8192, kRowSeqOffset = kMaxRowVals * 32;
 static constexpr uint32_t kMailEntries = 64;
+static constexpr uint32_t kRrEntries = 4096;
 
 struct ja_poly {
   size_t len = 0;

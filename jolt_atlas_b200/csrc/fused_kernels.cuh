@@ -99,6 +99,29 @@ JA_DEV bool mail_wait(Challenge& r, const MailRef& m) {
   return (v.w >> 31) == 0;
 }
 
+// How a round body obtains the challenge it binds first.  MailWaiter: the pre-launched one-round kernels (mailbox above).
+// The round-resident kernels (persist_kernels.cuh) pass their own waiter; NoWait: the challenge is already in `r`.
+struct MailWaiter {
+  MailRef m;
+  JA_DEV bool operator()(Challenge& r) const { return mail_wait(r, m); }
+};
+struct NoWait {
+  JA_DEV bool operator()(Challenge&) const { return true; }
+};
+// Polynomial loads of a round body.  CG = false: ld.global.nc (the arrays are read-only for the one-round kernels);
+// CG = true: ld.global.cg - the round-resident kernels read arrays that earlier rounds of the SAME kernel wrote (possibly
+// from another SM), which .nc must not be used for and a stale L1 line must not serve.
+template <bool CG> JA_DEV Fr fr_ld(const Fr* p) {
+  if (CG) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+  }
+  return fp_load(p);
+}
+
 // The same collection with tagged publication (store_tagged) into the context's mapped value buffer: the host picks the claims
 // up as soon as they land, without a stream synchronisation at the end of every sumcheck call.
 struct CollectIdxArgs {
@@ -116,17 +139,17 @@ struct FusedPolys {
 };
 
 // (lo, hi) = elements (2g, 2g+1) of the array the round evaluates
-template <bool FUSED>
+template <bool FUSED, bool CG = false>
 JA_DEV void load_pair_l2h(const Fr* __restrict__ in, Fr* __restrict__ out, size_t g, const Challenge& r, Fr& lo, Fr& hi) {
   if (FUSED) {
-    const Fr a0 = fp_load(in + 4 * g), a1 = fp_load(in + 4 * g + 1), a2 = fp_load(in + 4 * g + 2), a3 = fp_load(in + 4 * g + 3);
+    const Fr a0 = fr_ld<CG>(in + 4 * g), a1 = fr_ld<CG>(in + 4 * g + 1), a2 = fr_ld<CG>(in + 4 * g + 2), a3 = fr_ld<CG>(in + 4 * g + 3);
     lo = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
     hi = fp_add<FrParams>(a2, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a3, a2), r));
     fp_store(out + 2 * g, lo);
     fp_store(out + 2 * g + 1, hi);
   } else {
-    lo = fp_load(in + 2 * g);
-    hi = fp_load(in + 2 * g + 1);
+    lo = fr_ld<CG>(in + 2 * g);
+    hi = fr_ld<CG>(in + 2 * g + 1);
   }
 }
 
@@ -134,19 +157,17 @@ JA_DEV void load_pair_l2h(const Fr* __restrict__ in, Fr* __restrict__ out, size_
 // KID: 0 ADD, 1 SUB, 2 MUL, 3 SQUARE, 6 IDENT (ids of include/jolt_atlas_b200.h), 7 BOOLEANITY phase 2
 //      (booleanity.rs:254-301: [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] over n_polys one-hot chunks).
 template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 || KID == 7) ? 2 : 1; };
+template <int KID> struct SPolys { static constexpr int N = KID == 7 ? 0 : ((KID == 3 || KID == 6) ? 1 : 2); };   // register-staged operand polynomials
 
-template <int KID, bool FUSED>
-__global__ void __launch_bounds__(kBlock, 2)
-k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
-          size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
-          size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */,
-          MailRef mail = MailRef{}) {
+// The body works on the pairs [g_begin, g_end) of block bx of nb; k_round_s (one round per launch) and the round-resident
+// kernels (persist_kernels.cuh: every round of a sumcheck in one launch) both run it.
+template <int KID, bool FUSED, class WAITER, bool CG>
+JA_DEV void round_s_body(const FusedPolys& P, int n_polys, Challenge r, const WAITER& waiter, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+                         int bits_in, size_t g_begin, size_t g_end, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter,
+                         const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off) {
   constexpr int NOUT = SOut<KID>::N;
-  constexpr int NP = KID == 7 ? 0 : ((KID == 3 || KID == 6) ? 1 : 2);      // polynomials with register-staged operands
+  constexpr int NP = SPolys<KID>::N;      // polynomials with register-staged operands
   const size_t mask_in = (size_t(1) << bits_in) - 1;
-  const size_t g_begin = (size_t)blockIdx.x * tiles_per_block * kBlock;
-  size_t g_end = g_begin + tiles_per_block * kBlock;
-  if (g_end > G) g_end = G;
   // The operands of the thread's first pair (and its eq weight) do not depend on the challenge: a pre-launched kernel
   // issues these loads BEFORE it waits on the mailbox, so their latency is spent while the host is still hashing.
   Fr a[NP > 0 ? NP : 1][4];
@@ -159,14 +180,14 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       for (int q = 0; q < NP; q++) {
         if (FUSED) {
           const Fr* __restrict__ z = P.in[q] + 4 * g;
-          a[q][0] = fp_load(z); a[q][1] = fp_load(z + 1); a[q][2] = fp_load(z + 2); a[q][3] = fp_load(z + 3);
+          a[q][0] = fr_ld<CG>(z); a[q][1] = fr_ld<CG>(z + 1); a[q][2] = fr_ld<CG>(z + 2); a[q][3] = fr_ld<CG>(z + 3);
         } else {
-          a[q][0] = fp_load(P.in[q] + 2 * g); a[q][1] = fp_load(P.in[q] + 2 * g + 1);
+          a[q][0] = fr_ld<CG>(P.in[q] + 2 * g); a[q][1] = fr_ld<CG>(P.in[q] + 2 * g + 1);
         }
       }
     }
   }
-  if (FUSED && !mail_wait(r, mail)) return;
+  if (FUSED && !waiter(r)) return;
   Fr outer[NOUT], inner[NOUT];
 #pragma unroll
   for (int k = 0; k < NOUT; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
@@ -192,9 +213,9 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       for (int q = 0; q < NP; q++) {
         if (FUSED) {
           const Fr* __restrict__ z = P.in[q] + 4 * g;
-          a[q][0] = fp_load(z); a[q][1] = fp_load(z + 1); a[q][2] = fp_load(z + 2); a[q][3] = fp_load(z + 3);
+          a[q][0] = fr_ld<CG>(z); a[q][1] = fr_ld<CG>(z + 1); a[q][2] = fr_ld<CG>(z + 2); a[q][3] = fr_ld<CG>(z + 3);
         } else {
-          a[q][0] = fp_load(P.in[q] + 2 * g); a[q][1] = fp_load(P.in[q] + 2 * g + 1);
+          a[q][0] = fr_ld<CG>(P.in[q] + 2 * g); a[q][1] = fr_ld<CG>(P.in[q] + 2 * g + 1);
         }
       }
     }
@@ -203,7 +224,7 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
       v[0] = fp_zero<FrParams>(); v[1] = fp_zero<FrParams>();
       for (int q = 0; q < n_polys; q++) {
         Fr h0, h1;
-        load_pair_l2h<FUSED>(P.in[q], P.out[q], g, r, h0, h1);
+        load_pair_l2h<FUSED, CG>(P.in[q], P.out[q], g, r, h0, h1);
         const Fr gm = fp_load(gammas + q);
         const Fr b = fp_sub<FrParams>(h1, h0);
         v[0] = fp_add<FrParams>(v[0], fp_mul<FrParams>(fp_mul<FrParams>(gm, h0), fp_sub<FrParams>(h0, fp_one<FrParams>())));
@@ -235,7 +256,21 @@ k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, 
 #pragma unroll
     for (int k = 0; k < NOUT; k++) outer[k] = fp_add<FrParams>(outer[k], fp_mul<FrParams>(eo, inner[k]));
   }
-  grid_sum_ex<NOUT>(outer, partials, counter, pub.vals, blockIdx.x, gridDim.x, pub.value);
+  grid_sum_ex<NOUT>(outer, partials, counter, pub.vals, bx, nb, pub.value);
+}
+
+
+template <int KID, bool FUSED>
+__global__ void __launch_bounds__(kBlock, 2)
+k_round_s(FusedPolys P, int n_polys, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in,
+          size_t G, size_t tiles_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
+          size_t g_off = 0 /* first global pair of this GPU's hypercube slice (multi-GPU); eq tables are indexed globally */,
+          MailRef mail = MailRef{}) {
+  const size_t g_begin = (size_t)blockIdx.x * tiles_per_block * kBlock;
+  size_t g_end = g_begin + tiles_per_block * kBlock;
+  if (g_end > G) g_end = G;
+  round_s_body<KID, FUSED, MailWaiter, false>(P, n_polys, r, MailWaiter{mail}, e_out, e_in, bits_in, g_begin, g_end, gammas, partials, counter, pub,
+                                              blockIdx.x, gridDim.x, g_off);
 }
 
 // ---- product of d <= 16 linear factors, warp-transposed (see k_round_eval_prod_t), with the fused bind -------------
@@ -273,9 +308,9 @@ JA_DEV void prod_tail(Fr tot /* valid in threads < L */, Fr* partials, unsigned 
   if (threadIdx.x < L) store_tagged(pub.vals, threadIdx.x, tot, pub.value);
 }
 
-template <int L, bool SAME, bool FUSED, int BLOCK = kBlock>
-JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
-                            int bits_in, size_t G, size_t pairs_per_block, Fr* partials /* [nb][L] */, unsigned int* counter,
+template <int L, bool SAME, bool FUSED, int BLOCK = kBlock, class WAITER = MailWaiter, bool CG = false>
+JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const WAITER& waiter, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+                            int bits_in, size_t g_begin, size_t g_end, Fr* partials /* [nb][L] */, unsigned int* counter,
                             const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off = 0) {
   constexpr int GPB = BLOCK / L;
   const int li = threadIdx.x & (L - 1);
@@ -286,17 +321,14 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const MailR
   const Fr* __restrict__ zin = P.in[pi];
   Fr* __restrict__ zout = P.out[pi];
   const size_t mask_in = (size_t(1) << bits_in) - 1;
-  const size_t g_begin = (size_t)bx * pairs_per_block;
-  size_t g_end = g_begin + pairs_per_block;
-  if (g_end > G) g_end = G;
   Fr a0, a1, a2, a3;
   {
     const size_t g = g_begin + group;
     const size_t gl = g < g_end ? g : g_begin;
-    if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-    else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
+    if (FUSED) { a0 = fr_ld<CG>(zin + 4 * gl); a1 = fr_ld<CG>(zin + 4 * gl + 1); a2 = fr_ld<CG>(zin + 4 * gl + 2); a3 = fr_ld<CG>(zin + 4 * gl + 3); }
+    else { a0 = fr_ld<CG>(zin + 2 * gl); a1 = fr_ld<CG>(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
   }
-  if (FUSED && !mail_wait(r, mail)) return;
+  if (FUSED && !waiter(r)) return;
   Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
   size_t cur_xout = ~size_t(0);
   for (size_t base = g_begin; base < g_end; base += GPB) {
@@ -304,8 +336,8 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const MailR
     const bool active = g < g_end;
     const size_t gl = active ? g : g_begin;
     if (base != g_begin) {
-      if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-      else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); }
+      if (FUSED) { a0 = fr_ld<CG>(zin + 4 * gl); a1 = fr_ld<CG>(zin + 4 * gl + 1); a2 = fr_ld<CG>(zin + 4 * gl + 2); a3 = fr_ld<CG>(zin + 4 * gl + 3); }
+      else { a0 = fr_ld<CG>(zin + 2 * gl); a1 = fr_ld<CG>(zin + 2 * gl + 1); }
     }
     Fr p0, dp;
     if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
@@ -355,29 +387,26 @@ constexpr size_t kBigWideMinPairs = 2048;  // JA_BIGWIDE=1 only: the 64-threads-
 // sub-grids of the large-slab form: product blocks (3 of the 4 resident blocks per SM) and booleanity blocks
 static inline __host__ __device__ size_t big_wide_ppb_prod(size_t G) { size_t p = (G + (size_t)kSMs * 3 - 1) / ((size_t)kSMs * 3); return (p + 1) & ~size_t(1); }
 static inline __host__ __device__ size_t big_wide_ppb_bool(size_t G) { size_t p = (G + (size_t)kSMs - 1) / (size_t)kSMs; return (p + 7) & ~size_t(7); }
-template <bool FUSED>
-JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out,
-                                   const Fr* __restrict__ e_in, int bits_in, size_t G, size_t pairs_per_block /* multiple of 2 */,
+template <bool FUSED, int BLOCK = kWideBlock, class WAITER = MailWaiter, bool CG = false>
+JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, const WAITER& waiter, const Fr* __restrict__ e_out,
+                                   const Fr* __restrict__ e_in, int bits_in, size_t g_begin, size_t g_end,
                                    Fr* partials /* [nb][16] */, unsigned int* counter,
                                    const Publish& pub, unsigned int bx, unsigned int nb, size_t g_off = 0) {
-  constexpr int L = 16, PPB = kWideBlock / 64;
+  constexpr int L = 16, PPB = BLOCK / 64;
   const int t = threadIdx.x & 63, li = t & 15, s = t >> 4, group = threadIdx.x >> 6;
   const bool pad = li >= d;
   const bool hi8 = (li & 8) != 0, hi4 = (li & 4) != 0;
   const size_t mask_in = (size_t(1) << bits_in) - 1;
-  const size_t g_begin = (size_t)bx * pairs_per_block;
-  size_t g_end = g_begin + pairs_per_block;
-  if (g_end > G) g_end = G;
   const Fr* __restrict__ zin = P.in[pad ? 0 : li];
   Fr* __restrict__ zout = P.out[pad ? 0 : li];
   Fr a0, a1, a2, a3;
   {
     const size_t g = g_begin + group;
     const size_t gl = g < g_end ? g : g_begin;
-    if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-    else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
+    if (FUSED) { a0 = fr_ld<CG>(zin + 4 * gl); a1 = fr_ld<CG>(zin + 4 * gl + 1); a2 = fr_ld<CG>(zin + 4 * gl + 2); a3 = fr_ld<CG>(zin + 4 * gl + 3); }
+    else { a0 = fr_ld<CG>(zin + 2 * gl); a1 = fr_ld<CG>(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
   }
-  if (FUSED && !mail_wait(r, mail)) return;
+  if (FUSED && !waiter(r)) return;
   Fr outer = fp_zero<FrParams>(), inner = fp_zero<FrParams>();
   size_t cur_xout = ~size_t(0);
   for (size_t base = g_begin; base < g_end; base += PPB) {      // uniform trip count: every lane joins the shuffles
@@ -385,8 +414,8 @@ JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, cons
     const bool active = g < g_end;
     const size_t gl = active ? g : g_begin;
     if (base != g_begin) {
-      if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-      else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); }
+      if (FUSED) { a0 = fr_ld<CG>(zin + 4 * gl); a1 = fr_ld<CG>(zin + 4 * gl + 1); a2 = fr_ld<CG>(zin + 4 * gl + 2); a3 = fr_ld<CG>(zin + 4 * gl + 3); }
+      else { a0 = fr_ld<CG>(zin + 2 * gl); a1 = fr_ld<CG>(zin + 2 * gl + 1); }
     }
     Fr p0, dp;
     if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
@@ -433,7 +462,7 @@ JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, cons
 #pragma unroll
     for (int gp = 0; gp < PPB; gp++) tot = fp_add<FrParams>(tot, s_red[gp][threadIdx.x]);
   }
-  prod_tail<L, kWideBlock>(tot, partials, counter, pub, bx, nb);
+  prod_tail<L, BLOCK>(tot, partials, counter, pub, bx, nb);
 }
 
 template <int L, bool SAME, bool FUSED>
@@ -441,23 +470,27 @@ __global__ void __launch_bounds__(kBlock)
 k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0,
              MailRef mail = MailRef{}) {
-  round_prod_body<L, SAME, FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
+  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  const size_t g_end = g_begin + pairs_per_block < G ? g_begin + pairs_per_block : G;
+  round_prod_body<L, SAME, FUSED>(P, d, r, MailWaiter{mail}, e_out, e_in, bits_in, g_begin, g_end, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 template <bool FUSED>
 __global__ void __launch_bounds__(kWideBlock)
 k_round_prod16_wide(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
                     size_t pairs_per_block, Fr* partials /* [gridDim.x][16] */, unsigned int* counter, Publish pub, size_t g_off = 0,
                     MailRef mail = MailRef{}) {
-  round_prod16_wide_body<FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
+  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  const size_t g_end = g_begin + pairs_per_block < G ? g_begin + pairs_per_block : G;
+  round_prod16_wide_body<FUSED>(P, d, r, MailWaiter{mail}, e_out, e_in, bits_in, g_begin, g_end, partials, counter, pub, blockIdx.x, gridDim.x, g_off);
 }
 
 // ---- booleanity phase 2, lane-parallel (booleanity.rs:254-301) ---------------------------------------------------------
 // [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] per pair: a group of L = next_pow2(d) lanes owns one pair, lane i
 // loads polynomial i (with the fused bind), forms its two terms (4 products) and the group adds them up with shuffles —
 // d times more threads and d times shorter dependency chains than one thread looping over the d polynomials.
-template <int L, bool FUSED, int BLOCK = kBlock>
-JA_DEV void round_bool_body(const FusedPolys& P, int d, Challenge r, const MailRef& mail, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
-                            int bits_in, size_t G, size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials,
+template <int L, bool FUSED, int BLOCK = kBlock, class WAITER = MailWaiter, bool CG = false>
+JA_DEV void round_bool_body(const FusedPolys& P, int d, Challenge r, const WAITER& waiter, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in,
+                            int bits_in, size_t g_begin, size_t g_end, const Fr* __restrict__ gammas, Fr* partials,
                             unsigned int* counter, const Publish& pub, unsigned int bx, unsigned int nb) {
   constexpr int GPB = BLOCK / L;
   const int li = threadIdx.x & (L - 1);
@@ -467,17 +500,14 @@ JA_DEV void round_bool_body(const FusedPolys& P, int d, Challenge r, const MailR
   Fr* __restrict__ zout = P.out[pad ? 0 : li];
   const Fr gm = pad ? fp_zero<FrParams>() : fp_load(gammas + li);
   const size_t mask_in = (size_t(1) << bits_in) - 1;
-  const size_t g_begin = (size_t)bx * pairs_per_block;
-  size_t g_end = g_begin + pairs_per_block;
-  if (g_end > G) g_end = G;
   Fr a0, a1, a2, a3;
   {
     const size_t g = g_begin + group;
     const size_t gl = g < g_end ? g : g_begin;
-    if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-    else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
+    if (FUSED) { a0 = fr_ld<CG>(zin + 4 * gl); a1 = fr_ld<CG>(zin + 4 * gl + 1); a2 = fr_ld<CG>(zin + 4 * gl + 2); a3 = fr_ld<CG>(zin + 4 * gl + 3); }
+    else { a0 = fr_ld<CG>(zin + 2 * gl); a1 = fr_ld<CG>(zin + 2 * gl + 1); a2 = a0; a3 = a1; }
   }
-  if (FUSED && !mail_wait(r, mail)) return;
+  if (FUSED && !waiter(r)) return;
   Fr outer[2], inner[2];
 #pragma unroll
   for (int k = 0; k < 2; k++) { outer[k] = fp_zero<FrParams>(); inner[k] = fp_zero<FrParams>(); }
@@ -487,8 +517,8 @@ JA_DEV void round_bool_body(const FusedPolys& P, int d, Challenge r, const MailR
     const bool active = g < g_end;
     const size_t gl = active ? g : g_begin;
     if (base != g_begin) {
-      if (FUSED) { a0 = fp_load(zin + 4 * gl); a1 = fp_load(zin + 4 * gl + 1); a2 = fp_load(zin + 4 * gl + 2); a3 = fp_load(zin + 4 * gl + 3); }
-      else { a0 = fp_load(zin + 2 * gl); a1 = fp_load(zin + 2 * gl + 1); }
+      if (FUSED) { a0 = fr_ld<CG>(zin + 4 * gl); a1 = fr_ld<CG>(zin + 4 * gl + 1); a2 = fr_ld<CG>(zin + 4 * gl + 2); a3 = fr_ld<CG>(zin + 4 * gl + 3); }
+      else { a0 = fr_ld<CG>(zin + 2 * gl); a1 = fr_ld<CG>(zin + 2 * gl + 1); }
     }
     Fr v0 = fp_zero<FrParams>(), v1 = fp_zero<FrParams>();
     if (!pad) {
@@ -538,7 +568,9 @@ __global__ void __launch_bounds__(kBlock)
 k_round_bool(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, const Fr* __restrict__ gammas, Fr* partials, unsigned int* counter, Publish pub,
              MailRef mail = MailRef{}) {
-  round_bool_body<L, FUSED>(P, d, r, mail, e_out, e_in, bits_in, G, pairs_per_block, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
+  const size_t g_begin = (size_t)blockIdx.x * pairs_per_block;
+  const size_t g_end = g_begin + pairs_per_block < G ? g_begin + pairs_per_block : G;
+  round_bool_body<L, FUSED>(P, d, r, MailWaiter{mail}, e_out, e_in, bits_in, g_begin, g_end, gammas, partials, counter, pub, blockIdx.x, gridDim.x);
 }
 
 // ---- RA one-hot checks: RaVirtual (product of d) and Booleanity phase 2 of the same batch in ONE launch -------------------
@@ -560,44 +592,49 @@ struct PairArgs {
 template <int L, bool FUSED, int BLOCK = kBlock, bool WIDE = false>
 __global__ void __launch_bounds__(BLOCK)
 k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{}) {
+  const MailWaiter waiter{mail};
   if (blockIdx.y == 0) {
     if (blockIdx.x >= A.nb) return;
+    const size_t g_begin = (size_t)blockIdx.x * (size_t)A.ppb;
+    const size_t g_end = g_begin + (size_t)A.ppb < (size_t)A.G ? g_begin + (size_t)A.ppb : (size_t)A.G;
     if constexpr (L == 16 && BLOCK == kWideBlock && WIDE)
-      round_prod16_wide_body<FUSED>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
+      round_prod16_wide_body<FUSED>(A.P, A.d, r, waiter, A.e_out, A.e_in, A.bits_in, g_begin, g_end, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
     else
-      round_prod_body<L, false, FUSED, BLOCK>(A.P, A.d, r, mail, A.e_out, A.e_in, A.bits_in, (size_t)A.G, (size_t)A.ppb, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
+      round_prod_body<L, false, FUSED, BLOCK>(A.P, A.d, r, waiter, A.e_out, A.e_in, A.bits_in, g_begin, g_end, A.partials, A.counter, A.pub, blockIdx.x, A.nb);
   } else {
     if (blockIdx.x >= B.nb) return;
-    round_bool_body<L, FUSED, BLOCK>(B.P, B.d, r, mail, B.e_out, B.e_in, B.bits_in, (size_t)B.G, (size_t)B.ppb, B.gammas, B.partials, B.counter, B.pub, blockIdx.x, B.nb);
+    const size_t g_begin = (size_t)blockIdx.x * (size_t)B.ppb;
+    const size_t g_end = g_begin + (size_t)B.ppb < (size_t)B.G ? g_begin + (size_t)B.ppb : (size_t)B.G;
+    round_bool_body<L, FUSED, BLOCK>(B.P, B.d, r, waiter, B.e_out, B.e_in, B.bits_in, g_begin, g_end, B.gammas, B.partials, B.counter, B.pub, blockIdx.x, B.nb);
   }
 }
 
 // ---- family D (plain products at X in {0,2,3}, HighToLow), fused bind in place ------------------------------------------
-template <int NPOLY, bool FUSED>
-__global__ void __launch_bounds__(kBlock)
-k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array: it has 2G entries */, Fr* partials,
-            unsigned int* counter, Publish pub, MailRef mail = MailRef{}) {
-  if (FUSED && !mail_wait(r, mail)) return;
+template <int NPOLY, bool FUSED, class WAITER, bool CG>
+JA_DEV void round_dot_body(const FusedPolys& P, Challenge r, const WAITER& waiter, size_t G /* pairs of the evaluated array: it has 2G entries */,
+                           Fr* partials, unsigned int* counter, const Publish& pub, unsigned int bx, unsigned int nb) {
+  if (FUSED && !waiter(r)) return;
   constexpr int NOUT = NPOLY;
   Fr acc[NOUT];
 #pragma unroll
   for (int k = 0; k < NOUT; k++) acc[k] = fp_zero<FrParams>();
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride) {
+  const size_t stride = (size_t)nb * blockDim.x;
+  for (size_t i = (size_t)bx * blockDim.x + threadIdx.x; i < G; i += stride) {
     Fr prod[NOUT];
 #pragma unroll
     for (int q = 0; q < NPOLY; q++) {
       Fr a, b;
       if (FUSED) {
         Fr* z = P.out[q];      // in place
-        const Fr a0 = fp_load_rw(z + i), a1 = fp_load_rw(z + i + 2 * G), b0 = fp_load_rw(z + i + G), b1 = fp_load_rw(z + i + 3 * G);
+        const Fr a0 = CG ? fr_ld<true>(z + i) : fp_load_rw(z + i), a1 = CG ? fr_ld<true>(z + i + 2 * G) : fp_load_rw(z + i + 2 * G),
+                 b0 = CG ? fr_ld<true>(z + i + G) : fp_load_rw(z + i + G), b1 = CG ? fr_ld<true>(z + i + 3 * G) : fp_load_rw(z + i + 3 * G);
         a = fp_add<FrParams>(a0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(a1, a0), r));
         b = fp_add<FrParams>(b0, fp_mul_challenge<FrParams>(fp_sub<FrParams>(b1, b0), r));
         fp_store(z + i, a);
         fp_store(z + i + G, b);
       } else {
-        a = fp_load(P.in[q] + i);
-        b = fp_load(P.in[q] + i + G);
+        a = fr_ld<CG>(P.in[q] + i);
+        b = fr_ld<CG>(P.in[q] + i + G);
       }
       const Fr m = fp_sub<FrParams>(b, a);
       const Fr e = fp_add<FrParams>(b, m);   // X = 2
@@ -610,7 +647,12 @@ k_round_dot(FusedPolys P, Challenge r, size_t G /* pairs of the evaluated array:
 #pragma unroll
     for (int k = 0; k < NOUT; k++) acc[k] = fp_add<FrParams>(acc[k], prod[k]);
   }
-  grid_sum_ex<NOUT>(acc, partials, counter, pub.vals, blockIdx.x, gridDim.x, pub.value);
+  grid_sum_ex<NOUT>(acc, partials, counter, pub.vals, bx, nb, pub.value);
+}
+template <int NPOLY, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_round_dot(FusedPolys P, Challenge r, size_t G, Fr* partials, unsigned int* counter, Publish pub, MailRef mail = MailRef{}) {
+  round_dot_body<NPOLY, FUSED, MailWaiter, false>(P, r, MailWaiter{mail}, G, partials, counter, pub, blockIdx.x, gridDim.x);
 }
 
 // ---- opening reduction, HighToLow (opening_reduction.rs:355-403 dense, :630-673 one-hot cycle rounds) --------------------

@@ -22,6 +22,7 @@
 
 #include "common.hpp"
 #include "fused_kernels.cuh"
+#include "persist_kernels.cuh"
 #include "tma_round.cuh"
 #include "sumcheck_host.hpp"
 #include "transcript_host.hpp"
@@ -200,6 +201,66 @@ int32_t wait_slot_tagged(ja_ctx* c, const Slot& s, size_t n, uint64_t* out) {
   return wait_tagged(c, s.host_vals, s.pub.value, n, out, "sumcheck round kernel");
 }
 
+// ---- round-resident kernels (persist_kernels.cuh): host side of the per-call challenge channel ---------------------------------
+// JA_NO_PERSIST=1 keeps every round on the per-round kernels (tests compare the two paths); tool injection / blocking launches
+// do the same (a kernel that waits for the host cannot run under a tool that serialises or replays launches).
+bool persist_allowed() { return ahead_allowed() && getenv("JA_NO_PERSIST") == nullptr; }
+constexpr size_t kRrMaxLenS = size_t(1) << 16;      // family S: longer arrays start on the per-round kernels (TMA-staged from 2^17) and hand over
+constexpr size_t kRrMaxLenDot = size_t(1) << 12;    // one block
+constexpr size_t kRrMaxLenPair = size_t(1) << 15;   // RaVirtual + Booleanity pair
+struct PersistGroup {
+  volatile uint32_t* h_entries = nullptr;           // host view of this call's mailbox entries (one per round)
+  const uint4* d_entries = nullptr;
+  uint4* d_relay = nullptr;
+  int rounds = 0, posted = 0;
+  unsigned int tag0 = 0;                            // round i publishes with tag0 + i
+  int32_t reserve(ja_ctx* c, int n_rounds) {
+    JA_REQUIRE(n_rounds >= 1 && n_rounds <= kRrMaxRounds, "sumcheck: round-resident kernel: bad round count");
+    rounds = n_rounds;
+    if (c->rr_off + (uint32_t)rounds > kRrEntries) c->rr_off = 0;
+    const uint32_t off = c->rr_off;
+    c->rr_off += (uint32_t)rounds;
+    volatile uint32_t* e = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<char*>(c->h_rrmail) + 16 * (size_t)off);
+    for (int i = 0; i < 4 * rounds; i++) e[i] = 0;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    d_entries = reinterpret_cast<const uint4*>(c->d_rrmail) + off;
+    d_relay = reinterpret_cast<uint4*>(c->d_rrrelay) + off;
+    JA_CUDA(cudaMemsetAsync(d_relay, 0, 16 * (size_t)rounds, c->stream));
+    if (c->seq > 0xffffff00u) c->seq = 0;            // a call's tags are consecutive and never 0
+    tag0 = c->seq + 1;
+    c->seq += (unsigned int)rounds + 2;               // one tag per round and one for the final claims (per instance of a pair)
+    h_entries = e;
+    return JA_OK;
+  }
+  void post(size_t i, const uint64_t ch[4]) {
+    if (!h_entries || i >= (size_t)rounds || (int)i < posted) return;
+    const Challenge cc = to_challenge(ch);
+    volatile uint32_t* e = h_entries + 4 * i;
+    e[0] = cc.c[0]; e[1] = cc.c[1]; e[2] = cc.c[2];
+    __atomic_thread_fence(__ATOMIC_RELEASE);
+    e[3] = (cc.c[3] & 0x1fffffffu) | 0x20000000u;    // bit 29: valid
+    posted = (int)i + 1;
+  }
+  ~PersistGroup() {                                  // error paths: the kernel must never be left waiting
+    if (!h_entries) return;
+    for (int i = posted; i < rounds; i++) { __atomic_thread_fence(__ATOMIC_RELEASE); h_entries[4 * i + 3] = 0x80000000u; }
+  }
+};
+static inline RrEq rr_eq_state(const ja_spliteq* e) {
+  RrEq q;
+  q.out_levels = e->out_levels; q.in_levels = e->in_levels;
+  q.out_len = e->out_len; q.in_len = e->in_len; q.ci = e->current_index; q.m = e->m;
+  return q;
+}
+template <class ARGS>
+static inline int32_t rr_launch(ja_ctx* c, const void* kernel, unsigned int grid, ARGS& args) {
+  void* params[] = {&args};
+  cudaError_t e = cudaSuccess;
+  JA_LAUNCH(c, KC_SUMCHECK_FUSED, e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), params, 0, c->stream));
+  if (e != cudaSuccess) return fail(JA_ERR_CUDA, std::string("round-resident kernel launch: ") + cudaGetErrorString(e));
+  return JA_OK;
+}
+
 // ---- GruenSplitEqPolynomial on the host for K-entry address rounds (split_eq_poly.rs:86-145,331-372; LowToHigh) ----
 struct HostEq {
   std::vector<FrH> w;
@@ -259,6 +320,9 @@ struct Inst {
   // and receive its challenge through the context's mailbox.  can_ahead: this instance's round `next` may be enqueued
   // that way (host-only instances: always).  ahead_begin / ahead_end bracket the early launch (state as if the missing
   // challenge had been ingested, then back); ahead_commit runs at the top of the next iteration instead of launch().
+  // the round's challenge, right after the transcript squeeze (round-resident kernels take it from their mailbox)
+  virtual void post_challenge(const uint64_t* /*ch*/, size_t /*local round*/) {}
+  virtual void abort_persist() {}          // error paths: release a round-resident kernel that is still waiting for challenges
   virtual bool can_ahead(size_t /*next local round*/) { return false; }
   virtual int32_t ahead_begin(ja_ctx*) { return JA_OK; }
   virtual void ahead_end(ja_ctx*) {}
@@ -302,12 +366,20 @@ struct DevInst : Inst {
   // multi-GPU: the polynomials are this rank's contiguous hypercube slices (ja_set_sumcheck_shard)
   bool sharded = false, round_sharded = false;
   uint32_t sc_rank = 0, sc_world = 1;
+  // round-resident kernel (persist_kernels.cuh) running the remaining rounds of this instance
+  std::shared_ptr<PersistGroup> pg;
+  size_t pg_round0 = ~size_t(0);    // local round of the kernel's first round
+  bool pg_flip = false;             // the final claims end up in the OTHER ping-pong buffer
+  unsigned int pg_tag_off = 0;      // this instance's tag range inside the group's (pairs: product first, booleanity second)
+  bool c_rr_ok = false;             // the call's shape allows a round-resident kernel (ja_ctx::rr_call_ok at set-up) for its one device instance
+  bool c_rr_pair = false;           // ... for the RaVirtual + Booleanity pair
 
   int32_t setup(ja_ctx* c) {
     const size_t len = polys[0]->len;
     for (ja_poly* p : polys) JA_REQUIRE(p && p->len == len, "sumcheck: polynomials of one instance must have equal length");
     JA_REQUIRE(len >= 2 && is_pow2(len), "sumcheck: polynomial length must be a power of two >= 2");
     rounds = (size_t)log2z(len);
+    c_rr_ok = c->rr_call_ok; c_rr_pair = c->rr_call_pair;
     switch (kind) {
       case JA_EVAL_ADD: case JA_EVAL_SUB: n_out = 1; JA_REQUIRE(polys.size() == 2, "sumcheck: ADD/SUB take two polynomials"); fusable = true; break;
       case JA_EVAL_IDENT: n_out = 1; JA_REQUIRE(polys.size() == 1, "sumcheck: IDENT takes one polynomial"); fusable = true; break;
@@ -391,7 +463,7 @@ struct DevInst : Inst {
     }
   }
   bool pairable() const {
-    return !sharded && fusable && polys.size() >= 2 && polys.size() <= 16 && (kind == JA_EVAL_PROD || kind == 7);
+    return !pg && !sharded && fusable && polys.size() >= 2 && polys.size() <= 16 && (kind == JA_EVAL_PROD || kind == 7);
   }
   // this instance's half of a paired launch (k_round_prod_bool): slot armed, buffers ready, state advanced
   int32_t prepare_pair(ja_ctx* c, PairArgs* a, Prep* pr, int scratch_half) {
@@ -465,6 +537,12 @@ struct DevInst : Inst {
 
   bool can_ahead(size_t next) override {
     if (!fusable || sharded || next < 1 || next >= rounds) return false;
+    {
+      const size_t next_len = (pending ? polys[0]->len / 2 : polys[0]->len) / 2;
+      if (pg || persist_ok(next_len)) return false;                    // that round runs in (or starts) a round-resident kernel
+      if ((kind == JA_EVAL_PROD || kind == 7) && c_rr_pair && !sharded && polys.size() <= 16 && next_len >= 2 && next_len <= kRrMaxLenPair &&
+          persist_allowed()) return false;                             // ... the pair's
+    }
     switch (kind) {
       case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_MUL: case JA_EVAL_SQUARE: case JA_EVAL_IDENT: case 7:
       case JA_EVAL_PROD: case JA_EVAL_POW: case JA_EVAL_DOT2: case JA_EVAL_DOT3: break;
@@ -492,6 +570,96 @@ struct DevInst : Inst {
     ahead_consumed = true;
   }
   void ahead_commit() override { slot = slot_next; }
+
+  // ---- round-resident kernel: the remaining rounds of this instance in ONE launch (persist_kernels.cuh) ------------------------------
+  // len_now = length of the arrays the next round evaluates
+  bool persist_ok(size_t len_now) const {
+    if (!fusable || sharded || len_now < 2 || !c_rr_ok || !persist_allowed()) return false;
+    switch (kind) {
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_MUL: case JA_EVAL_SQUARE: case JA_EVAL_IDENT: return eq != nullptr && len_now <= kRrMaxLenS;
+      case JA_EVAL_DOT2: case JA_EVAL_DOT3: return len_now <= kRrMaxLenDot;
+      default: return false;
+    }
+  }
+  void post_challenge(const uint64_t* ch, size_t rnd) override { if (pg && rnd >= pg_round0) pg->post(rnd - pg_round0, ch); }
+  void abort_persist() override { pg.reset(); }
+  void arm_pg_slot(ja_ctx* c, size_t rnd) {
+    if (pg_round0 == ~size_t(0)) pg_round0 = rnd;
+    char* h = reinterpret_cast<char*>(c->h_mapped) + (size_t)slot_id * kSlotBytes;
+    slot = Slot();
+    slot.host_vals = reinterpret_cast<const uint64_t*>(h);
+    slot.pub.value = pg->tag0 + pg_tag_off + (unsigned int)(rnd - pg_round0);
+    slot.armed = true;
+    legacy = false; round_sharded = false;
+  }
+  // shared by the single-instance and the pair start: the other ping-pong buffer of every polynomial, common arguments
+  int32_t persist_prepare(ja_ctx* c, RrCommon* cm, std::shared_ptr<PersistGroup> g, Fr* (*bufs)[2]) {
+    const size_t len_in = polys[0]->len;
+    const size_t len_now = pending ? len_in / 2 : len_in;
+    const int nr = log2z(len_now);
+    cm->mail_host = g->d_entries; cm->mail_relay = g->d_relay; cm->rounds = nr;
+    cm->first_fused = pending ? 1 : 0; cm->r0 = to_challenge(pend_ch); cm->n_first = len_in;
+    for (size_t q = 0; q < polys.size(); q++) {
+      ja_poly* p = polys[q];
+      const int nxt = 1 - p->cur;
+      if (order == JA_LOW_TO_HIGH && p->cap[nxt] < len_in / 2) {
+        dev_free(c, p->buf[nxt]);
+        p->buf[nxt] = nullptr; p->cap[nxt] = 0;
+        int32_t st = dev_alloc(c, (len_in / 2) * sizeof(Fr), (void**)&p->buf[nxt]);
+        if (st) return st;
+        p->cap[nxt] = len_in / 2;
+      }
+      bufs[q][0] = p->buf[p->cur]; bufs[q][1] = order == JA_LOW_TO_HIGH ? p->buf[nxt] : p->buf[p->cur];
+    }
+    // LowToHigh: the array moves to the other buffer with every fused round, and once more with the final bind
+    const int fused_rounds = nr - (pending ? 0 : 1);
+    pg_flip = order == JA_LOW_TO_HIGH && ((fused_rounds + 1) & 1);
+    pg = g;
+    pg_round0 = ~size_t(0);
+    pending = false;
+    return JA_OK;
+  }
+  int32_t start_persist(ja_ctx* c) {
+    const size_t len_in = polys[0]->len;
+    const size_t len_now = pending ? len_in / 2 : len_in;
+    const int nr = log2z(len_now);
+    auto g = std::make_shared<PersistGroup>();
+    int32_t st = g->reserve(c, nr);
+    if (st) return st;
+    Fr* slot_vals = reinterpret_cast<Fr*>(reinterpret_cast<char*>(c->d_mapped) + (size_t)slot_id * kSlotBytes);
+    const size_t G0 = len_now / 2;
+    if (kind == JA_EVAL_DOT2 || kind == JA_EVAL_DOT3) {
+      RrDotArgs a;
+      memset(&a, 0, sizeof(a));
+      Fr* bufs[3][2];
+      if ((st = persist_prepare(c, &a.c, g, bufs))) return st;
+      for (size_t q = 0; q < polys.size(); q++) a.buf[q] = bufs[q][0];
+      a.partials = c->d_partials; a.counter = c->d_counter; a.slot_vals = slot_vals; a.tag0 = g->tag0;
+      return rr_launch(c, kind == JA_EVAL_DOT2 ? (const void*)k_rr_dot<2> : (const void*)k_rr_dot<3>, 1, a);
+    }
+    JA_REQUIRE(eq && eq->order == order, "sumcheck: split-eq binding order does not match the round body");
+    JA_REQUIRE((size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1))) == G0, "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+    RrSArgs a;
+    memset(&a, 0, sizeof(a));
+    Fr* bufs[2][2];
+    if ((st = persist_prepare(c, &a.c, g, bufs))) return st;
+    a.np = (int)polys.size();
+    for (int q = 0; q < a.np; q++) { a.buf[q][0] = bufs[q][0]; a.buf[q][1] = bufs[q][1]; }
+    if (a.np == 1) { a.buf[1][0] = a.buf[0][0]; a.buf[1][1] = a.buf[0][1]; }
+    a.eq = rr_eq_state(eq);
+    a.partials = c->d_partials; a.counter = c->d_counter; a.slot_vals = slot_vals; a.tag0 = g->tag0;
+    a.split = RrSplit{(unsigned int)kBlock, 128u, 512u};   // one pair per thread and pass; 512 pairs or fewer on one block
+    size_t w0 = G0 <= a.split.single_max ? 1 : std::min<size_t>(a.split.wmax, (G0 + a.split.ppp - 1) / a.split.ppp);
+    const void* k = nullptr;
+    switch (kind) {
+      case JA_EVAL_ADD: k = (const void*)k_rr_s<0>; break;
+      case JA_EVAL_SUB: k = (const void*)k_rr_s<1>; break;
+      case JA_EVAL_MUL: k = (const void*)k_rr_s<2>; break;
+      case JA_EVAL_SQUARE: k = (const void*)k_rr_s<3>; break;
+      default: k = (const void*)k_rr_s<6>; break;
+    }
+    return rr_launch(c, k, (unsigned int)w0, a);
+  }
 
   // fused round kernel (bind pend_ch first when `pending`)
   int32_t launch_fused(ja_ctx* c) {
@@ -590,9 +758,11 @@ struct DevInst : Inst {
   bool small_round = false, wide_round = false;   // prepare_pair chose the small-slab variants of the paired kernel
   bool paired_this_round = false;    // the driver already launched this round's kernel together with a partner
   DevInst* pair_candidate(size_t) override { return pairable() ? this : nullptr; }
-  int32_t launch(ja_ctx* c, size_t) override {
+  int32_t launch(ja_ctx* c, size_t rnd) override {
     int32_t st;
     if (paired_this_round) { paired_this_round = false; return JA_OK; }
+    if (!pg && persist_ok(pending ? polys[0]->len / 2 : polys[0]->len) && (st = start_persist(c))) return st;
+    if (pg) { arm_pg_slot(c, rnd); return JA_OK; }
     if (sharded && (pending ? polys[0]->len / 2 : polys[0]->len) < 2 && (st = unshard(c))) return st;
     legacy = !fusable;
     round_sharded = sharded;
@@ -698,6 +868,7 @@ struct DevInst : Inst {
       const FrH r = host::from_limbs(ch);
       nclaim = host::add(qc0, host::mul(r, host::add(qc1, host::mul(r, qc2))));
     }
+    if (pg) return JA_OK;                                           // the round-resident kernel binds it
     if (ahead_consumed) { ahead_consumed = false; return JA_OK; }   // the pre-launched kernel of the next round binds this challenge
     if (fusable) { memcpy(pend_ch, ch, 32); pending = true; return JA_OK; }
     return ja_bind_many(c, polys.data(), polys.size(), ch, order);
@@ -705,6 +876,16 @@ struct DevInst : Inst {
 
   int32_t finalize(ja_ctx* c, uint64_t* staging, size_t* count) override {
     int32_t st;
+    if (pg) {
+      // the kernel's final bind left the claims in element 0 of every polynomial and published them into the instance's slot
+      JA_REQUIRE(pg->posted == pg->rounds, "sumcheck: round-resident kernel did not receive every challenge");
+      const char* h = reinterpret_cast<const char*>(c->h_mapped) + (size_t)slot_id * kSlotBytes;
+      if ((st = wait_tagged(c, h, pg->tag0 + pg_tag_off + (unsigned int)pg->rounds, polys.size(), staging, "round-resident sumcheck kernel (final claims)"))) return st;
+      for (ja_poly* p : polys) { if (pg_flip) p->cur = 1 - p->cur; p->len = 1; }
+      pg.reset();
+      *count = polys.size();
+      return JA_OK;
+    }
     if (pending) {
       if ((st = ja_bind_many(c, polys.data(), polys.size(), pend_ch, order))) return st;
       pending = false;
@@ -722,6 +903,60 @@ struct DevInst : Inst {
     if (d_gammas) { dev_free(c, d_gammas); d_gammas = nullptr; }
   }
 };
+
+// RaVirtual (product of d) + Booleanity phase 2 of one RA one-hot check: every remaining round of both in ONE launch (k_rr_pair)
+bool persist_pair_ok(const DevInst* pa, const DevInst* pb) {
+  if (!pa->c_rr_pair || !pb->c_rr_pair || !persist_allowed() || pa->pg || pb->pg || pa->sharded || pb->sharded || !pa->eq || !pb->eq) return false;
+  const size_t len_now = pa->pending ? pa->polys[0]->len / 2 : pa->polys[0]->len;
+  return len_now >= 2 && len_now <= kRrMaxLenPair && pa->polys.size() <= 16;
+}
+int32_t start_persist_pair(ja_ctx* c, DevInst* pa, DevInst* pb) {
+  const size_t len_in = pa->polys[0]->len;
+  const size_t len_now = pa->pending ? len_in / 2 : len_in;
+  const int nr = log2z(len_now);
+  const size_t G0 = len_now / 2;
+  const int d = (int)pa->polys.size();
+  int L = 2; while (L < d) L <<= 1;
+  JA_REQUIRE((size_t(1) << ((pa->eq->out_len - 1) + (pa->eq->in_len - 1))) == G0 && (size_t(1) << ((pb->eq->out_len - 1) + (pb->eq->in_len - 1))) == G0,
+             "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
+  auto g = std::make_shared<PersistGroup>();
+  int32_t st = g->reserve(c, 2 * nr);                 // two tag ranges: [tag0, tag0 + nr) product, [tag0 + nr, tag0 + 2 nr) booleanity
+  if (st) return st;
+  g->rounds = nr;                                     // ... but one mailbox entry per round
+  RrPairArgs a;
+  memset(&a, 0, sizeof(a));
+  RrCommon cmB;
+  Fr* bufA[16][2];
+  Fr* bufB[16][2];
+  if ((st = pa->persist_prepare(c, &a.c, g, bufA))) return st;
+  if ((st = pb->persist_prepare(c, &cmB, g, bufB))) return st;
+  // sub-grids: the product of 16 costs ~3x the booleanity body per pair, below that they are about even
+  const unsigned int ppp = (unsigned int)(kBlock / L);
+  const unsigned int wmax_a = L == 16 ? 111u : 74u, wmax_b = (unsigned int)kSMs - wmax_a;
+  a.split_a = RrSplit{ppp, wmax_a, ppp};
+  a.split_wide = RrSplit{(unsigned int)(kBlock / 64), wmax_a, (unsigned int)(kBlock / 64)};
+  a.split_b = RrSplit{ppp, wmax_b, ppp};
+  a.wide_max_pairs = (L == 16 && getenv("JA_NO_WIDE") == nullptr) ? (unsigned int)kWideMaxPairs : 0u;
+  a.d = d;
+  for (int q = 0; q < d; q++) { a.bufA[q][0] = bufA[q][0]; a.bufA[q][1] = bufA[q][1]; a.bufB[q][0] = bufB[q][0]; a.bufB[q][1] = bufB[q][1]; }
+  a.eqA = rr_eq_state(pa->eq); a.eqB = rr_eq_state(pb->eq);
+  a.gammas = pb->d_gammas;
+  a.partialsA = c->d_partials; a.counterA = c->d_counter;
+  a.partialsB = c->d_partials + (size_t)kMaxGrid * kMaxOut / 2; a.counterB = c->d_counter + 1;
+  a.slotA = reinterpret_cast<Fr*>(reinterpret_cast<char*>(c->d_mapped) + (size_t)pa->slot_id * kSlotBytes);
+  a.slotB = reinterpret_cast<Fr*>(reinterpret_cast<char*>(c->d_mapped) + (size_t)pb->slot_id * kSlotBytes);
+  a.tagA0 = g->tag0; a.tagB0 = g->tag0 + (unsigned int)nr + 1;
+  pa->pg_tag_off = 0; pb->pg_tag_off = (unsigned int)nr + 1;
+  pa->prod_lanes = L;
+  const bool wide0 = a.wide_max_pairs && G0 <= a.wide_max_pairs;
+  const RrSplit& sa = wide0 ? a.split_wide : a.split_a;
+  const size_t wa0 = G0 <= sa.single_max ? 1 : std::min<size_t>(sa.wmax, (G0 + sa.ppp - 1) / sa.ppp);
+  const size_t wb0 = G0 <= a.split_b.single_max ? 1 : std::min<size_t>(a.split_b.wmax, (G0 + a.split_b.ppp - 1) / a.split_b.ppp);
+  a.off_b = (unsigned int)wa0;
+  const size_t w0 = wa0 + wb0;
+  const void* k = L == 2 ? (const void*)k_rr_pair<2> : L == 4 ? (const void*)k_rr_pair<4> : L == 8 ? (const void*)k_rr_pair<8> : (const void*)k_rr_pair<16>;
+  return rr_launch(c, k, (unsigned int)w0, a);
+}
 
 // HammingWeightSumcheckProver over the K-entry G tables (hamming_weight.rs:60-160): log K rounds, degree 1, host only
 struct HammingHostInst : Inst {
@@ -775,6 +1010,8 @@ struct BooleanityInst : Inst {
   void ahead_end(ja_ctx* c) override { p2->ahead_end(c); }
   void ahead_commit() override { p2->ahead_commit(); }
   DevInst* pair_candidate(size_t round) override { return round >= log_k && p2 && p2->pairable() ? p2.get() : nullptr; }
+  void post_challenge(const uint64_t* ch, size_t round) override { if (round >= log_k && p2) p2->post_challenge(ch, round - log_k); }
+  void abort_persist() override { if (p2) p2->abort_persist(); }
   int32_t launch(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->launch(c, round - log_k); }
   int32_t prework(ja_ctx* c, size_t round) override { return round < log_k ? (int32_t)JA_OK : p2->prework(c, round - log_k); }
   int32_t message(ja_ctx* c, size_t round, const FrH& prev, Coeffs* uni) override {
@@ -1234,8 +1471,11 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
           if (cand->kind == JA_EVAL_PROD && !pa) pa = cand;
           else if (cand->kind == 7 && !pb) pb = cand;
         }
-        if (pa && pb && pa->polys.size() == pb->polys.size() && pa->polys[0]->len == pb->polys[0]->len && pa->pending == pb->pending &&
-            (!pa->pending || memcmp(pa->pend_ch, pb->pend_ch, 32) == 0)) {
+        const bool pair_ok = pa && pb && pa->polys.size() == pb->polys.size() && pa->polys[0]->len == pb->polys[0]->len && pa->pending == pb->pending &&
+                             (!pa->pending || memcmp(pa->pend_ch, pb->pend_ch, 32) == 0);
+        if (pair_ok && persist_pair_ok(pa, pb)) {
+          if ((st = start_persist_pair(c, pa, pb))) return st;          // the instances' launch() below only arm their slots
+        } else if (pair_ok) {
           PairArgs A, B;
           DevInst::Prep ra, rb;
           if ((st = pa->prepare_pair(c, &A, &ra, 0))) return st;
@@ -1373,6 +1613,8 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     uint64_t ch[4];
     t.challenge_scalar_optimized(ch);                                                      // :126 / :586
     if (mail.entry) mail.post(ch);                                                         // releases the pre-launched kernels of the next round
+    for (size_t k = 0; k < n; k++)                                                         // ... and the round-resident ones
+      if (remaining <= insts[k]->rounds) insts[k]->post_challenge(ch, round - (max_rounds - insts[k]->rounds));
     const FrH r = host::from_limbs(ch);
 #pragma omp parallel for schedule(static) num_threads(nth) if (nth > 1)
     for (long k = 0; k < (long)n; k++) claims[k] = host::evaluate(unis[k], r);             // :130-134 / :589
@@ -1452,6 +1694,18 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
     if (addrs.size() >= 2) st = ja_addr_ra_evals_many(c, addrs.data(), pts.data(), lts.data(), addrs.size(), outs.data());
     else for (auto& v : pre) v.clear();
   }
+  {
+    // shape of the call: one device-backed instance, or [PROD, (host-only ...), BOOLEANITY] (the RA one-hot checks)
+    size_t n_dev = 0, n_prod = 0, n_bool = 0, n_open = 0;
+    for (size_t k = 0; k < n; k++) {
+      const int kd = descs[k].kind;
+      if (kd == JA_INST_BOOLEANITY) n_bool++;
+      else if (kd == JA_INST_OPENING_ONEHOT) n_open++;
+      else if (kd != JA_INST_HAMMING_TABLES) { n_dev++; if (kd == JA_EVAL_PROD) n_prod++; }
+    }
+    c->rr_call_ok = n_open == 0 && n_dev == 1 && n_bool == 0;
+    c->rr_call_pair = n_open == 0 && n_dev == 1 && n_prod == 1 && n_bool == 1;
+  }
   for (size_t k = 0; k < n && !st; k++) st = build_instance(c, descs[k], &insts, pre[k].empty() ? nullptr : pre[k].data());
   int next_slot = 0;
   for (auto& i : insts) if (i->needs_slot()) i->slot_id = next_slot++;
@@ -1465,7 +1719,10 @@ int32_t run(ja_ctx* c, const ja_sc_instance* descs, size_t n, bool batched, uint
   const auto t_built = std::chrono::steady_clock::now();
   if (!st) st = prove_loop(c, insts, batched, t, max_coeffs, out_coeffs, out_ncoeffs, out_challenges, ob.groups.empty() ? nullptr : &ob);
   const auto t_proved = std::chrono::steady_clock::now();
-  if (st) cudaStreamSynchronize(c->stream);      // nothing of this call may still be in flight when the handles are released
+  if (st) {
+    for (auto& i : insts) if (i) i->abort_persist();
+    cudaStreamSynchronize(c->stream);      // nothing of this call may still be in flight when the handles are released
+  }
   for (auto& i : insts) if (i) i->release(c);
   ob.release(c);
   if (g_trace.on) {
