@@ -64,6 +64,12 @@ enum {
                            mles_product_sum.rs:61-129   n_out=d (d = n_polys, 2..32) */
   JA_EVAL_POW = 5,      /* same-MLE power (p0 + X dp)^d on {1..d-1,inf}; d passed in aux_u32; cube.rs:159 */
   JA_EVAL_IDENT = 6,    /* [p0]  ps_shout / identity-RC cycle rounds, opening reduction; n_out=1 */
+  JA_EVAL_IFF = 8,      /* [m0*a0+(1-m0)*b0, dm*da-dm*db]  polys (mask, a, b)          ops/iff.rs:189-216   n_out=2 */
+  JA_EVAL_DIV = 9,      /* [r0*q0+R0-l0, dr*dq]            polys (l, r, q, R)          ops/div.rs:329-347   n_out=2 */
+  JA_EVAL_RSQRT = 10,   /* [x0*quot0+dr0-S^3+gamma*(out0^2+sr0-quot0), dx*dquot+gamma*dout^2]  polys (x, quotient, output,
+                           div_remainder, sqrt_remainder), aux_fr = {gamma, S^3}       ops/rsqrt.rs:390-418 n_out=2 */
+  JA_EVAL_LIN3 = 11,    /* [tau*q0+r0-in0]  polys (input, quotient, remainder), aux_fr = {tau}
+                           neural_teleport/division.rs:231-246; ScalarConstDiv's [l0-R0] (ops/scalar_const_div.rs:227) is JA_EVAL_SUB  n_out=1 */
   JA_EVAL_DOT2 = 16,    /* [sum l(0)r(0), sum l(2)r(2)]             einsum/dot.rs:292-303   n_out=2 */
   JA_EVAL_DOT3 = 17,    /* [sum l r e at 0,2,3], three MLEs of equal length  dot.rs:330-350   n_out=3 */
   JA_EVAL_SUM1 = 18,    /* [sum_i gamma_i * sum_j p_i[2j]]  LowToHigh one eval  hamming_weight.rs:118-139 (aux = gammas) */

@@ -29,9 +29,10 @@ class BindingOrder:
 
 class EvalKernel:
     ADD, SUB, MUL, SQUARE, PROD, POW, IDENT = 0, 1, 2, 3, 4, 5, 6
+    IFF, DIV, RSQRT, LIN3 = 8, 9, 10, 11           # ops/iff.rs:189, ops/div.rs:329, ops/rsqrt.rs:390, neural_teleport/division.rs:231
     DOT2, DOT3, SUM1, SUMHI, OPEN = 16, 17, 18, 19, 20
-    N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 16: 2, 17: 3, 18: 1, 19: 1}
-    FAMILY_S = (0, 1, 2, 3, 4, 5, 6)
+    N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 8: 2, 9: 2, 10: 2, 11: 1, 16: 2, 17: 3, 18: 1, 19: 1}
+    FAMILY_S = (0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11)
 
 
 class _Addr(C.c_void_p):

@@ -555,7 +555,8 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
   for (size_t i = 0; i < n_polys; i++)
     JA_REQUIRE(polys[i] && polys[i]->len == len, "ja_round_eval: polynomial length mismatch");
   EvalPolys P;
-  for (size_t i = 0; i < 4; i++) P.p[i] = i < n_polys ? polys[i]->data() : nullptr;
+  for (size_t i = 0; i < 6; i++) P.p[i] = i < n_polys ? polys[i]->data() : nullptr;
+  P.aux = nullptr;
   const size_t G = len / 2;
   size_t want_out = 0, want_polys = 0;
   enum { FAM_S, FAM_D, FAM_PROD, FAM_SUM } fam = FAM_S;
@@ -564,6 +565,10 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
     case JA_EVAL_MUL: want_out = 2; want_polys = 2; break;
     case JA_EVAL_SQUARE: want_out = 2; want_polys = 1; break;
     case JA_EVAL_IDENT: want_out = 1; want_polys = 1; break;
+    case JA_EVAL_IFF: want_out = 2; want_polys = 3; break;
+    case JA_EVAL_DIV: want_out = 2; want_polys = 4; break;
+    case JA_EVAL_RSQRT: want_out = 2; want_polys = 5; JA_REQUIRE(aux_fr && n_aux == 2, "ja_round_eval: RSQRT takes aux_fr = {gamma, S^3}"); break;
+    case JA_EVAL_LIN3: want_out = 1; want_polys = 3; JA_REQUIRE(aux_fr && n_aux == 1, "ja_round_eval: LIN3 takes aux_fr = {tau}"); break;
     case JA_EVAL_PROD: want_out = n_polys; want_polys = n_polys; fam = FAM_PROD; break;
     case JA_EVAL_POW: want_out = aux_u32; want_polys = 1; fam = FAM_PROD; break;
     case JA_EVAL_DOT2: want_out = 2; want_polys = 2; fam = FAM_D; break;
@@ -592,6 +597,18 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
       case JA_EVAL_MUL: launch_s<2>(c, P, eq, G); break;
       case JA_EVAL_SQUARE: launch_s<3>(c, P, eq, G); break;
       case JA_EVAL_IDENT: launch_s<6>(c, P, eq, G); break;
+      case JA_EVAL_IFF: launch_s<8>(c, P, eq, G); break;
+      case JA_EVAL_DIV: launch_s<9>(c, P, eq, G); break;
+      case JA_EVAL_RSQRT: case JA_EVAL_LIN3: {
+        Fr* d_aux = nullptr;                            // the body's scalars travel through the staging ring; stream-ordered reuse of the buffer
+        int32_t ast = dev_alloc(c, n_aux * sizeof(Fr), (void**)&d_aux);
+        if (ast) return ast;
+        if ((ast = stage_h2d(c, d_aux, aux_fr, n_aux * 32))) { dev_free(c, d_aux); return ast; }
+        P.aux = d_aux;
+        if (kernel_id == JA_EVAL_RSQRT) launch_s<10>(c, P, eq, G); else launch_s<11>(c, P, eq, G);
+        dev_free(c, d_aux);
+        break;
+      }
     }
   } else if (fam == FAM_PROD) {
     const int d = kernel_id == JA_EVAL_POW ? (int)aux_u32 : (int)n_polys;
@@ -848,7 +865,7 @@ int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys
       if (which == 0) JA_LAUNCH(c, KC_BIND, k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
       else            JA_LAUNCH(c, KC_BIND, k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
     } else {
-      EvalPolys P; P.p[0] = src[0]; P.p[1] = src[1]; P.p[2] = P.p[3] = nullptr;
+      EvalPolys P; P.p[0] = src[0]; P.p[1] = src[1]; P.p[2] = P.p[3] = P.p[4] = P.p[5] = nullptr; P.aux = nullptr;
       if (which == 2) launch_s<2>(c, P, eq, half);
       else if (which == 4) launch_s<0>(c, P, eq, half);
       else {

@@ -156,8 +156,14 @@ JA_DEV void load_pair_l2h(const Fr* __restrict__ in, Fr* __restrict__ out, size_
 // ---- family S (split-eq weighted, LowToHigh) ----------------------------------------------------------------------
 // KID: 0 ADD, 1 SUB, 2 MUL, 3 SQUARE, 6 IDENT (ids of include/jolt_atlas_b200.h), 7 BOOLEANITY phase 2
 //      (booleanity.rs:254-301: [sum_i gamma_i h_i0 (h_i0 - 1), sum_i gamma_i (dh_i)^2] over n_polys one-hot chunks).
-template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 || KID == 7) ? 2 : 1; };
-template <int KID> struct SPolys { static constexpr int N = KID == 7 ? 0 : ((KID == 3 || KID == 6) ? 1 : 2); };   // register-staged operand polynomials
+//      8 IFF, 9 DIV, 10 RSQRT, 11 LIN3: the three-to-five-operand bodies of poly_kernels.cuh (SGen), operands bound polynomial by polynomial
+template <int KID> struct SOut { static constexpr int N = (KID == 2 || KID == 3 || KID == 7 || KID == 8 || KID == 9 || KID == 10) ? 2 : 1; };
+template <int KID> struct SPolys { static constexpr int N = KID >= 7 ? 0 : ((KID == 3 || KID == 6) ? 1 : 2); };   // register-staged operand polynomials
+template <int KID> struct SGenPolys { static constexpr int N = 1; };
+template <> struct SGenPolys<8> { static constexpr int N = 3; };
+template <> struct SGenPolys<9> { static constexpr int N = 4; };
+template <> struct SGenPolys<10> { static constexpr int N = 5; };
+template <> struct SGenPolys<11> { static constexpr int N = 3; };
 
 // The body works on the pairs [g_begin, g_end) of block bx of nb; k_round_s (one round per launch) and the round-resident
 // kernels (persist_kernels.cuh: every round of a sumcheck in one launch) both run it.
@@ -220,7 +226,13 @@ JA_DEV void round_s_body(const FusedPolys& P, int n_polys, Challenge r, const WA
       }
     }
     Fr v[NOUT];
-    if (KID == 7) {
+    if constexpr (KID >= 8) {
+      constexpr int NG = SGenPolys<KID>::N;
+      Fr lo[NG], hi[NG];
+#pragma unroll
+      for (int q = 0; q < NG; q++) load_pair_l2h<FUSED, CG>(P.in[q], P.out[q], g, r, lo[q], hi[q]);
+      SGen<KID>::eval(lo, hi, gammas, v);
+    } else if (KID == 7) {
       v[0] = fp_zero<FrParams>(); v[1] = fp_zero<FrParams>();
       for (int q = 0; q < n_polys; q++) {
         Fr h0, h1;

@@ -24,6 +24,7 @@
 namespace ja {
 
 constexpr int kRrMaxRounds = 64;
+constexpr int kRrMaxSPolys = 5;
 constexpr unsigned long long kRrTimeoutNs = 30000000000ull;
 
 struct RrWaiter {
@@ -97,8 +98,9 @@ JA_DEV unsigned int rr_width(unsigned long long G, const RrSplit& s, unsigned in
 struct RrSArgs {
   RrCommon c;
   RrSplit split;
-  Fr* buf[2][2];                 // [polynomial][0 = array the first round reads, 1 = the other ping-pong buffer]
+  Fr* buf[kRrMaxSPolys][2];      // [polynomial][0 = array the first round reads, 1 = the other ping-pong buffer]; unused entries repeat polynomial 0
   int np;
+  const Fr* gammas;              // scalars of the body (RSQRT, LIN3)
   RrEq eq;                       // state at the first round
   Fr* partials; unsigned int* counter;
   Fr* slot_vals; unsigned int tag0;
@@ -129,12 +131,12 @@ __global__ void __launch_bounds__(kBlock) k_rr_s(const __grid_constant__ RrSArgs
     }
     FusedPolys P;
 #pragma unroll
-    for (int q = 0; q < 2; q++) { P.in[q] = a.buf[q < a.np ? q : 0][cur]; P.out[q] = a.buf[q < a.np ? q : 0][fused ? 1 - cur : cur]; }
+    for (int q = 0; q < kRrMaxSPolys; q++) { P.in[q] = a.buf[q][cur]; P.out[q] = a.buf[q][fused ? 1 - cur : cur]; }
     const size_t g_begin = (size_t)((unsigned long long)blockIdx.x * G / W), g_end = (size_t)((unsigned long long)(blockIdx.x + 1) * G / W);
     const Publish pub{a.slot_vals, nullptr, a.tag0 + (unsigned int)i};
     __syncthreads();
-    if (fused) round_s_body<KID, true, RrWaiter, true>(P, a.np, r, waiter, eq.e_out(), eq.e_in(), eq.in_len - 1, g_begin, g_end, nullptr, a.partials, a.counter, pub, blockIdx.x, W, 0);
-    else round_s_body<KID, false, RrWaiter, true>(P, a.np, r, waiter, eq.e_out(), eq.e_in(), eq.in_len - 1, g_begin, g_end, nullptr, a.partials, a.counter, pub, blockIdx.x, W, 0);
+    if (fused) round_s_body<KID, true, RrWaiter, true>(P, a.np, r, waiter, eq.e_out(), eq.e_in(), eq.in_len - 1, g_begin, g_end, a.gammas, a.partials, a.counter, pub, blockIdx.x, W, 0);
+    else round_s_body<KID, false, RrWaiter, true>(P, a.np, r, waiter, eq.e_out(), eq.e_in(), eq.in_len - 1, g_begin, g_end, a.gammas, a.partials, a.counter, pub, blockIdx.x, W, 0);
     __syncthreads();
     if (s_abort) return;
     if (fused) { cur = 1 - cur; n /= 2; }

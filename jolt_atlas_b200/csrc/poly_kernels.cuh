@@ -279,7 +279,50 @@ static __global__ void __launch_bounds__(kBlock) k_eq_expand(const Fr* __restric
 // Blocks own contiguous runs of g so a thread keeps one x_out for as long as possible and applies
 // E_out once per run (the reference's delayed outer product).
 struct EvalPolys {
-  const Fr* p[4];
+  const Fr* p[6];
+  const Fr* aux;                 // scalars of the body (device memory): RSQRT {gamma, S^3}, LIN3 {tau}
+};
+
+// Bodies with three to five operands (SURVEY 8a addendum, family S), written once on the pair values (x0 = value at 2g,
+// dx = x[2g+1] - x[2g]) and shared by the un-fused kernel below and the fused / round-resident kernels (fused_kernels.cuh):
+//   8  IFF    [m0 a0 + (1 - m0) b0,  dm da - dm db]                         ops/iff.rs:189-216          (mask, a, b)
+//   9  DIV    [r0 q0 + R0 - l0,  dr dq]                                     ops/div.rs:329-347          (l, r, q, R)
+//   10 RSQRT  [x0 quot0 + dr0 - S^3 + gamma (out0^2 + sr0 - quot0),  dx dquot + gamma dout^2]   ops/rsqrt.rs:390-418
+//                                                                         (x, quotient, output, div_remainder, sqrt_remainder; aux = gamma, S^3)
+//   11 LIN3   [tau q0 + r0 - in0]                                           neural_teleport/division.rs:231-246   (input, quotient, remainder; aux = tau)
+// (ScalarConstDiv's [l0 - R0], ops/scalar_const_div.rs:227-239, is body 1 = SUB.)
+template <int KID> struct SGen;
+template <> struct SGen<8> {
+  static constexpr int NP = 3, NOUT = 2;
+  JA_DEV static void eval(const Fr* lo, const Fr* hi, const Fr*, Fr* v) {
+    const Fr dm = fp_sub<FrParams>(hi[0], lo[0]), da = fp_sub<FrParams>(hi[1], lo[1]), db = fp_sub<FrParams>(hi[2], lo[2]);
+    v[0] = fp_add<FrParams>(lo[2], fp_mul<FrParams>(lo[0], fp_sub<FrParams>(lo[1], lo[2])));     // m a + (1 - m) b = b + m (a - b)
+    v[1] = fp_mul<FrParams>(dm, fp_sub<FrParams>(da, db));
+  }
+};
+template <> struct SGen<9> {
+  static constexpr int NP = 4, NOUT = 2;
+  JA_DEV static void eval(const Fr* lo, const Fr* hi, const Fr*, Fr* v) {
+    v[0] = fp_sub<FrParams>(fp_add<FrParams>(fp_mul<FrParams>(lo[1], lo[2]), lo[3]), lo[0]);
+    v[1] = fp_mul<FrParams>(fp_sub<FrParams>(hi[1], lo[1]), fp_sub<FrParams>(hi[2], lo[2]));
+  }
+};
+template <> struct SGen<10> {
+  static constexpr int NP = 5, NOUT = 2;
+  JA_DEV static void eval(const Fr* lo, const Fr* hi, const Fr* aux, Fr* v) {
+    const Fr gamma = fp_load(aux), s3 = fp_load(aux + 1);
+    const Fr div0 = fp_sub<FrParams>(fp_add<FrParams>(fp_mul<FrParams>(lo[0], lo[1]), lo[3]), s3);
+    const Fr sqrt0 = fp_sub<FrParams>(fp_add<FrParams>(fp_sqr<FrParams>(lo[2]), lo[4]), lo[1]);
+    const Fr dout = fp_sub<FrParams>(hi[2], lo[2]);
+    v[0] = fp_add<FrParams>(div0, fp_mul<FrParams>(gamma, sqrt0));
+    v[1] = fp_add<FrParams>(fp_mul<FrParams>(fp_sub<FrParams>(hi[0], lo[0]), fp_sub<FrParams>(hi[1], lo[1])), fp_mul<FrParams>(gamma, fp_sqr<FrParams>(dout)));
+  }
+};
+template <> struct SGen<11> {
+  static constexpr int NP = 3, NOUT = 1;
+  JA_DEV static void eval(const Fr* lo, const Fr*, const Fr* aux, Fr* v) {
+    v[0] = fp_sub<FrParams>(fp_add<FrParams>(fp_mul<FrParams>(fp_load(aux), lo[1]), lo[2]), lo[0]);
+  }
 };
 
 template <int KID> struct SBody;
@@ -313,6 +356,20 @@ template <> struct SBody<6> {  // IDENT  ps_shout/mod.rs:464-488, opening_reduct
   static constexpr int NOUT = 1;
   JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[1]) { v[0] = fp_load(P.p[0] + 2 * g); }
 };
+
+template <int KID> struct SBodyGen {
+  static constexpr int NOUT = SGen<KID>::NOUT;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[NOUT]) {
+    Fr lo[SGen<KID>::NP], hi[SGen<KID>::NP];
+#pragma unroll
+    for (int q = 0; q < SGen<KID>::NP; q++) { lo[q] = fp_load(P.p[q] + 2 * g); hi[q] = fp_load(P.p[q] + 2 * g + 1); }
+    SGen<KID>::eval(lo, hi, P.aux, v);
+  }
+};
+template <> struct SBody<8> : SBodyGen<8> {};
+template <> struct SBody<9> : SBodyGen<9> {};
+template <> struct SBody<10> : SBodyGen<10> {};
+template <> struct SBody<11> : SBodyGen<11> {};
 
 template <int KID>
 __global__ void __launch_bounds__(kBlock)

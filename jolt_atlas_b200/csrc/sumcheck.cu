@@ -386,6 +386,10 @@ struct DevInst : Inst {
       case JA_EVAL_MUL: n_out = 2; JA_REQUIRE(polys.size() == 2, "sumcheck: MUL takes two polynomials"); fusable = true; break;
       case JA_EVAL_SQUARE: n_out = 2; JA_REQUIRE(polys.size() == 1, "sumcheck: SQUARE takes one polynomial"); fusable = true; break;
       case 7: n_out = 2; fusable = true; break;
+      case JA_EVAL_IFF: n_out = 2; JA_REQUIRE(polys.size() == 3, "sumcheck: IFF takes three polynomials (mask, a, b)"); fusable = true; break;
+      case JA_EVAL_DIV: n_out = 2; JA_REQUIRE(polys.size() == 4, "sumcheck: DIV takes four polynomials (l, r, q, R)"); fusable = true; break;
+      case JA_EVAL_RSQRT: n_out = 2; JA_REQUIRE(polys.size() == 5 && gammas.size() == 2, "sumcheck: RSQRT takes five polynomials and aux = {gamma, S^3}"); fusable = true; break;
+      case JA_EVAL_LIN3: n_out = 1; JA_REQUIRE(polys.size() == 3 && gammas.size() == 1, "sumcheck: LIN3 takes three polynomials and aux = {tau}"); fusable = true; break;
       case JA_EVAL_PROD: n_out = polys.size(); fusable = polys.size() <= 16; break;
       case JA_EVAL_POW: n_out = pow_d; JA_REQUIRE(polys.size() == 1, "sumcheck: POW takes one polynomial"); fusable = pow_d <= 16; break;
       case JA_EVAL_DOT2: n_out = 2; order = JA_HIGH_TO_LOW; JA_REQUIRE(polys.size() == 2, "sumcheck: DOT2 takes two polynomials"); fusable = true; break;
@@ -401,15 +405,15 @@ struct DevInst : Inst {
       sharded = true; sc_rank = c->sc_rank; sc_world = c->sc_world;
       rounds += (size_t)log2z(sc_world);
     }
-    if (kind == 7) {
-      JA_REQUIRE(gammas.size() == polys.size(), "sumcheck: booleanity takes one gamma per polynomial");
+    if (kind == 7 || kind == JA_EVAL_RSQRT || kind == JA_EVAL_LIN3) {
+      JA_REQUIRE(kind != 7 || gammas.size() == polys.size(), "sumcheck: booleanity takes one gamma per polynomial");
       int32_t st = dev_alloc(c, gammas.size() * sizeof(Fr), (void**)&d_gammas);
       if (st) return st;
       if ((st = stage_h2d(c, d_gammas, gammas.data(), gammas.size() * sizeof(Fr)))) return st;
     }
     return JA_OK;
   }
-  bool uses_eq() const { return kind <= 7 || kind == JA_EVAL_OPEN; }
+  bool uses_eq() const { return kind <= JA_EVAL_LIN3 || kind == JA_EVAL_OPEN; }
   bool needs_slot() const override { return fusable; }
 
   // everything a fused round launch needs, computed before the launch (shared by the single and the paired launch)
@@ -545,6 +549,7 @@ struct DevInst : Inst {
     }
     switch (kind) {
       case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_MUL: case JA_EVAL_SQUARE: case JA_EVAL_IDENT: case 7:
+      case JA_EVAL_IFF: case JA_EVAL_DIV: case JA_EVAL_RSQRT: case JA_EVAL_LIN3:
       case JA_EVAL_PROD: case JA_EVAL_POW: case JA_EVAL_DOT2: case JA_EVAL_DOT3: break;
       default: return false;
     }
@@ -576,7 +581,8 @@ struct DevInst : Inst {
   bool persist_ok(size_t len_now) const {
     if (!fusable || sharded || len_now < 2 || !c_rr_ok || !persist_allowed()) return false;
     switch (kind) {
-      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_MUL: case JA_EVAL_SQUARE: case JA_EVAL_IDENT: return eq != nullptr && len_now <= kRrMaxLenS;
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_MUL: case JA_EVAL_SQUARE: case JA_EVAL_IDENT:
+      case JA_EVAL_IFF: case JA_EVAL_DIV: case JA_EVAL_RSQRT: case JA_EVAL_LIN3: return eq != nullptr && len_now <= kRrMaxLenS;
       case JA_EVAL_DOT2: case JA_EVAL_DOT3: return len_now <= kRrMaxLenDot;
       default: return false;
     }
@@ -641,11 +647,11 @@ struct DevInst : Inst {
     JA_REQUIRE((size_t(1) << ((eq->out_len - 1) + (eq->in_len - 1))) == G0, "sumcheck: split-eq tables do not cover len/2 (eq and polys out of lockstep)");
     RrSArgs a;
     memset(&a, 0, sizeof(a));
-    Fr* bufs[2][2];
+    Fr* bufs[kRrMaxSPolys][2];
     if ((st = persist_prepare(c, &a.c, g, bufs))) return st;
     a.np = (int)polys.size();
-    for (int q = 0; q < a.np; q++) { a.buf[q][0] = bufs[q][0]; a.buf[q][1] = bufs[q][1]; }
-    if (a.np == 1) { a.buf[1][0] = a.buf[0][0]; a.buf[1][1] = a.buf[0][1]; }
+    for (int q = 0; q < kRrMaxSPolys; q++) { const int qq = q < a.np ? q : 0; a.buf[q][0] = bufs[qq][0]; a.buf[q][1] = bufs[qq][1]; }
+    a.gammas = d_gammas;
     a.eq = rr_eq_state(eq);
     a.partials = c->d_partials; a.counter = c->d_counter; a.slot_vals = slot_vals; a.tag0 = g->tag0;
     a.split = RrSplit{(unsigned int)kBlock, 128u, 512u};   // one pair per thread and pass; 512 pairs or fewer on one block
@@ -656,6 +662,10 @@ struct DevInst : Inst {
       case JA_EVAL_SUB: k = (const void*)k_rr_s<1>; break;
       case JA_EVAL_MUL: k = (const void*)k_rr_s<2>; break;
       case JA_EVAL_SQUARE: k = (const void*)k_rr_s<3>; break;
+      case JA_EVAL_IFF: k = (const void*)k_rr_s<8>; break;
+      case JA_EVAL_DIV: k = (const void*)k_rr_s<9>; break;
+      case JA_EVAL_RSQRT: k = (const void*)k_rr_s<10>; break;
+      case JA_EVAL_LIN3: k = (const void*)k_rr_s<11>; break;
       default: k = (const void*)k_rr_s<6>; break;
     }
     return rr_launch(c, k, (unsigned int)w0, a);
@@ -745,6 +755,10 @@ struct DevInst : Inst {
         case JA_EVAL_MUL: JA_S_K(2); break;
         case JA_EVAL_SQUARE: JA_S_K(3); break;
         case JA_EVAL_IDENT: JA_S_K(6); break;
+        case JA_EVAL_IFF: JA_S_K(8); break;
+        case JA_EVAL_DIV: JA_S_K(9); break;
+        case JA_EVAL_RSQRT: JA_S_K(10); break;
+        case JA_EVAL_LIN3: JA_S_K(11); break;
         default: JA_S_K(7); break;
       }
 #undef JA_S_K
@@ -841,12 +855,12 @@ struct DevInst : Inst {
     for (size_t k = 0; k < n_out; k++) e[k] = host::from_limbs(ev + 4 * k);
     const FrH prev = has_scale ? host::mul(prev_in, scale_inv) : prev_in;
     switch (kind) {
-      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT: case JA_EVAL_OPEN: {
+      case JA_EVAL_ADD: case JA_EVAL_SUB: case JA_EVAL_IDENT: case JA_EVAL_OPEN: case JA_EVAL_LIN3: {
         const FrH q1 = gruen_q1(prev, e[0]);
         qc0 = e[0]; qc1 = host::sub(q1, e[0]); qc2 = host::FR_ZERO;
         *uni = host::gruen_poly_deg_2_q1(cs, cw, e[0], prev, q1); break;             // ops/add.rs:297-304, opening_reduction.rs:402
       }
-      case JA_EVAL_MUL: case JA_EVAL_SQUARE: case 7: {
+      case JA_EVAL_MUL: case JA_EVAL_SQUARE: case 7: case JA_EVAL_IFF: case JA_EVAL_DIV: case JA_EVAL_RSQRT: {
         const FrH q1 = gruen_q1(prev, e[0]);
         qc0 = e[0]; qc1 = host::sub(host::sub(q1, e[0]), e[1]); qc2 = e[1];
         *uni = host::gruen_poly_deg_3_q1(cs, cw, e[0], e[1], prev, q1); break;       // ops/mul.rs:177, booleanity.rs:295-300
@@ -1415,6 +1429,10 @@ int32_t build_instance(ja_ctx* c, const ja_sc_instance& d, std::vector<std::uniq
   std::unique_ptr<DevInst> v(new DevInst());
   v->kind = d.kind; v->pow_d = d.aux_u32;
   v->polys.assign(d.polys, d.polys + d.n_polys);
+  if ((d.kind == JA_EVAL_RSQRT || d.kind == JA_EVAL_LIN3) && d.aux_fr) {
+    v->gammas.resize(d.n_aux);
+    for (size_t i = 0; i < d.n_aux; i++) v->gammas[i] = host::from_limbs(d.aux_fr + 4 * i);
+  }
   if (d.kind == JA_EVAL_SUM1 && d.aux_fr) {
     JA_REQUIRE(d.n_aux == d.n_polys, "sumcheck: SUM1 takes one gamma per polynomial");
     v->gammas.resize(d.n_aux);

@@ -108,7 +108,12 @@ static int sumcheck_prove_t(int family, int kind, unsigned pow_d, const uint64_t
   std::vector<FrVec> ps;
   for (size_t i = 0; i < npoly; i++) ps.push_back(load_fr(polys + 4 * n * i, n));
   std::unique_ptr<Instance> inst;
-  if (family == 0) { FrVec ww = load_fr(w, m); inst.reset(new SplitEqInstance(kind, ww.data(), m, std::move(ps), Fr::from_raw(claim), pow_d)); }
+  if (family == 0) {
+    FrVec ww = load_fr(w, m);
+    std::vector<Fr> aux;      // RSQRT: gamma, S^3; LIN3: tau (passed in `gammas`)
+    if (gammas && (kind == S_RSQRT || kind == S_LIN3)) aux = load_fr(gammas, kind == S_RSQRT ? 2 : 1);
+    inst.reset(new SplitEqInstance(kind, ww.data(), m, std::move(ps), Fr::from_raw(claim), pow_d, aux));
+  }
   else if (family == 1) inst.reset(new DotInstance(std::move(ps), Fr::from_raw(claim)));
   else {
     std::vector<Fr> g(npoly, Fr::one());
@@ -144,7 +149,12 @@ static Instance* make_instance(const orc_inst& d) {
   std::vector<FrVec> ps;
   if (d.polys) for (size_t i = 0; i < d.n_polys; i++) ps.push_back(load_fr(d.polys + 4 * d.poly_len * i, d.poly_len));
   const Fr claim = Fr::from_raw(d.claim);
-  if (d.kind <= 6) { FrVec w = load_fr(d.eq_w, d.eq_m); return new SplitEqInstance(d.kind, w.data(), d.eq_m, std::move(ps), claim, d.aux_u32); }
+  if (d.kind <= 11) {
+    FrVec w = load_fr(d.eq_w, d.eq_m);
+    std::vector<Fr> aux;
+    if (d.aux_fr && d.kind >= 8) aux = load_fr(d.aux_fr, d.n_aux);
+    return new SplitEqInstance(d.kind, w.data(), d.eq_m, std::move(ps), claim, d.aux_u32, aux);
+  }
   if (d.kind == 16 || d.kind == 17) return new DotInstance(std::move(ps), claim);
   if (d.kind == 18) {
     std::vector<Fr> g(d.n_polys, Fr::one());

@@ -58,7 +58,11 @@ inline UniPoly gruen_poly_deg_2(const GruenSplitEq& eq, const Fr& q0, const Fr& 
   return UniPoly::from_evals({c0, c1, eq2 * l2});
 }
 
-enum SKind { S_ADD = 0, S_SUB = 1, S_MUL = 2, S_SQUARE = 3, S_PROD = 4, S_POW = 5, S_IDENT = 6 };
+enum SKind { S_ADD = 0, S_SUB = 1, S_MUL = 2, S_SQUARE = 3, S_PROD = 4, S_POW = 5, S_IDENT = 6,
+             S_IFF = 8,      // jolt-atlas-core/src/onnx_proof/ops/iff.rs:189-216
+             S_DIV = 9,      // ops/div.rs:329-347
+             S_RSQRT = 10,   // ops/rsqrt.rs:390-418  (aux = gamma, S^3)
+             S_LIN3 = 11 };  // neural_teleport/division.rs:231-246  (aux = tau)
 
 // Family S: split-eq weighted, LowToHigh
 struct SplitEqInstance : Instance {
@@ -66,11 +70,12 @@ struct SplitEqInstance : Instance {
   GruenSplitEq eq;
   std::vector<FrVec> polys;
   Fr claim;
-  SplitEqInstance(int kind_, const Fr* w, size_t m, std::vector<FrVec> p, Fr claim_, unsigned pow_d_ = 0)
-      : kind(kind_), pow_d(pow_d_), eq(w, m, LOW_TO_HIGH), polys(std::move(p)), claim(claim_) {}
+  std::vector<Fr> aux;      // scalars of the body (RSQRT: gamma, S^3; LIN3: tau)
+  SplitEqInstance(int kind_, const Fr* w, size_t m, std::vector<FrVec> p, Fr claim_, unsigned pow_d_ = 0, std::vector<Fr> aux_ = {})
+      : kind(kind_), pow_d(pow_d_), eq(w, m, LOW_TO_HIGH), polys(std::move(p)), claim(claim_), aux(std::move(aux_)) {}
   size_t num_rounds() const override { return eq.w.size(); }
   size_t degree() const override {
-    switch (kind) { case S_ADD: case S_SUB: case S_IDENT: return 2; case S_MUL: case S_SQUARE: return 3;
+    switch (kind) { case S_ADD: case S_SUB: case S_IDENT: case S_LIN3: return 2; case S_MUL: case S_SQUARE: case S_IFF: case S_DIV: case S_RSQRT: return 3;
                     case S_POW: return pow_d + 1; default: return polys.size() + 1; }
   }
   Fr input_claim() const override { return claim; }
@@ -101,6 +106,45 @@ struct SplitEqInstance : Instance {
       const FrVec& o = polys[0];
       eq.fold<2>([&](size_t g, Fr* v) { Fr d = o[2 * g + 1] - o[2 * g]; v[0] = o[2 * g].sqr(); v[1] = d.sqr(); }, q);
       return gruen_poly_deg_3(eq, q[0], q[1], prev);
+    }
+    if (kind == S_IFF) {      // iff.rs:197-215, literally
+      Fr q[2];
+      const FrVec &mk = polys[0], &a = polys[1], &b = polys[2];
+      eq.fold<2>([&](size_t g, Fr* v) {
+        Fr mask0 = mk[2 * g], mask1 = mk[2 * g + 1], mask_inf = mask1 - mask0;
+        Fr a0 = a[2 * g], a_inf = a[2 * g + 1] - a0;
+        Fr b0 = b[2 * g], b_inf = b[2 * g + 1] - b0;
+        v[0] = mask0 * a0 + (Fr::one() - mask0) * b0;
+        Fr f = (Fr::one() - mask1) - (Fr::one() - mask0);
+        v[1] = mask_inf * a_inf + f * b_inf; }, q);
+      return gruen_poly_deg_3(eq, q[0], q[1], prev);
+    }
+    if (kind == S_DIV) {      // div.rs:335-346
+      Fr q[2];
+      const FrVec &l = polys[0], &r = polys[1], &qq = polys[2], &R = polys[3];
+      eq.fold<2>([&](size_t g, Fr* v) {
+        v[0] = (r[2 * g] * qq[2 * g]) + R[2 * g] - l[2 * g];
+        v[1] = (r[2 * g + 1] - r[2 * g]) * (qq[2 * g + 1] - qq[2 * g]); }, q);
+      return gruen_poly_deg_3(eq, q[0], q[1], prev);
+    }
+    if (kind == S_RSQRT) {    // rsqrt.rs:399-417
+      Fr q[2];
+      const FrVec &x = polys[0], &quot = polys[1], &out = polys[2], &dr = polys[3], &sr = polys[4];
+      const Fr gamma = aux[0], s_cubed = aux[1];
+      eq.fold<2>([&](size_t g, Fr* v) {
+        Fr div0 = x[2 * g] * quot[2 * g] + dr[2 * g] - s_cubed;
+        Fr sqrt0 = out[2 * g] * out[2 * g] + sr[2 * g] - quot[2 * g];
+        Fr div_quad = (x[2 * g + 1] - x[2 * g]) * (quot[2 * g + 1] - quot[2 * g]);
+        Fr dout = out[2 * g + 1] - out[2 * g];
+        v[0] = div0 + gamma * sqrt0; v[1] = div_quad + gamma * (dout * dout); }, q);
+      return gruen_poly_deg_3(eq, q[0], q[1], prev);
+    }
+    if (kind == S_LIN3) {     // neural_teleport/division.rs:238-245
+      Fr q[1];
+      const FrVec &in = polys[0], &qu = polys[1], &rem = polys[2];
+      const Fr tau = aux[0];
+      eq.fold<1>([&](size_t g, Fr* v) { v[0] = (tau * qu[2 * g]) + rem[2 * g] - in[2 * g]; }, q);
+      return gruen_poly_deg_2(eq, q[0], prev);
     }
     const size_t d = kind == S_POW ? pow_d : polys.size();
     std::vector<Fr> sums(d);
