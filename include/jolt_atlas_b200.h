@@ -70,10 +70,21 @@ enum {
                            div_remainder, sqrt_remainder), aux_fr = {gamma, S^3}       ops/rsqrt.rs:390-418 n_out=2 */
   JA_EVAL_LIN3 = 11,    /* [tau*q0+r0-in0]  polys (input, quotient, remainder), aux_fr = {tau}
                            neural_teleport/division.rs:231-246; ScalarConstDiv's [l0-R0] (ops/scalar_const_div.rs:227) is JA_EVAL_SUB  n_out=1 */
+  JA_EVAL_WIDENT = 12,  /* [p0 * T[g >> s]] split-eq weighted; polys (p, T), T a smaller table, aux_u32 = s
+                           softmax_last_axis/recip_mult.rs:196-216 (phase 1)   n_out=1   (ja_round_eval only) */
   JA_EVAL_DOT2 = 16,    /* [sum l(0)r(0), sum l(2)r(2)]             einsum/dot.rs:292-303   n_out=2 */
   JA_EVAL_DOT3 = 17,    /* [sum l r e at 0,2,3], three MLEs of equal length  dot.rs:330-350   n_out=3 */
   JA_EVAL_SUM1 = 18,    /* [sum_i gamma_i * sum_j p_i[2j]]  LowToHigh one eval  hamming_weight.rs:118-139 (aux = gammas) */
   JA_EVAL_SUMHI = 19,   /* [sum_{j<n/2} p[j]]  HighToLow one eval  ops/sum/axis.rs:220-233 */
+  /* Two-phase / table-weighted bodies: through ja_round_eval only (the caller owns the phase logic; the table or eq polynomial is the
+   * LAST entry of polys and may be shorter than the operands; aux_u32 = s). */
+  JA_EVAL_WSUM = 21,        /* [sum_g p[2g] T[g >> s]]  LowToHigh, degree 1   softmax_last_axis/exp_sum.rs:146-158   polys (p, T)   n_out=1 */
+  JA_EVAL_WDOT2 = 22,       /* [sum_g T[g >> s] X(k) e(k), k=0,2,3]  LowToHigh  softmax_last_axis/max.rs:185-206   polys (X, e, T)  n_out=3 */
+  JA_EVAL_DOT2_L2H = 23,    /* [sum a(0)b(0), sum a(2)b(2)]  LowToHigh   ops/slice.rs:254, reshape.rs:286, concat.rs:290, gather/mod.rs:232 (b = table + gamma*identity)  n_out=2 */
+  JA_EVAL_SQ_EQHI = 24,     /* [sum_i l(k)^2 e(k), k=0,2,3]  HighToLow, e = eq polynomial at i >> s (length 1: its final claim)
+                               ops/mean_of_squares.rs:363-386   polys (l, eq)   n_out=3 */
+  JA_EVAL_DOT2_EQHI = 25,   /* [sum_i l(k) r(k) e(k)]  the same with two operands   ops/einsum/dot.rs:306-326 (EqSchedule::High)  polys (l, r, eq)  n_out=3 */
+  JA_EVAL_DOT2_EQLOW = 26,  /* [sum_i l(k) r(k) T[i & (2^s-1)]]   ops/einsum/dot.rs:328-347 (EqSchedule::Low, rounds < log_k)  polys (l, r, T)  n_out=3 */
   JA_EVAL_OPEN = 20     /* dense opening reduction: [sum_{j<n/2} eq(r, j) P[j]] HighToLow with a HighToLow split-eq
                            (DensePolynomialProverOpening, subprotocols/opening_reduction.rs:355-419); n_out=1.
                            Only through ja_sumcheck_prove / ja_batched_sumcheck_prove. */

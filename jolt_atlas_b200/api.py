@@ -30,9 +30,13 @@ class BindingOrder:
 class EvalKernel:
     ADD, SUB, MUL, SQUARE, PROD, POW, IDENT = 0, 1, 2, 3, 4, 5, 6
     IFF, DIV, RSQRT, LIN3 = 8, 9, 10, 11           # ops/iff.rs:189, ops/div.rs:329, ops/rsqrt.rs:390, neural_teleport/division.rs:231
+    WIDENT = 12                                    # softmax_last_axis/recip_mult.rs:196 (phase 1); ja_round_eval only
     DOT2, DOT3, SUM1, SUMHI, OPEN = 16, 17, 18, 19, 20
-    N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 8: 2, 9: 2, 10: 2, 11: 1, 16: 2, 17: 3, 18: 1, 19: 1}
-    FAMILY_S = (0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11)
+    # two-phase / table-weighted bodies (ja_round_eval only; the table or eq polynomial is the last polynomial, aux_u32 = shift)
+    WSUM, WDOT2, DOT2_L2H, SQ_EQHI, DOT2_EQHI, DOT2_EQLOW = 21, 22, 23, 24, 25, 26
+    N_OUT = {0: 1, 1: 1, 2: 2, 3: 2, 6: 1, 8: 2, 9: 2, 10: 2, 11: 1, 12: 1, 16: 2, 17: 3, 18: 1, 19: 1,
+             21: 1, 22: 3, 23: 2, 24: 3, 25: 3, 26: 3}
+    FAMILY_S = (0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12)
 
 
 class _Addr(C.c_void_p):

@@ -3,6 +3,7 @@
 #include <memory>
 #include "common.hpp"
 #include "poly_kernels.cuh"
+#include "aux_bodies.cuh"
 
 static thread_local std::string g_last_error;
 std::string& ja_err_slot() { return g_last_error; }
@@ -543,6 +544,52 @@ int32_t ja_round_eval(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys,
 
 // The asynchronous half: validates, launches the kernel and enqueues the D2H copy of the reduced sums into the
 // context's pinned staging buffer.  The caller may do host work (e.g. the round's field inversion) before collect.
+// table-weighted / eq-scheduled bodies (aux_bodies.cuh)
+static int32_t ja_round_eval_w_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys, uint32_t shift, size_t n_out,
+                                      RoundEvalPending* pend) {
+  const size_t len = polys[0]->len, half = len / 2;
+  WArgs a;
+  memset(&a, 0, sizeof(a));
+  a.shift = shift;
+  size_t want_polys = 0, want_out = 0;
+  switch (kernel_id) {
+    case JA_EVAL_WSUM: want_polys = 2; want_out = 1; break;
+    case JA_EVAL_WDOT2: want_polys = 3; want_out = 3; break;
+    case JA_EVAL_DOT2_L2H: want_polys = 2; want_out = 2; break;
+    case JA_EVAL_SQ_EQHI: want_polys = 2; want_out = 3; break;
+    case JA_EVAL_DOT2_EQHI: case JA_EVAL_DOT2_EQLOW: want_polys = 3; want_out = 3; break;
+    default: return fail(JA_ERR_UNSUPPORTED, "ja_round_eval: kernel_id not implemented");
+  }
+  JA_REQUIRE(n_polys == want_polys && n_out == want_out && shift < 60, "ja_round_eval: wrong n_polys / n_out / shift for kernel_id");
+  const size_t n_ops = kernel_id == JA_EVAL_DOT2_L2H ? 2 : n_polys - 1;
+  for (size_t q = 0; q < n_ops; q++) a.p[q] = polys[q]->data();
+  if (kernel_id != JA_EVAL_DOT2_L2H) {
+    const ja_poly* t = polys[n_polys - 1];
+    a.tab = t->data(); a.tab_len = t->len;
+    const size_t top = (half - 1) >> shift;
+    if (kernel_id == JA_EVAL_WSUM || kernel_id == JA_EVAL_WDOT2) JA_REQUIRE(top < t->len, "ja_round_eval: table shorter than (len/2) >> shift");
+    else if (kernel_id == JA_EVAL_DOT2_EQLOW) JA_REQUIRE((size_t(1) << shift) <= t->len, "ja_round_eval: table shorter than 2^shift");
+    else JA_REQUIRE(t->len == 1 || top < t->len / 2, "ja_round_eval: eq polynomial shorter than 2 * ((len/2) >> shift)");
+  }
+  unsigned grid = grid_for(half);
+  if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+#define JA_W(MODE) JA_LAUNCH(c, KC_ROUND_EVAL_DOT, k_round_eval_w<MODE><<<grid, kBlock, 0, c->stream>>>(a, half, c->d_partials, c->d_counter, c->d_out))
+  switch (kernel_id) {
+    case JA_EVAL_WSUM: JA_W(W_SUM); break;
+    case JA_EVAL_WDOT2: JA_W(W_DOT2); break;
+    case JA_EVAL_DOT2_L2H: JA_W(W_DOT2_L2H); break;
+    case JA_EVAL_SQ_EQHI: JA_W(W_SQ_EQHI); break;
+    case JA_EVAL_DOT2_EQHI: JA_W(W_DOT2_EQHI); break;
+    default: JA_W(W_DOT2_EQLOW); break;
+  }
+#undef JA_W
+  JA_CUDA(cudaGetLastError());
+  JA_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  pend->n_dev = n_out; pend->n_out = n_out; pend->n_polys = n_polys; pend->fam_sum = false; pend->aux_fr = nullptr;
+  pend->prod_lanes = 0; pend->prod_d = 0;
+  return JA_OK;
+}
+
 int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const* polys, size_t n_polys,
                              const ja_spliteq* eq, const uint64_t* aux_fr, size_t n_aux, uint32_t aux_u32, size_t n_out,
                              RoundEvalPending* pend) {
@@ -552,11 +599,20 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
   JA_CUDA(cudaSetDevice(c->device));
   const size_t len = polys[0]->len;
   JA_REQUIRE(len >= 2, "ja_round_eval: polynomial already fully bound");
+  // table-weighted bodies: the last polynomial is the (shorter) table / eq polynomial
+  const bool has_table = kernel_id == JA_EVAL_WIDENT || kernel_id == JA_EVAL_WSUM || kernel_id == JA_EVAL_WDOT2 || kernel_id == JA_EVAL_SQ_EQHI ||
+                         kernel_id == JA_EVAL_DOT2_EQHI || kernel_id == JA_EVAL_DOT2_EQLOW;
   for (size_t i = 0; i < n_polys; i++)
-    JA_REQUIRE(polys[i] && polys[i]->len == len, "ja_round_eval: polynomial length mismatch");
+    JA_REQUIRE(polys[i] && (polys[i]->len == len || (has_table && i + 1 == n_polys)), "ja_round_eval: polynomial length mismatch");
+  if (has_table || kernel_id == JA_EVAL_DOT2_L2H) {
+    if (kernel_id != JA_EVAL_WIDENT) {
+      JA_REQUIRE(eq == nullptr, "ja_round_eval: this kernel_id takes no split-eq handle");
+      return ja_round_eval_w_launch(c, kernel_id, polys, n_polys, aux_u32, n_out, pend);
+    }
+  }
   EvalPolys P;
   for (size_t i = 0; i < 6; i++) P.p[i] = i < n_polys ? polys[i]->data() : nullptr;
-  P.aux = nullptr;
+  P.aux = nullptr; P.shift = 0;
   const size_t G = len / 2;
   size_t want_out = 0, want_polys = 0;
   enum { FAM_S, FAM_D, FAM_PROD, FAM_SUM } fam = FAM_S;
@@ -565,6 +621,8 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
     case JA_EVAL_MUL: want_out = 2; want_polys = 2; break;
     case JA_EVAL_SQUARE: want_out = 2; want_polys = 1; break;
     case JA_EVAL_IDENT: want_out = 1; want_polys = 1; break;
+    case JA_EVAL_WIDENT: want_out = 1; want_polys = 2;
+      JA_REQUIRE(aux_u32 < 60 && ((len / 2 - 1) >> aux_u32) < polys[1]->len, "ja_round_eval: WIDENT table shorter than (len/2) >> shift"); break;
     case JA_EVAL_IFF: want_out = 2; want_polys = 3; break;
     case JA_EVAL_DIV: want_out = 2; want_polys = 4; break;
     case JA_EVAL_RSQRT: want_out = 2; want_polys = 5; JA_REQUIRE(aux_fr && n_aux == 2, "ja_round_eval: RSQRT takes aux_fr = {gamma, S^3}"); break;
@@ -597,6 +655,7 @@ int32_t ja_round_eval_launch(ja_ctx* c, int32_t kernel_id, const ja_poly* const*
       case JA_EVAL_MUL: launch_s<2>(c, P, eq, G); break;
       case JA_EVAL_SQUARE: launch_s<3>(c, P, eq, G); break;
       case JA_EVAL_IDENT: launch_s<6>(c, P, eq, G); break;
+      case JA_EVAL_WIDENT: P.shift = aux_u32; launch_s<12>(c, P, eq, G); break;
       case JA_EVAL_IFF: launch_s<8>(c, P, eq, G); break;
       case JA_EVAL_DIV: launch_s<9>(c, P, eq, G); break;
       case JA_EVAL_RSQRT: case JA_EVAL_LIN3: {
@@ -865,7 +924,7 @@ int32_t ja_bench_kernel(ja_ctx* c, int32_t which, int32_t log_n, int32_t n_polys
       if (which == 0) JA_LAUNCH(c, KC_BIND, k_bind<true><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
       else            JA_LAUNCH(c, KC_BIND, k_bind<false><<<grid, kBlock, 0, c->stream>>>(args, ch, half));
     } else {
-      EvalPolys P; P.p[0] = src[0]; P.p[1] = src[1]; P.p[2] = P.p[3] = P.p[4] = P.p[5] = nullptr; P.aux = nullptr;
+      EvalPolys P; P.p[0] = src[0]; P.p[1] = src[1]; P.p[2] = P.p[3] = P.p[4] = P.p[5] = nullptr; P.aux = nullptr; P.shift = 0;
       if (which == 2) launch_s<2>(c, P, eq, half);
       else if (which == 4) launch_s<0>(c, P, eq, half);
       else {

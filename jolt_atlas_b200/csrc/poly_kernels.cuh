@@ -281,6 +281,7 @@ static __global__ void __launch_bounds__(kBlock) k_eq_expand(const Fr* __restric
 struct EvalPolys {
   const Fr* p[6];
   const Fr* aux;                 // scalars of the body (device memory): RSQRT {gamma, S^3}, LIN3 {tau}
+  unsigned int shift;            // WIDENT: the table p[1] is indexed by g >> shift
 };
 
 // Bodies with three to five operands (SURVEY 8a addendum, family S), written once on the pair values (x0 = value at 2g,
@@ -365,6 +366,10 @@ template <int KID> struct SBodyGen {
     for (int q = 0; q < SGen<KID>::NP; q++) { lo[q] = fp_load(P.p[q] + 2 * g); hi[q] = fp_load(P.p[q] + 2 * g + 1); }
     SGen<KID>::eval(lo, hi, P.aux, v);
   }
+};
+template <> struct SBody<12> {  // WIDENT  softmax_last_axis/recip_mult.rs:196-216 (phase 1): [exp_q(k, 0) * inv_sum(k)], k = g >> shift
+  static constexpr int NOUT = 1;
+  JA_DEV static void eval(const EvalPolys& P, size_t g, Fr (&v)[1]) { v[0] = fp_mul<FrParams>(fp_load(P.p[0] + 2 * g), fp_load(P.p[1] + (g >> P.shift))); }
 };
 template <> struct SBody<8> : SBodyGen<8> {};
 template <> struct SBody<9> : SBodyGen<9> {};
