@@ -336,6 +336,18 @@ int32_t ja_round_eval_slice(ja_ctx*, int32_t kernel_id, const ja_poly* const* po
  * proof.  Split-eq (LowToHigh) bodies and PROD / POW only; world == 1 (or a NULL callback) restores the normal mode. */
 typedef int32_t (*ja_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
 int32_t ja_set_sumcheck_shard(ja_ctx*, uint32_t rank, uint32_t world, ja_allgather_fn allgather, void* user);
+/* In-library exchange (comm.cu): an NCCL communicator owned by the context, collectives on the context's stream.  Rank 0 calls
+ * ja_comm_unique_id and hands the 128 bytes to the other ranks by any means; every rank calls ja_comm_init.  From then on, with
+ * ja_set_msm_shard(rank, world), every MSM (ja_hyperkzg_open*, ja_msm_fr*, ...) multiplies this rank's index range and the partial
+ * POINTS are all-gathered and added inside the call (every rank returns the full result); ja_addr_commit_many deals the lists of a
+ * proof round-robin to the ranks and all-gathers the commitments; ja_set_sumcheck_shard(rank, world, NULL, NULL) all-gathers the
+ * partial round sums through the same communicator.  JA_ERR_UNSUPPORTED when libnccl.so.2 cannot be loaded.
+ * Reference: none (single-process rayon); the split points are joltworks/src/msm/mod.rs:27-181 (pairs by index) and
+ * jolt-atlas-core/src/onnx_proof/prover.rs:236-249 (one commitment per polynomial). */
+int32_t ja_comm_unique_id(uint8_t out[128]);
+int32_t ja_comm_init(ja_ctx*, uint32_t rank, uint32_t world, const uint8_t id[128]);
+void ja_comm_free(ja_ctx*);
+int32_t ja_comm_allgather(ja_ctx*, const void* send, size_t bytes, void* recv);   /* host buffers, recv = world x bytes, rank-major */
 /* Host-only (no ja_ctx, no GPU): add n affine points (complete addition) / add n_parts vectors of n_vals Fr. */
 int32_t ja_g1_sum_affine(const uint64_t* xy, const int32_t* is_inf, size_t n, uint64_t out_xy[8], int32_t* out_inf);
 int32_t ja_fr_sum(const uint64_t* vals, size_t n_parts, size_t n_vals, uint64_t* out);

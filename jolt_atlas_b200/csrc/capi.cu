@@ -111,6 +111,7 @@ int32_t ja_init(int32_t device, ja_ctx** out) {
 
 void ja_shutdown(ja_ctx* c) {
   if (!c) return;
+  ja_comm_free(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   dev_cache_release(c);

@@ -84,6 +84,10 @@ struct ja_ctx {
   void* d_rowvals = nullptr;
   // MSM index-range shard of this context (shard.cu): ja_msm_run restricts every job to its slice when count > 1
   uint32_t msm_shard_index = 0, msm_shard_count = 1;
+  // NCCL communicator of this context (comm.cu: ja_comm_init); with it, sharded MSMs / commitments / sumcheck rounds exchange
+  // their partial results inside the library
+  void* comm = nullptr;
+  uint32_t comm_rank = 0, comm_world = 1;
   // sharded sumcheck (ja_set_sumcheck_shard): device polynomials are contiguous hypercube slices, partial round sums
   // are all-gathered through the caller's callback
   uint32_t sc_rank = 0, sc_world = 1;
@@ -172,6 +176,9 @@ struct MsmJob {
   uint32_t dense_random = 0;
 };
 int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, uint64_t* out_xy, int32_t* is_inf);
+// comm.cu: all-gather over the context's communicator (host buffers, rank-major) and the point-wise sum of every rank's partial points
+int32_t comm_allgather(ja_ctx* c, const void* send, size_t bytes, void* recv);
+int32_t comm_combine_points(ja_ctx* c, uint64_t* xy, int32_t* inf, size_t count);
 
 struct ja_spliteq {
   int order = 0;

@@ -271,6 +271,13 @@ int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs
   int32_t st = msm_engine(c, srs, jobs, res.data());
   if (st) return st;
   for (size_t i = 0; i < jobs.size(); i++) store_result(res[i], out_xy + 8 * i, is_inf ? is_inf + i : nullptr);
+  // with a communicator the partial points of the index ranges are exchanged and added here: every rank returns the full results
+  if (c->msm_shard_count > 1 && c->comm && c->comm_world == c->msm_shard_count) {
+    std::vector<int32_t> flags(jobs.size());
+    for (size_t i = 0; i < jobs.size(); i++) flags[i] = (int32_t)res[i].inf;
+    if ((st = comm_combine_points(c, out_xy, flags.data(), jobs.size()))) return st;
+    if (is_inf) memcpy(is_inf, flags.data(), sizeof(int32_t) * jobs.size());
+  }
   return JA_OK;
 }
 

@@ -351,9 +351,26 @@ int32_t ja_addr_commit_many(ja_ctx* c, const ja_srs* srs, const ja_addr* const* 
     for (size_t i = 0; i < a->d; i++) { jobs.push_back(AddrJob{a->d_k + i * a->T, (uint32_t)a->T, (uint32_t)blocks, 0}); blocks += bpl; }
     JA_REQUIRE(blocks < (1ull << 31), "ja_addr_commit: batch too large");
   }
-  const size_t count = jobs.size();
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
+  // One proof on several GPUs (ja_comm_init + ja_set_msm_shard): the lists are dealt round-robin to the ranks - the commitments
+  // of a proof are independent of each other and of the transcript - and ONE all-gather makes every rank hold all of them.
+  const bool dealt = c->comm && c->msm_shard_count > 1 && c->comm_world == c->msm_shard_count && jobs.size() >= c->comm_world;
+  const size_t total_lists = jobs.size();
+  std::vector<size_t> owner_slot;               // list i -> its position among this rank's lists
+  if (dealt) {
+    std::vector<AddrJob> mine;
+    uint64_t nb = 0;
+    for (size_t i = 0; i < jobs.size(); i++) {
+      if (i % c->comm_world != c->comm_rank) continue;
+      AddrJob j = jobs[i];
+      const uint32_t bpl = (uint32_t)((j.T + kIdxBlock * kIdxRun - 1) / (kIdxBlock * kIdxRun));
+      j.first_block = (uint32_t)nb; nb += bpl;
+      mine.push_back(j);
+    }
+    jobs.swap(mine); blocks = nb;
+  }
+  const size_t count = jobs.size();
   auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
   const size_t o_part = align(sizeof(AddrJob) * count), o_out = align(o_part + sizeof(G1X) * blocks);
   char* ws = nullptr;
@@ -371,8 +388,24 @@ int32_t ja_addr_commit_many(ja_ctx* c, const ja_srs* srs, const ja_addr* const* 
   JA_CUDA(cudaStreamSynchronize(c->stream));
   dev_free(c, ws);
   std::vector<int32_t> inf(count);
-  host::xyzz_batch_to_affine(sums.data(), count, out_xy, inf.data());
-  if (is_inf) memcpy(is_inf, inf.data(), sizeof(int32_t) * count);
+  if (!dealt) {
+    host::xyzz_batch_to_affine(sums.data(), count, out_xy, inf.data());
+    if (is_inf) memcpy(is_inf, inf.data(), sizeof(int32_t) * count);
+    return JA_OK;
+  }
+  const size_t world = c->comm_world, per_rank = (total_lists + world - 1) / world;
+  std::vector<uint64_t> mine(per_rank * 9, 0), all(per_rank * 9 * world);
+  {
+    std::vector<uint64_t> xy(count * 8);
+    host::xyzz_batch_to_affine(sums.data(), count, xy.data(), inf.data());
+    for (size_t j = 0; j < count; j++) { memcpy(&mine[9 * j], &xy[8 * j], 64); mine[9 * j + 8] = (uint64_t)inf[j]; }
+  }
+  if ((st = comm_allgather(c, mine.data(), mine.size() * 8, all.data()))) return st;
+  for (size_t i = 0; i < total_lists; i++) {
+    const uint64_t* src = &all[((i % world) * per_rank + i / world) * 9];
+    memcpy(out_xy + 8 * i, src, 64);
+    if (is_inf) is_inf[i] = (int32_t)src[8];
+  }
   return JA_OK;
 }
 

@@ -1859,9 +1859,13 @@ int32_t ja_bench_fused(ja_ctx* c, int32_t which, int32_t log_n, int32_t iters, f
   return JA_OK;
 }
 
+static int32_t lib_allgather(void* user, const void* send, size_t bytes, void* recv) {
+  return comm_allgather(static_cast<ja_ctx*>(user), send, bytes, recv) == JA_OK ? 0 : -1;
+}
 int32_t ja_set_sumcheck_shard(ja_ctx* c, uint32_t rank, uint32_t world, ja_allgather_fn allgather, void* user) {
   JA_REQUIRE(c && world >= 1 && rank < world && is_pow2(world), "ja_set_sumcheck_shard: world must be a power of two and rank < world");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
+  if (!allgather && world > 1 && c->comm && c->comm_world == world && c->comm_rank == rank) { allgather = lib_allgather; user = c; }   // the context's own communicator
   c->sc_rank = rank; c->sc_world = allgather ? world : 1; c->sc_allgather = allgather; c->sc_user = user;
   return JA_OK;
 }

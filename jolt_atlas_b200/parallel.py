@@ -66,6 +66,42 @@ class Comm:
         return np.stack([o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in out])
 
 
+class LibComm:
+    """The library's OWN exchange (csrc/comm.cu): an NCCL communicator owned by the context, collectives on the context's stream,
+    no torch tensor and no numpy staging in the data path.  torch.distributed is used once, for the rendezvous (broadcast of the
+    128-byte NCCL unique id).  With `shard_on()` every MSM / one-hot commitment of the context is split over the ranks and its
+    partial points are combined INSIDE the library call: the ordinary single-GPU API then runs one proof on all GPUs."""
+    in_library = True
+
+    def __init__(self, ctx):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.plan = ShardPlan(self.rank, self.world)
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            check(lib.ja_comm_unique_id(buf))
+        obj = [buf.raw if self.rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        check(lib.ja_comm_init(ctx._h, self.rank, self.world, obj[0]))
+
+    def all_gather(self, a: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a)
+        out = np.empty((self.world,) + a.shape, dtype=a.dtype)
+        check(self.ctx._lib.ja_comm_allgather(self.ctx._h, a.ctypes.data, a.nbytes, out.ctypes.data))
+        return out
+
+    def shard_on(self):
+        check(self.ctx._lib.ja_set_msm_shard(self.ctx._h, self.rank, self.world))
+
+    def shard_off(self):
+        check(self.ctx._lib.ja_set_msm_shard(self.ctx._h, 0, 1))
+
+    def close(self):
+        self.ctx._lib.ja_comm_free(self.ctx._h)
+
+
 class LocalComm:
     """world == 1 stand-in (and the shape tests use it to run the sharded code path in one process)."""
     rank, world = 0, 1
@@ -249,8 +285,12 @@ def sharded_sumcheck_prove(ctx, kind, slice_polys, claim, transcript, comm, eq_w
     from . import api as A
     n_local = len(slice_polys[0])
     rounds = (n_local * comm.world).bit_length() - 1
-    cb = _allgather_callback(comm)
-    check(ctx._lib.ja_set_sumcheck_shard(ctx._h, comm.rank, comm.world, C.cast(cb, C.c_void_p), None))
+    if getattr(comm, "in_library", False):       # the context's own NCCL communicator: no callback
+        cb = None
+        check(ctx._lib.ja_set_sumcheck_shard(ctx._h, comm.rank, comm.world, None, None))
+    else:
+        cb = _allgather_callback(comm)
+        check(ctx._lib.ja_set_sumcheck_shard(ctx._h, comm.rank, comm.world, C.cast(cb, C.c_void_p), None))
     try:
         arr = (C.c_void_p * len(slice_polys))(*[p._h for p in slice_polys])
         w = A._fr_arg(eq_w).reshape(-1, 4)

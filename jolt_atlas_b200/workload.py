@@ -232,8 +232,11 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
         up = A.OneHotAddresses.upload_many(ctx, parts, K_CHUNK)
         hots = [(up[a], up[b] if b is not None else None) for a, b in where]
     sharded = comm is not None and comm.world > 1
+    in_lib = sharded and getattr(comm, "in_library", False)
+    if in_lib:
+        comm.shard_on()        # from here every MSM / commitment of the context is split over the ranks and combined inside the library
     all_hots = [h for pair in hots for h in pair if h is not None]
-    if sharded:
+    if sharded and not in_lib:
         from . import parallel as PAR0
         out["commitments"] = PAR0.sharded_commit_one_hot_batches(ctx, srs, all_hots, comm)
     else:
@@ -297,7 +300,7 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
     for h in batches:
         rlc.rlc_add_onehot(h, gammas[o:o + h.d])
         o += h.d
-    if sharded:
+    if sharded and not in_lib:
         out["open"] = PAR.sharded_hyperkzg_open(ctx, srs, rlc, r["challenges"], t, comm)
     else:
         out["open"] = A.hyperkzg_open(ctx, srs, rlc, r["challenges"], t)    # PCS::prove(rlc, r_sumcheck), prover.rs:164-170
@@ -308,6 +311,8 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
                 if h is not None:
                     h.free()
     out["states"].append(t.state)
+    if in_lib:
+        comm.shard_off()
     return out
 
 
@@ -421,8 +426,8 @@ def config_dict(config: str, inputs, world: int = 1, shard: bool = False) -> dic
             "l2": "no explicit flush: one pass streams %.0f MB of polynomial data through a 126 MB L2" %
                   (sum(algorithmic_bytes(inputs).values()) / 1e6),
             "parallelism": "1 GPU" if world == 1 else
-                           ("one proof on %d GPUs: commitments sharded by polynomial, opening MSMs by index range (3 all-gathers of points), "
-                            "sumchecks replicated" % world if shard else
+                           ("one proof on %d GPUs: commitments dealt by polynomial, opening MSMs split by index range, partial points exchanged inside the "
+                            "library (ncclAllGather on the context stream), Fiat-Shamir-sequential sumchecks replicated" % world if shard else
                             "%d replicas, one independent proof per GPU (no data-path collective)" % world)}
 
 

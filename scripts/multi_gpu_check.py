@@ -74,7 +74,47 @@ with A.Context(local) as ctx:
                                          claim2, tr_sh, comm, w2)
         assert all(np.array_equal(a, b) for a, b in zip(got["coeffs"], want["coeffs"])), "sharded sumcheck differs"
         assert np.array_equal(got["final_claims"], want["final_claims"]) and tr_one.state == tr_sh.state
+    # 5. the library's own NCCL communicator (csrc/comm.cu): the ORDINARY single-GPU calls run sharded, the exchange is inside them
+    lc = PAR.LibComm(ctx)
+    allg = lc.all_gather(np.arange(5, dtype=np.uint64) + 100 * lc.rank)
+    assert allg.shape == (lc.world, 5) and all(int(allg[r, 0]) == 100 * r for r in range(lc.world)), "ja_comm_allgather"
+    want_msm, want_inf = A.msm_fr(ctx, srs, poly)
+    lc.shard_on()
+    got, ginf = A.msm_fr(ctx, srs, poly)
+    t3 = A.Blake2bTranscriptState(b"open")
+    out3 = A.hyperkzg_open(ctx, srs, poly, point, t3)
+    lc.shard_off()
+    assert ginf == want_inf and np.array_equal(got, want_msm), "in-library sharded MSM differs"
+    for k in ("com", "w", "v"):
+        assert np.array_equal(ref[k], out3[k]), "in-library sharded opening differs in " + k
+    assert t3.state == t1.state
+    # one-hot commitments dealt to the ranks inside ja_addr_commit_many
+    hk = rng.integers(0, 16, size=(5, n // 16), dtype=np.uint32)
+    batches = [A.OneHotAddresses(ctx, hk[:3], 16), A.OneHotAddresses(ctx, hk[3:], 16)]
+    ref_c = A.commit_one_hot_batches(ctx, srs, batches)
+    lc.shard_on()
+    got_c = A.commit_one_hot_batches(ctx, srs, batches)
+    lc.shard_off()
+    for (a, ai), (b, bi) in zip(ref_c, got_c):
+        assert np.array_equal(a, b) and np.array_equal(np.asarray(ai, dtype=bool), np.asarray(bi, dtype=bool)), "in-library dealt commitments differ"
+    # sharded Sumcheck::prove with the partial sums all-gathered by the library
+    for kind, npoly in ((2, 2), (4, 4)):
+        tr_one, tr_sh = A.Blake2bTranscriptState(b"sc"), A.Blake2bTranscriptState(b"sc")
+        want2 = A.sumcheck_prove(ctx, kind, [A.MultilinearPolynomial.from_fr(ctx, host2[i]) for i in range(npoly)], claim2, tr_one, eq_w=w2)
+        got2 = PAR.sharded_sumcheck_prove(ctx, kind, [A.MultilinearPolynomial.from_fr(ctx, host2[i, lo:hi]) for i in range(npoly)],
+                                          claim2, tr_sh, lc, w2)
+        assert all(np.array_equal(a, b) for a, b in zip(got2["coeffs"], want2["coeffs"])), "in-library sharded sumcheck differs"
+        assert np.array_equal(got2["final_claims"], want2["final_claims"]) and tr_one.state == tr_sh.state
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lc.shard_on()
+    for _ in range(3):
+        A.hyperkzg_open(ctx, srs, poly, point, A.Blake2bTranscriptState(b"open"))
+    lc.shard_off()
+    dist.barrier(); t_lib = (time.perf_counter() - t0) / 3
+    lc.close()
     if comm.rank == 0:
+        print("in-library exchange: open sharded %.2f ms" % (t_lib * 1e3), flush=True)
         print("multi-gpu ok: world=%d ell=%d  open sharded %.2f ms vs single-GPU %.2f ms" % (comm.world, ell, t_sh * 1e3, t_one * 1e3), flush=True)
 dist.barrier()
 dist.destroy_process_group()
