@@ -408,20 +408,7 @@ def run_device_arm(args):
             line["speedup_vs_one_gpu"] = round(single_same / (ms_per_step / 1e3), 3)
             line["limiter"] = ("the Fiat-Shamir chain: %d strictly sequential sumcheck rounds run replicated on every rank; only the group "
                                "arithmetic (commitments, opening MSMs) is divided by the number of GPUs" % units["sumcheck_rounds"])
-        # MSM sweep (BASELINE.json config 5: Mscalar/s on random 254-bit scalars, one GPU)
-        msm = []
-        big = SRS.generate(ctx, g1_generator_mont(), tau_mont(), 1 << (10 if (args.no_sweep or world > 1) else 22)).precompute()
-        for log_n in (() if (args.no_sweep or world > 1) else (18, 20, 22)):
-            p = MultilinearPolynomial.random(ctx, 1 << log_n, 7)
-            from jolt_atlas_b200 import msm_fr
-            msm_fr(ctx, big, p)
-            best = 1e9
-            for _ in range(3):
-                ctx.timer_begin(); msm_fr(ctx, big, p); best = min(best, ctx.timer_end())
-            msm.append({"log_n": log_n, "ms": round(best, 3), "Mscalar_per_s": round((1 << log_n) / best / 1e3, 1)})
-            p.free()
-        big.free()
-        line["msm_sweep"] = msm
+        line["msm_sweep"] = []
         if world == 1 and not args.no_cpu:
             from oracle import cpu as ORC
             secs, sample = cpu_pass_seconds(srs.to_host(), inputs, None, 30.0)
@@ -433,8 +420,66 @@ def run_device_arm(args):
                     raise SystemExit("bench.py: the device pass differs from the CPU oracle pass (transcript states / claims / commitments / opening)")
             else:
                 line["parity_checked"] = False   # the oracle only ran a bounded sample of this workload
-    W.free_resident(resident)
-    srs.free()
+    # ---- MSM sweep (BASELINE.json config 5): Mscalar/s on pseudo-random 254-bit scalars.  One GPU: 2^18 .. 2^26 against an SRS
+    # with the fixed-base window tables (up to 2^24: 29x the SRS in HBM) and without them (plain Pippenger, every size), table build
+    # time reported, and a CPU Pippenger column (the oracle, all host cores) at the sizes it finishes in seconds.  N GPUs: the pairs
+    # split by index range over the ranks (ja_set_msm_shard + the library's communicator), on the pass's resident 2^24 SRS.
+    msm_rows = []
+    if not args.no_sweep:
+        from jolt_atlas_b200 import msm_fr
+
+        def time_msm(srs_h, log_n, reps=3):
+            p = MultilinearPolynomial.random(ctx, 1 << log_n, 7)
+            msm_fr(ctx, srs_h, p)
+            best = 1e9
+            for _ in range(reps):
+                barrier()
+                ctx.timer_begin(); msm_fr(ctx, srs_h, p); best = min(best, ctx.timer_end())
+            if world > 1:
+                t = torch.tensor([best], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t.item())
+            p.free()
+            return best
+        if world > 1 and shard:
+            comm.shard_on()
+            for log_n in (20, 22, 24):
+                if (1 << log_n) <= len(srs):
+                    ms = time_msm(srs, log_n)
+                    msm_rows.append({"log_n": log_n, "n_gpus": world, "table": True, "ms": round(ms, 3), "Mscalar_per_s": round((1 << log_n) / ms / 1e3, 1)})
+            comm.shard_off()
+        elif world == 1:
+            W.free_resident(resident); resident = None
+            srs.free(); srs = None
+            for top, sizes, table in ((24, (18, 20, 22, 24), True), (26, (18, 20, 22, 24, 26), False)):
+                t0 = time.perf_counter()
+                big = SRS.generate(ctx, g1_generator_mont(), tau_mont(), 1 << top)
+                ctx.sync()
+                t_gen = time.perf_counter() - t0
+                t_tab = None
+                if table:
+                    t0 = time.perf_counter(); big.precompute(); ctx.sync(); t_tab = time.perf_counter() - t0
+                for log_n in sizes:
+                    ms = time_msm(big, log_n)
+                    msm_rows.append({"log_n": log_n, "n_gpus": 1, "table": table, "srs_log_n": top, "ms": round(ms, 3),
+                                     "Mscalar_per_s": round((1 << log_n) / ms / 1e3, 1), "srs_generate_s": round(t_gen, 2),
+                                     "table_build_s": round(t_tab, 2) if t_tab is not None else None})
+                if table and not args.no_cpu:
+                    from oracle import cpu as ORC
+                    ORC.set_threads(os.cpu_count() or 1)
+                    host_srs = big.to_host(0, 1 << 20)
+                    for log_n in (18, 20):
+                        sc = synthetic_rlc_host(1 << log_n, 5)
+                        t0 = time.perf_counter(); ORC.msm_fr(host_srs[: 1 << log_n], sc); dt = time.perf_counter() - t0
+                        msm_rows.append({"log_n": log_n, "impl": "cpu oracle Pippenger (ark-ec style windows, OpenMP)", "cores": ORC.num_threads(),
+                                         "ms": round(dt * 1e3, 1), "Mscalar_per_s": round((1 << log_n) / dt / 1e6, 3)})
+                big.free()
+    if line is not None:
+        line["msm_sweep"] = msm_rows
+    if resident is not None:
+        W.free_resident(resident)
+    if srs is not None:
+        srs.free()
     ctx.close()
     if world > 1:
         dist.barrier()
