@@ -294,6 +294,32 @@ int32_t ja_poly_zeros(ja_ctx*, size_t n, ja_poly** out);
 int32_t ja_rlc_add_onehot(ja_ctx*, ja_poly* joint, const ja_addr*, const uint64_t* coeffs /* d Fr */);
 int32_t ja_rlc_add_dense(ja_ctx*, ja_poly* joint, const ja_poly* poly, const uint64_t coeff[4]);
 
+/* ---- prefix-suffix Shout: the T-sized passes of the read-raf sumcheck over a 2^LOG_K-entry table (clamp lookups: LOG_K = 64) ----
+ * joltworks/src/subprotocols/ps_shout/mod.rs.  The LOG_K address rounds run in NUM_PHASES phases over m = 2^(LOG_K / NUM_PHASES)-entry
+ * suffix polynomials: O(m) work per round that stays with the caller (prefix MLEs + checkpoints: joltworks/src/lookup_tables/, unchanged).
+ * The device does what scales with T at every phase boundary:
+ *   ja_psshout_new          lookup_indices (T x u64) resident; u_evals = EqPolynomial::evals(r_node_output)        mod.rs:226-267
+ *   ja_psshout_init_phase   init_phase (:269-303): u_evals[j] *= v[phase-1][k_bound(j)] (v_prev = the m-entry expanding table of the
+ *                           finished phase, NULL for phase 0), then init_suffix_polys (:305-335) / RafProverState::init_Q
+ *                           (poly/prefix_suffix.rs:294-351): out_Q[s][y] = sum_j u_evals[j] * suffix_s(suffix_bits(k_j)) over the entries
+ *                           with prefix_bits(k_j) & (m-1) == y, for the n_suffixes suffix kinds listed (read-checking and raf suffixes in
+ *                           one pass).  Suffix kinds = the clamp-table family of lookup_tables/suffixes/ with `bound` = BOUND of the
+ *                           table (31 for SaturationTable, 9 for the ONNX Clamp) and the identity suffix of the raf decomposition.
+ *   ja_psshout_materialize_ra   init_log_t_rounds (:420-446): ra[j] = prod_phase v[phase][k_bound(j, phase)], v = NUM_PHASES x m Fr;
+ *                           the result is the polynomial of the log T cycle rounds (JA_EVAL_IDENT with eq = r_node_output). */
+typedef struct ja_psshout ja_psshout;
+enum { JA_SUF_ONE = 0,               /* suffixes/one.rs */
+       JA_SUF_HIGHER_ALL_ZERO = 1,   /* suffixes/higher_all_zero.rs:9-29 */
+       JA_SUF_HZERO_MUL_LWORD = 2,   /* suffixes/hzero_mul_lword.rs:9-36 */
+       JA_SUF_HONE_MUL_LWORD = 3,    /* suffixes/hone_mul_lword.rs:10-37 */
+       JA_SUF_IDENTITY = 4 };        /* poly/identity_poly.rs (IdentityPolynomial as a SuffixPolynomial: the suffix value) */
+int32_t ja_psshout_new(ja_ctx*, const uint64_t* lookup_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
+                       uint32_t phases, ja_psshout** out);
+int32_t ja_psshout_init_phase(ja_ctx*, ja_psshout*, uint32_t phase, const uint64_t* v_prev, const uint32_t* suffix_kinds, size_t n_suffixes,
+                              uint32_t bound, uint64_t* out_Q /* n_suffixes x m Fr */);
+int32_t ja_psshout_materialize_ra(ja_ctx*, ja_psshout*, const uint64_t* v /* phases x m Fr */, ja_poly** out_ra);
+void ja_psshout_free(ja_ctx*, ja_psshout*);
+
 /* ---- HyperKZG::open (joltworks/src/poly/commitment/hyperkzg/mod.rs:400-447) --------------------------------------
  * Split at the two transcript interaction points so that a Rust caller keeps its own Blake2bTranscript:
  *   begin    Phase 1: l-1 folds Pi[j] = point[l-i-1]*(prev[2j+1]-prev[2j]) + prev[2j] (:413-428) and

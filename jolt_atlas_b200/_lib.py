@@ -87,6 +87,10 @@ SIGNATURES = {
     "ja_set_msm_shard": (C.c_int32, [vp, C.c_uint32, C.c_uint32]),
     "ja_msm_fr_range": (C.c_int32, [vp, vp, vp, C.c_size_t, C.c_size_t, u64p, i32p]),
     "ja_round_eval_slice": (C.c_int32, [vp, C.c_int32, vpp, C.c_size_t, vp, C.c_uint32, C.c_size_t, u64p, C.c_size_t]),
+    "ja_psshout_new": (C.c_int32, [vp, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint32, C.c_uint32, vpp]),
+    "ja_psshout_init_phase": (C.c_int32, [vp, vp, C.c_uint32, u64p, u32p, C.c_size_t, C.c_uint32, u64p]),
+    "ja_psshout_materialize_ra": (C.c_int32, [vp, vp, u64p, vpp]),
+    "ja_psshout_free": (None, [vp, vp]),
     "ja_comm_unique_id": (C.c_int32, [C.c_char_p]),
     "ja_comm_init": (C.c_int32, [vp, C.c_uint32, C.c_uint32, C.c_char_p]),
     "ja_comm_free": (None, [vp]),

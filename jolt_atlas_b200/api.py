@@ -633,6 +633,43 @@ def commit_one_hot_batches(ctx: Context, srs: SRS, batches):
     return res
 
 
+class SuffixKind:
+    """Suffix MLEs of the clamp-table family (joltworks/src/lookup_tables/suffixes/) and the identity suffix of the raf decomposition."""
+    ONE, HIGHER_ALL_ZERO, HZERO_MUL_LWORD, HONE_MUL_LWORD, IDENTITY = 0, 1, 2, 3, 4
+
+
+class PrefixSuffixShout:
+    """The T-sized passes of ReadRafSumcheckProver (joltworks/src/subprotocols/ps_shout/mod.rs): lookup indices and u_evals resident on
+    the device; init_phase(phase, v_prev) -> the m-entry suffix polynomials Q of the phase; materialize_ra(v) -> the cycle-round polynomial."""
+
+    def __init__(self, ctx: Context, lookup_indices, r_cycle, log_k: int = 64, phases: int = 8):
+        idx = np.ascontiguousarray(lookup_indices, dtype=np.uint64)
+        r = _fr_arg(r_cycle).reshape(-1, 4)
+        self.ctx, self.T, self.log_k, self.phases, self.m = ctx, idx.shape[0], log_k, phases, 1 << (log_k // phases)
+        h = C.c_void_p()
+        check(ctx._lib.ja_psshout_new(ctx._h, _u64p(idx), idx.shape[0], _u64p(r), r.shape[0], log_k, phases, C.byref(h)))
+        self._h = h
+
+    def init_phase(self, phase: int, v_prev, suffix_kinds, bound: int) -> np.ndarray:
+        kinds = np.ascontiguousarray(suffix_kinds, dtype=np.uint32)
+        out = np.empty((kinds.shape[0], self.m, 4), dtype=np.uint64)
+        v = _fr_arg(v_prev).reshape(-1, 4) if v_prev is not None else None
+        check(self.ctx._lib.ja_psshout_init_phase(self.ctx._h, self._h, phase, _u64p(v) if v is not None else None,
+                                                  kinds.ctypes.data_as(_lib.u32p), kinds.shape[0], bound, _u64p(out)))
+        return out
+
+    def materialize_ra(self, v) -> "MultilinearPolynomial":
+        v = _fr_arg(v).reshape(self.phases * self.m, 4)
+        h = C.c_void_p()
+        check(self.ctx._lib.ja_psshout_materialize_ra(self.ctx._h, self._h, _u64p(v), C.byref(h)))
+        return MultilinearPolynomial(self.ctx, h)
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_psshout_free(self.ctx._h, self._h)
+            self._h = None
+
+
 class InstanceKind:
     BOOLEANITY, HAMMING_TABLES, OPENING_ONEHOT = 32, 33, 34
 

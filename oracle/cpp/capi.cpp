@@ -10,6 +10,7 @@
 #include <vector>
 #include "sumcheck.hpp"
 #include "hyperkzg.hpp"
+#include "psshout.hpp"
 
 using namespace orc;
 
@@ -204,6 +205,31 @@ int orc_batched_sumcheck_prove(const orc_inst* descs, size_t n, uint8_t state[32
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
   return (int)pf.compressed_polys.size();
 }
+// ---- prefix-suffix Shout, T-sized passes (psshout.hpp) ------------------------------------------------------------------------
+void* orc_psshout_new(const uint64_t* idx, size_t T, const uint64_t* r_cycle, size_t log_t, unsigned log_k, unsigned phases) {
+  PsShout* p = new PsShout();
+  p->idx.assign(idx, idx + T);
+  FrVec r = load_fr(r_cycle, log_t);
+  p->u = eq_evals(r.data(), log_t);                 // u_evals = EqPolynomial::evals(r_node_output), mod.rs:236
+  p->log_k = log_k; p->phases = phases; p->log_m = log_k / phases;
+  return p;
+}
+void orc_psshout_init_phase(void* h, unsigned phase, const uint64_t* v_prev, const uint32_t* kinds, size_t n_suf, unsigned bound, uint64_t* out_Q) {
+  PsShout* p = static_cast<PsShout*>(h);
+  const size_t m = size_t(1) << p->log_m;
+  FrVec v = v_prev ? load_fr(v_prev, m) : FrVec();
+  std::vector<Fr> Q = p->init_phase(phase, v_prev ? v.data() : nullptr, kinds, n_suf, bound);
+  for (size_t i = 0; i < Q.size(); i++) store_fr(out_Q + 4 * i, Q[i]);
+}
+void orc_psshout_materialize_ra(void* h, const uint64_t* v, uint64_t* out) {
+  PsShout* p = static_cast<PsShout*>(h);
+  FrVec vv = load_fr(v, (size_t)p->phases << p->log_m);
+  std::vector<Fr> ra = p->materialize_ra(vv.data());
+  for (size_t i = 0; i < ra.size(); i++) store_fr(out + 4 * i, ra[i]);
+}
+void orc_psshout_free(void* h) { delete static_cast<PsShout*>(h); }
+uint64_t orc_suffix_mle(int kind, uint64_t bits, unsigned len, unsigned xlen, unsigned bound) { return suffix_mle(kind, bits, len, xlen, bound); }
+
 // compute_ra_evals (shout.rs:549-598): idx = d x T addresses, out = d x K Fr
 void orc_compute_ra_evals(const uint32_t* idx, size_t d, size_t T, size_t K, const uint64_t* r_cycle, size_t log_t, uint64_t* out) {
   std::vector<std::vector<uint32_t>> ix(d);

@@ -326,3 +326,38 @@ def eval_reduction_h(mle: np.ndarray, points: np.ndarray) -> np.ndarray:
     k = fn(_p(mle), C.c_size_t(mle.shape[0]), _p(pts), C.c_size_t(n), C.c_size_t(m), _p(out), C.c_size_t(out.shape[0]))
     assert k > 0
     return out[:k]
+
+
+class PsShout:
+    """T-sized passes of the prefix-suffix Shout prover (oracle/cpp/psshout.hpp; ps_shout/mod.rs:269-335,420-446)."""
+
+    def __init__(self, lookup_indices, r_cycle, log_k: int = 64, phases: int = 8):
+        idx = np.ascontiguousarray(lookup_indices, dtype=np.uint64)
+        r = np.ascontiguousarray(r_cycle, dtype=np.uint64).reshape(-1, 4)
+        self.T, self.phases, self.m = idx.shape[0], phases, 1 << (log_k // phases)
+        fn = lib().orc_psshout_new
+        fn.restype = C.c_void_p
+        self._h = C.c_void_p(fn(_p(idx), C.c_size_t(idx.shape[0]), _p(r), C.c_size_t(r.shape[0]), C.c_uint(log_k), C.c_uint(phases)))
+
+    def init_phase(self, phase: int, v_prev, suffix_kinds, bound: int) -> np.ndarray:
+        kinds = np.ascontiguousarray(suffix_kinds, dtype=np.uint32)
+        out = np.empty((kinds.shape[0], self.m, 4), dtype=np.uint64)
+        v = _p(np.ascontiguousarray(v_prev, dtype=np.uint64)) if v_prev is not None else None
+        lib().orc_psshout_init_phase(self._h, C.c_uint(phase), v, _p(kinds), C.c_size_t(kinds.shape[0]), C.c_uint(bound), _p(out))
+        return out
+
+    def materialize_ra(self, v) -> np.ndarray:
+        out = np.empty((self.T, 4), dtype=np.uint64)
+        lib().orc_psshout_materialize_ra(self._h, _p(np.ascontiguousarray(v, dtype=np.uint64)), _p(out))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().orc_psshout_free(self._h)
+            self._h = None
+
+
+def suffix_mle(kind: int, bits: int, length: int, xlen: int, bound: int) -> int:
+    fn = lib().orc_suffix_mle
+    fn.restype = C.c_uint64
+    return int(fn(C.c_int(kind), C.c_uint64(bits), C.c_uint(length), C.c_uint(xlen), C.c_uint(bound)))
