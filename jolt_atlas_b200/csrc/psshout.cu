@@ -16,7 +16,6 @@
 
 namespace {
 
-constexpr int kPsTile = 1024;        // entries per block
 constexpr int kPsMaxSuffixes = 8;
 
 // suffix MLEs of the clamp-table family (joltworks/src/lookup_tables/suffixes/{higher_all_zero,hzero_mul_lword,hone_mul_lword,one}.rs)
@@ -45,56 +44,109 @@ struct PsPhaseArgs {
   uint32_t prev_shift;             // k_bound of the previous phase = (k >> prev_shift) & m_mask
   uint32_t suffix_len, m_mask, bound, n_suf;
   uint32_t kinds[kPsMaxSuffixes];
-  Fr* partial;                     // [tiles][n_suf][m]
+  Fr* partial;                     // [gridDim.x][n_suf][m]
 };
+constexpr int kPsLimbs = 12;         // 32-bit limbs of an accumulator
+constexpr int kPsCols = 2 * kPsLimbs;  // ... held as 16-bit columns in 32-bit counters (native shared-memory atomics)
 
+// Scatter-add by an 8-bit key with INTEGER atomics on shared memory.  A (bin, suffix) accumulator is 24 columns: column c counts
+// the 16-bit digits of weight 2^(16 c) of the plain integer products u * t (u a Montgomery residue < p, t < 2^64 in two 32-bit
+// halves), so no carry is ever resolved atomically (a 32-bit counter takes 2^16 digits; a block sees at most 2^16 entries) and one
+// carry propagation + one Montgomery fold per accumulator finishes the block.  Every lane works on its own entry.  Skewed keys - a
+// 64-bit clamp lookup sends almost every entry of the early phases to the bins 0x00 / 0xff - would serialise the atomics, so lanes
+// of a warp that share a key in groups of 8 or more add their columns with warp reductions first and one lane issues the atomics.
+template <int NSUF>
 __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
-  __shared__ Fr s_u[kPsTile];
-  __shared__ unsigned long long s_suf[kPsTile];
-  __shared__ unsigned short s_key[kPsTile];
-  const size_t t0 = (size_t)blockIdx.x * kPsTile;
+  extern __shared__ unsigned int s_acc[];                // [m][NSUF][kPsCols]
   const uint32_t m = a.m_mask + 1;
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kPsTile; i += blockDim.x) {
-    const size_t j = t0 + i;
-    if (j < a.T) {
-      const unsigned long long k = a.idx[j];
-      Fr u = fp_load(a.u + j);
+  const uint32_t n_acc = m * NSUF;
+  for (uint32_t i = threadIdx.x; i < n_acc * kPsCols; i += blockDim.x) s_acc[i] = 0u;
+  __syncthreads();
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < a.T; base += stride) {       // uniform trip count: every lane joins the warp votes
+    const size_t j = base + threadIdx.x;
+    const bool valid = j < a.T;
+    unsigned long long k = 0;
+    Fr u = fp_zero<FrParams>();
+    if (valid) {
+      k = a.idx[j];
+      u = fp_load(a.u + j);
       if (a.v_prev) {                                                   // init_phase: u_evals[j] *= v[phase - 1][k_bound]
         u = fp_mul<FrParams>(u, fp_load(a.v_prev + ((k >> a.prev_shift) & a.m_mask)));
         fp_store(a.u + j, u);
       }
-      s_u[i] = u;
-      s_suf[i] = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
-      s_key[i] = (unsigned short)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask);
-    } else {
-      s_key[i] = 0xffff;
+    }
+    const unsigned long long sb = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
+    const uint32_t key = valid ? (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(full, key);
+    const bool big = valid && __popc(peers) >= 8;
+    const unsigned big_leaders = __ballot_sync(full, big && (peers & ((1u << lane) - 1)) == 0);
+#pragma unroll
+    for (int s = 0; s < NSUF; s++) {
+      const unsigned long long t = valid ? suffix_mle(a.kinds[s], sb, a.suffix_len, a.bound) : 0ull;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint32_t th = h == 0 ? (uint32_t)t : (uint32_t)(t >> 32);
+        if (!__any_sync(full, th != 0)) continue;
+        uint32_t col[9];
+        {
+          unsigned long long c = 0;
+#pragma unroll
+          for (int i = 0; i < 8; i++) { c += (unsigned long long)u.l[i] * th; col[i] = (uint32_t)c; c >>= 32; }   // c < 2^64: (2^32-1)^2 + (2^32-1)
+          col[8] = (uint32_t)c;
+        }
+        unsigned rem = big_leaders;
+        while (rem) {                                                   // at most 4 groups of 8 or more lanes
+          const int src = __ffs(rem) - 1;
+          rem &= rem - 1;
+          const uint32_t gkey = __shfl_sync(full, key, src);
+          const bool mine = key == gkey;
+          unsigned int* acc = s_acc + ((size_t)gkey * NSUF + s) * kPsCols + 2 * h;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            const uint32_t v = mine ? col[i] : 0u;
+            const unsigned lo = __reduce_add_sync(full, v & 0xffffu), hi = __reduce_add_sync(full, v >> 16);
+            if (lane == src) { if (lo) atomicAdd(acc + 2 * i, lo); if (hi) atomicAdd(acc + 2 * i + 1, hi); }
+          }
+        }
+        if (valid && !big && th != 0) {
+          unsigned int* acc = s_acc + ((size_t)key * NSUF + s) * kPsCols + 2 * h;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            if (col[i] & 0xffffu) atomicAdd(acc + 2 * i, col[i] & 0xffffu);
+            if (col[i] >> 16) atomicAdd(acc + 2 * i + 1, col[i] >> 16);
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  const uint32_t bin = threadIdx.x;
-  Acc320 acc[kPsMaxSuffixes];
-  Fr wide[kPsMaxSuffixes];            // suffix values beyond 32 bits (Identity): plain field accumulation
+  // accumulator -> field element: carry-propagate the 16-bit columns into a 384+ bit integer X = lo + hi 2^256, X mod p = mont(1_mont, lo) + mont(R^2, hi)
+  for (uint32_t q = threadIdx.x; q < n_acc; q += blockDim.x) {
+    const unsigned int* acc = s_acc + (size_t)q * kPsCols;
+    uint32_t w[kPsLimbs + 1];
+    unsigned long long c = 0;
 #pragma unroll
-  for (int s = 0; s < kPsMaxSuffixes; s++) { acc[s] = acc320_zero(); wide[s] = fp_zero<FrParams>(); }
-  if (bin < m) {
-    for (int i = 0; i < kPsTile; i++) {
-      if (s_key[i] != bin) continue;
-      const Fr u = s_u[i];
-      const unsigned long long sb = s_suf[i];
-#pragma unroll
-      for (int s = 0; s < kPsMaxSuffixes; s++) {
-        if ((uint32_t)s >= a.n_suf) break;
-        const unsigned long long t = suffix_mle(a.kinds[s], sb, a.suffix_len, a.bound);
-        if (t == 0) continue;
-        if (t >> 32) wide[s] = fp_add<FrParams>(wide[s], fp_mul_u64<FrParams>(u, t));
-        else acc320_mad(acc[s], u, (uint32_t)t);
-      }
+    for (int i = 0; i < kPsLimbs; i++) {
+      c += acc[2 * i];
+      const uint32_t d0 = (uint32_t)(c & 0xffffu);
+      c >>= 16;
+      c += acc[2 * i + 1];
+      const uint32_t d1 = (uint32_t)(c & 0xffffu);
+      c >>= 16;
+      w[i] = d0 | (d1 << 16);
     }
+    w[kPsLimbs] = (uint32_t)c;
+    Fr lo, hi = fp_zero<FrParams>();
 #pragma unroll
-    for (int s = 0; s < kPsMaxSuffixes; s++) {
-      if ((uint32_t)s >= a.n_suf) break;
-      fp_store(a.partial + ((size_t)blockIdx.x * a.n_suf + s) * m + bin, fp_add<FrParams>(acc320_reduce(acc[s]), wide[s]));
-    }
+    for (int i = 0; i < 8; i++) lo.l[i] = w[i];
+#pragma unroll
+    for (int i = 0; i < 5; i++) hi.l[i] = w[8 + i];
+    const Fr val = fp_add<FrParams>(fp_mul<FrParams>(fp_one<FrParams>(), lo), fp_mul<FrParams>(fp_r2<FrParams>(), hi));
+    const uint32_t key = q / NSUF, sfx = q % NSUF;
+    fp_store(a.partial + ((size_t)blockIdx.x * NSUF + sfx) * m + key, val);
   }
 }
 
@@ -164,8 +216,12 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   const uint32_t m = 1u << p->log_m;
-  const uint32_t tiles = (uint32_t)((p->T + kPsTile - 1) / kPsTile);
+  uint32_t tiles = (uint32_t)((p->T + 1023) / 1024);                    // at least 4 entries per thread, at most one block per SM
+  if (tiles > (uint32_t)kSMs) tiles = kSMs;
+  JA_REQUIRE((p->T + tiles - 1) / tiles <= 65536, "ja_psshout_init_phase: T too large for the 16-bit column counters");
   const size_t n_out = n_suffixes * m;
+  const size_t smem = n_out * kPsCols * sizeof(unsigned int);
+  JA_REQUIRE(smem <= 180 * 1024, "ja_psshout_init_phase: too many suffixes for the shared-memory accumulators");
   Fr *d_v = nullptr, *d_part = nullptr, *d_out = nullptr;
   int32_t st;
   if ((st = dev_alloc(c, (size_t)tiles * n_out * sizeof(Fr), (void**)&d_part))) return st;
@@ -182,11 +238,16 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   a.m_mask = m - 1; a.bound = bound; a.n_suf = (uint32_t)n_suffixes;
   for (size_t s = 0; s < n_suffixes; s++) a.kinds[s] = suffix_kinds[s];
   a.partial = d_part;
-  JA_LAUNCH(c, KC_SCATTER, k_ps_phase<<<tiles, 256, 0, c->stream>>>(a));
+#define JA_PS(N) case N: { JA_CUDA(cudaFuncSetAttribute(k_ps_phase<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); \
+                            JA_LAUNCH(c, KC_SCATTER, k_ps_phase<N><<<tiles, 256, smem, c->stream>>>(a)); break; }
+  switch (n_suffixes) { JA_PS(1) JA_PS(2) JA_PS(3) JA_PS(4) JA_PS(5) JA_PS(6) JA_PS(7) default: JA_PS(8) }
+#undef JA_PS
   JA_LAUNCH(c, KC_SCATTER, k_ps_phase_final<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(d_part, tiles, (uint32_t)n_out, d_out));
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_Q, d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream);
+  const bool pinned = n_out * sizeof(Fr) <= kPinnedBytes;              // pinned staging: a D2H into pageable memory is staged by the driver and slow
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pinned ? (void*)c->h_pinned : (void*)out_Q, d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess && pinned) memcpy(out_Q, c->h_pinned, n_out * sizeof(Fr));
   dev_free(c, d_part); dev_free(c, d_out); dev_free(c, d_v);
   if (e != cudaSuccess) return fail(JA_ERR_CUDA, std::string("ja_psshout_init_phase: ") + cudaGetErrorString(e));
   p->next_phase = phase + 1;

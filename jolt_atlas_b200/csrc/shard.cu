@@ -68,6 +68,30 @@ void ja_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
 }
 
+void ja_transcript_challenge_optimized(uint8_t state[32], uint32_t* n_rounds, uint64_t out[4]) {
+  host::Blake2bTranscript t(state, *n_rounds);
+  t.challenge_scalar_optimized(out);                                // blake2b.rs:233-238: 125-bit challenge {0, 0, lo, hi}
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+// ExpandingTable (joltworks/src/utils/expanding_table.rs:62-89) after `n` updates with the given challenges, starting from [1]:
+// HighToLow: values[2i] = v[i] - r v[i], values[2i+1] = r v[i]  (the first challenge ends up in the top index bit);
+// LowToHigh: values[i] = v[i] - r v[i], values[i + len] = r v[i].  out = 2^n Fr.  Host-only O(2^n) glue (n = 8 per ps_shout phase).
+int32_t ja_expanding_table(const uint64_t* challenges, size_t n, int32_t order, uint64_t* out) {
+  JA_REQUIRE((challenges || n == 0) && out && n <= 20, "ja_expanding_table: bad argument");
+  std::vector<FrH> v{host::FR_ONE};
+  for (size_t j = 0; j < n; j++) {
+    const FrH r = host::from_limbs(challenges + 4 * j);
+    std::vector<FrH> nv(v.size() * 2);
+    for (size_t i = 0; i < v.size(); i++) {
+      const FrH e1 = host::mul(r, v[i]), e0 = host::sub(v[i], e1);
+      if (order == JA_HIGH_TO_LOW) { nv[2 * i] = e0; nv[2 * i + 1] = e1; } else { nv[i] = e0; nv[i + v.size()] = e1; }
+    }
+    v.swap(nv);
+  }
+  memcpy(out, v.data(), v.size() * 32);
+  return JA_OK;
+}
+
 // ---- evaluation reduction (joltworks/src/subprotocols/evaluation_reduction.rs:91-148, :223-249) --------------------------
 // h = mle o l, where l is the degree n-1 curve through the n opening points (l(i) = point i, one UniPoly::from_evals per
 // variable, :213-221).  The reference folds the table with POLYNOMIAL-valued entries, serially; h is the unique polynomial

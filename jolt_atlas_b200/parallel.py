@@ -182,10 +182,25 @@ class Transcript:
         self._lib.ja_transcript_challenge_scalar(self._st, C.byref(self._nr), out.ctypes.data_as(_lib.u64p))
         return out
 
+    def challenge_optimized(self, n: int = 1) -> np.ndarray:
+        """n x challenge_scalar_optimized (blake2b.rs:233-238): (n, 4) limbs {0, 0, lo, hi}."""
+        out = np.zeros((n, 4), dtype=np.uint64)
+        for i in range(n):
+            self._lib.ja_transcript_challenge_optimized(self._st, C.byref(self._nr), out[i].ctypes.data_as(_lib.u64p))
+        return out
+
     def challenge_scalar_powers(self, n: int) -> np.ndarray:
         out = np.zeros((n, 4), dtype=np.uint64)
         self._lib.ja_transcript_challenge_scalar_powers(self._st, C.byref(self._nr), n, out.ctypes.data_as(_lib.u64p))
         return out
+
+
+def expanding_table(challenges: np.ndarray, order: int = 1) -> np.ndarray:
+    """ExpandingTable after len(challenges) updates from [1] (utils/expanding_table.rs:62-89); order 1 = HighToLow."""
+    ch = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty((1 << ch.shape[0], 4), dtype=np.uint64)
+    check(_lib.load().ja_expanding_table(ch.ctypes.data_as(_lib.u64p), ch.shape[0], order, out.ctypes.data_as(_lib.u64p)))
+    return out
 
 
 # ---- sharded device operations ---------------------------------------------------------------------------------------------

@@ -289,6 +289,23 @@ void orc_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_round
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
 }
 
+void orc_transcript_challenge_optimized(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out) {
+  Transcript t(state, *n_rounds);
+  for (size_t i = 0; i < n; i++) t.challenge_optimized(out + 4 * i);       // blake2b.rs:233-238
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+// ExpandingTable::update, HighToLow (utils/expanding_table.rs:76-86), n updates from [1]
+void orc_expanding_table_h2l(const uint64_t* challenges, size_t n, uint64_t* out) {
+  std::vector<Fr> v{Fr::one()};
+  for (size_t j = 0; j < n; j++) {
+    const Fr r = Fr::from_raw(challenges + 4 * j);
+    std::vector<Fr> nv(v.size() * 2);
+    for (size_t i = 0; i < v.size(); i++) { const Fr e1 = r * v[i]; nv[2 * i] = v[i] - e1; nv[2 * i + 1] = e1; }
+    v.swap(nv);
+  }
+  for (size_t i = 0; i < v.size(); i++) store_fr(out + 4 * i, v[i]);
+}
+
 // ---- curve / MSM ----
 void orc_srs_powers(const uint64_t tau_mont[4], size_t n, uint64_t* out_xy) {
   std::vector<G1Affine> s = srs_powers(Fr::from_raw(tau_mont), n);

@@ -361,3 +361,19 @@ def suffix_mle(kind: int, bits: int, length: int, xlen: int, bound: int) -> int:
     fn = lib().orc_suffix_mle
     fn.restype = C.c_uint64
     return int(fn(C.c_int(kind), C.c_uint64(bits), C.c_uint(length), C.c_uint(xlen), C.c_uint(bound)))
+
+
+def transcript_challenge_optimized(t: TranscriptState, n: int) -> np.ndarray:
+    out = np.zeros((n, 4), dtype=np.uint64)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    lib().orc_transcript_challenge_optimized(st, C.byref(nr), C.c_size_t(n), _p(out))
+    t.state, t.n_rounds = st.raw, nr.value
+    return out
+
+
+def expanding_table_h2l(challenges: np.ndarray) -> np.ndarray:
+    ch = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty((1 << ch.shape[0], 4), dtype=np.uint64)
+    lib().orc_expanding_table_h2l(_p(ch), C.c_size_t(ch.shape[0]), _p(out))
+    return out

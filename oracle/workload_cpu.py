@@ -43,9 +43,18 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
             if hi > lo:
                 coms = [ORC.sum_indexed(srs_host, idx) for idx in lists[lo:hi]]
                 out["commitments"].append((np.stack([c[0] for c in coms]), np.array([c[1] for c in coms])))
-        ra0 = _ra_checks(ni, 0, D_CLAMP, claim, t, out)
-        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra0]), ni.eq_w, claim, t)
+        # clamp lookup read-raf: ps_shout phase passes, each phase represented by its transcript traffic (see workload.run_device)
+        ps = ORC.PsShout(ni.acc, ni.eq_w, 64, 8)
+        vs = []
+        for phase in range(8):
+            Q = ps.init_phase(phase, vs[-1] if phase else None, (1, 2, 3, 0, 0, 4), 31)
+            ORC.transcript_append_scalars(t, Q[:, 0])
+            vs.append(ORC.expanding_table_h2l(ORC.transcript_challenge_optimized(t, 8)))
+        ra_ps = ps.materialize_ra(np.concatenate(vs))
+        ps.free()
+        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra_ps]), ni.eq_w, claim, t)
         out["finals"].append(r["final_claims"])
+        _ra_checks(ni, 0, D_CLAMP, claim, t, out)
         if spec.kind == "einsum":
             left = ORC.tensor_fold_i32(ni.A, ORC.eq_evals(ni.eq_rows), False)
             right = ORC.tensor_fold_i32(ni.B, ORC.eq_evals(ni.eq_cols), True)
