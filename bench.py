@@ -348,6 +348,15 @@ def run_device_arm(args):
         ms = float(t.item())
     ms_per_step = ms / args.steps
 
+    # ---- continuity leg (one GPU): the ROUND-1 stage list (no ps_shout phase passes), resident inputs, same timing rules ----
+    r1_ms = None
+    if world == 1:
+        W.run_device(ctx, srs, inputs, resident=resident, ps_shout=False)
+        barrier()
+        ctx.timer_begin()
+        for _ in range(args.steps):
+            W.run_device(ctx, srs, inputs, resident=resident, ps_shout=False)
+        r1_ms = ctx.timer_end() / args.steps
     # ---- end-to-end leg: host buffers in, proof data out, every step ----
     W.run_device(ctx, srs, inputs, comm=comm)          # warm the upload path
     barrier()
@@ -403,6 +412,8 @@ def run_device_arm(args):
                 "wall_ms_per_step": wall_ms / args.steps,
                 "units_per_step": units,
                 "roofline": roof["dominant"], "kernel_classes": roof["classes"], "kernel_sweep": roof["sweep"]}
+        if r1_ms is not None:
+            line["value_round1_stage_list_s"] = r1_ms / 1e3      # the same pass WITHOUT the ps_shout phase passes added in round 2 (BENCH_r01's workload)
         if shard:
             line["one_gpu_same_config_s"] = single_same          # this config on one GPU of the same box, same run
             line["speedup_vs_one_gpu"] = round(single_same / (ms_per_step / 1e3), 3)

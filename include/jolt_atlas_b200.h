@@ -383,7 +383,7 @@ void ja_transcript_append_points(uint8_t state[32], uint32_t* n_rounds, const ui
 void ja_transcript_append_scalars(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n);
 void ja_transcript_challenge_scalar(uint8_t state[32], uint32_t* n_rounds, uint64_t out[4]);
 void ja_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out);
-void ja_transcript_challenge_optimized(uint8_t state[32], uint32_t* n_rounds, uint64_t out[4]);   /* challenge_scalar_optimized: {0,0,lo,hi} */
+void ja_transcript_challenge_optimized(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out);   /* n x challenge_scalar_optimized: {0,0,lo,hi} each */
 /* ExpandingTable (joltworks/src/utils/expanding_table.rs:62-89) after n updates from [1]: out = 2^n Fr.  Host-only O(2^n) glue
  * (the expanding tables v[phase] of ps_shout and the F tables of the one-hot address rounds). */
 int32_t ja_expanding_table(const uint64_t* challenges, size_t n, int32_t order, uint64_t* out);

@@ -102,7 +102,7 @@ SIGNATURES = {
     "ja_transcript_append_scalars": (None, [C.c_char_p, u32p, u64p, C.c_size_t]),
     "ja_transcript_challenge_scalar": (None, [C.c_char_p, u32p, u64p]),
     "ja_transcript_challenge_scalar_powers": (None, [C.c_char_p, u32p, C.c_size_t, u64p]),
-    "ja_transcript_challenge_optimized": (None, [C.c_char_p, u32p, u64p]),
+    "ja_transcript_challenge_optimized": (None, [C.c_char_p, u32p, C.c_size_t, u64p]),
     "ja_expanding_table": (C.c_int32, [u64p, C.c_size_t, C.c_int32, u64p]),
     "ja_profile_begin": (C.c_int32, [vp]),
     "ja_profile_end": (C.c_int32, [vp, u64p, C.POINTER(C.c_double), C.c_size_t]),

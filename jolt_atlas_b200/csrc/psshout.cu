@@ -45,16 +45,27 @@ struct PsPhaseArgs {
   uint32_t suffix_len, m_mask, bound, n_suf;
   uint32_t kinds[kPsMaxSuffixes];
   Fr* partial;                     // [gridDim.x][n_suf][m]
+  unsigned int* counter;           // zero on entry, reset on exit
+  Fr* host_out;                    // n_suf x m results, host-mapped
+  volatile unsigned int* host_seq; unsigned int seq_value;
 };
+JA_DEV Fr fr_ld_cg(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+  Fr r;
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
 constexpr int kPsLimbs = 12;         // 32-bit limbs of an accumulator
 constexpr int kPsCols = 2 * kPsLimbs;  // ... held as 16-bit columns in 32-bit counters (native shared-memory atomics)
 
 // Scatter-add by an 8-bit key with INTEGER atomics on shared memory.  A (bin, suffix) accumulator is 24 columns: column c counts
 // the 16-bit digits of weight 2^(16 c) of the plain integer products u * t (u a Montgomery residue < p, t < 2^64 in two 32-bit
-// halves), so no carry is ever resolved atomically (a 32-bit counter takes 2^16 digits; a block sees at most 2^16 entries) and one
-// carry propagation + one Montgomery fold per accumulator finishes the block.  Every lane works on its own entry.  Skewed keys - a
-// 64-bit clamp lookup sends almost every entry of the early phases to the bins 0x00 / 0xff - would serialise the atomics, so lanes
-// of a warp that share a key in groups of 8 or more add their columns with warp reductions first and one lane issues the atomics.
+// halves), so no carry is ever resolved atomically and one carry propagation + one Montgomery fold per accumulator finishes the
+// block.  A thread takes kPsRun CONSECUTIVE entries and adds their limb columns in registers for as long as the key stays the same
+// (clamp lookups send almost every entry of the early phases to the bins 0x00 / 0xff: one flush per thread, suffix and half
+// instead of one per entry), then flushes the run with native 32-bit shared-memory atomics.
+constexpr int kPsRun = 2;
 template <int NSUF>
 __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
   extern __shared__ unsigned int s_acc[];                // [m][NSUF][kPsCols]
@@ -62,62 +73,60 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
   const uint32_t n_acc = m * NSUF;
   for (uint32_t i = threadIdx.x; i < n_acc * kPsCols; i += blockDim.x) s_acc[i] = 0u;
   __syncthreads();
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < a.T; base += stride) {       // uniform trip count: every lane joins the warp votes
-    const size_t j = base + threadIdx.x;
-    const bool valid = j < a.T;
-    unsigned long long k = 0;
-    Fr u = fp_zero<FrParams>();
-    if (valid) {
-      k = a.idx[j];
-      u = fp_load(a.u + j);
-      if (a.v_prev) {                                                   // init_phase: u_evals[j] *= v[phase - 1][k_bound]
-        u = fp_mul<FrParams>(u, fp_load(a.v_prev + ((k >> a.prev_shift) & a.m_mask)));
-        fp_store(a.u + j, u);
+  const size_t chunk = (size_t)blockDim.x * kPsRun;
+  for (size_t base = (size_t)blockIdx.x * chunk; base < a.T; base += (size_t)gridDim.x * chunk) {
+    Fr u[kPsRun];
+    unsigned long long sb[kPsRun];
+    uint32_t key[kPsRun];
+#pragma unroll
+    for (int e = 0; e < kPsRun; e++) {
+      const size_t j = base + (size_t)threadIdx.x * kPsRun + e;
+      key[e] = 0xffffffffu; sb[e] = 0ull; u[e] = fp_zero<FrParams>();
+      if (j < a.T) {
+        const unsigned long long k = a.idx[j];
+        u[e] = fp_load(a.u + j);
+        if (a.v_prev) {                                                 // init_phase: u_evals[j] *= v[phase - 1][k_bound]
+          u[e] = fp_mul<FrParams>(u[e], fp_load(a.v_prev + ((k >> a.prev_shift) & a.m_mask)));
+          fp_store(a.u + j, u[e]);
+        }
+        sb[e] = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
+        key[e] = (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask);
       }
     }
-    const unsigned long long sb = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
-    const uint32_t key = valid ? (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask) : 0xffffffffu;
-    const unsigned peers = __match_any_sync(full, key);
-    const bool big = valid && __popc(peers) >= 8;
-    const unsigned big_leaders = __ballot_sync(full, big && (peers & ((1u << lane) - 1)) == 0);
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < NSUF; s++) {
-      const unsigned long long t = valid ? suffix_mle(a.kinds[s], sb, a.suffix_len, a.bound) : 0ull;
+      const int halves = (a.kinds[s] == JA_SUF_IDENTITY && a.suffix_len > 32) ? 2 : 1;     // only the identity suffix exceeds 32 bits
+#pragma unroll 1
+      for (int h = 0; h < halves; h++) {
+        unsigned long long acc[9];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const uint32_t th = h == 0 ? (uint32_t)t : (uint32_t)(t >> 32);
-        if (!__any_sync(full, th != 0)) continue;
-        uint32_t col[9];
-        {
+        for (int i = 0; i < 9; i++) acc[i] = 0ull;
+        uint32_t cur = 0xffffffffu;
+        bool dirty = false;
+#pragma unroll
+        for (int e = 0; e <= kPsRun; e++) {
+          const uint32_t ke = e < kPsRun ? key[e] : 0xffffffffu;
+          if (dirty && ke != cur) {                                      // the run ends: flush it
+            unsigned int* dst = s_acc + ((size_t)cur * NSUF + s) * kPsCols + 2 * h;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+              const unsigned int lo = (unsigned int)(acc[i] & 0xffffull), hi = (unsigned int)(acc[i] >> 16);
+              if (lo) atomicAdd(dst + 2 * i, lo);
+              if (hi) atomicAdd(dst + 2 * i + 1, hi);
+              acc[i] = 0ull;
+            }
+            dirty = false;
+          }
+          if (e == kPsRun || ke == 0xffffffffu) continue;
+          cur = ke;
+          const unsigned long long t = suffix_mle(a.kinds[s], sb[e], a.suffix_len, a.bound);
+          const uint32_t th = h == 0 ? (uint32_t)t : (uint32_t)(t >> 32);
+          if (th == 0) continue;
           unsigned long long c = 0;
 #pragma unroll
-          for (int i = 0; i < 8; i++) { c += (unsigned long long)u.l[i] * th; col[i] = (uint32_t)c; c >>= 32; }   // c < 2^64: (2^32-1)^2 + (2^32-1)
-          col[8] = (uint32_t)c;
-        }
-        unsigned rem = big_leaders;
-        while (rem) {                                                   // at most 4 groups of 8 or more lanes
-          const int src = __ffs(rem) - 1;
-          rem &= rem - 1;
-          const uint32_t gkey = __shfl_sync(full, key, src);
-          const bool mine = key == gkey;
-          unsigned int* acc = s_acc + ((size_t)gkey * NSUF + s) * kPsCols + 2 * h;
-#pragma unroll
-          for (int i = 0; i < 9; i++) {
-            const uint32_t v = mine ? col[i] : 0u;
-            const unsigned lo = __reduce_add_sync(full, v & 0xffffu), hi = __reduce_add_sync(full, v >> 16);
-            if (lane == src) { if (lo) atomicAdd(acc + 2 * i, lo); if (hi) atomicAdd(acc + 2 * i + 1, hi); }
-          }
-        }
-        if (valid && !big && th != 0) {
-          unsigned int* acc = s_acc + ((size_t)key * NSUF + s) * kPsCols + 2 * h;
-#pragma unroll
-          for (int i = 0; i < 9; i++) {
-            if (col[i] & 0xffffu) atomicAdd(acc + 2 * i, col[i] & 0xffffu);
-            if (col[i] >> 16) atomicAdd(acc + 2 * i + 1, col[i] >> 16);
-          }
+          for (int i = 0; i < 8; i++) { c += (unsigned long long)u[e].l[i] * th; acc[i] += c & 0xffffffffull; c >>= 32; }   // c < 2^64
+          acc[8] += c;
+          dirty = true;
         }
       }
     }
@@ -148,14 +157,23 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
     const uint32_t key = q / NSUF, sfx = q % NSUF;
     fp_store(a.partial + ((size_t)blockIdx.x * NSUF + sfx) * m + key, val);
   }
-}
-
-__global__ void __launch_bounds__(256) k_ps_phase_final(const Fr* __restrict__ partial, uint32_t tiles, uint32_t n_out /* n_suf * m */, Fr* __restrict__ out) {
-  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n_out) return;
-  Fr tot = fp_zero<FrParams>();
-  for (uint32_t b = 0; b < tiles; b++) tot = fp_add<FrParams>(tot, fp_load(partial + (size_t)b * n_out + id));
-  fp_store(out + id, tot);
+  // the block that finishes last adds the blocks' partial tables and ships the result to the host (mapped memory + flag): one launch
+  // per phase, no D2H copy call
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(a.counter, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (uint32_t id = threadIdx.x; id < n_acc; id += blockDim.x) {
+    Fr tot = fp_zero<FrParams>();
+    for (uint32_t b = 0; b < gridDim.x; b++) tot = fp_add<FrParams>(tot, fr_ld_cg(a.partial + (size_t)b * n_acc + id));
+    fp_store(a.host_out + id, tot);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *a.host_seq = a.seq_value;
 }
 
 // init_log_t_rounds (mod.rs:427-441): ra[j] = prod_phase v[phase][(k >> ((phases - 1 - phase) * log_m)) & m_mask]
@@ -216,19 +234,19 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   const uint32_t m = 1u << p->log_m;
-  uint32_t tiles = (uint32_t)((p->T + 1023) / 1024);                    // at least 4 entries per thread, at most one block per SM
-  if (tiles > (uint32_t)kSMs) tiles = kSMs;
-  JA_REQUIRE((p->T + tiles - 1) / tiles <= 65536, "ja_psshout_init_phase: T too large for the 16-bit column counters");
+  uint32_t tiles = (uint32_t)((p->T + 1023) / 1024);   // ~4 entries per thread (the block that finishes last adds `tiles` partial tables), at most one block per SM
+  if (tiles > (uint32_t)kSMs) tiles = std::max<uint32_t>(kSMs, (uint32_t)((p->T + (size_t(1) << 15) - 1) >> 15));   // a 32-bit column takes 2^16 digits of 16 bits
+  JA_REQUIRE((p->T + tiles - 1) / tiles <= (size_t(1) << 15), "ja_psshout_init_phase: T too large for the column counters");
   const size_t n_out = n_suffixes * m;
   const size_t smem = n_out * kPsCols * sizeof(unsigned int);
   JA_REQUIRE(smem <= 180 * 1024, "ja_psshout_init_phase: too many suffixes for the shared-memory accumulators");
-  Fr *d_v = nullptr, *d_part = nullptr, *d_out = nullptr;
+  JA_REQUIRE(n_out <= (size_t)kMaxRowVals, "ja_psshout_init_phase: result larger than the mapped value buffer");
+  Fr *d_v = nullptr, *d_part = nullptr;
   int32_t st;
   if ((st = dev_alloc(c, (size_t)tiles * n_out * sizeof(Fr), (void**)&d_part))) return st;
-  if ((st = dev_alloc(c, n_out * sizeof(Fr), (void**)&d_out))) { dev_free(c, d_part); return st; }
   if (v_prev) {
-    if ((st = dev_alloc(c, m * sizeof(Fr), (void**)&d_v))) { dev_free(c, d_part); dev_free(c, d_out); return st; }
-    if ((st = stage_h2d(c, d_v, v_prev, m * sizeof(Fr)))) { dev_free(c, d_part); dev_free(c, d_out); dev_free(c, d_v); return st; }
+    if ((st = dev_alloc(c, m * sizeof(Fr), (void**)&d_v))) { dev_free(c, d_part); return st; }
+    if ((st = stage_h2d(c, d_v, v_prev, m * sizeof(Fr)))) { dev_free(c, d_part); dev_free(c, d_v); return st; }
   }
   PsPhaseArgs a;
   memset(&a, 0, sizeof(a));
@@ -238,18 +256,34 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   a.m_mask = m - 1; a.bound = bound; a.n_suf = (uint32_t)n_suffixes;
   for (size_t s = 0; s < n_suffixes; s++) a.kinds[s] = suffix_kinds[s];
   a.partial = d_part;
-#define JA_PS(N) case N: { JA_CUDA(cudaFuncSetAttribute(k_ps_phase<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); \
+  a.counter = c->d_counter + 2;
+  a.host_out = reinterpret_cast<Fr*>(c->d_rowvals);
+  a.host_seq = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<char*>(c->d_rowvals) + kRowSeqOffset);
+  a.seq_value = next_tag(c);
+  static bool attr_set[kPsMaxSuffixes + 1] = {false};
+#define JA_PS(N) case N: { if (!attr_set[N]) { JA_CUDA(cudaFuncSetAttribute(k_ps_phase<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); attr_set[N] = true; } \
                             JA_LAUNCH(c, KC_SCATTER, k_ps_phase<N><<<tiles, 256, smem, c->stream>>>(a)); break; }
   switch (n_suffixes) { JA_PS(1) JA_PS(2) JA_PS(3) JA_PS(4) JA_PS(5) JA_PS(6) JA_PS(7) default: JA_PS(8) }
 #undef JA_PS
-  JA_LAUNCH(c, KC_SCATTER, k_ps_phase_final<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(d_part, tiles, (uint32_t)n_out, d_out));
   cudaError_t e = cudaGetLastError();
-  const bool pinned = n_out * sizeof(Fr) <= kPinnedBytes;              // pinned staging: a D2H into pageable memory is staged by the driver and slow
-  if (e == cudaSuccess) e = cudaMemcpyAsync(pinned ? (void*)c->h_pinned : (void*)out_Q, d_out, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  if (e == cudaSuccess && pinned) memcpy(out_Q, c->h_pinned, n_out * sizeof(Fr));
-  dev_free(c, d_part); dev_free(c, d_out); dev_free(c, d_v);
+  dev_free(c, d_part); dev_free(c, d_v);                               // stream-ordered reuse
   if (e != cudaSuccess) return fail(JA_ERR_CUDA, std::string("ja_psshout_init_phase: ") + cudaGetErrorString(e));
+  {
+    // wait for the flag (bounded: a failed or finished stream and a 20 s timeout end the spin)
+    const volatile unsigned int* h_seq = reinterpret_cast<const volatile unsigned int*>(reinterpret_cast<char*>(c->h_rowvals) + kRowSeqOffset);
+    uint64_t spins = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (*h_seq != a.seq_value) {
+      if ((++spins & 0xffff) == 0) {
+        const cudaError_t q = cudaStreamQuery(c->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(JA_ERR_CUDA, std::string("ja_psshout_init_phase: ") + cudaGetErrorString(q));
+        if (q == cudaSuccess && *h_seq != a.seq_value) return fail(JA_ERR_CUDA, "ja_psshout_init_phase: kernel finished without publishing");
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) return fail(JA_ERR_CUDA, "ja_psshout_init_phase: timed out");
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    memcpy(out_Q, c->h_rowvals, n_out * sizeof(Fr));
+  }
   p->next_phase = phase + 1;
   return JA_OK;
 }

@@ -68,9 +68,9 @@ void ja_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
 }
 
-void ja_transcript_challenge_optimized(uint8_t state[32], uint32_t* n_rounds, uint64_t out[4]) {
+void ja_transcript_challenge_optimized(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out) {
   host::Blake2bTranscript t(state, *n_rounds);
-  t.challenge_scalar_optimized(out);                                // blake2b.rs:233-238: 125-bit challenge {0, 0, lo, hi}
+  for (size_t i = 0; i < n; i++) t.challenge_scalar_optimized(out + 4 * i);      // blake2b.rs:233-238: 125-bit challenges {0, 0, lo, hi}
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
 }
 // ExpandingTable (joltworks/src/utils/expanding_table.rs:62-89) after `n` updates with the given challenges, starting from [1]:

@@ -185,8 +185,7 @@ class Transcript:
     def challenge_optimized(self, n: int = 1) -> np.ndarray:
         """n x challenge_scalar_optimized (blake2b.rs:233-238): (n, 4) limbs {0, 0, lo, hi}."""
         out = np.zeros((n, 4), dtype=np.uint64)
-        for i in range(n):
-            self._lib.ja_transcript_challenge_optimized(self._st, C.byref(self._nr), out[i].ctypes.data_as(_lib.u64p))
+        self._lib.ja_transcript_challenge_optimized(self._st, C.byref(self._nr), n, out.ctypes.data)
         return out
 
     def challenge_scalar_powers(self, n: int) -> np.ndarray:

@@ -31,6 +31,7 @@ PS_PHASES = 8         # ps_shout/mod.rs:56 NUM_PHASES
 SAT_BOUND = 31        # SaturationTable: clamp to [-2^31, 2^31 - 1] (lookup_tables/clamp.rs, SIGN_BIT_I32)
 # suffixes of the pass: SaturationTable read-checking suffixes (clamp.rs:78-86) then the unary raf's [One, Identity] (signed_identity_poly.rs:160-167)
 PS_SUFFIXES = (1, 2, 3, 0, 0, 4)
+_PS_KINDS = np.array(PS_SUFFIXES, dtype=np.uint32)
 P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 R = (1 << 256) % P
 MASK64 = (1 << 64) - 1
@@ -212,7 +213,7 @@ def _ra_checks(A, ctx, addr, ni, lo, hi, claim, t, out, sc, keep_first=True):
     return first
 
 
-def run_device(ctx, srs, inputs, resident=None, comm=None):
+def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
     """One prove-shaped pass on the GPU.  Returns dict(commitments, states, finals, open) for parity checks.
     `resident` (from make_resident) supplies device-resident copies of the per-proof inputs; without it every input is
     uploaded from the host arrays inside this call (the end-to-end path).
@@ -267,22 +268,27 @@ def run_device(ctx, srs, inputs, resident=None, comm=None):
         #    checkpoints: joltworks/src/lookup_tables/, the Rust prover's unchanged code) and are NOT reproduced: each phase is
         #    represented by its transcript traffic only - the phase's suffix polynomials are absorbed (first entry of each), its 8
         #    challenges drawn, and the expanding table v[phase] built from them (utils/expanding_table.rs:76-86).
-        ps = res["ps"].restart() if res else A.PrefixSuffixShout(ctx, ni.acc, ni.eq_w, CLAMP_LOG_K, PS_PHASES)
-        tr = PAR.Transcript(state=t.state, n_rounds=t.n_rounds)
-        vs = []
-        for phase in range(PS_PHASES):
-            Q = ps.init_phase(phase, vs[-1] if phase else None, PS_SUFFIXES, SAT_BOUND)
-            tr.append_scalars(Q[:, 0])
-            vs.append(PAR.expanding_table(tr.challenge_optimized(CLAMP_LOG_K // PS_PHASES)))
-            out["msg_bytes"] += Q.nbytes
-        t.state, t.n_rounds = tr.state, tr.n_rounds
-        ra_ps = ps.materialize_ra(np.concatenate(vs))
-        if not res:
-            ps.free()
-        _sc(ctx, A.EvalKernel.IDENT, [ra_ps], claim, t, eq_w=ni.eq_w)
-        ra_ps.free()
+        #    ps_shout=False (bench.py's continuity leg): the round-1 stage list - cycle rounds on the first RA polynomial, no phase passes.
+        if ps_shout:
+            ps = res["ps"].restart() if res else A.PrefixSuffixShout(ctx, ni.acc, ni.eq_w, CLAMP_LOG_K, PS_PHASES)
+            tr = PAR.Transcript(state=t.state, n_rounds=t.n_rounds)
+            vs = []
+            for phase in range(PS_PHASES):
+                Q = ps.init_phase(phase, vs[-1] if phase else None, _PS_KINDS, SAT_BOUND)
+                tr.append_scalars(Q[:, 0])
+                vs.append(PAR.expanding_table(tr.challenge_optimized(CLAMP_LOG_K // PS_PHASES)))
+                out["msg_bytes"] += Q.nbytes
+            t.state, t.n_rounds = tr.state, tr.n_rounds
+            ra_ps = ps.materialize_ra(np.concatenate(vs))
+            if not res:
+                ps.free()
+            _sc(ctx, A.EvalKernel.IDENT, [ra_ps], claim, t, eq_w=ni.eq_w)
+            ra_ps.free()
         # C. RA one-hot checks of the clamp lookup (batched: product of 16, Hamming weight, booleanity)
-        _ra_checks(A, ctx, hot16, ni, 0, D_CLAMP, claim, t, out, _sc, keep_first=False)
+        ra0 = _ra_checks(A, ctx, hot16, ni, 0, D_CLAMP, claim, t, out, _sc, keep_first=not ps_shout)
+        if not ps_shout:
+            _sc(ctx, A.EvalKernel.IDENT, [ra0], claim, t, eq_w=ni.eq_w)
+            ra0.free()
         # D. the operator's own sumcheck
         if spec.kind == "einsum":
             # EinsumDotProver::initialize (einsum/dot.rs:259-283): fold both operands with the eq tables, then log k dot rounds
@@ -527,16 +533,19 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx,
             ms = ctx.bench_kernel(which, log_n, 1, 10)
             gb = bytes_per_n * (1 << log_n) / ms / 1e6
             sweep.append({"kernel": name, "log_n": log_n, "ms": round(ms, 4), "GBps": round(gb, 1), "frac_hbm": round(gb / hbm, 4)})
-    # fused bind + evaluate round kernels: 48 n bytes per polynomial and launch; the mul-bound bodies also as Gmul/s
-    fused = ((7, "fused_round_add_tma", 2, 24, 2 * 2 + 2), (7, "fused_round_add_tma", 2, 26, 2 * 2 + 2), (8, "fused_round_ident_tma", 1, 26, 1 + 2),
-             (0, "fused_round_add", 2, 24, 2 * 2 + 2), (1, "fused_round_mul", 2, 24, 4 + 2 * 2), (2, "fused_round_ident", 1, 24, 1 + 2),
-             (6, "fused_round_open_h2l", 1, 24, 2 + 2), (3, "fused_round_product4", 4, 22, 16 + 4 + 4), (4, "fused_round_product16", 16, 20, 256 + 16 + 16),
-             (5, "fused_round_booleanity16", 16, 20, 16 * 5 + 16 + 2))
-    for which, name, npoly, log_n, muls_per_pair in fused:
+    # fused bind + evaluate round kernels: 48 n bytes per polynomial and launch; the mul-bound bodies also as Gmul/s.
+    # Products per pair = (full Montgomery products, 4-row challenge products of the bind): a challenge product is half the
+    # IMAD.WIDE rows of a full one and is counted as 0.5, so that frac_mul is a fraction of the calibrated full-product peak.
+    fused = ((7, "fused_round_add_tma", 2, 24, (2, 4)), (7, "fused_round_add_tma", 2, 26, (2, 4)), (8, "fused_round_ident_tma", 1, 26, (2, 2)),
+             (0, "fused_round_add", 2, 24, (2, 4)), (1, "fused_round_mul", 2, 24, (4, 4)), (2, "fused_round_ident", 1, 24, (2, 2)),
+             (6, "fused_round_open_h2l", 1, 24, (2, 2)), (3, "fused_round_product4", 4, 22, (16 + 4, 8)), (4, "fused_round_product16", 16, 20, (256 + 16, 32)),
+             (5, "fused_round_booleanity16", 16, 20, (16 * 4 + 2, 32)))
+    for which, name, npoly, log_n, (full_muls, chal_muls) in fused:
         ms = ctx.bench_fused(which, log_n, 10)
         n = 1 << log_n
         gb = 48 * n * npoly / ms / 1e6
-        gm = muls_per_pair * (n // 4) / ms / 1e6
+        gm = (full_muls + 0.5 * chal_muls) * (n // 4) / ms / 1e6
         sweep.append({"kernel": name, "log_n": log_n, "n_polys": npoly, "ms": round(ms, 4), "GBps": round(gb, 1),
-                      "frac_hbm": round(gb / hbm, 4), "Gmul_per_s": round(gm, 2), "frac_mul": round(gm / mul_peak, 4)})
+                      "frac_hbm": round(gb / hbm, 4), "full_products_per_pair": full_muls, "challenge_products_per_pair": chal_muls,
+                      "Gmul_per_s": round(gm, 2), "frac_mul": round(gm / mul_peak, 4)})
     return {"dominant": dominant, "classes": classes, "sweep": sweep, "fr_mul_peak_Gmul_s": mul_peak}
