@@ -39,7 +39,7 @@ JA_DEV unsigned long long suffix_mle(uint32_t kind, unsigned long long bits, uin
 }
 
 struct PsPhaseArgs {
-  const unsigned long long* idx; Fr* u; const Fr* v_prev;
+  const unsigned long long* idx; const Fr* u; Fr* u_out; const Fr* v_prev;
   unsigned long long T;
   uint32_t prev_shift;             // k_bound of the previous phase = (k >> prev_shift) & m_mask
   uint32_t suffix_len, m_mask, bound, n_suf;
@@ -66,11 +66,15 @@ constexpr int kPsCols = 2 * kPsLimbs;  // ... held as 16-bit columns in 32-bit c
 // (clamp lookups send almost every entry of the early phases to the bins 0x00 / 0xff: one flush per thread, suffix and half
 // instead of one per entry), then flushes the run with native 32-bit shared-memory atomics.
 constexpr int kPsRun = 2;
-template <int NSUF>
+// A block accumulates kPsSufPerBlock suffixes (blockIdx.y selects which): 48 KB of static shared memory, no opt-in carve-out
+// (a 147 KB dynamic allocation for all six suffixes made every launch reconfigure the SM's L1 / shared split).
+constexpr int kPsSufPerBlock = 2;
 __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
-  extern __shared__ unsigned int s_acc[];                // [m][NSUF][kPsCols]
+  constexpr int NSUF = kPsSufPerBlock;
+  __shared__ unsigned int s_acc[256 * kPsSufPerBlock * kPsCols];     // [m][NSUF][kPsCols]
   const uint32_t m = a.m_mask + 1;
   const uint32_t n_acc = m * NSUF;
+  const uint32_t s0 = blockIdx.y * NSUF;                  // first suffix of this block
   for (uint32_t i = threadIdx.x; i < n_acc * kPsCols; i += blockDim.x) s_acc[i] = 0u;
   __syncthreads();
   const size_t chunk = (size_t)blockDim.x * kPsRun;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
         u[e] = fp_load(a.u + j);
         if (a.v_prev) {                                                 // init_phase: u_evals[j] *= v[phase - 1][k_bound]
           u[e] = fp_mul<FrParams>(u[e], fp_load(a.v_prev + ((k >> a.prev_shift) & a.m_mask)));
-          fp_store(a.u + j, u[e]);
+          if (blockIdx.y == gridDim.y - 1) fp_store(a.u_out + j, u[e]);  // every suffix group forms the same product; one of them keeps it
         }
         sb[e] = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
         key[e] = (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask);
@@ -95,7 +99,9 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
     }
 #pragma unroll 1
     for (int s = 0; s < NSUF; s++) {
-      const int halves = (a.kinds[s] == JA_SUF_IDENTITY && a.suffix_len > 32) ? 2 : 1;     // only the identity suffix exceeds 32 bits
+      if (s0 + s >= a.n_suf) break;
+      const uint32_t kind = a.kinds[s0 + s];
+      const int halves = (kind == JA_SUF_IDENTITY && a.suffix_len > 32) ? 2 : 1;     // only the identity suffix exceeds 32 bits
 #pragma unroll 1
       for (int h = 0; h < halves; h++) {
         unsigned long long acc[9];
@@ -106,6 +112,28 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
 #pragma unroll
         for (int e = 0; e <= kPsRun; e++) {
           const uint32_t ke = e < kPsRun ? key[e] : 0xffffffffu;
+          if (e == kPsRun) {
+            // end of the thread's run: when the WHOLE warp holds the same key (the skewed phases) the lanes' columns are added with
+            // warp reductions and one lane issues the atomics - 32 lanes hammering one shared-memory word serialise otherwise
+            const uint32_t kk = dirty ? cur : 0xfffffffeu;
+            const uint32_t k0 = __shfl_sync(0xffffffffu, kk, 0);
+            if (__all_sync(0xffffffffu, kk == k0) && k0 < 0xfffffffeu) {
+              unsigned int* dst = s_acc + ((size_t)k0 * NSUF + s) * kPsCols + 2 * h;
+#pragma unroll
+              for (int i = 0; i < 9; i++) {
+                // acc[i] < 2^34: three digits of 16 / 16 / 2+ bits, each warp sum below 2^21
+                const unsigned d0 = __reduce_add_sync(0xffffffffu, (unsigned)(acc[i] & 0xffffull));
+                const unsigned d1 = __reduce_add_sync(0xffffffffu, (unsigned)((acc[i] >> 16) & 0xffffull));
+                const unsigned d2 = __reduce_add_sync(0xffffffffu, (unsigned)(acc[i] >> 32));
+                if ((threadIdx.x & 31) == 0) {
+                  if (d0) atomicAdd(dst + 2 * i, d0);
+                  const unsigned hi = d1 + (d2 << 16);
+                  if (hi) atomicAdd(dst + 2 * i + 1, hi);
+                }
+              }
+              dirty = false;
+            }
+          }
           if (dirty && ke != cur) {                                      // the run ends: flush it
             unsigned int* dst = s_acc + ((size_t)cur * NSUF + s) * kPsCols + 2 * h;
 #pragma unroll
@@ -119,7 +147,7 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
           }
           if (e == kPsRun || ke == 0xffffffffu) continue;
           cur = ke;
-          const unsigned long long t = suffix_mle(a.kinds[s], sb[e], a.suffix_len, a.bound);
+          const unsigned long long t = suffix_mle(kind, sb[e], a.suffix_len, a.bound);
           const uint32_t th = h == 0 ? (uint32_t)t : (uint32_t)(t >> 32);
           if (th == 0) continue;
           unsigned long long c = 0;
@@ -154,26 +182,30 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
 #pragma unroll
     for (int i = 0; i < 5; i++) hi.l[i] = w[8 + i];
     const Fr val = fp_add<FrParams>(fp_mul<FrParams>(fp_one<FrParams>(), lo), fp_mul<FrParams>(fp_r2<FrParams>(), hi));
-    const uint32_t key = q / NSUF, sfx = q % NSUF;
-    fp_store(a.partial + ((size_t)blockIdx.x * NSUF + sfx) * m + key, val);
+    const uint32_t key = q / NSUF, sfx = s0 + q % NSUF;
+    if (sfx < a.n_suf) fp_store(a.partial + ((size_t)blockIdx.x * a.n_suf + sfx) * m + key, val);
   }
-  // the block that finishes last adds the blocks' partial tables and ships the result to the host (mapped memory + flag): one launch
-  // per phase, no D2H copy call
-  __shared__ bool s_last;
+  // the block that finishes last in its suffix group adds the tiles' partial tables of the group's suffixes and stores them to the
+  // host (mapped memory); the group that finishes last raises the flag: one launch per phase, no D2H copy call
   __threadfence();
+  __syncthreads();                                       // the accumulators are dead from here: word 0 carries the "last block" flag
+  if (threadIdx.x == 0) s_acc[0] = atomicInc(a.counter + 1 + blockIdx.y, gridDim.x - 1) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicInc(a.counter, gridDim.x - 1) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
+  if (!s_acc[0]) return;
   __threadfence();
-  for (uint32_t id = threadIdx.x; id < n_acc; id += blockDim.x) {
+  for (uint32_t q = threadIdx.x; q < n_acc; q += blockDim.x) {
+    const uint32_t sfx = s0 + q / m, key = q % m;
+    if (sfx >= a.n_suf) continue;
     Fr tot = fp_zero<FrParams>();
-    for (uint32_t b = 0; b < gridDim.x; b++) tot = fp_add<FrParams>(tot, fr_ld_cg(a.partial + (size_t)b * n_acc + id));
-    fp_store(a.host_out + id, tot);
+    for (uint32_t b = 0; b < gridDim.x; b++) tot = fp_add<FrParams>(tot, fr_ld_cg(a.partial + ((size_t)b * a.n_suf + sfx) * m + key));
+    fp_store(a.host_out + (size_t)sfx * m + key, tot);
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) *a.host_seq = a.seq_value;
+  if (threadIdx.x == 0) {
+    const bool all = atomicInc(a.counter, gridDim.y - 1) == gridDim.y - 1;
+    if (all) { __threadfence_system(); *a.host_seq = a.seq_value; }
+  }
 }
 
 // init_log_t_rounds (mod.rs:427-441): ra[j] = prod_phase v[phase][(k >> ((phases - 1 - phase) * log_m)) & m_mask]
@@ -195,6 +227,7 @@ __global__ void __launch_bounds__(kBlock) k_ps_ra(const unsigned long long* __re
 struct ja_psshout {
   unsigned long long* d_idx = nullptr;
   Fr* d_u = nullptr;                 // u_evals: eq(r_cycle, j), then times the expanding tables of the finished phases
+  Fr* d_u2 = nullptr;                // ping-pong partner (a phase reads the old values in every suffix group)
   size_t T = 0;
   uint32_t log_k = 0, phases = 0, log_m = 0;
   uint32_t next_phase = 0;
@@ -238,8 +271,6 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   if (tiles > (uint32_t)kSMs) tiles = std::max<uint32_t>(kSMs, (uint32_t)((p->T + (size_t(1) << 15) - 1) >> 15));   // a 32-bit column takes 2^16 digits of 16 bits
   JA_REQUIRE((p->T + tiles - 1) / tiles <= (size_t(1) << 15), "ja_psshout_init_phase: T too large for the column counters");
   const size_t n_out = n_suffixes * m;
-  const size_t smem = n_out * kPsCols * sizeof(unsigned int);
-  JA_REQUIRE(smem <= 180 * 1024, "ja_psshout_init_phase: too many suffixes for the shared-memory accumulators");
   JA_REQUIRE(n_out <= (size_t)kMaxRowVals, "ja_psshout_init_phase: result larger than the mapped value buffer");
   Fr *d_v = nullptr, *d_part = nullptr;
   int32_t st;
@@ -256,15 +287,18 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   a.m_mask = m - 1; a.bound = bound; a.n_suf = (uint32_t)n_suffixes;
   for (size_t s = 0; s < n_suffixes; s++) a.kinds[s] = suffix_kinds[s];
   a.partial = d_part;
-  a.counter = c->d_counter + 2;
+  a.counter = c->d_counter + 8;                                        // [0]: groups done, [1 + y]: blocks done of group y
   a.host_out = reinterpret_cast<Fr*>(c->d_rowvals);
   a.host_seq = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<char*>(c->d_rowvals) + kRowSeqOffset);
   a.seq_value = next_tag(c);
-  static bool attr_set[kPsMaxSuffixes + 1] = {false};
-#define JA_PS(N) case N: { if (!attr_set[N]) { JA_CUDA(cudaFuncSetAttribute(k_ps_phase<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); attr_set[N] = true; } \
-                            JA_LAUNCH(c, KC_SCATTER, k_ps_phase<N><<<tiles, 256, smem, c->stream>>>(a)); break; }
-  switch (n_suffixes) { JA_PS(1) JA_PS(2) JA_PS(3) JA_PS(4) JA_PS(5) JA_PS(6) JA_PS(7) default: JA_PS(8) }
-#undef JA_PS
+  // u_evals ping-pong: the suffix groups of a phase all read the OLD u_evals while one of them writes the new ones
+  if (v_prev) {
+    if (!p->d_u2 && (st = dev_alloc(c, p->T * sizeof(Fr), (void**)&p->d_u2))) { dev_free(c, d_part); dev_free(c, d_v); return st; }
+    a.u_out = p->d_u2;
+  }
+  const unsigned groups = (unsigned)((n_suffixes + kPsSufPerBlock - 1) / kPsSufPerBlock);
+  JA_LAUNCH(c, KC_SCATTER, k_ps_phase<<<dim3(tiles, groups), 256, 0, c->stream>>>(a));
+  if (v_prev) std::swap(p->d_u, p->d_u2);
   cudaError_t e = cudaGetLastError();
   dev_free(c, d_part); dev_free(c, d_v);                               // stream-ordered reuse
   if (e != cudaSuccess) return fail(JA_ERR_CUDA, std::string("ja_psshout_init_phase: ") + cudaGetErrorString(e));
@@ -309,7 +343,7 @@ void ja_psshout_free(ja_ctx* c, ja_psshout* p) {
   if (!c || !p) return;
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   cudaSetDevice(c->device);
-  dev_free(c, p->d_idx); dev_free(c, p->d_u);
+  dev_free(c, p->d_idx); dev_free(c, p->d_u); dev_free(c, p->d_u2);
   delete p;
 }
 
