@@ -320,6 +320,25 @@ int32_t ja_psshout_init_phase(ja_ctx*, ja_psshout*, uint32_t phase, const uint64
 int32_t ja_psshout_materialize_ra(ja_ctx*, ja_psshout*, const uint64_t* v /* phases x m Fr */, ja_poly** out_ra);
 void ja_psshout_free(ja_ctx*, ja_psshout*);
 
+/* ---- witness generation of a fused node on the device (jolt-atlas-core/src/onnx_proof/witness.rs:142-214 generate_node_witnesses) ----
+ * From the node's resident i32 operands: acc = einsum_acc_i64 (op EINSUM_MK_KN: A m x k, B k x n; atlas-onnx-tracer/src/ops/einsum.rs:248-258),
+ * a * b (MUL, ops/mul.rs:51-60) or a +- b (ADD / SUB, sat_binop_intermediate) in i64; quotient = acc.div_euclid(2^S), remainder =
+ * acc.rem_euclid(2^S) (ops/mod.rs:224-249); then, zero-padded to T entries, the 16 ClampRaD chunk lists (4-bit chunks of the
+ * quotient as u64, clamp_lookups/mod.rs:245-252 + joltworks/src/config.rs:75-77), the ceil(S/4) RescaleRemainderRaD chunk lists
+ * (witness.rs:601-617), the lookup indices of the clamp read-raf and the clamped i32 output - all born in HBM, ready for
+ * ja_addr_commit_many / ja_addr_ra_evals / ja_addr_gather / ja_psshout_from_witness.  The address batches are owned by the witness. */
+typedef struct ja_witness ja_witness;
+enum { JA_WIT_EINSUM_MK_KN = 0, JA_WIT_MUL = 1, JA_WIT_ADD = 2, JA_WIT_SUB = 3 };
+int32_t ja_witness_fused(ja_ctx*, int32_t op, const ja_tensor_i32* A, const ja_tensor_i32* B, uint32_t scale_bits, size_t T, ja_witness** out);
+const ja_addr* ja_witness_clamp_addr(const ja_witness*);      /* d = 16, K = 16 */
+const ja_addr* ja_witness_rem_addr(const ja_witness*);        /* d = ceil(S / 4), K = 16; NULL when scale_bits == 0 */
+int32_t ja_witness_to_host(ja_ctx*, const ja_witness*, uint64_t* out_idx /* T */, int32_t* out_i32 /* T */, uint32_t* out_clamp_k /* 16 x T */,
+                           uint32_t* out_rem_k /* ceil(S/4) x T */);    /* any pointer may be NULL */
+int32_t ja_psshout_from_witness(ja_ctx*, const ja_witness*, const uint64_t* r_cycle, size_t log_t, uint32_t log_k, uint32_t phases, ja_psshout** out);
+int32_t ja_psshout_new_dev(ja_ctx*, const unsigned long long* d_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
+                           uint32_t phases, ja_psshout** out);          /* lookup indices already in device memory */
+void ja_witness_free(ja_ctx*, ja_witness*);
+
 /* ---- HyperKZG::open (joltworks/src/poly/commitment/hyperkzg/mod.rs:400-447) --------------------------------------
  * Split at the two transcript interaction points so that a Rust caller keeps its own Blake2bTranscript:
  *   begin    Phase 1: l-1 folds Pi[j] = point[l-i-1]*(prev[2j+1]-prev[2j]) + prev[2j] (:413-428) and

@@ -7,5 +7,5 @@ Importing this package does not load CUDA; `api.Context()` does and fails loudly
 from .api import (  # noqa: F401
     BindingOrder, Blake2bTranscriptState, Context, HyperKZGOpening, hyperkzg_open, EqPolynomial, EvalKernel, GruenSplitEqPolynomial, JoltAtlasError,
     MsmWidth, MultilinearPolynomial, OneHotBatch, SRS, bind_many, g1_sum_indexed, g1_sum_indexed_batch, msm_fr, msm_fr_batch,
-    msm_host, round_eval, sumcheck_prove, tensor_fold_i32, OneHotAddresses, InstanceKind, commit_one_hot_batches, eval_reduction_h, batched_sumcheck_prove, TensorI32,
+    msm_host, round_eval, sumcheck_prove, tensor_fold_i32, OneHotAddresses, InstanceKind, commit_one_hot_batches, eval_reduction_h, batched_sumcheck_prove, TensorI32, FusedWitness, PrefixSuffixShout, SuffixKind,
 )

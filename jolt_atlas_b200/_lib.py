@@ -91,6 +91,13 @@ SIGNATURES = {
     "ja_psshout_init_phase": (C.c_int32, [vp, vp, C.c_uint32, u64p, u32p, C.c_size_t, C.c_uint32, u64p]),
     "ja_psshout_materialize_ra": (C.c_int32, [vp, vp, u64p, vpp]),
     "ja_psshout_free": (None, [vp, vp]),
+    "ja_witness_fused": (C.c_int32, [vp, C.c_int32, vp, vp, C.c_uint32, C.c_size_t, vpp]),
+    "ja_witness_clamp_addr": (C.c_void_p, [vp]),
+    "ja_witness_rem_addr": (C.c_void_p, [vp]),
+    "ja_witness_to_host": (C.c_int32, [vp, vp, vp, vp, vp, vp]),
+    "ja_psshout_from_witness": (C.c_int32, [vp, vp, u64p, C.c_size_t, C.c_uint32, C.c_uint32, vpp]),
+    "ja_psshout_new_dev": (C.c_int32, [vp, vp, C.c_size_t, u64p, C.c_size_t, C.c_uint32, C.c_uint32, vpp]),
+    "ja_witness_free": (None, [vp, vp]),
     "ja_comm_unique_id": (C.c_int32, [C.c_char_p]),
     "ja_comm_init": (C.c_int32, [vp, C.c_uint32, C.c_uint32, C.c_char_p]),
     "ja_comm_free": (None, [vp]),

@@ -574,6 +574,13 @@ class OneHotAddresses:
         self._h = h
 
     @classmethod
+    def _view(cls, ctx: Context, handle, d: int, T: int, K: int):
+        """A batch owned by another object (FusedWitness): free() is a no-op."""
+        o = cls.__new__(cls)
+        o.ctx, o.d, o.T, o.K, o._h, o._borrowed = ctx, d, T, K, C.c_void_p(handle), True
+        return o
+
+    @classmethod
     def upload_many(cls, ctx: Context, ks, K: int):
         """All address batches of a proof in one call (ja_addr_upload_many): copies and device-side validation enqueued back
         to back, one synchronisation.  ks: list of (d_i, T_i) uint32 arrays -> list of OneHotAddresses."""
@@ -614,9 +621,9 @@ class OneHotAddresses:
         return out
 
     def free(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             self.ctx._lib.ja_addr_free(self.ctx._h, self._h)
-            self._h = None
+        self._h = None
 
 
 def commit_one_hot_batches(ctx: Context, srs: SRS, batches):
@@ -667,6 +674,46 @@ class PrefixSuffixShout:
     def free(self):
         if self._h:
             self.ctx._lib.ja_psshout_free(self.ctx._h, self._h)
+            self._h = None
+
+
+class FusedWitness:
+    """generate_node_witnesses (jolt-atlas-core/src/onnx_proof/witness.rs:142-214) for a fused node, on the device: from the resident
+    i32 operands to the ClampRaD / RescaleRemainderRaD address batches, the clamp lookup indices and the clamped output.
+    op: 0 einsum mk,kn->mn, 1 Mul, 2 Add, 3 Sub.  `.clamp` / `.rem` are OneHotAddresses views owned by the witness."""
+    EINSUM_MK_KN, MUL, ADD, SUB = 0, 1, 2, 3
+
+    def __init__(self, ctx: Context, op: int, A: "TensorI32", B: "TensorI32", scale_bits: int, T: int):
+        self.ctx, self.T = ctx, T
+        h = C.c_void_p()
+        check(ctx._lib.ja_witness_fused(ctx._h, op, A._h, B._h, scale_bits, T, C.byref(h)))
+        self._h = h
+        self.clamp = OneHotAddresses._view(ctx, ctx._lib.ja_witness_clamp_addr(h), 16, T, 16)
+        d_rem = (scale_bits + 3) // 4
+        self.rem = OneHotAddresses._view(ctx, ctx._lib.ja_witness_rem_addr(h), d_rem, T, 16) if d_rem else None
+
+    def ps_shout(self, r_cycle, log_k: int = 64, phases: int = 8) -> "PrefixSuffixShout":
+        r = _fr_arg(r_cycle).reshape(-1, 4)
+        ps = PrefixSuffixShout.__new__(PrefixSuffixShout)
+        ps.ctx, ps.T, ps.log_k, ps.phases, ps.m = self.ctx, self.T, log_k, phases, 1 << (log_k // phases)
+        h = C.c_void_p()
+        check(self.ctx._lib.ja_psshout_from_witness(self.ctx._h, self._h, _u64p(r), r.shape[0], log_k, phases, C.byref(h)))
+        ps._h = h
+        return ps
+
+    def to_host(self):
+        """(lookup indices (T,) u64, clamped output (T,) i32, clamp chunks (16, T) u32, remainder chunks (d_rem, T) u32 or None)."""
+        idx = np.empty(self.T, dtype=np.uint64)
+        o = np.empty(self.T, dtype=np.int32)
+        ck = np.empty((16, self.T), dtype=np.uint32)
+        rk = np.empty((self.rem.d, self.T), dtype=np.uint32) if self.rem is not None else None
+        check(self.ctx._lib.ja_witness_to_host(self.ctx._h, self._h, idx.ctypes.data, o.ctypes.data, ck.ctypes.data,
+                                               rk.ctypes.data if rk is not None else None))
+        return idx, o, ck, rk
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.ja_witness_free(self.ctx._h, self._h)
             self._h = None
 
 

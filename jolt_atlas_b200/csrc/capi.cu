@@ -825,10 +825,6 @@ int32_t ja_tensor_fold_i32(ja_ctx* c, const int32_t* A, size_t rows, size_t cols
 
 // Model weights / activations of a node live on the device for the whole proof (they are inputs of several stages):
 // upload once, fold any number of times.
-struct ja_tensor_i32 {
-  int* data = nullptr;
-  size_t rows = 0, cols = 0;
-};
 int32_t ja_tensor_i32_upload(ja_ctx* c, const int32_t* A, size_t rows, size_t cols, ja_tensor_i32** out) {
   JA_REQUIRE(c && A && out && rows && cols, "ja_tensor_i32_upload: null or empty argument");
   std::lock_guard<std::recursive_mutex> lk(c->mu);

@@ -162,6 +162,11 @@ struct ja_onehot {
   uint64_t max_index = 0;
 };
 
+struct ja_tensor_i32 {
+  int* data = nullptr;       // rows x cols, row-major, device
+  size_t rows = 0, cols = 0;
+};
+
 struct ja_addr {
   uint32_t* d_k = nullptr;   // d lists x T addresses in [0, K), 0xFFFFFFFF = None
   size_t d = 0, T = 0, K = 0;
@@ -176,6 +181,9 @@ struct MsmJob {
   uint32_t dense_random = 0;
 };
 int32_t ja_msm_run(ja_ctx* c, const ja_srs* srs, const std::vector<MsmJob>& jobs, uint64_t* out_xy, int32_t* is_inf);
+struct ja_psshout;
+extern "C" int32_t ja_psshout_new_dev(ja_ctx* c, const unsigned long long* d_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
+                                      uint32_t phases, ja_psshout** out);
 // comm.cu: all-gather over the context's communicator (host buffers, rank-major) and the point-wise sum of every rank's partial points
 int32_t comm_allgather(ja_ctx* c, const void* send, size_t bytes, void* recv);
 int32_t comm_combine_points(ja_ctx* c, uint64_t* xy, int32_t* inf, size_t count);

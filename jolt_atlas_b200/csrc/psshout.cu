@@ -235,8 +235,19 @@ struct ja_psshout {
 
 extern "C" {
 
+static int32_t psshout_new_impl(ja_ctx* c, const uint64_t* lookup_indices, bool on_device, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
+                                uint32_t phases, ja_psshout** out);
 int32_t ja_psshout_new(ja_ctx* c, const uint64_t* lookup_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
                        uint32_t phases, ja_psshout** out) {
+  return psshout_new_impl(c, lookup_indices, false, T, r_cycle, log_t, log_k, phases, out);
+}
+// the same over lookup indices that already live in HBM (witness.cu): device-to-device copy
+int32_t ja_psshout_new_dev(ja_ctx* c, const unsigned long long* d_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
+                           uint32_t phases, ja_psshout** out) {
+  return psshout_new_impl(c, reinterpret_cast<const uint64_t*>(d_indices), true, T, r_cycle, log_t, log_k, phases, out);
+}
+static int32_t psshout_new_impl(ja_ctx* c, const uint64_t* lookup_indices, bool on_device, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
+                                uint32_t phases, ja_psshout** out) {
   JA_REQUIRE(c && lookup_indices && out && (r_cycle || log_t == 0), "ja_psshout_new: null argument");
   JA_REQUIRE(T == (size_t(1) << log_t) && phases >= 1 && log_k >= phases && log_k <= 64 && log_k % phases == 0 && log_k / phases <= 8,
              "ja_psshout_new: T = 2^log_t, LOG_K a multiple of the number of phases, at most 8 address bits per phase");
@@ -246,14 +257,14 @@ int32_t ja_psshout_new(ja_ctx* c, const uint64_t* lookup_indices, size_t T, cons
   p->T = T; p->log_k = log_k; p->phases = phases; p->log_m = log_k / phases;
   int32_t st = dev_alloc(c, T * 8, (void**)&p->d_idx);
   if (st) { delete p; return st; }
-  JA_CUDA(cudaMemcpyAsync(p->d_idx, lookup_indices, T * 8, cudaMemcpyHostToDevice, c->stream));
+  JA_CUDA(cudaMemcpyAsync(p->d_idx, lookup_indices, T * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   // u_evals = EqPolynomial::evals(r_node_output) (mod.rs:236)
   ja_poly* eq = nullptr;
   if ((st = ja_eq_evals(c, r_cycle, log_t, nullptr, &eq))) { dev_free(c, p->d_idx); delete p; return st; }
   p->d_u = eq->buf[eq->cur];
   eq->buf[eq->cur] = nullptr;
   ja_poly_free(c, eq);
-  JA_CUDA(cudaStreamSynchronize(c->stream));            // the index array is borrowed for the duration of the call
+  if (!on_device) JA_CUDA(cudaStreamSynchronize(c->stream));            // the host index array is borrowed for the duration of the call
   *out = p;
   return JA_OK;
 }
