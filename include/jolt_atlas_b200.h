@@ -296,8 +296,8 @@ int32_t ja_rlc_add_dense(ja_ctx*, ja_poly* joint, const ja_poly* poly, const uin
 
 /* ---- prefix-suffix Shout: the T-sized passes of the read-raf sumcheck over a 2^LOG_K-entry table (clamp lookups: LOG_K = 64) ----
  * joltworks/src/subprotocols/ps_shout/mod.rs.  The LOG_K address rounds run in NUM_PHASES phases over m = 2^(LOG_K / NUM_PHASES)-entry
- * suffix polynomials: O(m) work per round that stays with the caller (prefix MLEs + checkpoints: joltworks/src/lookup_tables/, unchanged).
- * The device does what scales with T at every phase boundary:
+ * suffix polynomials: O(m) work per round, done by ja_psshout_prove_address on the HOST next to the transcript (a device round would
+ * pay a PCIe round trip for ~1 us of arithmetic on 256-entry tables).  The device does what scales with T at every phase boundary:
  *   ja_psshout_new          lookup_indices (T x u64) resident; u_evals = EqPolynomial::evals(r_node_output)        mod.rs:226-267
  *   ja_psshout_init_phase   init_phase (:269-303): u_evals[j] *= v[phase-1][k_bound(j)] (v_prev = the m-entry expanding table of the
  *                           finished phase, NULL for phase 0), then init_suffix_polys (:305-335) / RafProverState::init_Q
@@ -306,7 +306,19 @@ int32_t ja_rlc_add_dense(ja_ctx*, ja_poly* joint, const ja_poly* poly, const uin
  *                           one pass).  Suffix kinds = the clamp-table family of lookup_tables/suffixes/ with `bound` = BOUND of the
  *                           table (31 for SaturationTable, 9 for the ONNX Clamp) and the identity suffix of the raf decomposition.
  *   ja_psshout_materialize_ra   init_log_t_rounds (:420-446): ra[j] = prod_phase v[phase][k_bound(j, phase)], v = NUM_PHASES x m Fr;
- *                           the result is the polynomial of the log T cycle rounds (JA_EVAL_IDENT with eq = r_node_output). */
+ *                           the result is the polynomial of the log T cycle rounds (JA_EVAL_IDENT with eq = r_node_output).  v = NULL
+ *                           uses the tables of the last ja_psshout_prove_address; `scale` (NULL = 1) multiplies ra by the constant
+ *                           val + raf_val of the cycle rounds (mod.rs:484-487), so that JA_EVAL_IDENT over the result emits the
+ *                           reference's gruen_poly_deg_2(eval_at_0 * (val + raf_val), claim); its final claim is scale * ra(r).
+ *   ja_psshout_prove_address    the LOG_K address rounds of Sumcheck::prove over ReadRafSumcheckProver<SaturationTable-style clamp,
+ *                           UnaryRafPS> (subprotocols/sumcheck.rs:565-599; mod.rs:337-418 compute_prefix_suffix_prover_message,
+ *                           :491-560 ingest_challenge; lookup_tables/clamp.rs:94-118 combine with prefixes/{higher_all_zero,
+ *                           higher_all_one,lower_word,msb}.rs; ps_shout/unary.rs:45-87 + poly/signed_identity_poly.rs:183-217 for the
+ *                           raf part): runs init_phase on the device at the 8 phase boundaries and the rounds in between on the
+ *                           host, appends every compressed round polynomial [c0, c2] to the transcript, draws the challenges.
+ *                           claim_in = rv_claim + gamma * operand_claim (params.input_claim, mod.rs:108-110); NULL = use the sum the
+ *                           prover derives from its own phase-0 tables, also returned in out_input_claim.  out_val / out_raf_val =
+ *                           val / raf_val of mod.rs:527-556; out_claim = the running claim handed to the cycle rounds. */
 typedef struct ja_psshout ja_psshout;
 enum { JA_SUF_ONE = 0,               /* suffixes/one.rs */
        JA_SUF_HIGHER_ALL_ZERO = 1,   /* suffixes/higher_all_zero.rs:9-29 */
@@ -317,7 +329,13 @@ int32_t ja_psshout_new(ja_ctx*, const uint64_t* lookup_indices, size_t T, const 
                        uint32_t phases, ja_psshout** out);
 int32_t ja_psshout_init_phase(ja_ctx*, ja_psshout*, uint32_t phase, const uint64_t* v_prev, const uint32_t* suffix_kinds, size_t n_suffixes,
                               uint32_t bound, uint64_t* out_Q /* n_suffixes x m Fr */);
-int32_t ja_psshout_materialize_ra(ja_ctx*, ja_psshout*, const uint64_t* v /* phases x m Fr */, ja_poly** out_ra);
+int32_t ja_psshout_materialize_ra(ja_ctx*, ja_psshout*, const uint64_t* v /* phases x m Fr, or NULL */, const uint64_t* scale /* Fr or NULL */,
+                                  ja_poly** out_ra);
+int32_t ja_psshout_prove_address(ja_ctx*, ja_psshout*, uint32_t bound, const uint64_t* gamma, const uint64_t* claim_in /* or NULL */,
+                                 uint8_t transcript_state[32], uint32_t* transcript_n_rounds, uint64_t* out_coeffs /* LOG_K x 2 Fr */,
+                                 uint32_t* out_ncoeffs /* LOG_K */, uint64_t* out_challenges /* LOG_K x 4 limbs */,
+                                 uint64_t* out_input_claim, uint64_t* out_val, uint64_t* out_raf_val, uint64_t* out_claim);
+int32_t ja_psshout_tables(ja_ctx*, ja_psshout*, uint64_t* out_v /* phases x m Fr: the expanding tables of the address rounds */);
 void ja_psshout_free(ja_ctx*, ja_psshout*);
 
 /* ---- witness generation of a fused node on the device (jolt-atlas-core/src/onnx_proof/witness.rs:142-214 generate_node_witnesses) ----

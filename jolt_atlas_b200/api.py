@@ -640,6 +640,14 @@ def commit_one_hot_batches(ctx: Context, srs: SRS, batches):
     return res
 
 
+def fr_add(a, b) -> np.ndarray:
+    """(a + b) mod r on Montgomery limbs (addition does not depend on the representation): host glue between two library calls."""
+    R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    to_i = lambda x: sum(int(v) << (64 * i) for i, v in enumerate(np.asarray(x, dtype=np.uint64).reshape(4)))
+    s_ = (to_i(a) + to_i(b)) % R_MOD
+    return np.array([(s_ >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
 class SuffixKind:
     """Suffix MLEs of the clamp-table family (joltworks/src/lookup_tables/suffixes/) and the identity suffix of the raf decomposition."""
     ONE, HIGHER_ALL_ZERO, HZERO_MUL_LWORD, HONE_MUL_LWORD, IDENTITY = 0, 1, 2, 3, 4
@@ -665,11 +673,38 @@ class PrefixSuffixShout:
                                                   kinds.ctypes.data_as(_lib.u32p), kinds.shape[0], bound, _u64p(out)))
         return out
 
-    def materialize_ra(self, v) -> "MultilinearPolynomial":
-        v = _fr_arg(v).reshape(self.phases * self.m, 4)
+    def materialize_ra(self, v=None, scale=None) -> "MultilinearPolynomial":
+        """v = None: the expanding tables of the last prove_address.  scale: the constant val + raf_val of the cycle rounds, folded into ra."""
+        v = _fr_arg(v).reshape(self.phases * self.m, 4) if v is not None else None
+        sc = _fr_arg(scale).reshape(4) if scale is not None else None
         h = C.c_void_p()
-        check(self.ctx._lib.ja_psshout_materialize_ra(self.ctx._h, self._h, _u64p(v), C.byref(h)))
+        check(self.ctx._lib.ja_psshout_materialize_ra(self.ctx._h, self._h, _u64p(v) if v is not None else None,
+                                                      _u64p(sc) if sc is not None else None, C.byref(h)))
         return MultilinearPolynomial(self.ctx, h)
+
+    def prove_address(self, transcript: "Blake2bTranscriptState", gamma, bound: int, claim=None) -> dict:
+        """The LOG_K address rounds of the read-raf sumcheck (ps_shout/mod.rs:337-418, :491-560 under sumcheck.rs:565-599): the phase
+        passes on the device, the 256-entry rounds on the host next to the library transcript.  claim = None: the prover's own sum."""
+        n = self.log_k
+        out = dict(coeffs=np.zeros((n, 2, 4), dtype=np.uint64), ncoeffs=np.zeros(n, dtype=np.uint32),
+                   challenges=np.zeros((n, 4), dtype=np.uint64), input_claim=np.zeros(4, dtype=np.uint64),
+                   val=np.zeros(4, dtype=np.uint64), raf_val=np.zeros(4, dtype=np.uint64), claim=np.zeros(4, dtype=np.uint64))
+        st = C.create_string_buffer(transcript.state, 32)
+        nr = C.c_uint32(transcript.n_rounds)
+        g = _fr_arg(gamma).reshape(4)
+        cl = _fr_arg(claim).reshape(4) if claim is not None else None
+        check(self.ctx._lib.ja_psshout_prove_address(self.ctx._h, self._h, bound, _u64p(g), _u64p(cl) if cl is not None else None, st,
+                                                     C.byref(nr), _u64p(out["coeffs"]), out["ncoeffs"].ctypes.data_as(_lib.u32p),
+                                                     _u64p(out["challenges"]), _u64p(out["input_claim"]), _u64p(out["val"]),
+                                                     _u64p(out["raf_val"]), _u64p(out["claim"])))
+        transcript.state, transcript.n_rounds = st.raw, nr.value
+        out["msg_bytes"] = 32 * int(out["ncoeffs"].sum())
+        return out
+
+    def tables(self) -> np.ndarray:
+        v = np.zeros((self.phases, self.m, 4), dtype=np.uint64)
+        check(self.ctx._lib.ja_psshout_tables(self.ctx._h, self._h, _u64p(v)))
+        return v
 
     def free(self):
         if self._h:

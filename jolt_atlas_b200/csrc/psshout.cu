@@ -13,6 +13,8 @@
 // suffix.  Tile partials are added by a second small kernel.  Deterministic: field addition is exact in any order.
 #include "common.hpp"
 #include "poly_kernels.cuh"
+#include "sumcheck_host.hpp"
+#include "transcript_host.hpp"
 
 namespace {
 
@@ -231,6 +233,7 @@ struct ja_psshout {
   size_t T = 0;
   uint32_t log_k = 0, phases = 0, log_m = 0;
   uint32_t next_phase = 0;
+  std::vector<ja::host::FrH> h_v;    // expanding tables of ja_psshout_prove_address (phases x m), for ja_psshout_materialize_ra
 };
 
 extern "C" {
@@ -333,20 +336,234 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   return JA_OK;
 }
 
-int32_t ja_psshout_materialize_ra(ja_ctx* c, ja_psshout* p, const uint64_t* v, ja_poly** out_ra) {
-  JA_REQUIRE(c && p && v && out_ra, "ja_psshout_materialize_ra: null argument");
+int32_t ja_psshout_materialize_ra(ja_ctx* c, ja_psshout* p, const uint64_t* v, const uint64_t* scale, ja_poly** out_ra) {
+  JA_REQUIRE(c && p && out_ra, "ja_psshout_materialize_ra: null argument");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   const uint32_t m = 1u << p->log_m;
-  const size_t tab_bytes = (size_t)p->phases * m * sizeof(Fr);
+  const size_t n_tab = (size_t)p->phases * m;
+  const size_t tab_bytes = n_tab * sizeof(Fr);
+  JA_REQUIRE(v || p->h_v.size() == n_tab, "ja_psshout_materialize_ra: no expanding tables (pass v, or run ja_psshout_prove_address first)");
+  std::vector<ja::host::FrH> tab(n_tab);
+  memcpy((void*)tab.data(), v ? (const void*)v : (const void*)p->h_v.data(), tab_bytes);
+  if (scale) {
+    // ra * (val + raf_val) (the constant factor of the cycle rounds, mod.rs:484-487), folded into the LAST expanding table: the
+    // round polynomials of the cycle rounds over the scaled ra are the reference's gruen_poly_deg_2(eval_at_0 * (val + raf_val), claim)
+    const ja::host::FrH sc = ja::host::from_limbs(scale);
+    for (size_t i = n_tab - m; i < n_tab; i++) tab[i] = ja::host::mul(tab[i], sc);
+  }
   Fr* d_v = nullptr;
   int32_t st = dev_alloc(c, tab_bytes, (void**)&d_v);
   if (st) return st;
-  if ((st = stage_h2d(c, d_v, v, tab_bytes))) { dev_free(c, d_v); return st; }
+  if ((st = stage_h2d(c, d_v, tab.data(), tab_bytes))) { dev_free(c, d_v); return st; }
   if ((st = ja_poly_alloc(c, p->T, out_ra))) { dev_free(c, d_v); return st; }
   JA_LAUNCH(c, KC_CONVERT, k_ps_ra<<<grid_for(p->T), kBlock, 0, c->stream>>>(p->d_idx, p->T, d_v, p->phases, p->log_m, (*out_ra)->buf[0]));
   JA_CUDA(cudaGetLastError());
   dev_free(c, d_v);
+  return JA_OK;
+}
+
+// ---- the LOG_K address rounds (ps_shout/mod.rs:337-418, :491-560 under Sumcheck::prove, subprotocols/sumcheck.rs:565-599) ----------
+// The tables of these rounds have m = 2^(LOG_K / phases) <= 256 entries: they stay on the HOST, next to the transcript - a
+// device round would pay a host<->device round trip (3.8 us measured, profiles/r2_persist_probe.txt) for ~1 us of arithmetic.
+// The T-sized work of a phase (init_phase: u_evals update + six suffix-polynomial scatters) is the kernel above; its Q rows
+// arrive in mapped host memory.  The reference evaluates four prefix MLEs per (b, c) and ClampSpec::combine per b
+// (lookup_tables/prefixes/{higher_all_zero,higher_all_one,lower_word,msb}.rs, clamp.rs:94-118).  Those prefixes depend on b only
+// through (1) the indicator that b's "higher" bits are all zero / all one and (2) the integer value of b's lower-word bits, so
+// the sum over b of combine(...) regroups EXACTLY (field arithmetic) into a handful of plain sums of the suffix polynomials over
+// contiguous b ranges and index-weighted sums  sum_b b * Q[b]  (two additions per entry), times per-round scalars: a round costs
+// O(m) additions and ~40 products instead of ~60 m products.  Same for the raf part: the signed-identity prefix polynomial
+// (poly/signed_identity_poly.rs:183-217) is affine in b, so its H2L-bound values are  B + c * kappa + 2^s * b.
+namespace {
+using ja::host::FrH;
+using ja::host::add; using ja::host::sub; using ja::host::mul; using ja::host::dbl; using ja::host::neg;
+
+struct PsCp { bool has = false; FrH v; };
+enum { P_HAZ = 0, P_HAO = 1, P_LW = 2, P_MSB = 3 };
+
+// the b-independent factor / offset of SparseDensePrefix::prefix_mle at round j (r_x = the previous challenge when j is odd)
+static FrH ps_prefix_scalar(int kind, const PsCp cp[4], const FrH* r_x, uint32_t c, unsigned j, unsigned bound_index, const FrH* pow2, unsigned xlen) {
+  const FrH cf = ja::host::from_u64(c);
+  if (kind == P_MSB) return j == 0 ? cf : (j == 1 ? *r_x : cp[P_MSB].v);
+  if (kind == P_HAZ || kind == P_HAO) {
+    const bool zero = kind == P_HAZ;
+    FrH r = cp[kind].has ? cp[kind].v : ja::host::FR_ONE;
+    if (r_x && j > 0 && j - 1 <= bound_index) r = mul(r, zero ? sub(ja::host::FR_ONE, *r_x) : *r_x);
+    if (j <= bound_index) r = mul(r, zero ? sub(ja::host::FR_ONE, cf) : cf);
+    return r;
+  }
+  FrH r = cp[P_LW].has ? cp[P_LW].v : ja::host::FR_ZERO;
+  if (r_x && j > 0 && j - 1 > bound_index) r = add(r, mul(pow2[xlen - (j - 1) - 1], *r_x));
+  if (j > bound_index) r = add(r, mul(pow2[xlen - j - 1], cf));
+  return r;
+}
+static PsCp ps_update_checkpoint(int kind, const PsCp cp[4], const FrH& r_x, const FrH& r_y, unsigned j, unsigned bound_index, const FrH* pow2, unsigned xlen) {
+  PsCp o;
+  if (kind == P_MSB) {
+    if (j == 0) return o;
+    if (j == 1) { o.has = true; o.v = r_x; return o; }
+    return cp[P_MSB];
+  }
+  o.has = true;
+  if (kind == P_HAZ || kind == P_HAO) {
+    const bool zero = kind == P_HAZ;
+    FrH r = cp[kind].has ? cp[kind].v : ja::host::FR_ONE;
+    if (j > 0 && j - 1 <= bound_index) r = mul(r, zero ? sub(ja::host::FR_ONE, r_x) : r_x);
+    if (j <= bound_index) r = mul(r, zero ? sub(ja::host::FR_ONE, r_y) : r_y);
+    o.v = r;
+    return o;
+  }
+  FrH r = cp[P_LW].has ? cp[P_LW].v : ja::host::FR_ZERO;
+  if (j > 0 && j - 1 > bound_index) r = add(r, mul(pow2[xlen - (j - 1) - 1], r_x));
+  if (j > bound_index) r = add(r, mul(pow2[xlen - j - 1], r_y));
+  o.v = r;
+  return o;
+}
+static inline FrH ps_sum(const FrH* x, size_t n) { FrH a = ja::host::FR_ZERO; for (size_t i = 0; i < n; i++) a = add(a, x[i]); return a; }
+// sum_b b * x[b], b < n: the running suffix sum added once per step
+static inline FrH ps_wsum(const FrH* x, size_t n) {
+  FrH acc = ja::host::FR_ZERO, tot = ja::host::FR_ZERO;
+  for (size_t b = n; b-- > 1;) { acc = add(acc, x[b]); tot = add(tot, acc); }
+  return tot;
+}
+struct PsSide { FrH s1, r1, w_all, a_haz, a_hz, a_one, a_w, b_ho, b_one, b_w; };
+}  // namespace
+
+int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const uint64_t* gamma_in, const uint64_t* claim_in, uint8_t state[32],
+                                 uint32_t* n_rounds, uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_input_claim,
+                                 uint64_t* out_val, uint64_t* out_raf_val, uint64_t* out_claim) {
+  JA_REQUIRE(c && p && gamma_in && state && n_rounds && out_coeffs && out_ncoeffs && out_challenges, "ja_psshout_prove_address: null argument");
+  JA_REQUIRE(p->next_phase == 0, "ja_psshout_prove_address: the address rounds start from a fresh state (phase 0)");
+  const unsigned xlen = p->log_k, log_m = p->log_m, phases = p->phases;
+  JA_REQUIRE(bound < xlen && xlen <= 64 && log_m >= 2, "ja_psshout_prove_address: clamp bound must be below the index width");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  const size_t m = size_t(1) << log_m;
+  const unsigned bound_index = xlen - bound - 1;
+  FrH pow2[66];
+  pow2[0] = ja::host::FR_ONE;
+  for (int i = 1; i < 66; i++) pow2[i] = dbl(pow2[i - 1]);
+  const FrH gamma = ja::host::from_limbs(gamma_in);
+  const FrH const_upper = sub(pow2[bound], ja::host::FR_ONE);
+  const FrH lower_coeff = add(dbl(const_upper), ja::host::FR_ONE);
+  const uint32_t kinds[6] = {JA_SUF_HIGHER_ALL_ZERO, JA_SUF_HZERO_MUL_LWORD, JA_SUF_HONE_MUL_LWORD, JA_SUF_ONE, JA_SUF_ONE, JA_SUF_IDENTITY};
+  ja::host::Blake2bTranscript t(state, *n_rounds);
+  PsCp cp[4];
+  FrH cp_id = ja::host::FR_ZERO;                         // PrefixRegistry checkpoint of Prefix::SignedIdentity (None = 0)
+  FrH claim = claim_in ? ja::host::from_limbs(claim_in) : ja::host::FR_ZERO;
+  std::vector<FrH> Qbuf(6 * m), r_all;
+  std::vector<FrH> v_cur, v_next;
+  p->h_v.assign((size_t)phases * m, ja::host::FR_ZERO);
+  FrH r_prev = ja::host::FR_ZERO;
+  for (unsigned phase = 0; phase < phases; phase++) {
+    int32_t st = ja_psshout_init_phase(c, p, phase, phase ? reinterpret_cast<const uint64_t*>(p->h_v.data() + (size_t)(phase - 1) * m) : nullptr,
+                                       kinds, 6, bound, reinterpret_cast<uint64_t*>(Qbuf.data()));
+    if (st) return st;
+    // rows: 0 higher-all-zero, 1 hzero*lword, 2 hone*lword, 3 one (== row 4, the raf decomposition's One suffix), 5 identity
+    FrH* Q[5] = {Qbuf.data(), Qbuf.data() + m, Qbuf.data() + 2 * m, Qbuf.data() + 3 * m, Qbuf.data() + 5 * m};
+    const unsigned s_len = xlen - (phase + 1) * log_m;                 // suffix_len of the phase
+    FrH bid = cp_id;
+    v_cur.assign(1, ja::host::FR_ONE);
+    for (unsigned tt = 0; tt < log_m; tt++) {
+      const unsigned j = phase * log_m + tt, b_len = log_m - 1 - tt;
+      const size_t half = size_t(1) << b_len;
+      const unsigned n_hi = bound_index >= j ? std::min<unsigned>(bound_index - j, b_len) : 0;   // b's top n_hi bits are "higher" bits
+      const unsigned n_lo = b_len - n_hi;
+      const size_t n_z = size_t(1) << n_lo;                            // Z = [0, n_z): higher bits of b all zero; O = [half - n_z, half): all one
+      const size_t o_off = half - n_z;
+      PsSide side[2];
+      for (int sd = 0; sd < 2; sd++) {
+        const size_t off = sd ? half : 0;
+        PsSide& S = side[sd];
+        S.s1 = ps_sum(Q[3] + off, half);
+        S.r1 = ps_sum(Q[4] + off, half);
+        S.w_all = ps_wsum(Q[3] + off, half);
+        S.a_haz = ps_sum(Q[0] + off, n_z);
+        S.a_hz = ps_sum(Q[1] + off, n_z);
+        if (n_hi == 0) { S.a_one = S.s1; S.a_w = S.w_all; S.b_one = S.s1; S.b_w = S.w_all; }
+        else {
+          S.a_one = ps_sum(Q[3] + off, n_z); S.a_w = ps_wsum(Q[3] + off, n_z);
+          S.b_one = ps_sum(Q[3] + off + o_off, n_z); S.b_w = ps_wsum(Q[3] + off + o_off, n_z);   // (b & low_mask) = b - o_off on O
+        }
+        S.b_ho = ps_sum(Q[2] + off + o_off, n_z);
+      }
+      const FrH* r_x = (j & 1) ? &r_prev : nullptr;
+      const FrH two_s = pow2[s_len];
+      const FrH kappa = j == 0 ? neg(pow2[xlen - 1]) : pow2[b_len + s_len];        // coefficient of the current variable in the identity prefix
+      // E(c, side) = sum_b combine(P_c(b), Q_side(b)); raf(c, side) = sum_b P_c(b) Q_one(b) + Q_id(b)
+      auto table_part = [&](uint32_t cc, const PsSide& S) {
+        const FrH hz = ps_prefix_scalar(P_HAZ, cp, r_x, cc, j, bound_index, pow2, xlen), ho = ps_prefix_scalar(P_HAO, cp, r_x, cc, j, bound_index, pow2, xlen);
+        const FrH lw = ps_prefix_scalar(P_LW, cp, r_x, cc, j, bound_index, pow2, xlen), msb = ps_prefix_scalar(P_MSB, cp, r_x, cc, j, bound_index, pow2, xlen);
+        FrH e = mul(sub(const_upper, mul(msb, lower_coeff)), S.s1);
+        const FrH zt = sub(add(add(S.a_hz, mul(lw, S.a_one)), mul(two_s, S.a_w)), mul(const_upper, S.a_haz));
+        const FrH ot = add(add(S.b_ho, mul(lw, S.b_one)), mul(two_s, S.b_w));
+        e = add(e, mul(hz, zt));
+        return add(e, mul(ho, ot));
+      };
+      auto raf_part = [&](uint32_t cc, const PsSide& S) {
+        const FrH base = cc == 0 ? bid : (cc == 1 ? add(bid, kappa) : add(bid, dbl(kappa)));
+        return add(add(mul(base, S.s1), mul(two_s, S.w_all)), S.r1);
+      };
+      if (j == 0) {
+        // the claimed sum as the prover sees it: s(0) + s(1) = rv(r_cycle) + gamma * operand(r_cycle)
+        const FrH s0 = add(table_part(0, side[0]), mul(gamma, raf_part(0, side[0])));
+        const FrH s1 = add(table_part(1, side[1]), mul(gamma, raf_part(1, side[1])));
+        const FrH derived = add(s0, s1);
+        if (out_input_claim) memcpy(out_input_claim, derived.l, 32);
+        if (!claim_in) claim = derived;
+      }
+      const FrH e0 = add(table_part(0, side[0]), mul(gamma, raf_part(0, side[0])));
+      const FrH t2l = table_part(2, side[0]), t2h = table_part(2, side[1]);
+      const FrH a2l = raf_part(2, side[0]), a2r = raf_part(2, side[1]);
+      const FrH e2 = add(sub(dbl(t2h), t2l), mul(gamma, sub(dbl(a2r), a2l)));
+      const ja::host::Coeffs uni = ja::host::from_evals_and_hint(claim, {e0, e2});
+      const ja::host::Coeffs cpr = ja::host::compress(uni);
+      JA_REQUIRE(cpr.size() <= 2, "ja_psshout_prove_address: round polynomial of degree > 2");
+      t.append_message("UniPoly_begin");
+      for (auto& x : cpr) t.append_scalar(x);
+      t.append_message("UniPoly_end");
+      uint64_t ch[4];
+      t.challenge_scalar_optimized(ch);
+      const FrH rj = ja::host::from_limbs(ch);
+      claim = ja::host::evaluate(uni, rj);
+      out_ncoeffs[j] = (uint32_t)cpr.size();
+      for (size_t k = 0; k < 2; k++) memcpy(out_coeffs + 4 * (2 * j + k), k < cpr.size() ? cpr[k].l : ja::host::FR_ZERO.l, 32);
+      memcpy(out_challenges + 4 * j, ch, 32);
+      // ingest_challenge (mod.rs:491-560)
+      for (int q = 0; q < 5; q++)
+        for (size_t b = 0; b < half; b++) Q[q][b] = add(Q[q][b], mul(rj, sub(Q[q][b + half], Q[q][b])));
+      bid = add(bid, mul(rj, kappa));
+      v_next.resize(v_cur.size() * 2);                                             // ExpandingTable::update, HighToLow (expanding_table.rs:76-86)
+      for (size_t i = 0; i < v_cur.size(); i++) { const FrH e1 = mul(rj, v_cur[i]); v_next[2 * i] = sub(v_cur[i], e1); v_next[2 * i + 1] = e1; }
+      v_cur.swap(v_next);
+      if (j & 1) {
+        PsCp prev[4] = {cp[0], cp[1], cp[2], cp[3]};
+        for (int k = 0; k < 4; k++) cp[k] = ps_update_checkpoint(k, prev, r_prev, rj, j, bound_index, pow2, xlen);
+      }
+      r_prev = rj;
+    }
+    cp_id = bid;                                                                   // PrefixRegistry::update_checkpoints
+    memcpy((void*)(p->h_v.data() + (size_t)phase * m), v_cur.data(), m * sizeof(FrH));
+  }
+  // val = combine(prefix checkpoints, suffixes of the empty suffix) (mod.rs:527-552): suffixes [1, 0, 0, 1]
+  {
+    const FrH haz = cp[P_HAZ].has ? cp[P_HAZ].v : ja::host::FR_ONE, hao = cp[P_HAO].has ? cp[P_HAO].v : ja::host::FR_ONE;
+    const FrH lw = cp[P_LW].has ? cp[P_LW].v : ja::host::FR_ZERO, msb = cp[P_MSB].has ? cp[P_MSB].v : ja::host::FR_ZERO;
+    FrH val = sub(const_upper, mul(msb, lower_coeff));
+    val = add(val, mul(haz, sub(lw, const_upper)));
+    val = add(val, mul(hao, lw));
+    const FrH raf_val = mul(gamma, cp_id);                                         // UnaryRafPS::raf_val (unary.rs:82-86)
+    if (out_val) memcpy(out_val, val.l, 32);
+    if (out_raf_val) memcpy(out_raf_val, raf_val.l, 32);
+  }
+  if (out_claim) memcpy(out_claim, claim.l, 32);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+  return JA_OK;
+}
+// the expanding tables of the last ja_psshout_prove_address (phases x m Fr)
+int32_t ja_psshout_tables(ja_ctx* c, ja_psshout* p, uint64_t* out_v) {
+  JA_REQUIRE(c && p && out_v, "ja_psshout_tables: null argument");
+  JA_REQUIRE(p->h_v.size() == ((size_t)p->phases << p->log_m), "ja_psshout_tables: run ja_psshout_prove_address first");
+  memcpy(out_v, p->h_v.data(), p->h_v.size() * sizeof(ja::host::FrH));
   return JA_OK;
 }
 

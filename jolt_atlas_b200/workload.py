@@ -142,6 +142,32 @@ class NodeInputs:
     eq_cols: np.ndarray | None = None
 
 
+MODEL_SCALE = 14      # common/src/consts/general.rs (rescale bits S of Einsum / Mul; Add carries no rescale)
+
+
+def witness_op(spec: NodeSpec):
+    """(FusedWitness op code, rescale bits) of a node."""
+    return {"einsum": (0, MODEL_SCALE), "mul": (1, MODEL_SCALE), "add": (2, 0)}[spec.kind]
+
+
+def host_witness(spec: NodeSpec, A: np.ndarray, B: np.ndarray, T: int):
+    """numpy twin of ja_witness_fused for workload synthesis: (lookup indices (T,) u64, chunk lists (16 [+ 4], T) u32)."""
+    op, S = witness_op(spec)
+    a, b = A.astype(np.int64), B.astype(np.int64)
+    if op == 0:      # i8-range operands, contraction <= 2^10: every partial sum < 2^53, the f64 (BLAS) product is exact
+        acc = (A.astype(np.float64) @ B.astype(np.float64)).astype(np.int64).reshape(-1)
+    else:
+        acc = (a * b).reshape(-1) if op == 1 else (a + b).reshape(-1)
+    pad = np.zeros(T, dtype=np.int64)
+    pad[: acc.shape[0]] = acc
+    q, r = pad >> S, pad & ((1 << S) - 1)
+    idx = q.view(np.uint64)
+    rows = [((idx >> np.uint64(4 * (15 - d))) & np.uint64(15)).astype(np.uint32) for d in range(16)]
+    d_rem = (S + 3) // 4
+    rows += [((r >> (4 * (d_rem - 1 - d))) & 15).astype(np.uint32) for d in range(d_rem)]
+    return np.ascontiguousarray(idx), np.ascontiguousarray(np.stack(rows))
+
+
 def build_inputs(config: str, seed: int | None = None):
     """Seeded synthetic inputs of the traced shapes: i32 tensors in the i8 range (Tensor::random_small,
     atlas-onnx-tracer/src/tensor/mod.rs:178-183), u32 one-hot addresses, 125-bit challenges."""
@@ -151,14 +177,9 @@ def build_inputs(config: str, seed: int | None = None):
     for spec in cfg["nodes"]():
         T = 1 << spec.log_t
         d_hot = D_CLAMP + (0 if spec.kind == "add" else D_REM)
-        ni = NodeInputs(spec=spec, d_hot=d_hot,
-                        hot_k=rng.integers(0, K_CHUNK, size=(d_hot, T), dtype=np.uint32),
+        ni = NodeInputs(spec=spec, d_hot=d_hot, hot_k=None,
                         tables=np.stack([_challenges(rng, K_CHUNK) for _ in range(d_hot)]),
                         eq_w=_challenges(rng, spec.log_t), gammas=_challenges(rng, d_hot), r_addr=_challenges(rng, LOG_K))
-        # pre-clamp accumulations as the clamp lookups see them (clamp_lookups/mod.rs:108-140): mostly small, one in eight saturating
-        small = rng.integers(-(1 << 20), 1 << 20, size=T)
-        big = rng.integers(-(1 << 40), 1 << 40, size=T)
-        ni.acc = np.where(rng.integers(0, 8, size=T) == 0, big, small).astype(np.int64).view(np.uint64)
         if spec.kind == "einsum":
             kp = 1 << (spec.k - 1).bit_length()            # contraction axis zero-padded to a power of two (MLE length)
             ni.A = np.zeros((spec.m, kp), dtype=np.int32)
@@ -170,6 +191,10 @@ def build_inputs(config: str, seed: int | None = None):
         else:
             ni.A = rng.integers(-128, 128, size=T, dtype=np.int32)
             ni.B = rng.integers(-128, 128, size=T, dtype=np.int32)
+        # the node's committed one-hot polynomials are the WITNESS of its operands (witness.rs:142-214): 4-bit chunks of the floor-rebased
+        # i64 accumulation (the clamp lookup index) and of the rescale remainder.  Host copy here (numpy, exact integers) for the
+        # resident leg's uploads and the CPU twin; the end-to-end leg derives them on the device from the operands (FusedWitness).
+        ni.acc, ni.hot_k = host_witness(spec, ni.A, ni.B, T)
         nodes.append(ni)
     ell = cfg["ell"]
     open_point = _challenges(rng, ell)
@@ -189,9 +214,9 @@ def h2d_bytes(inputs) -> int:
     """Bytes of per-proof inputs that cross host->device in the end-to-end path."""
     total = 0
     for ni in inputs["nodes"]:
-        total += ni.hot_k.nbytes                                   # one-hot addresses, 4 B per entry, uploaded once per node
-        total += ni.acc.nbytes                                     # clamp lookup indices (8 B per entry)
-        total += 2 * ni.tables.nbytes + ni.A.nbytes + ni.B.nbytes   # RA tables (gather) + G tables (batched instances)
+        # the one-hot addresses and the clamp lookup indices are generated on the device from the operands (FusedWitness): only
+        # the operands (once for the witness, once more for the operator's own polynomials / folds) and the small tables cross PCIe
+        total += 2 * ni.tables.nbytes + 2 * (ni.A.nbytes + ni.B.nbytes)
     return total
 
 
@@ -234,20 +259,20 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
         return r
     # A. witness commitment of EVERY one-hot polynomial before the IOP, as ONNXProof::prove does
     #    (mod.rs:152-200 step 4: commit_witness_polynomials -> prover.rs:236-249 -> hyperkzg/mod.rs:558-596)
-    hots = []
+    hots, wits = [], []
     if resident:
         for i, ni in enumerate(inputs["nodes"]):
             hots.append((resident["nodes"][i]["hot16"], resident["nodes"][i]["hot4"]))
     else:
-        # every index array of the proof in ONE upload call (copies + device-side validation back to back, one synchronisation)
-        parts, where = [], []
+        # generate_node_witnesses on the device (witness.rs:142-214): the operands go up, the address batches and the clamp lookup
+        # indices are born in HBM - no index array crosses PCIe
         for ni in inputs["nodes"]:
-            where.append((len(parts), len(parts) + 1 if ni.d_hot > D_CLAMP else None))
-            parts.append(ni.hot_k[:D_CLAMP])
-            if ni.d_hot > D_CLAMP:
-                parts.append(ni.hot_k[D_CLAMP:])
-        up = A.OneHotAddresses.upload_many(ctx, parts, K_CHUNK)
-        hots = [(up[a], up[b] if b is not None else None) for a, b in where]
+            op, S = witness_op(ni.spec)
+            ta = A.TensorI32(ctx, ni.A if ni.A.ndim == 2 else ni.A.reshape(1, -1))
+            tb = A.TensorI32(ctx, ni.B if ni.B.ndim == 2 else ni.B.reshape(1, -1))
+            w = A.FusedWitness(ctx, op, ta, tb, S, 1 << ni.spec.log_t)
+            wits.append((w, ta, tb))
+            hots.append((w.clamp, w.rem))
     sharded = comm is not None and comm.world > 1
     in_lib = sharded and getattr(comm, "in_library", False)
     if in_lib:
@@ -262,27 +287,21 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
         spec = ni.spec
         res = resident["nodes"][i] if resident else None
         hot16, hot4 = hots[i]
-        # B. clamp lookup read-raf (ps_shout/mod.rs): the T-sized passes at the 8 phase boundaries on the device (init_phase,
-        #    init_suffix_polys, raf init_Q), then the log T cycle rounds on the materialised ra (mod.rs:420-446, :464-488).
-        #    The 64 address rounds themselves are O(256) host work per round on the Q tables returned here (prefix MLEs with
-        #    checkpoints: joltworks/src/lookup_tables/, the Rust prover's unchanged code) and are NOT reproduced: each phase is
-        #    represented by its transcript traffic only - the phase's suffix polynomials are absorbed (first entry of each), its 8
-        #    challenges drawn, and the expanding table v[phase] built from them (utils/expanding_table.rs:76-86).
+        # B. clamp lookup read-raf (ps_shout/mod.rs; ReadRafSumcheckProver over the saturating clamp table + UnaryRafPS): the 64
+        #    address rounds in 8 phases - the T-sized passes at the phase boundaries on the device (init_phase, init_suffix_polys,
+        #    raf init_Q), the 256-entry rounds on the host next to the transcript (ja_psshout_prove_address) - then the log T cycle
+        #    rounds on the materialised ra * (val + raf_val) (mod.rs:420-446, :464-488).  A REAL sumcheck: the input claim is the
+        #    prover's own rv(r_cycle) + gamma * operand(r_cycle); the cycle rounds continue from the running claim.
         #    ps_shout=False (bench.py's continuity leg): the round-1 stage list - cycle rounds on the first RA polynomial, no phase passes.
         if ps_shout:
-            ps = res["ps"].restart() if res else A.PrefixSuffixShout(ctx, ni.acc, ni.eq_w, CLAMP_LOG_K, PS_PHASES)
-            tr = PAR.Transcript(state=t.state, n_rounds=t.n_rounds)
-            vs = []
-            for phase in range(PS_PHASES):
-                Q = ps.init_phase(phase, vs[-1] if phase else None, _PS_KINDS, SAT_BOUND)
-                tr.append_scalars(Q[:, 0])
-                vs.append(PAR.expanding_table(tr.challenge_optimized(CLAMP_LOG_K // PS_PHASES)))
-                out["msg_bytes"] += Q.nbytes
-            t.state, t.n_rounds = tr.state, tr.n_rounds
-            ra_ps = ps.materialize_ra(np.concatenate(vs))
+            ps = res["ps"].restart() if res else wits[i][0].ps_shout(ni.eq_w, CLAMP_LOG_K, PS_PHASES)
+            pa = ps.prove_address(t, ni.gammas[0], SAT_BOUND)
+            out["msg_bytes"] += pa["msg_bytes"] + PS_PHASES * len(PS_SUFFIXES) * (1 << (CLAMP_LOG_K // PS_PHASES)) * 32   # round polynomials + the Q rows of every phase (mapped memory)
+            out["finals"].append(np.stack([pa["val"], pa["raf_val"], pa["claim"]]))
+            ra_ps = ps.materialize_ra(scale=A.fr_add(pa["val"], pa["raf_val"]))
             if not res:
                 ps.free()
-            _sc(ctx, A.EvalKernel.IDENT, [ra_ps], claim, t, eq_w=ni.eq_w)
+            _sc(ctx, A.EvalKernel.IDENT, [ra_ps], pa["claim"], t, eq_w=ni.eq_w)
             ra_ps.free()
         # C. RA one-hot checks of the clamp lookup (batched: product of 16, Hamming weight, booleanity)
         ra0 = _ra_checks(A, ctx, hot16, ni, 0, D_CLAMP, claim, t, out, _sc, keep_first=not ps_shout)
@@ -296,9 +315,8 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
             eq_c = A.EqPolynomial.evals(ctx, ni.eq_cols)
             if res:                                                        # weights / node inputs resident on the device
                 left, right = res["A"].fold(eq_r, transpose=False), res["B"].fold(eq_c, transpose=True)
-            else:
-                left = A.tensor_fold_i32(ctx, ni.A, eq_r, transpose=False)     # (m x k) folded over rows -> k
-                right = A.tensor_fold_i32(ctx, ni.B, eq_c, transpose=True)     # (k x n) folded over columns -> k
+            else:                                                          # the tensors uploaded for the witness serve the folds too
+                left, right = wits[i][1].fold(eq_r, transpose=False), wits[i][2].fold(eq_c, transpose=True)
             _sc(ctx, A.EvalKernel.DOT2, [left, right], claim, t)
             A.MultilinearPolynomial.free_many([eq_r, eq_c, left, right])
         else:
@@ -344,11 +362,8 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
     else:
         out["open"] = A.hyperkzg_open(ctx, srs, rlc, r["challenges"], t)    # PCS::prove(rlc, r_sumcheck), prover.rs:164-170
     rlc.free()
-    if not resident:
-        for pair in hots:
-            for h in pair:
-                if h is not None:
-                    h.free()
+    for w, ta, tb in wits:
+        w.free(); ta.free(); tb.free()
     out["states"].append(t.state)
     if in_lib:
         comm.shard_off()
@@ -412,9 +427,10 @@ def count_units(inputs) -> dict:
         rounds += (LOG_K + lt) + lt + ((LOG_K + lt) + lt if ni.d_hot > D_CLAMP else 0)     # batched RA checks + cycle rounds
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
     rounds += inputs["ell"]                                             # the batched opening reduction
-    return {"sumcheck_rounds": rounds, "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"],
-            "ps_shout_phase_passes": PS_PHASES * len(inputs["nodes"]),
-            "ps_shout_address_rounds_not_reproduced": CLAMP_LOG_K * len(inputs["nodes"])}
+    addr = CLAMP_LOG_K * len(inputs["nodes"])                           # read-raf address rounds (host, 256-entry tables)
+    return {"sumcheck_rounds": rounds + addr, "sumcheck_rounds_device": rounds, "ps_shout_address_rounds": addr,
+            "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"],
+            "ps_shout_phase_passes": PS_PHASES * len(inputs["nodes"])}
 
 
 # ---- measurement helpers (bench.py) -------------------------------------------------------------------------------

@@ -228,6 +228,47 @@ void orc_psshout_materialize_ra(void* h, const uint64_t* v, uint64_t* out) {
   for (size_t i = 0; i < ra.size(); i++) store_fr(out + 4 * i, ra[i]);
 }
 void orc_psshout_free(void* h) { delete static_cast<PsShout*>(h); }
+// the LOG_K address rounds of Sumcheck::prove over the read-raf instance (subprotocols/sumcheck.rs:565-599 with
+// ps_shout/mod.rs:464-560): compressed round polynomials [c0, c2], challenges, expanding tables, val, raf_val, running claim
+void orc_psshout_prove_address(void* h, unsigned bound, const uint64_t* gamma, const uint64_t* claim_in, uint8_t state[32], uint32_t* n_rounds,
+                               uint64_t* out_coeffs, uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_v, uint64_t* out_val,
+                               uint64_t* out_raf_val, uint64_t* out_claim) {
+  PsShout* p = static_cast<PsShout*>(h);
+  PsReadRaf rr;
+  rr.ps = p; rr.XLEN = p->log_k; rr.BOUND = bound; rr.gamma = Fr::from_raw(gamma);
+  rr.v.resize(p->phases);
+  Transcript t(state, *n_rounds);
+  rr.init_phase(0);
+  Fr claim = claim_in ? Fr::from_raw(claim_in) : rr.derived_input_claim();
+  for (unsigned round = 0; round < p->log_k; round++) {
+    Fr e[2];
+    rr.message(round, e);
+    UniPoly uni = UniPoly::from_evals_and_hint(claim, {e[0], e[1]});
+    std::vector<Fr> cp = uni.compress();
+    append_compressed(t, cp);
+    uint64_t ch[4];
+    t.challenge_optimized(ch);
+    const Fr rj = Fr::from_raw(ch);
+    claim = uni.evaluate(rj);
+    rr.ingest(rj, round);
+    out_ncoeffs[round] = (uint32_t)cp.size();
+    for (size_t k = 0; k < cp.size() && k < 2; k++) store_fr(out_coeffs + 4 * (2 * round + k), cp[k]);
+    memcpy(out_challenges + 4 * round, ch, 32);
+  }
+  const size_t m = size_t(1) << p->log_m;
+  for (unsigned ph = 0; ph < p->phases; ph++)
+    for (size_t i = 0; i < m; i++) store_fr(out_v + 4 * (ph * m + i), rr.v[ph][i]);
+  store_fr(out_val, rr.val); store_fr(out_raf_val, rr.raf_val); store_fr(out_claim, claim);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+void orc_clamp_evaluate_mle(const uint64_t* r, unsigned xlen, unsigned bound, uint64_t* out) {
+  FrVec rr = load_fr(r, xlen);
+  store_fr(out, clamp_evaluate_mle(rr.data(), xlen, bound));
+}
+void orc_signed_identity_evaluate(const uint64_t* r, unsigned n, uint64_t* out) {
+  FrVec rr = load_fr(r, n);
+  store_fr(out, signed_identity_evaluate(rr.data(), n));
+}
 uint64_t orc_suffix_mle(int kind, uint64_t bits, unsigned len, unsigned xlen, unsigned bound) { return suffix_mle(kind, bits, len, xlen, bound); }
 
 // compute_ra_evals (shout.rs:549-598): idx = d x T addresses, out = d x K Fr

@@ -351,10 +351,41 @@ class PsShout:
         lib().orc_psshout_materialize_ra(self._h, _p(np.ascontiguousarray(v, dtype=np.uint64)), _p(out))
         return out
 
+    def prove_address(self, t: "TranscriptState", gamma, claim, bound: int) -> dict:
+        """The LOG_K address rounds of the read-raf sumcheck (ps_shout/mod.rs:337-418, :491-560 under sumcheck.rs:565-599), on a
+        FRESH state (phase 0 not yet initialised).  -> coeffs (rounds, 2, 4) compressed [c0, c2], ncoeffs, challenges, v, val,
+        raf_val, claim (the running claim handed to the cycle rounds)."""
+        log_k = self.phases * (self.m.bit_length() - 1)
+        out = dict(coeffs=np.zeros((log_k, 2, 4), dtype=np.uint64), ncoeffs=np.zeros(log_k, dtype=np.uint32),
+                   challenges=np.zeros((log_k, 4), dtype=np.uint64), v=np.zeros((self.phases, self.m, 4), dtype=np.uint64),
+                   val=np.zeros(4, dtype=np.uint64), raf_val=np.zeros(4, dtype=np.uint64), claim=np.zeros(4, dtype=np.uint64))
+        st = C.create_string_buffer(t.state, 32)
+        nr = C.c_uint32(t.n_rounds)
+        lib().orc_psshout_prove_address(self._h, C.c_uint(bound), _p(np.ascontiguousarray(gamma, dtype=np.uint64)),
+                                        _p(np.ascontiguousarray(claim, dtype=np.uint64)) if claim is not None else None, st, C.byref(nr), _p(out["coeffs"]),
+                                        _p(out["ncoeffs"]), _p(out["challenges"]), _p(out["v"]), _p(out["val"]), _p(out["raf_val"]),
+                                        _p(out["claim"]))
+        t.state, t.n_rounds = st.raw, nr.value
+        return out
+
     def free(self):
         if self._h:
             lib().orc_psshout_free(self._h)
             self._h = None
+
+
+def clamp_evaluate_mle(r, xlen: int, bound: int) -> np.ndarray:
+    """ClampBoundedTable<XLEN, BOUND, true>::evaluate_mle (lookup_tables/clamp.rs:140-192); r = xlen Montgomery coordinates, MSB first."""
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_clamp_evaluate_mle(_p(np.ascontiguousarray(r, dtype=np.uint64)), C.c_uint(xlen), C.c_uint(bound), _p(out))
+    return out
+
+
+def signed_identity_evaluate(r, n: int) -> np.ndarray:
+    """SignedIdentityPoly::evaluate (poly/signed_identity_poly.rs:43-59)."""
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_signed_identity_evaluate(_p(np.ascontiguousarray(r, dtype=np.uint64)), C.c_uint(n), _p(out))
+    return out
 
 
 def suffix_mle(kind: int, bits: int, length: int, xlen: int, bound: int) -> int:

@@ -12,6 +12,10 @@ def accumulate(op: int, A: np.ndarray, B: np.ndarray) -> np.ndarray:
     (sat_binop_intermediate): i64, flattened row-major."""
     a, b = A.astype(np.int64), B.astype(np.int64)
     if op == 0:
+        # exact in f64 (BLAS) whenever every partial sum stays below 2^53; the integer product otherwise
+        bound = int(np.abs(a).max(initial=0)) * int(np.abs(b).max(initial=0)) * a.shape[1]
+        if bound < (1 << 52):
+            return (A.astype(np.float64) @ B.astype(np.float64)).astype(np.int64).reshape(-1)
         return (a @ b).reshape(-1)
     if op == 1:
         return (a * b).reshape(-1)

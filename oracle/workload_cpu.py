@@ -6,6 +6,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import cpu as ORC
+from .pyref import witness as WT
 
 D_CLAMP = 16
 
@@ -38,21 +39,28 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
     nodes = inputs["nodes"] if node_limit is None else inputs["nodes"][:node_limit]
     for ni in (nodes if iop else []):
         spec = ni.spec
+        # witness generation is part of prove (ONNXProof::commit_witness_polynomials, prover.rs:72-87 -> witness.rs:142-214): the twin
+        # re-derives the chunk lists from the operands and checks them against the workload's
+        from jolt_atlas_b200.workload import witness_op
+        op, S = witness_op(spec)
+        idx, _, ck, rk = WT.fused_witness(op, ni.A if ni.A.ndim == 2 else ni.A.reshape(1, -1), ni.B if ni.B.ndim == 2 else ni.B.reshape(1, -1),
+                                          S, 1 << spec.log_t)
+        assert np.array_equal(idx, ni.acc) and np.array_equal(ck, ni.hot_k[:D_CLAMP]) and (rk is None or np.array_equal(rk, ni.hot_k[D_CLAMP:]))
         lists = _index_lists(ni)
         for lo, hi in ((0, D_CLAMP), (D_CLAMP, ni.d_hot)):
             if hi > lo:
                 coms = [ORC.sum_indexed(srs_host, idx) for idx in lists[lo:hi]]
                 out["commitments"].append((np.stack([c[0] for c in coms]), np.array([c[1] for c in coms])))
-        # clamp lookup read-raf: ps_shout phase passes, each phase represented by its transcript traffic (see workload.run_device)
+        # clamp lookup read-raf: the 64 address rounds (8 phase passes + per-b prefix/suffix rounds), then the cycle rounds on
+        # ra * (val + raf_val) from the running claim (see workload.run_device)
         ps = ORC.PsShout(ni.acc, ni.eq_w, 64, 8)
-        vs = []
-        for phase in range(8):
-            Q = ps.init_phase(phase, vs[-1] if phase else None, (1, 2, 3, 0, 0, 4), 31)
-            ORC.transcript_append_scalars(t, Q[:, 0])
-            vs.append(ORC.expanding_table_h2l(ORC.transcript_challenge_optimized(t, 8)))
-        ra_ps = ps.materialize_ra(np.concatenate(vs))
+        pa = ps.prove_address(t, ni.gammas[0], None, 31)
+        out["finals"].append(np.stack([pa["val"], pa["raf_val"], pa["claim"]]))
+        scale = ORC.fr_binop(0, pa["val"].reshape(1, 4), pa["raf_val"].reshape(1, 4))[0]
+        ra_ps = ps.materialize_ra(pa["v"].reshape(-1, 4))
+        ra_ps = ORC.fr_binop(2, ra_ps, np.broadcast_to(scale, ra_ps.shape).copy())
         ps.free()
-        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra_ps]), ni.eq_w, claim, t)
+        r = ORC.sumcheck_prove_st(0, 6, np.stack([ra_ps]), ni.eq_w, pa["claim"], t)
         out["finals"].append(r["final_claims"])
         _ra_checks(ni, 0, D_CLAMP, claim, t, out)
         if spec.kind == "einsum":

@@ -44,3 +44,47 @@ def test_phase_order_is_enforced(ctx):
     with pytest.raises(JoltAtlasError):
         dev.init_phase(1, _chal(rng, 256), [ONE], 31)          # phase 0 first
     dev.free()
+
+
+@pytest.mark.parametrize("log_t,bound,given_claim", [(5, 31, True), (10, 31, False), (14, 31, True), (9, 9, False)])
+def test_address_rounds_match_oracle(ctx, log_t, bound, given_claim):
+    """ja_psshout_prove_address (phase passes on the device, regrouped 256-entry rounds on the host) against the oracle's per-b
+    restatement of ps_shout/mod.rs:337-418, :491-560: round polynomials, challenges, transcript, expanding tables, val, raf_val,
+    running claim - then the cycle rounds over ra * (val + raf_val) against the oracle's scaled IDENT sumcheck."""
+    from jolt_atlas_b200 import api as A
+    from tests.test_oracle_psshout_address import P, clamp_entry, lookup_indices
+    from tests.util import from_mont_array, to_mont_array
+    rng = np.random.default_rng(7 * log_t + bound)
+    T = 1 << log_t
+    idx = lookup_indices(rng, T, bound)
+    r = _chal(rng, log_t)
+    gamma = _chal(rng, 1)[0]
+    # the true input claim rv(r) + gamma * operand(r), brute force
+    eq = from_mont_array(ORC.eq_evals(r))
+    g_i = from_mont_array(gamma.reshape(1, 4))[0]
+    signed = [int(x) - (1 << 64) if int(x) >> 63 else int(x) for x in idx]
+    true_claim = (sum(e * clamp_entry(int(k), bound) for e, k in zip(eq, idx)) + g_i * sum(e * s for e, s in zip(eq, signed))) % P
+    claim = to_mont_array([true_claim])[0]
+    dev, cpu = A.PrefixSuffixShout(ctx, idx, r), ORC.PsShout(idx, r)
+    td, tc = A.Blake2bTranscriptState(b"ps_addr"), ORC.TranscriptState(b"ps_addr")
+    got = dev.prove_address(td, gamma, bound, claim if given_claim else None)
+    want = cpu.prove_address(tc, gamma, claim, bound)
+    assert np.array_equal(got["input_claim"], claim)               # the sum the prover derives from its phase-0 tables IS the claim
+    assert np.array_equal(got["ncoeffs"], want["ncoeffs"])
+    assert np.array_equal(got["coeffs"], want["coeffs"])
+    assert np.array_equal(got["challenges"], want["challenges"])
+    assert td.state == tc.state and td.n_rounds == tc.n_rounds
+    assert np.array_equal(dev.tables(), want["v"])
+    for k in ("val", "raf_val", "claim"):
+        assert np.array_equal(got[k], want[k]), k
+    # cycle rounds: gruen_poly_deg_2(eval_at_0 * (val + raf_val), claim) (mod.rs:464-488) == IDENT over ra * (val + raf_val)
+    scale = ORC.fr_binop(0, got["val"].reshape(1, 4), got["raf_val"].reshape(1, 4))[0]
+    ra = dev.materialize_ra(scale=scale)
+    ra_cpu = cpu.materialize_ra(want["v"].reshape(-1, 4))
+    ra_scaled = ORC.fr_binop(2, ra_cpu, np.broadcast_to(scale, ra_cpu.shape).copy())
+    assert np.array_equal(ra.to_host(), ra_scaled)
+    rd = A.sumcheck_prove(ctx, A.EvalKernel.IDENT, [ra], got["claim"], td, eq_w=r)
+    rc = ORC.sumcheck_prove_st(0, 6, ra_scaled[None], r, want["claim"], tc)
+    assert all(np.array_equal(a, b) for a, b in zip(rd["coeffs"], rc["coeffs"]))
+    assert td.state == tc.state
+    dev.free(); cpu.free()
