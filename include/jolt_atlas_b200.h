@@ -324,7 +324,8 @@ enum { JA_SUF_ONE = 0,               /* suffixes/one.rs */
        JA_SUF_HIGHER_ALL_ZERO = 1,   /* suffixes/higher_all_zero.rs:9-29 */
        JA_SUF_HZERO_MUL_LWORD = 2,   /* suffixes/hzero_mul_lword.rs:9-36 */
        JA_SUF_HONE_MUL_LWORD = 3,    /* suffixes/hone_mul_lword.rs:10-37 */
-       JA_SUF_IDENTITY = 4 };        /* poly/identity_poly.rs (IdentityPolynomial as a SuffixPolynomial: the suffix value) */
+       JA_SUF_IDENTITY = 4,          /* poly/identity_poly.rs:153-158 (IdentityPolynomial as a SuffixPolynomial: the suffix value) */
+       JA_SUF_SHIFT = 5 };           /* poly/identity_poly.rs:160-166 (ShiftSuffixPolynomial: 2^suffix_len) */
 int32_t ja_psshout_new(ja_ctx*, const uint64_t* lookup_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
                        uint32_t phases, ja_psshout** out);
 int32_t ja_psshout_init_phase(ja_ctx*, ja_psshout*, uint32_t phase, const uint64_t* v_prev, const uint32_t* suffix_kinds, size_t n_suffixes,
@@ -335,6 +336,13 @@ int32_t ja_psshout_prove_address(ja_ctx*, ja_psshout*, uint32_t bound, const uin
                                  uint8_t transcript_state[32], uint32_t* transcript_n_rounds, uint64_t* out_coeffs /* LOG_K x 2 Fr */,
                                  uint32_t* out_ncoeffs /* LOG_K */, uint64_t* out_challenges /* LOG_K x 4 limbs */,
                                  uint64_t* out_input_claim, uint64_t* out_val, uint64_t* out_raf_val, uint64_t* out_claim);
+/* IdentityRCProver (subprotocols/identity_range_check.rs:140-325): the LOG_K address rounds of a remainder range check over the
+ * unsigned identity decomposition (suffixes [Shift, Identity], poly/identity_poly.rs:113-166); phases per IdentityRCProvider::phases
+ * (:416-431: LOG_K / 4 if LOG_K % 4 == 0, else LOG_K / 2).  out_raf_val = the identity checkpoint (the constant of the cycle
+ * rounds: ja_psshout_materialize_ra(scale = raf_val) then JA_EVAL_IDENT). */
+int32_t ja_psshout_prove_identity_rc(ja_ctx*, ja_psshout*, const uint64_t* claim_in /* or NULL */, uint8_t transcript_state[32],
+                                     uint32_t* transcript_n_rounds, uint64_t* out_coeffs /* LOG_K x 2 Fr */, uint32_t* out_ncoeffs,
+                                     uint64_t* out_challenges, uint64_t* out_input_claim, uint64_t* out_raf_val, uint64_t* out_claim);
 int32_t ja_psshout_tables(ja_ctx*, ja_psshout*, uint64_t* out_v /* phases x m Fr: the expanding tables of the address rounds */);
 void ja_psshout_free(ja_ctx*, ja_psshout*);
 
@@ -353,6 +361,8 @@ const ja_addr* ja_witness_rem_addr(const ja_witness*);        /* d = ceil(S / 4)
 int32_t ja_witness_to_host(ja_ctx*, const ja_witness*, uint64_t* out_idx /* T */, int32_t* out_i32 /* T */, uint32_t* out_clamp_k /* 16 x T */,
                            uint32_t* out_rem_k /* ceil(S/4) x T */);    /* any pointer may be NULL */
 int32_t ja_psshout_from_witness(ja_ctx*, const ja_witness*, const uint64_t* r_cycle, size_t log_t, uint32_t log_k, uint32_t phases, ja_psshout** out);
+/* ... and over the rescale remainders (LOG_K = scale_bits): the state of the remainder range check */
+int32_t ja_psshout_from_witness_rem(ja_ctx*, const ja_witness*, const uint64_t* r_cycle, size_t log_t, uint32_t phases, ja_psshout** out);
 int32_t ja_psshout_new_dev(ja_ctx*, const unsigned long long* d_indices, size_t T, const uint64_t* r_cycle, size_t log_t, uint32_t log_k,
                            uint32_t phases, ja_psshout** out);          /* lookup indices already in device memory */
 void ja_witness_free(ja_ctx*, ja_witness*);

@@ -650,7 +650,7 @@ def fr_add(a, b) -> np.ndarray:
 
 class SuffixKind:
     """Suffix MLEs of the clamp-table family (joltworks/src/lookup_tables/suffixes/) and the identity suffix of the raf decomposition."""
-    ONE, HIGHER_ALL_ZERO, HZERO_MUL_LWORD, HONE_MUL_LWORD, IDENTITY = 0, 1, 2, 3, 4
+    ONE, HIGHER_ALL_ZERO, HZERO_MUL_LWORD, HONE_MUL_LWORD, IDENTITY, SHIFT = 0, 1, 2, 3, 4, 5
 
 
 class PrefixSuffixShout:
@@ -701,6 +701,23 @@ class PrefixSuffixShout:
         out["msg_bytes"] = 32 * int(out["ncoeffs"].sum())
         return out
 
+    def prove_identity_rc(self, transcript: "Blake2bTranscriptState", claim=None) -> dict:
+        """IdentityRCProver's LOG_K address rounds (identity_range_check.rs:140-325): the remainder range check."""
+        n = self.log_k
+        out = dict(coeffs=np.zeros((n, 2, 4), dtype=np.uint64), ncoeffs=np.zeros(n, dtype=np.uint32),
+                   challenges=np.zeros((n, 4), dtype=np.uint64), input_claim=np.zeros(4, dtype=np.uint64),
+                   raf_val=np.zeros(4, dtype=np.uint64), claim=np.zeros(4, dtype=np.uint64))
+        st = C.create_string_buffer(transcript.state, 32)
+        nr = C.c_uint32(transcript.n_rounds)
+        cl = _fr_arg(claim).reshape(4) if claim is not None else None
+        check(self.ctx._lib.ja_psshout_prove_identity_rc(self.ctx._h, self._h, _u64p(cl) if cl is not None else None, st, C.byref(nr),
+                                                         _u64p(out["coeffs"]), out["ncoeffs"].ctypes.data_as(_lib.u32p),
+                                                         _u64p(out["challenges"]), _u64p(out["input_claim"]), _u64p(out["raf_val"]),
+                                                         _u64p(out["claim"])))
+        transcript.state, transcript.n_rounds = st.raw, nr.value
+        out["msg_bytes"] = 32 * int(out["ncoeffs"].sum())
+        return out
+
     def tables(self) -> np.ndarray:
         v = np.zeros((self.phases, self.m, 4), dtype=np.uint64)
         check(self.ctx._lib.ja_psshout_tables(self.ctx._h, self._h, _u64p(v)))
@@ -719,7 +736,7 @@ class FusedWitness:
     EINSUM_MK_KN, MUL, ADD, SUB = 0, 1, 2, 3
 
     def __init__(self, ctx: Context, op: int, A: "TensorI32", B: "TensorI32", scale_bits: int, T: int):
-        self.ctx, self.T = ctx, T
+        self.ctx, self.T, self.scale_bits = ctx, T, scale_bits
         h = C.c_void_p()
         check(ctx._lib.ja_witness_fused(ctx._h, op, A._h, B._h, scale_bits, T, C.byref(h)))
         self._h = h
@@ -733,6 +750,16 @@ class FusedWitness:
         ps.ctx, ps.T, ps.log_k, ps.phases, ps.m = self.ctx, self.T, log_k, phases, 1 << (log_k // phases)
         h = C.c_void_p()
         check(self.ctx._lib.ja_psshout_from_witness(self.ctx._h, self._h, _u64p(r), r.shape[0], log_k, phases, C.byref(h)))
+        ps._h = h
+        return ps
+
+    def rem_shout(self, r_cycle, phases: int) -> "PrefixSuffixShout":
+        """ps_shout state of the remainder range check (LOG_K = the rescale bits)."""
+        r = _fr_arg(r_cycle).reshape(-1, 4)
+        ps = PrefixSuffixShout.__new__(PrefixSuffixShout)
+        ps.ctx, ps.T, ps.log_k, ps.phases, ps.m = self.ctx, self.T, self.scale_bits, phases, 1 << (self.scale_bits // phases)
+        h = C.c_void_p()
+        check(self.ctx._lib.ja_psshout_from_witness_rem(self.ctx._h, self._h, _u64p(r), r.shape[0], phases, C.byref(h)))
         ps._h = h
         return ps
 

@@ -36,6 +36,7 @@ JA_DEV unsigned long long suffix_mle(uint32_t kind, unsigned long long bits, uin
       const unsigned long long ones = hi_len >= 64 ? ~0ull : ((1ull << hi_len) - 1);
       return hi == ones ? low : 0ull;
     }
+    case JA_SUF_SHIFT: return 1ull << len;   // ShiftSuffixPolynomial (poly/identity_poly.rs:160-166)
     default: return bits;   // JA_SUF_IDENTITY
   }
 }
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
     for (int s = 0; s < NSUF; s++) {
       if (s0 + s >= a.n_suf) break;
       const uint32_t kind = a.kinds[s0 + s];
-      const int halves = (kind == JA_SUF_IDENTITY && a.suffix_len > 32) ? 2 : 1;     // only the identity suffix exceeds 32 bits
+      const int halves = ((kind == JA_SUF_IDENTITY && a.suffix_len > 32) || (kind == JA_SUF_SHIFT && a.suffix_len >= 32)) ? 2 : 1;   // only the identity / shift suffixes exceed 32 bits
 #pragma unroll 1
       for (int h = 0; h < halves; h++) {
         unsigned long long acc[9];
@@ -277,7 +278,7 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   JA_REQUIRE(c && p && suffix_kinds && out_Q && n_suffixes >= 1 && n_suffixes <= (size_t)kPsMaxSuffixes, "ja_psshout_init_phase: bad argument");
   JA_REQUIRE(phase == p->next_phase && phase < p->phases, "ja_psshout_init_phase: phases run in order 0 .. NUM_PHASES - 1");
   JA_REQUIRE((phase == 0) == (v_prev == nullptr), "ja_psshout_init_phase: the expanding table of the previous phase is required from phase 1 on");
-  for (size_t s = 0; s < n_suffixes; s++) JA_REQUIRE(suffix_kinds[s] <= JA_SUF_IDENTITY, "ja_psshout_init_phase: unknown suffix kind");
+  for (size_t s = 0; s < n_suffixes; s++) JA_REQUIRE(suffix_kinds[s] <= JA_SUF_SHIFT, "ja_psshout_init_phase: unknown suffix kind");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   JA_CUDA(cudaSetDevice(c->device));
   const uint32_t m = 1u << p->log_m;
@@ -555,6 +556,85 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
     if (out_val) memcpy(out_val, val.l, 32);
     if (out_raf_val) memcpy(out_raf_val, raf_val.l, 32);
   }
+  if (out_claim) memcpy(out_claim, claim.l, 32);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+  return JA_OK;
+}
+// IdentityRCProver (joltworks/src/subprotocols/identity_range_check.rs:140-325): the LOG_K address rounds of the remainder range
+// check - the unsigned identity prefix-suffix decomposition alone (poly/identity_poly.rs:113-166: suffixes [Shift, Identity],
+// prefix polynomial  checkpoint * 2^chunk_len + i), no lookup table.  Same split as above: phase passes on the device, the
+// m-entry rounds on the host; the prefix polynomial is affine in b, so a round is two plain sums and one index-weighted sum.
+int32_t ja_psshout_prove_identity_rc(ja_ctx* c, ja_psshout* p, const uint64_t* claim_in, uint8_t state[32], uint32_t* n_rounds, uint64_t* out_coeffs,
+                                     uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_input_claim, uint64_t* out_raf_val,
+                                     uint64_t* out_claim) {
+  JA_REQUIRE(c && p && state && n_rounds && out_coeffs && out_ncoeffs && out_challenges, "ja_psshout_prove_identity_rc: null argument");
+  JA_REQUIRE(p->next_phase == 0, "ja_psshout_prove_identity_rc: the address rounds start from a fresh state (phase 0)");
+  const unsigned log_m = p->log_m, phases = p->phases;
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  const size_t m = size_t(1) << log_m;
+  FrH pow2[66];
+  pow2[0] = ja::host::FR_ONE;
+  for (int i = 1; i < 66; i++) pow2[i] = dbl(pow2[i - 1]);
+  const uint32_t kinds[2] = {JA_SUF_SHIFT, JA_SUF_IDENTITY};
+  ja::host::Blake2bTranscript t(state, *n_rounds);
+  FrH cp = ja::host::FR_ZERO;                                      // PrefixRegistry checkpoint of Prefix::Identity (None = 0)
+  FrH claim = claim_in ? ja::host::from_limbs(claim_in) : ja::host::FR_ZERO;
+  std::vector<FrH> Qbuf(2 * m), v_cur, v_next;
+  p->h_v.assign((size_t)phases * m, ja::host::FR_ZERO);
+  for (unsigned phase = 0; phase < phases; phase++) {
+    int32_t st = ja_psshout_init_phase(c, p, phase, phase ? reinterpret_cast<const uint64_t*>(p->h_v.data() + (size_t)(phase - 1) * m) : nullptr,
+                                       kinds, 2, 0, reinterpret_cast<uint64_t*>(Qbuf.data()));
+    if (st) return st;
+    FrH* Q0 = Qbuf.data();
+    FrH* Q1 = Qbuf.data() + m;
+    FrH bid = mul(cp, pow2[log_m]);                                  // identity_poly.rs:143-147: bound_value * 2^chunk_len + i
+    v_cur.assign(1, ja::host::FR_ONE);
+    for (unsigned tt = 0; tt < log_m; tt++) {
+      const unsigned j = phase * log_m + tt, b_len = log_m - 1 - tt;
+      const size_t half = size_t(1) << b_len;
+      const FrH kappa = pow2[b_len];
+      FrH s0[2], w0[2], s1[2];
+      for (int sd = 0; sd < 2; sd++) {
+        const size_t off = sd ? half : 0;
+        s0[sd] = ps_sum(Q0 + off, half); w0[sd] = ps_wsum(Q0 + off, half); s1[sd] = ps_sum(Q1 + off, half);
+      }
+      auto part = [&](uint32_t cc, int sd) {
+        const FrH base = cc == 0 ? bid : (cc == 1 ? add(bid, kappa) : add(bid, dbl(kappa)));
+        return add(add(mul(base, s0[sd]), w0[sd]), s1[sd]);
+      };
+      if (j == 0) {
+        const FrH derived = add(part(0, 0), part(1, 1));
+        if (out_input_claim) memcpy(out_input_claim, derived.l, 32);
+        if (!claim_in) claim = derived;
+      }
+      const FrH e0 = part(0, 0);
+      const FrH e2 = sub(dbl(part(2, 1)), part(2, 0));
+      const ja::host::Coeffs uni = ja::host::from_evals_and_hint(claim, {e0, e2});
+      const ja::host::Coeffs cpr = ja::host::compress(uni);
+      JA_REQUIRE(cpr.size() <= 2, "ja_psshout_prove_identity_rc: round polynomial of degree > 2");
+      t.append_message("UniPoly_begin");
+      for (auto& x : cpr) t.append_scalar(x);
+      t.append_message("UniPoly_end");
+      uint64_t ch[4];
+      t.challenge_scalar_optimized(ch);
+      const FrH rj = ja::host::from_limbs(ch);
+      claim = ja::host::evaluate(uni, rj);
+      out_ncoeffs[j] = (uint32_t)cpr.size();
+      for (size_t k = 0; k < 2; k++) memcpy(out_coeffs + 4 * (2 * j + k), k < cpr.size() ? cpr[k].l : ja::host::FR_ZERO.l, 32);
+      memcpy(out_challenges + 4 * j, ch, 32);
+      for (size_t b = 0; b < half; b++) {
+        Q0[b] = add(Q0[b], mul(rj, sub(Q0[b + half], Q0[b])));
+        Q1[b] = add(Q1[b], mul(rj, sub(Q1[b + half], Q1[b])));
+      }
+      bid = add(bid, mul(rj, kappa));
+      v_next.resize(v_cur.size() * 2);
+      for (size_t i = 0; i < v_cur.size(); i++) { const FrH e1 = mul(rj, v_cur[i]); v_next[2 * i] = sub(v_cur[i], e1); v_next[2 * i + 1] = e1; }
+      v_cur.swap(v_next);
+    }
+    cp = bid;
+    memcpy((void*)(p->h_v.data() + (size_t)phase * m), v_cur.data(), m * sizeof(FrH));
+  }
+  if (out_raf_val) memcpy(out_raf_val, cp.l, 32);                   // identity_range_check.rs:316-319
   if (out_claim) memcpy(out_claim, claim.l, 32);
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
   return JA_OK;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kBlock) k_wit_elementwise(int op, const int* _
 __global__ void __launch_bounds__(kBlock)
 k_wit_chunks(const long long* __restrict__ acc, size_t n_valid, size_t T, uint32_t scale_bits, uint32_t d_rem,
              unsigned long long* __restrict__ idx /* T */, uint32_t* __restrict__ clamp_k /* 16 x T */, uint32_t* __restrict__ rem_k /* d_rem x T */,
-             int* __restrict__ out_i32 /* T */) {
+             int* __restrict__ out_i32 /* T */, unsigned long long* __restrict__ rem_idx /* T, or null */) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += stride) {
     const long long v = t < n_valid ? acc[t] : 0ll;
@@ -55,6 +55,7 @@ k_wit_chunks(const long long* __restrict__ acc, size_t n_valid, size_t T, uint32
     const unsigned long long r = (unsigned long long)v & ((1ull << scale_bits) - 1);     // rem_euclid
     const unsigned long long uq = (unsigned long long)q;
     idx[t] = uq;
+    if (rem_idx) rem_idx[t] = r;
 #pragma unroll
     for (int d = 0; d < 16; d++) clamp_k[(size_t)d * T + t] = (uint32_t)((uq >> (4 * (15 - d))) & 15ull);
     for (uint32_t d = 0; d < d_rem; d++) rem_k[(size_t)d * T + t] = (uint32_t)((r >> (4 * (d_rem - 1 - d))) & 15ull);
@@ -68,6 +69,8 @@ k_wit_chunks(const long long* __restrict__ acc, size_t n_valid, size_t T, uint32
 struct ja_witness {
   unsigned long long* d_idx = nullptr;     // T lookup indices of the clamp read-raf (quotient as u64)
   int* d_out = nullptr;                    // T clamped outputs
+  unsigned long long* d_rem_idx = nullptr; // T rescale remainders: the lookup indices of the remainder range check (absent for scale 0)
+  uint32_t scale_bits = 0;
   ja_addr* clamp = nullptr;                // 16 x T, K = 16
   ja_addr* rem = nullptr;                  // ceil(S / 4) x T, K = 16 (absent for scale 0)
   size_t T = 0;
@@ -90,14 +93,15 @@ int32_t ja_witness_fused(ja_ctx* c, int32_t op, const ja_tensor_i32* A, const ja
   JA_CUDA(cudaSetDevice(c->device));
   const uint32_t d_rem = (scale_bits + 3) / 4;
   std::unique_ptr<ja_witness> w(new ja_witness());
-  w->T = T;
+  w->T = T; w->scale_bits = scale_bits;
   long long* d_acc = nullptr;
   int32_t st;
   if ((st = dev_alloc(c, n_valid * 8, (void**)&d_acc))) return st;
   uint32_t *d_ck = nullptr, *d_rk = nullptr;
   if ((st = dev_alloc(c, T * 8, (void**)&w->d_idx)) || (st = dev_alloc(c, T * 4, (void**)&w->d_out)) ||
-      (st = dev_alloc(c, 16 * T * 4, (void**)&d_ck)) || (d_rem && (st = dev_alloc(c, (size_t)d_rem * T * 4, (void**)&d_rk)))) {
-    dev_free(c, d_acc); dev_free(c, w->d_idx); dev_free(c, w->d_out); dev_free(c, d_ck); dev_free(c, d_rk);
+      (st = dev_alloc(c, 16 * T * 4, (void**)&d_ck)) || (d_rem && (st = dev_alloc(c, (size_t)d_rem * T * 4, (void**)&d_rk))) ||
+      (d_rem && (st = dev_alloc(c, T * 8, (void**)&w->d_rem_idx)))) {
+    dev_free(c, d_acc); dev_free(c, w->d_idx); dev_free(c, w->d_out); dev_free(c, d_ck); dev_free(c, d_rk); dev_free(c, w->d_rem_idx);
     return st;
   }
   if (op == JA_WIT_EINSUM_MK_KN) {
@@ -106,7 +110,7 @@ int32_t ja_witness_fused(ja_ctx* c, int32_t op, const ja_tensor_i32* A, const ja
   } else {
     JA_LAUNCH(c, KC_TENSOR_FOLD, k_wit_elementwise<<<grid_for(n_valid), kBlock, 0, c->stream>>>(op, A->data, B->data, n_valid, d_acc));
   }
-  JA_LAUNCH(c, KC_CONVERT, k_wit_chunks<<<grid_for(T), kBlock, 0, c->stream>>>(d_acc, n_valid, T, scale_bits, d_rem, w->d_idx, d_ck, d_rk, w->d_out));
+  JA_LAUNCH(c, KC_CONVERT, k_wit_chunks<<<grid_for(T), kBlock, 0, c->stream>>>(d_acc, n_valid, T, scale_bits, d_rem, w->d_idx, d_ck, d_rk, w->d_out, w->d_rem_idx));
   JA_CUDA(cudaGetLastError());
   dev_free(c, d_acc);                                  // stream-ordered reuse
   w->clamp = new ja_addr();
@@ -137,11 +141,18 @@ int32_t ja_psshout_from_witness(ja_ctx* c, const ja_witness* w, const uint64_t* 
   return ja_psshout_new_dev(c, w->d_idx, w->T, r_cycle, log_t, log_k, phases, out);
 }
 
+// ps_shout state of the remainder range check (IdentityRCProver over the rescale remainders): LOG_K = the rescale bits
+int32_t ja_psshout_from_witness_rem(ja_ctx* c, const ja_witness* w, const uint64_t* r_cycle, size_t log_t, uint32_t phases, ja_psshout** out) {
+  JA_REQUIRE(c && w && out && (size_t(1) << log_t) == w->T, "ja_psshout_from_witness_rem: T = 2^log_t");
+  JA_REQUIRE(w->d_rem_idx, "ja_psshout_from_witness_rem: the node has no rescale remainder (scale 0)");
+  return ja_psshout_new_dev(c, w->d_rem_idx, w->T, r_cycle, log_t, w->scale_bits, phases, out);
+}
+
 void ja_witness_free(ja_ctx* c, ja_witness* w) {
   if (!c || !w) return;
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   cudaSetDevice(c->device);
-  dev_free(c, w->d_idx); dev_free(c, w->d_out);
+  dev_free(c, w->d_idx); dev_free(c, w->d_out); dev_free(c, w->d_rem_idx);
   if (w->clamp) { dev_free(c, w->clamp->d_k); delete w->clamp; }
   if (w->rem) { dev_free(c, w->rem->d_k); delete w->rem; }
   delete w;

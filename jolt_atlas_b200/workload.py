@@ -135,6 +135,7 @@ class NodeInputs:
     eq_w: np.ndarray           # (log_t, 4) eq point of the node's split-eq sumchecks
     gammas: np.ndarray         # (d_hot, 4) batching coefficients (booleanity gammas; Hamming-weight gamma powers stand-ins)
     r_addr: np.ndarray = None  # (log K, 4) booleanity address point
+    rem: np.ndarray = None     # (T,) uint64: the rescale remainders = lookup indices of the remainder range check
     acc: np.ndarray = None     # (T,) uint64: the pre-clamp i64 accumulations (two's complement) = lookup indices of the clamp read-raf
     A: np.ndarray | None = None    # einsum left operand (m x k) i32 / mul, add: left operand (T,) i32
     B: np.ndarray | None = None
@@ -151,7 +152,7 @@ def witness_op(spec: NodeSpec):
 
 
 def host_witness(spec: NodeSpec, A: np.ndarray, B: np.ndarray, T: int):
-    """numpy twin of ja_witness_fused for workload synthesis: (lookup indices (T,) u64, chunk lists (16 [+ 4], T) u32)."""
+    """numpy twin of ja_witness_fused for workload synthesis: (lookup indices (T,) u64, remainders (T,) u64, chunk lists (16 [+ 4], T) u32)."""
     op, S = witness_op(spec)
     a, b = A.astype(np.int64), B.astype(np.int64)
     if op == 0:      # i8-range operands, contraction <= 2^10: every partial sum < 2^53, the f64 (BLAS) product is exact
@@ -165,7 +166,29 @@ def host_witness(spec: NodeSpec, A: np.ndarray, B: np.ndarray, T: int):
     rows = [((idx >> np.uint64(4 * (15 - d))) & np.uint64(15)).astype(np.uint32) for d in range(16)]
     d_rem = (S + 3) // 4
     rows += [((r >> (4 * (d_rem - 1 - d))) & 15).astype(np.uint32) for d in range(d_rem)]
-    return np.ascontiguousarray(idx), np.ascontiguousarray(np.stack(rows))
+    return np.ascontiguousarray(idx), np.ascontiguousarray(r.astype(np.uint64)), np.ascontiguousarray(np.stack(rows))
+
+
+def device_rc_phases(log_k: int) -> int:
+    """Phase count of the device prover for a LOG_K-bit identity range check.  The phase structure is the prover's own choice: a
+    round polynomial is a sum over the remaining address bits and the cycles whatever chunking computes it, and
+    ra = prod_phase v[phase][chunk] = eq(r_address, k) for every chunking - so the device uses the FEWEST phases its kernel takes
+    (chunks of at most 8 bits: 2 T-sized passes instead of the reference's 7 for LOG_K = 14) and emits the reference's transcript bit
+    for bit (tests/test_gpu_psshout.py::test_identity_rc_phase_count_is_free)."""
+    n = 1
+    while log_k % n or log_k // n > 8:
+        n += 1
+    return n
+
+
+def identity_rc_phases(log_k: int) -> int:
+    """IdentityRCProvider::phases (joltworks/src/subprotocols/identity_range_check.rs:416-431)."""
+    if log_k <= 2:
+        return 1
+    if log_k % 4 == 0:
+        return log_k // 4
+    assert log_k % 2 == 0, "odd LOG_K is not supported by the prefix-suffix decomposition"
+    return log_k // 2
 
 
 def build_inputs(config: str, seed: int | None = None):
@@ -194,7 +217,7 @@ def build_inputs(config: str, seed: int | None = None):
         # the node's committed one-hot polynomials are the WITNESS of its operands (witness.rs:142-214): 4-bit chunks of the floor-rebased
         # i64 accumulation (the clamp lookup index) and of the rescale remainder.  Host copy here (numpy, exact integers) for the
         # resident leg's uploads and the CPU twin; the end-to-end leg derives them on the device from the operands (FusedWitness).
-        ni.acc, ni.hot_k = host_witness(spec, ni.A, ni.B, T)
+        ni.acc, ni.rem, ni.hot_k = host_witness(spec, ni.A, ni.B, T)
         nodes.append(ni)
     ell = cfg["ell"]
     open_point = _challenges(rng, ell)
@@ -328,10 +351,22 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
             A.MultilinearPolynomial.free_many([a, b])
         if hot4 is not None:
             # F. remainder RA checks (batched: product of d = 4, Hamming weight, booleanity)
-            rem0 = _ra_checks(A, ctx, hot4, ni, D_CLAMP, ni.d_hot, claim, t, out, _sc)
-            # E. remainder range-check cycle rounds (identity_range_check.rs:332-358)
-            _sc(ctx, A.EvalKernel.IDENT, [rem0], claim, t, eq_w=ni.eq_w)
-            rem0.free()
+            rem0 = _ra_checks(A, ctx, hot4, ni, D_CLAMP, ni.d_hot, claim, t, out, _sc, keep_first=not ps_shout)
+            # E. remainder range check (IdentityRCProver, identity_range_check.rs:140-325): LOG_K = 14 address rounds in 7 phases
+            #    (phase passes on the device, 4-entry rounds on the host), then the cycle rounds on ra * raf_val (:253-283)
+            if ps_shout:
+                rp = res["ps_rem"].restart() if res else wits[i][0].rem_shout(ni.eq_w, device_rc_phases(MODEL_SCALE))
+                pr = rp.prove_identity_rc(t)
+                out["msg_bytes"] += pr["msg_bytes"] + rp.phases * 2 * rp.m * 32
+                out["finals"].append(np.stack([pr["raf_val"], pr["claim"]]))
+                ra_rem = rp.materialize_ra(scale=pr["raf_val"])
+                if not res:
+                    rp.free()
+                _sc(ctx, A.EvalKernel.IDENT, [ra_rem], pr["claim"], t, eq_w=ni.eq_w)
+                ra_rem.free()
+            else:
+                _sc(ctx, A.EvalKernel.IDENT, [rem0], claim, t, eq_w=ni.eq_w)
+                rem0.free()
         out["states"].append(t.state)
     # G. prove_reduced_openings (prover.rs:141-176): ONE BatchedSumcheck over every committed polynomial
     #    (opening_proof.rs:500-532), gamma powers (:611-643), the materialised RLC (rlc_polynomial.rs:13-78) and the
@@ -376,6 +411,7 @@ def make_resident(ctx, inputs):
     nodes = []
     for ni in inputs["nodes"]:
         d = {"ps": _ResidentPs(ctx, A, ni),
+             "ps_rem": _ResidentPs(ctx, A, ni, rem=True) if ni.d_hot > D_CLAMP else None,
              "hot16": A.OneHotAddresses(ctx, ni.hot_k[:D_CLAMP], K_CHUNK),
              "hot4": A.OneHotAddresses(ctx, ni.hot_k[D_CLAMP:], K_CHUNK) if ni.d_hot > D_CLAMP else None}
         if ni.spec.kind != "einsum":
@@ -393,12 +429,15 @@ class _ResidentPs:
     without re-uploading the indices is not part of the C ABI, so the resident leg re-creates the state from host indices kept
     pinned; only the index upload (8 B per entry) is repeated."""
 
-    def __init__(self, ctx, A, ni):
-        self.ctx, self.A, self.ni, self.cur = ctx, A, ni, None
+    def __init__(self, ctx, A, ni, rem=False):
+        self.ctx, self.A, self.ni, self.cur, self.rem = ctx, A, ni, None, rem
 
     def restart(self):
         self.free()
-        self.cur = self.A.PrefixSuffixShout(self.ctx, self.ni.acc, self.ni.eq_w, CLAMP_LOG_K, PS_PHASES)
+        if self.rem:
+            self.cur = self.A.PrefixSuffixShout(self.ctx, self.ni.rem, self.ni.eq_w, MODEL_SCALE, device_rc_phases(MODEL_SCALE))
+        else:
+            self.cur = self.A.PrefixSuffixShout(self.ctx, self.ni.acc, self.ni.eq_w, CLAMP_LOG_K, PS_PHASES)
         return self.cur
 
     def free(self):
@@ -410,6 +449,8 @@ class _ResidentPs:
 def free_resident(res):
     for d in res["nodes"]:
         d["ps"].free()
+        if d["ps_rem"] is not None:
+            d["ps_rem"].free()
         d["hot16"].free()
         if d["hot4"] is not None:
             d["hot4"].free()
@@ -427,10 +468,11 @@ def count_units(inputs) -> dict:
         rounds += (LOG_K + lt) + lt + ((LOG_K + lt) + lt if ni.d_hot > D_CLAMP else 0)     # batched RA checks + cycle rounds
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
     rounds += inputs["ell"]                                             # the batched opening reduction
-    addr = CLAMP_LOG_K * len(inputs["nodes"])                           # read-raf address rounds (host, 256-entry tables)
+    n_rem = sum(1 for ni in inputs["nodes"] if ni.d_hot > D_CLAMP)
+    addr = CLAMP_LOG_K * len(inputs["nodes"]) + MODEL_SCALE * n_rem     # read-raf + remainder range-check address rounds (host, small tables)
     return {"sumcheck_rounds": rounds + addr, "sumcheck_rounds_device": rounds, "ps_shout_address_rounds": addr,
             "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"],
-            "ps_shout_phase_passes": PS_PHASES * len(inputs["nodes"])}
+            "ps_shout_phase_passes": PS_PHASES * len(inputs["nodes"]) + device_rc_phases(MODEL_SCALE) * n_rem}
 
 
 # ---- measurement helpers (bench.py) -------------------------------------------------------------------------------

@@ -261,6 +261,35 @@ void orc_psshout_prove_address(void* h, unsigned bound, const uint64_t* gamma, c
   store_fr(out_val, rr.val); store_fr(out_raf_val, rr.raf_val); store_fr(out_claim, claim);
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
 }
+void orc_psshout_prove_identity_rc(void* h, const uint64_t* claim_in, uint8_t state[32], uint32_t* n_rounds, uint64_t* out_coeffs,
+                                   uint32_t* out_ncoeffs, uint64_t* out_challenges, uint64_t* out_v, uint64_t* out_raf_val, uint64_t* out_claim) {
+  PsShout* p = static_cast<PsShout*>(h);
+  PsIdentityRC rc;
+  rc.ps = p; rc.v.resize(p->phases);
+  Transcript t(state, *n_rounds);
+  rc.init_phase(0);
+  Fr claim = claim_in ? Fr::from_raw(claim_in) : rc.derived_input_claim();
+  for (unsigned round = 0; round < p->log_k; round++) {
+    Fr e[2];
+    rc.message(e);
+    UniPoly uni = UniPoly::from_evals_and_hint(claim, {e[0], e[1]});
+    std::vector<Fr> cp = uni.compress();
+    append_compressed(t, cp);
+    uint64_t ch[4];
+    t.challenge_optimized(ch);
+    const Fr rj = Fr::from_raw(ch);
+    claim = uni.evaluate(rj);
+    rc.ingest(rj, round);
+    out_ncoeffs[round] = (uint32_t)cp.size();
+    for (size_t k = 0; k < cp.size() && k < 2; k++) store_fr(out_coeffs + 4 * (2 * round + k), cp[k]);
+    memcpy(out_challenges + 4 * round, ch, 32);
+  }
+  const size_t m = size_t(1) << p->log_m;
+  for (unsigned ph = 0; ph < p->phases; ph++)
+    for (size_t i = 0; i < m; i++) store_fr(out_v + 4 * (ph * m + i), rc.v[ph][i]);
+  store_fr(out_raf_val, rc.raf_val); store_fr(out_claim, claim);
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
 void orc_clamp_evaluate_mle(const uint64_t* r, unsigned xlen, unsigned bound, uint64_t* out) {
   FrVec rr = load_fr(r, xlen);
   store_fr(out, clamp_evaluate_mle(rr.data(), xlen, bound));

@@ -17,12 +17,13 @@ inline void lb_split(uint64_t bits, unsigned len, unsigned suffix_len, uint64_t*
   (void)len;
 }
 
-enum { SUF_ONE = 0, SUF_HIGHER_ALL_ZERO = 1, SUF_HZERO_MUL_LWORD = 2, SUF_HONE_MUL_LWORD = 3, SUF_IDENTITY = 4 };
+enum { SUF_ONE = 0, SUF_HIGHER_ALL_ZERO = 1, SUF_HZERO_MUL_LWORD = 2, SUF_HONE_MUL_LWORD = 3, SUF_IDENTITY = 4, SUF_SHIFT = 5 };
 
 // suffixes/higher_all_zero.rs:9-29, hzero_mul_lword.rs:9-36, hone_mul_lword.rs:10-37, one.rs, identity as a suffix polynomial
 inline uint64_t suffix_mle(int kind, uint64_t bits_u64, unsigned len, unsigned XLEN, unsigned BOUND) {
   if (kind == SUF_ONE) return 1;
   if (kind == SUF_IDENTITY) return bits_u64;
+  if (kind == SUF_SHIFT) return uint64_t(1) << len;      // ShiftSuffixPolynomial (poly/identity_poly.rs:160-166)
   const unsigned bound_index = XLEN - BOUND - 1;
   const unsigned suffix_start_index = XLEN - len;
   uint64_t lower_word = 0;
@@ -300,6 +301,57 @@ struct PsReadRaf {
       val = clamp_combine(p, s, BOUND);
       raf_val = gamma * cp_id.v;                                                               // UnaryRafPS::raf_val (unary.rs:82-86)
     }
+  }
+};
+
+
+// IdentityRCProver (subprotocols/identity_range_check.rs:140-325), address rounds: PrefixSuffixDecomposition<F, 2, false> over
+// IdentityPolynomial (poly/identity_poly.rs:113-166), per b as the reference sums it (poly/prefix_suffix.rs:437-482)
+struct PsIdentityRC {
+  PsShout* ps = nullptr;
+  OptFr cp;                          // PrefixRegistry checkpoint of Prefix::Identity
+  std::vector<Fr> Q[2], P;
+  std::vector<std::vector<Fr>> v;
+  Fr raf_val;
+  void init_phase(unsigned phase) {  // identity_range_check.rs:188-207
+    const uint32_t kinds[2] = {SUF_SHIFT, SUF_IDENTITY};
+    const size_t m = size_t(1) << ps->log_m;
+    std::vector<Fr> all = ps->init_phase(phase, phase ? v[phase - 1].data() : nullptr, kinds, 2, 0);
+    for (int s = 0; s < 2; s++) Q[s].assign(all.begin() + s * m, all.begin() + (s + 1) * m);
+    const Fr bound_value = cp.has ? cp.v : Fr::zero();
+    P.assign(m, Fr::zero());
+    for (size_t i = 0; i < m; i++) P[i] = bound_value * two_pow(ps->log_m) + Fr::from_u64(i);   // identity_poly.rs:143-147
+    v[phase].assign(1, Fr::one());
+  }
+  void message(Fr out[2]) const {    // prover_msg (:215-229)
+    const size_t half = Q[0].size() / 2;
+    Fr e0 = Fr::zero(), e2 = Fr::zero();
+    for (size_t b = 0; b < half; b++) {
+      const Fr pe0 = P[b], pe2 = P[b + half] + P[b + half] - P[b];
+      const Fr a0 = pe0 * Q[0][b] + Q[1][b];
+      const Fr a2l = pe2 * Q[0][b] + Q[1][b];
+      const Fr a2r = pe2 * Q[0][b + half] + Q[1][b + half];
+      e0 += a0; e2 += a2r + a2r - a2l;
+    }
+    out[0] = e0; out[1] = e2;
+  }
+  Fr derived_input_claim() const {
+    Fr acc = Fr::zero();
+    for (size_t i = 0; i < Q[0].size(); i++) acc += P[i] * Q[0][i] + Q[1][i];
+    return acc;
+  }
+  void ingest(const Fr& rj, unsigned round) {   // :286-311
+    const unsigned log_m = ps->log_m, phase = round / log_m;
+    PsReadRaf::bind_h2l(Q[0], rj); PsReadRaf::bind_h2l(Q[1], rj); PsReadRaf::bind_h2l(P, rj);
+    std::vector<Fr>& t = v[phase];
+    std::vector<Fr> nv(t.size() * 2);
+    for (size_t i = 0; i < t.size(); i++) { const Fr e1 = rj * t[i]; nv[2 * i] = t[i] - e1; nv[2 * i + 1] = e1; }
+    t.swap(nv);
+    if ((round + 1) % log_m == 0) {
+      cp.has = true; cp.v = P[0];
+      if (phase != ps->phases - 1) init_phase(phase + 1);
+    }
+    if (round + 1 == ps->log_k) raf_val = cp.v;
   }
 };
 

@@ -368,6 +368,20 @@ class PsShout:
         t.state, t.n_rounds = st.raw, nr.value
         return out
 
+    def prove_identity_rc(self, t: "TranscriptState", claim) -> dict:
+        """IdentityRCProver's LOG_K address rounds (identity_range_check.rs:140-325) on a fresh state; claim None = derived."""
+        log_k = self.phases * (self.m.bit_length() - 1)
+        out = dict(coeffs=np.zeros((log_k, 2, 4), dtype=np.uint64), ncoeffs=np.zeros(log_k, dtype=np.uint32),
+                   challenges=np.zeros((log_k, 4), dtype=np.uint64), v=np.zeros((self.phases, self.m, 4), dtype=np.uint64),
+                   raf_val=np.zeros(4, dtype=np.uint64), claim=np.zeros(4, dtype=np.uint64))
+        st = C.create_string_buffer(t.state, 32)
+        nr = C.c_uint32(t.n_rounds)
+        lib().orc_psshout_prove_identity_rc(self._h, _p(np.ascontiguousarray(claim, dtype=np.uint64)) if claim is not None else None, st,
+                                            C.byref(nr), _p(out["coeffs"]), _p(out["ncoeffs"]), _p(out["challenges"]), _p(out["v"]),
+                                            _p(out["raf_val"]), _p(out["claim"]))
+        t.state, t.n_rounds = st.raw, nr.value
+        return out
+
     def free(self):
         if self._h:
             lib().orc_psshout_free(self._h)

@@ -72,8 +72,16 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
             r = ORC.sumcheck_prove_st(0, 2 if spec.kind == "mul" else 0, np.stack([a, b]), ni.eq_w, claim, t)
         out["finals"].append(r["final_claims"])
         if ni.d_hot > D_CLAMP:
-            rem0 = _ra_checks(ni, D_CLAMP, ni.d_hot, claim, t, out)
-            r = ORC.sumcheck_prove_st(0, 6, np.stack([rem0]), ni.eq_w, claim, t)
+            _ra_checks(ni, D_CLAMP, ni.d_hot, claim, t, out)
+            # remainder range check: IdentityRCProver's 14 address rounds (7 phases), then the cycle rounds on ra * raf_val
+            from jolt_atlas_b200.workload import identity_rc_phases
+            rp = ORC.PsShout(ni.rem, ni.eq_w, S, identity_rc_phases(S))
+            pr = rp.prove_identity_rc(t, None)
+            out["finals"].append(np.stack([pr["raf_val"], pr["claim"]]))
+            ra_rem = rp.materialize_ra(pr["v"].reshape(-1, 4))
+            ra_rem = ORC.fr_binop(2, ra_rem, np.broadcast_to(pr["raf_val"], ra_rem.shape).copy())
+            rp.free()
+            r = ORC.sumcheck_prove_st(0, 6, np.stack([ra_rem]), ni.eq_w, pr["claim"], t)
             out["finals"].append(r["final_claims"])
         out["states"].append(t.state)
     if do_open:

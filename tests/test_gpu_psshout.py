@@ -88,3 +88,57 @@ def test_address_rounds_match_oracle(ctx, log_t, bound, given_claim):
     assert all(np.array_equal(a, b) for a, b in zip(rd["coeffs"], rc["coeffs"]))
     assert td.state == tc.state
     dev.free(); cpu.free()
+
+
+@pytest.mark.parametrize("log_t,log_k,phases,given_claim", [(5, 14, 7, True), (12, 14, 7, False), (14, 16, 4, False), (9, 8, 2, True)])
+def test_identity_range_check_rounds_match_oracle(ctx, log_t, log_k, phases, given_claim):
+    """ja_psshout_prove_identity_rc against the oracle's per-b IdentityRCProver (identity_range_check.rs:140-325), then the cycle
+    rounds over ra * raf_val against the oracle's IDENT sumcheck (gruen_poly_deg_2(eval_at_0 * raf_val, claim), :253-283)."""
+    from jolt_atlas_b200 import api as A
+    from tests.test_oracle_psshout_address import P
+    from tests.util import from_mont_array, to_mont_array
+    rng = np.random.default_rng(13 * log_t + log_k)
+    T = 1 << log_t
+    idx = rng.integers(0, 1 << log_k, size=T, dtype=np.uint64)
+    r = _chal(rng, log_t)
+    eq = from_mont_array(ORC.eq_evals(r))
+    claim = to_mont_array([sum(e * int(k) for e, k in zip(eq, idx)) % P])[0]
+    dev, cpu = A.PrefixSuffixShout(ctx, idx, r, log_k, phases), ORC.PsShout(idx, r, log_k, phases)
+    td, tc = A.Blake2bTranscriptState(b"identity_rc"), ORC.TranscriptState(b"identity_rc")
+    got = dev.prove_identity_rc(td, claim if given_claim else None)
+    want = cpu.prove_identity_rc(tc, claim)
+    assert np.array_equal(got["input_claim"], claim)
+    for k in ("ncoeffs", "coeffs", "challenges", "raf_val", "claim"):
+        assert np.array_equal(got[k], want[k]), k
+    assert td.state == tc.state and td.n_rounds == tc.n_rounds
+    assert np.array_equal(dev.tables(), want["v"])
+    ra = dev.materialize_ra(scale=got["raf_val"])
+    ra_cpu = cpu.materialize_ra(want["v"].reshape(-1, 4))
+    ra_scaled = ORC.fr_binop(2, ra_cpu, np.broadcast_to(want["raf_val"], ra_cpu.shape).copy())
+    assert np.array_equal(ra.to_host(), ra_scaled)
+    rd = A.sumcheck_prove(ctx, A.EvalKernel.IDENT, [ra], got["claim"], td, eq_w=r)
+    rc = ORC.sumcheck_prove_st(0, 6, ra_scaled[None], r, want["claim"], tc)
+    assert all(np.array_equal(a, b) for a, b in zip(rd["coeffs"], rc["coeffs"]))
+    assert td.state == tc.state
+    dev.free(); cpu.free()
+
+
+def test_identity_rc_phase_count_is_free(ctx):
+    """The device prover with 2 phases of 7 bits emits the transcript of the reference's 7 phases of 2 bits (LOG_K = 14): round
+    polynomials, challenges, raf_val, running claim and the materialised ra are identical - the chunking is a prover-side choice."""
+    from jolt_atlas_b200 import api as A
+    from jolt_atlas_b200.workload import device_rc_phases, identity_rc_phases
+    rng = np.random.default_rng(5)
+    log_t, log_k = 11, 14
+    assert (device_rc_phases(log_k), identity_rc_phases(log_k)) == (2, 7)
+    idx = rng.integers(0, 1 << log_k, size=1 << log_t, dtype=np.uint64)
+    r = _chal(rng, log_t)
+    dev, cpu = A.PrefixSuffixShout(ctx, idx, r, log_k, 2), ORC.PsShout(idx, r, log_k, 7)
+    td, tc = A.Blake2bTranscriptState(b"rc"), ORC.TranscriptState(b"rc")
+    got, want = dev.prove_identity_rc(td), cpu.prove_identity_rc(tc, None)
+    for k in ("ncoeffs", "coeffs", "challenges", "raf_val", "claim"):
+        assert np.array_equal(got[k], want[k]), k
+    assert td.state == tc.state
+    ra = dev.materialize_ra()
+    assert np.array_equal(ra.to_host(), cpu.materialize_ra(want["v"].reshape(-1, 4)))
+    ra.free(); dev.free(); cpu.free()

@@ -57,3 +57,26 @@ def test_device_born_addresses_commit_and_ps_shout(ctx):
     for o in (p1, p2, *up, srs, ta, tb):
         o.free()
     w.free()
+
+
+def test_remainder_range_check_from_device_witness(ctx):
+    """The remainder lookup indices born on the device (ja_psshout_from_witness_rem) drive IdentityRCProver's address rounds to the
+    same proof as the oracle over the numpy witness' remainders."""
+    from jolt_atlas_b200 import api as A
+    from jolt_atlas_b200.workload import identity_rc_phases
+    from oracle.pyref import witness as WT
+    rng = np.random.default_rng(77)
+    a = rng.integers(-128, 128, size=(16, 32), dtype=np.int32)
+    b = rng.integers(-128, 128, size=(32, 16), dtype=np.int32)
+    S, T = 14, 256
+    ta, tb = A.TensorI32(ctx, a), A.TensorI32(ctx, b)
+    w = A.FusedWitness(ctx, 0, ta, tb, S, T)
+    acc = WT.accumulate(0, a, b)
+    rem = (acc & ((1 << S) - 1)).astype(np.uint64)
+    r = np.ascontiguousarray(rng.integers(1, 1 << 60, size=(8, 4), dtype=np.uint64))
+    r[:, 3] &= np.uint64((1 << 58) - 1)
+    dev, cpu = w.rem_shout(r, identity_rc_phases(S)), ORC.PsShout(rem, r, S, identity_rc_phases(S))
+    td, tc = A.Blake2bTranscriptState(b"rem"), ORC.TranscriptState(b"rem")
+    got, want = dev.prove_identity_rc(td), cpu.prove_identity_rc(tc, None)
+    assert np.array_equal(got["coeffs"], want["coeffs"]) and td.state == tc.state
+    dev.free(); cpu.free(); w.free(); ta.free(); tb.free()

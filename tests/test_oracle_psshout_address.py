@@ -95,3 +95,42 @@ def test_expanding_tables_match_the_challenges():
     out = c["out"]
     for ph in range(8):
         assert np.array_equal(out["v"][ph], ORC.expanding_table_h2l(out["challenges"][8 * ph: 8 * ph + 8]))
+
+
+@pytest.mark.parametrize("seed,log_t,log_k,phases", [(1, 5, 14, 7), (2, 7, 16, 4), (3, 4, 8, 2)])
+def test_identity_range_check_rounds_verify(seed, log_t, log_k, phases):
+    """IdentityRCProver (identity_range_check.rs:140-325) pinned by IdentityRCVerifier::expected_output_claim (:369-389): after the
+    LOG_K address rounds the claim is  sum_j eq(r, j) * ra(r_address, j) * IdentityPolynomial(r_address); the input claim is the
+    brute-force MLE of the remainders at r.  Phases per IdentityRCProvider::phases (:416-431)."""
+    rng = np.random.default_rng(seed)
+    T = 1 << log_t
+    idx = rng.integers(0, 1 << log_k, size=T, dtype=np.uint64)
+    idx[:2] = [0, (1 << log_k) - 1]
+    r_cycle = to_mont_array([int(x) for x in rng.integers(1, 1 << 62, size=log_t)])
+    eq = from_mont_array(ORC.eq_evals(r_cycle))
+    claim = sum(e * int(k) for e, k in zip(eq, idx)) % P
+    t = ORC.TranscriptState(b"identity_rc")
+    ps = ORC.PsShout(idx, r_cycle, log_k, phases)
+    out = ps.prove_identity_rc(t, to_mont_array([claim])[0])
+    ps.free()
+    ps2, t2 = ORC.PsShout(idx, r_cycle, log_k, phases), ORC.TranscriptState(b"identity_rc")
+    out2 = ps2.prove_identity_rc(t2, None)                          # derived claim == true claim: same proof
+    ps2.free()
+    assert np.array_equal(out["coeffs"], out2["coeffs"]) and t.state == t2.state
+    ch = from_mont_array(out["challenges"])
+    for j in range(log_k):
+        c0, c2 = from_mont_array(out["coeffs"][j])
+        c1 = (claim - 2 * c0 - c2) % P
+        claim = (c0 + c1 * ch[j] + c2 * ch[j] * ch[j]) % P
+    assert claim == from_mont_array(out["claim"].reshape(1, 4))[0]
+    ident = sum(ch[i] << (log_k - 1 - i) for i in range(log_k)) % P          # IdentityPolynomial::evaluate, big-endian point
+    assert ident == from_mont_array(out["raf_val"].reshape(1, 4))[0]
+    log_m = log_k // phases
+    v = [from_mont_array(out["v"][ph]) for ph in range(phases)]
+    total = 0
+    for e, k in zip(eq, idx):
+        ra = 1
+        for ph in range(phases):
+            ra = ra * v[ph][(int(k) >> (log_m * (phases - 1 - ph))) & ((1 << log_m) - 1)] % P
+        total += e * ra
+    assert claim == total % P * ident % P
