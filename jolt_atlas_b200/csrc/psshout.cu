@@ -10,7 +10,7 @@
 // Scatter by an 8-bit key without atomics on field elements: a block = m key bins (one thread each) scans a tile of entries
 // staged in shared memory; every entry hits exactly one bin, whose thread adds u * t for every suffix as a 320-bit integer
 // (t < 2^32: acc320_mad; the 64-bit Identity suffix goes through one Montgomery product) - one reduction per bin, tile and
-// suffix.  Tile partials are added by a second small kernel.  Deterministic: field addition is exact in any order.
+// suffix.  Deterministic: the columns are integer sums, exact in any order.
 #include "common.hpp"
 #include "poly_kernels.cuh"
 #include "sumcheck_host.hpp"
@@ -47,10 +47,10 @@ struct PsPhaseArgs {
   uint32_t prev_shift;             // k_bound of the previous phase = (k >> prev_shift) & m_mask
   uint32_t suffix_len, m_mask, bound, n_suf;
   uint32_t kinds[kPsMaxSuffixes];
-  Fr* partial;                     // [gridDim.x][n_suf][m]
+  unsigned long long* gcols;       // [n_suf][m][kPsCols] global column table, zero on entry, zeroed again by the folding block
   unsigned int* counter;           // zero on entry, reset on exit
-  Fr* host_out;                    // n_suf x m results, host-mapped
-  volatile unsigned int* host_seq; unsigned int seq_value;
+  Fr* host_out;                    // n_suf x m results, host-mapped, tagged 48-byte elements (store_tagged)
+  unsigned int seq_value;
 };
 JA_DEV Fr fr_ld_cg(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -65,10 +65,7 @@ constexpr int kPsCols = 2 * kPsLimbs;  // ... held as 16-bit columns in 32-bit c
 // Scatter-add by an 8-bit key with INTEGER atomics on shared memory.  A (bin, suffix) accumulator is 24 columns: column c counts
 // the 16-bit digits of weight 2^(16 c) of the plain integer products u * t (u a Montgomery residue < p, t < 2^64 in two 32-bit
 // halves), so no carry is ever resolved atomically and one carry propagation + one Montgomery fold per accumulator finishes the
-// block.  A thread takes kPsRun CONSECUTIVE entries and adds their limb columns in registers for as long as the key stays the same
-// (clamp lookups send almost every entry of the early phases to the bins 0x00 / 0xff: one flush per thread, suffix and half
-// instead of one per entry), then flushes the run with native 32-bit shared-memory atomics.
-constexpr int kPsRun = 2;
+// block.
 // A block accumulates kPsSufPerBlock suffixes (blockIdx.y selects which): 48 KB of static shared memory, no opt-in carve-out
 // (a 147 KB dynamic allocation for all six suffixes made every launch reconfigure the SM's L1 / shared split).
 constexpr int kPsSufPerBlock = 2;
@@ -80,100 +77,124 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
   const uint32_t s0 = blockIdx.y * NSUF;                  // first suffix of this block
   for (uint32_t i = threadIdx.x; i < n_acc * kPsCols; i += blockDim.x) s_acc[i] = 0u;
   __syncthreads();
-  const size_t chunk = (size_t)blockDim.x * kPsRun;
-  for (size_t base = (size_t)blockIdx.x * chunk; base < a.T; base += (size_t)gridDim.x * chunk) {
-    Fr u[kPsRun];
-    unsigned long long sb[kPsRun];
-    uint32_t key[kPsRun];
-#pragma unroll
-    for (int e = 0; e < kPsRun; e++) {
-      const size_t j = base + (size_t)threadIdx.x * kPsRun + e;
-      key[e] = 0xffffffffu; sb[e] = 0ull; u[e] = fp_zero<FrParams>();
-      if (j < a.T) {
-        const unsigned long long k = a.idx[j];
-        u[e] = fp_load(a.u + j);
-        if (a.v_prev) {                                                 // init_phase: u_evals[j] *= v[phase - 1][k_bound]
-          u[e] = fp_mul<FrParams>(u[e], fp_load(a.v_prev + ((k >> a.prev_shift) & a.m_mask)));
-          if (blockIdx.y == gridDim.y - 1) fp_store(a.u_out + j, u[e]);  // every suffix group forms the same product; one of them keeps it
-        }
-        sb[e] = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
-        key[e] = (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask);
+  const uint32_t lane = threadIdx.x & 31;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < a.T; base += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = base + threadIdx.x;
+    Fr u = fp_zero<FrParams>();
+    unsigned long long sb = 0ull;
+    uint32_t key = 0xffffffffu;                                         // no entry
+    if (j < a.T) {
+      const unsigned long long k = a.idx[j];
+      u = fp_load(a.u + j);
+      if (a.v_prev) {                                                   // init_phase: u_evals[j] *= v[phase - 1][k_bound]
+        u = fp_mul<FrParams>(u, fp_load(a.v_prev + ((k >> a.prev_shift) & a.m_mask)));
+        if (blockIdx.y == gridDim.y - 1) fp_store(a.u_out + j, u);       // every suffix group forms the same product; one of them keeps it
       }
+      sb = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
+      key = (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask);
     }
+    // Shared-memory atomics cost 2 cycles per LANE (64 per warp instruction, 18 of them per entry, suffix and half), and clamp
+    // lookups send whole warps to the bins 0x00 / 0xff in most phases.  So the warp first settles its (up to) two most common bins
+    // with FULL-mask warp reductions - lanes outside the bin contribute zeros, one lane issues the 18 atomics - and only the
+    // lanes left over use their own atomics.  hot[0] = lane 0's bin, hot[1] = the first bin that differs from it.
+    uint32_t hot[2];
+    unsigned hot_mask[2];
+    hot[0] = __shfl_sync(0xffffffffu, key, 0);
+    hot_mask[0] = __ballot_sync(0xffffffffu, key == hot[0]);
+    {
+      const unsigned rest = ~hot_mask[0];
+      const int src = rest ? __ffs(rest) - 1 : 0;
+      hot[1] = __shfl_sync(0xffffffffu, key, src);
+      hot_mask[1] = rest ? __ballot_sync(0xffffffffu, key == hot[1]) : (__ballot_sync(0xffffffffu, false));
+    }
+    int mine = -1;                                                      // which hot pass covers this lane (-1: own atomics)
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+      if (hot[g] != 0xffffffffu && __popc(hot_mask[g]) >= 4 && key == hot[g]) mine = g;
 #pragma unroll 1
     for (int s = 0; s < NSUF; s++) {
       if (s0 + s >= a.n_suf) break;
       const uint32_t kind = a.kinds[s0 + s];
       const int halves = ((kind == JA_SUF_IDENTITY && a.suffix_len > 32) || (kind == JA_SUF_SHIFT && a.suffix_len >= 32)) ? 2 : 1;   // only the identity / shift suffixes exceed 32 bits
+      const unsigned long long t = key != 0xffffffffu ? suffix_mle(kind, sb, a.suffix_len, a.bound) : 0ull;
 #pragma unroll 1
       for (int h = 0; h < halves; h++) {
-        unsigned long long acc[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) acc[i] = 0ull;
-        uint32_t cur = 0xffffffffu;
-        bool dirty = false;
-#pragma unroll
-        for (int e = 0; e <= kPsRun; e++) {
-          const uint32_t ke = e < kPsRun ? key[e] : 0xffffffffu;
-          if (e == kPsRun) {
-            // end of the thread's run: when the WHOLE warp holds the same key (the skewed phases) the lanes' columns are added with
-            // warp reductions and one lane issues the atomics - 32 lanes hammering one shared-memory word serialise otherwise
-            const uint32_t kk = dirty ? cur : 0xfffffffeu;
-            const uint32_t k0 = __shfl_sync(0xffffffffu, kk, 0);
-            if (__all_sync(0xffffffffu, kk == k0) && k0 < 0xfffffffeu) {
-              unsigned int* dst = s_acc + ((size_t)k0 * NSUF + s) * kPsCols + 2 * h;
-#pragma unroll
-              for (int i = 0; i < 9; i++) {
-                // acc[i] < 2^34: three digits of 16 / 16 / 2+ bits, each warp sum below 2^21
-                const unsigned d0 = __reduce_add_sync(0xffffffffu, (unsigned)(acc[i] & 0xffffull));
-                const unsigned d1 = __reduce_add_sync(0xffffffffu, (unsigned)((acc[i] >> 16) & 0xffffull));
-                const unsigned d2 = __reduce_add_sync(0xffffffffu, (unsigned)(acc[i] >> 32));
-                if ((threadIdx.x & 31) == 0) {
-                  if (d0) atomicAdd(dst + 2 * i, d0);
-                  const unsigned hi = d1 + (d2 << 16);
-                  if (hi) atomicAdd(dst + 2 * i + 1, hi);
-                }
-              }
-              dirty = false;
-            }
-          }
-          if (dirty && ke != cur) {                                      // the run ends: flush it
-            unsigned int* dst = s_acc + ((size_t)cur * NSUF + s) * kPsCols + 2 * h;
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-              const unsigned int lo = (unsigned int)(acc[i] & 0xffffull), hi = (unsigned int)(acc[i] >> 16);
-              if (lo) atomicAdd(dst + 2 * i, lo);
-              if (hi) atomicAdd(dst + 2 * i + 1, hi);
-              acc[i] = 0ull;
-            }
-            dirty = false;
-          }
-          if (e == kPsRun || ke == 0xffffffffu) continue;
-          cur = ke;
-          const unsigned long long t = suffix_mle(kind, sb[e], a.suffix_len, a.bound);
-          const uint32_t th = h == 0 ? (uint32_t)t : (uint32_t)(t >> 32);
-          if (th == 0) continue;
+        const uint32_t th = h == 0 ? (uint32_t)t : (uint32_t)(t >> 32);
+        uint32_t prod[9];                                               // u * th, 288 bits
+        {
           unsigned long long c = 0;
 #pragma unroll
-          for (int i = 0; i < 8; i++) { c += (unsigned long long)u[e].l[i] * th; acc[i] += c & 0xffffffffull; c >>= 32; }   // c < 2^64
-          acc[8] += c;
-          dirty = true;
+          for (int i = 0; i < 8; i++) { c += (unsigned long long)u.l[i] * th; prod[i] = (uint32_t)c; c >>= 32; }
+          prod[8] = (uint32_t)c;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+          if (hot[g] == 0xffffffffu || __popc(hot_mask[g]) < 4) continue;          // warp-uniform
+          if (__ballot_sync(0xffffffffu, mine == g && th != 0u) == 0u) continue;   // nothing to add for this bin (warp-uniform)
+          unsigned int* dst = s_acc + ((size_t)hot[g] * NSUF + s) * kPsCols + 2 * h;
+          const bool in = mine == g;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            const uint32_t v = in ? prod[i] : 0u;
+            const unsigned d0 = __reduce_add_sync(0xffffffffu, v & 0xffffu);       // 32 digits of 16 bits: below 2^21
+            const unsigned d1 = __reduce_add_sync(0xffffffffu, v >> 16);
+            if (lane == 0) {
+              if (d0) atomicAdd(dst + 2 * i, d0);
+              if (d1) atomicAdd(dst + 2 * i + 1, d1);
+            }
+          }
+        }
+        if (mine < 0 && th != 0u && key != 0xffffffffu) {
+          unsigned int* dst = s_acc + ((size_t)key * NSUF + s) * kPsCols + 2 * h;
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            const unsigned int lo = prod[i] & 0xffffu, hi = prod[i] >> 16;
+            if (lo) atomicAdd(dst + 2 * i, lo);
+            if (hi) atomicAdd(dst + 2 * i + 1, hi);
+          }
         }
       }
     }
   }
   __syncthreads();
-  // accumulator -> field element: carry-propagate the 16-bit columns into a 384+ bit integer X = lo + hi 2^256, X mod p = mont(1_mont, lo) + mont(R^2, hi)
+  // block -> grid: the non-zero 16-bit columns go to the phase's global column table with 64-bit reductions at L2 (fire and forget;
+  // a column is a plain integer sum, so no carry is resolved here either).  No per-tile fold, no partial tables: the fold to a field
+  // element happens ONCE per accumulator, in the block that finishes last.
+  for (uint32_t i = threadIdx.x; i < n_acc * kPsCols; i += blockDim.x) {
+    const unsigned int v = s_acc[i];
+    if (v == 0u) continue;
+    const uint32_t q = i / kPsCols, col = i % kPsCols;
+    const uint32_t key = q / NSUF, sfx = s0 + q % NSUF;
+    if (sfx < a.n_suf) atomicAdd(a.gcols + ((size_t)sfx * m + key) * kPsCols + col, (unsigned long long)v);
+  }
+  // the block that finishes last in its suffix group folds the group's accumulators and stores them to the host (mapped memory);
+  // the group that finishes last raises the flag: one launch per phase, no D2H copy call
+  __threadfence();
+  __syncthreads();                                       // the shared accumulators are dead from here: word 0 carries the "last block" flag
+  if (threadIdx.x == 0) s_acc[0] = atomicInc(a.counter + 1 + blockIdx.y, gridDim.x - 1) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_acc[0]) return;
+  __threadfence();
   for (uint32_t q = threadIdx.x; q < n_acc; q += blockDim.x) {
-    const unsigned int* acc = s_acc + (size_t)q * kPsCols;
+    const uint32_t sfx = s0 + q / m, key = q % m;
+    if (sfx >= a.n_suf) continue;
+    unsigned long long* g = a.gcols + ((size_t)sfx * m + key) * kPsCols;
+    unsigned long long cols[kPsCols];
+#pragma unroll
+    for (int i = 0; i < kPsCols; i += 2) {               // 24 independent L2 loads per accumulator, the table is zero again for the next phase
+      const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(g + i));
+      cols[i] = v.x; cols[i + 1] = v.y;
+      *reinterpret_cast<ulonglong2*>(g + i) = make_ulonglong2(0ull, 0ull);
+    }
+    // columns -> integer X = lo + hi 2^256 (carry propagation), X mod p = mont(1_mont, lo) + mont(R^2, hi)
     uint32_t w[kPsLimbs + 1];
     unsigned long long c = 0;
 #pragma unroll
     for (int i = 0; i < kPsLimbs; i++) {
-      c += acc[2 * i];
+      c += cols[2 * i];
       const uint32_t d0 = (uint32_t)(c & 0xffffu);
       c >>= 16;
-      c += acc[2 * i + 1];
+      c += cols[2 * i + 1];
       const uint32_t d1 = (uint32_t)(c & 0xffffu);
       c >>= 16;
       w[i] = d0 | (d1 << 16);
@@ -185,29 +206,7 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
 #pragma unroll
     for (int i = 0; i < 5; i++) hi.l[i] = w[8 + i];
     const Fr val = fp_add<FrParams>(fp_mul<FrParams>(fp_one<FrParams>(), lo), fp_mul<FrParams>(fp_r2<FrParams>(), hi));
-    const uint32_t key = q / NSUF, sfx = s0 + q % NSUF;
-    if (sfx < a.n_suf) fp_store(a.partial + ((size_t)blockIdx.x * a.n_suf + sfx) * m + key, val);
-  }
-  // the block that finishes last in its suffix group adds the tiles' partial tables of the group's suffixes and stores them to the
-  // host (mapped memory); the group that finishes last raises the flag: one launch per phase, no D2H copy call
-  __threadfence();
-  __syncthreads();                                       // the accumulators are dead from here: word 0 carries the "last block" flag
-  if (threadIdx.x == 0) s_acc[0] = atomicInc(a.counter + 1 + blockIdx.y, gridDim.x - 1) == gridDim.x - 1 ? 1u : 0u;
-  __syncthreads();
-  if (!s_acc[0]) return;
-  __threadfence();
-  for (uint32_t q = threadIdx.x; q < n_acc; q += blockDim.x) {
-    const uint32_t sfx = s0 + q / m, key = q % m;
-    if (sfx >= a.n_suf) continue;
-    Fr tot = fp_zero<FrParams>();
-    for (uint32_t b = 0; b < gridDim.x; b++) tot = fp_add<FrParams>(tot, fr_ld_cg(a.partial + ((size_t)b * a.n_suf + sfx) * m + key));
-    fp_store(a.host_out + (size_t)sfx * m + key, tot);
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const bool all = atomicInc(a.counter, gridDim.y - 1) == gridDim.y - 1;
-    if (all) { __threadfence_system(); *a.host_seq = a.seq_value; }
+    store_tagged(a.host_out, (int)(sfx * m + key), val, a.seq_value);   // self-validating 48-byte element: no system fence, no flag
   }
 }
 
@@ -231,6 +230,7 @@ struct ja_psshout {
   unsigned long long* d_idx = nullptr;
   Fr* d_u = nullptr;                 // u_evals: eq(r_cycle, j), then times the expanding tables of the finished phases
   Fr* d_u2 = nullptr;                // ping-pong partner (a phase reads the old values in every suffix group)
+  unsigned long long* d_cols = nullptr;   // global column table of the phase pass (zero between passes)
   size_t T = 0;
   uint32_t log_k = 0, phases = 0, log_m = 0;
   uint32_t next_phase = 0;
@@ -280,19 +280,30 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   JA_REQUIRE((phase == 0) == (v_prev == nullptr), "ja_psshout_init_phase: the expanding table of the previous phase is required from phase 1 on");
   for (size_t s = 0; s < n_suffixes; s++) JA_REQUIRE(suffix_kinds[s] <= JA_SUF_SHIFT, "ja_psshout_init_phase: unknown suffix kind");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
+  static const bool ps_trace = getenv("JA_PS_TRACE") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
   JA_CUDA(cudaSetDevice(c->device));
   const uint32_t m = 1u << p->log_m;
-  uint32_t tiles = (uint32_t)((p->T + 1023) / 1024);   // ~4 entries per thread (the block that finishes last adds `tiles` partial tables), at most one block per SM
-  if (tiles > (uint32_t)kSMs) tiles = std::max<uint32_t>(kSMs, (uint32_t)((p->T + (size_t(1) << 15) - 1) >> 15));   // a 32-bit column takes 2^16 digits of 16 bits
+  static const int tile_log = getenv("JA_PS_TILE_LOG") ? atoi(getenv("JA_PS_TILE_LOG")) : 8;
+  const unsigned groups = (unsigned)((n_suffixes + kPsSufPerBlock - 1) / kPsSufPerBlock);
+  // 2^tile_log entries per block (one or two per thread): many small blocks, several per SM - a block's cost is its per-entry
+  // instruction chain (~1000 instructions per entry and suffix pair), so the pass wants all the warps the SMs can hold
+  uint32_t tiles = (uint32_t)((p->T + (size_t(1) << tile_log) - 1) >> tile_log);
+  const uint32_t max_tiles = std::max<uint32_t>(1u, 4u * (uint32_t)kSMs / groups);
+  if (tiles > max_tiles) tiles = std::max<uint32_t>(max_tiles, (uint32_t)((p->T + (size_t(1) << 15) - 1) >> 15));   // a 32-bit shared column takes 2^16 digits of 16 bits
   JA_REQUIRE((p->T + tiles - 1) / tiles <= (size_t(1) << 15), "ja_psshout_init_phase: T too large for the column counters");
   const size_t n_out = n_suffixes * m;
-  JA_REQUIRE(n_out <= (size_t)kMaxRowVals, "ja_psshout_init_phase: result larger than the mapped value buffer");
-  Fr *d_v = nullptr, *d_part = nullptr;
+  JA_REQUIRE(n_out * 48 <= kRowSeqOffset, "ja_psshout_init_phase: result larger than the mapped value buffer");
+  Fr* d_v = nullptr;
   int32_t st;
-  if ((st = dev_alloc(c, (size_t)tiles * n_out * sizeof(Fr), (void**)&d_part))) return st;
+  if (!p->d_cols) {
+    const size_t bytes = (size_t)kPsMaxSuffixes * 256 * kPsCols * sizeof(unsigned long long);
+    if ((st = dev_alloc(c, bytes, (void**)&p->d_cols))) return st;
+    JA_CUDA(cudaMemsetAsync(p->d_cols, 0, bytes, c->stream));
+  }
   if (v_prev) {
-    if ((st = dev_alloc(c, m * sizeof(Fr), (void**)&d_v))) { dev_free(c, d_part); return st; }
-    if ((st = stage_h2d(c, d_v, v_prev, m * sizeof(Fr)))) { dev_free(c, d_part); dev_free(c, d_v); return st; }
+    if ((st = dev_alloc(c, m * sizeof(Fr), (void**)&d_v))) return st;
+    if ((st = stage_h2d(c, d_v, v_prev, m * sizeof(Fr)))) { dev_free(c, d_v); return st; }
   }
   PsPhaseArgs a;
   memset(&a, 0, sizeof(a));
@@ -301,37 +312,29 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   a.suffix_len = (p->phases - 1 - phase) * p->log_m;                   // mod.rs:309
   a.m_mask = m - 1; a.bound = bound; a.n_suf = (uint32_t)n_suffixes;
   for (size_t s = 0; s < n_suffixes; s++) a.kinds[s] = suffix_kinds[s];
-  a.partial = d_part;
+  a.gcols = p->d_cols;
   a.counter = c->d_counter + 8;                                        // [0]: groups done, [1 + y]: blocks done of group y
   a.host_out = reinterpret_cast<Fr*>(c->d_rowvals);
-  a.host_seq = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<char*>(c->d_rowvals) + kRowSeqOffset);
   a.seq_value = next_tag(c);
   // u_evals ping-pong: the suffix groups of a phase all read the OLD u_evals while one of them writes the new ones
   if (v_prev) {
-    if (!p->d_u2 && (st = dev_alloc(c, p->T * sizeof(Fr), (void**)&p->d_u2))) { dev_free(c, d_part); dev_free(c, d_v); return st; }
+    if (!p->d_u2 && (st = dev_alloc(c, p->T * sizeof(Fr), (void**)&p->d_u2))) { dev_free(c, d_v); return st; }
     a.u_out = p->d_u2;
   }
-  const unsigned groups = (unsigned)((n_suffixes + kPsSufPerBlock - 1) / kPsSufPerBlock);
   JA_LAUNCH(c, KC_SCATTER, k_ps_phase<<<dim3(tiles, groups), 256, 0, c->stream>>>(a));
   if (v_prev) std::swap(p->d_u, p->d_u2);
   cudaError_t e = cudaGetLastError();
-  dev_free(c, d_part); dev_free(c, d_v);                               // stream-ordered reuse
+  dev_free(c, d_v);                                                    // stream-ordered reuse
   if (e != cudaSuccess) return fail(JA_ERR_CUDA, std::string("ja_psshout_init_phase: ") + cudaGetErrorString(e));
+  const auto tr1 = std::chrono::steady_clock::now();
   {
-    // wait for the flag (bounded: a failed or finished stream and a 20 s timeout end the spin)
-    const volatile unsigned int* h_seq = reinterpret_cast<const volatile unsigned int*>(reinterpret_cast<char*>(c->h_rowvals) + kRowSeqOffset);
-    uint64_t spins = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    while (*h_seq != a.seq_value) {
-      if ((++spins & 0xffff) == 0) {
-        const cudaError_t q = cudaStreamQuery(c->stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(JA_ERR_CUDA, std::string("ja_psshout_init_phase: ") + cudaGetErrorString(q));
-        if (q == cudaSuccess && *h_seq != a.seq_value) return fail(JA_ERR_CUDA, "ja_psshout_init_phase: kernel finished without publishing");
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) return fail(JA_ERR_CUDA, "ja_psshout_init_phase: timed out");
-      }
+    // the results land in mapped host memory as self-validating tagged elements (bounded wait: common.hpp wait_tagged)
+    if ((st = wait_tagged(c, c->h_rowvals, a.seq_value, n_out, out_Q, "ja_psshout_init_phase"))) return st;
+    if (ps_trace) {
+      const auto tr2 = std::chrono::steady_clock::now();
+      auto us = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
+      fprintf(stderr, "[ps_trace] phase %u T %zu tiles %u: submit %.1f us, wait %.1f us\n", phase, p->T, tiles, us(tr0, tr1), us(tr1, tr2));
     }
-    __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    memcpy(out_Q, c->h_rowvals, n_out * sizeof(Fr));
   }
   p->next_phase = phase + 1;
   return JA_OK;
@@ -651,7 +654,7 @@ void ja_psshout_free(ja_ctx* c, ja_psshout* p) {
   if (!c || !p) return;
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   cudaSetDevice(c->device);
-  dev_free(c, p->d_idx); dev_free(c, p->d_u); dev_free(c, p->d_u2);
+  dev_free(c, p->d_idx); dev_free(c, p->d_u); dev_free(c, p->d_u2); dev_free(c, p->d_cols);
   delete p;
 }
 
