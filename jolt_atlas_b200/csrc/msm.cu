@@ -381,10 +381,12 @@ int32_t ja_msm_fr_batch(ja_ctx* c, const ja_srs* srs, const ja_poly* const* poly
                                          std::to_string(polys[i]->len));
     jobs[i] = MsmJob{polys[i]->data(), polys[i]->len, MSM_FR, 254, 0};
   }
-  std::vector<MsmResult> res(count);
-  int32_t st = msm_engine(c, srs, jobs, res.data());
+  // through the sharded runner: with ja_set_msm_shard every rank multiplies its index range, and with the library communicator
+  // the partial points are exchanged and added before the call returns (every rank holds the full results)
+  std::vector<int32_t> flags(count ? count : 1);
+  int32_t st = ja_msm_run(c, srs, jobs, out_xy, flags.data());
   if (st) return st;
-  for (size_t i = 0; i < count; i++) store_result(res[i], out_xy + 8 * i, is_inf ? is_inf + i : nullptr);
+  if (is_inf) memcpy(is_inf, flags.data(), sizeof(int32_t) * count);
   return JA_OK;
 }
 
