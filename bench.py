@@ -388,15 +388,18 @@ def run_device_arm(args):
         os.environ.pop("JA_NO_PERSIST", None)
         pk, pk_kind = peaks()
         roof = W.roofline_from_profile(prof, inputs, pk, pk_kind, ctx, sweep=not (args.no_sweep or world > 1))
-        # `traffic` of the class is an average over thousands of launches of different sizes and stays null; the committed
-        # `ncu --set full` captures of single launches of the dominant kernel (profiles/r1_ncu_pair_v14.*) ride along instead.
-        probe_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_pair_v14.json")
+        # `traffic`: DRAM bytes per launch of the class's dominant kernel form from the committed `ncu --set full` capture of ONE launch
+        # (profiles/r2_ncu_pair.json, scripts/r2_measure.sh; cold-cache replay) next to that launch's algorithmic bytes; the class itself
+        # mixes thousands of launches of different sizes, whose live average is `per_launch_ms`.
+        probe_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_pair.json")
         if os.path.exists(probe_file):
             try:
                 forms = json.load(open(probe_file))["forms"]
+                wide = forms["wide"]                    # k_round_prod_bool<16, 1, 128, 1>: the form with the largest share of the launch list
+                roof["dominant"]["traffic"] = int(wide["dram_read"] + wide["dram_write"])
                 roof["dominant"]["traffic_probe"] = {
-                    "source": "profiles/r1_ncu_pair_v14.json (ncu --set full, one launch per form, cold-cache replay)",
-                    "launches": [{"kernel": f["kernel"], "pairs": f["pairs"], "dram_bytes": f["dram_read"] + f["dram_write"],
+                    "source": "profiles/r2_ncu_pair.json (ncu --set full, one launch per form, cold-cache replay); `traffic` is the 'wide' form",
+                    "launches": [{"kernel": f["kernel"], "pairs": f["pairs"], "dram_bytes": int(f["dram_read"] + f["dram_write"]),
                                   "algorithmic_bytes": f["algorithmic_read"] + f["algorithmic_write"]} for f in forms.values()]}
             except (OSError, KeyError, ValueError):
                 pass

@@ -425,6 +425,16 @@ int32_t ja_comm_allgather(ja_ctx*, const void* send, size_t bytes, void* recv); 
 int32_t ja_g1_sum_affine(const uint64_t* xy, const int32_t* is_inf, size_t n, uint64_t out_xy[8], int32_t* out_inf);
 int32_t ja_fr_sum(const uint64_t* vals, size_t n_parts, size_t n_vals, uint64_t* out);
 /* The library's Blake2b transcript (joltworks/src/transcripts/blake2b.rs) for callers that own state + round counter. */
+/* cache_openings (SumcheckInstanceProver::cache_openings -> ProverOpeningAccumulator::append_{dense,sparse,virtual},
+ * joltworks/src/poly/opening_proof.rs:281, :338, :398): the reference appends every opening claim an instance caches to the transcript at
+ * the end of Sumcheck::prove / BatchedSumcheck::prove.  OFF by default: ja_sumcheck_prove / ja_batched_sumcheck_prove stop after the last
+ * round and return the final claims; the caller owns the accumulator and appends what its instances cache.  ON: the drivers append the
+ * final claims of every instance (instance order, polynomial order within an instance) with Transcript::append_scalar before they return -
+ * right for every instance whose cached openings ARE its polynomials' final claims (all JA_EVAL_* bodies, RaVirtual, Booleanity, the
+ * opening reduction).  An instance that caches something else (the read-raf cycle rounds cache ra(r), not the scaled polynomial this
+ * library binds) runs with the flag off and the caller appends through ja_transcript_append_scalar_each. */
+int32_t ja_set_cache_openings(ja_ctx*, int32_t on);
+void ja_transcript_append_scalar_each(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n);
 void ja_transcript_new(const char* label, uint8_t state[32], uint32_t* n_rounds);
 void ja_transcript_append_points(uint8_t state[32], uint32_t* n_rounds, const uint64_t* xy, const int32_t* is_inf, size_t n);
 void ja_transcript_append_scalars(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n);

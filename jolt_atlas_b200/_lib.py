@@ -92,6 +92,8 @@ SIGNATURES = {
     "ja_psshout_materialize_ra": (C.c_int32, [vp, vp, u64p, u64p, vpp]),
     "ja_psshout_prove_address": (C.c_int32, [vp, vp, C.c_uint32, u64p, u64p, C.c_char_p, C.POINTER(C.c_uint32), u64p, u32p, u64p, u64p, u64p, u64p, u64p]),
     "ja_psshout_tables": (C.c_int32, [vp, vp, u64p]),
+    "ja_set_cache_openings": (C.c_int32, [vp, C.c_int32]),
+    "ja_transcript_append_scalar_each": (None, [C.c_char_p, C.POINTER(C.c_uint32), u64p, C.c_size_t]),
     "ja_psshout_prove_identity_rc": (C.c_int32, [vp, vp, u64p, C.c_char_p, C.POINTER(C.c_uint32), u64p, u32p, u64p, u64p, u64p, u64p]),
     "ja_psshout_from_witness_rem": (C.c_int32, [vp, vp, u64p, C.c_size_t, C.c_uint32, vpp]),
     "ja_psshout_free": (None, [vp, vp]),

@@ -648,6 +648,23 @@ def fr_add(a, b) -> np.ndarray:
     return np.array([(s_ >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
 
 
+def fr_div(a, b) -> np.ndarray:
+    """a / b on Montgomery limbs (a_m * b_m^-1 * R mod r): host glue between two library calls."""
+    R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    to_i = lambda x: sum(int(v) << (64 * i) for i, v in enumerate(np.asarray(x, dtype=np.uint64).reshape(4)))
+    q = to_i(a) * pow(to_i(b), -1, R_MOD) % R_MOD * pow(2, 256, R_MOD) % R_MOD
+    return np.array([(q >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def transcript_append_scalar_each(ctx: Context, transcript: "Blake2bTranscriptState", fr):
+    """cache_openings of one instance: one Transcript::append_scalar per claim (poly/opening_proof.rs:281, :338, :398)."""
+    fr = _fr_arg(fr).reshape(-1, 4)
+    st = C.create_string_buffer(transcript.state, 32)
+    nr = C.c_uint32(transcript.n_rounds)
+    ctx._lib.ja_transcript_append_scalar_each(st, C.byref(nr), _u64p(fr), fr.shape[0])
+    transcript.state, transcript.n_rounds = st.raw, nr.value
+
+
 class SuffixKind:
     """Suffix MLEs of the clamp-table family (joltworks/src/lookup_tables/suffixes/) and the identity suffix of the raf decomposition."""
     ONE, HIGHER_ALL_ZERO, HZERO_MUL_LWORD, HONE_MUL_LWORD, IDENTITY, SHIFT = 0, 1, 2, 3, 4, 5

@@ -78,6 +78,7 @@ struct ja_ctx {
   uint32_t rr_off = 0;
   // A round-resident kernel occupies the stream until its last round: a call may run ONE of them (its only device-backed
   // instance, or the RaVirtual + Booleanity pair of an RA one-hot check); set per call by the sumcheck driver
+  bool cache_openings = false;       // ja_set_cache_openings: the sumcheck drivers append every final claim to the transcript
   bool rr_call_ok = false, rr_call_pair = false;
   // flat host-mapped value array of the batched opening reduction (kMaxRowVals Fr + a sequence word at kRowSeqOffset)
   void* h_rowvals = nullptr;

@@ -128,6 +128,19 @@ int32_t ja_eval_reduction_h(ja_ctx* c, const ja_poly* mle, const uint64_t* point
 }
 
 // ---- device-side slice entry points --------------------------------------------------------------------------------------
+int32_t ja_set_cache_openings(ja_ctx* c, int32_t on) {
+  JA_REQUIRE(c, "ja_set_cache_openings: null context");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  c->cache_openings = on != 0;
+  return JA_OK;
+}
+// n x Transcript::append_scalar (no vector framing): what cache_openings does with the claims of one instance
+void ja_transcript_append_scalar_each(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n) {
+  ja::host::Blake2bTranscript t(state, *n_rounds);
+  for (size_t i = 0; i < n; i++) t.append_scalar(ja::host::from_limbs(fr + 4 * i));
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
+
 int32_t ja_set_msm_shard(ja_ctx* c, uint32_t index, uint32_t count) {
   JA_REQUIRE(c && count >= 1 && index < count, "ja_set_msm_shard: bad shard");
   std::lock_guard<std::recursive_mutex> lk(c->mu);

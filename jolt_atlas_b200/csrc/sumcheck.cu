@@ -1646,6 +1646,8 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
   }
   // final claims: flush the deferred binds, ONE synchronisation for the whole batch
   uint64_t* staging = c->h_pinned;
+  const uint64_t* fin_src = nullptr;
+  std::vector<uint64_t> got;
   c->collect.clear();
   std::vector<std::pair<size_t, size_t>> span(n);
   size_t used = 0;
@@ -1660,7 +1662,7 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
     // tagged publication of the final claims: no stream synchronisation at the end of the call (everything the caller
     // does next with these buffers is stream-ordered behind the kernels of this call)
     const uint32_t tag = next_tag(c);
-    std::vector<uint64_t> got(4 * (used ? used : 1));
+    got.assign(4 * (used ? used : 1), 0);
     memcpy(got.data(), staging, used * 32);                 // host-only instances wrote their claims into the staging area directly
     std::vector<unsigned int> published;
     published.reserve(c->collect.size());
@@ -1680,11 +1682,20 @@ int32_t prove_loop(ja_ctx* c, std::vector<std::unique_ptr<Inst>>& insts, bool ba
       if ((st = wait_tagged(c, reinterpret_cast<const char*>(c->h_rowvals) + (size_t)idx * 48, tag, 1, got.data() + 4 * (size_t)idx, "final-claim collection"))) return st;
     for (size_t k = 0; k < n; k++)
       if (insts[k]->out_final) memcpy(insts[k]->out_final, got.data() + 4 * span[k].first, span[k].second * 32);
+    fin_src = got.data();
   } else {
     if ((st = flush_collect(c))) return st;
     JA_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t k = 0; k < n; k++)
       if (insts[k]->out_final) memcpy(insts[k]->out_final, staging + 4 * span[k].first, span[k].second * 32);
+    fin_src = staging;
+  }
+  if (c->cache_openings) {
+    // SumcheckInstanceProver::cache_openings at the end of Sumcheck::prove / BatchedSumcheck::prove (sumcheck.rs:167-176, :593-597):
+    // every opening claim an instance hands to the accumulator is appended to the transcript (opening_proof.rs:281, :338, :398),
+    // instance by instance, in the order of the instance's polynomials
+    for (size_t k = 0; k < n; k++)
+      for (size_t i = 0; i < span[k].second; i++) t.append_scalar(host::from_limbs(fin_src + 4 * (span[k].first + i)));
   }
   if (g_trace.on)
     fprintf(stderr, "[sc n=%zu rounds=%zu] cumulative us: launch=%.0f inv=%.0f wait+interp=%.0f transcript=%.0f ingest=%.0f\n", n, max_rounds,

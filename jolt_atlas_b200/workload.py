@@ -274,12 +274,31 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
     t = A.Blake2bTranscriptState(b"ONNXProof")
     out = {"commitments": [], "states": [], "finals": [], "msg_bytes": 0}
     claim = inputs["claim"]
+    # cache_openings (opening_proof.rs:281, :338, :398): the drivers append every instance's final claims to the transcript
+    A.check(ctx._lib.ja_set_cache_openings(ctx._h, 1))
+    try:
+        return _run_device(A, PAR, ctx, srs, inputs, resident, comm, ps_shout, t, out, claim)
+    finally:
+        ctx._lib.ja_set_cache_openings(ctx._h, 0)
+
+
+def _run_device(A, PAR, ctx, srs, inputs, resident, comm, ps_shout, t, out, claim):
 
     def _sc(*a, **kw):
         r = A.sumcheck_prove(*a, **kw)
         out["msg_bytes"] += r["msg_bytes"]                         # round polynomials read back from the device
         out["finals"].append(r["final_claims"])
         return r
+    def _sc_scaled(ra_scaled, run_claim, scale, ni):
+        # cycle rounds of a read-raf / identity range check over ra * scale; the instance caches ra(r) itself (mod.rs:562-578,
+        # identity_range_check.rs:326-341), so this call runs with the drivers' appends off and the unscaled claim is appended here
+        ctx._lib.ja_set_cache_openings(ctx._h, 0)
+        r = _sc(ctx, A.EvalKernel.IDENT, [ra_scaled], run_claim, t, eq_w=ni.eq_w)
+        ctx._lib.ja_set_cache_openings(ctx._h, 1)
+        ra_claim = A.fr_div(r["final_claims"][0], scale)
+        A.transcript_append_scalar_each(ctx, t, ra_claim)
+        out["finals"].append(ra_claim.reshape(1, 4))
+        ra_scaled.free()
     # A. witness commitment of EVERY one-hot polynomial before the IOP, as ONNXProof::prove does
     #    (mod.rs:152-200 step 4: commit_witness_polynomials -> prover.rs:236-249 -> hyperkzg/mod.rs:558-596)
     hots, wits = [], []
@@ -321,11 +340,11 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
             pa = ps.prove_address(t, ni.gammas[0], SAT_BOUND)
             out["msg_bytes"] += pa["msg_bytes"] + PS_PHASES * len(PS_SUFFIXES) * (1 << (CLAMP_LOG_K // PS_PHASES)) * 32   # round polynomials + the Q rows of every phase (mapped memory)
             out["finals"].append(np.stack([pa["val"], pa["raf_val"], pa["claim"]]))
-            ra_ps = ps.materialize_ra(scale=A.fr_add(pa["val"], pa["raf_val"]))
+            scale = A.fr_add(pa["val"], pa["raf_val"])
+            ra_ps = ps.materialize_ra(scale=scale)
             if not res:
                 ps.free()
-            _sc(ctx, A.EvalKernel.IDENT, [ra_ps], pa["claim"], t, eq_w=ni.eq_w)
-            ra_ps.free()
+            _sc_scaled(ra_ps, pa["claim"], scale, ni)
         # C. RA one-hot checks of the clamp lookup (batched: product of 16, Hamming weight, booleanity)
         ra0 = _ra_checks(A, ctx, hot16, ni, 0, D_CLAMP, claim, t, out, _sc, keep_first=not ps_shout)
         if not ps_shout:
@@ -362,8 +381,7 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
                 ra_rem = rp.materialize_ra(scale=pr["raf_val"])
                 if not res:
                     rp.free()
-                _sc(ctx, A.EvalKernel.IDENT, [ra_rem], pr["claim"], t, eq_w=ni.eq_w)
-                ra_rem.free()
+                _sc_scaled(ra_rem, pr["claim"], pr["raf_val"], ni)
             else:
                 _sc(ctx, A.EvalKernel.IDENT, [rem0], claim, t, eq_w=ni.eq_w)
                 rem0.free()
@@ -371,7 +389,8 @@ def run_device(ctx, srs, inputs, resident=None, comm=None, ps_shout=True):
     # G. prove_reduced_openings (prover.rs:141-176): ONE BatchedSumcheck over every committed polynomial
     #    (opening_proof.rs:500-532), gamma powers (:611-643), the materialised RLC (rlc_polynomial.rs:13-78) and the
     #    single HyperKZG opening at r_sumcheck.  Every polynomial is opened at its node's (r_address, r_cycle).
-    from . import parallel as PAR
+    #    The reduction's instances cache nothing: its claims go to the transcript as ONE vector (:611-617), below.
+    ctx._lib.ja_set_cache_openings(ctx._h, 0)
     groups, batches = [], []
     for (hot16, hot4), ni in zip(hots, inputs["nodes"]):
         for h, lo, hi in ((hot16, 0, D_CLAMP), (hot4, D_CLAMP, ni.d_hot)):

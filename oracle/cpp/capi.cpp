@@ -352,6 +352,12 @@ void orc_transcript_append_scalars(uint8_t state[32], uint32_t* n_rounds, const 
   t.append_scalars(load_fr(fr, n));
   memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
 }
+// n x Transcript::append_scalar: cache_openings of one instance (poly/opening_proof.rs:281, :338, :398)
+void orc_transcript_append_scalar_each(uint8_t state[32], uint32_t* n_rounds, const uint64_t* fr, size_t n) {
+  Transcript t(state, *n_rounds);
+  for (size_t i = 0; i < n; i++) t.append_scalar(Fr::from_raw(fr + 4 * i));
+  memcpy(state, t.state, 32); *n_rounds = t.n_rounds;
+}
 void orc_transcript_challenge_scalar_powers(uint8_t state[32], uint32_t* n_rounds, size_t n, uint64_t* out) {
   Transcript t(state, *n_rounds);
   std::vector<Fr> q = t.challenge_scalar_powers(n);

@@ -306,6 +306,15 @@ def transcript_append_scalars(t: TranscriptState, fr: np.ndarray):
     t.state, t.n_rounds = st.raw, nr.value
 
 
+def transcript_append_scalar_each(t: TranscriptState, fr: np.ndarray):
+    """cache_openings: one Transcript::append_scalar per claim (poly/opening_proof.rs:281, :338, :398)."""
+    fr = np.ascontiguousarray(fr, dtype=np.uint64).reshape(-1, 4)
+    st = C.create_string_buffer(t.state, 32)
+    nr = C.c_uint32(t.n_rounds)
+    lib().orc_transcript_append_scalar_each(st, C.byref(nr), _p(fr), C.c_size_t(fr.shape[0]))
+    t.state, t.n_rounds = st.raw, nr.value
+
+
 def transcript_challenge_scalar_powers(t: TranscriptState, n: int) -> np.ndarray:
     out = np.zeros((n, 4), dtype=np.uint64)
     st = C.create_string_buffer(t.state, 32)

@@ -17,6 +17,22 @@ def _index_lists(ni):
     return [ni.hot_k[i].astype(np.uint64) * np.uint64(T) + t for i in range(ni.d_hot)]
 
 
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def _fr_div(a, b):
+    """a / b on Montgomery limbs."""
+    to_i = lambda x: sum(int(v) << (64 * i) for i, v in enumerate(np.asarray(x, dtype=np.uint64).reshape(4)))
+    q = to_i(a) * pow(to_i(b), -1, R_MOD) % R_MOD * pow(2, 256, R_MOD) % R_MOD
+    return np.array([(q >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def _cache(t, final_claims):
+    """cache_openings (opening_proof.rs:281, :338, :398): every cached claim is appended to the transcript."""
+    for fc in (final_claims if isinstance(final_claims, (list, tuple)) else [final_claims]):
+        ORC.transcript_append_scalar_each(t, fc)
+
+
 def _ra_checks(ni, lo, hi, claim, t, out):
     k = np.ascontiguousarray(ni.hot_k[lo:hi])
     G = ORC.compute_ra_evals(k, 16, ni.eq_w)
@@ -26,6 +42,7 @@ def _ra_checks(ni, lo, hi, claim, t, out):
         {"kind": 18, "polys": G, "aux_fr": ni.gammas[lo:hi], "claim": claim},
         {"kind": 32, "polys": G, "idx": k, "eq_w": ni.eq_w, "aux_u32": 4, "aux_fr": np.concatenate([ni.gammas[lo:hi], ni.r_addr])},
     ], t)
+    _cache(t, r["final_claims"])
     out["finals"].extend(r["final_claims"])
     return ra[0]
 
@@ -62,6 +79,9 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
         ps.free()
         r = ORC.sumcheck_prove_st(0, 6, np.stack([ra_ps]), ni.eq_w, pa["claim"], t)
         out["finals"].append(r["final_claims"])
+        ra_claim = _fr_div(r["final_claims"][0], scale)          # the instance caches ra(r), not the scaled polynomial's claim
+        _cache(t, ra_claim)
+        out["finals"].append(ra_claim.reshape(1, 4))
         _ra_checks(ni, 0, D_CLAMP, claim, t, out)
         if spec.kind == "einsum":
             left = ORC.tensor_fold_i32(ni.A, ORC.eq_evals(ni.eq_rows), False)
@@ -70,6 +90,7 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
         else:
             a, b = ORC.fr_from_i64(ni.A), ORC.fr_from_i64(ni.B)
             r = ORC.sumcheck_prove_st(0, 2 if spec.kind == "mul" else 0, np.stack([a, b]), ni.eq_w, claim, t)
+        _cache(t, r["final_claims"])
         out["finals"].append(r["final_claims"])
         if ni.d_hot > D_CLAMP:
             _ra_checks(ni, D_CLAMP, ni.d_hot, claim, t, out)
@@ -83,6 +104,9 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
             rp.free()
             r = ORC.sumcheck_prove_st(0, 6, np.stack([ra_rem]), ni.eq_w, pr["claim"], t)
             out["finals"].append(r["final_claims"])
+            ra_claim = _fr_div(r["final_claims"][0], pr["raf_val"])
+            _cache(t, ra_claim)
+            out["finals"].append(ra_claim.reshape(1, 4))
         out["states"].append(t.state)
     if do_open:
         # prove_reduced_openings: batched opening reduction over every one-hot polynomial, gamma powers, RLC, HyperKZG open
