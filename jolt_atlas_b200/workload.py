@@ -611,10 +611,12 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx,
             gb = bytes_per_n * (1 << log_n) / ms / 1e6
             sweep.append({"kernel": name, "log_n": log_n, "ms": round(ms, 4), "GBps": round(gb, 1), "frac_hbm": round(gb / hbm, 4)})
     # fused bind + evaluate round kernels: 48 n bytes per polynomial and launch; the mul-bound bodies also as Gmul/s.
-    # Products per pair = (full Montgomery products, 4-row challenge products of the bind): a challenge product is half the
-    # IMAD.WIDE rows of a full one and is counted as 0.5, so that frac_mul is a fraction of the calibrated full-product peak.
-    fused = ((7, "fused_round_add_tma", 2, 24, (2, 4)), (7, "fused_round_add_tma", 2, 26, (2, 4)), (8, "fused_round_ident_tma", 1, 26, (2, 2)),
-             (0, "fused_round_add", 2, 24, (2, 4)), (1, "fused_round_mul", 2, 24, (4, 4)), (2, "fused_round_ident", 1, 24, (2, 2)),
+    # Products per pair = (full Montgomery products, 4-row challenge products of the bind) THE KERNEL EXECUTES (ADD / IDENT weight one
+    # eq-free value per pair with e_in; e_out is applied once per x_out group): a challenge product is half the IMAD.WIDE rows of a
+    # full one and is counted as 0.5, and so is the UNREDUCED full product of the TMA-staged kernels (delayed Montgomery reduction: 64 of
+    # 136 rows), so that frac_mul is a fraction of the calibrated full-product peak and stays below 1.
+    fused = ((7, "fused_round_add_tma", 2, 24, (0.5, 4)), (7, "fused_round_add_tma", 2, 26, (0.5, 4)), (8, "fused_round_ident_tma", 1, 26, (0.5, 2)),
+             (0, "fused_round_add", 2, 24, (1, 4)), (1, "fused_round_mul", 2, 24, (4, 4)), (2, "fused_round_ident", 1, 24, (1, 2)),
              (6, "fused_round_open_h2l", 1, 24, (2, 2)), (3, "fused_round_product4", 4, 22, (16 + 4, 8)), (4, "fused_round_product16", 16, 20, (256 + 16, 32)),
              (5, "fused_round_booleanity16", 16, 20, (16 * 4 + 2, 32)))
     for which, name, npoly, log_n, (full_muls, chal_muls) in fused:
