@@ -75,6 +75,24 @@ static inline FrH mul(const FrH& a, const FrH& b) {
   if (t[4] || geq_p(r.l)) sub_p(r.l);
   return r;
 }
+// a * r for a 125-bit challenge r in its Montgomery form {0, 0, lo, hi} (field/challenge/mont_ark_u128.rs:25-92): the CIOS iterations of
+// the two zero limbs are no-ops (t stays 0, m = 0), so the product is exactly mul(a, r) at half the cost
+static inline FrH mul_chal(const FrH& a, const FrH& r) {
+  if (r.l[0] | r.l[1]) return mul(a, r);
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 2; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a.l[j] * r.l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * FR_INV;
+    c = (u128)m * FR_P[0] + t[0]; c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * FR_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  FrH o = {{t[0], t[1], t[2], t[3]}};
+  if (t[4] || geq_p(o.l)) sub_p(o.l);
+  return o;
+}
 static inline FrH sqr(const FrH& a) { return mul(a, a); }
 static inline FrH from_u64(uint64_t v) { FrH t = {{v, 0, 0, 0}}; return mul(t, FR_R2); }
 static inline FrH from_i64(int64_t v) {

@@ -533,11 +533,15 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       for (size_t k = 0; k < 2; k++) memcpy(out_coeffs + 4 * (2 * j + k), k < cpr.size() ? cpr[k].l : ja::host::FR_ZERO.l, 32);
       memcpy(out_challenges + 4 * j, ch, 32);
       // ingest_challenge (mod.rs:491-560)
+      // H2L binds: clamp lookups leave most entries of most rows zero in the sign-extension phases - a zero difference costs no product
       for (int q = 0; q < 5; q++)
-        for (size_t b = 0; b < half; b++) Q[q][b] = add(Q[q][b], mul(rj, sub(Q[q][b + half], Q[q][b])));
-      bid = add(bid, mul(rj, kappa));
+        for (size_t b = 0; b < half; b++) {
+          const FrH d = sub(Q[q][b + half], Q[q][b]);
+          if (!d.is_zero()) Q[q][b] = add(Q[q][b], ja::host::mul_chal(d, rj));
+        }
+      bid = add(bid, ja::host::mul_chal(kappa, rj));
       v_next.resize(v_cur.size() * 2);                                             // ExpandingTable::update, HighToLow (expanding_table.rs:76-86)
-      for (size_t i = 0; i < v_cur.size(); i++) { const FrH e1 = mul(rj, v_cur[i]); v_next[2 * i] = sub(v_cur[i], e1); v_next[2 * i + 1] = e1; }
+      for (size_t i = 0; i < v_cur.size(); i++) { const FrH e1 = ja::host::mul_chal(v_cur[i], rj); v_next[2 * i] = sub(v_cur[i], e1); v_next[2 * i + 1] = e1; }
       v_cur.swap(v_next);
       if (j & 1) {
         PsCp prev[4] = {cp[0], cp[1], cp[2], cp[3]};
@@ -626,12 +630,13 @@ int32_t ja_psshout_prove_identity_rc(ja_ctx* c, ja_psshout* p, const uint64_t* c
       for (size_t k = 0; k < 2; k++) memcpy(out_coeffs + 4 * (2 * j + k), k < cpr.size() ? cpr[k].l : ja::host::FR_ZERO.l, 32);
       memcpy(out_challenges + 4 * j, ch, 32);
       for (size_t b = 0; b < half; b++) {
-        Q0[b] = add(Q0[b], mul(rj, sub(Q0[b + half], Q0[b])));
-        Q1[b] = add(Q1[b], mul(rj, sub(Q1[b + half], Q1[b])));
+        const FrH d0 = sub(Q0[b + half], Q0[b]), d1 = sub(Q1[b + half], Q1[b]);
+        if (!d0.is_zero()) Q0[b] = add(Q0[b], ja::host::mul_chal(d0, rj));
+        if (!d1.is_zero()) Q1[b] = add(Q1[b], ja::host::mul_chal(d1, rj));
       }
-      bid = add(bid, mul(rj, kappa));
+      bid = add(bid, ja::host::mul_chal(kappa, rj));
       v_next.resize(v_cur.size() * 2);
-      for (size_t i = 0; i < v_cur.size(); i++) { const FrH e1 = mul(rj, v_cur[i]); v_next[2 * i] = sub(v_cur[i], e1); v_next[2 * i + 1] = e1; }
+      for (size_t i = 0; i < v_cur.size(); i++) { const FrH e1 = ja::host::mul_chal(v_cur[i], rj); v_next[2 * i] = sub(v_cur[i], e1); v_next[2 * i + 1] = e1; }
       v_cur.swap(v_next);
     }
     cp = bid;
