@@ -387,18 +387,20 @@ enum { P_HAZ = 0, P_HAO = 1, P_LW = 2, P_MSB = 3 };
 
 // the b-independent factor / offset of SparseDensePrefix::prefix_mle at round j (r_x = the previous challenge when j is odd)
 static FrH ps_prefix_scalar(int kind, const PsCp cp[4], const FrH* r_x, uint32_t c, unsigned j, unsigned bound_index, const FrH* pow2, unsigned xlen) {
-  const FrH cf = ja::host::from_u64(c);
-  if (kind == P_MSB) return j == 0 ? cf : (j == 1 ? *r_x : cp[P_MSB].v);
+  // c is 0, 1 or 2: products by c / (1 - c) are selections, additions and negations; r_x is a 125-bit challenge (mul_chal)
+  auto times_c = [&](const FrH& x) { return c == 0 ? ja::host::FR_ZERO : (c == 1 ? x : dbl(x)); };
+  auto times_1mc = [&](const FrH& x) { return c == 0 ? x : (c == 1 ? ja::host::FR_ZERO : neg(x)); };
+  if (kind == P_MSB) return j == 0 ? times_c(ja::host::FR_ONE) : (j == 1 ? *r_x : cp[P_MSB].v);
   if (kind == P_HAZ || kind == P_HAO) {
     const bool zero = kind == P_HAZ;
     FrH r = cp[kind].has ? cp[kind].v : ja::host::FR_ONE;
-    if (r_x && j > 0 && j - 1 <= bound_index) r = mul(r, zero ? sub(ja::host::FR_ONE, *r_x) : *r_x);
-    if (j <= bound_index) r = mul(r, zero ? sub(ja::host::FR_ONE, cf) : cf);
+    if (r_x && j > 0 && j - 1 <= bound_index) r = zero ? sub(r, ja::host::mul_chal(r, *r_x)) : ja::host::mul_chal(r, *r_x);   // r (1 - r_x) = r - r r_x
+    if (j <= bound_index) r = zero ? times_1mc(r) : times_c(r);
     return r;
   }
   FrH r = cp[P_LW].has ? cp[P_LW].v : ja::host::FR_ZERO;
-  if (r_x && j > 0 && j - 1 > bound_index) r = add(r, mul(pow2[xlen - (j - 1) - 1], *r_x));
-  if (j > bound_index) r = add(r, mul(pow2[xlen - j - 1], cf));
+  if (r_x && j > 0 && j - 1 > bound_index) r = add(r, ja::host::mul_chal(pow2[xlen - (j - 1) - 1], *r_x));
+  if (j > bound_index) r = add(r, times_c(pow2[xlen - j - 1]));
   return r;
 }
 static PsCp ps_update_checkpoint(int kind, const PsCp cp[4], const FrH& r_x, const FrH& r_y, unsigned j, unsigned bound_index, const FrH* pow2, unsigned xlen) {
@@ -423,13 +425,34 @@ static PsCp ps_update_checkpoint(int kind, const PsCp cp[4], const FrH& r_x, con
   o.v = r;
   return o;
 }
-static inline FrH ps_sum(const FrH* x, size_t n) { FrH a = ja::host::FR_ZERO; for (size_t i = 0; i < n; i++) a = add(a, x[i]); return a; }
-// sum_b b * x[b], b < n: the running suffix sum added once per step
-static inline FrH ps_wsum(const FrH* x, size_t n) {
-  FrH acc = ja::host::FR_ZERO, tot = ja::host::FR_ZERO;
-  for (size_t b = n; b-- > 1;) { acc = add(acc, x[b]); tot = add(tot, acc); }
-  return tot;
+// Plain sums of up to 256 field elements run as 320-bit INTEGER accumulations (4 add-with-carry per element instead of a modular
+// addition with its compare-and-subtract: 14 -> 2 ns per element measured) and fold back into the field once: X mod p =
+// mont(lo, 1_mont) + mont(hi, R^2) (sumcheck_host.hpp fold320).
+struct PsAcc { uint64_t l[5] = {0, 0, 0, 0, 0}; };
+static inline void ps_acc_add(PsAcc& a, const uint64_t* x, int limbs) {
+  unsigned __int128 c = 0;
+  for (int i = 0; i < 5; i++) { c += (unsigned __int128)a.l[i] + (i < limbs ? x[i] : 0ull); a.l[i] = (uint64_t)c; c >>= 64; }
 }
+static inline FrH ps_acc_fold(const PsAcc& a) { return ja::host::fold320(a.l, ja::host::FR_ONE, ja::host::FR_R2); }
+static inline FrH ps_sum(const FrH* x, size_t n) {
+  if (n <= 4) { FrH a = ja::host::FR_ZERO; for (size_t i = 0; i < n; i++) a = add(a, x[i]); return a; }
+  PsAcc a;
+  for (size_t i = 0; i < n; i++) ps_acc_add(a, x[i].l, 4);
+  return ps_acc_fold(a);
+}
+// sum = sum_b x[b] and wsum = sum_b b * x[b], b < n <= 256: the running suffix sum added once per step (acc < 2^262, tot < 2^270)
+static inline void ps_sum_wsum(const FrH* x, size_t n, FrH* sum, FrH* wsum) {
+  if (n <= 2) {
+    *wsum = n == 2 ? x[1] : ja::host::FR_ZERO;
+    *sum = n == 2 ? add(x[0], x[1]) : (n == 1 ? x[0] : ja::host::FR_ZERO);
+    return;
+  }
+  PsAcc acc, tot;
+  for (size_t b = n; b-- > 1;) { ps_acc_add(acc, x[b].l, 4); ps_acc_add(tot, acc.l, 5); }
+  ps_acc_add(acc, x[0].l, 4);
+  *sum = ps_acc_fold(acc); *wsum = ps_acc_fold(tot);
+}
+static inline FrH ps_wsum(const FrH* x, size_t n) { FrH s_, w_; ps_sum_wsum(x, n, &s_, &w_); return w_; }
 struct PsSide { FrH s1, r1, w_all, a_haz, a_hz, a_one, a_w, b_ho, b_one, b_w; };
 }  // namespace
 
@@ -467,6 +490,7 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
     const unsigned s_len = xlen - (phase + 1) * log_m;                 // suffix_len of the phase
     FrH bid = cp_id;
     v_cur.assign(1, ja::host::FR_ONE);
+    const auto t_rounds = std::chrono::steady_clock::now();
     for (unsigned tt = 0; tt < log_m; tt++) {
       const unsigned j = phase * log_m + tt, b_len = log_m - 1 - tt;
       const size_t half = size_t(1) << b_len;
@@ -478,15 +502,14 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       for (int sd = 0; sd < 2; sd++) {
         const size_t off = sd ? half : 0;
         PsSide& S = side[sd];
-        S.s1 = ps_sum(Q[3] + off, half);
+        ps_sum_wsum(Q[3] + off, half, &S.s1, &S.w_all);
         S.r1 = ps_sum(Q[4] + off, half);
-        S.w_all = ps_wsum(Q[3] + off, half);
         S.a_haz = ps_sum(Q[0] + off, n_z);
         S.a_hz = ps_sum(Q[1] + off, n_z);
         if (n_hi == 0) { S.a_one = S.s1; S.a_w = S.w_all; S.b_one = S.s1; S.b_w = S.w_all; }
         else {
-          S.a_one = ps_sum(Q[3] + off, n_z); S.a_w = ps_wsum(Q[3] + off, n_z);
-          S.b_one = ps_sum(Q[3] + off + o_off, n_z); S.b_w = ps_wsum(Q[3] + off + o_off, n_z);   // (b & low_mask) = b - o_off on O
+          ps_sum_wsum(Q[3] + off, n_z, &S.a_one, &S.a_w);
+          ps_sum_wsum(Q[3] + off + o_off, n_z, &S.b_one, &S.b_w);                              // (b & low_mask) = b - o_off on O
         }
         S.b_ho = ps_sum(Q[2] + off + o_off, n_z);
       }
@@ -494,30 +517,44 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       const FrH two_s = pow2[s_len];
       const FrH kappa = j == 0 ? neg(pow2[xlen - 1]) : pow2[b_len + s_len];        // coefficient of the current variable in the identity prefix
       // E(c, side) = sum_b combine(P_c(b), Q_side(b)); raf(c, side) = sum_b P_c(b) Q_one(b) + Q_id(b)
-      auto table_part = [&](uint32_t cc, const PsSide& S) {
-        const FrH hz = ps_prefix_scalar(P_HAZ, cp, r_x, cc, j, bound_index, pow2, xlen), ho = ps_prefix_scalar(P_HAO, cp, r_x, cc, j, bound_index, pow2, xlen);
-        const FrH lw = ps_prefix_scalar(P_LW, cp, r_x, cc, j, bound_index, pow2, xlen), msb = ps_prefix_scalar(P_MSB, cp, r_x, cc, j, bound_index, pow2, xlen);
-        FrH e = mul(sub(const_upper, mul(msb, lower_coeff)), S.s1);
-        const FrH zt = sub(add(add(S.a_hz, mul(lw, S.a_one)), mul(two_s, S.a_w)), mul(const_upper, S.a_haz));
-        const FrH ot = add(add(S.b_ho, mul(lw, S.b_one)), mul(two_s, S.b_w));
-        e = add(e, mul(hz, zt));
-        return add(e, mul(ho, ot));
+      // products that do not depend on c, once per side: 2^s A_w - CU A_haz, 2^s B_w, 2^s W_all
+      FrH zc[2], oc[2], wc[2];
+      for (int sd = 0; sd < 2; sd++) {
+        zc[sd] = sub(mul(two_s, side[sd].a_w), mul(const_upper, side[sd].a_haz));
+        oc[sd] = n_hi == 0 ? mul(two_s, side[sd].a_w) : mul(two_s, side[sd].b_w);
+        wc[sd] = n_hi == 0 ? oc[sd] : mul(two_s, side[sd].w_all);
+      }
+      struct PsScal { FrH hz, ho, lw, msb_term; };
+      auto scalars = [&](uint32_t cc) {
+        PsScal q;
+        q.hz = ps_prefix_scalar(P_HAZ, cp, r_x, cc, j, bound_index, pow2, xlen); q.ho = ps_prefix_scalar(P_HAO, cp, r_x, cc, j, bound_index, pow2, xlen);
+        q.lw = ps_prefix_scalar(P_LW, cp, r_x, cc, j, bound_index, pow2, xlen);
+        q.msb_term = sub(const_upper, mul(ps_prefix_scalar(P_MSB, cp, r_x, cc, j, bound_index, pow2, xlen), lower_coeff));
+        return q;
       };
-      auto raf_part = [&](uint32_t cc, const PsSide& S) {
+      auto table_part = [&](const PsScal& q, int sd) {
+        const PsSide& S = side[sd];
+        FrH e = mul(q.msb_term, S.s1);
+        const FrH zt = add(add(S.a_hz, mul(q.lw, S.a_one)), zc[sd]);
+        const FrH ot = add(add(S.b_ho, mul(q.lw, S.b_one)), oc[sd]);
+        e = add(e, mul(q.hz, zt));
+        return add(e, mul(q.ho, ot));
+      };
+      auto raf_part = [&](uint32_t cc, int sd) {
         const FrH base = cc == 0 ? bid : (cc == 1 ? add(bid, kappa) : add(bid, dbl(kappa)));
-        return add(add(mul(base, S.s1), mul(two_s, S.w_all)), S.r1);
+        return add(add(mul(base, side[sd].s1), wc[sd]), side[sd].r1);
       };
+      const PsScal q0 = scalars(0), q2 = scalars(2);
+      const FrH e0 = add(table_part(q0, 0), mul(gamma, raf_part(0, 0)));
       if (j == 0) {
         // the claimed sum as the prover sees it: s(0) + s(1) = rv(r_cycle) + gamma * operand(r_cycle)
-        const FrH s0 = add(table_part(0, side[0]), mul(gamma, raf_part(0, side[0])));
-        const FrH s1 = add(table_part(1, side[1]), mul(gamma, raf_part(1, side[1])));
-        const FrH derived = add(s0, s1);
+        const PsScal q1 = scalars(1);
+        const FrH derived = add(e0, add(table_part(q1, 1), mul(gamma, raf_part(1, 1))));
         if (out_input_claim) memcpy(out_input_claim, derived.l, 32);
         if (!claim_in) claim = derived;
       }
-      const FrH e0 = add(table_part(0, side[0]), mul(gamma, raf_part(0, side[0])));
-      const FrH t2l = table_part(2, side[0]), t2h = table_part(2, side[1]);
-      const FrH a2l = raf_part(2, side[0]), a2r = raf_part(2, side[1]);
+      const FrH t2l = table_part(q2, 0), t2h = table_part(q2, 1);
+      const FrH a2l = raf_part(2, 0), a2r = raf_part(2, 1);
       const FrH e2 = add(sub(dbl(t2h), t2l), mul(gamma, sub(dbl(a2r), a2l)));
       const ja::host::Coeffs uni = ja::host::from_evals_and_hint(claim, {e0, e2});
       const ja::host::Coeffs cpr = ja::host::compress(uni);
@@ -549,6 +586,7 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       }
       r_prev = rj;
     }
+    if (getenv("JA_PS_TRACE")) fprintf(stderr, "[ps_trace] phase %u host rounds %.1f us\n", phase, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_rounds).count());
     cp_id = bid;                                                                   // PrefixRegistry::update_checkpoints
     memcpy((void*)(p->h_v.data() + (size_t)phase * m), v_cur.data(), m * sizeof(FrH));
   }
@@ -603,7 +641,7 @@ int32_t ja_psshout_prove_identity_rc(ja_ctx* c, ja_psshout* p, const uint64_t* c
       FrH s0[2], w0[2], s1[2];
       for (int sd = 0; sd < 2; sd++) {
         const size_t off = sd ? half : 0;
-        s0[sd] = ps_sum(Q0 + off, half); w0[sd] = ps_wsum(Q0 + off, half); s1[sd] = ps_sum(Q1 + off, half);
+        ps_sum_wsum(Q0 + off, half, &s0[sd], &w0[sd]); s1[sd] = ps_sum(Q1 + off, half);
       }
       auto part = [&](uint32_t cc, int sd) {
         const FrH base = cc == 0 ? bid : (cc == 1 ? add(bid, kappa) : add(bid, dbl(kappa)));
