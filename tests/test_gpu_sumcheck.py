@@ -171,3 +171,39 @@ def test_prelaunched_rounds_survive_mailbox_reuse(ctx):
             assert t.state == want["state"]
         else:
             assert key == first, it
+
+
+@pytest.mark.parametrize("kind,npoly,m", [("mul", 2, 9), ("dot2", 2, 7), ("prod", 4, 6)])
+def test_cache_openings_appends_the_final_claims(ctx, kind, npoly, m):
+    """ja_set_cache_openings: the driver appends every final claim with Transcript::append_scalar at the end of the proof
+    (SumcheckInstanceProver::cache_openings -> opening_proof.rs:281, :338, :398).  Same state as the oracle's transcript after the
+    oracle's proof + one append_scalar per claim; OFF (the default) leaves the transcript where the last round left it."""
+    from jolt_atlas_b200 import api as A
+    rng = random.Random(77 + m)
+    n = 1 << m
+    polys = [to_mont_array(rand_fr(rng, n)) for _ in range(npoly)]
+    w = np.array([F.challenge_limbs(rand_challenge(rng)) for _ in range(m)], dtype=np.uint64)
+    claim = to_mont_array([rng.randrange(P)])[0]
+    fam, kid = ORC_KIND[kind]
+    tc = ORC.TranscriptState(b"cache")
+    want = ORC.sumcheck_prove_st(fam, kid, np.stack(polys), w if fam == 0 else None, claim, tc)
+    state_plain = tc.state
+    ORC.transcript_append_scalar_each(tc, want["final_claims"])
+    states = {}
+    for on in (0, 1):
+        A.check(ctx._lib.ja_set_cache_openings(ctx._h, on))
+        try:
+            ps = [A.MultilinearPolynomial.from_fr(ctx, z) for z in polys]
+            t = A.Blake2bTranscriptState(b"cache")
+            got = A.sumcheck_prove(ctx, KIND[kind], ps, claim, t, eq_w=w if KIND[kind] < 16 else None)
+            states[on] = (t.state, t.n_rounds)
+            assert np.array_equal(got["final_claims"], want["final_claims"])
+        finally:
+            ctx._lib.ja_set_cache_openings(ctx._h, 0)
+    assert states[0][0] == state_plain
+    assert states[1] == (tc.state, tc.n_rounds)
+    # the caller-side form of the same appends
+    t2 = A.Blake2bTranscriptState(b"cache")
+    t2.state, t2.n_rounds = states[0]
+    A.transcript_append_scalar_each(ctx, t2, want["final_claims"])
+    assert (t2.state, t2.n_rounds) == states[1]
