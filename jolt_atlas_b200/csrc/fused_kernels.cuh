@@ -362,12 +362,7 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const WAITE
       p0 = a0;
       dp = fp_sub<FrParams>(a1, p0);
     }
-    Fr v[L];
-    Fr cur = p0;
-#pragma unroll
-    for (int k = 0; k < L - 1; k++) { cur = fp_add<FrParams>(cur, dp); v[k] = cur; }
-    v[L - 1] = pad ? p0 : dp;
-    LaneProduct<L>::run(v, li);
+    const Fr pv = lane_product<L>(p0, dp, pad, d, li);
     if (active) {
       const size_t x_out = (g + g_off) >> bits_in;
       if (x_out != cur_xout) {
@@ -377,7 +372,7 @@ JA_DEV void round_prod_body(const FusedPolys& P, int d, Challenge r, const WAITE
         }
         cur_xout = x_out;
       }
-      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), v[0]));
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), pv));
     }
   }
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));

@@ -520,6 +520,46 @@ template <int M> struct LaneProduct {     // M = number of values currently held
 };
 template <> struct LaneProduct<1> { JA_DEV static void run(Fr (&)[1], int) {} };
 
+// Value of the product of the L lanes' linear factors p0 + X dp at this lane's evaluation point (points X = 1 .. L-1 and the
+// leading coefficient "at infinity" in slot L-1; a pad lane is the constant 1).  Generic form: L values per lane, log2 L
+// butterfly stages, L - 1 products per lane.  L = 16: the FIRST stage multiplies two LINEAR factors, whose product is the
+// quadratic c0 + c1 X + c2 X^2 - three products (c0 = p0 q0, c2 = dp dq, q(1) = (p0 + dp)(q0 + dq)) and a second-difference
+// recurrence (two additions per point) instead of eight products, and two exchanged field elements instead of eight:
+// 10 products per lane instead of 15 (mles_product_sum.rs:61-129 computes the same values; the field is exact, the order free).
+template <int L>
+JA_DEV Fr lane_product(const Fr& p0, const Fr& dp, bool pad, int d, int li) {
+  Fr v[L];
+  Fr cur = p0;
+#pragma unroll
+  for (int k = 0; k < L - 1; k++) { cur = fp_add<FrParams>(cur, dp); v[k] = cur; }
+  v[L - 1] = pad ? p0 : dp;
+  LaneProduct<L>::run(v, li);
+  return v[0];
+}
+template <>
+JA_DEV Fr lane_product<16>(const Fr& p0, const Fr& dp, bool pad, int d, int li) {
+  const Fr q0 = fr_shfl_xor(p0, 8), dq = fr_shfl_xor(dp, 8);
+  const bool partner_pad = (li ^ 8) >= d;
+  const Fr c0 = fp_mul<FrParams>(p0, q0), c2 = fp_mul<FrParams>(dp, dq);
+  Fr q = fp_mul<FrParams>(fp_add<FrParams>(p0, dp), fp_add<FrParams>(q0, dq));                  // q(1) = c0 + c1 + c2
+  const Fr two_c2 = fp_add<FrParams>(c2, c2);
+  Fr dlt = fp_add<FrParams>(fp_sub<FrParams>(q, c0), two_c2);                                  // q(2) - q(1) = c1 + 3 c2
+  // slot 15 of the pair: product of the two leading coefficients, a pad factor counting as 1
+  const Fr inf = pad ? (partner_pad ? p0 : dq) : (partner_pad ? dp : c2);
+  const bool hi = (li & 8) != 0;
+  Fr nv[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { nv[j] = q; q = fp_add<FrParams>(q, dlt); dlt = fp_add<FrParams>(dlt, two_c2); }      // X = 1 .. 8 (low lanes)
+#pragma unroll
+  for (int j = 0; j < 7; j++) {                                                                                       // X = 9 .. 15 (high lanes)
+    nv[j] = fr_select(hi, q, nv[j]);
+    if (j < 6) { q = fp_add<FrParams>(q, dlt); dlt = fp_add<FrParams>(dlt, two_c2); }
+  }
+  nv[7] = fr_select(hi, inf, nv[7]);
+  LaneProduct<8>::run(nv, li);
+  return nv[0];
+}
+
 // sum of `v` over all threads of the block that share (threadIdx.x % L); valid in threads t < L afterwards
 template <int L, int BLOCK = kBlock>
 JA_DEV Fr block_sum_by_lane(Fr v) {
@@ -559,12 +599,7 @@ k_round_eval_prod_t(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* 
     Fr p0, dp;
     if (pad) { p0 = fp_one<FrParams>(); dp = fp_zero<FrParams>(); }
     else { p0 = fp_load(z + 2 * gl); dp = fp_sub<FrParams>(fp_load(z + 2 * gl + 1), p0); }
-    Fr v[L];
-    Fr cur = p0;
-#pragma unroll
-    for (int k = 0; k < L - 1; k++) { cur = fp_add<FrParams>(cur, dp); v[k] = cur; }
-    v[L - 1] = pad ? p0 : dp;
-    LaneProduct<L>::run(v, li);
+    const Fr pv = lane_product<L>(p0, dp, pad, d, li);
     if (active) {
       const size_t x_out = (g + g_off) >> bits_in;
       if (x_out != cur_xout) {
@@ -574,7 +609,7 @@ k_round_eval_prod_t(ProdPolys P, int d, const Fr* __restrict__ e_out, const Fr* 
         }
         cur_xout = x_out;
       }
-      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), v[0]));
+      inner = fp_add<FrParams>(inner, fp_mul<FrParams>(fp_load(e_in + ((g + g_off) & mask_in)), pv));
     }
   }
   if (cur_xout != ~size_t(0)) outer = fp_add<FrParams>(outer, fp_mul<FrParams>(fp_load(e_out + cur_xout), inner));

@@ -614,10 +614,11 @@ def roofline_from_profile(prof: dict, inputs, peaks: dict, peaks_kind: str, ctx,
     # Products per pair = (full Montgomery products, 4-row challenge products of the bind) THE KERNEL EXECUTES (ADD / IDENT weight one
     # eq-free value per pair with e_in; e_out is applied once per x_out group): a challenge product is half the IMAD.WIDE rows of a
     # full one and is counted as 0.5, and so is the UNREDUCED full product of the TMA-staged kernels (delayed Montgomery reduction: 64 of
-    # 136 rows), so that frac_mul is a fraction of the calibrated full-product peak and stays below 1.
+    # 136 rows), so that frac_mul is a fraction of the calibrated full-product peak and stays below 1.  product16: 10 products per lane
+    # since the quadratic first stage (lane_product<16>, was 15) + the e_in weighting; its ~30 field additions per lane are not counted.
     fused = ((7, "fused_round_add_tma", 2, 24, (0.5, 4)), (7, "fused_round_add_tma", 2, 26, (0.5, 4)), (8, "fused_round_ident_tma", 1, 26, (0.5, 2)),
              (0, "fused_round_add", 2, 24, (1, 4)), (1, "fused_round_mul", 2, 24, (4, 4)), (2, "fused_round_ident", 1, 24, (1, 2)),
-             (6, "fused_round_open_h2l", 1, 24, (2, 2)), (3, "fused_round_product4", 4, 22, (16 + 4, 8)), (4, "fused_round_product16", 16, 20, (256 + 16, 32)),
+             (6, "fused_round_open_h2l", 1, 24, (2, 2)), (3, "fused_round_product4", 4, 22, (16 + 4, 8)), (4, "fused_round_product16", 16, 20, (160 + 16, 32)),
              (5, "fused_round_booleanity16", 16, 20, (16 * 4 + 2, 32)))
     for which, name, npoly, log_n, (full_muls, chal_muls) in fused:
         ms = ctx.bench_fused(which, log_n, 10)
