@@ -473,7 +473,7 @@ JA_DEV void round_prod16_wide_body(const FusedPolys& P, int d, Challenge r, cons
 }
 
 template <int L, bool SAME, bool FUSED>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, L == 16 ? 2 : 0)      // 0 = unspecified; L = 16: two blocks per SM (128 registers, 128 B of spills) beat one at 168
 k_round_prod(FusedPolys P, int d, Challenge r, const Fr* __restrict__ e_out, const Fr* __restrict__ e_in, int bits_in, size_t G,
              size_t pairs_per_block, Fr* partials /* [gridDim.x][L] */, unsigned int* counter, Publish pub, size_t g_off = 0,
              MailRef mail = MailRef{}) {
@@ -597,7 +597,7 @@ struct PairArgs {
   Publish pub;
 };
 template <int L, bool FUSED, int BLOCK = kBlock, bool WIDE = false>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, (L == 16 && BLOCK == kBlock && !WIDE) ? 2 : 0)
 k_round_prod_bool(PairArgs A, PairArgs B, Challenge r, MailRef mail = MailRef{}) {
   const MailWaiter waiter{mail};
   if (blockIdx.y == 0) {
