@@ -23,7 +23,7 @@ constexpr int kPsMaxSuffixes = 8;
 // suffix MLEs of the clamp-table family (joltworks/src/lookup_tables/suffixes/{higher_all_zero,hzero_mul_lword,hone_mul_lword,one}.rs)
 // and of the identity polynomial (poly/identity_poly.rs: the suffix value itself), in closed form: `bits` = the low `len` bits of
 // the XLEN-bit index; the "higher" bits are those of significance >= 2^bound.
-JA_DEV unsigned long long suffix_mle(uint32_t kind, unsigned long long bits, uint32_t len, uint32_t bound) {
+__host__ JA_DEV unsigned long long suffix_mle(uint32_t kind, unsigned long long bits, uint32_t len, uint32_t bound) {
   const unsigned long long low_mask = bound >= 64 ? ~0ull : ((1ull << bound) - 1);
   const unsigned long long low = bits & low_mask;
   const unsigned long long hi = (len > bound) ? (bits >> bound) : 0ull;
@@ -51,6 +51,7 @@ struct PsPhaseArgs {
   unsigned int* counter;           // zero on entry, reset on exit
   Fr* host_out;                    // n_suf x m results, host-mapped, tagged 48-byte elements (store_tagged)
   unsigned int seq_value;
+  unsigned int* sig_max;           // optional: max over the entries of the bits their SIGNED value needs (v in [-2^b, 2^b)); published as element n_suf * m
 };
 JA_DEV Fr fr_ld_cg(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
   for (uint32_t i = threadIdx.x; i < n_acc * kPsCols; i += blockDim.x) s_acc[i] = 0u;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
+  unsigned sig_local = 0;
   for (size_t base = (size_t)blockIdx.x * blockDim.x; base < a.T; base += (size_t)gridDim.x * blockDim.x) {
     const size_t j = base + threadIdx.x;
     Fr u = fp_zero<FrParams>();
@@ -92,6 +94,10 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
       }
       sb = a.suffix_len >= 64 ? k : (k & ((1ull << a.suffix_len) - 1));
       key = (uint32_t)((a.suffix_len >= 64 ? 0ull : (k >> a.suffix_len)) & a.m_mask);
+      if (a.sig_max && blockIdx.y == 0) {                               // bits of the signed value: 64 - clz(v >= 0 ? v : ~v)
+        const unsigned long long mag = (k >> 63) ? ~k : k;
+        sig_local = max(sig_local, 64u - (unsigned)__clzll((long long)mag));
+      }
     }
     // Shared-memory atomics cost 2 cycles per LANE (64 per warp instruction, 18 of them per entry, suffix and half), and clamp
     // lookups send whole warps to the bins 0x00 / 0xff in most phases.  So the warp first settles its (up to) two most common bins
@@ -156,6 +162,10 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
       }
     }
   }
+  if (a.sig_max && blockIdx.y == 0) {
+    const unsigned mx = __reduce_max_sync(0xffffffffu, sig_local);
+    if (lane == 0 && mx) atomicMax(a.sig_max, mx);
+  }
   __syncthreads();
   // block -> grid: the non-zero 16-bit columns go to the phase's global column table with 64-bit reductions at L2 (fire and forget;
   // a column is a plain integer sum, so no carry is resolved here either).  No per-tile fold, no partial tables: the fold to a field
@@ -207,6 +217,11 @@ __global__ void __launch_bounds__(256) k_ps_phase(const PsPhaseArgs a) {
     for (int i = 0; i < 5; i++) hi.l[i] = w[8 + i];
     const Fr val = fp_add<FrParams>(fp_mul<FrParams>(fp_one<FrParams>(), lo), fp_mul<FrParams>(fp_r2<FrParams>(), hi));
     store_tagged(a.host_out, (int)(sfx * m + key), val, a.seq_value);   // self-validating 48-byte element: no system fence, no flag
+  }
+  if (a.sig_max && blockIdx.y == 0 && threadIdx.x == 0) {              // every block of group 0 has added its maximum (fence + counter above)
+    Fr v = fp_zero<FrParams>();
+    v.l[0] = atomicExch(a.sig_max, 0u);
+    store_tagged(a.host_out, (int)(a.n_suf * m), v, a.seq_value);
   }
 }
 
@@ -273,10 +288,21 @@ static int32_t psshout_new_impl(ja_ctx* c, const uint64_t* lookup_indices, bool 
   return JA_OK;
 }
 
+static int32_t ps_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const uint64_t* v_prev, const uint32_t* suffix_kinds, size_t n_suffixes,
+                             uint32_t bound, uint64_t* out_Q, uint32_t* out_sigbits);
 int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const uint64_t* v_prev, const uint32_t* suffix_kinds, size_t n_suffixes,
                               uint32_t bound, uint64_t* out_Q) {
-  JA_REQUIRE(c && p && suffix_kinds && out_Q && n_suffixes >= 1 && n_suffixes <= (size_t)kPsMaxSuffixes, "ja_psshout_init_phase: bad argument");
+  JA_REQUIRE(c && p, "ja_psshout_init_phase: bad argument");
   JA_REQUIRE(phase == p->next_phase && phase < p->phases, "ja_psshout_init_phase: phases run in order 0 .. NUM_PHASES - 1");
+  return ps_init_phase(c, p, phase, v_prev, suffix_kinds, n_suffixes, bound, out_Q, nullptr);
+}
+// out_sigbits (optional): the largest number of bits the SIGNED value of a lookup index needs (scan fused into the pass).
+// `phase` may skip ahead of p->next_phase (ja_psshout_prove_address: leading phases done on the host): v_prev then stands for the
+// PRODUCT of the skipped phases' expanding-table entries, indexed by the chunk of phase - 1.
+static int32_t ps_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const uint64_t* v_prev, const uint32_t* suffix_kinds, size_t n_suffixes,
+                             uint32_t bound, uint64_t* out_Q, uint32_t* out_sigbits) {
+  JA_REQUIRE(c && p && suffix_kinds && out_Q && n_suffixes >= 1 && n_suffixes <= (size_t)kPsMaxSuffixes, "ja_psshout_init_phase: bad argument");
+  JA_REQUIRE(phase >= p->next_phase && phase < p->phases, "ja_psshout_init_phase: phases run in order 0 .. NUM_PHASES - 1");
   JA_REQUIRE((phase == 0) == (v_prev == nullptr), "ja_psshout_init_phase: the expanding table of the previous phase is required from phase 1 on");
   for (size_t s = 0; s < n_suffixes; s++) JA_REQUIRE(suffix_kinds[s] <= JA_SUF_SHIFT, "ja_psshout_init_phase: unknown suffix kind");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
@@ -293,7 +319,7 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   if (tiles > max_tiles) tiles = std::max<uint32_t>(max_tiles, (uint32_t)((p->T + (size_t(1) << 15) - 1) >> 15));   // a 32-bit shared column takes 2^16 digits of 16 bits
   JA_REQUIRE((p->T + tiles - 1) / tiles <= (size_t(1) << 15), "ja_psshout_init_phase: T too large for the column counters");
   const size_t n_out = n_suffixes * m;
-  JA_REQUIRE(n_out * 48 <= kRowSeqOffset, "ja_psshout_init_phase: result larger than the mapped value buffer");
+  JA_REQUIRE((n_out + 1) * 48 <= kRowSeqOffset, "ja_psshout_init_phase: result larger than the mapped value buffer");
   Fr* d_v = nullptr;
   int32_t st;
   if (!p->d_cols) {
@@ -313,6 +339,7 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   a.m_mask = m - 1; a.bound = bound; a.n_suf = (uint32_t)n_suffixes;
   for (size_t s = 0; s < n_suffixes; s++) a.kinds[s] = suffix_kinds[s];
   a.gcols = p->d_cols;
+  a.sig_max = out_sigbits ? c->d_counter + 8 + 1 + kPsMaxSuffixes : nullptr;     // behind the group counters, zero between passes
   a.counter = c->d_counter + 8;                                        // [0]: groups done, [1 + y]: blocks done of group y
   a.host_out = reinterpret_cast<Fr*>(c->d_rowvals);
   a.seq_value = next_tag(c);
@@ -330,6 +357,11 @@ int32_t ja_psshout_init_phase(ja_ctx* c, ja_psshout* p, uint32_t phase, const ui
   {
     // the results land in mapped host memory as self-validating tagged elements (bounded wait: common.hpp wait_tagged)
     if ((st = wait_tagged(c, c->h_rowvals, a.seq_value, n_out, out_Q, "ja_psshout_init_phase"))) return st;
+    if (out_sigbits) {
+      uint64_t sv[4];
+      if ((st = wait_tagged(c, reinterpret_cast<const char*>(c->h_rowvals) + n_out * 48, a.seq_value, 1, sv, "ja_psshout_init_phase"))) return st;
+      *out_sigbits = (uint32_t)sv[0];
+    }
     if (ps_trace) {
       const auto tr2 = std::chrono::steady_clock::now();
       auto us = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
@@ -481,10 +513,78 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
   std::vector<FrH> v_cur, v_next;
   p->h_v.assign((size_t)phases * m, ja::host::FR_ZERO);
   FrH r_prev = ja::host::FR_ZERO;
+  // Sign-extension phases.  Clamp lookups index the table with small SIGNED values (a rescaled accumulation): when every index needs at
+  // most `sig` bits (v in [-2^sig, 2^sig), sig <= BOUND; scanned inside the phase-0 pass), the chunk of every phase p whose suffix is
+  // at least sig bits long is 0x00 (v >= 0) or 0xff (v < 0) for EVERY entry.  The suffix polynomials of such a phase have two non-zero
+  // entries, u_evals = eq * (product of the finished phases' v[0x00] resp. v[0xff]), and every suffix MLE is affine in v on a sign
+  // class (t = alpha + beta v): Q_s[0x00] = cP (alpha S_P + beta V_P), Q_s[0xff] = cN (alpha S_N + beta V_N) with the four sums
+  // S = sum eq, V = sum eq v per class - all four are entries of the phase-0 tables.  So those phases need NO pass over the T entries:
+  // the host builds their tables, and the first real pass afterwards takes the product table [cP .. cN] as its "previous" one.
+  // (alpha, beta) come from the suffix MLE itself at two representatives and are checked at a third: a suffix that is not affine
+  // on the class switches the fast path off.  Same tables, same transcript as the reference's eight passes (tests/test_gpu_psshout.py).
+  static const bool no_skip = getenv("JA_PS_NO_SKIP") != nullptr;
+  unsigned n_virtual_end = 0;                              // phases 1 .. n_virtual_end - 1 are built on the host
+  FrH S_cls[2], V_cls[2], c_cls[2] = {ja::host::FR_ONE, ja::host::FR_ONE};
+  uint32_t sig = 64;
+  auto suffix_len_of = [&](unsigned ph) { return xlen - (ph + 1) * log_m; };
+  auto affine = [&](uint32_t kind, unsigned len, int cls, FrH* alpha, int* beta) -> bool {
+    const unsigned long long mask = len >= 64 ? ~0ull : ((1ull << len) - 1);
+    const long long v0 = cls ? -1ll : 0ll, v1 = cls ? -2ll : 1ll, v2 = cls ? -(1ll << sig) : ((1ll << sig) - 1);
+    const unsigned long long t0 = suffix_mle(kind, (unsigned long long)v0 & mask, len, bound), t1 = suffix_mle(kind, (unsigned long long)v1 & mask, len, bound),
+                             t2 = suffix_mle(kind, (unsigned long long)v2 & mask, len, bound);
+    const __int128 b = sig == 0 ? 0 : ((__int128)t1 - (__int128)t0) / (v1 - v0);
+    if (b != 0 && b != 1) return false;
+    const __int128 a0 = (__int128)t0 - b * v0;
+    if (a0 < 0 || a0 > (__int128)~0ull) return false;
+    if (sig != 0 && (__int128)t1 != a0 + b * v1) return false;
+    if ((__int128)t2 != a0 + b * v2) return false;
+    *alpha = ja::host::from_u64((uint64_t)a0); *beta = (int)b;
+    return true;
+  };
   for (unsigned phase = 0; phase < phases; phase++) {
-    int32_t st = ja_psshout_init_phase(c, p, phase, phase ? reinterpret_cast<const uint64_t*>(p->h_v.data() + (size_t)(phase - 1) * m) : nullptr,
-                                       kinds, 6, bound, reinterpret_cast<uint64_t*>(Qbuf.data()));
-    if (st) return st;
+    int32_t st = JA_OK;
+    if (phase >= 1 && phase < n_virtual_end) {
+      bool ok = true;
+      std::fill(Qbuf.begin(), Qbuf.end(), ja::host::FR_ZERO);
+      for (int r = 0; r < 6 && ok; r++)
+        for (int cls = 0; cls < 2 && ok; cls++) {
+          FrH alpha; int beta = 0;
+          ok = affine(kinds[r], suffix_len_of(phase), cls, &alpha, &beta);
+          if (!ok) break;
+          FrH a = mul(alpha, S_cls[cls]);
+          if (beta) a = add(a, V_cls[cls]);
+          Qbuf[(size_t)r * m + (cls ? m - 1 : 0)] = mul(c_cls[cls], a);
+        }
+      JA_REQUIRE(ok, "ja_psshout_prove_address: internal error (sign-extension phase lost its affine form)");   // checked for every phase up front
+    } else {
+      std::vector<FrH> tab;
+      const uint64_t* vprev = nullptr;
+      if (phase) {
+        if (phase == n_virtual_end && n_virtual_end > 1) {         // first real pass after host-built phases: u_evals = eq * c[class]
+          tab.assign(m, ja::host::FR_ZERO);
+          tab[0] = c_cls[0]; tab[m - 1] = c_cls[1];
+          vprev = reinterpret_cast<const uint64_t*>(tab.data());
+        } else {
+          vprev = reinterpret_cast<const uint64_t*>(p->h_v.data() + (size_t)(phase - 1) * m);
+        }
+      }
+      st = ps_init_phase(c, p, phase, vprev, kinds, 6, bound, reinterpret_cast<uint64_t*>(Qbuf.data()), phase == 0 && !no_skip ? &sig : nullptr);
+      if (st) return st;
+      if (phase == 0 && !no_skip && sig <= bound && sig < 63 && m >= 2) {
+        unsigned h = 0;
+        while (h < phases && suffix_len_of(h) >= sig) h++;
+        bool ok = h >= 2;
+        for (unsigned ph = 1; ph < h && ok; ph++)
+          for (int r = 0; r < 6 && ok; r++)
+            for (int cls = 0; cls < 2 && ok; cls++) { FrH al; int be; ok = affine(kinds[r], suffix_len_of(ph), cls, &al, &be); }
+        if (ok) {
+          // the four class sums from the phase-0 tables: One suffix -> S, Identity suffix -> V (for v < 0 the suffix value is 2^len + v)
+          S_cls[0] = Qbuf[3 * m]; S_cls[1] = Qbuf[3 * m + m - 1];
+          V_cls[0] = Qbuf[5 * m]; V_cls[1] = sub(Qbuf[5 * m + m - 1], mul(pow2[suffix_len_of(0)], S_cls[1]));
+          n_virtual_end = h;
+        }
+      }
+    }
     // rows: 0 higher-all-zero, 1 hzero*lword, 2 hone*lword, 3 one (== row 4, the raf decomposition's One suffix), 5 identity
     FrH* Q[5] = {Qbuf.data(), Qbuf.data() + m, Qbuf.data() + 2 * m, Qbuf.data() + 3 * m, Qbuf.data() + 5 * m};
     const unsigned s_len = xlen - (phase + 1) * log_m;                 // suffix_len of the phase
@@ -589,6 +689,7 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
     if (getenv("JA_PS_TRACE")) fprintf(stderr, "[ps_trace] phase %u host rounds %.1f us\n", phase, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_rounds).count());
     cp_id = bid;                                                                   // PrefixRegistry::update_checkpoints
     memcpy((void*)(p->h_v.data() + (size_t)phase * m), v_cur.data(), m * sizeof(FrH));
+    c_cls[0] = mul(c_cls[0], v_cur[0]); c_cls[1] = mul(c_cls[1], v_cur[m - 1]);
   }
   // val = combine(prefix checkpoints, suffixes of the empty suffix) (mod.rs:527-552): suffixes [1, 0, 0, 1]
   {

@@ -488,10 +488,21 @@ def count_units(inputs) -> dict:
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
     rounds += inputs["ell"]                                             # the batched opening reduction
     n_rem = sum(1 for ni in inputs["nodes"] if ni.d_hot > D_CLAMP)
+    # T-sized passes the device actually runs for the clamp read-raf: the sign-extension phases of small signed lookup values are
+    # built on the host from the phase-0 pass (ja_psshout_prove_address), see DESIGN 4b
+    dev_passes = 0
+    for ni in inputs["nodes"]:
+        v = ni.acc.view(np.int64)
+        mag = np.where(v < 0, ~v, v).astype(np.uint64)
+        sig = int(mag.max()).bit_length() if mag.size else 0
+        log_m = CLAMP_LOG_K // PS_PHASES
+        h = sum(1 for ph in range(PS_PHASES) if CLAMP_LOG_K - (ph + 1) * log_m >= sig) if sig <= SAT_BOUND else 0
+        dev_passes += PS_PHASES - (h - 1 if h >= 2 else 0)
     addr = CLAMP_LOG_K * len(inputs["nodes"]) + MODEL_SCALE * n_rem     # read-raf + remainder range-check address rounds (host, small tables)
     return {"sumcheck_rounds": rounds + addr, "sumcheck_rounds_device": rounds, "ps_shout_address_rounds": addr,
             "onehot_point_additions": adds, "open_msm_pairs": 4 << inputs["ell"],
-            "ps_shout_phase_passes": PS_PHASES * len(inputs["nodes"]) + device_rc_phases(MODEL_SCALE) * n_rem}
+            "ps_shout_phase_passes": PS_PHASES * len(inputs["nodes"]) + device_rc_phases(MODEL_SCALE) * n_rem,
+            "ps_shout_device_passes": dev_passes + device_rc_phases(MODEL_SCALE) * n_rem}
 
 
 # ---- measurement helpers (bench.py) -------------------------------------------------------------------------------

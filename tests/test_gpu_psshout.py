@@ -142,3 +142,33 @@ def test_identity_rc_phase_count_is_free(ctx):
     ra = dev.materialize_ra()
     assert np.array_equal(ra.to_host(), cpu.materialize_ra(want["v"].reshape(-1, 4)))
     ra.free(); dev.free(); cpu.free()
+
+
+@pytest.mark.parametrize("log_t,bound,lo,hi", [(10, 31, -64, 64), (12, 31, -(1 << 20), 1 << 20), (9, 31, -(1 << 31), 1 << 31), (8, 31, -1, 1),
+                                               (11, 31, 0, 1000), (10, 31, -5000, 0), (10, 9, -300, 300), (9, 31, -(1 << 40), 1 << 40)])
+def test_sign_extension_phases_match_oracle(ctx, log_t, bound, lo, hi):
+    """Small signed lookup values: ja_psshout_prove_address builds the suffix polynomials of the sign-extension phases on the host
+    from the four class sums of the phase-0 pass (no T-sized pass for them) - the proof must stay the oracle's, which runs all eight
+    passes.  Ranges: a few bits, 20 bits, the full i32 range (sig = BOUND), {-1, 0}, one-sided, BOUND = 9 with values beyond it, and
+    values wider than BOUND (fast path off).  JA_PS_NO_SKIP is the library's switch for the all-passes form."""
+    from jolt_atlas_b200 import api as A
+    rng = np.random.default_rng(31 * log_t + (hi - lo) % 1000)
+    T = 1 << log_t
+    idx = rng.integers(lo, hi, size=T).astype(np.int64)
+    idx[0], idx[1] = lo, hi - 1
+    idx = idx.view(np.uint64)
+    r = _chal(rng, log_t)
+    gamma = _chal(rng, 1)[0]
+    dev, cpu = A.PrefixSuffixShout(ctx, idx, r), ORC.PsShout(idx, r)
+    td, tc = A.Blake2bTranscriptState(b"ps_sign"), ORC.TranscriptState(b"ps_sign")
+    got = dev.prove_address(td, gamma, bound)
+    want = cpu.prove_address(tc, gamma, None, bound)
+    for k in ("ncoeffs", "coeffs", "challenges", "val", "raf_val", "claim"):
+        assert np.array_equal(got[k], want[k]), k
+    assert td.state == tc.state and td.n_rounds == tc.n_rounds
+    assert np.array_equal(dev.tables(), want["v"])
+    scale = ORC.fr_binop(0, got["val"].reshape(1, 4), got["raf_val"].reshape(1, 4))[0]
+    ra = dev.materialize_ra(scale=scale)
+    ra_cpu = cpu.materialize_ra(want["v"].reshape(-1, 4))
+    assert np.array_equal(ra.to_host(), ORC.fr_binop(2, ra_cpu, np.broadcast_to(scale, ra_cpu.shape).copy()))
+    ra.free(); dev.free(); cpu.free()
