@@ -591,7 +591,12 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
     FrH bid = cp_id;
     v_cur.assign(1, ja::host::FR_ONE);
     const auto t_rounds = std::chrono::steady_clock::now();
+    double tr_acc[4] = {0, 0, 0, 0};
+    static const bool tr_on = getenv("JA_PS_TRACE") != nullptr;
+    auto tr_now = [] { return std::chrono::steady_clock::now(); };
+    auto tr_us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     for (unsigned tt = 0; tt < log_m; tt++) {
+      const auto tq0 = tr_now();
       const unsigned j = phase * log_m + tt, b_len = log_m - 1 - tt;
       const size_t half = size_t(1) << b_len;
       const unsigned n_hi = bound_index >= j ? std::min<unsigned>(bound_index - j, b_len) : 0;   // b's top n_hi bits are "higher" bits
@@ -617,6 +622,7 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       const FrH two_s = pow2[s_len];
       const FrH kappa = j == 0 ? neg(pow2[xlen - 1]) : pow2[b_len + s_len];        // coefficient of the current variable in the identity prefix
       // E(c, side) = sum_b combine(P_c(b), Q_side(b)); raf(c, side) = sum_b P_c(b) Q_one(b) + Q_id(b)
+      const auto tq1 = tr_now();
       // products that do not depend on c, once per side: 2^s A_w - CU A_haz, 2^s B_w, 2^s W_all
       FrH zc[2], oc[2], wc[2];
       for (int sd = 0; sd < 2; sd++) {
@@ -656,6 +662,7 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       const FrH t2l = table_part(q2, 0), t2h = table_part(q2, 1);
       const FrH a2l = raf_part(2, 0), a2r = raf_part(2, 1);
       const FrH e2 = add(sub(dbl(t2h), t2l), mul(gamma, sub(dbl(a2r), a2l)));
+      const auto tq2 = tr_now();
       const ja::host::Coeffs uni = ja::host::from_evals_and_hint(claim, {e0, e2});
       const ja::host::Coeffs cpr = ja::host::compress(uni);
       JA_REQUIRE(cpr.size() <= 2, "ja_psshout_prove_address: round polynomial of degree > 2");
@@ -669,12 +676,15 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
       out_ncoeffs[j] = (uint32_t)cpr.size();
       for (size_t k = 0; k < 2; k++) memcpy(out_coeffs + 4 * (2 * j + k), k < cpr.size() ? cpr[k].l : ja::host::FR_ZERO.l, 32);
       memcpy(out_challenges + 4 * j, ch, 32);
+      const auto tq3 = tr_now();
       // ingest_challenge (mod.rs:491-560)
       // H2L binds: clamp lookups leave most entries of most rows zero in the sign-extension phases - a zero difference costs no product
       for (int q = 0; q < 5; q++)
         for (size_t b = 0; b < half; b++) {
-          const FrH d = sub(Q[q][b + half], Q[q][b]);
-          if (!d.is_zero()) Q[q][b] = add(Q[q][b], ja::host::mul_chal(d, rj));
+          const FrH &lo_ = Q[q][b], &hi_ = Q[q][b + half];
+          if ((lo_.l[0] | lo_.l[1] | lo_.l[2] | lo_.l[3] | hi_.l[0] | hi_.l[1] | hi_.l[2] | hi_.l[3]) == 0) continue;   // both zero: nothing to bind
+          const FrH d = sub(hi_, lo_);
+          if (!d.is_zero()) Q[q][b] = add(lo_, ja::host::mul_chal(d, rj));
         }
       bid = add(bid, ja::host::mul_chal(kappa, rj));
       v_next.resize(v_cur.size() * 2);                                             // ExpandingTable::update, HighToLow (expanding_table.rs:76-86)
@@ -685,8 +695,10 @@ int32_t ja_psshout_prove_address(ja_ctx* c, ja_psshout* p, uint32_t bound, const
         for (int k = 0; k < 4; k++) cp[k] = ps_update_checkpoint(k, prev, r_prev, rj, j, bound_index, pow2, xlen);
       }
       r_prev = rj;
+      if (tr_on) { const auto tq4 = tr_now(); tr_acc[0] += tr_us(tq0, tq1); tr_acc[1] += tr_us(tq1, tq2); tr_acc[2] += tr_us(tq2, tq3); tr_acc[3] += tr_us(tq3, tq4); }
     }
-    if (getenv("JA_PS_TRACE")) fprintf(stderr, "[ps_trace] phase %u host rounds %.1f us\n", phase, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_rounds).count());
+    if (tr_on) fprintf(stderr, "[ps_trace] phase %u host rounds %.1f us (sums %.1f, scalars+parts %.1f, interp+transcript %.1f, ingest %.1f)\n", phase,
+                       tr_us(t_rounds, tr_now()), tr_acc[0], tr_acc[1], tr_acc[2], tr_acc[3]);
     cp_id = bid;                                                                   // PrefixRegistry::update_checkpoints
     memcpy((void*)(p->h_v.data() + (size_t)phase * m), v_cur.data(), m * sizeof(FrH));
     c_cls[0] = mul(c_cls[0], v_cur[0]); c_cls[1] = mul(c_cls[1], v_cur[m - 1]);
