@@ -114,6 +114,7 @@ void ja_shutdown(ja_ctx* c) {
   ja_comm_free(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (EqTableCacheEntry& e : c->eq_cache) { dev_free(c, e.out_levels); dev_free(c, e.in_levels); e.out_levels = e.in_levels = nullptr; }
   dev_cache_release(c);
   cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out);
   cudaFreeHost(c->h_pinned);
@@ -399,10 +400,43 @@ int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, co
     s->current_index = 0;
   }
   s->out_len = (int)n_out_vars + 1; s->in_len = (int)n_in_vars + 1;
+  // table cache: same (order, point) -> the tables already on the device
+  static const bool no_eq_cache = getenv("JA_NO_EQ_CACHE") != nullptr;
+  constexpr size_t kEqCacheSlots = 6;
+  std::vector<uint64_t> key;
+  if (!no_eq_cache && m >= 1) {
+    key.resize(2 + 4 * m);
+    key[0] = (uint64_t)order; key[1] = m;
+    memcpy(key.data() + 2, w, 32 * m);
+    for (size_t i = 0; i < c->eq_cache.size(); i++) {
+      EqTableCacheEntry& e = c->eq_cache[i];
+      if (e.out_levels && e.key == key) {
+        e.refs++; e.stamp = ++c->eq_cache_clock;
+        s->out_levels = e.out_levels; s->in_levels = e.in_levels; s->cache_slot = (int)i;
+        *out = s;
+        return JA_OK;
+      }
+    }
+  }
   int32_t st = dev_alloc(c, (size_t(2) << n_out_vars) * sizeof(Fr), (void**)&s->out_levels);
   if (st) { delete s; return st; }
   st = dev_alloc(c, (size_t(2) << n_in_vars) * sizeof(Fr), (void**)&s->in_levels);
   if (st) { delete s; return st; }
+  if (!key.empty()) {
+    // take a free slot, or the least recently used one nobody references (its buffers return to the allocator: stream-ordered reuse)
+    int slot = -1;
+    if (c->eq_cache.size() < kEqCacheSlots) { c->eq_cache.emplace_back(); slot = (int)c->eq_cache.size() - 1; }
+    else {
+      for (size_t i = 0; i < c->eq_cache.size(); i++)
+        if (c->eq_cache[i].refs == 0 && (slot < 0 || c->eq_cache[i].stamp < c->eq_cache[slot].stamp)) slot = (int)i;
+      if (slot >= 0 && c->eq_cache[slot].out_levels) { dev_free(c, c->eq_cache[slot].out_levels); dev_free(c, c->eq_cache[slot].in_levels); }
+    }
+    if (slot >= 0) {
+      EqTableCacheEntry& e = c->eq_cache[slot];
+      e.key = std::move(key); e.out_levels = s->out_levels; e.in_levels = s->in_levels; e.refs = 1; e.stamp = ++c->eq_cache_clock;
+      s->cache_slot = slot;
+    }
+  }
   const int rev = order == JA_HIGH_TO_LOW ? 1 : 0;
   if (n_out_vars <= (size_t)kEqValMax && n_in_vars <= (size_t)kEqValMax) {
     // the point travels in the kernel parameters: no staged copy ahead of the launch
@@ -417,9 +451,15 @@ int32_t ja_spliteq_new(ja_ctx* c, const uint64_t* w, size_t m, int32_t order, co
     return JA_OK;
   }
   Fr* d_w = nullptr;
+  auto drop = [&](int32_t e) {        // error exit: the half-built tables must not stay in the cache
+    if (s->cache_slot >= 0) { c->eq_cache[s->cache_slot].out_levels = nullptr; c->eq_cache[s->cache_slot].in_levels = nullptr; c->eq_cache[s->cache_slot].refs = 0; }
+    dev_free(c, s->out_levels); dev_free(c, s->in_levels); dev_free(c, d_w);
+    delete s;
+    return e;
+  };
   st = dev_alloc(c, (m ? m : 1) * sizeof(Fr), (void**)&d_w);
-  if (st) { delete s; return st; }
-  if (m && (st = stage_h2d(c, d_w, w, m * 32))) { delete s; return st; }
+  if (st) return drop(st);
+  if (m && (st = stage_h2d(c, d_w, w, m * 32))) return drop(st);
   EqLevelsArgs a;
   a.w[0] = d_w + off_out; a.m[0] = (int)n_out_vars; a.rev[0] = rev; a.buf[0] = s->out_levels; a.scale[0] = to_dev(host::FR_ONE);
   a.w[1] = d_w + off_in;  a.m[1] = (int)n_in_vars;  a.rev[1] = rev; a.buf[1] = s->in_levels;  a.scale[1] = to_dev(host::FR_ONE);
@@ -493,7 +533,11 @@ void ja_spliteq_free(ja_ctx* c, ja_spliteq* s) {
   if (!c || !s) return;
   std::lock_guard<std::recursive_mutex> lk(c->mu);
   cudaSetDevice(c->device);
-  dev_free(c, s->out_levels); dev_free(c, s->in_levels);
+  if (s->cache_slot >= 0 && (size_t)s->cache_slot < c->eq_cache.size() && c->eq_cache[s->cache_slot].out_levels == s->out_levels) {
+    if (c->eq_cache[s->cache_slot].refs > 0) c->eq_cache[s->cache_slot].refs--;      // the cache keeps the tables
+  } else {
+    dev_free(c, s->out_levels); dev_free(c, s->in_levels);
+  }
   delete s;
 }
 

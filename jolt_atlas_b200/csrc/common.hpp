@@ -39,8 +39,20 @@ static inline int32_t fail(int32_t code, const std::string& msg) {
 #define JA_REQUIRE(cond, msg) \
   do { if (!(cond)) return fail(JA_ERR_INVALID, msg); } while (0)
 
+// Split-eq prefix tables are read-only once built and depend on (order, point) only: the instances of a node (read-raf cycle rounds,
+// RA checks, operator, range check) share r_node_output, so the context keeps the last few table pairs and hands them out by reference
+// count (the reference's ProverOpeningAccumulator::eq_cycle_map caches the same thing for the opening reduction).
+struct EqTableCacheEntry {
+  std::vector<uint64_t> key;         // order, m, then the 4 m limbs of the point
+  Fr* out_levels = nullptr;
+  Fr* in_levels = nullptr;
+  int refs = 0;
+  uint64_t stamp = 0;
+};
 struct ja_ctx {
   int device = 0;
+  std::vector<EqTableCacheEntry> eq_cache;
+  uint64_t eq_cache_clock = 0;
   cudaStream_t stream = nullptr;
   std::recursive_mutex mu;
   Fr* d_partials = nullptr;        // kMaxGrid * kMaxOut
@@ -198,6 +210,7 @@ struct ja_spliteq {
   // prefix tables: level k (2^k entries) at offset 2^k - 1
   Fr* out_levels = nullptr;
   Fr* in_levels = nullptr;
+  int cache_slot = -1;               // >= 0: the tables belong to ja_ctx::eq_cache[cache_slot]
   int out_len = 1;   // E_out_vec.len()  (current table = level out_len-1)
   int in_len = 1;    // E_in_vec.len()
   const Fr* e_out() const { return out_levels + ((size_t(1) << (out_len - 1)) - 1); }
