@@ -429,8 +429,14 @@ def make_resident(ctx, inputs):
     from . import api as A
     nodes = []
     for ni in inputs["nodes"]:
-        d = {"ps": _ResidentPs(ctx, A, ni),
-             "ps_rem": _ResidentPs(ctx, A, ni, rem=True) if ni.d_hot > D_CLAMP else None,
+        # the node's witness stays on the device (lookup indices of both ps_shout instances): a pass starts its states device to device
+        op, S = witness_op(ni.spec)
+        ta = A.TensorI32(ctx, ni.A if ni.A.ndim == 2 else ni.A.reshape(1, -1))
+        tb = A.TensorI32(ctx, ni.B if ni.B.ndim == 2 else ni.B.reshape(1, -1))
+        wit = A.FusedWitness(ctx, op, ta, tb, S, 1 << ni.spec.log_t)
+        ta.free(); tb.free()
+        d = {"wit": wit, "ps": _ResidentPs(ctx, A, ni, wit),
+             "ps_rem": _ResidentPs(ctx, A, ni, wit, rem=True) if ni.d_hot > D_CLAMP else None,
              "hot16": A.OneHotAddresses(ctx, ni.hot_k[:D_CLAMP], K_CHUNK),
              "hot4": A.OneHotAddresses(ctx, ni.hot_k[D_CLAMP:], K_CHUNK) if ni.d_hot > D_CLAMP else None}
         if ni.spec.kind != "einsum":
@@ -444,19 +450,17 @@ def make_resident(ctx, inputs):
 
 
 class _ResidentPs:
-    """Device-resident lookup indices of a node's clamp read-raf (the resident leg of the bench): a fresh ps_shout state per pass
-    without re-uploading the indices is not part of the C ABI, so the resident leg re-creates the state from host indices kept
-    pinned; only the index upload (8 B per entry) is repeated."""
+    """A fresh ps_shout state per pass over the lookup indices of the node's device-resident witness (device-to-device copy)."""
 
-    def __init__(self, ctx, A, ni, rem=False):
-        self.ctx, self.A, self.ni, self.cur, self.rem = ctx, A, ni, None, rem
+    def __init__(self, ctx, A, ni, wit, rem=False):
+        self.ctx, self.A, self.ni, self.wit, self.cur, self.rem = ctx, A, ni, wit, None, rem
 
     def restart(self):
         self.free()
         if self.rem:
-            self.cur = self.A.PrefixSuffixShout(self.ctx, self.ni.rem, self.ni.eq_w, MODEL_SCALE, device_rc_phases(MODEL_SCALE))
+            self.cur = self.wit.rem_shout(self.ni.eq_w, device_rc_phases(MODEL_SCALE))
         else:
-            self.cur = self.A.PrefixSuffixShout(self.ctx, self.ni.acc, self.ni.eq_w, CLAMP_LOG_K, PS_PHASES)
+            self.cur = self.wit.ps_shout(self.ni.eq_w, CLAMP_LOG_K, PS_PHASES)
         return self.cur
 
     def free(self):
@@ -470,6 +474,7 @@ def free_resident(res):
         d["ps"].free()
         if d["ps_rem"] is not None:
             d["ps_rem"].free()
+        d["wit"].free()
         d["hot16"].free()
         if d["hot4"] is not None:
             d["hot4"].free()
