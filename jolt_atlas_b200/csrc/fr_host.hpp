@@ -100,8 +100,18 @@ static inline FrH from_i64(int64_t v) {
 }
 // Montgomery limbs -> canonical integer limbs
 static inline void to_canonical(const FrH& a, uint64_t out[4]) {
-  FrH one = {{1, 0, 0, 0}};
-  FrH r = mul(a, one);
+  // one REDC pass (a * R^-1 mod p): the four reduction steps of the CIOS product without its multiply rows - every scalar the
+  // transcript absorbs goes through here
+  uint64_t t[5] = {a.l[0], a.l[1], a.l[2], a.l[3], 0};
+  for (int i = 0; i < 4; i++) {
+    const uint64_t m = t[0] * FR_INV;
+    u128 c = (u128)m * FR_P[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * FR_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = (uint64_t)(c >> 64);
+  }
+  FrH r = {{t[0], t[1], t[2], t[3]}};
+  if (t[4] || geq_p(r.l)) sub_p(r.l);
   memcpy(out, r.l, 32);
 }
 static inline FrH from_canonical(const uint64_t in[4]) { FrH t; memcpy(t.l, in, 32); return mul(t, FR_R2); }
