@@ -143,6 +143,35 @@ class NodeInputs:
     eq_cols: np.ndarray | None = None
 
 
+# Transformer operators WITHOUT lookups that a real graph carries per layer next to the fused nodes: the causal mask (Iff, ops/iff.rs:189),
+# the softmax normalisation (Div, ops/div.rs:329), the two layer norms (Rsqrt with its gamma pair, ops/rsqrt.rs:390) and their means
+# (ScalarConstDiv / neural-teleport division = the three-operand linear body, ops/scalar_const_div.rs:227, neural_teleport/division.rs:231).
+# (kernel id, polynomials, aux scalars, "scores" or "embed" sized); sizes follow the layer's score / projection nodes.
+AUX_PER_LAYER = ((8, 3, 0, "scores"), (9, 4, 0, "scores"), (10, 5, 2, "embed"), (11, 3, 1, "embed"), (10, 5, 2, "embed"), (11, 3, 1, "embed"))
+NODES_PER_LAYER = 10
+
+
+@dataclass
+class AuxInputs:
+    kind: int
+    log_t: int
+    polys: np.ndarray          # (npoly, T) int32 operands (small integers; the Iff condition is a 0/1 mask)
+    aux: np.ndarray | None     # (naux, 4) Fr scalars of the body (Rsqrt gammas, the constant of the linear body)
+    eq_w: np.ndarray           # (log_t, 4)
+
+
+def build_aux(rng: np.random.Generator, layer_specs) -> list:
+    sizes = {"scores": layer_specs[1].log_t, "embed": layer_specs[4].log_t}
+    out = []
+    for kind, npoly, naux, size in AUX_PER_LAYER:
+        log_t = sizes[size]
+        polys = rng.integers(-(1 << 12), 1 << 12, size=(npoly, 1 << log_t), dtype=np.int32)
+        if kind == 8:
+            polys[0] = rng.integers(0, 2, size=1 << log_t, dtype=np.int32)
+        out.append(AuxInputs(kind, log_t, np.ascontiguousarray(polys), _challenges(rng, naux) if naux else None, _challenges(rng, log_t)))
+    return out
+
+
 MODEL_SCALE = 14      # common/src/consts/general.rs (rescale bits S of Einsum / Mul; Add carries no rescale)
 
 
@@ -222,8 +251,13 @@ def build_inputs(config: str, seed: int | None = None):
     ell = cfg["ell"]
     open_point = _challenges(rng, ell)
     claim = _challenges(rng, 1)[0]       # the prover never checks its input claim; one fixed value feeds every instance
-    return {"config": config, "nodes": nodes, "ell": ell, "open_point": open_point, "claim": claim,
-            "rlc_seed": int(rng.integers(1, 1 << 31))}
+    rlc_seed = int(rng.integers(1, 1 << 31))
+    # per-layer operators without lookups (after the fused nodes of the layer); drawn last so that the fused nodes keep their inputs
+    specs = [ni.spec for ni in nodes]
+    aux = {}
+    for layer in range(len(nodes) // NODES_PER_LAYER):
+        aux[(layer + 1) * NODES_PER_LAYER - 1] = build_aux(rng, specs[layer * NODES_PER_LAYER:(layer + 1) * NODES_PER_LAYER])
+    return {"config": config, "nodes": nodes, "aux": aux, "ell": ell, "open_point": open_point, "claim": claim, "rlc_seed": rlc_seed}
 
 
 def onehot_index_lists(ni: NodeInputs):
@@ -240,6 +274,8 @@ def h2d_bytes(inputs) -> int:
         # the one-hot addresses and the clamp lookup indices are generated on the device from the operands (FusedWitness): only
         # the operands (once for the witness, once more for the operator's own polynomials / folds) and the small tables cross PCIe
         total += 2 * ni.tables.nbytes + 2 * (ni.A.nbytes + ni.B.nbytes)
+    for lst in inputs.get("aux", {}).values():
+        total += sum(ax.polys.nbytes for ax in lst)
     return total
 
 
@@ -385,6 +421,15 @@ def _run_device(A, PAR, ctx, srs, inputs, resident, comm, ps_shout, t, out, clai
             else:
                 _sc(ctx, A.EvalKernel.IDENT, [rem0], claim, t, eq_w=ni.eq_w)
                 rem0.free()
+        # H. the layer's operators without lookups (mask, softmax normalisation, layer norms): one split-eq sumcheck each
+        if ps_shout:
+            for j, ax in enumerate(inputs.get("aux", {}).get(i, ())):
+                if res:
+                    polys = [p_.clone() for p_ in resident["aux"][i][j]]
+                else:
+                    polys = [A.MultilinearPolynomial.from_i32(ctx, col) for col in ax.polys]
+                _sc(ctx, ax.kind, polys, claim, t, eq_w=ax.eq_w, gammas=ax.aux)
+                A.MultilinearPolynomial.free_many(polys)
         out["states"].append(t.state)
     # G. prove_reduced_openings (prover.rs:141-176): ONE BatchedSumcheck over every committed polynomial
     #    (opening_proof.rs:500-532), gamma powers (:611-643), the materialised RLC (rlc_polynomial.rs:13-78) and the
@@ -424,6 +469,11 @@ def _run_device(A, PAR, ctx, srs, inputs, resident, comm, ps_shout, t, out, clai
     return out
 
 
+def A_free_many(polys):
+    from . import api as A
+    A.MultilinearPolynomial.free_many(polys)
+
+
 def make_resident(ctx, inputs):
     """Upload every per-proof input once (the device-resident leg of the bench reuses these)."""
     from . import api as A
@@ -446,7 +496,8 @@ def make_resident(ctx, inputs):
             d["A"] = A.TensorI32(ctx, ni.A)
             d["B"] = A.TensorI32(ctx, ni.B)
         nodes.append(d)
-    return {"nodes": nodes}
+    aux = {i: [[A.MultilinearPolynomial.from_i32(ctx, col) for col in ax.polys] for ax in lst] for i, lst in inputs.get("aux", {}).items()}
+    return {"nodes": nodes, "aux": aux}
 
 
 class _ResidentPs:
@@ -470,6 +521,9 @@ class _ResidentPs:
 
 
 def free_resident(res):
+    for lst in res.get("aux", {}).values():
+        for polys in lst:
+            A_free_many(polys)
     for d in res["nodes"]:
         d["ps"].free()
         if d["ps_rem"] is not None:
@@ -491,6 +545,7 @@ def count_units(inputs) -> dict:
         adds += ni.d_hot * (1 << lt)
         rounds += (LOG_K + lt) + lt + ((LOG_K + lt) + lt if ni.d_hot > D_CLAMP else 0)     # batched RA checks + cycle rounds
         rounds += (ni.spec.k - 1).bit_length() if ni.spec.kind == "einsum" else lt
+    rounds += sum(ax.log_t for lst in inputs.get("aux", {}).values() for ax in lst)      # mask / div / rsqrt / linear bodies
     rounds += inputs["ell"]                                             # the batched opening reduction
     n_rem = sum(1 for ni in inputs["nodes"] if ni.d_hot > D_CLAMP)
     # T-sized passes the device actually runs for the clamp read-raf: the sign-extension phases of small signed lookup values are
@@ -573,9 +628,10 @@ def algorithmic_fieldmuls(inputs) -> dict:
 
 def config_dict(config: str, inputs, world: int = 1, shard: bool = False) -> dict:
     u = count_units(inputs)
-    return {"workload": "%s-shaped prove pass: %d nodes (one-hot commits K=16, lookup/RA/operator/range-check sumchecks, "
-                        "chained Blake2b transcript) + HyperKZG open ell=%d; synthetic i8-range tensors" %
-                        (config, len(inputs["nodes"]), inputs["ell"]),
+    n_aux = sum(len(v) for v in inputs.get("aux", {}).values())
+    return {"workload": "%s-shaped prove pass: %d fused nodes (witness generation, one-hot commits K=16, read-raf / RA / operator / range-check "
+                        "sumchecks) + %d mask / div / rsqrt / linear operator sumchecks, chained Blake2b transcript, HyperKZG open ell=%d; "
+                        "synthetic i8-range tensors" % (config, len(inputs["nodes"]), n_aux, inputs["ell"]),
             "sumcheck_rounds": u["sumcheck_rounds"], "onehot_point_additions": u["onehot_point_additions"],
             "open_msm_pairs": u["open_msm_pairs"],
             "l2": "no explicit flush: one pass streams %.0f MB of polynomial data through a 126 MB L2" %

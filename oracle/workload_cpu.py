@@ -54,7 +54,7 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
     out = {"commitments": [], "states": [], "finals": []}
     claim = inputs["claim"]
     nodes = inputs["nodes"] if node_limit is None else inputs["nodes"][:node_limit]
-    for ni in (nodes if iop else []):
+    for node_index, ni in enumerate(nodes if iop else []):
         spec = ni.spec
         # witness generation is part of prove (ONNXProof::commit_witness_polynomials, prover.rs:72-87 -> witness.rs:142-214): the twin
         # re-derives the chunk lists from the operands and checks them against the workload's
@@ -107,6 +107,12 @@ def run_cpu(srs_host: np.ndarray, inputs, rlc_host=None, node_limit: int | None 
             ra_claim = _fr_div(r["final_claims"][0], pr["raf_val"])
             _cache(t, ra_claim)
             out["finals"].append(ra_claim.reshape(1, 4))
+        # the layer's operators without lookups (mask, softmax normalisation, layer norms)
+        for ax in inputs.get("aux", {}).get(node_index, ()):
+            polys = np.stack([ORC.fr_from_i64(col) for col in ax.polys])
+            r = ORC.sumcheck_prove_st(0, ax.kind, polys, ax.eq_w, claim, t, gammas=ax.aux)
+            _cache(t, r["final_claims"])
+            out["finals"].append(r["final_claims"])
         out["states"].append(t.state)
     if do_open:
         # prove_reduced_openings: batched opening reduction over every one-hot polynomial, gamma powers, RLC, HyperKZG open
