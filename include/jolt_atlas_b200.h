@@ -105,6 +105,8 @@ int32_t ja_poly_from_fr(ja_ctx*, const uint64_t* z, size_t n, ja_poly** out);
 /* I32Scalars(CompactPolynomial<i32>) — `MultilinearPolynomial::from(tensor.padded_next_power_of_two())`
  * (ops/mul.rs:146-147).  Stays 4 B/coeff on device until the first bind (compact_polynomial.rs:272-353). */
 int32_t ja_poly_from_i32(ja_ctx*, const int32_t* z, size_t n, ja_poly** out);
+/* `count` polynomials of n coefficients each from one row-major i32 matrix: one copy, one synchronisation (the operands of a node) */
+int32_t ja_poly_from_i32_many(ja_ctx*, const int32_t* z, size_t count, size_t n, ja_poly** out);
 /* RaPolynomial materialisation (joltworks/src/poly/ra_poly.rs:31-81; shout.rs:549-598): out[t] = table[idx[t]] with
  * table = K eq evaluations; idx[t] == 0xFFFFFFFF (None) -> 0.  n must be a power of two. */
 int32_t ja_poly_from_lookup(ja_ctx*, const uint64_t* table, size_t K, const uint32_t* idx, size_t n, ja_poly** out);

@@ -24,6 +24,7 @@ SIGNATURES = {
     "ja_launch_count": (C.c_uint64, [vp]),
     "ja_poly_from_fr": (C.c_int32, [vp, u64p, C.c_size_t, vpp]),
     "ja_poly_from_i32": (C.c_int32, [vp, i32p, C.c_size_t, vpp]),
+    "ja_poly_from_i32_many": (C.c_int32, [vp, i32p, C.c_size_t, C.c_size_t, vpp]),
     "ja_poly_from_lookup": (C.c_int32, [vp, u64p, C.c_size_t, u32p, C.c_size_t, vpp]),
     "ja_poly_alloc": (C.c_int32, [vp, C.c_size_t, vpp]),
     "ja_poly_clone": (C.c_int32, [vp, vp, vpp]),

@@ -150,6 +150,14 @@ class MultilinearPolynomial:
         return MultilinearPolynomial(ctx, h)
 
     @staticmethod
+    def from_i32_many(ctx: Context, mat) -> list:
+        """One polynomial per row of an (npoly, n) int32 matrix: one copy and one synchronisation for all of them."""
+        mat = np.ascontiguousarray(mat, dtype=np.int32)
+        hs = (C.c_void_p * mat.shape[0])()
+        check(ctx._lib.ja_poly_from_i32_many(ctx._h, mat.ctypes.data_as(_lib.i32p), mat.shape[0], mat.shape[1], hs))
+        return [MultilinearPolynomial(ctx, C.c_void_p(h)) for h in hs]
+
+    @staticmethod
     def from_lookup(ctx: Context, table, idx) -> "MultilinearPolynomial":
         """RaPolynomial materialisation: out[t] = table[idx[t]] (idx 0xFFFFFFFF = None -> 0)."""
         table = _fr_arg(table).reshape(-1, 4)

@@ -179,6 +179,26 @@ int32_t ja_poly_from_i32(ja_ctx* c, const int32_t* z, size_t n, ja_poly** out) {
   return JA_OK;
 }
 
+// the same for `count` polynomials of n coefficients each (row-major): one copy, one synchronisation
+int32_t ja_poly_from_i32_many(ja_ctx* c, const int32_t* z, size_t count, size_t n, ja_poly** out) {
+  JA_REQUIRE(c && z && out && count >= 1, "ja_poly_from_i32_many: null argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  JA_CUDA(cudaSetDevice(c->device));
+  int* tmp = nullptr;
+  int32_t st = dev_alloc(c, count * n * sizeof(int), (void**)&tmp);
+  if (st) return st;
+  for (size_t i = 0; i < count; i++) out[i] = nullptr;
+  for (size_t i = 0; i < count && !st; i++) st = ja_poly_alloc(c, n, &out[i]);
+  if (st) { for (size_t i = 0; i < count; i++) if (out[i]) { ja_poly_free(c, out[i]); out[i] = nullptr; } dev_free(c, tmp); return st; }
+  JA_CUDA(cudaMemcpyAsync(tmp, z, count * n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  for (size_t i = 0; i < count; i++)
+    JA_LAUNCH(c, KC_CONVERT, k_i32_to_fr<<<grid_for(n), kBlock, 0, c->stream>>>(tmp + i * n, out[i]->buf[0], n));
+  JA_CUDA(cudaGetLastError());
+  dev_free(c, tmp);
+  JA_CUDA(cudaStreamSynchronize(c->stream));      // the host array is borrowed for the duration of the call
+  return JA_OK;
+}
+
 int32_t ja_poly_from_lookup(ja_ctx* c, const uint64_t* table, size_t K, const uint32_t* idx, size_t n, ja_poly** out) {
   JA_REQUIRE(c && table && idx && out && K > 0, "ja_poly_from_lookup: null argument");
   for (size_t i = 0; i < n; i++)

@@ -401,7 +401,7 @@ def _run_device(A, PAR, ctx, srs, inputs, resident, comm, ps_shout, t, out, clai
             if res:
                 a, b = res["A"].clone(), res["B"].clone()
             else:
-                a, b = A.MultilinearPolynomial.from_i32(ctx, ni.A), A.MultilinearPolynomial.from_i32(ctx, ni.B)
+                a, b = A.MultilinearPolynomial.from_i32_many(ctx, np.stack([ni.A, ni.B]))
             _sc(ctx, A.EvalKernel.MUL if spec.kind == "mul" else A.EvalKernel.ADD, [a, b], claim, t, eq_w=ni.eq_w)
             A.MultilinearPolynomial.free_many([a, b])
         if hot4 is not None:
@@ -427,7 +427,7 @@ def _run_device(A, PAR, ctx, srs, inputs, resident, comm, ps_shout, t, out, clai
                 if res:
                     polys = [p_.clone() for p_ in resident["aux"][i][j]]
                 else:
-                    polys = [A.MultilinearPolynomial.from_i32(ctx, col) for col in ax.polys]
+                    polys = A.MultilinearPolynomial.from_i32_many(ctx, ax.polys)
                 _sc(ctx, ax.kind, polys, claim, t, eq_w=ax.eq_w, gammas=ax.aux)
                 A.MultilinearPolynomial.free_many(polys)
         out["states"].append(t.state)
