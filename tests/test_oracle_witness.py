@@ -24,3 +24,25 @@ def test_identities(op, shape_a, shape_b, S):
         assert a == q * (1 << S) + r and 0 <= r < (1 << S) or (S == 0 and a == q)
         assert sum(int(ck[d, t]) << (4 * (15 - d)) for d in range(16)) == int(idx[t])
         assert int(out[t]) == max(-(1 << 31), min(q, (1 << 31) - 1))
+
+
+def test_workload_host_witness_is_the_oracle_witness():
+    """workload.host_witness (the numpy synthesis of a node's committed polynomials, exact f64 BLAS product for the einsum) equals the
+    oracle's integer restatement for the three fused operators; phase counts of the remainder range check."""
+    from jolt_atlas_b200 import workload as W
+    rng = np.random.default_rng(3)
+    for spec, A, B in ((W.NodeSpec("einsum", 8, 12, 64, 16), rng.integers(-128, 128, size=(12, 64), dtype=np.int32), rng.integers(-128, 128, size=(64, 16), dtype=np.int32)),
+                       (W.NodeSpec("mul", 7), rng.integers(-128, 128, size=100, dtype=np.int32), rng.integers(-128, 128, size=100, dtype=np.int32)),
+                       (W.NodeSpec("add", 7), rng.integers(-128, 128, size=128, dtype=np.int32), rng.integers(-128, 128, size=128, dtype=np.int32))):
+        T = 1 << spec.log_t
+        op, S = W.witness_op(spec)
+        idx, rem, rows = W.host_witness(spec, A, B, T)
+        a2, b2 = (A, B) if A.ndim == 2 else (A.reshape(1, -1), B.reshape(1, -1))
+        widx, _, ck, rk = WT.fused_witness(op, a2, b2, S, T)
+        assert np.array_equal(idx, widx) and np.array_equal(rows[:16], ck)
+        assert (rk is None and rows.shape[0] == 16) or np.array_equal(rows[16:], rk)
+        acc = WT.accumulate(op, a2, b2)
+        assert np.array_equal(rem[: acc.shape[0]], (acc & ((1 << S) - 1)).astype(np.uint64))
+    assert (W.identity_rc_phases(14), W.device_rc_phases(14)) == (7, 2)
+    assert (W.identity_rc_phases(16), W.device_rc_phases(16)) == (4, 2)
+    assert (W.identity_rc_phases(2), W.device_rc_phases(8)) == (1, 1)
