@@ -127,6 +127,8 @@ struct ToomInt {
   bool ok = false;
   std::vector<int64_t> N;          // m x m
   std::vector<FrH> s;              // s_k, Montgomery form
+  std::vector<int64_t> s_int;      // s_k as integers (|s_k| <= (m-1)! < 2^63)
+  FrH fact;                        // Mont((m-1)!)
   FrH k_lo, k_hi;                  // Mont(1 / (m-1)!) and the same times R
 };
 static inline const ToomInt& toom_int(size_t n /* values: m = n - 1 points and the leading coefficient */) {
@@ -166,14 +168,15 @@ static inline const ToomInt& toom_int(size_t n /* values: m = n - 1 points and t
         for (size_t k = 0; k < full.size(); k++) { nx[k + 1] += full[k]; nx[k] -= full[k] * (i128)j; }
         full.swap(nx);
       }
-      t.s.resize(m);
+      t.s.resize(m); t.s_int.resize(m);
       for (size_t k = 0; k < m && ok; k++) {
         const i128 v = full[k];
-        if (v > (i128)INT64_MAX || v < -(i128)INT64_MAX) { ok = false; break; }
-        t.s[k] = from_i64((int64_t)v);
+        if (v > (i128)INT64_MAX / 2 || v < -((i128)INT64_MAX / 2)) { ok = false; break; }
+        t.s[k] = from_i64((int64_t)v); t.s_int[k] = (int64_t)v;
       }
       FrH fact = FR_ONE;
       for (size_t i = 2; i < m; i++) fact = mul(fact, from_u64(i));
+      t.fact = fact;
       t.k_lo = inv(fact);
       t.k_hi = mul(t.k_lo, FR_R2);                       // K * R (Montgomery form of K R)
     }
@@ -189,9 +192,26 @@ static inline void mac_256x64(uint64_t acc[5], const uint64_t a[4], uint64_t w) 
 }
 // (320-bit integer X) * K mod p for the Montgomery constants k_lo = Mont(K), k_hi = Mont(K R): X = lo + hi 2^256 and the
 // CIOS product takes an unreduced first operand < 2^256 (result < 2 p before its final subtraction)
+// a0 * b * R^-1 for a single-limb first operand: the CIOS product without the multiply rows of the three zero limbs
+static inline FrH mul_limb(uint64_t a0, const FrH& b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = (u128)a0 * b.l[i] + t[0];
+    t[0] = (uint64_t)c; c >>= 64;
+    for (int j = 1; j < 4; j++) { c += t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    const uint64_t m = t[0] * FR_INV;
+    c = (u128)m * FR_P[0] + t[0]; c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * FR_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  FrH r = {{t[0], t[1], t[2], t[3]}};
+  if (t[4] || geq_p(r.l)) sub_p(r.l);
+  return r;
+}
 static inline FrH fold320(const uint64_t x[5], const FrH& k_lo, const FrH& k_hi) {
-  const FrH lo = {{x[0], x[1], x[2], x[3]}}, hi = {{x[4], 0, 0, 0}};
-  return add(mul(lo, k_lo), mul(hi, k_hi));
+  const FrH lo = {{x[0], x[1], x[2], x[3]}};
+  return x[4] ? add(mul(lo, k_lo), mul_limb(x[4], k_hi)) : mul(lo, k_lo);
 }
 // values at 0..n-2 and the leading coefficient (value "at infinity") -> n coefficients, no trimming (unipoly.rs:104-134)
 static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
@@ -200,6 +220,9 @@ static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
   if (!t.ok) return apply_matrix(interp_matrix(n, true), e);
   const size_t m = t.m;
   const FrH& lead = e[m];
+  // c_k = K (sum_i N[k][i] e_i + s_k (m-1)! lead): the leading-coefficient term joins the integer accumulation (one product for
+  // (m-1)! lead instead of one per row)
+  const FrH lead_f = mul(lead, t.fact);
   Coeffs out(n);
   for (size_t k = 0; k < m; k++) {
     uint64_t pos[5] = {0, 0, 0, 0, 0}, ngt[5] = {0, 0, 0, 0, 0};
@@ -209,6 +232,9 @@ static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
       if (w > 0) mac_256x64(pos, e[i].l, (uint64_t)w);
       else if (w < 0) mac_256x64(ngt, e[i].l, (uint64_t)(-w));
     }
+    const int64_t sk = t.s_int[k];
+    if (sk > 0) mac_256x64(pos, lead_f.l, (uint64_t)sk);
+    else if (sk < 0) mac_256x64(ngt, lead_f.l, (uint64_t)(-sk));
     // |pos - ngt| as a 320-bit integer, one fold, sign applied in the field
     bool ge = true;
     for (int j = 4; j >= 0; j--) if (pos[j] != ngt[j]) { ge = pos[j] > ngt[j]; break; }
@@ -221,7 +247,7 @@ static inline Coeffs from_evals_toom(const std::vector<FrH>& e) {
       df[j] = (uint64_t)d; br = (unsigned char)((d >> 64) & 1);
     }
     const FrH f = fold320(df, t.k_lo, t.k_hi);
-    out[k] = add(ge ? f : neg(f), mul(t.s[k], lead));
+    out[k] = ge ? f : neg(f);
   }
   out[m] = lead;
   return out;
@@ -241,7 +267,7 @@ static inline Coeffs from_evals_toom_slow(const std::vector<FrH>& e) {
 }
 static inline FrH evaluate(const Coeffs& c, const FrH& r) {    // unipoly.rs:219-245
   FrH acc = c.back();                                            // Horner: one product per coefficient, same field value
-  for (size_t i = c.size() - 1; i-- > 0;) acc = add(mul(acc, r), c[i]);
+  for (size_t i = c.size() - 1; i-- > 0;) acc = add(mul_chal(acc, r), c[i]);     // r is a 125-bit challenge on the round path (plain product otherwise)
   return acc;
 }
 static inline Coeffs compress(const Coeffs& c) {                 // unipoly.rs:307-318: everything but the linear term
