@@ -74,6 +74,28 @@ int main() {
     const FrH n2 = add(q0, mul(r, sub(q1, q0)));
     if (evaluate(a2, r) != mul(mul(cs, f), n2)) { bad++; printf("running claim (deg 2) mismatch it=%d\n", it); }
   }
+  // round-2 primitives: the challenge-aware product, the single-limb product, the one-pass REDC and Horner on a 125-bit challenge
+  for (int it = 0; it < 2000; it++) {
+    const FrH a = it == 0 ? FR_ZERO : (it == 1 ? sub(FR_ZERO, FR_ONE) : rnd());
+    FrH ch = {{0, 0, rng(), rng() >> 3}};                       // Montgomery limbs {0, 0, lo, hi} of a challenge
+    if (it == 2) ch = FR_ZERO;
+    if (it == 3) ch = {{0, 0, ~0ull, ~0ull >> 3}};
+    if (mul_chal(a, ch) != mul(a, ch)) { bad++; printf("mul_chal mismatch it=%d\n", it); }
+    const FrH full = rnd();
+    if (mul_chal(a, full) != mul(a, full)) { bad++; printf("mul_chal (full operand) mismatch it=%d\n", it); }
+    const uint64_t x = it == 4 ? ~0ull : (it == 5 ? 0 : rng());
+    const FrH xl = {{x, 0, 0, 0}};
+    if (mul_limb(x, a) != mul(xl, a)) { bad++; printf("mul_limb mismatch it=%d\n", it); }
+    uint64_t c1[4]; to_canonical(a, c1);
+    const FrH one = {{1, 0, 0, 0}};
+    const FrH c2 = mul(a, one);
+    if (c1[0] != c2.l[0] || c1[1] != c2.l[1] || c1[2] != c2.l[2] || c1[3] != c2.l[3]) { bad++; printf("to_canonical mismatch it=%d\n", it); }
+    if (from_canonical(c1) != a) { bad++; printf("canonical round trip mismatch it=%d\n", it); }
+    std::vector<FrH> c(1 + it % 18); for (auto& y : c) y = rnd();
+    FrH acc = c[0], pw = ch;
+    for (size_t i = 1; i < c.size(); i++) { acc = add(acc, mul(pw, c[i])); pw = mul(pw, ch); }
+    if (evaluate(c, ch) != acc) { bad++; printf("evaluate on a challenge mismatch it=%d\n", it); }
+  }
   printf("bad=%d\n", bad);
   return bad != 0;
 }
