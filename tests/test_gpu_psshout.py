@@ -145,7 +145,8 @@ def test_identity_rc_phase_count_is_free(ctx):
 
 
 @pytest.mark.parametrize("log_t,bound,lo,hi", [(10, 31, -64, 64), (12, 31, -(1 << 20), 1 << 20), (9, 31, -(1 << 31), 1 << 31), (8, 31, -1, 1),
-                                               (11, 31, 0, 1000), (10, 31, -5000, 0), (10, 9, -300, 300), (9, 31, -(1 << 40), 1 << 40)])
+                                               (11, 31, 0, 1000), (10, 31, -5000, 0), (10, 9, -300, 300), (9, 31, -(1 << 40), 1 << 40),
+                                               (2, 31, -5, 5), (1, 31, -(1 << 40), 1 << 40)])
 def test_sign_extension_phases_match_oracle(ctx, log_t, bound, lo, hi):
     """Small signed lookup values: ja_psshout_prove_address builds the suffix polynomials of the sign-extension phases on the host
     from the four class sums of the phase-0 pass (no T-sized pass for them) - the proof must stay the oracle's, which runs all eight
